@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the bixverse co-expression correlation hot path on B200.
+
+Metric (BASELINE.json): gene-pair correlations/sec on config 2 - Spearman correlation of
+20 000 genes x 1 000 samples with the |r|^6 soft-threshold adjacency, packed upper triangle
+(P = 199 990 000 pairs) - plus the 20k-gene TOM wall time (config 4) as an extra key.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f64|i8|tf32]
+
+N > 1 is launched by torchrun (one process per GPU); the triangle is sharded into contiguous
+block-row ranges balanced by pair count, no data-path collective (`scaling: weak` does not
+apply - total work is fixed, so `scaling` is "strong").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_SAMPLES, N_GENES, BETA, SEED = 1000, 20000, 6.0, 2024
+METRIC = "gene_pair_correlations_per_sec"
+UNIT = "pairs/s"
+CPU_SAMPLE_GENES = 8000  # bounded CPU sample: first 8000 genes x all 1000 samples (31 996 000 pairs)
+
+
+def _env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "src": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_input():
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    return synthetic_bulk(N_SAMPLES, N_GENES, seed=SEED, tie_heavy=True)
+
+
+# --------------------------------------------------------------------------------------- CPU baseline
+def cpu_step(x_sample):
+    """One pass of the reference algorithm shape on the host (oracle port): rank -> standardise ->
+    FULL p x p Gram (OpenBLAS dgemm, all host threads) -> row-major triangle gather -> |r|^6."""
+    from oracle import oracle as o
+
+    t0 = time.perf_counter()
+    r = o.cor_upper_triangle(x_sample, True, True)
+    a = o.soft_threshold(r, BETA)
+    dt = time.perf_counter() - t0
+    return a.shape[0], dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    x = make_input()[:, :CPU_SAMPLE_GENES]
+    x = np.asfortranarray(x)
+    for _ in range(args.warmup):
+        cpu_step(x)
+    tot_pairs, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        pairs, dt = cpu_step(x)
+        tot_pairs += pairs
+        tot_t += dt
+    v = tot_pairs / tot_t
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: Spearman 20000 genes x 1000 samples + |r|^6, packed upper triangle (shift=1)",
+                   "n_samples": N_SAMPLES, "n_genes": N_GENES, "beta": BETA, "seed": SEED},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {CPU_SAMPLE_GENES} genes x {N_SAMPLES} samples per step "
+                                   f"({CPU_SAMPLE_GENES * (CPU_SAMPLE_GENES - 1) // 2} pairs); numpy/OpenBLAS restatement of the "
+                                   "reference algorithm shape (the Rust crate cannot be built here)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from bixverse_b200 import _lib, api
+    from bixverse_b200.distributed import packed_offset, pair_balanced_rows
+
+    world = _env_int("WORLD_SIZE", 1)
+    rank = _env_int("RANK", 0)
+    local = _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    api.init(1, local)
+    prec = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3}[args.precision]
+    peaks = load_peaks()
+
+    n, p = N_SAMPLES, N_GENES
+    x_host = make_input()  # identical on every rank (same seed)
+    P_total = p * (p - 1) // 2
+    r0, r1 = pair_balanced_rows(p, 1, world, rank)
+    o0, o1 = packed_offset(r0, p, 1), packed_offset(r1, p, 1)
+    my_pairs = o1 - o0
+
+    # ---- HBM-resident arm: inputs already on the device, library runs on torch's current stream
+    x_dev = torch.from_numpy(np.ascontiguousarray(x_host.T)).to(dev)  # p x n row-major == n x p column-major
+    out_dev = torch.empty(max(my_pairs, 1), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream))
+    _lib.check(lib.bixcor_dev_set_async(1))
+
+    def step_dev():
+        _lib.check(lib.bixcor_dev_cor_upper_rows(x_dev.data_ptr(), n, p, 1, 1, BETA, prec, r0, r1, out_dev.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    _lib.check(lib.bixcor_timing_enable(1))
+    launches0 = lib.bixcor_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = lib.bixcor_launch_count() - launches0
+    tm = _lib.last_timing()
+    _lib.check(lib.bixcor_timing_enable(0))
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_step = float(t_ms.item()) / args.steps
+    value = P_total / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (the Gram kernel of this rank)
+    gemm_ms_step = tm["gemm_ms"] / args.steps
+    cols_ms_step = tm["cols_ms"] / args.steps
+    alg_flops = 2.0 * n * my_pairs  # 2n flop per pair, upper-triangle count
+    achieved_tf = alg_flops / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
+    if prec == _lib.PREC_F64:
+        # FP64 tensor peak is not in MEASURED_PEAKS.json: measure cuBLAS DGEMM 8192^3 live
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        best = 1e9
+        for i in range(6):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            torch.matmul(a, b)
+            s1.record()
+            torch.cuda.synchronize(dev)
+            if i:
+                best = min(best, s0.elapsed_time(s1))
+        peak_tf = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        peak_note = "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry); nominal 40"
+        del a, b
+    elif prec == _lib.PREC_I8EXACT:
+        peak_tf = 2.0 * peaks["bf16_tflops"]
+        peak_note = f"2 x {peaks['src']} bf16 dense (int8 tensor rate); the kernel issues 4 int8 MMAs per algorithmic flop pair"
+    else:
+        peak_tf = 0.5 * peaks["bf16_tflops"]
+        peak_note = f"0.5 x {peaks['src']} bf16 dense (tf32 tensor rate); the kernel issues 3 tf32 MMAs per algorithmic flop pair"
+    roofline = {"bound": "tensor", "kernel": "gram_dmma_kernel" if prec == _lib.PREC_F64 else "gram_umma_kernel",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_note,
+                "kernel_ms_per_step": gemm_ms_step, "kernel_share_of_step": gemm_ms_step / ms_step if ms_step else None,
+                "launches_per_step": tm["gemm_launches"] / args.steps,
+                "rank_kernel": {"bound": "hbm", "ms_per_step": cols_ms_step,
+                                "achieved_gbs": (2.0 * 8 * n * p) / (cols_ms_step * 1e-3) / 1e9 if cols_ms_step > 0 else None,
+                                "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]}}
+
+    # ---- end-to-end arm: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region
+    _lib.check(lib.bixcor_dev_set_async(0))
+    _lib.check(lib.bixcor_dev_set_stream(None))
+    del out_dev
+    x_pin = torch.from_numpy(np.ascontiguousarray(x_host.T)).pin_memory()
+    out_pin = torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        _lib.check(lib.bixcor_cor_upper_rows(x_pin.data_ptr(), n, p, 1, 1, BETA, prec, r0, r1, out_pin.data_ptr()))
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_val = P_total / (float(t_e.item()) / e2e_steps)
+    checksum = float(out_pin[: min(my_pairs, 1 << 20)].sum())
+
+    # ---- TOM wall time (config 4) as an extra metric, device resident, packed output
+    tom = None
+    if not args.no_tom:
+        try:
+            from bixverse_b200.distributed import DeviceBackend, sharded_tom_from_exp
+
+            be = DeviceBackend(dev)
+            tprec = _lib.PREC_TF32X3 if args.precision == "tf32" else _lib.PREC_F64
+            barrier()
+            t0 = time.perf_counter()
+            t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)
+            barrier()
+            t_tom = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_tom, op=dist.ReduceOp.MAX)
+            tom = {"metric": "tom_from_exp_wall_ms", "value": 1e3 * float(t_tom.item()), "unit": "ms",
+                   "config": "config4: signed TOM v1, 20000 genes x 1000 samples, Pearson, beta=6, packed output, HBM resident",
+                   "precision": "tf32x3" if tprec == _lib.PREC_TF32X3 else "f64", "alg_flops": 8.4e12,
+                   "achieved_tflops": 8.4e12 / float(t_tom.item()) / 1e12}
+            del t_out
+        except Exception as ex:  # report, do not hide
+            tom = {"error": str(ex)}
+
+    # ---- CPU baseline leg (rank 0, N = 1 only): bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        xs = np.asfortranarray(x_host[:, :CPU_SAMPLE_GENES])
+        pairs, dtc = cpu_step(xs)
+        cpu_baseline = {"value": pairs / dtc, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                        "sample": f"first {CPU_SAMPLE_GENES} genes x {N_SAMPLES} samples, one pass ({pairs} pairs, {dtc:.2f} s): "
+                                  "numpy/OpenBLAS oracle following the reference algorithm shape (rank -> standardise -> full "
+                                  "p x p dgemm -> triangle gather); the Rust crate itself cannot be built in this image"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"f64": "f64", "i8": "int8->int32 (exact), f64 epilogue", "tf32": "tf32x3->f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "config2: Spearman 20000 genes x 1000 samples + |r|^6, packed upper triangle (shift=1)",
+                       "n_samples": n, "n_genes": p, "beta": BETA, "seed": SEED, "precision": args.precision,
+                       "sharding": f"{world} contiguous block-row ranges balanced by pair count, no collective",
+                       "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(8 * n * p),
+                    "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps,
+                    "note": "bixcor_cor_upper_rows through the C ABI with pinned host buffers; per-rank bytes"},
+            "gpu_launches": int(lt.item()),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "tom": tom,
+            "checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "f64"), choices=["f64", "i8", "tf32"])
+    ap.add_argument("--no-tom", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,234 @@
+"""Host-side mirror of bixverse's operator interface for the co-expression
+correlation path, calling the CUDA library through its C ABI.
+
+Function names, argument meaning and error behaviour follow the reference's
+extendr functions so that tests read like the reference's own tinytest files:
+
+=========================== =================================================
+here                        reference
+=========================== =================================================
+rs_cor                      src/rust/src/base/r_cors_similarity.rs:70-77
+rs_cor_upper_triangle       src/rust/src/base/r_cors_similarity.rs:251-268
+rs_differential_cor         src/rust/src/methods/r_diffcor.rs:45-74
+rs_tom                      src/rust/src/methods/r_coremo.rs:46-59
+rs_rank_matrix_col          src/rust/src/enrichment/r_singscore.rs:89-95
+rs_upper_triangle_to_dense  src/rust/src/base/r_helpers.rs:75-94
+rs_dense_to_upper_triangle  src/rust/src/base/r_helpers.rs:113-134
+calculate_tom               R/functions_stats.R:43-59
+calculate_tom_from_exp      R/functions_stats.R:103-121
+UpperTriangularSymMat       R/classes_triangular_mat.R:10-211
+UpperTriangleDiffcorMat     R/classes_triangular_mat.R:224-341
+=========================== =================================================
+
+Matrices are samples x genes; they are handed to the library in R's
+column-major layout (``np.asfortranarray``).  Extra keyword arguments
+(``precision``, ``beta``) are the north-star extensions and default to the
+reference behaviour.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._lib import PREC_F64, PREC_I8EXACT, PREC_TF32X3, TOM_V1, TOM_V2, BixcorError, check
+
+__all__ = [
+    "rs_cor", "rs_cor_upper_triangle", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
+    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "calculate_tom", "calculate_tom_from_exp",
+    "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
+    "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "BixcorError",
+]
+
+
+def init(n_gpus: int = 1, first_device: int = 0) -> None:
+    check(_lib.load().bixcor_init_devices(int(first_device), int(n_gpus)))
+
+
+def _fmat(x, name="x") -> np.ndarray:
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be a matrix")
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data
+
+
+def _parse_tom_types(tom_type: str) -> int:
+    # crate parse_tom_types: "v1" / "v2", anything else is an error (r_coremo.rs:50-52)
+    if tom_type == "v1":
+        return TOM_V1
+    if tom_type == "v2":
+        return TOM_V2
+    raise ValueError(f"Invalid TOM version type: {tom_type}")
+
+
+def shard_rows(p: int, shift: bool, world: int, rank: int) -> tuple[int, int]:
+    import ctypes as C
+
+    r0, r1 = C.c_int64(), C.c_int64()
+    check(_lib.load().bixcor_shard_rows(p, int(bool(shift)), world, rank, C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+def rs_rank_matrix_col(x) -> np.ndarray:
+    a = _fmat(x)
+    out = np.empty(a.shape, dtype=np.float64, order="F")
+    check(_lib.load().bixcor_rank_columns(_p(a), a.shape[0], a.shape[1], _p(out)))
+    return out
+
+
+def rs_cor(x, spearman: bool, precision: int = PREC_F64) -> np.ndarray:
+    a = _fmat(x)
+    n, p = a.shape
+    out = np.empty((p, p), dtype=np.float64, order="F")
+    check(_lib.load().bixcor_cor_dense(_p(a), n, p, int(bool(spearman)), precision, _p(out)))
+    return out
+
+
+def rs_cor_upper_triangle(x, spearman: bool, shift: bool = True, beta: float = 1.0,
+                          precision: int = PREC_F64, rows: tuple[int, int] | None = None) -> np.ndarray:
+    a = _fmat(x)
+    n, p = a.shape
+    lib = _lib.load()
+    s = int(bool(shift))
+    if rows is None:
+        out = np.empty(lib.bixcor_packed_len(p, s), dtype=np.float64)
+        check(lib.bixcor_cor_upper(_p(a), n, p, int(bool(spearman)), s, float(beta), precision, _p(out)))
+    else:
+        r0, r1 = rows
+        ln = lib.bixcor_packed_offset(r1, p, s) - lib.bixcor_packed_offset(r0, p, s)
+        out = np.empty(max(ln, 0), dtype=np.float64)
+        check(lib.bixcor_cor_upper_rows(_p(a), n, p, int(bool(spearman)), s, float(beta), precision, r0, r1, _p(out)))
+    return out
+
+
+def rs_differential_cor(x_a, x_b, spearman: bool, precision: int = PREC_F64) -> dict:
+    a, b = _fmat(x_a, "x_a"), _fmat(x_b, "x_b")
+    if a.shape[1] != b.shape[1]:
+        # the reference asserts (panics) here: r_diffcor.rs:51-56
+        raise ValueError(
+            "Input matrices must have the same number of columns. Found "
+            f"{a.shape[1]} columns in first matrix and {b.shape[1]} in second."
+        )
+    p = a.shape[1]
+    lib = _lib.load()
+    ln = lib.bixcor_packed_len(p, 1)
+    res = {k: np.empty(ln, dtype=np.float64) for k in ("r_a", "r_b", "z_score", "p_val")}
+    check(lib.bixcor_diffcor(_p(a), a.shape[0], _p(b), b.shape[0], p, int(bool(spearman)), precision,
+                             _p(res["r_a"]), _p(res["r_b"]), _p(res["z_score"]), _p(res["p_val"])))
+    return res
+
+
+def rs_tom(x, tom_type: str, signed: bool, precision: int = PREC_F64) -> np.ndarray:
+    version = _parse_tom_types(tom_type)
+    a = _fmat(x)
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("x must be a square affinity matrix")
+    p = a.shape[0]
+    out = np.empty((p, p), dtype=np.float64, order="F")
+    check(_lib.load().bixcor_tom(_p(a), p, int(bool(signed)), version, precision, _p(out)))
+    return out
+
+
+def calculate_tom(cor_mat, signed: bool, version: str = "v1", precision: int = PREC_F64) -> np.ndarray:
+    if version not in ("v1", "v2"):
+        raise ValueError("version must be one of 'v1', 'v2'")
+    cor_mat = np.asarray(cor_mat, dtype=np.float64)
+    if not signed:
+        cor_mat = np.abs(cor_mat)  # R/functions_stats.R:52-54
+    return rs_tom(cor_mat, version, signed, precision)
+
+
+def calculate_tom_from_exp(x, signed: bool, version: str, cor_method: str = "pearson", beta: float = 1.0,
+                           precision: int = PREC_F64, packed: bool = False) -> np.ndarray:
+    """Fused on-device rs_cor -> (abs) -> rs_tom chain; the p x p correlation never leaves HBM."""
+    if version not in ("v1", "v2"):
+        raise ValueError("version must be one of 'v1', 'v2'")
+    a = _fmat(x)
+    n, p = a.shape
+    lib = _lib.load()
+    out = np.empty(lib.bixcor_packed_len(p, 1), dtype=np.float64) if packed else np.empty((p, p), dtype=np.float64, order="F")
+    check(lib.bixcor_tom_from_exp(_p(a), n, p, int(cor_method == "spearman"), int(bool(signed)),
+                                  _parse_tom_types(version), float(beta), precision, int(bool(packed)), _p(out)))
+    return out
+
+
+def rs_upper_triangle_to_dense(data, shift: bool, n: int) -> np.ndarray:
+    v = np.ascontiguousarray(data, dtype=np.float64)
+    lib = _lib.load()
+    if v.shape[0] != lib.bixcor_packed_len(n, int(bool(shift))):
+        raise ValueError("packed length does not match n")
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    check(lib.bixcor_upper_to_dense(_p(v), int(bool(shift)), n, _p(out)))
+    return out
+
+
+def rs_dense_to_upper_triangle(x, shift: bool) -> np.ndarray:
+    a = _fmat(x)
+    p = a.shape[1]
+    lib = _lib.load()
+    out = np.empty(lib.bixcor_packed_len(p, int(bool(shift))), dtype=np.float64)
+    check(lib.bixcor_dense_to_upper(_p(a), int(bool(shift)), p, _p(out)))
+    return out
+
+
+def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int, precision: int = PREC_F64) -> np.ndarray:
+    """All-pairs Pearson over a cells x genes CSR matrix (north-star extension of
+    rs_pairwise_gene_cors_mc, src/rust/src/meta_cell/r_mc_processing.rs:258-283)."""
+    ip = np.ascontiguousarray(indptr, dtype=np.int64)
+    ix = np.ascontiguousarray(indices, dtype=np.int32)
+    dt = np.ascontiguousarray(data, dtype=np.float32)
+    if ip.shape[0] != cells + 1:
+        raise ValueError("indptr must have cells + 1 entries")
+    lib = _lib.load()
+    out = np.empty(lib.bixcor_packed_len(genes, 1), dtype=np.float64)
+    check(lib.bixcor_sparse_gram_cor(_p(ip), _p(ix), _p(dt), cells, genes, precision, _p(out)))
+    return out
+
+
+class UpperTriangularSymMat:
+    """Mirror of the R6 class upper_triangular_sym_mat (R/classes_triangular_mat.R:10-211)."""
+
+    def __init__(self, values, features, shift: bool = True):
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        self.features = list(features)
+        self.shift = bool(shift)
+        p = len(self.features)
+        expected = p * (p - 1) // 2 if self.shift else p * (p + 1) // 2
+        if self.values.shape[0] != expected:  # length check, classes_triangular_mat.R:33-38
+            raise ValueError(f"expected {expected} values for {p} features, got {self.values.shape[0]}")
+
+    def get_sym_matrix(self) -> np.ndarray:
+        return rs_upper_triangle_to_dense(self.values, self.shift, len(self.features))
+
+
+class UpperTriangleDiffcorMat:
+    """Mirror of R/classes_triangular_mat.R:224-341 (shift fixed to 1)."""
+
+    REQUIRED = ("r_a", "r_b", "z_score", "p_val")
+
+    def __init__(self, diff_cor_res: dict, features):
+        missing = [k for k in self.REQUIRED if k not in diff_cor_res]
+        if missing:
+            raise ValueError(f"diff_cor_res is missing {missing}")
+        lens = {len(diff_cor_res[k]) for k in self.REQUIRED}
+        if len(lens) != 1:
+            raise ValueError("all differential correlation vectors must have equal length")
+        self.features = list(features)
+        p = len(self.features)
+        if lens.pop() != p * (p - 1) // 2:
+            raise ValueError("vector length does not match the number of features")
+        self.data = {k: np.asarray(diff_cor_res[k], dtype=np.float64) for k in self.REQUIRED}
+
+    def get_cor_matrix(self, which: str = "r_a") -> np.ndarray:
+        return rs_upper_triangle_to_dense(self.data[which], True, len(self.features))
+
+    def get_data_table(self) -> dict:
+        p = len(self.features)
+        i, j = np.triu_indices(p, 1)
+        keep = self.data["p_val"] != 0  # classes_triangular_mat.R:298-300
+        out = {"feature_a": np.asarray(self.features)[i][keep], "feature_b": np.asarray(self.features)[j][keep]}
+        out.update({k: v[keep] for k, v in self.data.items()})
+        return out

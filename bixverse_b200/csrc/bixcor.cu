@@ -1,0 +1,1296 @@
+// libbixcor: C-ABI + host runtime of the B200-native co-expression correlation path.
+// See include/bixcor.h for the boundary contract and the reference call sites replaced.
+#include "../../include/bixcor.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "columns.cuh"
+#include "common.cuh"
+#include "gram_dmma.cuh"
+#include "gram_umma.cuh"
+
+namespace bixcor {
+
+// ----------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------
+static std::mutex g_err_mu;
+static std::string g_err = "";
+static std::atomic<int64_t> g_launches{0};
+static double g_fieller = 1.06;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                    \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(e__ == cudaErrorMemoryAllocation ? BIXCOR_ERR_OOM : BIXCOR_ERR_CUDA, "%s:%d %s: %s",  \
+                  __FILE__, __LINE__, #expr, cudaGetErrorString(e__));                                  \
+  } while (0)
+#define RC_TRY(expr)        \
+  do {                      \
+    int rc__ = (expr);      \
+    if (rc__ != BIXCOR_OK) return rc__; \
+  } while (0)
+
+// ----------------------------------------------------------------------------
+// per-device context
+// ----------------------------------------------------------------------------
+struct Buffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BIXCOR_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    CU_TRY(cudaMalloc(&ptr, want));
+    cap = want;
+    return BIXCOR_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinnedBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BIXCOR_OK;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+    CU_TRY(cudaMallocHost(&ptr, bytes));
+    cap = bytes;
+    return BIXCOR_OK;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+struct TileList {
+  int2* d_tiles = nullptr;
+  int ntiles = 0;
+  // group g covers tiles [group_tile[g], group_tile[g+1]) and rows [group_row[g], group_row[g+1])
+  std::vector<int> group_tile;
+  std::vector<int64_t> group_row;
+};
+
+enum TimeCat : int { T_COLS = 0, T_GEMM = 1, T_OTHER = 2 };
+
+struct Ctx {
+  int device = -1;
+  int sm_count = 148;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  bool owns_compute = true;
+  Buffer x[2];          // staged expression matrices
+  Buffer op[2];         // Gram operands (Z / digit planes / TF32 planes)
+  Buffer aux[2];        // per-gene vectors (inv norm)
+  Buffer out;           // packed / dense result
+  Buffer out2;          // affinity matrix for TOM
+  Buffer vec;           // k, diag, colsum
+  Buffer panel;         // sparse dense panel
+  Buffer sparse_in;     // staged CSR
+  PinnedBuffer stage[2];
+  std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
+  // timing
+  std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> timed;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  double last_ms[3] = {0, 0, 0};
+  int last_gemm_launches = 0;
+};
+
+static std::vector<Ctx*> g_ctx;
+static std::mutex g_init_mu;
+static int g_dmma_variant = 1;
+static bool g_timing = false;   // bixcor_timing_enable
+static bool g_async = false;    // device-pointer entry points return without synchronising
+
+static int ctx_create(int device, Ctx** out) {
+  Ctx* c = new Ctx();
+  c->device = device;
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    delete c;
+    return fail(BIXCOR_ERR_NO_GPU, "device %d is sm_%d%d; libbixcor is built for sm_100a only", device, prop.major,
+                prop.minor);
+  }
+  c->sm_count = prop.multiProcessorCount;
+  CU_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  *out = c;
+  return BIXCOR_OK;
+}
+
+static void ctx_destroy(Ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& b : c->x) b.release();
+  for (auto& b : c->op) b.release();
+  for (auto& b : c->aux) b.release();
+  c->out.release();
+  c->out2.release();
+  c->vec.release();
+  c->panel.release();
+  c->sparse_in.release();
+  for (auto& b : c->stage) b.release();
+  for (auto& kv : c->tile_cache)
+    if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  if (c->compute && c->owns_compute) cudaStreamDestroy(c->compute);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
+  delete c;
+}
+
+static int ensure_init() {
+  {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!g_ctx.empty()) return BIXCOR_OK;
+  }
+  return bixcor_init_devices(0, 1);
+}
+
+// ---- timing helpers ---------------------------------------------------------
+static cudaEvent_t ctx_event(Ctx* c) {
+  if (c->events_used == c->event_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->event_pool.push_back(e);
+  }
+  return c->event_pool[c->events_used++];
+}
+static void timing_reset(Ctx* c) {
+  c->timed.clear();
+  c->events_used = 0;
+  c->last_ms[0] = c->last_ms[1] = c->last_ms[2] = 0;
+  c->last_gemm_launches = 0;
+}
+// per-call housekeeping: the event pool is recycled unless the caller is accumulating timings
+static void call_begin(Ctx* c) {
+  if (!g_timing) c->events_used = 0;
+}
+struct Timed {
+  Ctx* c;
+  int cat;
+  cudaEvent_t e0, e1;
+  Timed(Ctx* c_, int cat_) : c(c_), cat(cat_), e0(nullptr), e1(nullptr) {
+    if (!g_timing || c->events_used > 16384) return;
+    e0 = ctx_event(c);
+    e1 = ctx_event(c);
+    cudaEventRecord(e0, c->compute);
+  }
+  ~Timed() {
+    if (cat == T_GEMM) c->last_gemm_launches++;
+    if (!e0) return;
+    cudaEventRecord(e1, c->compute);
+    c->timed.emplace_back(cat, e0, e1);
+  }
+};
+static void timing_collect(Ctx* c) {
+  for (auto& t : c->timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)) == cudaSuccess) c->last_ms[std::get<0>(t)] += ms;
+  }
+  c->timed.clear();
+}
+
+// ----------------------------------------------------------------------------
+// tile lists: upper-triangle (or full strip) tiles of the block rows covering
+// [row_begin,row_end), ordered in bands of `band` block rows so that the CTAs of
+// one wave share operand rows in L2 and every band completes one contiguous
+// packed range (the unit of the D2H pipeline).
+// ----------------------------------------------------------------------------
+static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int upper_only, int band, TileList** out) {
+  auto key = std::make_tuple(p, row_begin, row_end, upper_only, band);
+  auto it = c->tile_cache.find(key);
+  if (it != c->tile_cache.end()) {
+    *out = &it->second;
+    return BIXCOR_OK;
+  }
+  if (c->tile_cache.size() > 64) {
+    for (auto& kv : c->tile_cache)
+      if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
+    c->tile_cache.clear();
+  }
+  const int nb = (int)((p + kTile - 1) / kTile);
+  const int b0 = (int)(row_begin / kTile), b1 = (int)((row_end + kTile - 1) / kTile);
+  std::vector<int2> tiles;
+  TileList tl;
+  for (int bb = b0; bb < b1; bb += band) {
+    const int be = std::min(b1, bb + band);
+    tl.group_tile.push_back((int)tiles.size());
+    tl.group_row.push_back(std::max<int64_t>(row_begin, (int64_t)bb * kTile));
+    const int j0 = upper_only ? bb : 0;
+    for (int bj = j0; bj < nb; ++bj)
+      for (int bi = bb; bi < be; ++bi)
+        if (!upper_only || bi <= bj) tiles.push_back(make_int2(bi, bj));
+  }
+  tl.group_tile.push_back((int)tiles.size());
+  tl.group_row.push_back(row_end);
+  tl.ntiles = (int)tiles.size();
+  if (tl.ntiles > 0) {
+    CU_TRY(cudaMalloc(&tl.d_tiles, sizeof(int2) * tiles.size()));
+    CU_TRY(cudaMemcpyAsync(tl.d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->compute));
+    CU_TRY(cudaStreamSynchronize(c->compute));
+  }
+  auto ins = c->tile_cache.emplace(key, std::move(tl));
+  *out = &ins.first->second;
+  return BIXCOR_OK;
+}
+
+// ----------------------------------------------------------------------------
+// Gram operand preparation
+// ----------------------------------------------------------------------------
+struct Operand {
+  int precision = BIXCOR_PREC_F64;
+  int K = 0;  // padded contraction length
+  int64_t p = 0;
+  const double* z64 = nullptr;  // F64: p x K
+  const int8_t* i8 = nullptr;   // I8EXACT: 3 planes p x K
+  const float* f32 = nullptr;   // TF32X3: 2 planes p x K
+  const double* inv_norm = nullptr;
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int k_padding(int precision) {
+  return precision == BIXCOR_PREC_F64 ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
+}
+
+static int check_precision(int precision, int spearman, int64_t n) {
+  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3) return BIXCOR_OK;
+  if (precision == BIXCOR_PREC_I8EXACT) {
+    if (!spearman) return fail(BIXCOR_ERR_INVALID, "BIXCOR_PREC_I8EXACT is defined for Spearman only");
+    if (n > 2025) return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_I8EXACT supports n <= 2025 samples (got %lld)", (long long)n);
+    return BIXCOR_OK;
+  }
+  return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
+}
+
+// d_x: device n x p column-major.  Builds the operand in ctx slot `slot`.
+static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int slot,
+                           Operand* op) {
+  if (n < 2) return fail(BIXCOR_ERR_INVALID, "need at least 2 samples (n = %lld)", (long long)n);
+  if (n > (spearman ? 16384 : (1 << 30)))
+    return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman rank kernel supports n <= 16384 samples (got %lld)", (long long)n);
+  RC_TRY(check_precision(precision, spearman, n));
+  const int K = round_up((int)n, k_padding(precision));
+  ColumnOut co;
+  memset(&co, 0, sizeof co);
+  co.kpad = K;
+  op->precision = precision;
+  op->K = K;
+  op->p = p;
+  if (precision == BIXCOR_PREC_F64) {
+    RC_TRY(c->op[slot].reserve(sizeof(double) * (size_t)K * p));
+    co.mode = COL_Z64;
+    co.f64 = (double*)c->op[slot].ptr;
+    co.ld64 = K;
+    op->z64 = co.f64;
+  } else if (precision == BIXCOR_PREC_I8EXACT) {
+    RC_TRY(c->op[slot].reserve((size_t)3 * K * p));
+    RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
+    co.mode = COL_I8;
+    co.i8 = (int8_t*)c->op[slot].ptr;
+    co.ld8 = K;
+    co.plane8 = (int64_t)K * p;
+    co.inv_norm = (double*)c->aux[slot].ptr;
+    op->i8 = co.i8;
+    op->inv_norm = co.inv_norm;
+  } else {
+    RC_TRY(c->op[slot].reserve(sizeof(float) * 2 * (size_t)K * p));
+    co.mode = COL_TF32;
+    co.f32 = (float*)c->op[slot].ptr;
+    co.ld32 = K;
+    co.plane32 = (int64_t)K * p;
+    op->f32 = co.f32;
+  }
+  Timed tm(c, T_COLS);
+  if (spearman) {
+    int npow2 = 32;
+    while (npow2 < n) npow2 <<= 1;
+    const int threads = std::min(256, npow2);
+    const size_t smem = (size_t)npow2 * 12;
+    CU_TRY(cudaFuncSetAttribute(rank_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rank_columns_kernel<<<(unsigned)p, threads, smem, c->compute>>>(d_x, n, (int)n, npow2, co);
+  } else {
+    standardise_columns_kernel<<<(unsigned)p, 128, 0, c->compute>>>(d_x, n, (int)n, co);
+  }
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
+// ----------------------------------------------------------------------------
+// Gram launch (dispatch over precision / epilogue)
+// ----------------------------------------------------------------------------
+template <int EPI>
+static int launch_dmma(Ctx* c, const dmma::Params& P, int ntiles) {
+  if (ntiles <= 0) return BIXCOR_OK;
+  Timed tm(c, T_GEMM);
+#define BIXCOR_DMMA_CASE(V)                                                                               \
+  case V: {                                                                                               \
+    auto kern = dmma::gram_dmma_kernel<EPI, V>;                                                           \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma::SMEM_BYTES));    \
+    kern<<<ntiles, dmma::THREADS, dmma::SMEM_BYTES, c->compute>>>(P);                                     \
+  } break;
+  switch (g_dmma_variant) {
+    BIXCOR_DMMA_CASE(0)
+    BIXCOR_DMMA_CASE(1)
+    BIXCOR_DMMA_CASE(2)
+    default:
+      return fail(BIXCOR_ERR_INVALID, "bad DMMA variant %d", g_dmma_variant);
+  }
+#undef BIXCOR_DMMA_CASE
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
+struct EpiArgs {
+  int epi = dmma::EPI_PACKED;
+  double* out = nullptr;
+  int64_t out_base = 0;
+  int64_t ldo = 0;
+  int shift = 1;
+  int mirror = 0;
+  int diag_one = 0;
+  double beta = 1.0;
+  int keep_sign = 0;
+  double *r_a = nullptr, *r_b = nullptr, *z = nullptr, *pv = nullptr;
+  double inv_se = 0.0;
+  const double* A = nullptr;
+  const double* kvec = nullptr;
+  const double* dvec = nullptr;
+  int tom_v2 = 0;
+  int tom_packed = 0;
+};
+
+static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, const int2* tiles, int ntiles,
+                       const EpiArgs& e) {
+  if (ntiles <= 0) return BIXCOR_OK;
+  if (a.precision == BIXCOR_PREC_F64) {
+    dmma::Params P;
+    memset(&P, 0, sizeof P);
+    P.R0 = P.C0 = a.z64;
+    P.ld0 = a.K;
+    P.K0 = a.K;
+    if (b) {
+      P.R1 = P.C1 = b->z64;
+      P.ld1 = b->K;
+      P.K1 = b->K;
+    }
+    P.p = (int)p;
+    P.tiles = tiles;
+    P.out = e.out;
+    P.out_base = e.out_base;
+    P.ldo = e.ldo;
+    P.shift = e.shift;
+    P.mirror = e.mirror;
+    P.diag_one = e.diag_one;
+    P.beta = e.beta;
+    P.keep_sign = e.keep_sign;
+    P.r_a = e.r_a;
+    P.r_b = e.r_b;
+    P.z = e.z;
+    P.pv = e.pv;
+    P.inv_se = e.inv_se;
+    P.A = e.A;
+    P.kvec = e.kvec;
+    P.dvec = e.dvec;
+    P.tom_v2 = e.tom_v2;
+    P.tom_packed = e.tom_packed;
+    switch (e.epi) {
+      case dmma::EPI_PACKED: return launch_dmma<dmma::EPI_PACKED>(c, P, ntiles);
+      case dmma::EPI_DENSE: return launch_dmma<dmma::EPI_DENSE>(c, P, ntiles);
+      case dmma::EPI_DIFFCOR: return launch_dmma<dmma::EPI_DIFFCOR>(c, P, ntiles);
+      case dmma::EPI_TOM: return launch_dmma<dmma::EPI_TOM>(c, P, ntiles);
+      case dmma::EPI_ACCUM: return launch_dmma<dmma::EPI_ACCUM>(c, P, ntiles);
+    }
+    return fail(BIXCOR_ERR_INVALID, "bad epilogue %d", e.epi);
+  }
+  return umma::launch_gram_umma(c->compute, c->sm_count, a.precision, a.K, a.i8, a.f32, a.inv_norm,
+                                b ? b->K : 0, b ? b->i8 : nullptr, b ? b->f32 : nullptr, b ? b->inv_norm : nullptr,
+                                p, tiles, ntiles, e.epi, e.out, e.out_base, e.ldo, e.shift, e.mirror, e.diag_one,
+                                e.beta, e.keep_sign, e.r_a, e.r_b, e.z, e.pv, e.inv_se, e.A, e.kvec, e.dvec,
+                                e.tom_v2, e.tom_packed) == 0
+             ? (g_launches++, BIXCOR_OK)
+             : fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
+}
+
+// ----------------------------------------------------------------------------
+// host <-> device staging
+// ----------------------------------------------------------------------------
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  const size_t kMin = size_t(8) << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nthr = (int)std::min<size_t>(std::max(1u, std::min(hw, 16u)), std::max<size_t>(1, bytes / kMin));
+  if (nthr <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = ((bytes + nthr - 1) / nthr + 63) & ~size_t(63);
+  for (int t = 0; t < nthr; ++t) {
+    const size_t o = (size_t)t * chunk;
+    if (o >= bytes) break;
+    const size_t len = std::min(chunk, bytes - o);
+    th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, len); });
+  }
+  for (auto& t : th) t.join();
+}
+
+constexpr size_t kStageBytes = size_t(64) << 20;
+
+// Host -> device.  Pinned sources are DMA'd directly; pageable ones are copied
+// through a pinned double buffer (multi-threaded memcpy overlapping the DMA).
+static int h2d(Ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return BIXCOR_OK;
+  if (is_pinned(h_src)) {
+    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
+    return BIXCOR_OK;
+  }
+  for (auto& b : c->stage) RC_TRY(b.reserve(kStageBytes));
+  cudaEvent_t done[2];
+  for (auto& e : done) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  int buf = 0;
+  for (size_t o = 0; o < bytes; o += kStageBytes, buf ^= 1) {
+    const size_t len = std::min(kStageBytes, bytes - o);
+    if (o >= 2 * kStageBytes) CU_TRY(cudaEventSynchronize(done[buf]));
+    parallel_memcpy(c->stage[buf].ptr, (const char*)h_src + o, len);
+    CU_TRY(cudaMemcpyAsync((char*)d_dst + o, c->stage[buf].ptr, len, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaEventRecord(done[buf], s));
+  }
+  CU_TRY(cudaStreamSynchronize(s));
+  for (auto& e : done) cudaEventDestroy(e);
+  return BIXCOR_OK;
+}
+
+// Device -> host of one finished range; `ready` (may be null) gates the copy.
+struct D2HPipe {
+  Ctx* c;
+  bool pinned_dst;
+  int buf = 0;
+  struct Pending {
+    void* h_dst;
+    size_t len;
+    cudaEvent_t ev;
+    bool active = false;
+  } pend[2];
+  explicit D2HPipe(Ctx* c_, const void* h_dst_probe) : c(c_), pinned_dst(is_pinned(h_dst_probe)) {}
+  int flush_slot(int b) {
+    if (!pend[b].active) return BIXCOR_OK;
+    CU_TRY(cudaEventSynchronize(pend[b].ev));
+    parallel_memcpy(pend[b].h_dst, c->stage[b].ptr, pend[b].len);
+    cudaEventDestroy(pend[b].ev);
+    pend[b].active = false;
+    return BIXCOR_OK;
+  }
+  int push(void* h_dst, const void* d_src, size_t bytes, cudaEvent_t ready) {
+    if (bytes == 0) return BIXCOR_OK;
+    if (ready) CU_TRY(cudaStreamWaitEvent(c->copy_out, ready, 0));
+    if (pinned_dst) {
+      CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->copy_out));
+      return BIXCOR_OK;
+    }
+    for (auto& b : c->stage) RC_TRY(b.reserve(kStageBytes));
+    for (size_t o = 0; o < bytes; o += kStageBytes) {
+      const size_t len = std::min(kStageBytes, bytes - o);
+      RC_TRY(flush_slot(buf));
+      CU_TRY(cudaMemcpyAsync(c->stage[buf].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
+      CU_TRY(cudaEventCreateWithFlags(&pend[buf].ev, cudaEventDisableTiming));
+      CU_TRY(cudaEventRecord(pend[buf].ev, c->copy_out));
+      pend[buf].h_dst = (char*)h_dst + o;
+      pend[buf].len = len;
+      pend[buf].active = true;
+      buf ^= 1;
+    }
+    return BIXCOR_OK;
+  }
+  int finish() {
+    RC_TRY(flush_slot(buf));
+    RC_TRY(flush_slot(buf ^ 1));
+    CU_TRY(cudaStreamSynchronize(c->copy_out));
+    return BIXCOR_OK;
+  }
+};
+
+// ----------------------------------------------------------------------------
+// device-level building blocks (all pointers device, ctx current)
+// ----------------------------------------------------------------------------
+static int validate_rows(int64_t p, int64_t row_begin, int64_t row_end) {
+  if (p < 1) return fail(BIXCOR_ERR_INVALID, "p must be >= 1");
+  if (row_begin < 0 || row_end > p || row_begin > row_end)
+    return fail(BIXCOR_ERR_INVALID, "bad row range [%lld,%lld) for p = %lld", (long long)row_begin, (long long)row_end,
+                (long long)p);
+  if (row_begin % kTile != 0)
+    return fail(BIXCOR_ERR_INVALID, "row_begin (%lld) must be a multiple of %d", (long long)row_begin, kTile);
+  return BIXCOR_OK;
+}
+
+// Packed correlation of rows [row_begin,row_end).  If `pipe` is given, every
+// finished band is copied to h_out (host slice) while later bands compute.
+static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                              int precision, int64_t row_begin, int64_t row_end, double* d_out, D2HPipe* pipe,
+                              double* h_out) {
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (row_begin == row_end) return BIXCOR_OK;
+  Operand op;
+  RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
+  EpiArgs e;
+  e.epi = dmma::EPI_PACKED;
+  e.out = d_out;
+  e.out_base = packed_row_offset(row_begin, p, shift);
+  e.shift = shift;
+  e.beta = beta;
+  e.keep_sign = 0;
+  const int ngroups = (int)tl->group_tile.size() - 1;
+  for (int g = 0; g < ngroups; ++g) {
+    const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
+    RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, e));
+    if (pipe) {
+      cudaEvent_t ev = ctx_event(c);
+      CU_TRY(cudaEventRecord(ev, c->compute));
+      const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - e.out_base;
+      const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - e.out_base;
+      RC_TRY(pipe->push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev));
+    }
+  }
+  return BIXCOR_OK;
+}
+
+static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
+                            int spearman, int precision, int64_t row_begin, int64_t row_end, double* d_ra,
+                            double* d_rb, double* d_z, double* d_pv, D2HPipe* pipe, double* h_ra, double* h_rb,
+                            double* h_z, double* h_pv) {
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (na < 4 || nb < 4) return fail(BIXCOR_ERR_INVALID, "differential correlation needs n_a, n_b >= 4");
+  if (row_begin == row_end) return BIXCOR_OK;
+  Operand a, b;
+  RC_TRY(prepare_operand(c, d_xa, na, p, spearman, precision, 0, &a));
+  RC_TRY(prepare_operand(c, d_xb, nb, p, spearman, precision, 1, &b));
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
+  const double cf = spearman ? g_fieller : 1.0;
+  EpiArgs e;
+  e.epi = dmma::EPI_DIFFCOR;
+  e.out_base = packed_row_offset(row_begin, p, 1);
+  e.shift = 1;
+  e.r_a = d_ra;
+  e.r_b = d_rb;
+  e.z = d_z;
+  e.pv = d_pv;
+  e.inv_se = 1.0 / std::sqrt(cf / (double)(na - 3) + cf / (double)(nb - 3));
+  const int ngroups = (int)tl->group_tile.size() - 1;
+  for (int g = 0; g < ngroups; ++g) {
+    const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
+    RC_TRY(launch_gram(c, a, &b, p, tl->d_tiles + t0, t1 - t0, e));
+    if (pipe) {
+      cudaEvent_t ev = ctx_event(c);
+      CU_TRY(cudaEventRecord(ev, c->compute));
+      const int64_t o0 = packed_row_offset(tl->group_row[g], p, 1) - e.out_base;
+      const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, 1) - e.out_base;
+      const size_t bytes = sizeof(double) * (size_t)(o1 - o0);
+      RC_TRY(pipe->push(h_ra + o0, d_ra + o0, bytes, ev));
+      RC_TRY(pipe->push(h_rb + o0, d_rb + o0, bytes, nullptr));
+      RC_TRY(pipe->push(h_z + o0, d_z + o0, bytes, nullptr));
+      RC_TRY(pipe->push(h_pv + o0, d_pv + o0, bytes, nullptr));
+    }
+  }
+  return BIXCOR_OK;
+}
+
+// Dense correlation / affinity.  Full range + mirror on one GPU; a strict sub-range
+// computes the full strip (all block columns) of the requested genes' columns.
+static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, double beta, int keep_sign,
+                        int precision, int64_t row_begin, int64_t row_end, double* d_app) {
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (row_begin == row_end) return BIXCOR_OK;
+  Operand op;
+  RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
+  const bool full = (row_begin == 0 && row_end == p);
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, full ? 1 : 0, 8, &tl));
+  EpiArgs e;
+  e.epi = dmma::EPI_DENSE;
+  e.out = d_app;
+  e.ldo = p;
+  e.mirror = full ? 1 : 0;
+  e.diag_one = 1;
+  e.beta = beta;
+  e.keep_sign = keep_sign;
+  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, e);
+}
+
+static int dev_tom_connectivity(Ctx* c, double* d_a, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
+                                double* d_k) {
+  if (row_begin < 0 || row_end > p || row_begin > row_end) return fail(BIXCOR_ERR_INVALID, "bad row range");
+  if (row_begin == row_end) return BIXCOR_OK;
+  Timed tm(c, T_OTHER);
+  tom_connectivity_kernel<<<(unsigned)(row_end - row_begin), 256, 0, c->compute>>>(d_a, p, row_begin, signed_ ? 0 : 1, d_k);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
+// The TOM GEMM operand is the affinity matrix itself (A symmetric: column i == row i).
+static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p, int signed_, int version,
+                        int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out) {
+  (void)signed_;  // |A| was substituted in place by the connectivity pass when unsigned
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
+    return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
+  if (row_begin == row_end) return BIXCOR_OK;
+  RC_TRY(c->vec.reserve(sizeof(double) * (size_t)p * 4));
+  double* d_diag = (double*)c->vec.ptr;  // first p entries: diagonal
+  {
+    Timed tm(c, T_OTHER);
+    extract_diag_kernel<<<(unsigned)((p + 255) / 256), 256, 0, c->compute>>>(d_a, p, d_diag);
+    g_launches++;
+  }
+  Operand op;
+  op.precision = precision;
+  op.p = p;
+  if (precision == BIXCOR_PREC_F64) {
+    if (p % dmma::BK != 0) {
+      // pad K: copy A into a K-padded operand buffer
+      const int K = round_up((int)p, dmma::BK);
+      RC_TRY(c->op[1].reserve(sizeof(double) * (size_t)K * p));
+      CU_TRY(cudaMemsetAsync(c->op[1].ptr, 0, sizeof(double) * (size_t)K * p, c->compute));
+      CU_TRY(cudaMemcpy2DAsync(c->op[1].ptr, sizeof(double) * K, d_a, sizeof(double) * p, sizeof(double) * p, p,
+                               cudaMemcpyDeviceToDevice, c->compute));
+      op.K = K;
+      op.z64 = (const double*)c->op[1].ptr;
+    } else {
+      op.K = (int)p;
+      op.z64 = d_a;
+    }
+  } else if (precision == BIXCOR_PREC_TF32X3) {
+    const int K = round_up((int)p, 32);
+    RC_TRY(c->op[1].reserve(sizeof(float) * 2 * (size_t)K * p));
+    ColumnOut co;
+    memset(&co, 0, sizeof co);
+    co.mode = COL_TF32;
+    co.kpad = K;
+    co.f32 = (float*)c->op[1].ptr;
+    co.ld32 = K;
+    co.plane32 = (int64_t)K * p;
+    Timed tm(c, T_COLS);
+    split_tf32_kernel<<<(unsigned)p, 256, 0, c->compute>>>(d_a, p, (int)p, co);
+    g_launches++;
+    op.K = K;
+    op.f32 = co.f32;
+  } else {
+    return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64 and BIXCOR_PREC_TF32X3");
+  }
+  const bool full = (row_begin == 0 && row_end == p);
+  const int upper = (packed || full) ? 1 : 0;
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, upper, 8, &tl));
+  EpiArgs e;
+  e.epi = dmma::EPI_TOM;
+  e.out = d_out;
+  e.ldo = p;
+  e.shift = 1;
+  e.out_base = packed ? packed_row_offset(row_begin, p, 1) : 0;
+  e.mirror = (!packed && full) ? 1 : 0;
+  e.A = d_a;
+  e.kvec = d_k;
+  e.dvec = d_diag;
+  e.tom_v2 = (version == BIXCOR_TOM_V2);
+  e.tom_packed = packed ? 1 : 0;
+  // non-packed strip mode writes into out + 0 with absolute (i*p + j) addressing
+  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, e);
+}
+
+static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
+                                 int64_t cells, int64_t genes, int precision, double* d_gram, double* d_colsum) {
+  if (precision != BIXCOR_PREC_F64)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram currently runs on the FP64 path only");
+  const int chunk = 8192;  // cells per dense panel (K of one Gram accumulation pass)
+  RC_TRY(c->panel.reserve(sizeof(double) * (size_t)chunk * genes));
+  TileList* tl;
+  RC_TRY(get_tiles(c, genes, 0, genes, 1, 8, &tl));
+  for (int64_t c0 = 0; c0 < cells; c0 += chunk) {
+    const int nc = (int)std::min<int64_t>(chunk, cells - c0);
+    const int K = round_up(nc, dmma::BK);
+    {
+      Timed tm(c, T_OTHER);
+      CU_TRY(cudaMemsetAsync(c->panel.ptr, 0, sizeof(double) * (size_t)K * genes, c->compute));
+      csr_densify_kernel<<<(nc * 32 + 255) / 256, 256, 0, c->compute>>>(d_indptr, d_indices, d_data, c0, nc, genes,
+                                                                         (double*)c->panel.ptr, K);
+      panel_rowsum_kernel<<<(unsigned)genes, 128, 0, c->compute>>>((const double*)c->panel.ptr, K, nc, d_colsum);
+      g_launches += 2;
+    }
+    Operand op;
+    op.precision = BIXCOR_PREC_F64;
+    op.K = K;
+    op.p = genes;
+    op.z64 = (const double*)c->panel.ptr;
+    EpiArgs e;
+    e.epi = dmma::EPI_ACCUM;
+    e.out = d_gram;
+    e.ldo = genes;
+    RC_TRY(launch_gram(c, op, nullptr, genes, tl->d_tiles, tl->ntiles, e));
+  }
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
+static int dev_sparse_finalise(Ctx* c, const double* d_gram, const double* d_colsum, int64_t total_cells,
+                               int64_t genes, double* d_out) {
+  Timed tm(c, T_OTHER);
+  dim3 grid((unsigned)((genes + 255) / 256), (unsigned)genes);
+  sparse_finalise_kernel<<<grid, 256, 0, c->compute>>>(d_gram, d_colsum, (double)total_cells, genes, d_out);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
+static int finish(Ctx* c) {
+  CU_TRY(cudaStreamSynchronize(c->compute));
+  return BIXCOR_OK;
+}
+static int finish_dev(Ctx* c) { return g_async ? BIXCOR_OK : finish(c); }
+
+// run fn(ctx, rank) on every device of the process (one host thread per device)
+template <class F>
+static int for_each_device(F fn) {
+  const int nd = (int)g_ctx.size();
+  if (nd == 1) {
+    CU_TRY(cudaSetDevice(g_ctx[0]->device));
+    call_begin(g_ctx[0]);
+    return fn(g_ctx[0], 0, 1);
+  }
+  std::vector<int> rcs(nd, BIXCOR_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; ++d)
+    th.emplace_back([&, d] {
+      if (cudaSetDevice(g_ctx[d]->device) != cudaSuccess) {
+        rcs[d] = fail(BIXCOR_ERR_CUDA, "cudaSetDevice(%d) failed", g_ctx[d]->device);
+        return;
+      }
+      call_begin(g_ctx[d]);
+      rcs[d] = fn(g_ctx[d], d, nd);
+    });
+  for (auto& t : th) t.join();
+  for (int rc : rcs)
+    if (rc != BIXCOR_OK) return rc;
+  return BIXCOR_OK;
+}
+
+static void shard_rows_impl(int64_t p, int shift, int world, int rank, int64_t* r0, int64_t* r1) {
+  const double total = shift ? 0.5 * (double)p * (double)(p - 1) : 0.5 * (double)p * (double)(p + 1);
+  auto boundary = [&](int q) -> int64_t {
+    if (q <= 0) return 0;
+    if (q >= world) return p;
+    const double target = total * (double)q / (double)world;
+    const double a = shift ? 2.0 * p - 1.0 : 2.0 * p + 1.0;
+    const double disc = std::max(0.0, a * a - 8.0 * target);
+    double r = (a - std::sqrt(disc)) / 2.0;
+    int64_t rr = (int64_t)std::nearbyint(r / kTile) * kTile;
+    return std::max<int64_t>(0, std::min<int64_t>(p, rr));
+  };
+  *r0 = boundary(rank);
+  *r1 = boundary(rank + 1);
+}
+
+}  // namespace bixcor
+
+// ============================================================================
+// C ABI
+// ============================================================================
+using namespace bixcor;
+
+extern "C" {
+
+const char* bixcor_last_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_err;
+  return copy.c_str();
+}
+
+int64_t bixcor_launch_count(void) { return g_launches.load(); }
+
+int bixcor_set_fieller(double c) {
+  if (!(c > 0.0)) return fail(BIXCOR_ERR_INVALID, "Fieller factor must be positive");
+  g_fieller = c;
+  return BIXCOR_OK;
+}
+
+int bixcor_init(int n_gpus) { return bixcor_init_devices(0, n_gpus); }
+
+int bixcor_init_devices(int first_device, int n_gpus) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (!g_ctx.empty()) {
+    if ((int)g_ctx.size() == n_gpus && g_ctx[0]->device == first_device) return BIXCOR_OK;
+    for (auto* c : g_ctx) ctx_destroy(c);
+    g_ctx.clear();
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(BIXCOR_ERR_NO_GPU, "no CUDA device visible (%s); libbixcor has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (n_gpus < 1 || first_device < 0 || first_device + n_gpus > count)
+    return fail(BIXCOR_ERR_INVALID, "requested devices [%d,%d) but %d visible", first_device, first_device + n_gpus,
+                count);
+  if (const char* v = getenv("BIXCOR_DMMA_VARIANT")) g_dmma_variant = atoi(v);
+  for (int d = 0; d < n_gpus; ++d) {
+    Ctx* c = nullptr;
+    int rc = ctx_create(first_device + d, &c);
+    if (rc != BIXCOR_OK) {
+      for (auto* cc : g_ctx) ctx_destroy(cc);
+      g_ctx.clear();
+      return rc;
+    }
+    g_ctx.push_back(c);
+  }
+  return BIXCOR_OK;
+}
+
+void bixcor_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  for (auto* c : g_ctx) ctx_destroy(c);
+  g_ctx.clear();
+}
+
+int bixcor_timing_enable(int on) {
+  g_timing = on != 0;
+  for (auto* c : g_ctx) timing_reset(c);
+  return BIXCOR_OK;
+}
+
+int bixcor_dev_set_async(int on) {
+  g_async = on != 0;
+  return BIXCOR_OK;
+}
+
+int bixcor_dev_set_stream(void* stream) {
+  RC_TRY(ensure_init());
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaStreamSynchronize(c->compute));
+  if (c->owns_compute && c->compute) cudaStreamDestroy(c->compute);
+  if (stream) {
+    c->compute = (cudaStream_t)stream;
+    c->owns_compute = false;
+  } else {
+    CU_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    c->owns_compute = true;
+  }
+  return BIXCOR_OK;
+}
+
+int bixcor_dev_synchronize(void) {
+  RC_TRY(ensure_init());
+  for (auto* c : g_ctx) {
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->compute));
+  }
+  return BIXCOR_OK;
+}
+
+int bixcor_last_timing(double* what4) {
+  if (g_ctx.empty()) return fail(BIXCOR_ERR_INVALID, "not initialised");
+  for (auto* c : g_ctx) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->compute);
+    timing_collect(c);
+  }
+  // max over devices (they run concurrently)
+  for (int i = 0; i < 4; ++i) what4[i] = 0;
+  for (auto* c : g_ctx) {
+    for (int i = 0; i < 3; ++i) what4[i] = std::max(what4[i], c->last_ms[i]);
+    what4[3] = std::max(what4[3], (double)c->last_gemm_launches);
+  }
+  return BIXCOR_OK;
+}
+
+// ---- packed helpers ---------------------------------------------------------
+int64_t bixcor_packed_len(int64_t p, int shift) { return shift ? p * (p - 1) / 2 : p * (p + 1) / 2; }
+int64_t bixcor_packed_offset(int64_t i, int64_t p, int shift) { return packed_row_offset(i, p, shift ? 1 : 0); }
+
+int bixcor_upper_to_dense(const double* packed, int shift, int64_t p, double* out) {
+  if (!packed || !out || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
+  int64_t idx = 0;
+  for (int64_t i = 0; i < p; ++i)
+    for (int64_t j = i; j < p; ++j) {
+      if (shift && i == j) {
+        out[i + j * p] = 1.0;
+      } else {
+        out[i + j * p] = packed[idx];
+        out[j + i * p] = packed[idx];
+        ++idx;
+      }
+    }
+  return BIXCOR_OK;
+}
+
+int bixcor_dense_to_upper(const double* dense, int shift, int64_t p, double* out) {
+  if (!dense || !out || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
+  int64_t idx = 0;
+  const int64_t s = shift ? 1 : 0;
+  for (int64_t i = 0; i < p; ++i)
+    for (int64_t j = i + s; j < p; ++j) out[idx++] = dense[i + j * p];
+  return BIXCOR_OK;
+}
+
+int bixcor_shard_rows(int64_t p, int shift, int world, int rank, int64_t* row_begin, int64_t* row_end) {
+  if (world < 1 || rank < 0 || rank >= world || p < 0 || !row_begin || !row_end)
+    return fail(BIXCOR_ERR_INVALID, "bad shard arguments");
+  shard_rows_impl(p, shift ? 1 : 0, world, rank, row_begin, row_end);
+  return BIXCOR_OK;
+}
+
+// ---- device-pointer entry points -------------------------------------------
+#define DEV_PROLOGUE()                      \
+  RC_TRY(ensure_init());                    \
+  Ctx* c = g_ctx[0];                        \
+  CU_TRY(cudaSetDevice(c->device));         \
+  call_begin(c);
+
+int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_out) {
+  DEV_PROLOGUE();
+  if (n < 1 || p < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
+  if (n > 16384) return fail(BIXCOR_ERR_UNSUPPORTED, "rank kernel supports n <= 16384");
+  ColumnOut co;
+  memset(&co, 0, sizeof co);
+  co.mode = COL_RANKS;
+  co.f64 = d_out;
+  co.ld64 = n;
+  co.kpad = (int)n;
+  int npow2 = 32;
+  while (npow2 < n) npow2 <<= 1;
+  const int threads = std::min(256, npow2);
+  const size_t smem = (size_t)npow2 * 12;
+  CU_TRY(cudaFuncSetAttribute(rank_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    Timed tm(c, T_COLS);
+    rank_columns_kernel<<<(unsigned)p, threads, smem, c->compute>>>(d_x, n, (int)n, npow2, co);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  return finish_dev(c);
+}
+
+int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                              int precision, int64_t row_begin, int64_t row_end, double* d_out) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_cor_upper_rows(c, d_x, n, p, spearman, shift ? 1 : 0, beta, precision, row_begin, row_end, d_out, nullptr,
+                            nullptr));
+  return finish_dev(c);
+}
+
+int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_affinity(c, d_x, n, p, spearman, 1.0, 1, precision, 0, p, d_out));
+  return finish_dev(c);
+}
+
+int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p, int spearman,
+                            int precision, int64_t row_begin, int64_t row_end, double* d_r_a, double* d_r_b,
+                            double* d_z, double* d_pval) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_diffcor_rows(c, d_xa, na, d_xb, nb, p, spearman, precision, row_begin, row_end, d_r_a, d_r_b, d_z, d_pval,
+                          nullptr, nullptr, nullptr, nullptr, nullptr));
+  return finish_dev(c);
+}
+
+int bixcor_dev_affinity_cols(const double* d_x, int64_t n, int64_t p, int spearman, int signed_, double beta,
+                             int precision, int64_t row_begin, int64_t row_end, double* d_a_pp) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_affinity(c, d_x, n, p, spearman, beta, signed_ ? 1 : 0, precision, row_begin, row_end, d_a_pp));
+  return finish_dev(c);
+}
+
+int bixcor_dev_tom_connectivity(double* d_a_pp, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
+                                double* d_k) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_tom_connectivity(c, d_a_pp, p, signed_, row_begin, row_end, d_k));
+  return finish_dev(c);
+}
+
+int bixcor_dev_tom_rows(const double* d_a_pp, const double* d_k, int64_t p, int signed_, int version, int precision,
+                        int packed, int64_t row_begin, int64_t row_end, double* d_out) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_tom_rows(c, d_a_pp, d_k, p, signed_, version, precision, packed, row_begin, row_end, d_out));
+  return finish_dev(c);
+}
+
+int bixcor_dev_sparse_gram_accumulate(const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
+                                      int64_t cells, int64_t genes, int precision, double* d_gram_pp,
+                                      double* d_colsum) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_sparse_accumulate(c, d_indptr, d_indices, d_data, cells, genes, precision, d_gram_pp, d_colsum));
+  return finish_dev(c);
+}
+
+int bixcor_dev_sparse_gram_finalise(const double* d_gram_pp, const double* d_colsum, int64_t total_cells,
+                                    int64_t genes, double* d_out_packed) {
+  DEV_PROLOGUE();
+  RC_TRY(dev_sparse_finalise(c, d_gram_pp, d_colsum, total_cells, genes, d_out_packed));
+  return finish_dev(c);
+}
+
+// ---- host-pointer entry points ---------------------------------------------
+int bixcor_rank_columns(const double* x, int64_t n, int64_t p, double* out) {
+  RC_TRY(ensure_init());
+  if (!x || !out) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (n == 0 || p == 0) return BIXCOR_OK;
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t bytes = sizeof(double) * (size_t)n * p;
+  RC_TRY(c->x[0].reserve(bytes));
+  RC_TRY(c->out.reserve(bytes));
+  RC_TRY(h2d(c, c->x[0].ptr, x, bytes, c->compute));
+  RC_TRY(bixcor_dev_rank_columns((const double*)c->x[0].ptr, n, p, (double*)c->out.ptr));
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out);
+  RC_TRY(pipe.push(out, c->out.ptr, bytes, nullptr));
+  return pipe.finish();
+}
+
+static int host_shape_check(const void* x, int64_t n, int64_t p, const void* out) {
+  if (!x || !out) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (n < 2) return fail(BIXCOR_ERR_INVALID, "need at least 2 samples (n = %lld)", (long long)n);
+  if (p < 1) return fail(BIXCOR_ERR_INVALID, "need at least 1 gene (p = %lld)", (long long)p);
+  if (p > 2000000) return fail(BIXCOR_ERR_UNSUPPORTED, "p too large");
+  return BIXCOR_OK;
+}
+
+int bixcor_cor_upper_rows(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta, int precision,
+                          int64_t row_begin, int64_t row_end, double* out_slice) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out_slice));
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  shift = shift ? 1 : 0;
+  // split the requested rows over the process's devices (contiguous packed ranges)
+  return for_each_device([&](Ctx* c, int d, int nd) -> int {
+    // sub-shard [row_begin,row_end) by pair count: reuse the global partition on the remaining triangle
+    int64_t r0 = row_begin, r1 = row_end;
+    if (nd > 1) {
+      int64_t q0, q1;
+      shard_rows_impl(p - row_begin, shift, nd, d, &q0, &q1);
+      r0 = row_begin + q0;
+      r1 = std::min(row_end, row_begin + q1);
+      if (d == nd - 1) r1 = row_end;
+      if (r0 > r1) r0 = r1;
+    }
+    const size_t in_bytes = sizeof(double) * (size_t)n * p;
+    const int64_t base = packed_row_offset(row_begin, p, shift);
+    const int64_t o0 = packed_row_offset(r0, p, shift), o1 = packed_row_offset(r1, p, shift);
+    RC_TRY(c->x[0].reserve(in_bytes));
+    RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o1 - o0)));
+    RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
+    D2HPipe pipe(c, out_slice);
+    RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[0].ptr, n, p, spearman, shift, beta, precision, r0, r1,
+                              (double*)c->out.ptr, &pipe, out_slice + (o0 - base)));
+    RC_TRY(finish(c));
+    return pipe.finish();
+  });
+}
+
+int bixcor_cor_upper(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta, int precision,
+                     double* out_packed) {
+  return bixcor_cor_upper_rows(x, n, p, spearman, shift, beta, precision, 0, p, out_packed);
+}
+
+int bixcor_cor_dense(const double* x, int64_t n, int64_t p, int spearman, int precision, double* out_pp) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out_pp));
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t in_bytes = sizeof(double) * (size_t)n * p, out_bytes = sizeof(double) * (size_t)p * p;
+  RC_TRY(c->x[0].reserve(in_bytes));
+  RC_TRY(c->out.reserve(out_bytes));
+  RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
+  RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, 1.0, 1, precision, 0, p, (double*)c->out.ptr));
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out_pp);
+  RC_TRY(pipe.push(out_pp, c->out.ptr, out_bytes, nullptr));
+  return pipe.finish();
+}
+
+int bixcor_diffcor_rows(const double* xa, int64_t na, const double* xb, int64_t nb, int64_t p, int spearman,
+                        int precision, int64_t row_begin, int64_t row_end, double* r_a, double* r_b, double* z,
+                        double* pval) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(xa, na, p, r_a));
+  RC_TRY(host_shape_check(xb, nb, p, r_b));
+  if (!z || !pval) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  return for_each_device([&](Ctx* c, int d, int nd) -> int {
+    int64_t r0 = row_begin, r1 = row_end;
+    if (nd > 1) {
+      int64_t q0, q1;
+      shard_rows_impl(p - row_begin, 1, nd, d, &q0, &q1);
+      r0 = row_begin + q0;
+      r1 = std::min(row_end, row_begin + q1);
+      if (d == nd - 1) r1 = row_end;
+      if (r0 > r1) r0 = r1;
+    }
+    const int64_t base = packed_row_offset(row_begin, p, 1);
+    const int64_t o0 = packed_row_offset(r0, p, 1), o1 = packed_row_offset(r1, p, 1);
+    const size_t len = (size_t)std::max<int64_t>(1, o1 - o0);
+    RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)na * p));
+    RC_TRY(c->x[1].reserve(sizeof(double) * (size_t)nb * p));
+    RC_TRY(c->out.reserve(sizeof(double) * 4 * len));
+    RC_TRY(h2d(c, c->x[0].ptr, xa, sizeof(double) * (size_t)na * p, c->compute));
+    RC_TRY(h2d(c, c->x[1].ptr, xb, sizeof(double) * (size_t)nb * p, c->compute));
+    double* d_out = (double*)c->out.ptr;
+    D2HPipe pipe(c, r_a);
+    const int64_t ho = o0 - base;
+    RC_TRY(dev_diffcor_rows(c, (const double*)c->x[0].ptr, na, (const double*)c->x[1].ptr, nb, p, spearman, precision,
+                            r0, r1, d_out, d_out + len, d_out + 2 * len, d_out + 3 * len, &pipe, r_a + ho, r_b + ho,
+                            z + ho, pval + ho));
+    RC_TRY(finish(c));
+    return pipe.finish();
+  });
+}
+
+int bixcor_diffcor(const double* xa, int64_t na, const double* xb, int64_t nb, int64_t p, int spearman, int precision,
+                   double* r_a, double* r_b, double* z, double* pval) {
+  return bixcor_diffcor_rows(xa, na, xb, nb, p, spearman, precision, 0, p, r_a, r_b, z, pval);
+}
+
+static int tom_common(Ctx* c, double* d_a, int64_t p, int signed_, int version, int precision, int packed,
+                      double* out) {
+  RC_TRY(c->vec.reserve(sizeof(double) * (size_t)p * 4));
+  double* d_k = (double*)c->vec.ptr + p;  // [0,p) is the diagonal scratch of dev_tom_rows
+  RC_TRY(dev_tom_connectivity(c, d_a, p, signed_, 0, p, d_k));
+  const size_t out_elems = packed ? (size_t)std::max<int64_t>(1, p * (p - 1) / 2) : (size_t)p * p;
+  RC_TRY(c->out.reserve(sizeof(double) * out_elems));
+  RC_TRY(dev_tom_rows(c, d_a, d_k, p, signed_, version, precision, packed, 0, p, (double*)c->out.ptr));
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out);
+  RC_TRY(pipe.push(out, c->out.ptr, sizeof(double) * (packed ? (size_t)(p * (p - 1) / 2) : (size_t)p * p), nullptr));
+  return pipe.finish();
+}
+
+int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int precision, double* out_pp) {
+  RC_TRY(ensure_init());
+  if (!a_pp || !out_pp) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (p < 1) return fail(BIXCOR_ERR_INVALID, "p must be >= 1");
+  if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
+    return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t bytes = sizeof(double) * (size_t)p * p;
+  RC_TRY(c->out2.reserve(bytes));
+  RC_TRY(h2d(c, c->out2.ptr, a_pp, bytes, c->compute));
+  return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, 0, out_pp);
+}
+
+int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int signed_, int version, double beta,
+                        int precision, int packed, double* out) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out));
+  if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
+    return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t in_bytes = sizeof(double) * (size_t)n * p;
+  RC_TRY(c->x[0].reserve(in_bytes));
+  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
+  RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
+  // the correlation feeding the TOM is always the exact / requested-precision Gram
+  const int cor_prec = (precision == BIXCOR_PREC_TF32X3) ? BIXCOR_PREC_TF32X3 : BIXCOR_PREC_F64;
+  RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
+                      (double*)c->out2.ptr));
+  return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, packed, out);
+}
+
+int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                           int64_t genes, int precision, double* out_packed) {
+  RC_TRY(ensure_init());
+  if (!indptr || !out_packed) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (cells < 2 || genes < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
+  const int64_t nnz = indptr[cells];
+  if (nnz < 0 || (nnz > 0 && (!indices || !data))) return fail(BIXCOR_ERR_INVALID, "bad CSR arrays");
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t b_ptr = sizeof(int64_t) * (size_t)(cells + 1), b_idx = sizeof(int32_t) * (size_t)nnz,
+               b_dat = sizeof(float) * (size_t)nnz;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + 256));
+  char* base = (char*)c->sparse_in.ptr;
+  int64_t* d_ptr = (int64_t*)base;
+  int32_t* d_idx = (int32_t*)(base + al(b_ptr));
+  float* d_dat = (float*)(base + al(b_ptr) + al(b_idx));
+  RC_TRY(h2d(c, d_ptr, indptr, b_ptr, c->compute));
+  RC_TRY(h2d(c, d_idx, indices, b_idx, c->compute));
+  RC_TRY(h2d(c, d_dat, data, b_dat, c->compute));
+  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)genes * genes));
+  RC_TRY(c->vec.reserve(sizeof(double) * (size_t)genes * 4));
+  CU_TRY(cudaMemsetAsync(c->out2.ptr, 0, sizeof(double) * (size_t)genes * genes, c->compute));
+  CU_TRY(cudaMemsetAsync(c->vec.ptr, 0, sizeof(double) * (size_t)genes, c->compute));
+  RC_TRY(dev_sparse_accumulate(c, d_ptr, d_idx, d_dat, cells, genes, precision, (double*)c->out2.ptr,
+                               (double*)c->vec.ptr));
+  const size_t out_bytes = sizeof(double) * (size_t)(genes * (genes - 1) / 2);
+  RC_TRY(c->out.reserve(std::max<size_t>(out_bytes, 8)));
+  RC_TRY(dev_sparse_finalise(c, (const double*)c->out2.ptr, (const double*)c->vec.ptr, cells, genes,
+                             (double*)c->out.ptr));
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out_packed);
+  RC_TRY(pipe.push(out_packed, c->out.ptr, out_bytes, nullptr));
+  return pipe.finish();
+}
+
+}  // extern "C"

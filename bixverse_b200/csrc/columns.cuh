@@ -1,0 +1,275 @@
+// Per-gene column kernels: Spearman average-tie rank transform and Pearson
+// standardisation.  Both write the Gram operand directly in the layout the
+// GEMM kernels consume (K-major: the samples of one gene are contiguous and
+// zero padded to `kpad`), so the standardised matrix never makes an extra
+// round trip through HBM.
+//
+// Reference semantics restated (see oracle/oracle.py): crate
+// core::math::matrix_helpers::rank_matrix_col (exposed at
+// src/rust/src/enrichment/r_singscore.rs:89-95) == base R
+// rank(ties.method = "average"); column_pairwise_cor
+// (src/rust/src/base/r_cors_similarity.rs:70-77) == base R cor().
+#pragma once
+
+#include "common.cuh"
+
+namespace bixcor {
+
+enum ColumnMode : int {
+  COL_RANKS = 0,  // f64 average ranks (1-based), ld = n
+  COL_Z64 = 1,    // f64 unit-norm centred column, zero padded to kpad
+  COL_I8 = 2,     // centred integer ranks d = 2*rank-(n+1) as base-16 digits (h, 16*l, l) + 1/|d|
+  COL_TF32 = 3,   // unit-norm centred column split into TF32 hi / lo planes
+};
+
+struct ColumnOut {
+  int mode;
+  int kpad;            // padded K (>= n); elements [n, kpad) are zero filled
+  double* f64;         // COL_RANKS / COL_Z64
+  int64_t ld64;
+  int8_t* i8;          // COL_I8: 3 planes, plane stride `plane8` bytes
+  int64_t ld8;
+  int64_t plane8;
+  float* f32;          // COL_TF32: 2 planes, plane stride `plane32` floats
+  int64_t ld32;
+  int64_t plane32;
+  double* inv_norm;    // COL_I8: 1/sqrt(sum d^2) per gene
+};
+
+__device__ __forceinline__ uint64_t sortable_key(double v) {
+  v = v + 0.0;  // -0.0 -> +0.0 so that signed zeros tie (base-R semantics)
+  uint64_t b = (uint64_t)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// exclusive prefix-max over the threads of the block (identity -1)
+__device__ __forceinline__ int block_excl_prefix_max(int v, int* scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, t);
+  }
+  __syncthreads();
+  if (lane == 31) scr[warp] = inc;
+  __syncthreads();
+  int wp = -1;
+  for (int w = 0; w < warp; ++w) wp = max(wp, scr[w]);
+  int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = -1;
+  return max(wp, ex);
+}
+
+// exclusive suffix-min over the threads of the block (identity INT_MAX)
+__device__ __forceinline__ int block_excl_suffix_min(int v, int* scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_down_sync(0xffffffffu, inc, o);
+    if (lane + o < 32) inc = min(inc, t);
+  }
+  __syncthreads();
+  if (lane == 0) scr[warp] = inc;
+  __syncthreads();
+  int ws = 0x7fffffff;
+  for (int w = warp + 1; w < nwarp; ++w) ws = min(ws, scr[w]);
+  int ex = __shfl_down_sync(0xffffffffu, inc, 1);
+  if (lane == 31) ex = 0x7fffffff;
+  return min(ws, ex);
+}
+
+// Write one standardised column in the requested operand layout.
+// `val(i)` yields the centred value of sample i (double), `scale_div` the norm.
+__device__ __forceinline__ void emit_tf32(const ColumnOut& out, int64_t j, int i, double z) {
+  float hi = to_tf32((float)z);
+  float lo = to_tf32((float)(z - (double)hi));
+  out.f32[j * out.ld32 + i] = hi;
+  out.f32[out.plane32 + j * out.ld32 + i] = lo;
+}
+
+// One CTA per gene.  Dynamic smem: npow2 * 12 bytes (u64 key + u32 index).
+// blockDim.x must be a power of two, a multiple of 32 and <= npow2.
+__global__ void __launch_bounds__(256)
+rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2, ColumnOut out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* idx = reinterpret_cast<uint32_t*>(key + npow2);
+  __shared__ long long scr_ll[32];
+  __shared__ int scr_i[32];
+  __shared__ int s_nan;
+
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t j = blockIdx.x;
+  const double* col = x + j * ldx;
+
+  if (tid == 0) s_nan = 0;
+  __syncthreads();
+  bool has_nan = false;
+  for (int i = tid; i < npow2; i += nt) {
+    uint64_t k = ~0ull;
+    if (i < n) {
+      double v = col[i];
+      if (v != v) has_nan = true;
+      k = sortable_key(v);
+    }
+    key[i] = k;
+    idx[i] = (uint32_t)i;
+  }
+  if (has_nan) s_nan = 1;
+  __syncthreads();
+
+  if (s_nan) {  // base-R cor(): a column holding NA correlates to NA with everything
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    if (out.mode == COL_RANKS) {
+      for (int i = tid; i < n; i += nt) out.f64[j * out.ld64 + i] = qnan;
+    } else if (out.mode == COL_Z64) {
+      for (int i = tid; i < out.kpad; i += nt) out.f64[j * out.ld64 + i] = (i < n) ? qnan : 0.0;
+    } else if (out.mode == COL_I8) {
+      for (int i = tid; i < out.kpad; i += nt) {
+        out.i8[j * out.ld8 + i] = 0;
+        out.i8[out.plane8 + j * out.ld8 + i] = 0;
+        out.i8[2 * out.plane8 + j * out.ld8 + i] = 0;
+      }
+      if (tid == 0) out.inv_norm[j] = qnan;
+    } else {
+      for (int i = tid; i < out.kpad; i += nt) {
+        float f = (i < n) ? __int_as_float(0x7fc00000) : 0.f;
+        out.f32[j * out.ld32 + i] = f;
+        out.f32[out.plane32 + j * out.ld32 + i] = 0.f;
+      }
+    }
+    return;
+  }
+
+  // ---- bitonic sort of (key, idx) in shared memory -------------------------
+  const int half = npow2 >> 1;
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int t = tid; t < half; t += nt) {
+        const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+        const int l = i | jj;
+        const bool up = (i & k) == 0;
+        const uint64_t ki = key[i], kl = key[l];
+        if ((ki > kl) == up && ki != kl) {
+          key[i] = kl;
+          key[l] = ki;
+          const uint32_t ti = idx[i];
+          idx[i] = idx[l];
+          idx[l] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- tie groups: flag the first position of every run of equal keys -------
+  for (int s = tid; s < npow2; s += nt) {
+    const bool start = (s >= n) || (s == 0) || (key[s] != key[s - 1]);
+    if (start) idx[s] |= 0x80000000u;
+  }
+  __syncthreads();  // keys are dead from here on; their storage is reused
+
+  uint32_t* val = reinterpret_cast<uint32_t*>(key);          // lo+hi+2 per sorted position
+  uint32_t* rk2 = reinterpret_cast<uint32_t*>(key) + npow2;  // 2*rank per original position
+  const int c = npow2 / nt;
+  const int s0 = tid * c, s1 = s0 + c;
+
+  int last = -1;
+  for (int s = s0; s < s1; ++s)
+    if (idx[s] & 0x80000000u) last = s;
+  int cur = block_excl_prefix_max(last, scr_i);
+  for (int s = s0; s < s1; ++s) {
+    if (idx[s] & 0x80000000u) cur = s;
+    val[s] = (uint32_t)cur;  // lo: first position of the run
+  }
+  int first = 0x7fffffff;  // smallest run-end position inside this thread's chunk
+  for (int s = s0; s < s1; ++s) {
+    const bool end = (s + 1 >= npow2) || (idx[s + 1] & 0x80000000u);
+    if (end) { first = s; break; }
+  }
+  cur = block_excl_suffix_min(first, scr_i);
+  for (int s = s1 - 1; s >= s0; --s) {
+    const bool end = (s + 1 >= npow2) || (idx[s + 1] & 0x80000000u);
+    if (end) cur = s;
+    val[s] += (uint32_t)cur + 2u;  // lo + hi + 2 == 2 * average 1-based rank
+  }
+  __syncthreads();
+  for (int s = tid; s < n; s += nt) rk2[idx[s] & 0x7fffffffu] = val[s];
+  __syncthreads();
+
+  // ---- emit ----------------------------------------------------------------
+  if (out.mode == COL_RANKS) {
+    for (int i = tid; i < n; i += nt) out.f64[j * out.ld64 + i] = 0.5 * (double)rk2[i];
+    return;
+  }
+  // centred integer rank d = 2*rank - (n+1); the rank mean is (n+1)/2 with or without ties
+  long long ss = 0;
+  for (int i = tid; i < n; i += nt) {
+    const long long d = (long long)rk2[i] - (long long)(n + 1);
+    ss += d * d;
+  }
+  ss = block_sum_ll(ss, scr_ll);
+  const double norm = sqrt((double)ss);
+  if (out.mode == COL_Z64) {
+    for (int i = tid; i < out.kpad; i += nt) {
+      double z = 0.0;
+      if (i < n) z = (double)((int)rk2[i] - (n + 1)) / norm;
+      out.f64[j * out.ld64 + i] = z;
+    }
+  } else if (out.mode == COL_I8) {
+    for (int i = tid; i < out.kpad; i += nt) {
+      int d = (i < n) ? (int)rk2[i] - (n + 1) : 0;
+      const int l = ((d + 8) & 15) - 8;  // low digit in [-8, 7]
+      const int h = (d - l) >> 4;        // |h| <= 127 for n <= 2025
+      out.i8[j * out.ld8 + i] = (int8_t)h;
+      out.i8[out.plane8 + j * out.ld8 + i] = (int8_t)(16 * l);
+      out.i8[2 * out.plane8 + j * out.ld8 + i] = (int8_t)l;
+    }
+    if (tid == 0) out.inv_norm[j] = 1.0 / norm;
+  } else {
+    for (int i = tid; i < out.kpad; i += nt) {
+      double z = 0.0;
+      if (i < n) z = (double)((int)rk2[i] - (n + 1)) / norm;
+      emit_tf32(out, j, i, z);
+    }
+  }
+}
+
+// Pearson: centre and scale one gene per CTA to unit Euclidean norm, so that
+// Z'Z is the correlation matrix (sd == 0 -> 0/0 = NaN column, IEEE propagation).
+__global__ void __launch_bounds__(128)
+standardise_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, ColumnOut out) {
+  __shared__ double scr[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t j = blockIdx.x;
+  const double* col = x + j * ldx;
+  double s = 0.0;
+  for (int i = tid; i < n; i += nt) s += col[i];
+  const double mean = block_sum(s, scr) / (double)n;
+  double q = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    const double c = col[i] - mean;
+    q += c * c;
+  }
+  const double norm = sqrt(block_sum(q, scr));
+  for (int i = tid; i < out.kpad; i += nt) {
+    double z = 0.0;
+    if (i < n) z = (col[i] - mean) / norm;
+    if (out.mode == COL_Z64) out.f64[j * out.ld64 + i] = z;
+    else emit_tf32(out, j, i, z);
+  }
+}
+
+// Split an existing f64 matrix (ld = ldin, `rows` x `k`) into TF32 hi/lo planes
+// (used for the TOM A*A fast path, where the operand is the affinity matrix itself).
+__global__ void split_tf32_kernel(const double* __restrict__ in, int64_t ldin, int k, ColumnOut out) {
+  const int64_t j = blockIdx.x;
+  for (int i = threadIdx.x; i < out.kpad; i += blockDim.x) {
+    double z = (i < k) ? in[j * ldin + i] : 0.0;
+    emit_tf32(out, j, i, z);
+  }
+}
+
+}  // namespace bixcor

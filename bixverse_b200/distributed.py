@@ -1,0 +1,169 @@
+"""One-process-per-GPU drivers for the sharded path.
+
+Bulk correlation / differential correlation shard the packed triangle into
+contiguous block-row ranges balanced by pair count: no data-path collective.
+TOM has one real exchange step: every rank builds the affinity columns of its
+gene slab, the slabs are exchanged over NCCL (NVLink/NVSwitch) so that each
+rank holds the full A operand, and the connectivity vector k is all-reduced.
+The sparse single-cell Gram is sharded by cells and the partial Gram matrices
+are all-reduced.
+
+The compute calls go through a *backend* object; the product backend is
+``DeviceBackend`` (device pointers into libbixcor, tensors in HBM).  The
+world_size-2 gloo tests inject a CPU stand-in to exercise the partitioning and
+collective plumbing without a GPU; that stand-in lives in ``tests/``, never here.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import PREC_F64, TOM_V1, TOM_V2, check
+
+TILE = 128
+
+
+def packed_offset(i: int, p: int, shift: int) -> int:
+    return i * (2 * p - i - 1) // 2 if shift else i * (2 * p - i + 1) // 2
+
+
+def pair_balanced_rows(p: int, shift: int, world: int, rank: int) -> tuple[int, int]:
+    """Same partition as bixcor_shard_rows (include/bixcor.h)."""
+    import ctypes as C
+
+    r0, r1 = C.c_int64(), C.c_int64()
+    check(_lib.load().bixcor_shard_rows(p, int(shift), world, rank, C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+def even_slab(p: int, world: int, rank: int) -> tuple[int, int]:
+    """Gene slab [c0,c1) for full-width strips: equal tile counts, 128-aligned."""
+    nb = (p + TILE - 1) // TILE
+    b0 = nb * rank // world
+    b1 = nb * (rank + 1) // world
+    return min(p, b0 * TILE), min(p, b1 * TILE)
+
+
+class DeviceBackend:
+    """libbixcor on the current CUDA device; tensors stay resident in HBM."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = _lib.load()
+
+    def _sync_in(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float64, device=self.device)
+
+    def cor_upper_rows(self, x, n, p, spearman, shift, beta, precision, r0, r1):
+        ln = packed_offset(r1, p, shift) - packed_offset(r0, p, shift)
+        out = self.empty(max(ln, 1))[:ln]
+        self._sync_in()
+        check(self.lib.bixcor_dev_cor_upper_rows(x.data_ptr(), n, p, int(spearman), int(shift), float(beta), precision,
+                                                 r0, r1, out.data_ptr()))
+        return out
+
+    def diffcor_rows(self, xa, na, xb, nb, p, spearman, precision, r0, r1):
+        ln = packed_offset(r1, p, 1) - packed_offset(r0, p, 1)
+        outs = [self.empty(max(ln, 1))[:ln] for _ in range(4)]
+        self._sync_in()
+        check(self.lib.bixcor_dev_diffcor_rows(xa.data_ptr(), na, xb.data_ptr(), nb, p, int(spearman), precision, r0, r1,
+                                               *[o.data_ptr() for o in outs]))
+        return dict(zip(("r_a", "r_b", "z_score", "p_val"), outs))
+
+    def affinity_cols(self, x, n, p, spearman, signed, beta, precision, c0, c1, a_full):
+        self._sync_in()
+        check(self.lib.bixcor_dev_affinity_cols(x.data_ptr(), n, p, int(spearman), int(signed), float(beta), precision,
+                                                c0, c1, a_full.data_ptr()))
+
+    def tom_connectivity(self, a_full, p, signed, c0, c1, k):
+        self._sync_in()
+        check(self.lib.bixcor_dev_tom_connectivity(a_full.data_ptr(), p, int(signed), c0, c1, k.data_ptr()))
+
+    def tom_rows(self, a_full, k, p, signed, version, precision, r0, r1):
+        ln = packed_offset(r1, p, 1) - packed_offset(r0, p, 1)
+        out = self.empty(max(ln, 1))[:ln]
+        self._sync_in()
+        check(self.lib.bixcor_dev_tom_rows(a_full.data_ptr(), k.data_ptr(), p, int(signed), version, precision, 1,
+                                           r0, r1, out.data_ptr()))
+        return out
+
+    def sparse_accumulate(self, indptr, indices, data, cells, genes, precision, gram, colsum):
+        self._sync_in()
+        check(self.lib.bixcor_dev_sparse_gram_accumulate(indptr.data_ptr(), indices.data_ptr(), data.data_ptr(), cells,
+                                                         genes, precision, gram.data_ptr(), colsum.data_ptr()))
+
+    def sparse_finalise(self, gram, colsum, total_cells, genes):
+        out = self.empty(max(genes * (genes - 1) // 2, 1))[: genes * (genes - 1) // 2]
+        self._sync_in()
+        check(self.lib.bixcor_dev_sparse_gram_finalise(gram.data_ptr(), colsum.data_ptr(), total_cells, genes,
+                                                       out.data_ptr()))
+        return out
+
+
+def _world(group=None) -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def sharded_cor_upper(backend, x, n, p, spearman, shift=1, beta=1.0, precision=PREC_F64, group=None):
+    """Rank-local slice of the packed correlation vector and its [o0,o1) range."""
+    rank, world = _world(group)
+    r0, r1 = pair_balanced_rows(p, shift, world, rank)
+    out = backend.cor_upper_rows(x, n, p, spearman, shift, beta, precision, r0, r1)
+    return out, (packed_offset(r0, p, shift), packed_offset(r1, p, shift))
+
+
+def sharded_diffcor(backend, xa, na, xb, nb, p, spearman, precision=PREC_F64, group=None):
+    rank, world = _world(group)
+    r0, r1 = pair_balanced_rows(p, 1, world, rank)
+    res = backend.diffcor_rows(xa, na, xb, nb, p, spearman, precision, r0, r1)
+    return res, (packed_offset(r0, p, 1), packed_offset(r1, p, 1))
+
+
+def sharded_tom_from_exp(backend, x, n, p, spearman, signed, version, beta=1.0, precision=PREC_F64, group=None):
+    """calculate_tom_from_exp, packed (shift = 1) output slice of this rank.
+
+    phase 1  affinity columns of this rank's gene slab (full-width strip)
+    phase 2  connectivity of the slab (and |A| in place when unsigned)
+    exchange slabs -> full A on every rank; all-reduce(sum) of k
+    phase 3  TOM block rows of the pair-balanced range, upper tiles only
+    """
+    rank, world = _world(group)
+    ver = TOM_V1 if version in ("v1", TOM_V1) else TOM_V2
+    a_full = backend.empty(p, p)  # row i of this tensor == column i of the column-major matrix
+    k = backend.zeros(p)
+    c0, c1 = even_slab(p, world, rank)
+    cor_prec = precision if precision != _lib.PREC_I8EXACT else PREC_F64
+    backend.affinity_cols(x, n, p, spearman, signed, beta, cor_prec, c0, c1, a_full)
+    backend.tom_connectivity(a_full, p, signed, c0, c1, k)
+    if world > 1:
+        for r in range(world):
+            s0, s1 = even_slab(p, world, r)
+            if s1 > s0:
+                dist.broadcast(a_full[s0:s1], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        dist.all_reduce(k, op=dist.ReduceOp.SUM, group=group)
+    r0, r1 = pair_balanced_rows(p, 1, world, rank)
+    out = backend.tom_rows(a_full, k, p, signed, ver, precision, r0, r1)
+    return out, (packed_offset(r0, p, 1), packed_offset(r1, p, 1))
+
+
+def sharded_sparse_gram_cor(backend, indptr, indices, data, local_cells, genes, precision=PREC_F64, group=None):
+    """Cell-sharded all-pairs Pearson: partial Gram + column sums, all-reduced, finalised on every rank."""
+    rank, world = _world(group)
+    gram = backend.zeros(genes, genes)
+    colsum = backend.zeros(genes)
+    backend.sparse_accumulate(indptr, indices, data, local_cells, genes, precision, gram, colsum)
+    total = torch.tensor([float(local_cells)], dtype=torch.float64, device=gram.device)
+    if world > 1:
+        dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return backend.sparse_finalise(gram, colsum, int(total.item()), genes)

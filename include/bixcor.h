@@ -1,0 +1,172 @@
+/*
+ * bixcor.h - C ABI of libbixcor, the B200-native drop-in for the co-expression
+ * correlation hot path of GregorLueg/bixverse.
+ *
+ * The library replaces the four calls that bixverse's extendr binding layer makes
+ * into the CPU crate `bixverse-rs` 0.4.4 on this path; everything above the
+ * `#[extendr] fn` bodies (R wrappers, result classes) is unchanged.  Reference
+ * interfaces replaced (paths relative to the bixverse repository root):
+ *
+ *   column_pairwise_cor(&MatRef<f64>, bool) -> Mat<f64>
+ *       src/rust/src/base/r_cors_similarity.rs:70-77      -> bixcor_cor_dense
+ *   column_pairwise_cor + upper_triangle_indices + scalar gather
+ *       src/rust/src/base/r_cors_similarity.rs:251-268    -> bixcor_cor_upper
+ *   calculate_diff_correlation::<f64>(&cor_a,&cor_b,n_a,n_b,spearman)
+ *       src/rust/src/methods/r_diffcor.rs:45-74           -> bixcor_diffcor
+ *   calc_tom(MatRef<f64>, signed, TomType) (+ parse_tom_types)
+ *       src/rust/src/methods/r_coremo.rs:46-59            -> bixcor_tom
+ *   rs_cor -> abs -> rs_tom chain of calculate_tom_from_exp
+ *       R/functions_stats.R:103-121                       -> bixcor_tom_from_exp
+ *   rank_matrix_col (average ties)
+ *       src/rust/src/enrichment/r_singscore.rs:89-95      -> bixcor_rank_columns
+ *   packed triangle index order
+ *       src/rust/src/base/r_helpers.rs:75-134             -> bixcor_packed_offset,
+ *                                                            bixcor_upper_to_dense,
+ *                                                            bixcor_dense_to_upper
+ *   rs_pairwise_gene_cors_mc semantic anchor (pair list over sparse columns)
+ *       src/rust/src/meta_cell/r_mc_processing.rs:258-283 -> bixcor_sparse_gram_cor
+ *
+ * Conventions
+ *   - All matrices are column-major `double` exactly as R stores them: an n x p
+ *     expression matrix has the n samples of gene j contiguous at x + j*n.
+ *   - Pointers are HOST pointers unless the function name contains `_dev_`; host
+ *     buffers may be pageable or pinned (pinned buffers are DMA'd directly).
+ *   - Outputs are caller-allocated; the library never keeps a caller pointer
+ *     past return and never frees caller memory.
+ *   - Every function returns BIXCOR_OK (0) or a negative error code; the message
+ *     is available from bixcor_last_error().  No C++ exception crosses the ABI.
+ *   - There is NO CPU fallback: without a usable sm_100 GPU every compute entry
+ *     point fails with BIXCOR_ERR_NO_GPU.
+ *   - Calls are blocking and not re-entrant (R calls on one thread).
+ *   - Packed upper-triangle order (0-based, i < j, shift = 1):
+ *       idx(i,j) = i*(2p - i - 1)/2 + (j - i - 1);  shift = 0 keeps the diagonal:
+ *       idx(i,j) = i*(2p - i + 1)/2 + (j - i).
+ */
+#ifndef BIXCOR_H
+#define BIXCOR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIXCOR_OK 0
+#define BIXCOR_ERR_NO_GPU (-1)
+#define BIXCOR_ERR_INVALID (-2)
+#define BIXCOR_ERR_CUDA (-3)
+#define BIXCOR_ERR_OOM (-4)
+#define BIXCOR_ERR_UNSUPPORTED (-5)
+
+/* `precision` argument */
+#define BIXCOR_PREC_F64 0    /* FP64 tensor-core (DMMA) Gram: exact path, <=1e-10 */
+#define BIXCOR_PREC_TF32X3 1 /* tcgen05 3xTF32 split, FP32 accumulate in TMEM: fast path, <=1e-5 */
+#define BIXCOR_PREC_I8EXACT 2 /* Spearman only: exact integer Gram of centred ranks on tcgen05 kind::i8 */
+
+/* `version` argument of the TOM entry points ("v1"/"v2" of parse_tom_types) */
+#define BIXCOR_TOM_V1 1
+#define BIXCOR_TOM_V2 2
+
+/* ---- lifecycle --------------------------------------------------------- */
+/* Bind the calling process to `n_gpus` visible devices starting at `first_device`
+ * (bixcor_init(n) == bixcor_init_devices(0, n)).  One process per GPU (torchrun)
+ * passes first_device = LOCAL_RANK, n_gpus = 1.  Idempotent; lazily called with
+ * (0, 1) by the compute entry points. */
+int bixcor_init(int n_gpus);
+int bixcor_init_devices(int first_device, int n_gpus);
+void bixcor_shutdown(void);
+const char* bixcor_last_error(void);
+/* number of kernels launched by this library since init (bench `gpu_launches`) */
+int64_t bixcor_launch_count(void);
+/* Fisher-z variance inflation for Spearman (default 1.06, Fieller); Pearson uses 1. */
+int bixcor_set_fieller(double c);
+
+/* ---- packed triangle helpers (pure index logic, run on the host) ------- */
+int64_t bixcor_packed_len(int64_t p, int shift);
+int64_t bixcor_packed_offset(int64_t i, int64_t p, int shift);
+int bixcor_upper_to_dense(const double* packed, int shift, int64_t p, double* out_pp);
+int bixcor_dense_to_upper(const double* dense_pp, int shift, int64_t p, double* out_packed);
+/* Block-row range [row_begin,row_end) of rank `rank` of `world`: equal pair-count
+ * quantiles rounded to 128 rows, so every rank owns one contiguous packed range. */
+int bixcor_shard_rows(int64_t p, int shift, int world, int rank, int64_t* row_begin, int64_t* row_end);
+
+/* ---- host-pointer entry points (the drop-in boundary) ------------------ */
+int bixcor_rank_columns(const double* x, int64_t n, int64_t p, double* out_np);
+
+int bixcor_cor_dense(const double* x, int64_t n, int64_t p, int spearman, int precision, double* out_pp);
+
+/* beta == 1: plain r.  beta != 1: soft-threshold extension |r|^beta. */
+int bixcor_cor_upper(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                     int precision, double* out_packed);
+/* Same, restricted to rows [row_begin,row_end): out_slice receives the packed range
+ * starting at bixcor_packed_offset(row_begin,p,shift). */
+int bixcor_cor_upper_rows(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                          int precision, int64_t row_begin, int64_t row_end, double* out_slice);
+
+int bixcor_diffcor(const double* xa, int64_t na, const double* xb, int64_t nb, int64_t p, int spearman,
+                   int precision, double* r_a, double* r_b, double* z, double* pval);
+int bixcor_diffcor_rows(const double* xa, int64_t na, const double* xb, int64_t nb, int64_t p, int spearman,
+                        int precision, int64_t row_begin, int64_t row_end, double* r_a, double* r_b,
+                        double* z, double* pval);
+
+int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int precision, double* out_pp);
+
+/* packed != 0: out is the shift=1 packed vector (cor_module_tom layout), else dense p x p. */
+int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int signed_, int version,
+                        double beta, int precision, int packed, double* out);
+
+/* cells x genes CSR (int64 indptr[cells+1], int32 indices, float data) -> packed shift=1 Pearson */
+int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                           int64_t genes, int precision, double* out_packed);
+
+/* ---- device-pointer entry points (inputs/outputs resident in HBM) ------ */
+/* All pointers are device pointers on the library's current device; work is
+ * enqueued on the library's compute stream and the call returns after
+ * synchronising it.  Used by bench.py for the HBM-resident `value` and by the
+ * one-process-per-GPU multi-GPU drivers, which run collectives between phases. */
+int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_out_np);
+int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                              int precision, int64_t row_begin, int64_t row_end, double* d_out_slice);
+int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out_pp);
+int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
+                            int spearman, int precision, int64_t row_begin, int64_t row_end, double* d_r_a,
+                            double* d_r_b, double* d_z, double* d_pval);
+/* TOM in three phases so that a multi-process driver can all-gather A and
+ * all-reduce k between them:
+ *   phase 1: affinity block rows [row_begin,row_end) of the dense p x p matrix
+ *            d_a (full columns of those genes: d_a + row_begin*p) from expression;
+ *   phase 2: connectivity k_i = sum_j |a_ij| for columns [row_begin,row_end)
+ *            (unsigned: also replaces a by |a| in place);
+ *   phase 3: TOM for block rows [row_begin,row_end) from the full A and full k. */
+int bixcor_dev_affinity_cols(const double* d_x, int64_t n, int64_t p, int spearman, int signed_, double beta,
+                             int precision, int64_t row_begin, int64_t row_end, double* d_a_pp);
+int bixcor_dev_tom_connectivity(double* d_a_pp, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
+                                double* d_k);
+int bixcor_dev_tom_rows(const double* d_a_pp, const double* d_k, int64_t p, int signed_, int version,
+                        int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out);
+/* sparse: accumulate the partial Gram (dense genes x genes, upper tiles valid) and
+ * column sums of this rank's cell shard; finalise after the all-reduce. */
+int bixcor_dev_sparse_gram_accumulate(const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
+                                      int64_t cells, int64_t genes, int precision, double* d_gram_pp,
+                                      double* d_colsum);
+int bixcor_dev_sparse_gram_finalise(const double* d_gram_pp, const double* d_colsum, int64_t total_cells,
+                                    int64_t genes, double* d_out_packed);
+
+/* Run the device-pointer entry points on a caller-owned CUDA stream (e.g. torch's
+ * current stream; NULL restores the library's own stream), and optionally let them
+ * return without synchronising so that consecutive calls queue back to back. */
+int bixcor_dev_set_stream(void* cuda_stream);
+int bixcor_dev_set_async(int on);
+int bixcor_dev_synchronize(void);
+
+/* Per-kernel CUDA-event timing on the compute stream.  Enable, run any number of
+ * calls, then read the accumulated milliseconds: what[0]=rank/standardise kernels,
+ * [1]=Gram/TOM GEMM kernels, [2]=other kernels, [3]=number of GEMM launches.
+ * bixcor_timing_enable(x) also resets the accumulators. */
+int bixcor_timing_enable(int on);
+int bixcor_last_timing(double* what4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIXCOR_H */

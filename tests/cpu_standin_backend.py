@@ -1,0 +1,57 @@
+"""CPU stand-in for bixverse_b200.distributed.DeviceBackend built on the oracle.
+Lives in tests/ on purpose: it exists only to exercise the multi-rank plumbing
+(partitioning + collectives) under gloo without a GPU."""
+import numpy as np
+import torch
+
+from oracle import oracle as o
+
+
+class OracleBackend:
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float64)
+
+    @staticmethod
+    def _slice(packed, p, shift, r0, r1):
+        return packed[int(o.packed_offset(r0, p, shift)) : int(o.packed_offset(r1, p, shift))]
+
+    def cor_upper_rows(self, x, n, p, spearman, shift, beta, precision, r0, r1):
+        full = o.soft_threshold(o.cor_upper_triangle(x.numpy().T, spearman, bool(shift)), beta)
+        return torch.from_numpy(np.ascontiguousarray(self._slice(full, p, shift, r0, r1)))
+
+    def diffcor_rows(self, xa, na, xb, nb, p, spearman, precision, r0, r1):
+        res = o.differential_cor(xa.numpy().T, xb.numpy().T, spearman)
+        return {k: torch.from_numpy(np.ascontiguousarray(self._slice(v, p, 1, r0, r1))) for k, v in res.items()}
+
+    def affinity_cols(self, x, n, p, spearman, signed, beta, precision, c0, c1, a_full):
+        r = o.column_pairwise_cor(x.numpy().T, spearman)
+        a = o.soft_threshold(r, beta, signed=bool(signed)) if beta != 1.0 else r
+        np.fill_diagonal(a, 1.0)
+        a_full[c0:c1] = torch.from_numpy(a[c0:c1])
+
+    def tom_connectivity(self, a_full, p, signed, c0, c1, k):
+        if not signed:
+            a_full[c0:c1] = a_full[c0:c1].abs()
+        k[c0:c1] = a_full[c0:c1].abs().sum(dim=1)
+
+    def tom_rows(self, a_full, k, p, signed, version, precision, r0, r1):
+        a = a_full.numpy()
+        assert np.allclose(k.numpy(), np.abs(a).sum(axis=1))  # the all-reduced k is the full connectivity
+        t = o.calc_tom(a, True, "v1" if version == 1 else "v2")  # |A| already substituted when unsigned
+        return torch.from_numpy(np.ascontiguousarray(self._slice(o.dense_to_upper_triangle(t, True), p, 1, r0, r1)))
+
+    def sparse_accumulate(self, indptr, indices, data, cells, genes, precision, gram, colsum):
+        d = o._csr_to_dense(indptr.numpy(), indices.numpy(), data.numpy(), cells, genes)
+        gram += torch.from_numpy(d.T @ d)
+        colsum += torch.from_numpy(d.sum(axis=0))
+
+    def sparse_finalise(self, gram, colsum, total_cells, genes):
+        g, s = gram.numpy(), colsum.numpy()
+        cov = g - np.outer(s, s) / total_cells
+        var = np.diag(cov).copy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = cov / np.sqrt(np.outer(var, var))
+        return torch.from_numpy(o.dense_to_upper_triangle(r, True))

@@ -1,0 +1,113 @@
+"""C-ABI surface checks that need no GPU: the library loads, exports every symbol
+include/bixcor.h declares, host-only helpers work, compute fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bixcor.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bixcor_\w+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib_built):
+    from bixverse_b200 import _lib
+
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bixcor.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+
+
+def test_packed_helpers_match_oracle(lib_built):
+    from bixverse_b200 import api, _lib
+
+    lib = _lib.load()
+    for p in (1, 2, 7, 130):
+        for shift in (0, 1):
+            assert lib.bixcor_packed_len(p, shift) == o.upper_triangle_indices(p, shift)[0].shape[0]
+            for i in range(p):
+                assert lib.bixcor_packed_offset(i, p, shift) == int(o.packed_offset(i, p, shift))
+    rng = np.random.default_rng(2)
+    m = rng.normal(size=(9, 9))
+    m = m + m.T
+    for shift in (True, False):
+        v = api.rs_dense_to_upper_triangle(m, shift)
+        assert np.array_equal(v, o.dense_to_upper_triangle(m, shift))
+        d = api.rs_upper_triangle_to_dense(v, shift, 9)
+        assert np.array_equal(d, o.upper_triangle_to_dense(v, shift, 9))
+    with pytest.raises(ValueError):
+        api.rs_upper_triangle_to_dense(np.zeros(5), True, 9)
+
+
+def test_reference_sparse_vector(lib_built, golden_dir):
+    import json
+
+    from bixverse_b200 import api
+
+    kat = json.load(open(os.path.join(golden_dir, "reference_kat.json")))
+    d = api.rs_upper_triangle_to_dense(kat["sparse_input_packed"], True, 4)
+    assert np.array_equal(d, np.array(kat["sparse_dense_expected"]))
+
+
+def test_shard_rows_matches_oracle(lib_built):
+    from bixverse_b200 import api
+
+    for p in (100, 2000, 20000, 20011):
+        for shift in (False, True):
+            for world in (1, 2, 4, 8):
+                for r in range(world):
+                    assert api.shard_rows(p, shift, world, r) == o.shard_rows(p, int(shift), world, r)
+
+
+def test_no_cpu_fallback(lib_built):
+    """Without a GPU every compute entry point must fail with BIXCOR_ERR_NO_GPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bixverse_b200 import api
+
+    x = np.random.default_rng(0).normal(size=(8, 5))
+    for call in (lambda: api.rs_cor(x, False), lambda: api.rs_cor_upper_triangle(x, True),
+                 lambda: api.rs_tom(np.eye(4), "v1", True), lambda: api.rs_rank_matrix_col(x)):
+        with pytest.raises(api.BixcorError) as ei:
+            call()
+        assert ei.value.code == -1 and "no CPU fallback" in ei.value.message
+
+
+def test_host_side_argument_errors(lib_built):
+    from bixverse_b200 import api
+
+    with pytest.raises(ValueError, match="same number of columns"):
+        api.rs_differential_cor(np.zeros((5, 3)), np.zeros((5, 4)), False)
+    with pytest.raises(ValueError, match="Invalid TOM version type: v3"):
+        api.rs_tom(np.eye(3), "v3", True)
+    with pytest.raises(ValueError):
+        api.UpperTriangularSymMat(np.zeros(4), ["a", "b", "c"], shift=True)
+    m = api.UpperTriangularSymMat(np.array([0.1, 0.2, 0.3]), ["a", "b", "c"], shift=True)
+    assert m.get_sym_matrix()[0, 2] == 0.2 and m.get_sym_matrix()[1, 1] == 1.0
+    with pytest.raises(ValueError, match="missing"):
+        api.UpperTriangleDiffcorMat({"r_a": [0.0]}, ["a", "b"])
+    d = api.UpperTriangleDiffcorMat({"r_a": [0.1], "r_b": [0.2], "z_score": [1.0], "p_val": [0.0]}, ["a", "b"])
+    assert d.get_data_table()["r_a"].shape[0] == 0  # p_val == 0 rows dropped
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bixverse_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt, f

@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run with -m gpu on a B200.
+
+Bars: ranks and packed indexing bit-exact; correlations / TOM / z within 1e-10 on the FP64 path
+(BIXCOR_PREC_F64) and within 1e-5 on the TF32x3 path; the int8 Spearman path is held to 1e-12.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-10
+TOL32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def api(lib_built):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a GPU"
+    from bixverse_b200 import api as _api
+
+    _api.init(1, 0)
+    return _api
+
+
+def _maxerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    m = ~np.isnan(a)
+    return float(np.abs(a[m] - b[m]).max()) if m.any() else 0.0
+
+
+# ----------------------------------------------------------------------------- golden vectors
+def test_r_equality_golden(api, golden_dir):
+    """inst/tinytest/test_R_rust_equality.R:5-72 on the reference's own set.seed(123) matrix."""
+    g = json.load(open(os.path.join(golden_dir, "r_equality_seed123.json")))
+    mat = np.array(g["mat"])
+    assert _maxerr(api.rs_cor(mat, False), np.array(g["pearson"])) < 1e-14 * 100
+    assert _maxerr(api.rs_cor(mat, True), np.array(g["spearman"])) < 1e-14 * 100
+    assert np.array_equal(api.rs_rank_matrix_col(mat), np.array(g["ranks"]))
+    packed = api.rs_cor_upper_triangle(mat, False, True)
+    cls = api.UpperTriangularSymMat(packed, [f"feature_{i}" for i in range(14)], True)
+    assert _maxerr(cls.get_sym_matrix(), np.array(g["pearson"])) < 1e-12
+
+
+@pytest.mark.parametrize("signed,version", [(True, "v1"), (True, "v2"), (False, "v1"), (False, "v2")])
+def test_tom_known_answer(api, golden_dir, signed, version):
+    """inst/tinytest/test_cor_modules.R:9-110."""
+    kat = json.load(open(os.path.join(golden_dir, "reference_kat.json")))
+    cor = api.rs_upper_triangle_to_dense(kat["tom_input_packed"], True, 4)
+    tom = api.calculate_tom(cor, signed, version)
+    got = api.rs_dense_to_upper_triangle(tom, True)
+    exp = np.array(kat[f"tom_{'signed' if signed else 'unsigned'}_{version}"])
+    assert np.abs(got - exp).max() < kat["tom_tolerance"]
+    assert _maxerr(tom, o.calc_tom(cor, signed, version)) < 1e-13
+
+
+# ----------------------------------------------------------------------------- ranks (bit-exact)
+@pytest.mark.parametrize("n,p", [(2, 3), (31, 5), (32, 4), (33, 7), (200, 64), (1000, 50), (1025, 9), (4097, 3)])
+def test_ranks_bit_exact(api, n, p):
+    rng = np.random.default_rng(n * 131 + p)
+    x = rng.normal(size=(n, p))
+    assert np.array_equal(api.rs_rank_matrix_col(x), o.rank_matrix_col(x))
+    xt = np.round(x, 1)  # tie heavy
+    xt[0, 0], xt[n - 1, 0] = 0.0, -0.0
+    assert np.array_equal(api.rs_rank_matrix_col(xt), o.rank_matrix_col(xt))
+    xc = xt.copy()
+    xc[:, p - 1] = 2.5  # one all-ties column
+    if p > 1:
+        xc[n // 2, 0] = np.nan  # one NaN column
+    assert np.array_equal(api.rs_rank_matrix_col(xc), o.rank_matrix_col(xc), equal_nan=True)
+    xi = x.copy()
+    xi[0, 0], xi[1, 0] = np.inf, -np.inf
+    assert np.array_equal(api.rs_rank_matrix_col(xi), o.rank_matrix_col(xi))
+
+
+# ----------------------------------------------------------------------------- correlations
+@pytest.mark.parametrize("n,p", [(12, 14), (200, 2000), (57, 129), (16, 128), (17, 300), (1000, 257)])
+@pytest.mark.parametrize("spearman", [False, True])
+def test_cor_upper_and_dense(api, n, p, spearman):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(n, p, seed=n + p) if n >= 50 else np.random.default_rng(n + p).normal(size=(n, p))
+    dense_ref = o.column_pairwise_cor(x, spearman)
+    for shift in (True, False):
+        got = api.rs_cor_upper_triangle(x, spearman, shift)
+        assert _maxerr(got, o.dense_to_upper_triangle(dense_ref, shift)) < TOL64
+    dense = api.rs_cor(x, spearman)
+    ref = dense_ref.copy()
+    np.fill_diagonal(ref, 1.0)
+    assert _maxerr(dense, ref) < TOL64
+    assert np.array_equal(dense, dense.T, equal_nan=True)
+
+
+def test_config1_pearson_packed(api):
+    """BASELINE config 1: Pearson 2000 genes x 200 samples, packed shift=1 (P = 1 999 000)."""
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(200, 2000, seed=123)
+    got = api.rs_cor_upper_triangle(x, False, True)
+    assert got.shape[0] == 1_999_000
+    assert _maxerr(got, o.cor_upper_triangle(x, False, True)) < TOL64
+
+
+def test_soft_threshold_beta(api):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(100, 300, seed=9, tie_heavy=True)
+    r = o.cor_upper_triangle(x, True, True)
+    base = api.rs_cor_upper_triangle(x, True, True, beta=1.0)
+    assert _maxerr(base, r) < TOL64
+    assert np.array_equal(api.rs_cor_upper_triangle(x, True, True), base)  # beta == 1 is a bit-identical no-op
+    assert _maxerr(api.rs_cor_upper_triangle(x, True, True, beta=6.0), o.soft_threshold(r, 6.0)) < TOL64
+
+
+def test_zero_variance_and_nan_columns(api):
+    x = np.random.default_rng(4).normal(size=(40, 140))
+    x[:, 3] = 1.0
+    x[7, 130] = np.nan
+    for spearman in (False, True):
+        got = api.rs_cor_upper_triangle(x, spearman, True)
+        ref = o.cor_upper_triangle(x, spearman, True)
+        assert _maxerr(got, ref) < TOL64
+        assert np.isnan(got).sum() == np.isnan(ref).sum() > 0
+
+
+def test_row_sharded_calls_tile_the_packed_vector(api):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    n, p = 64, 700
+    x = synthetic_bulk(n, p, seed=77)
+    full = api.rs_cor_upper_triangle(x, True, True, beta=2.0)
+    for world in (2, 3):
+        parts = [api.rs_cor_upper_triangle(x, True, True, beta=2.0, rows=api.shard_rows(p, True, world, r)) for r in range(world)]
+        assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_pageable_and_pinned_hosts_agree(api):
+    import torch
+
+    n, p = 100, 900
+    x = np.random.default_rng(1).normal(size=(n, p))
+    a = api.rs_cor_upper_triangle(x, False, True)
+    xp = torch.from_numpy(np.ascontiguousarray(x.T)).pin_memory()  # p x n row-major == n x p column-major
+    from bixverse_b200 import _lib
+
+    lib = _lib.load()
+    out = torch.empty(p * (p - 1) // 2, dtype=torch.float64).pin_memory()
+    _lib.check(lib.bixcor_cor_upper(xp.data_ptr(), n, p, 0, 1, 1.0, 0, out.data_ptr()))
+    assert np.array_equal(out.numpy(), a)
+
+
+# ----------------------------------------------------------------------------- differential correlation
+@pytest.mark.parametrize("spearman", [False, True])
+def test_diffcor(api, spearman):
+    from bixverse_b200.synthetic import synthetic_pair
+
+    xa, xb = synthetic_pair(60, 75, 333, seed=2025)
+    got = api.rs_differential_cor(xa, xb, spearman)
+    ref = o.differential_cor(xa, xb, spearman)
+    assert _maxerr(got["r_a"], ref["r_a"]) < TOL64 and _maxerr(got["r_b"], ref["r_b"]) < TOL64
+    assert _maxerr(got["z_score"], ref["z_score"]) < 1e-9
+    assert np.allclose(got["p_val"], ref["p_val"], rtol=1e-8, atol=1e-300, equal_nan=True)
+    m = api.UpperTriangleDiffcorMat(got, [f"g{i}" for i in range(333)])
+    assert m.get_cor_matrix("r_a").shape == (333, 333)
+
+
+# ----------------------------------------------------------------------------- TOM
+@pytest.mark.parametrize("p", [5, 130, 400])
+@pytest.mark.parametrize("signed", [True, False])
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_tom_random(api, p, signed, version):
+    x = np.random.default_rng(p).normal(size=(30, p))
+    cor = o.column_pairwise_cor(x, False)
+    np.fill_diagonal(cor, 1.0)
+    got = api.calculate_tom(cor, signed, version)
+    ref = o.calc_tom(np.abs(cor) if not signed else cor, signed, version)
+    assert _maxerr(got, ref) < TOL64
+    assert np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("cor_method", ["pearson", "spearman"])
+def test_tom_from_exp(api, cor_method):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(80, 390, seed=2026)
+    sp = cor_method == "spearman"
+    for signed in (True, False):
+        ref = o.tom_from_exp(x, signed, "v1", sp, 1.0)
+        assert _maxerr(api.calculate_tom_from_exp(x, signed, "v1", cor_method), ref) < TOL64
+        refb = o.tom_from_exp(x, signed, "v2", sp, 6.0)
+        gotb = api.calculate_tom_from_exp(x, signed, "v2", cor_method, beta=6.0, packed=True)
+        assert _maxerr(gotb, o.dense_to_upper_triangle(refb, True)) < TOL64
+
+
+def test_tom_invalid_version_is_error(api):
+    with pytest.raises(ValueError, match="Invalid TOM version type"):
+        api.rs_tom(np.eye(4), "v9", True)
+    from bixverse_b200 import _lib
+
+    a = np.eye(4, order="F")
+    out = np.empty((4, 4), order="F")
+    rc = _lib.load().bixcor_tom(a.ctypes.data, 4, 1, 7, 0, out.ctypes.data)
+    assert rc == _lib.ERR_INVALID and b"Invalid TOM version type" in _lib.load().bixcor_last_error()
+
+
+# ----------------------------------------------------------------------------- sparse single-cell
+def test_sparse_gram_cor(api):
+    from bixverse_b200.synthetic import synthetic_sparse_cells
+
+    cells, genes = 9000, 300  # > one 8192-cell panel: exercises accumulation
+    ip, ix, d = synthetic_sparse_cells(cells, genes, 2027, density=0.05)
+    got = api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes)
+    ref = o.sparse_gram_cor(ip, ix, d, cells, genes)
+    assert _maxerr(got, ref) < 1e-9
+    i, j = o.upper_triangle_indices(genes, 1)
+    sel = np.arange(0, i.shape[0], 997)
+    pl = o.pairwise_gene_cors(ip, ix, d, cells, genes, i[sel], j[sel])  # rs_pairwise_gene_cors_mc semantics
+    ok = ~np.isnan(pl)
+    assert np.abs(pl[ok] - got[sel][ok]).max() < 1e-9
+
+
+# ----------------------------------------------------------------------------- fast / exact tensor paths
+def _precisions():
+    from bixverse_b200 import _lib
+
+    return _lib.PREC_TF32X3, _lib.PREC_I8EXACT
+
+
+@pytest.mark.parametrize("n,p", [(200, 2000), (1000, 257), (57, 129)])
+def test_spearman_int8_exact_path(api, n, p):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    _, i8 = _precisions()
+    x = synthetic_bulk(n, p, seed=3 * n + p, tie_heavy=True)
+    got = api.rs_cor_upper_triangle(x, True, True, precision=i8)
+    assert _maxerr(got, o.cor_upper_triangle(x, True, True)) < 1e-12
+    got6 = api.rs_cor_upper_triangle(x, True, False, beta=6.0, precision=i8)
+    assert _maxerr(got6, o.soft_threshold(o.cor_upper_triangle(x, True, False), 6.0)) < 1e-12
+
+
+@pytest.mark.parametrize("n,p", [(200, 2000), (1000, 257), (57, 129)])
+@pytest.mark.parametrize("spearman", [False, True])
+def test_tf32x3_fast_path(api, n, p, spearman):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    tf32, _ = _precisions()
+    x = synthetic_bulk(n, p, seed=5 * n + p)
+    got = api.rs_cor_upper_triangle(x, spearman, True, precision=tf32)
+    assert _maxerr(got, o.cor_upper_triangle(x, spearman, True)) < TOL32
+    dense = api.rs_cor(x, spearman, precision=tf32)
+    ref = o.column_pairwise_cor(x, spearman)
+    np.fill_diagonal(ref, 1.0)
+    assert _maxerr(dense, ref) < TOL32
+
+
+def test_tom_tf32x3_fast_path(api):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    tf32, _ = _precisions()
+    x = synthetic_bulk(100, 520, seed=8)
+    for signed in (True, False):
+        got = api.calculate_tom_from_exp(x, signed, "v1", "pearson", beta=2.0, precision=tf32)
+        assert _maxerr(got, o.tom_from_exp(x, signed, "v1", False, 2.0)) < TOL32
+
+
+def test_diffcor_fast_paths(api):
+    from bixverse_b200.synthetic import synthetic_pair
+
+    tf32, i8 = _precisions()
+    xa, xb = synthetic_pair(60, 75, 333, seed=2025)
+    ref = o.differential_cor(xa, xb, True)
+    got = api.rs_differential_cor(xa, xb, True, precision=i8)
+    assert _maxerr(got["r_a"], ref["r_a"]) < 1e-12 and _maxerr(got["z_score"], ref["z_score"]) < 1e-9
+    got = api.rs_differential_cor(xa, xb, False, precision=tf32)
+    refp = o.differential_cor(xa, xb, False)
+    assert _maxerr(got["r_b"], refp["r_b"]) < TOL32 and _maxerr(got["z_score"], refp["z_score"]) < 1e-3
+
+
+# ----------------------------------------------------------------------------- full-size properties (BASELINE sizes)
+def test_config2_full_size_properties(api):
+    """Spearman 20k x 1k + |r|^6 at full size: sampled rows against the oracle, plus
+    size-independent properties (range, symmetry of a mirrored sub-block, sharded == unsharded)."""
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    n, p = 1000, 20000
+    x = synthetic_bulk(n, p, seed=2024, tie_heavy=True)
+    got = api.rs_cor_upper_triangle(x, True, True, beta=6.0)
+    assert got.shape[0] == 199_990_000
+    assert np.nanmin(got) >= 0.0 and np.nanmax(got) <= 1.0 + 1e-12
+    # oracle on sampled rows: correlation of gene i against all j > i
+    ranks = o.rank_matrix_col(x[:, :])
+    z = ranks - ranks.mean(axis=0)
+    z /= np.sqrt((z * z).sum(axis=0))
+    for i in (0, 1, 127, 128, 5000, 12345, 19871, 19998):
+        ref = np.abs(z[:, i] @ z[:, i + 1 :]) ** 6.0
+        off = int(o.packed_offset(i, p, 1))
+        assert np.abs(got[off : off + p - 1 - i] - ref).max() < TOL64, i
+    r0, r1 = api.shard_rows(p, True, 8, 5)
+    part = api.rs_cor_upper_triangle(x, True, True, beta=6.0, rows=(r0, r1))
+    assert np.array_equal(part, got[int(o.packed_offset(r0, p, 1)) : int(o.packed_offset(r1, p, 1))])

@@ -1,0 +1,174 @@
+"""Pins the CPU oracle against the reference's golden vectors (CPU only)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import rankdata, spearmanr
+
+from oracle import oracle as o
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "reference_kat.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def req(golden_dir):
+    with open(os.path.join(golden_dir, "r_equality_seed123.json")) as f:
+        return {k: (np.array(v) if isinstance(v, list) else v) for k, v in json.load(f).items()}
+
+
+# inst/tinytest/test_cor_modules.R:9-110 (tolerance 1e-5)
+@pytest.mark.parametrize("signed,version", [(True, "v1"), (True, "v2"), (False, "v1"), (False, "v2")])
+def test_tom_known_answer(kat, signed, version):
+    cor = o.upper_triangle_to_dense(kat["tom_input_packed"], True, kat["tom_n"])
+    a = cor if signed else np.abs(cor)  # calculate_tom takes abs() first when unsigned
+    got = o.dense_to_upper_triangle(o.calc_tom(a, signed, version), True)
+    exp = np.array(kat[f"tom_{'signed' if signed else 'unsigned'}_{version}"])
+    assert np.abs(got - exp).max() < kat["tom_tolerance"]
+
+
+def test_tom_invalid_version():
+    with pytest.raises(ValueError, match="Invalid TOM version type"):
+        o.calc_tom(np.eye(3), True, "v3")
+
+
+# inst/tinytest/test_sparse.R:5-9 and r_helpers.rs:75-134
+def test_triangle_dense_roundtrip(kat):
+    v = np.array(kat["sparse_input_packed"], dtype=float)
+    d = o.upper_triangle_to_dense(v, True, kat["sparse_n"])
+    assert np.array_equal(d, np.array(kat["sparse_dense_expected"]))
+    assert np.array_equal(o.dense_to_upper_triangle(d, True), v)
+    # shift = 0 keeps the diagonal
+    v0 = o.dense_to_upper_triangle(d, False)
+    assert v0.shape[0] == 10 and np.array_equal(o.upper_triangle_to_dense(v0, False, 4), d)
+
+
+def test_packed_offsets_match_loop_order():
+    for p in (1, 2, 5, 17):
+        for shift in (0, 1):
+            r, c = o.upper_triangle_indices(p, shift)
+            idx = 0
+            for i in range(p):
+                assert o.packed_offset(i, p, shift) == idx
+                for j in range(i + shift, p):
+                    assert (r[idx], c[idx]) == (i, j)
+                    idx += 1
+            assert idx == r.shape[0]
+
+
+# inst/tinytest/test_R_rust_equality.R:5-72 on the reference's own set.seed(123) matrix
+def test_pearson_spearman_cov_equal_base_r_standin(req):
+    mat = req["mat"]
+    assert mat.shape == (12, 14)
+    assert np.abs(o.column_pairwise_cor(mat, False) - req["pearson"]).max() < 1e-14
+    assert np.abs(o.column_pairwise_cor(mat, True) - req["spearman"]).max() < 1e-14
+    assert np.abs(o.column_pairwise_cov(mat) - req["cov"]).max() < 1e-14
+    assert np.array_equal(o.rank_matrix_col(mat), req["ranks"])
+    # independent implementation
+    assert np.abs(o.column_pairwise_cor(mat, True) - spearmanr(mat).statistic).max() < 1e-14
+    # upper-triangle class round trip (test_R_rust_equality.R:60-72)
+    packed = o.cor_upper_triangle(mat, False, True)
+    assert np.abs(o.upper_triangle_to_dense(packed, True, 14) - req["pearson"]).max() < 1e-14
+
+
+def test_rank_average_ties_signed_zero_nan():
+    rng = np.random.default_rng(7)
+    x = np.round(rng.normal(size=(257, 11)), 1)
+    x[3, 0], x[9, 0] = 0.0, -0.0
+    assert np.array_equal(o.rank_matrix_col(x), np.apply_along_axis(rankdata, 0, x))
+    x[5, 2] = np.nan
+    r = o.rank_matrix_col(x)
+    assert np.isnan(r[:, 2]).all() and not np.isnan(r[:, 1]).any()
+    assert np.array_equal(o.rank_average(np.array([2.0, 2.0, 2.0])), np.array([2.0, 2.0, 2.0]))
+
+
+def test_zero_variance_column_is_nan():
+    x = np.random.default_rng(0).normal(size=(10, 4))
+    x[:, 1] = 3.0
+    r = o.column_pairwise_cor(x, False)
+    assert np.isnan(r[1]).all() and np.isnan(r[:, 1]).all() and not np.isnan(r[0, 2])
+
+
+def test_soft_threshold_identity_and_power():
+    r = np.array([-0.5, 0.25, 1.0])
+    assert np.array_equal(o.soft_threshold(r, 1.0), r)
+    assert np.allclose(o.soft_threshold(r, 6.0), np.abs(r) ** 6)
+    assert np.allclose(o.soft_threshold(r, 3.0, signed=True), np.sign(r) * np.abs(r) ** 3)
+
+
+def test_diffcor_definition():
+    rng = np.random.default_rng(3)
+    xa, xb = rng.normal(size=(30, 6)), rng.normal(size=(40, 6))
+    res = o.differential_cor(xa, xb, spearman=False)
+    ra = o.cor_upper_triangle(xa, False, True)
+    rb = o.cor_upper_triangle(xb, False, True)
+    z = (np.arctanh(ra) - np.arctanh(rb)) / np.sqrt(1 / 27 + 1 / 37)
+    assert np.allclose(res["z_score"], z, rtol=1e-14)
+    from scipy.stats import norm
+
+    assert np.allclose(res["p_val"], 2 * norm.sf(np.abs(z)), rtol=1e-12)
+    sp = o.differential_cor(xa, xb, spearman=True)
+    assert np.allclose(sp["z_score"] * np.sqrt(1.06), (np.arctanh(sp["r_a"]) - np.arctanh(sp["r_b"])) / np.sqrt(1 / 27 + 1 / 37))
+    with pytest.raises(ValueError, match="same number of columns"):
+        o.differential_cor(xa, xb[:, :5], False)
+
+
+def test_tom_from_exp_matches_chain():
+    x = np.random.default_rng(5).normal(size=(25, 9))
+    cor = o.column_pairwise_cor(x, False)
+    assert np.allclose(o.tom_from_exp(x, True, "v1"), o.calc_tom(cor, True, "v1"))
+    assert np.allclose(o.tom_from_exp(x, False, "v2"), o.calc_tom(np.abs(cor), False, "v2"))
+
+
+def test_sparse_gram_matches_dense_and_pairs():
+    from bixverse_b200.synthetic import synthetic_sparse_cells
+
+    cells, genes = 700, 40
+    ip, ix, d = synthetic_sparse_cells(cells, genes, 11, density=0.2)
+    packed = o.sparse_gram_cor(ip, ix, d, cells, genes, chunk=256)
+    dense = o._csr_to_dense(ip, ix, d, cells, genes)
+    ref = o.cor_upper_triangle(dense, False, True)
+    ok = ~np.isnan(ref)
+    assert np.abs(packed[ok] - ref[ok]).max() < 1e-12
+    i, j = o.upper_triangle_indices(genes, 1)
+    sel = np.arange(0, i.shape[0], 37)
+    pl = o.pairwise_gene_cors(ip, ix, d, cells, genes, i[sel], j[sel])
+    okp = ~np.isnan(pl)
+    assert np.abs(pl[okp] - packed[sel][okp]).max() < 1e-12
+
+
+def test_c_restatement_agrees_with_numpy_oracle(lib_built):
+    from oracle import c_binding as cb
+
+    rng = np.random.default_rng(21)
+    x = np.round(rng.normal(size=(33, 12)), 1)
+    assert np.array_equal(cb.rank_matrix_col(x), o.rank_matrix_col(x))
+    for sp in (False, True):
+        assert np.abs(cb.cor_dense(x, sp) - o.column_pairwise_cor(x, sp)).max() < 1e-14
+        for shift in (False, True):
+            assert np.abs(cb.cor_upper(x, sp, shift) - o.cor_upper_triangle(x, sp, shift)).max() < 1e-14
+    a = o.column_pairwise_cor(x, False)
+    for signed in (True, False):
+        for ver in (1, 2):
+            assert np.abs(cb.tom(a, signed, ver) - o.calc_tom(a, signed, f"v{ver}")).max() < 1e-13
+    ra, rb = o.cor_upper_triangle(x[:20], False), o.cor_upper_triangle(x[13:], False)
+    z, pv = cb.diffcor(ra, rb, 20, 20, 1.0)
+    ref = o.calculate_diff_correlation(ra, rb, 20, 20, False)
+    assert np.allclose(z, ref["z_score"], rtol=1e-13) and np.allclose(pv, ref["p_val"], rtol=1e-12)
+
+
+def test_shard_rows_partition_properties():
+    for p in (100, 2000, 20000, 20011):
+        for shift in (0, 1):
+            for world in (1, 2, 3, 4, 8):
+                bounds = [o.shard_rows(p, shift, world, r) for r in range(world)]
+                assert bounds[0][0] == 0 and bounds[-1][1] == p
+                for a, b in zip(bounds[:-1], bounds[1:]):
+                    assert a[1] == b[0] and a[0] % 128 == 0
+                if p >= 20000:
+                    pairs = [o.packed_offset(b, p, shift) - o.packed_offset(a, p, shift) for a, b in bounds]
+                    assert max(pairs) / (sum(pairs) / world) < 1.06  # balanced by pair count
