@@ -189,8 +189,9 @@ def run_ours(args):
     # ---- HBM-resident arm: inputs already on the device, library runs on torch's current stream
     x_dev = torch.from_numpy(np.ascontiguousarray(x_host.T)).to(dev)  # p x n row-major == n x p column-major
     out_dev = torch.empty(max(my_pairs, 1), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev)
-    _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream))
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream, 1))
     _lib.check(lib.bixcor_dev_set_async(1))
 
     def step_dev():
@@ -266,7 +267,7 @@ def run_ours(args):
 
     # ---- end-to-end arm: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region
     _lib.check(lib.bixcor_dev_set_async(0))
-    _lib.check(lib.bixcor_dev_set_stream(None))
+    _lib.check(lib.bixcor_dev_set_stream(None, 0))
     del out_dev
     x_pin = torch.from_numpy(np.ascontiguousarray(x_host.T)).pin_memory()
     out_pin = torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()

@@ -50,7 +50,7 @@ SIGNATURES = {
     "bixcor_dev_tom_rows": (i32, [ptr, ptr, i64, i32, i32, i32, i32, i64, i64, ptr]),
     "bixcor_dev_sparse_gram_accumulate": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr, ptr]),
     "bixcor_dev_sparse_gram_finalise": (i32, [ptr, ptr, i64, i64, ptr]),
-    "bixcor_dev_set_stream": (i32, [ptr]),
+    "bixcor_dev_set_stream": (i32, [ptr, i32]),
     "bixcor_dev_set_async": (i32, [i32]),
     "bixcor_dev_synchronize": (i32, []),
     "bixcor_timing_enable": (i32, [i32]),

@@ -284,7 +284,7 @@ struct Operand {
   int K = 0;  // padded contraction length
   int64_t p = 0;
   const double* z64 = nullptr;  // F64: p x K
-  const int8_t* i8 = nullptr;   // I8EXACT: 3 planes p x K
+  const int8_t* i8 = nullptr;   // I8EXACT: 2 planes (h, l) p x K
   const float* f32 = nullptr;   // TF32X3: 2 planes p x K
   const double* inv_norm = nullptr;
 };
@@ -326,7 +326,7 @@ static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int 
     co.ld64 = K;
     op->z64 = co.f64;
   } else if (precision == BIXCOR_PREC_I8EXACT) {
-    RC_TRY(c->op[slot].reserve((size_t)3 * K * p));
+    RC_TRY(c->op[slot].reserve((size_t)2 * K * p));
     RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
     co.mode = COL_I8;
     co.i8 = (int8_t*)c->op[slot].ptr;
@@ -385,27 +385,24 @@ static int launch_dmma(Ctx* c, const dmma::Params& P, int ntiles) {
   return BIXCOR_OK;
 }
 
-struct EpiArgs {
-  int epi = dmma::EPI_PACKED;
-  double* out = nullptr;
-  int64_t out_base = 0;
-  int64_t ldo = 0;
-  int shift = 1;
-  int mirror = 0;
-  int diag_one = 0;
-  double beta = 1.0;
-  int keep_sign = 0;
-  double *r_a = nullptr, *r_b = nullptr, *z = nullptr, *pv = nullptr;
-  double inv_se = 0.0;
-  const double* A = nullptr;
-  const double* kvec = nullptr;
-  const double* dvec = nullptr;
-  int tom_v2 = 0;
-  int tom_packed = 0;
-};
+static EpiParams make_epi(int64_t p) {
+  EpiParams e;
+  memset(&e, 0, sizeof e);
+  e.p = p;
+  e.shift = 1;
+  e.beta = 1.0;
+  return e;
+}
 
-static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, const int2* tiles, int ntiles,
-                       const EpiArgs& e) {
+static void set_beta(EpiParams& e, double beta, int keep_sign) {
+  e.beta = beta;
+  e.keep_sign = keep_sign;
+  e.beta_int = 0;
+  if (beta > 1.0 && beta <= 64.0 && beta == std::floor(beta)) e.beta_int = (int)beta;
+}
+
+static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, const int2* tiles, int ntiles, int epi,
+                       const EpiParams& e) {
   if (ntiles <= 0) return BIXCOR_OK;
   if (a.precision == BIXCOR_PREC_F64) {
     dmma::Params P;
@@ -420,40 +417,25 @@ static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, co
     }
     P.p = (int)p;
     P.tiles = tiles;
-    P.out = e.out;
-    P.out_base = e.out_base;
-    P.ldo = e.ldo;
-    P.shift = e.shift;
-    P.mirror = e.mirror;
-    P.diag_one = e.diag_one;
-    P.beta = e.beta;
-    P.keep_sign = e.keep_sign;
-    P.r_a = e.r_a;
-    P.r_b = e.r_b;
-    P.z = e.z;
-    P.pv = e.pv;
-    P.inv_se = e.inv_se;
-    P.A = e.A;
-    P.kvec = e.kvec;
-    P.dvec = e.dvec;
-    P.tom_v2 = e.tom_v2;
-    P.tom_packed = e.tom_packed;
-    switch (e.epi) {
-      case dmma::EPI_PACKED: return launch_dmma<dmma::EPI_PACKED>(c, P, ntiles);
-      case dmma::EPI_DENSE: return launch_dmma<dmma::EPI_DENSE>(c, P, ntiles);
-      case dmma::EPI_DIFFCOR: return launch_dmma<dmma::EPI_DIFFCOR>(c, P, ntiles);
-      case dmma::EPI_TOM: return launch_dmma<dmma::EPI_TOM>(c, P, ntiles);
-      case dmma::EPI_ACCUM: return launch_dmma<dmma::EPI_ACCUM>(c, P, ntiles);
+    P.E = e;
+    switch (epi) {
+      case EPI_PACKED: return launch_dmma<EPI_PACKED>(c, P, ntiles);
+      case EPI_DENSE: return launch_dmma<EPI_DENSE>(c, P, ntiles);
+      case EPI_DIFFCOR: return launch_dmma<EPI_DIFFCOR>(c, P, ntiles);
+      case EPI_TOM: return launch_dmma<EPI_TOM>(c, P, ntiles);
+      case EPI_ACCUM: return launch_dmma<EPI_ACCUM>(c, P, ntiles);
     }
-    return fail(BIXCOR_ERR_INVALID, "bad epilogue %d", e.epi);
+    return fail(BIXCOR_ERR_INVALID, "bad epilogue %d", epi);
   }
-  return umma::launch_gram_umma(c->compute, c->sm_count, a.precision, a.K, a.i8, a.f32, a.inv_norm,
-                                b ? b->K : 0, b ? b->i8 : nullptr, b ? b->f32 : nullptr, b ? b->inv_norm : nullptr,
-                                p, tiles, ntiles, e.epi, e.out, e.out_base, e.ldo, e.shift, e.mirror, e.diag_one,
-                                e.beta, e.keep_sign, e.r_a, e.r_b, e.z, e.pv, e.inv_se, e.A, e.kvec, e.dvec,
-                                e.tom_v2, e.tom_packed) == 0
-             ? (g_launches++, BIXCOR_OK)
-             : fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
+  const int kind = a.precision == BIXCOR_PREC_I8EXACT ? umma::KIND_I8 : umma::KIND_TF32;
+  const void* pl0 = kind == umma::KIND_I8 ? (const void*)a.i8 : (const void*)a.f32;
+  const void* pl1 = b ? (kind == umma::KIND_I8 ? (const void*)b->i8 : (const void*)b->f32) : nullptr;
+  Timed tm(c, T_GEMM);
+  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
+                             b ? b->inv_norm : nullptr, tiles, ntiles, e) != 0)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
+  g_launches++;
+  return BIXCOR_OK;
 }
 
 // ----------------------------------------------------------------------------
@@ -586,17 +568,17 @@ static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, i
   RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
-  EpiArgs e;
-  e.epi = dmma::EPI_PACKED;
+  EpiParams e = make_epi(p);
   e.out = d_out;
   e.out_base = packed_row_offset(row_begin, p, shift);
   e.shift = shift;
-  e.beta = beta;
-  e.keep_sign = 0;
+  set_beta(e, beta, 0);
+  if (!pipe)  // results stay in HBM: one launch over all tiles (no per-band tail)
+    return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_PACKED, e);
   const int ngroups = (int)tl->group_tile.size() - 1;
   for (int g = 0; g < ngroups; ++g) {
     const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
-    RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, e));
+    RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e));
     if (pipe) {
       cudaEvent_t ev = ctx_event(c);
       CU_TRY(cudaEventRecord(ev, c->compute));
@@ -621,8 +603,7 @@ static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
   const double cf = spearman ? g_fieller : 1.0;
-  EpiArgs e;
-  e.epi = dmma::EPI_DIFFCOR;
+  EpiParams e = make_epi(p);
   e.out_base = packed_row_offset(row_begin, p, 1);
   e.shift = 1;
   e.r_a = d_ra;
@@ -630,10 +611,11 @@ static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double
   e.z = d_z;
   e.pv = d_pv;
   e.inv_se = 1.0 / std::sqrt(cf / (double)(na - 3) + cf / (double)(nb - 3));
+  if (!pipe) return launch_gram(c, a, &b, p, tl->d_tiles, tl->ntiles, EPI_DIFFCOR, e);
   const int ngroups = (int)tl->group_tile.size() - 1;
   for (int g = 0; g < ngroups; ++g) {
     const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
-    RC_TRY(launch_gram(c, a, &b, p, tl->d_tiles + t0, t1 - t0, e));
+    RC_TRY(launch_gram(c, a, &b, p, tl->d_tiles + t0, t1 - t0, EPI_DIFFCOR, e));
     if (pipe) {
       cudaEvent_t ev = ctx_event(c);
       CU_TRY(cudaEventRecord(ev, c->compute));
@@ -660,15 +642,13 @@ static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spe
   const bool full = (row_begin == 0 && row_end == p);
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, full ? 1 : 0, 8, &tl));
-  EpiArgs e;
-  e.epi = dmma::EPI_DENSE;
+  EpiParams e = make_epi(p);
   e.out = d_app;
   e.ldo = p;
   e.mirror = full ? 1 : 0;
   e.diag_one = 1;
-  e.beta = beta;
-  e.keep_sign = keep_sign;
-  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, e);
+  set_beta(e, beta, keep_sign);
+  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_DENSE, e);
 }
 
 static int dev_tom_connectivity(Ctx* c, double* d_a, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
@@ -736,8 +716,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   const int upper = (packed || full) ? 1 : 0;
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, upper, 8, &tl));
-  EpiArgs e;
-  e.epi = dmma::EPI_TOM;
+  EpiParams e = make_epi(p);
   e.out = d_out;
   e.ldo = p;
   e.shift = 1;
@@ -749,7 +728,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   e.tom_v2 = (version == BIXCOR_TOM_V2);
   e.tom_packed = packed ? 1 : 0;
   // non-packed strip mode writes into out + 0 with absolute (i*p + j) addressing
-  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, e);
+  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_TOM, e);
 }
 
 static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
@@ -776,11 +755,10 @@ static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t*
     op.K = K;
     op.p = genes;
     op.z64 = (const double*)c->panel.ptr;
-    EpiArgs e;
-    e.epi = dmma::EPI_ACCUM;
+    EpiParams e = make_epi(genes);
     e.out = d_gram;
     e.ldo = genes;
-    RC_TRY(launch_gram(c, op, nullptr, genes, tl->d_tiles, tl->ntiles, e));
+    RC_TRY(launch_gram(c, op, nullptr, genes, tl->d_tiles, tl->ntiles, EPI_ACCUM, e));
   }
   CU_TRY(cudaGetLastError());
   return BIXCOR_OK;
@@ -918,13 +896,13 @@ int bixcor_dev_set_async(int on) {
   return BIXCOR_OK;
 }
 
-int bixcor_dev_set_stream(void* stream) {
+int bixcor_dev_set_stream(void* stream, int external) {
   RC_TRY(ensure_init());
   Ctx* c = g_ctx[0];
   CU_TRY(cudaSetDevice(c->device));
   CU_TRY(cudaStreamSynchronize(c->compute));
   if (c->owns_compute && c->compute) cudaStreamDestroy(c->compute);
-  if (stream) {
+  if (external) {  // a NULL handle is the legacy default stream
     c->compute = (cudaStream_t)stream;
     c->owns_compute = false;
   } else {

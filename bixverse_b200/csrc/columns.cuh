@@ -18,7 +18,7 @@ namespace bixcor {
 enum ColumnMode : int {
   COL_RANKS = 0,  // f64 average ranks (1-based), ld = n
   COL_Z64 = 1,    // f64 unit-norm centred column, zero padded to kpad
-  COL_I8 = 2,     // centred integer ranks d = 2*rank-(n+1) as base-16 digits (h, 16*l, l) + 1/|d|
+  COL_I8 = 2,     // centred integer ranks d = 2*rank-(n+1) as base-16 digits (h, l) + 1/|d|
   COL_TF32 = 3,   // unit-norm centred column split into TF32 hi / lo planes
 };
 
@@ -27,7 +27,7 @@ struct ColumnOut {
   int kpad;            // padded K (>= n); elements [n, kpad) are zero filled
   double* f64;         // COL_RANKS / COL_Z64
   int64_t ld64;
-  int8_t* i8;          // COL_I8: 3 planes, plane stride `plane8` bytes
+  int8_t* i8;          // COL_I8: 2 planes (h, l), plane stride `plane8` bytes
   int64_t ld8;
   int64_t plane8;
   float* f32;          // COL_TF32: 2 planes, plane stride `plane32` floats
@@ -130,7 +130,6 @@ rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2,
       for (int i = tid; i < out.kpad; i += nt) {
         out.i8[j * out.ld8 + i] = 0;
         out.i8[out.plane8 + j * out.ld8 + i] = 0;
-        out.i8[2 * out.plane8 + j * out.ld8 + i] = 0;
       }
       if (tid == 0) out.inv_norm[j] = qnan;
     } else {
@@ -224,8 +223,7 @@ rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2,
       const int l = ((d + 8) & 15) - 8;  // low digit in [-8, 7]
       const int h = (d - l) >> 4;        // |h| <= 127 for n <= 2025
       out.i8[j * out.ld8 + i] = (int8_t)h;
-      out.i8[out.plane8 + j * out.ld8 + i] = (int8_t)(16 * l);
-      out.i8[2 * out.plane8 + j * out.ld8 + i] = (int8_t)l;
+      out.i8[out.plane8 + j * out.ld8 + i] = (int8_t)l;
     }
     if (tid == 0) out.inv_norm[j] = 1.0 / norm;
   } else {

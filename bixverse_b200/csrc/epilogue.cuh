@@ -1,0 +1,127 @@
+// Fused Gram epilogues shared by the FP64 (DMMA) and tcgen05 (TF32x3 / int8) kernels.
+//
+// Every epilogue receives one Gram value v = G[i][j] and writes it where the
+// reference's result layout wants it:
+//   EPI_PACKED   packed upper triangle, order of src/rust/src/base/r_helpers.rs:126-131,
+//                optional soft-threshold power (north-star extension, beta == 1 is a no-op)
+//   EPI_DENSE    dense column-major p x p (rs_cor, r_cors_similarity.rs:70-77), mirrored
+//   EPI_DIFFCOR  Fisher-z differential correlation (calculate_diff_correlation,
+//                src/rust/src/methods/r_diffcor.rs:65-73): r_a, r_b, z, two-sided p
+//   EPI_TOM      topological overlap normalisation (calc_tom, r_coremo.rs:54; formulas
+//                R/functions_stats.R:15-37)
+//   EPI_ACCUM    G += v (sparse single-cell partial Gram)
+#pragma once
+
+#include "common.cuh"
+
+namespace bixcor {
+
+enum Epi : int { EPI_PACKED = 0, EPI_DENSE = 1, EPI_DIFFCOR = 2, EPI_TOM = 3, EPI_ACCUM = 4 };
+
+struct EpiParams {
+  int64_t p;
+  double* out;
+  int64_t out_base;  // packed: offset of out[0] (and of r_a..pv[0]) in the full packed vector
+  int64_t ldo;       // dense leading dimension
+  int shift;
+  int mirror;        // dense: also write the transposed element
+  int diag_one;      // dense: force 1.0 on the diagonal
+  double beta;
+  int beta_int;      // > 0: beta is this small integer (multiplication chain instead of pow)
+  int keep_sign;
+  double* r_a;
+  double* r_b;
+  double* z;
+  double* pv;
+  double inv_se;
+  const double* A;     // TOM: dense p x p affinity (symmetric), ld = p
+  const double* kvec;  // TOM: connectivity
+  const double* dvec;  // TOM: diagonal of A
+  int tom_v2;
+  int tom_packed;
+};
+
+__device__ __forceinline__ double epi_power(const EpiParams& E, double r) {
+  if (E.beta == 1.0) return r;
+  double a = fabs(r);
+  if (E.beta_int > 0) {
+    double acc = 1.0, base = a;
+    int e = E.beta_int;
+    while (e) {
+      if (e & 1) acc *= base;
+      base *= base;
+      e >>= 1;
+    }
+    a = acc;
+  } else {
+    a = pow(a, E.beta);
+  }
+  return E.keep_sign ? copysign(a, r) : a;
+}
+
+// Per-row constants hoisted out of the column loop.
+struct EpiRow {
+  int64_t i;
+  int64_t ro;  // packed: index of (i, j) is ro + j
+  double k_i, d_i;
+};
+
+template <int EPI>
+__device__ __forceinline__ EpiRow epi_row(const EpiParams& E, int64_t i) {
+  EpiRow R;
+  R.i = i;
+  const int shift = (EPI == EPI_DIFFCOR || (EPI == EPI_TOM)) ? 1 : E.shift;
+  R.ro = packed_row_offset(i, E.p, shift) - E.out_base - i - shift;
+  R.k_i = 0.0;
+  R.d_i = 0.0;
+  if (EPI == EPI_TOM) {
+    R.k_i = E.kvec[i];
+    R.d_i = E.dvec[i];
+  }
+  return R;
+}
+
+// pass: 0 for everything except the second Gram of EPI_DIFFCOR (pass 1).  In pass 0 of
+// EPI_DIFFCOR the value is r_a and is parked in its final location.
+template <int EPI>
+__device__ __forceinline__ void epi_store(const EpiParams& E, const EpiRow& R, int64_t j, double v, int pass) {
+  const int64_t i = R.i;
+  if (EPI == EPI_PACKED) {
+    if (j >= i + E.shift) E.out[R.ro + j] = epi_power(E, v);
+  } else if (EPI == EPI_DENSE) {
+    if (E.mirror && j < i) return;  // lower half of a diagonal tile: filled by the mirror write
+    double w = epi_power(E, v);
+    if (i == j && E.diag_one) w = 1.0;
+    E.out[i * E.ldo + j] = w;
+    if (E.mirror && i != j) E.out[j * E.ldo + i] = w;
+  } else if (EPI == EPI_ACCUM) {
+    E.out[i * E.ldo + j] += v;
+  } else if (EPI == EPI_DIFFCOR) {
+    if (j > i) {
+      if (pass == 0) {
+        E.r_a[R.ro + j] = v;
+      } else {
+        const double ra = E.r_a[R.ro + j];  // parked by this very thread in pass 0
+        const double zz = (atanh(ra) - atanh(v)) * E.inv_se;
+        E.r_b[R.ro + j] = v;
+        E.z[R.ro + j] = zz;
+        E.pv[R.ro + j] = erfc(fabs(zz) * 0.70710678118654752440);
+      }
+    }
+  } else if (EPI == EPI_TOM) {
+    const double a = E.A[i * E.p + j];
+    const double absa = fabs(a);
+    const double shared = v - a * (R.d_i + E.dvec[j]);
+    const double mk = fmin(R.k_i, E.kvec[j]);
+    double tom = E.tom_v2 ? 0.5 * (a + shared / (mk + absa)) : (a + shared) / (mk + 1.0 - absa);
+    if (i == j) tom = 1.0;
+    if (E.tom_packed) {
+      if (j > i) E.out[R.ro + j] = tom;
+    } else if (!(E.mirror && j < i)) {
+      E.out[i * E.ldo + j] = tom;
+      if (E.mirror && i != j) E.out[j * E.ldo + i] = tom;
+    }
+  }
+}
+
+}  // namespace bixcor

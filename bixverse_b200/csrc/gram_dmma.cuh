@@ -20,6 +20,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace bixcor {
 namespace dmma {
@@ -28,8 +29,6 @@ constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
 constexpr int OPERAND_DOUBLES = BM * BK;           // one operand tile of one stage
 constexpr int STAGE_DOUBLES = 2 * OPERAND_DOUBLES;  // A + B
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);  // 128 KB
-
-enum Epi : int { EPI_PACKED = 0, EPI_DENSE = 1, EPI_DIFFCOR = 2, EPI_TOM = 3, EPI_ACCUM = 4 };
 
 struct Params {
   // operand set 0 (rows / cols may alias), K multiple of BK, rows zero padded in K
@@ -42,29 +41,9 @@ struct Params {
   const double* C1;
   int64_t ld1;
   int K1;
-  int p;             // number of genes (rows and cols of G)
+  int p;              // number of genes (rows and cols of G)
   const int2* tiles;  // (block row, block col) list
-  // packed / dense output
-  double* out;
-  int64_t out_base;  // packed: offset of out[0] in the full packed vector
-  int64_t ldo;       // dense leading dimension
-  int shift;
-  int mirror;        // dense: also write the transposed element
-  int diag_one;      // dense: force 1.0 on the diagonal
-  double beta;
-  int keep_sign;
-  // diffcor outputs (all packed, shift = 1, based at out_base)
-  double* r_a;
-  double* r_b;
-  double* z;
-  double* pv;
-  double inv_se;
-  // TOM
-  const double* A;     // dense p x p affinity (symmetric), ld = p
-  const double* kvec;  // connectivity
-  const double* dvec;  // diagonal of A
-  int tom_v2;
-  int tom_packed;
+  EpiParams E;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -207,6 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_dmma_kernel(const Params P) {
   const int wm = warp >> 2, wn = warp & 3;
   const int g = lane >> 2, t = lane & 3;
   const int64_t p = P.p;
+  const EpiParams& E = P.E;
 
   double acc[8][4][2];
 #pragma unroll
@@ -214,75 +194,29 @@ __global__ void __launch_bounds__(THREADS, 1) gram_dmma_kernel(const Params P) {
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-  gram_mainloop<MMA_VARIANT>(acc, smem, P.R0, P.C0, P.ld0, P.K0, row0, col0, P.p, tid);
-
-  if (EPI == EPI_DIFFCOR) {
-    // stash r_a in its final location, then run the second Gram on the same tile
+  constexpr int NPASS = (EPI == EPI_DIFFCOR) ? 2 : 1;
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; ++pass) {
+    if (pass == 0)
+      gram_mainloop<MMA_VARIANT>(acc, smem, P.R0, P.C0, P.ld0, P.K0, row0, col0, P.p, tid);
+    else
+      gram_mainloop<MMA_VARIANT>(acc, smem, P.R1, P.C1, P.ld1, P.K1, row0, col0, P.p, tid);
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
       const int64_t i = row0 + wm * 64 + mt * 8 + g;
-      const int64_t ro = packed_row_offset(i, p, 1) - P.out_base - i - 1;
+      if (i < p) {
+        const EpiRow R = epi_row<EPI>(E, i);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int64_t j = col0 + wn * 32 + nt * 8 + 2 * t + e;
-          if (i < p && j < p && j > i) P.r_a[ro + j] = acc[mt][nt][e];
-          acc[mt][nt][e] = 0.0;
-        }
-    }
-    gram_mainloop<MMA_VARIANT>(acc, smem, P.R1, P.C1, P.ld1, P.K1, row0, col0, P.p, tid);
-  }
-
-#pragma unroll
-  for (int mt = 0; mt < 8; ++mt) {
-    const int64_t i = row0 + wm * 64 + mt * 8 + g;
-    if (i >= p) continue;
-    double k_i = 0.0, d_i = 0.0;
-    if (EPI == EPI_TOM) {
-      k_i = P.kvec[i];
-      d_i = P.dvec[i];
-    }
-    const int64_t ro = packed_row_offset(i, p, P.shift) - P.out_base - i - P.shift;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int64_t j = col0 + wn * 32 + nt * 8 + 2 * t + e;
-        if (j >= p) continue;
-        const double v = acc[mt][nt][e];
-        if (EPI == EPI_PACKED) {
-          if (j >= i + P.shift) P.out[ro + j] = soft_power(v, P.beta, P.keep_sign);
-        } else if (EPI == EPI_DENSE) {
-          double w = soft_power(v, P.beta, P.keep_sign);
-          if (i == j && P.diag_one) w = 1.0;
-          P.out[i * P.ldo + j] = w;
-          if (P.mirror && i != j) P.out[j * P.ldo + i] = w;
-        } else if (EPI == EPI_ACCUM) {
-          P.out[i * P.ldo + j] += v;
-        } else if (EPI == EPI_DIFFCOR) {
-          if (j > i) {
-            const double ra = P.r_a[ro + j];  // written by this very thread above
-            const double zz = (atanh(ra) - atanh(v)) * P.inv_se;
-            P.r_b[ro + j] = v;
-            P.z[ro + j] = zz;
-            P.pv[ro + j] = erfc(fabs(zz) * 0.70710678118654752440);
+          for (int e = 0; e < 2; ++e) {
+            const int64_t j = col0 + wn * 32 + nt * 8 + 2 * t + e;
+            if (j < p) epi_store<EPI>(E, R, j, acc[mt][nt][e], pass);
           }
-        } else if (EPI == EPI_TOM) {
-          const double a = P.A[i * p + j];
-          const double absa = fabs(a);
-          const double shared = v - a * (d_i + P.dvec[j]);
-          const double mk = fmin(k_i, P.kvec[j]);
-          double tom = P.tom_v2 ? 0.5 * (a + shared / (mk + absa)) : (a + shared) / (mk + 1.0 - absa);
-          if (i == j) tom = 1.0;
-          if (P.tom_packed) {
-            if (j > i) P.out[ro + j] = tom;
-          } else {
-            P.out[i * P.ldo + j] = tom;
-            if (P.mirror && i != j) P.out[j * P.ldo + i] = tom;
-          }
-        }
       }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    }
   }
 }
 

@@ -1,14 +1,452 @@
-// tcgen05 / TMEM Gram kernels (fast 3xTF32 path and exact int8 Spearman path).
+// tcgen05 / TMEM Gram kernels: the fast 3xTF32 path and the exact int8 Spearman path.
+//
+//   G[i][j] = sum_k R[i][k] * C[j][k]   with both operands K-major, exactly the shape of
+//   Z'Z (column_pairwise_cor, src/rust/src/base/r_cors_similarity.rs:74) and of the A*A of
+//   calc_tom (src/rust/src/methods/r_coremo.rs:54).
+//
+// Operands live in HBM as two "digit planes" per matrix:
+//   KIND_TF32  plane 0 = hi = tf32(z), plane 1 = lo = tf32(z - hi); the product is recovered as
+//              hi*hi + hi*lo + lo*hi (3 MMAs, FP32 accumulation in one TMEM accumulator).
+//   KIND_I8    Spearman only.  d = 2*rank - (n+1) is an integer, d = 16*h + l with |h| <= 127,
+//              l in [-8,7]; plane 0 = h, plane 1 = l (int8).  Three exact int32 accumulators
+//              hh, hl+lh, ll; the epilogue recombines S = 256*hh + 16*(hl+lh) + ll exactly in
+//              FP64 and scales by 1/(|d_i||d_j|): an integer-exact Gram at int8 tensor rate.
+//
+// Structure (persistent, warp specialised, one CTA per SM):
+//   warp 0   TMA producer: 4 x cp.async.bulk.tensor (A hi/lo, B hi/lo tiles of 128 rows x 128 B,
+//            SWIZZLE_128B) per pipeline stage, completion on an mbarrier (complete_tx)
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1 (M=128, N=128) with
+//            shared-memory descriptors; tcgen05.commit releases smem stages / publishes accumulators
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 16 columns, fused epilogue (epilogue.cuh), direct
+//            stores into the packed triangular layout
 #pragma once
+
+#include <cuda.h>
+
 #include "common.cuh"
+#include "epilogue.cuh"
+
 namespace bixcor {
 namespace umma {
-inline const char* last_error() { return "tcgen05 Gram path not built yet"; }
-inline int launch_gram_umma(cudaStream_t, int, int, int, const int8_t*, const float*, const double*, int,
-                            const int8_t*, const float*, const double*, int64_t, const int2*, int, int, double*,
-                            int64_t, int64_t, int, int, int, double, int, double*, double*, double*, double*, double,
-                            const double*, const double*, const double*, int, int) {
+
+enum Kind : int { KIND_TF32 = 0, KIND_I8 = 1 };
+
+constexpr int BM = 128, BN = 128;
+constexpr int ROW_BYTES = 128;                    // one SWIZZLE_128B row: 32 tf32 or 128 int8
+constexpr int PLANE_TILE_BYTES = BM * ROW_BYTES;  // 16 KB
+constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;  // A hi, A lo, B hi, B lo
+constexpr int STAGES = 3;
+constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Params {
+  int ntiles;
+  const int2* tiles;
+  int npass;         // 2 for the differential correlation (operand set 1 in pass 1)
+  int kblocks[2];    // 128-byte K blocks per pass
+  const double* inv_norm[2];  // KIND_I8: 1/|d| per gene and pass
+  EpiParams E;
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == KIND_TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1, layout 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor: dense, K-major A and B, M = 128, N = 128
+template <int KIND>
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (KIND == KIND_TF32 ? (1u << 4) | (2u << 7) | (2u << 10)    // D = F32, A = B = TF32
+                            : (2u << 4) | (1u << 7) | (1u << 10))   // D = S32, A = B = signed int8
+         | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int KIND>
+struct KindTraits;
+template <>
+struct KindTraits<KIND_TF32> {
+  static constexpr int NACC = 1;        // one FP32 accumulator
+  static constexpr int ACC_STAGES = 2;  // double buffered: epilogue of tile t overlaps MMA of tile t+1
+  static constexpr int NPROD = 3;
+};
+template <>
+struct KindTraits<KIND_I8> {
+  static constexpr int NACC = 3;  // hh, hl+lh, ll
+  static constexpr int ACC_STAGES = 1;
+  static constexpr int NPROD = 4;
+};
+
+template <int KIND, int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
+  using T = KindTraits<KIND>;
+  constexpr int TMEM_COLS = (T::NACC * T::ACC_STAGES * BN <= 256) ? 256 : 512;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map0) : "memory");
+    if (P.npass > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&map1) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+        const int2 tile = P.tiles[t];
+        for (int pass = 0; pass < P.npass; ++pass) {
+          const CUtensorMap* map = pass ? &map1 : &map0;
+          const int kb_n = P.kblocks[pass];
+          const int kelems = (KIND == KIND_TF32) ? 32 : 128;
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            const uint32_t s0 = base + stage * STAGE_BYTES;
+            tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.x * BM, 0);
+            tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.x * BM, 1);
+            tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.y * BN, 0);
+            tma_load_3d(s0 + 3 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.y * BN, 1);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<KIND>();
+      int stage = 0, acc_stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+        for (int pass = 0; pass < P.npass; ++pass) {
+          mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);  // epilogue has drained this accumulator set
+          tc_fence_after();
+          const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * T::NACC * BN);
+          const int kb_n = P.kblocks[pass];
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t s0 = base + stage * STAGE_BYTES;
+            const uint64_t dA0 = make_smem_desc(s0 + 0 * PLANE_TILE_BYTES);
+            const uint64_t dA1 = make_smem_desc(s0 + 1 * PLANE_TILE_BYTES);
+            const uint64_t dB0 = make_smem_desc(s0 + 2 * PLANE_TILE_BYTES);
+            const uint64_t dB1 = make_smem_desc(s0 + 3 * PLANE_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {              // 4 x 32-byte K steps inside the 128-byte swizzle row
+              const uint64_t ko = (uint64_t)(k * 2);    // +32 bytes, in 16-byte descriptor units
+              const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+              if (KIND == KIND_TF32) {
+                tc_mma<KIND>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
+                tc_mma<KIND>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
+                tc_mma<KIND>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
+              } else {
+                tc_mma<KIND>(acc0 + 0 * BN, dA0 + ko, dB0 + ko, idesc, first);  // h*h
+                tc_mma<KIND>(acc0 + 1 * BN, dA0 + ko, dB1 + ko, idesc, first);  // h*l
+                tc_mma<KIND>(acc0 + 1 * BN, dA1 + ko, dB0 + ko, idesc, 1u);     // l*h
+                tc_mma<KIND>(acc0 + 2 * BN, dA1 + ko, dB1 + ko, idesc, first);  // l*l
+              }
+            }
+            tc_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc_commit(tfull_bar(acc_stage));  // accumulators complete -> epilogue
+          if (++acc_stage == T::ACC_STAGES) {
+            acc_stage = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue ================================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may access
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    const EpiParams& E = P.E;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+      const int2 tile = P.tiles[t];
+      const int64_t i = (int64_t)tile.x * BM + ew * 32 + lane;
+      const int64_t col0 = (int64_t)tile.y * BN;
+      for (int pass = 0; pass < P.npass; ++pass) {
+        mbar_wait(tfull_bar(acc_stage), acc_phase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
+        const bool row_ok = i < E.p;
+        EpiRow R;
+        double inv_i = 0.0;
+        if (row_ok) {
+          R = epi_row<EPI>(E, i);
+          if (KIND == KIND_I8) inv_i = P.inv_norm[pass][i];
+        }
+        // skip column chunks that lie entirely below the diagonal of a diagonal tile (nothing to store)
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16(tacc + c, r0);
+          if (KIND == KIND_I8) {
+            tmem_ld16(tacc + BN + c, r1);
+            tmem_ld16(tacc + 2 * BN + c, r2);
+          }
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int64_t j = col0 + c + q;
+              if (j < E.p) {
+                double v;
+                if (KIND == KIND_TF32) {
+                  v = (double)__uint_as_float(r0[q]);
+                } else {
+                  const double s = 256.0 * (double)(int)r0[q] + 16.0 * (double)(int)r1[q] + (double)(int)r2[q];
+                  v = s * inv_i * P.inv_norm[pass][j];
+                }
+                epi_store<EPI>(E, R, j, v, pass);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc_stage));
+        if (++acc_stage == T::ACC_STAGES) {
+          acc_stage = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline char* err_buf() {
+  static char buf[512] = "";
+  return buf;
+}
+inline const char* last_error() { return err_buf(); }
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 3-D map over [plane][row][K]: dims (K, rows, 2), box (128 bytes of K, 128 rows, 1 plane), SWIZZLE_128B,
+// out-of-range rows are zero filled (ragged last tile).
+inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, int K) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    snprintf(err_buf(), 512, "cuTensorMapEncodeTiled entry point not available");
+    return -1;
+  }
+  const int es = kind == KIND_TF32 ? 4 : 1;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err_buf(), 512, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%d es=%d)", (int)r,
+             (long long)rows, K, es);
+    return -1;
+  }
+  return 0;
+}
+
+template <int KIND, int EPI>
+inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, const CUtensorMap& m1, const Params& P) {
+  auto kern = gram_umma_kernel<KIND, EPI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) {
+    snprintf(err_buf(), 512, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  const int grid = P.ntiles < sm_count ? P.ntiles : sm_count;
+  kern<<<grid, THREADS, SMEM_BYTES, stream>>>(m0, m1, P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err_buf(), 512, "gram_umma_kernel launch: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
+// operand set s: planes pointer (2 planes, [plane][rows][K]), K elements (padded), inv_norm (KIND_I8)
+inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int64_t rows, const void* planes0,
+                            int K0, const double* inv0, const void* planes1, int K1, const double* inv1,
+                            const int2* tiles, int ntiles, const EpiParams& E) {
+  if (ntiles <= 0) return 0;
+  const int kelems = kind == KIND_TF32 ? 32 : 128;
+  if (K0 % kelems != 0 || (planes1 && K1 % kelems != 0)) {
+    snprintf(err_buf(), 512, "operand K must be padded to %d elements", kelems);
+    return -1;
+  }
+  CUtensorMap m0, m1;
+  if (make_map(&m0, kind, planes0, rows, K0)) return -1;
+  if (planes1) {
+    if (make_map(&m1, kind, planes1, rows, K1)) return -1;
+  } else {
+    m1 = m0;
+  }
+  Params P;
+  P.ntiles = ntiles;
+  P.tiles = tiles;
+  P.npass = planes1 ? 2 : 1;
+  P.kblocks[0] = K0 / kelems;
+  P.kblocks[1] = planes1 ? K1 / kelems : 0;
+  P.inv_norm[0] = inv0;
+  P.inv_norm[1] = inv1;
+  P.E = E;
+#define BIXCOR_UMMA_CASE(KIND, EPI) \
+  if (kind == KIND && epi == EPI) return launch_one<KIND, EPI>(stream, sm_count, m0, m1, P);
+  BIXCOR_UMMA_CASE(KIND_TF32, EPI_PACKED)
+  BIXCOR_UMMA_CASE(KIND_TF32, EPI_DENSE)
+  BIXCOR_UMMA_CASE(KIND_TF32, EPI_DIFFCOR)
+  BIXCOR_UMMA_CASE(KIND_TF32, EPI_TOM)
+  BIXCOR_UMMA_CASE(KIND_I8, EPI_PACKED)
+  BIXCOR_UMMA_CASE(KIND_I8, EPI_DENSE)
+  BIXCOR_UMMA_CASE(KIND_I8, EPI_DIFFCOR)
+#undef BIXCOR_UMMA_CASE
+  snprintf(err_buf(), 512, "no tcgen05 kernel for kind %d / epilogue %d", kind, epi);
   return -1;
 }
+
 }  // namespace umma
 }  // namespace bixcor

@@ -152,10 +152,11 @@ int bixcor_dev_sparse_gram_accumulate(const int64_t* d_indptr, const int32_t* d_
 int bixcor_dev_sparse_gram_finalise(const double* d_gram_pp, const double* d_colsum, int64_t total_cells,
                                     int64_t genes, double* d_out_packed);
 
-/* Run the device-pointer entry points on a caller-owned CUDA stream (e.g. torch's
- * current stream; NULL restores the library's own stream), and optionally let them
- * return without synchronising so that consecutive calls queue back to back. */
-int bixcor_dev_set_stream(void* cuda_stream);
+/* Run the device-pointer entry points on a caller-owned CUDA stream (external != 0;
+ * e.g. torch's current stream, a NULL handle then means the legacy default stream) or
+ * back on the library's own stream (external == 0), and optionally let them return
+ * without synchronising so that consecutive calls queue back to back. */
+int bixcor_dev_set_stream(void* cuda_stream, int external);
 int bixcor_dev_set_async(int on);
 int bixcor_dev_synchronize(void);
 
