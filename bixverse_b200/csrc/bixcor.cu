@@ -299,10 +299,37 @@ static int check_precision(int precision, int spearman, int64_t n) {
   if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3) return BIXCOR_OK;
   if (precision == BIXCOR_PREC_I8EXACT) {
     if (!spearman) return fail(BIXCOR_ERR_INVALID, "BIXCOR_PREC_I8EXACT is defined for Spearman only");
-    if (n > 2025) return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_I8EXACT supports n <= 2025 samples (got %lld)", (long long)n);
+    // sum d_i d_j <= n(n^2-1)/3 must fit the int32 recombination of the three digit accumulators
+    if (n > 1860) return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_I8EXACT supports n <= 1860 samples (got %lld)", (long long)n);
     return BIXCOR_OK;
   }
   return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
+}
+
+// Spearman column kernel dispatch: warp-per-gene register sort for n <= 1024, CTA shared-memory sort above.
+static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, const ColumnOut& co) {
+  if (n <= 1024) {
+    int e = 1;
+    while (32 * e < n) e <<= 1;
+    const unsigned grid = (unsigned)((p + 3) / 4);
+    switch (e) {
+      case 1: rank_columns_warp_kernel<1><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
+      case 2: rank_columns_warp_kernel<2><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
+      case 4: rank_columns_warp_kernel<4><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
+      case 8: rank_columns_warp_kernel<8><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
+      case 16: rank_columns_warp_kernel<16><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
+      default: rank_columns_warp_kernel<32><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
+    }
+  } else {
+    int npow2 = 2048;
+    while (npow2 < n) npow2 <<= 1;
+    const size_t smem = (size_t)npow2 * 12;
+    CU_TRY(cudaFuncSetAttribute(rank_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rank_columns_kernel<<<(unsigned)p, 256, smem, c->compute>>>(d_x, n, (int)n, npow2, co);
+  }
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
 }
 
 // d_x: device n x p column-major.  Builds the operand in ctx slot `slot`.
@@ -344,16 +371,8 @@ static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int 
     op->f32 = co.f32;
   }
   Timed tm(c, T_COLS);
-  if (spearman) {
-    int npow2 = 32;
-    while (npow2 < n) npow2 <<= 1;
-    const int threads = std::min(256, npow2);
-    const size_t smem = (size_t)npow2 * 12;
-    CU_TRY(cudaFuncSetAttribute(rank_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rank_columns_kernel<<<(unsigned)p, threads, smem, c->compute>>>(d_x, n, (int)n, npow2, co);
-  } else {
-    standardise_columns_kernel<<<(unsigned)p, 128, 0, c->compute>>>(d_x, n, (int)n, co);
-  }
+  if (spearman) return launch_rank_kernel(c, d_x, n, p, co);
+  standardise_columns_kernel<<<(unsigned)p, 128, 0, c->compute>>>(d_x, n, (int)n, co);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return BIXCOR_OK;
@@ -990,17 +1009,10 @@ int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_o
   co.f64 = d_out;
   co.ld64 = n;
   co.kpad = (int)n;
-  int npow2 = 32;
-  while (npow2 < n) npow2 <<= 1;
-  const int threads = std::min(256, npow2);
-  const size_t smem = (size_t)npow2 * 12;
-  CU_TRY(cudaFuncSetAttribute(rank_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     Timed tm(c, T_COLS);
-    rank_columns_kernel<<<(unsigned)p, threads, smem, c->compute>>>(d_x, n, (int)n, npow2, co);
-    g_launches++;
+    RC_TRY(launch_rank_kernel(c, d_x, n, p, co));
   }
-  CU_TRY(cudaGetLastError());
   return finish_dev(c);
 }
 

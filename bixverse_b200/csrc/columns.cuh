@@ -235,6 +235,199 @@ rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2,
   }
 }
 
+// ----------------------------------------------------------------------------
+// Warp-per-gene rank kernel for n <= 1024: the whole column lives in registers
+// (E = npow2/32 elements per lane, sorted position s = lane*E + r).  Bitonic
+// stages whose partner distance is below E are compare-exchanges between
+// registers of one thread; the others are lane exchanges by shuffle.  No
+// shared-memory traffic and no block barrier in the sort.
+// ----------------------------------------------------------------------------
+template <typename RK>
+__device__ __forceinline__ void emit_ranked_column_warp(const ColumnOut& out, int64_t j, int n, const RK* rk2, int lane) {
+  if (out.mode == COL_RANKS) {
+    for (int i = lane; i < n; i += 32) out.f64[j * out.ld64 + i] = 0.5 * (double)rk2[i];
+    return;
+  }
+  long long ss = 0;
+  for (int i = lane; i < n; i += 32) {
+    const long long d = (long long)rk2[i] - (long long)(n + 1);
+    ss += d * d;
+  }
+  ss = warp_sum_ll(ss);
+  const double norm = sqrt((double)ss);
+  if (out.mode == COL_Z64) {
+    for (int i = lane; i < out.kpad; i += 32) {
+      double z = 0.0;
+      if (i < n) z = (double)((int)rk2[i] - (n + 1)) / norm;
+      out.f64[j * out.ld64 + i] = z;
+    }
+  } else if (out.mode == COL_I8) {
+    // four samples per lane and store: one 32-bit word of each digit plane
+    for (int i4 = lane * 4; i4 < out.kpad; i4 += 128) {
+      uint32_t wh = 0, wl = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i4 + q;
+        const int d = (i < n) ? (int)rk2[i] - (n + 1) : 0;
+        const int l = ((d + 8) & 15) - 8;
+        const int h = (d - l) >> 4;
+        wh |= (uint32_t)(h & 0xff) << (8 * q);
+        wl |= (uint32_t)(l & 0xff) << (8 * q);
+      }
+      *reinterpret_cast<uint32_t*>(out.i8 + j * out.ld8 + i4) = wh;
+      *reinterpret_cast<uint32_t*>(out.i8 + out.plane8 + j * out.ld8 + i4) = wl;
+    }
+    if (lane == 0) out.inv_norm[j] = 1.0 / norm;
+  } else {
+    for (int i = lane; i < out.kpad; i += 32) {
+      double z = 0.0;
+      if (i < n) z = (double)((int)rk2[i] - (n + 1)) / norm;
+      emit_tf32(out, j, i, z);
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(128)
+rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out) {
+  constexpr int NP = 32 * E;
+  __shared__ uint16_t rk2s[4][NP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * 4 + warp;
+  if (j >= p) return;  // whole warp leaves; no block-level barrier below
+  const double* col = x + j * ldx;
+
+  uint64_t key[E];
+  uint32_t idx[E];
+  bool has_nan = false;
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int i = r * 32 + lane;  // coalesced load; the initial order is irrelevant to a sort
+    uint64_t k = ~0ull;
+    if (i < n) {
+      const double v = col[i];
+      if (v != v) has_nan = true;
+      k = sortable_key(v);
+    }
+    key[r] = k;
+    idx[r] = (uint32_t)i;
+  }
+  if (__any_sync(0xffffffffu, has_nan)) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    if (out.mode == COL_RANKS) {
+      for (int i = lane; i < n; i += 32) out.f64[j * out.ld64 + i] = qnan;
+    } else if (out.mode == COL_Z64) {
+      for (int i = lane; i < out.kpad; i += 32) out.f64[j * out.ld64 + i] = (i < n) ? qnan : 0.0;
+    } else if (out.mode == COL_I8) {
+      for (int i = lane; i < out.kpad; i += 32) {
+        out.i8[j * out.ld8 + i] = 0;
+        out.i8[out.plane8 + j * out.ld8 + i] = 0;
+      }
+      if (lane == 0) out.inv_norm[j] = qnan;
+    } else {
+      for (int i = lane; i < out.kpad; i += 32) {
+        out.f32[j * out.ld32 + i] = (i < n) ? __int_as_float(0x7fc00000) : 0.f;
+        out.f32[out.plane32 + j * out.ld32 + i] = 0.f;
+      }
+    }
+    return;
+  }
+
+  // ---- bitonic sort, position s = lane*E + r --------------------------------
+#pragma unroll
+  for (int k = 2; k <= NP; k <<= 1) {
+#pragma unroll
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      if (jj >= E) {
+        const int lm = jj / E;                          // partner lane = lane ^ lm
+        const bool up = ((lane * E) & k) == 0;          // k >= 2E here: the direction bit is a lane bit
+        const bool keep_min = ((lane & lm) == 0) == up;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
+          const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
+          const bool take = keep_min ? (ok < key[r]) : (ok > key[r]);
+          if (take) {
+            key[r] = ok;
+            idx[r] = oi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          if ((r & jj) == 0) {
+            const int l = r | jj;
+            const bool up = (k < E) ? ((r & k) == 0) : (((lane * E) & k) == 0);
+            const bool sw = up ? (key[r] > key[l]) : (key[r] < key[l]);
+            if (sw) {
+              const uint64_t tk = key[r];
+              key[r] = key[l];
+              key[l] = tk;
+              const uint32_t ti = idx[r];
+              idx[r] = idx[l];
+              idx[l] = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- tie runs -> 2 * average rank ------------------------------------------
+  const uint64_t prev_last = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
+  uint32_t start_mask = 0;  // bit r: position lane*E + r starts a run of equal keys
+  int last = -1;
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int s = lane * E + r;
+    const uint64_t prev = (r == 0) ? prev_last : key[r - 1];
+    const bool st = (s >= n) || (s == 0) || (key[r] != prev);
+    if (st) {
+      start_mask |= 1u << r;
+      last = s;
+    }
+  }
+  // exclusive prefix max of `last` over lanes
+  int inc = last;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, t);
+  }
+  int cur = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) cur = -1;
+  uint32_t lo[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    if (start_mask & (1u << r)) cur = lane * E + r;
+    lo[r] = (uint32_t)cur;
+  }
+  // run ends: position s ends a run iff s+1 starts one (or s is the last slot)
+  uint32_t next_first = __shfl_down_sync(0xffffffffu, start_mask & 1u, 1);
+  if (lane == 31) next_first = 1u;
+  const uint32_t end_mask = (E == 32) ? ((start_mask >> 1) | (next_first << 31))
+                                      : (((start_mask >> 1) | (next_first << (E - 1))) & ((E == 32) ? 0xffffffffu : ((1u << E) - 1u)));
+  int first = 0x7fffffff;
+  if (end_mask) first = lane * E + (__ffs(end_mask) - 1);
+  int dec = first;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, dec, o);
+    if (lane + o < 32) dec = min(dec, t);
+  }
+  cur = __shfl_down_sync(0xffffffffu, dec, 1);
+  if (lane == 31) cur = 0x7fffffff;
+  uint16_t* rk2 = rk2s[warp];
+#pragma unroll
+  for (int r = E - 1; r >= 0; --r) {
+    const int s = lane * E + r;
+    if (end_mask & (1u << r)) cur = s;
+    if (s < n) rk2[idx[r]] = (uint16_t)(lo[r] + (uint32_t)cur + 2u);  // lo + hi + 2 == 2 * average rank
+  }
+  __syncwarp();
+  emit_ranked_column_warp(out, j, n, rk2, lane);
+}
+
 // Pearson: centre and scale one gene per CTA to unit Euclidean norm, so that
 // Z'Z is the correlation matrix (sd == 0 -> 0/0 = NaN column, IEEE propagation).
 __global__ void __launch_bounds__(128)

@@ -83,19 +83,26 @@ __device__ __forceinline__ EpiRow epi_row(const EpiParams& E, int64_t i) {
 
 // pass: 0 for everything except the second Gram of EPI_DIFFCOR (pass 1).  In pass 0 of
 // EPI_DIFFCOR the value is r_a and is parked in its final location.
-template <int EPI>
-__device__ __forceinline__ void epi_store(const EpiParams& E, const EpiRow& R, int64_t j, double v, int pass) {
+// Returns the value written to the primary location.  MIRROR_INLINE = false leaves the
+// transposed write of the dense modes to the caller (epi_mirror), so that a kernel can issue
+// it from a thread mapping in which it is coalesced.
+template <int EPI, bool MIRROR_INLINE = true>
+__device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R, int64_t j, double v, int pass) {
   const int64_t i = R.i;
   if (EPI == EPI_PACKED) {
-    if (j >= i + E.shift) E.out[R.ro + j] = epi_power(E, v);
+    const double w = epi_power(E, v);
+    if (j >= i + E.shift) E.out[R.ro + j] = w;
+    return w;
   } else if (EPI == EPI_DENSE) {
-    if (E.mirror && j < i) return;  // lower half of a diagonal tile: filled by the mirror write
     double w = epi_power(E, v);
     if (i == j && E.diag_one) w = 1.0;
+    if (E.mirror && j < i) return w;  // lower half of a diagonal tile: filled by the mirror write
     E.out[i * E.ldo + j] = w;
-    if (E.mirror && i != j) E.out[j * E.ldo + i] = w;
+    if (MIRROR_INLINE && E.mirror && i != j) E.out[j * E.ldo + i] = w;
+    return w;
   } else if (EPI == EPI_ACCUM) {
     E.out[i * E.ldo + j] += v;
+    return v;
   } else if (EPI == EPI_DIFFCOR) {
     if (j > i) {
       if (pass == 0) {
@@ -108,7 +115,8 @@ __device__ __forceinline__ void epi_store(const EpiParams& E, const EpiRow& R, i
         E.pv[R.ro + j] = erfc(fabs(zz) * 0.70710678118654752440);
       }
     }
-  } else if (EPI == EPI_TOM) {
+    return v;
+  } else {  // EPI_TOM
     const double a = E.A[i * E.p + j];
     const double absa = fabs(a);
     const double shared = v - a * (R.d_i + E.dvec[j]);
@@ -119,9 +127,22 @@ __device__ __forceinline__ void epi_store(const EpiParams& E, const EpiRow& R, i
       if (j > i) E.out[R.ro + j] = tom;
     } else if (!(E.mirror && j < i)) {
       E.out[i * E.ldo + j] = tom;
-      if (E.mirror && i != j) E.out[j * E.ldo + i] = tom;
+      if (MIRROR_INLINE && E.mirror && i != j) E.out[j * E.ldo + i] = tom;
     }
+    return tom;
   }
+}
+
+// does this epilogue configuration need the separate transposed write?
+template <int EPI>
+__device__ __forceinline__ bool epi_wants_mirror(const EpiParams& E) {
+  if (EPI == EPI_DENSE) return E.mirror != 0;
+  if (EPI == EPI_TOM) return E.mirror != 0 && !E.tom_packed;
+  return false;
+}
+
+__device__ __forceinline__ void epi_mirror(const EpiParams& E, int64_t i, int64_t j, double w) {
+  if (j > i) E.out[j * E.ldo + i] = w;
 }
 
 }  // namespace bixcor

@@ -38,7 +38,9 @@ constexpr int PLANE_TILE_BYTES = BM * ROW_BYTES;  // 16 KB
 constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;  // A hi, A lo, B hi, B lo
 constexpr int STAGES = 3;
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STAGE_LD = 33;                                  // doubles per staged row (odd: conflict-free both ways)
+constexpr int EPI_STAGE_BYTES = 4 * 32 * STAGE_LD * 8;        // one 32 x 32 double transpose buffer per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 struct Params {
   int ntiles;
@@ -121,6 +123,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4,
@@ -147,14 +160,18 @@ struct KindTraits;
 template <>
 struct KindTraits<KIND_TF32> {
   static constexpr int NACC = 1;        // one FP32 accumulator
-  static constexpr int ACC_STAGES = 2;  // double buffered: epilogue of tile t overlaps MMA of tile t+1
-  static constexpr int NPROD = 3;
+  static constexpr int ACC_STAGES = 2;  // double buffered in TMEM
+  // The tensor core adds into its FP32 accumulator with truncation, a bias that grows linearly with
+  // the number of accumulations.  The MMA therefore only accumulates CHUNK_KB K-blocks (128 samples)
+  // at a time; the epilogue warps drain every chunk from TMEM and sum the chunks in FP32 registers
+  // with round-to-nearest (measured: 1e-5 -> <1e-6 at n = 1000, and independent of K).
+  static constexpr int CHUNK_KB = 4;
 };
 template <>
 struct KindTraits<KIND_I8> {
-  static constexpr int NACC = 3;  // hh, hl+lh, ll
+  static constexpr int NACC = 3;  // hh, hl+lh, ll (exact int32)
   static constexpr int ACC_STAGES = 1;
-  static constexpr int NPROD = 4;
+  static constexpr int CHUNK_KB = 1 << 30;  // integer accumulation is exact: one chunk = whole K
 };
 
 template <int KIND, int EPI>
@@ -171,6 +188,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  double* epi_stage_all = reinterpret_cast<double*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -236,43 +254,46 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         for (int pass = 0; pass < P.npass; ++pass) {
-          mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);  // epilogue has drained this accumulator set
-          tc_fence_after();
-          const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * T::NACC * BN);
           const int kb_n = P.kblocks[pass];
-          for (int kb = 0; kb < kb_n; ++kb) {
-            mbar_wait(full_bar(stage), phase);
+          for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
+            const int kb1 = (kb_n - kb0 > T::CHUNK_KB) ? kb0 + T::CHUNK_KB : kb_n;
+            mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);  // epilogue has drained this accumulator set
             tc_fence_after();
-            const uint32_t s0 = base + stage * STAGE_BYTES;
-            const uint64_t dA0 = make_smem_desc(s0 + 0 * PLANE_TILE_BYTES);
-            const uint64_t dA1 = make_smem_desc(s0 + 1 * PLANE_TILE_BYTES);
-            const uint64_t dB0 = make_smem_desc(s0 + 2 * PLANE_TILE_BYTES);
-            const uint64_t dB1 = make_smem_desc(s0 + 3 * PLANE_TILE_BYTES);
+            const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * T::NACC * BN);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t s0 = base + stage * STAGE_BYTES;
+              const uint64_t dA0 = make_smem_desc(s0 + 0 * PLANE_TILE_BYTES);
+              const uint64_t dA1 = make_smem_desc(s0 + 1 * PLANE_TILE_BYTES);
+              const uint64_t dB0 = make_smem_desc(s0 + 2 * PLANE_TILE_BYTES);
+              const uint64_t dB1 = make_smem_desc(s0 + 3 * PLANE_TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {              // 4 x 32-byte K steps inside the 128-byte swizzle row
-              const uint64_t ko = (uint64_t)(k * 2);    // +32 bytes, in 16-byte descriptor units
-              const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-              if (KIND == KIND_TF32) {
-                tc_mma<KIND>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
-                tc_mma<KIND>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
-                tc_mma<KIND>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
-              } else {
-                tc_mma<KIND>(acc0 + 0 * BN, dA0 + ko, dB0 + ko, idesc, first);  // h*h
-                tc_mma<KIND>(acc0 + 1 * BN, dA0 + ko, dB1 + ko, idesc, first);  // h*l
-                tc_mma<KIND>(acc0 + 1 * BN, dA1 + ko, dB0 + ko, idesc, 1u);     // l*h
-                tc_mma<KIND>(acc0 + 2 * BN, dA1 + ko, dB1 + ko, idesc, first);  // l*l
+              for (int k = 0; k < 4; ++k) {             // 4 x 32-byte K steps inside the 128-byte swizzle row
+                const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes, in 16-byte descriptor units
+                const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+                if (KIND == KIND_TF32) {
+                  tc_mma<KIND>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
+                  tc_mma<KIND>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
+                  tc_mma<KIND>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
+                } else {
+                  tc_mma<KIND>(acc0 + 0 * BN, dA0 + ko, dB0 + ko, idesc, first);  // h*h
+                  tc_mma<KIND>(acc0 + 1 * BN, dA0 + ko, dB1 + ko, idesc, first);  // h*l
+                  tc_mma<KIND>(acc0 + 1 * BN, dA1 + ko, dB0 + ko, idesc, 1u);     // l*h
+                  tc_mma<KIND>(acc0 + 2 * BN, dA1 + ko, dB1 + ko, idesc, first);  // l*l
+                }
+              }
+              tc_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
               }
             }
-            tc_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1u;
+            tc_commit(tfull_bar(acc_stage));  // chunk accumulators complete -> epilogue warps
+            if (++acc_stage == T::ACC_STAGES) {
+              acc_stage = 0;
+              acc_phase ^= 1u;
             }
-          }
-          tc_commit(tfull_bar(acc_stage));  // accumulators complete -> epilogue
-          if (++acc_stage == T::ACC_STAGES) {
-            acc_stage = 0;
-            acc_phase ^= 1u;
           }
         }
       }
@@ -283,53 +304,114 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     const EpiParams& E = P.E;
+    double* stg = epi_stage_all + ew * (32 * STAGE_LD);
+    const bool want_mirror = epi_wants_mirror<EPI>(E);
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
       const int2 tile = P.tiles[t];
-      const int64_t i = (int64_t)tile.x * BM + ew * 32 + lane;
+      const int64_t row_base = (int64_t)tile.x * BM + ew * 32;
+      const int64_t i = row_base + lane;
       const int64_t col0 = (int64_t)tile.y * BN;
       for (int pass = 0; pass < P.npass; ++pass) {
-        mbar_wait(tfull_bar(acc_stage), acc_phase);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
+        // ---- drain: TMEM -> registers, chunk by chunk (FP32 round-to-nearest / exact int32 sums)
+        uint32_t racc[BN];
+        const int kb_n = P.kblocks[pass];
+        for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
+          mbar_wait(tfull_bar(acc_stage), acc_phase);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
+          if (KIND == KIND_I8) {
+#pragma unroll
+            for (int c = 0; c < BN; c += 16) {
+              uint32_t r0[16], r1[16], r2[16];
+              tmem_ld16(tacc + c, r0);
+              tmem_ld16(tacc + BN + c, r1);
+              tmem_ld16(tacc + 2 * BN + c, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q)  // S = 256*hh + 16*(hl+lh) + ll, exact in int32 for n <= 1860
+                racc[c + q] = (uint32_t)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+              uint32_t r0[32];
+              tmem_ld32(tacc + c, r0);
+              tmem_ld_wait();
+              if (kb0 == 0) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) racc[c + q] = r0[q];
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                  racc[c + q] = __float_as_uint(__uint_as_float(racc[c + q]) + __uint_as_float(r0[q]));
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc_stage));  // TMEM buffer free: the MMA warp moves on
+          if (++acc_stage == T::ACC_STAGES) {
+            acc_stage = 0;
+            acc_phase ^= 1u;
+          }
+        }
+        // ---- fused epilogue from registers, transposed through shared memory so that every
+        //      store instruction writes one contiguous 256-byte run of a packed row
         const bool row_ok = i < E.p;
         EpiRow R;
+        R.i = i;
+        R.ro = 0;
+        R.k_i = R.d_i = 0.0;
         double inv_i = 0.0;
         if (row_ok) {
           R = epi_row<EPI>(E, i);
           if (KIND == KIND_I8) inv_i = P.inv_norm[pass][i];
         }
-        // skip column chunks that lie entirely below the diagonal of a diagonal tile (nothing to store)
-        for (int c = 0; c < BN; c += 16) {
-          uint32_t r0[16], r1[16], r2[16];
-          tmem_ld16(tacc + c, r0);
-          if (KIND == KIND_I8) {
-            tmem_ld16(tacc + BN + c, r1);
-            tmem_ld16(tacc + 2 * BN + c, r2);
-          }
-          tmem_ld_wait();
-          if (row_ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int64_t j = col0 + c + q;
-              if (j < E.p) {
-                double v;
-                if (KIND == KIND_TF32) {
-                  v = (double)__uint_as_float(r0[q]);
-                } else {
-                  const double s = 256.0 * (double)(int)r0[q] + 16.0 * (double)(int)r1[q] + (double)(int)r2[q];
-                  v = s * inv_i * P.inv_norm[pass][j];
-                }
-                epi_store<EPI>(E, R, j, v, pass);
-              }
+        for (int c = 0; c < BN; c += 32) {
+          // chunks entirely below the diagonal of a diagonal tile hold nothing to store (warp uniform)
+          if (EPI != EPI_ACCUM && tile.x == tile.y && c + 31 < ew * 32 &&
+              (EPI == EPI_PACKED || EPI == EPI_DIFFCOR || want_mirror || (EPI == EPI_TOM && E.tom_packed)))
+            continue;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const double v = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
+            stg[lane * STAGE_LD + q] = v;
+          }
+          __syncwarp();
+          const int64_t j = col0 + c + lane;
+          const bool col_ok = j < E.p;
+          double inv_j = 1.0;
+          if (KIND == KIND_I8 && col_ok) inv_j = P.inv_norm[pass][j];
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            EpiRow Rr;
+            Rr.i = row_base + r;
+            Rr.ro = __shfl_sync(0xffffffffu, R.ro, r);
+            if (EPI == EPI_TOM) {
+              Rr.k_i = __shfl_sync(0xffffffffu, R.k_i, r);
+              Rr.d_i = __shfl_sync(0xffffffffu, R.d_i, r);
+            } else {
+              Rr.k_i = Rr.d_i = 0.0;
+            }
+            if (Rr.i < E.p && col_ok) {
+              double v = stg[r * STAGE_LD + lane];
+              if (KIND == KIND_I8) v *= inv_j;
+              const double w = epi_store<EPI, false>(E, Rr, j, v, pass);
+              if (want_mirror) stg[r * STAGE_LD + lane] = w;
             }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc_stage));
-        if (++acc_stage == T::ACC_STAGES) {
-          acc_stage = 0;
-          acc_phase ^= 1u;
+          __syncwarp();
+          if (want_mirror) {  // transposed element: consecutive lanes = consecutive rows i -> coalesced
+            if (row_ok) {
+#pragma unroll 4
+              for (int q = 0; q < 32; ++q) {
+                const int64_t jj = col0 + c + q;
+                if (jj < E.p) epi_mirror(E, i, jj, stg[lane * STAGE_LD + q]);
+              }
+            }
+            __syncwarp();
+          }
         }
       }
     }

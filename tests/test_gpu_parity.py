@@ -14,7 +14,7 @@ from oracle import oracle as o
 pytestmark = pytest.mark.gpu
 
 TOL64 = 1e-10
-TOL32 = 1e-5
+TOL32 = 1e-5  # north-star bar for the FP32 path
 
 
 @pytest.fixture(scope="module")
