@@ -395,6 +395,7 @@ static int launch_dmma(Ctx* c, const dmma::Params& P, int ntiles) {
     BIXCOR_DMMA_CASE(0)
     BIXCOR_DMMA_CASE(1)
     BIXCOR_DMMA_CASE(2)
+    BIXCOR_DMMA_CASE(3)
     default:
       return fail(BIXCOR_ERR_INVALID, "bad DMMA variant %d", g_dmma_variant);
   }

@@ -334,39 +334,39 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
   }
 
   // ---- bitonic sort, position s = lane*E + r --------------------------------
-#pragma unroll
+  // The merge level k is a RUNTIME loop: the fully unrolled network is ~190 KB of code and
+  // is instruction-fetch bound; this form is one lane-exchange body plus log2(E) register stages.
+#pragma unroll 1
   for (int k = 2; k <= NP; k <<= 1) {
+    const bool up_lane = ((lane * E) & k) == 0;  // direction bit when it is a lane bit (k >= E)
+#pragma unroll 1
+    for (int jj = k >> 1; jj >= E; jj >>= 1) {
+      const int lm = jj / E;  // partner lane = lane ^ lm
+      const bool keep_min = ((lane & lm) == 0) == up_lane;
 #pragma unroll
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      if (jj >= E) {
-        const int lm = jj / E;                          // partner lane = lane ^ lm
-        const bool up = ((lane * E) & k) == 0;          // k >= 2E here: the direction bit is a lane bit
-        const bool keep_min = ((lane & lm) == 0) == up;
+      for (int r = 0; r < E; ++r) {
+        const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
+        const bool take = keep_min ? (ok < key[r]) : (ok > key[r]);
+        key[r] = take ? ok : key[r];  // selects, not branches
+        idx[r] = take ? oi : idx[r];
+      }
+    }
 #pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
-          const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
-          const bool take = keep_min ? (ok < key[r]) : (ok > key[r]);
-          if (take) {
-            key[r] = ok;
-            idx[r] = oi;
-          }
-        }
-      } else {
+    for (int jj = E / 2; jj > 0; jj >>= 1) {
+      if (jj < k) {  // warp uniform
 #pragma unroll
         for (int r = 0; r < E; ++r) {
           if ((r & jj) == 0) {
             const int l = r | jj;
-            const bool up = (k < E) ? ((r & k) == 0) : (((lane * E) & k) == 0);
-            const bool sw = up ? (key[r] > key[l]) : (key[r] < key[l]);
-            if (sw) {
-              const uint64_t tk = key[r];
-              key[r] = key[l];
-              key[l] = tk;
-              const uint32_t ti = idx[r];
-              idx[r] = idx[l];
-              idx[l] = ti;
-            }
+            const bool up = (k < E) ? ((r & k) == 0) : up_lane;
+            const uint64_t ka = key[r], kb = key[l];
+            const uint32_t ia = idx[r], ib = idx[l];
+            const bool sw = (ka > kb) == up;  // equal keys may swap: harmless inside one thread
+            key[r] = sw ? kb : ka;            // selects, not branches
+            key[l] = sw ? ka : kb;
+            idx[r] = sw ? ib : ia;
+            idx[l] = sw ? ia : ib;
           }
         }
       }

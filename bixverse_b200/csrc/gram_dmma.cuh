@@ -65,7 +65,7 @@ __device__ __forceinline__ void mma_16x8x8(double (&c0)[2], double (&c1)[2], dou
       : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
 }
 __device__ __forceinline__ void mma_8x8x4(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
@@ -98,7 +98,9 @@ __device__ __forceinline__ void load_stage(double* stage, const double* __restri
   }
 }
 
-// MMA_VARIANT: 0 = m8n8k4, 1 = m16n8k8, 2 = m16n8k16
+// MMA_VARIANT: 0 = m8n8k4 (two dependent MMAs per accumulator back to back), 1 = m16n8k8,
+// 2 = m16n8k16, 3 = m8n8k4 with the k slice as the outer loop (32 independent MMAs between
+// two MMAs on the same accumulator)
 template <int MMA_VARIANT>
 __device__ __forceinline__ void gram_mainloop(double (&acc)[8][4][2], double* smem, const double* __restrict__ R,
                                               const double* __restrict__ C, int64_t ld, int K, int row0, int col0,
@@ -160,6 +162,15 @@ __device__ __forceinline__ void gram_mainloop(double (&acc)[8][4][2], double* sm
             for (int nt = 0; nt < 4; ++nt)
               mma_16x8x8(acc[2 * m2][nt], acc[2 * m2 + 1][nt], a[2 * m2].x, a[2 * m2 + 1].x, a[2 * m2].y,
                          a[2 * m2 + 1].y, b[nt].x, b[nt].y);
+        } else if (MMA_VARIANT == 3) {
+#pragma unroll
+          for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_8x8x4(acc[mt][nt], a[mt].x, b[nt].x);
+#pragma unroll
+          for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_8x8x4(acc[mt][nt], a[mt].y, b[nt].y);
         } else {
 #pragma unroll
           for (int mt = 0; mt < 8; ++mt)
