@@ -135,7 +135,7 @@ struct Ctx {
 
 static std::vector<Ctx*> g_ctx;
 static std::mutex g_init_mu;
-static int g_dmma_variant = 1;
+static int g_dmma_variant = 1;  // dmma::Shape<CFG>, env BIXCOR_DMMA_VARIANT
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
 
@@ -385,19 +385,18 @@ template <int EPI>
 static int launch_dmma(Ctx* c, const dmma::Params& P, int ntiles) {
   if (ntiles <= 0) return BIXCOR_OK;
   Timed tm(c, T_GEMM);
-#define BIXCOR_DMMA_CASE(V)                                                                               \
-  case V: {                                                                                               \
-    auto kern = dmma::gram_dmma_kernel<EPI, V>;                                                           \
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma::SMEM_BYTES));    \
-    kern<<<ntiles, dmma::THREADS, dmma::SMEM_BYTES, c->compute>>>(P);                                     \
+#define BIXCOR_DMMA_CASE(V)                                                                                  \
+  case V: {                                                                                                  \
+    auto kern = dmma::gram_dmma_kernel<EPI, V>;                                                              \
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dmma::smem_bytes_of<V>())); \
+    kern<<<ntiles * (128 / dmma::Shape<V>::BN), dmma::threads_of<V>(), dmma::smem_bytes_of<V>(), c->compute>>>(P); \
   } break;
   switch (g_dmma_variant) {
     BIXCOR_DMMA_CASE(0)
     BIXCOR_DMMA_CASE(1)
     BIXCOR_DMMA_CASE(2)
-    BIXCOR_DMMA_CASE(3)
     default:
-      return fail(BIXCOR_ERR_INVALID, "bad DMMA variant %d", g_dmma_variant);
+      return fail(BIXCOR_ERR_INVALID, "bad DMMA kernel shape %d", g_dmma_variant);
   }
 #undef BIXCOR_DMMA_CASE
   g_launches++;

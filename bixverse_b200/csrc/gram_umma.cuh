@@ -48,6 +48,7 @@ struct Params {
   int npass;         // 2 for the differential correlation (operand set 1 in pass 1)
   int kblocks[2];    // 128-byte K blocks per pass
   const double* inv_norm[2];  // KIND_I8: 1/|d| per gene and pass
+  int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = no global stores, 3 = no MMA issue
   EpiParams E;
 };
 
@@ -272,6 +273,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               for (int k = 0; k < 4; ++k) {             // 4 x 32-byte K steps inside the 128-byte swizzle row
                 const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes, in 16-byte descriptor units
                 const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+                if (P.dbg == 3) continue;
                 if (KIND == KIND_TF32) {
                   tc_mma<KIND>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
                   tc_mma<KIND>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
@@ -357,7 +359,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         }
         // ---- fused epilogue from registers, transposed through shared memory so that every
         //      store instruction writes one contiguous 256-byte run of a packed row
-        const bool row_ok = i < E.p;
+        if (P.dbg == 1) continue;
+        const bool row_ok = (P.dbg == 2) ? false : (i < E.p);
         EpiRow R;
         R.i = i;
         R.ro = 0;
@@ -394,7 +397,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             } else {
               Rr.k_i = Rr.d_i = 0.0;
             }
-            if (Rr.i < E.p && col_ok) {
+            if (Rr.i < E.p && col_ok && P.dbg != 2) {
               double v = stg[r * STAGE_LD + lane];
               if (KIND == KIND_I8) v *= inv_j;
               const double w = epi_store<EPI, false>(E, Rr, j, v, pass);
@@ -516,6 +519,10 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   P.inv_norm[0] = inv0;
   P.inv_norm[1] = inv1;
   P.E = E;
+  {
+    const char* d = getenv("BIXCOR_UMMA_DEBUG");
+    P.dbg = d ? atoi(d) : 0;
+  }
 #define BIXCOR_UMMA_CASE(KIND, EPI) \
   if (kind == KIND && epi == EPI) return launch_one<KIND, EPI>(stream, sm_count, m0, m1, P);
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_PACKED)
