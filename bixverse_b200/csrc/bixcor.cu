@@ -135,7 +135,7 @@ struct Ctx {
 
 static std::vector<Ctx*> g_ctx;
 static std::mutex g_init_mu;
-static int g_dmma_variant = 1;  // dmma::Shape<CFG>, env BIXCOR_DMMA_VARIANT
+static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM: measured fastest), env BIXCOR_DMMA_VARIANT
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
 

@@ -44,15 +44,30 @@ struct EpiParams {
 __device__ __forceinline__ double epi_power(const EpiParams& E, double r) {
   if (E.beta == 1.0) return r;
   double a = fabs(r);
-  if (E.beta_int > 0) {
-    double acc = 1.0, base = a;
-    int e = E.beta_int;
-    while (e) {
-      if (e & 1) acc *= base;
-      base *= base;
-      e >>= 1;
+  const int bi = E.beta_int;  // warp-uniform: the branches below never diverge
+  if (bi > 0) {
+    const double sq = a * a;
+    if (bi == 2) {
+      a = sq;
+    } else if (bi == 3) {
+      a = sq * a;
+    } else if (bi == 4) {
+      a = sq * sq;
+    } else if (bi == 6) {
+      a = sq * sq * sq;
+    } else if (bi == 8) {
+      const double q = sq * sq;
+      a = q * q;
+    } else {
+      double acc = 1.0, base = a;
+      int e = bi;
+      while (e) {
+        if (e & 1) acc *= base;
+        base *= base;
+        e >>= 1;
+      }
+      a = acc;
     }
-    a = acc;
   } else {
     a = pow(a, E.beta);
   }
@@ -61,7 +76,7 @@ __device__ __forceinline__ double epi_power(const EpiParams& E, double r) {
 
 // Per-row constants hoisted out of the column loop.
 struct EpiRow {
-  int64_t i;
+  int i;
   int64_t ro;  // packed: index of (i, j) is ro + j
   double k_i, d_i;
 };
@@ -69,7 +84,7 @@ struct EpiRow {
 template <int EPI>
 __device__ __forceinline__ EpiRow epi_row(const EpiParams& E, int64_t i) {
   EpiRow R;
-  R.i = i;
+  R.i = (int)i;
   const int shift = (EPI == EPI_DIFFCOR || (EPI == EPI_TOM)) ? 1 : E.shift;
   R.ro = packed_row_offset(i, E.p, shift) - E.out_base - i - shift;
   R.k_i = 0.0;
@@ -87,8 +102,8 @@ __device__ __forceinline__ EpiRow epi_row(const EpiParams& E, int64_t i) {
 // transposed write of the dense modes to the caller (epi_mirror), so that a kernel can issue
 // it from a thread mapping in which it is coalesced.
 template <int EPI, bool MIRROR_INLINE = true>
-__device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R, int64_t j, double v, int pass) {
-  const int64_t i = R.i;
+__device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R, int j, double v, int pass) {
+  const int i = R.i;
   if (EPI == EPI_PACKED) {
     const double w = epi_power(E, v);
     if (j >= i + E.shift) E.out[R.ro + j] = w;
@@ -97,11 +112,11 @@ __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R,
     double w = epi_power(E, v);
     if (i == j && E.diag_one) w = 1.0;
     if (E.mirror && j < i) return w;  // lower half of a diagonal tile: filled by the mirror write
-    E.out[i * E.ldo + j] = w;
-    if (MIRROR_INLINE && E.mirror && i != j) E.out[j * E.ldo + i] = w;
+    E.out[(int64_t)i * E.ldo + j] = w;
+    if (MIRROR_INLINE && E.mirror && i != j) E.out[(int64_t)j * E.ldo + i] = w;
     return w;
   } else if (EPI == EPI_ACCUM) {
-    E.out[i * E.ldo + j] += v;
+    E.out[(int64_t)i * E.ldo + j] += v;
     return v;
   } else if (EPI == EPI_DIFFCOR) {
     if (j > i) {
@@ -117,7 +132,7 @@ __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R,
     }
     return v;
   } else {  // EPI_TOM
-    const double a = E.A[i * E.p + j];
+    const double a = E.A[(int64_t)i * E.p + j];
     const double absa = fabs(a);
     const double shared = v - a * (R.d_i + E.dvec[j]);
     const double mk = fmin(R.k_i, E.kvec[j]);
@@ -126,8 +141,8 @@ __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R,
     if (E.tom_packed) {
       if (j > i) E.out[R.ro + j] = tom;
     } else if (!(E.mirror && j < i)) {
-      E.out[i * E.ldo + j] = tom;
-      if (MIRROR_INLINE && E.mirror && i != j) E.out[j * E.ldo + i] = tom;
+      E.out[(int64_t)i * E.ldo + j] = tom;
+      if (MIRROR_INLINE && E.mirror && i != j) E.out[(int64_t)j * E.ldo + i] = tom;
     }
     return tom;
   }
@@ -141,8 +156,8 @@ __device__ __forceinline__ bool epi_wants_mirror(const EpiParams& E) {
   return false;
 }
 
-__device__ __forceinline__ void epi_mirror(const EpiParams& E, int64_t i, int64_t j, double w) {
-  if (j > i) E.out[j * E.ldo + i] = w;
+__device__ __forceinline__ void epi_mirror(const EpiParams& E, int i, int j, double w) {
+  if (j > i) E.out[(int64_t)j * E.ldo + i] = w;
 }
 
 }  // namespace bixcor

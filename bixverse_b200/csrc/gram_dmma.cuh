@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(threads_of<CFG>(), Shape<CFG>::MIN_CTAS) gram_
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int64_t j = col0 + wn * WTN + nt * 8 + 2 * t + e;
-            if (j < p) epi_store<EPI>(E, R, j, acc[mt][nt][e], pass);
+            const int j = col0 + wn * WTN + nt * 8 + 2 * t + e;
+            if (j < P.p) epi_store<EPI>(E, R, j, acc[mt][nt][e], pass);
           }
       }
 #pragma unroll

@@ -18,8 +18,9 @@
 //   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1 (M=128, N=128) with
 //            shared-memory descriptors; tcgen05.commit releases smem stages / publishes accumulators
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 16 columns, fused epilogue (epilogue.cuh), direct
-//            stores into the packed triangular layout
+//   warps 4-11 epilogue (two per scheduler): drain the accumulators with tcgen05.ld into registers
+//            (releasing TMEM to the MMA warp at once), then run the fused epilogue (epilogue.cuh)
+//            through a swizzled shared-memory transpose so stores are contiguous row runs
 #pragma once
 
 #include <cuda.h>
@@ -37,9 +38,11 @@ constexpr int ROW_BYTES = 128;                    // one SWIZZLE_128B row: 32 tf
 constexpr int PLANE_TILE_BYTES = BM * ROW_BYTES;  // 16 KB
 constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;  // A hi, A lo, B hi, B lo
 constexpr int STAGES = 3;
-constexpr int THREADS = 256;
-constexpr int STAGE_LD = 33;                                  // doubles per staged row (odd: conflict-free both ways)
-constexpr int EPI_STAGE_BYTES = 4 * 32 * STAGE_LD * 8;        // one 32 x 32 double transpose buffer per epilogue warp
+constexpr int EPI_WARPS = 8;                                  // two per scheduler: (TMEM lane quarter) x (column half)
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);                // accumulator columns owned by one epilogue warp
+constexpr int EPI_CHUNK = 16;                                 // columns transposed per step
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_CHUNK * 8;  // one 32 x 16 double transpose buffer per warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 struct Params {
@@ -206,7 +209,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -302,28 +305,34 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     }
   } else if (warp >= 4) {
     // ============================ epilogue ================================
-    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may access
+    // Warp e = warp - 4 owns TMEM lanes [32*(e%4), +32) (its hardware lane quarter) and the
+    // accumulator columns [EPI_COLS*(e/4), +EPI_COLS) of every tile.
+    const int ew = (warp - 4) & 3;
+    const int ch = (warp - 4) >> 2;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     const EpiParams& E = P.E;
-    double* stg = epi_stage_all + ew * (32 * STAGE_LD);
+    double* stg = epi_stage_all + (warp - 4) * (32 * EPI_CHUNK);
     const bool want_mirror = epi_wants_mirror<EPI>(E);
+    const int pp = (int)E.p;
+    const int dbg = P.dbg;
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
       const int2 tile = P.tiles[t];
-      const int64_t row_base = (int64_t)tile.x * BM + ew * 32;
-      const int64_t i = row_base + lane;
-      const int64_t col0 = (int64_t)tile.y * BN;
+      const int row_base = tile.x * BM + ew * 32;
+      const int i = row_base + lane;
+      const int col_base = tile.y * BN + ch * EPI_COLS;
       for (int pass = 0; pass < P.npass; ++pass) {
         // ---- drain: TMEM -> registers, chunk by chunk (FP32 round-to-nearest / exact int32 sums)
-        uint32_t racc[BN];
+        uint32_t racc[EPI_COLS];
         const int kb_n = P.kblocks[pass];
         for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
           mbar_wait(tfull_bar(acc_stage), acc_phase);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
+          const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
           if (KIND == KIND_I8) {
 #pragma unroll
-            for (int c = 0; c < BN; c += 16) {
+            for (int c = 0; c < EPI_COLS; c += 16) {
               uint32_t r0[16], r1[16], r2[16];
               tmem_ld16(tacc + c, r0);
               tmem_ld16(tacc + BN + c, r1);
@@ -335,7 +344,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < EPI_COLS; c += 32) {
               uint32_t r0[32];
               tmem_ld32(tacc + c, r0);
               tmem_ld_wait();
@@ -357,10 +366,11 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             acc_phase ^= 1u;
           }
         }
-        // ---- fused epilogue from registers, transposed through shared memory so that every
-        //      store instruction writes one contiguous 256-byte run of a packed row
-        if (P.dbg == 1) continue;
-        const bool row_ok = (P.dbg == 2) ? false : (i < E.p);
+        if (dbg == 1) continue;
+        // ---- fused epilogue from registers.  Each 32 x 16 block is transposed through shared
+        //      memory (XOR-swizzled, conflict free) so that one store instruction writes two
+        //      contiguous 128-byte runs of the packed rows instead of 32 scattered doubles.
+        const bool row_ok = i < pp;
         EpiRow R;
         R.i = i;
         R.ro = 0;
@@ -370,24 +380,27 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           R = epi_row<EPI>(E, i);
           if (KIND == KIND_I8) inv_i = P.inv_norm[pass][i];
         }
+        const int rr = lane >> 4, cc = lane & 15;
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-          // chunks entirely below the diagonal of a diagonal tile hold nothing to store (warp uniform)
-          if (EPI != EPI_ACCUM && tile.x == tile.y && c + 31 < ew * 32 &&
+        for (int c = 0; c < EPI_COLS; c += EPI_CHUNK) {
+          const int jb = col_base + c;
+          // blocks entirely below the diagonal of a diagonal tile hold nothing to store (warp uniform)
+          if (EPI != EPI_ACCUM && jb + EPI_CHUNK - 1 < row_base &&
               (EPI == EPI_PACKED || EPI == EPI_DIFFCOR || want_mirror || (EPI == EPI_TOM && E.tom_packed)))
             continue;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
+          for (int q = 0; q < EPI_CHUNK; ++q) {
             const double v = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
-            stg[lane * STAGE_LD + q] = v;
+            stg[lane * EPI_CHUNK + (q ^ (lane & 15))] = v;
           }
           __syncwarp();
-          const int64_t j = col0 + c + lane;
-          const bool col_ok = j < E.p;
+          const int j = jb + cc;
+          const bool col_ok = j < pp;
           double inv_j = 1.0;
           if (KIND == KIND_I8 && col_ok) inv_j = P.inv_norm[pass][j];
 #pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
+          for (int r2 = 0; r2 < 32; r2 += 2) {
+            const int r = r2 + rr;
             EpiRow Rr;
             Rr.i = row_base + r;
             Rr.ro = __shfl_sync(0xffffffffu, R.ro, r);
@@ -397,20 +410,20 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             } else {
               Rr.k_i = Rr.d_i = 0.0;
             }
-            if (Rr.i < E.p && col_ok && P.dbg != 2) {
-              double v = stg[r * STAGE_LD + lane];
+            if (Rr.i < pp && col_ok && dbg != 2) {
+              double v = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
               if (KIND == KIND_I8) v *= inv_j;
               const double w = epi_store<EPI, false>(E, Rr, j, v, pass);
-              if (want_mirror) stg[r * STAGE_LD + lane] = w;
+              if (want_mirror) stg[r * EPI_CHUNK + (cc ^ (r & 15))] = w;
             }
           }
           __syncwarp();
           if (want_mirror) {  // transposed element: consecutive lanes = consecutive rows i -> coalesced
             if (row_ok) {
 #pragma unroll 4
-              for (int q = 0; q < 32; ++q) {
-                const int64_t jj = col0 + c + q;
-                if (jj < E.p) epi_mirror(E, i, jj, stg[lane * STAGE_LD + q]);
+              for (int q = 0; q < EPI_CHUNK; ++q) {
+                const int jj = jb + q;
+                if (jj < pp) epi_mirror(E, i, jj, stg[lane * EPI_CHUNK + (q ^ (lane & 15))]);
               }
             }
             __syncwarp();

@@ -305,3 +305,27 @@ def test_config2_full_size_properties(api):
     r0, r1 = api.shard_rows(p, True, 8, 5)
     part = api.rs_cor_upper_triangle(x, True, True, beta=6.0, rows=(r0, r1))
     assert np.array_equal(part, got[int(o.packed_offset(r0, p, 1)) : int(o.packed_offset(r1, p, 1))])
+
+
+# ----------------------------------------------------------------------------- several devices in one process
+def test_in_process_multi_device(api):
+    """bixcor_init(n): the packed triangle is split over the process's devices by pair count."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from bixverse_b200.synthetic import synthetic_bulk, synthetic_pair
+
+    x = synthetic_bulk(100, 1500, seed=31)
+    single = api.rs_cor_upper_triangle(x, True, True, beta=3.0)
+    xa, xb = synthetic_pair(60, 70, 700, seed=5)
+    dsingle = api.rs_differential_cor(xa, xb, False)
+    try:
+        api.init(2, 0)
+        multi = api.rs_cor_upper_triangle(x, True, True, beta=3.0)
+        dmulti = api.rs_differential_cor(xa, xb, False)
+    finally:
+        api.init(1, 0)
+    assert np.array_equal(single, multi)
+    for k in dsingle:
+        assert np.array_equal(dsingle[k], dmulti[k], equal_nan=True)
