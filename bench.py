@@ -158,6 +158,11 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+PREC_NAMES = {"f64": "FP64 DMMA (mma.sync) exact path", "i8": "exact-integer Spearman on tcgen05 kind::i8",
+              "tf32": "3xTF32 tcgen05 fast path"}
+DTYPES = {"f64": "f64", "i8": "int8 x int8 -> int32 (exact), f64 epilogue", "tf32": "tf32 x3 -> f32, f64 epilogue"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -176,8 +181,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     api.init(1, local)
-    prec = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3}[args.precision]
+    PREC = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3}
     peaks = load_peaks()
+    steps, warmup = args.steps, max(args.warmup, 3)
 
     n, p = N_SAMPLES, N_GENES
     x_host = make_input()  # identical on every rank (same seed)
@@ -186,96 +192,129 @@ def run_ours(args):
     o0, o1 = packed_offset(r0, p, 1), packed_offset(r1, p, 1)
     my_pairs = o1 - o0
 
-    # ---- HBM-resident arm: inputs already on the device, library runs on torch's current stream
-    x_dev = torch.from_numpy(np.ascontiguousarray(x_host.T)).to(dev)  # p x n row-major == n x p column-major
-    out_dev = torch.empty(max(my_pairs, 1), dtype=torch.float64, device=dev)
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-    _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream, 1))
-    _lib.check(lib.bixcor_dev_set_async(1))
-
-    def step_dev():
-        _lib.check(lib.bixcor_dev_cor_upper_rows(x_dev.data_ptr(), n, p, 1, 1, BETA, prec, r0, r1, out_dev.data_ptr()))
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-    barrier()
-    _lib.check(lib.bixcor_timing_enable(1))
-    launches0 = lib.bixcor_launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_dev()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = lib.bixcor_launch_count() - launches0
-    tm = _lib.last_timing()
-    _lib.check(lib.bixcor_timing_enable(0))
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    ms_step = float(t_ms.item()) / args.steps
-    value = P_total / (ms_step * 1e-3)
+    def allmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- roofline of the dominant kernel (the Gram kernel of this rank)
-    gemm_ms_step = tm["gemm_ms"] / args.steps
-    cols_ms_step = tm["cols_ms"] / args.steps
-    alg_flops = 2.0 * n * my_pairs  # 2n flop per pair, upper-triangle count
-    achieved_tf = alg_flops / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
-    if prec == _lib.PREC_F64:
-        # FP64 tensor peak is not in MEASURED_PEAKS.json: measure cuBLAS DGEMM 8192^3 live
-        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-        best = 1e9
-        for i in range(6):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            torch.matmul(a, b)
-            s1.record()
-            torch.cuda.synchronize(dev)
-            if i:
-                best = min(best, s0.elapsed_time(s1))
-        peak_tf = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
-        peak_note = "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry); nominal 40"
-        del a, b
-    elif prec == _lib.PREC_I8EXACT:
-        peak_tf = 2.0 * peaks["bf16_tflops"]
-        peak_note = f"2 x {peaks['src']} bf16 dense (int8 tensor rate); the kernel issues 4 int8 MMAs per algorithmic flop pair"
-    else:
-        peak_tf = 0.5 * peaks["bf16_tflops"]
-        peak_note = f"0.5 x {peaks['src']} bf16 dense (tf32 tensor rate); the kernel issues 3 tf32 MMAs per algorithmic flop pair"
-    roofline = {"bound": "tensor", "kernel": "gram_dmma_kernel" if prec == _lib.PREC_F64 else "gram_umma_kernel",
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_note,
-                "kernel_ms_per_step": gemm_ms_step, "kernel_share_of_step": gemm_ms_step / ms_step if ms_step else None,
-                "launches_per_step": tm["gemm_launches"] / args.steps,
-                "rank_kernel": {"bound": "hbm", "ms_per_step": cols_ms_step,
-                                "achieved_gbs": (2.0 * 8 * n * p) / (cols_ms_step * 1e-3) / 1e9 if cols_ms_step > 0 else None,
-                                "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]}}
+    def allsum(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- HBM-resident arm: inputs already on the device, the library runs on a torch stream, K steps queued
+    x_dev = torch.from_numpy(np.ascontiguousarray(x_host.T)).to(dev)  # p x n row-major == n x p column-major
+    out_dev = torch.empty(max(my_pairs, 1), dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+
+    fp64_peak = {}
+
+    def dgemm_peak():
+        if "v" not in fp64_peak:
+            a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+            b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+            best = 1e9
+            for i in range(6):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                torch.matmul(a, b)
+                s1.record()
+                torch.cuda.synchronize(dev)
+                if i:
+                    best = min(best, s0.elapsed_time(s1))
+            fp64_peak["v"] = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        return fp64_peak["v"]
+
+    def measure_dev(pname, k_steps):
+        prec = PREC[pname]
+        _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream, 1))
+        _lib.check(lib.bixcor_dev_set_async(1))
+
+        def step():
+            _lib.check(lib.bixcor_dev_cor_upper_rows(x_dev.data_ptr(), n, p, 1, 1, BETA, prec, r0, r1, out_dev.data_ptr()))
+
+        for _ in range(warmup):
+            step()
+        barrier()
+        _lib.check(lib.bixcor_timing_enable(1))
+        launches0 = lib.bixcor_launch_count()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(k_steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = lib.bixcor_launch_count() - launches0
+        tm = _lib.last_timing()
+        _lib.check(lib.bixcor_timing_enable(0))
+        _lib.check(lib.bixcor_dev_set_async(0))
+        _lib.check(lib.bixcor_dev_set_stream(None, 0))
+        ms_step = allmax(ms) / k_steps
+        gemm_ms = tm["gemm_ms"] / k_steps
+        cols_ms = tm["cols_ms"] / k_steps
+        alg_flops = 2.0 * n * my_pairs  # 2n flop per pair, upper-triangle count
+        ach = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        if pname == "f64":
+            peak = dgemm_peak()
+            note = "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry; nominal 40)"
+            mmas = 1
+        elif pname == "i8":
+            peak = 2.0 * peaks["bf16_tflops"]
+            note = f"2 x {peaks['src']} dense bf16 (= int8 tensor rate); the kernel issues 4 int8 MMAs per algorithmic flop pair"
+            mmas = 4
+        else:
+            peak = 0.5 * peaks["bf16_tflops"]
+            note = f"0.5 x {peaks['src']} dense bf16 (= tf32 tensor rate); the kernel issues 3 tf32 MMAs per algorithmic flop pair"
+            mmas = 3
+        out_bytes = 8.0 * my_pairs
+        roof = {"bound": "tensor", "kernel": "gram_dmma_kernel" if pname == "f64" else "gram_umma_kernel",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
+                "peak_source": note, "mma_issue_frac": mmas * ach / peak if peak else None,
+                "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / ms_step if ms_step else None,
+                "launches_per_step": tm["gemm_launches"] / k_steps,
+                "hbm_view": {"algorithmic_bytes": out_bytes + (8.0 if pname == "f64" else (2.0 if pname == "i8" else 8.0)) * 1024 * p,
+                             "achieved_gbs": out_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None,
+                             "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]},
+                "column_kernel": {"kernel": "rank_columns_warp_kernel", "bound": "hbm", "ms_per_step": cols_ms,
+                                  "algorithmic_bytes": 8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0}[pname] * 1024 * p,
+                                  "achieved_gbs": (8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0}[pname] * 1024 * p) / (cols_ms * 1e-3) / 1e9 if cols_ms > 0 else None,
+                                  "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]}}
+        return {"value": P_total / (ms_step * 1e-3), "ms_per_step": ms_step, "roofline": roof, "clocks": clocks,
+                "gpu_launches": int(allsum(launches)), "dtype": DTYPES[pname], "path": PREC_NAMES[pname]}
+
+    primary = args.precision
+    main = measure_dev(primary, steps)
+    paths = {}
+    if not args.no_alt:
+        for alt in ("f64", "i8", "tf32"):
+            if alt != primary:
+                r = measure_dev(alt, max(2, min(steps, 5)))
+                paths[alt] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "path": r["path"],
+                              "roofline_frac": r["roofline"]["frac"], "roofline_achieved": r["roofline"]["achieved"],
+                              "roofline_peak": r["roofline"]["peak"], "kernel_ms_per_step": r["roofline"]["kernel_ms_per_step"]}
 
     # ---- end-to-end arm: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region
-    _lib.check(lib.bixcor_dev_set_async(0))
-    _lib.check(lib.bixcor_dev_set_stream(None, 0))
     del out_dev
     x_pin = torch.from_numpy(np.ascontiguousarray(x_host.T)).pin_memory()
     out_pin = torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
 
     def step_e2e():
-        _lib.check(lib.bixcor_cor_upper_rows(x_pin.data_ptr(), n, p, 1, 1, BETA, prec, r0, r1, out_pin.data_ptr()))
+        _lib.check(lib.bixcor_cor_upper_rows(x_pin.data_ptr(), n, p, 1, 1, BETA, PREC[primary], r0, r1, out_pin.data_ptr()))
 
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(steps, 5))
     for _ in range(2):
         step_e2e()
     barrier()
@@ -283,11 +322,7 @@ def run_ours(args):
     for _ in range(e2e_steps):
         step_e2e()
     torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_val = P_total / (float(t_e.item()) / e2e_steps)
+    e2e_val = P_total / (allmax(time.perf_counter() - t0) / e2e_steps)
     checksum = float(out_pin[: min(my_pairs, 1 << 20)].sum())
 
     # ---- TOM wall time (config 4) as an extra metric, device resident, packed output
@@ -297,26 +332,25 @@ def run_ours(args):
             from bixverse_b200.distributed import DeviceBackend, sharded_tom_from_exp
 
             be = DeviceBackend(dev)
-            tprec = _lib.PREC_TF32X3 if args.precision == "tf32" else _lib.PREC_F64
-            t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)  # warm-up
-            del t_out
-            _lib.check(lib.bixcor_timing_enable(1))
-            barrier()
-            t0 = time.perf_counter()
-            t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)
-            barrier()
-            t_tom = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            ttm = _lib.last_timing()
-            _lib.check(lib.bixcor_timing_enable(0))
-            if world > 1:
-                dist.all_reduce(t_tom, op=dist.ReduceOp.MAX)
-            tom = {"metric": "tom_from_exp_wall_ms", "value": 1e3 * float(t_tom.item()), "unit": "ms",
-                   "config": "config4: signed TOM v1, 20000 genes x 1000 samples, Pearson, beta=6, packed output, HBM resident",
-                   "precision": "tf32x3" if tprec == _lib.PREC_TF32X3 else "f64", "alg_flops": 8.4e12,
-                   "achieved_tflops": 8.4e12 / float(t_tom.item()) / 1e12,
-                   "kernel_ms_rank0": {"gemm": ttm["gemm_ms"], "columns": ttm["cols_ms"], "other": ttm["other_ms"],
-                                       "gemm_launches": ttm["gemm_launches"]}}
-            del t_out
+            tom = {}
+            for tname in (("tf32", "f64") if not args.no_alt else ("tf32",)):
+                tprec = PREC[tname]
+                t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)  # warm-up
+                del t_out
+                _lib.check(lib.bixcor_timing_enable(1))
+                barrier()
+                t0 = time.perf_counter()
+                t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)
+                barrier()
+                t_tom = allmax(time.perf_counter() - t0)
+                ttm = _lib.last_timing()
+                _lib.check(lib.bixcor_timing_enable(0))
+                del t_out
+                tom[tname] = {"metric": "tom_from_exp_wall_ms", "value": 1e3 * t_tom, "unit": "ms", "alg_flops": 8.4e12,
+                              "achieved_tflops": 8.4e12 / t_tom / 1e12,
+                              "kernel_ms_rank0": {"gemm": ttm["gemm_ms"], "columns": ttm["cols_ms"], "other": ttm["other_ms"]}}
+            tom["config"] = ("config4: signed TOM v1 from expression, 20000 genes x 1000 samples, Pearson, beta=6, packed "
+                             "output, HBM resident; slabs exchanged + k all-reduced over NCCL when N > 1")
         except Exception as ex:  # report, do not hide
             tom = {"error": str(ex)}
 
@@ -332,21 +366,21 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"f64": "f64", "i8": "int8->int32 (exact), f64 epilogue", "tf32": "tf32x3->f32"}[args.precision],
-            "data": "synthetic",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": main["dtype"], "data": "synthetic",
             "config": {"workload": "config2: Spearman 20000 genes x 1000 samples + |r|^6, packed upper triangle (shift=1)",
-                       "n_samples": n, "n_genes": p, "beta": BETA, "seed": SEED, "precision": args.precision,
+                       "n_samples": n, "n_genes": p, "beta": BETA, "seed": SEED, "precision": primary, "path": main["path"],
                        "sharding": f"{world} contiguous block-row ranges balanced by pair count, no collective",
                        "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
-            "clocks": clocks,
+            "clocks": main["clocks"],
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(8 * n * p),
                     "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps,
                     "note": "bixcor_cor_upper_rows through the C ABI with pinned host buffers; per-rank bytes"},
-            "gpu_launches": int(lt.item()),
-            "roofline": roofline,
+            "gpu_launches": main["gpu_launches"],
+            "roofline": main["roofline"],
             "cpu_baseline": cpu_baseline,
+            "paths": paths,
             "tom": tom,
             "checksum": checksum,
         }
@@ -363,7 +397,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "f64"), choices=["f64", "i8", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "i8"), choices=["f64", "i8", "tf32"],
+                    help="Gram path of the headline number: i8 = exact-integer Spearman (default), f64 = FP64 DMMA, tf32 = 3xTF32")
+    ap.add_argument("--no-alt", action="store_true", help="skip the other precision paths and the FP64 TOM")
     ap.add_argument("--no-tom", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

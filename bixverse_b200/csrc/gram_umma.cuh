@@ -316,6 +316,13 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const bool want_mirror = epi_wants_mirror<EPI>(E);
     const int pp = (int)E.p;
     const int dbg = P.dbg;
+    // loop invariants pulled out of the constant bank once
+    double* const out = E.out;
+    const int64_t ldo = E.ldo;
+    const int shift = E.shift;
+    const int diag_one = E.diag_one;
+    const int keep_sign = E.keep_sign;
+    const int pw_mode = (E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0);  // 1 identity, 6 = WGCNA default, 0 generic
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
       const int2 tile = P.tiles[t];
       const int row_base = tile.x * BM + ew * 32;
@@ -381,6 +388,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           if (KIND == KIND_I8) inv_i = P.inv_norm[pass][i];
         }
         const int rr = lane >> 4, cc = lane & 15;
+        const double* inv_col = (KIND == KIND_I8) ? P.inv_norm[pass] : nullptr;
 #pragma unroll
         for (int c = 0; c < EPI_COLS; c += EPI_CHUNK) {
           const int jb = col_base + c;
@@ -388,33 +396,71 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           if (EPI != EPI_ACCUM && jb + EPI_CHUNK - 1 < row_base &&
               (EPI == EPI_PACKED || EPI == EPI_DIFFCOR || want_mirror || (EPI == EPI_TOM && E.tom_packed)))
             continue;
+          // phase A (lane = row): finish the Gram value.  All mode decisions are warp uniform and sit
+          // OUTSIDE the element loops, so each loop body is a handful of FP64 instructions.
+          double vals[EPI_CHUNK];
 #pragma unroll
-          for (int q = 0; q < EPI_CHUNK; ++q) {
-            const double v = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
-            stg[lane * EPI_CHUNK + (q ^ (lane & 15))] = v;
+          for (int q = 0; q < EPI_CHUNK; ++q)
+            vals[q] = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
+          if (KIND == KIND_I8) {
+#pragma unroll
+            for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= (jb + q < pp) ? __ldg(inv_col + jb + q) : 0.0;
           }
-          __syncwarp();
-          const int j = jb + cc;
-          const bool col_ok = j < pp;
-          double inv_j = 1.0;
-          if (KIND == KIND_I8 && col_ok) inv_j = P.inv_norm[pass][j];
-#pragma unroll 4
-          for (int r2 = 0; r2 < 32; r2 += 2) {
-            const int r = r2 + rr;
-            EpiRow Rr;
-            Rr.i = row_base + r;
-            Rr.ro = __shfl_sync(0xffffffffu, R.ro, r);
-            if (EPI == EPI_TOM) {
-              Rr.k_i = __shfl_sync(0xffffffffu, R.k_i, r);
-              Rr.d_i = __shfl_sync(0xffffffffu, R.d_i, r);
-            } else {
-              Rr.k_i = Rr.d_i = 0.0;
+          if (EPI == EPI_PACKED || EPI == EPI_DENSE) {
+            if (pw_mode == 6) {
+#pragma unroll
+              for (int q = 0; q < EPI_CHUNK; ++q) {
+                const double sq = vals[q] * vals[q];
+                const double w = sq * sq * sq;
+                vals[q] = keep_sign ? copysign(w, vals[q]) : w;
+              }
+            } else if (pw_mode != 1) {
+#pragma unroll 1
+              for (int q = 0; q < EPI_CHUNK; ++q) vals[q] = epi_power(E, vals[q]);
             }
-            if (Rr.i < pp && col_ok && dbg != 2) {
+          }
+#pragma unroll
+          for (int q = 0; q < EPI_CHUNK; ++q) stg[lane * EPI_CHUNK + (q ^ (lane & 15))] = vals[q];
+          __syncwarp();
+          // phase B (lane = 2 rows x 16 columns): contiguous 128-byte runs per row
+          const int j = jb + cc;
+          const bool col_ok = (j < pp) && (dbg != 2);
+          if (EPI == EPI_PACKED) {
+#pragma unroll 8
+            for (int r2 = 0; r2 < 32; r2 += 2) {
+              const int r = r2 + rr;
+              const int ir = row_base + r;
+              const int64_t ro_r = __shfl_sync(0xffffffffu, R.ro, r);
+              const double v = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
+              if (col_ok && ir < pp && j >= ir + shift) out[ro_r + j] = v;
+            }
+          } else if (EPI == EPI_DENSE) {
+#pragma unroll 8
+            for (int r2 = 0; r2 < 32; r2 += 2) {
+              const int r = r2 + rr;
+              const int ir = row_base + r;
               double v = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
-              if (KIND == KIND_I8) v *= inv_j;
-              const double w = epi_store<EPI, false>(E, Rr, j, v, pass);
-              if (want_mirror) stg[r * EPI_CHUNK + (cc ^ (r & 15))] = w;
+              if (ir == j && diag_one) v = 1.0;
+              if (col_ok && ir < pp && !(want_mirror && j < ir)) out[(int64_t)ir * ldo + j] = v;
+            }
+          } else {
+#pragma unroll 2
+            for (int r2 = 0; r2 < 32; r2 += 2) {
+              const int r = r2 + rr;
+              EpiRow Rr;
+              Rr.i = row_base + r;
+              Rr.ro = __shfl_sync(0xffffffffu, R.ro, r);
+              if (EPI == EPI_TOM) {
+                Rr.k_i = __shfl_sync(0xffffffffu, R.k_i, r);
+                Rr.d_i = __shfl_sync(0xffffffffu, R.d_i, r);
+              } else {
+                Rr.k_i = Rr.d_i = 0.0;
+              }
+              if (Rr.i < pp && col_ok) {
+                const double v = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
+                const double w = epi_store<EPI, false>(E, Rr, j, v, pass);
+                if (want_mirror) stg[r * EPI_CHUNK + (cc ^ (r & 15))] = w;
+              }
             }
           }
           __syncwarp();
@@ -423,7 +469,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll 4
               for (int q = 0; q < EPI_CHUNK; ++q) {
                 const int jj = jb + q;
-                if (jj < pp) epi_mirror(E, i, jj, stg[lane * EPI_CHUNK + (q ^ (lane & 15))]);
+                if (jj < pp && jj > i) out[(int64_t)jj * ldo + i] = stg[lane * EPI_CHUNK + (q ^ (lane & 15))];
               }
             }
             __syncwarp();

@@ -26,11 +26,7 @@ def run(tag, prec, spearman=1, n=1000, p=20000, **env):
     r = subprocess.run([sys.executable, __file__, "child", str(prec), str(spearman), str(n), str(p)], env=e, capture_output=True, text=True, timeout=600)
     print(tag, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ("ERR " + r.stderr[-300:]), flush=True)
 
-for v in (1,):
-    run(f"dmma shape {v}", 0, BIXCOR_DMMA_VARIANT=v)
-for d in (0, 1, 2, 3):
-    run(f"umma i8 dbg {d}", 2, BIXCOR_UMMA_DEBUG=d)
-for d in (0, 1, 2, 3):
-    run(f"umma tf32 dbg {d}", 1, BIXCOR_UMMA_DEBUG=d)
-run("pearson standardise f64", 0, spearman=0)
-run("spearman n=500", 0, n=500)
+probes = sys.argv[1:] or ["i8:0", "i8:1", "i8:2", "i8:3", "tf32:0", "tf32:1"]
+for pr in probes:
+    kind, d = pr.split(":")
+    run(f"umma {kind} dbg {d}", 2 if kind == "i8" else 1, BIXCOR_UMMA_DEBUG=d)
