@@ -406,33 +406,44 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= (jb + q < pp) ? __ldg(inv_col + jb + q) : 0.0;
           }
-          if (EPI == EPI_PACKED || EPI == EPI_DENSE) {
-            if (pw_mode == 6) {
+          if ((EPI == EPI_PACKED || EPI == EPI_DENSE) && pw_mode == 6) {
 #pragma unroll
-              for (int q = 0; q < EPI_CHUNK; ++q) {
-                const double sq = vals[q] * vals[q];
-                const double w = sq * sq * sq;
-                vals[q] = keep_sign ? copysign(w, vals[q]) : w;
-              }
-            } else if (pw_mode != 1) {
-#pragma unroll 1
-              for (int q = 0; q < EPI_CHUNK; ++q) vals[q] = epi_power(E, vals[q]);
+            for (int q = 0; q < EPI_CHUNK; ++q) {
+              const double sq = vals[q] * vals[q];
+              const double w = sq * sq * sq;
+              vals[q] = keep_sign ? copysign(w, vals[q]) : w;
             }
           }
 #pragma unroll
           for (int q = 0; q < EPI_CHUNK; ++q) stg[lane * EPI_CHUNK + (q ^ (lane & 15))] = vals[q];
+          if ((EPI == EPI_PACKED || EPI == EPI_DENSE) && pw_mode == 0) {
+            // generic exponent: transform the staged values in place (keeps vals[] in registers above)
+#pragma unroll 1
+            for (int q = 0; q < EPI_CHUNK; ++q) {
+              double* sp = stg + lane * EPI_CHUNK + (q ^ (lane & 15));
+              *sp = epi_power(E, *sp);
+            }
+          }
           __syncwarp();
-          // phase B (lane = 2 rows x 16 columns): contiguous 128-byte runs per row
+          // phase B (lane = 2 rows x 16 columns): contiguous 128-byte runs per row.  Shuffles and
+          // shared loads are issued for all 16 row pairs before the predicated stores (no branches).
           const int j = jb + cc;
           const bool col_ok = (j < pp) && (dbg != 2);
           if (EPI == EPI_PACKED) {
-#pragma unroll 8
-            for (int r2 = 0; r2 < 32; r2 += 2) {
-              const int r = r2 + rr;
-              const int ir = row_base + r;
-              const int64_t ro_r = __shfl_sync(0xffffffffu, R.ro, r);
-              const double v = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
-              if (col_ok && ir < pp && j >= ir + shift) out[ro_r + j] = v;
+            int64_t ro_r[16];
+            double vv[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+              const int r = 2 * k2 + rr;
+              ro_r[k2] = __shfl_sync(0xffffffffu, R.ro, r);
+              vv[k2] = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+              const int ir = row_base + 2 * k2 + rr;
+              const bool ok = col_ok && (ir < pp) && (j >= ir + shift);
+              double* dst = out + (ro_r[k2] + j);
+              if (ok) *dst = vv[k2];
             }
           } else if (EPI == EPI_DENSE) {
 #pragma unroll 8
