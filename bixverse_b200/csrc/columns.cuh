@@ -336,6 +336,8 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
   // ---- bitonic sort, position s = lane*E + r --------------------------------
   // The merge level k is a RUNTIME loop: the fully unrolled network is ~190 KB of code and
   // is instruction-fetch bound; this form is one lane-exchange body plus log2(E) register stages.
+  // Compare-exchanges are inline setp/selp (ptxas otherwise turns the selects into branches); a
+  // descending exchange is the ascending one on keys XORed with all-ones.
 #pragma unroll 1
   for (int k = 2; k <= NP; k <<= 1) {
     const bool up_lane = ((lane * E) & k) == 0;  // direction bit when it is a lane bit (k >= E)
@@ -343,13 +345,18 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
     for (int jj = k >> 1; jj >= E; jj >>= 1) {
       const int lm = jj / E;  // partner lane = lane ^ lm
       const bool keep_min = ((lane & lm) == 0) == up_lane;
+      const uint64_t flip = keep_min ? 0ull : ~0ull;
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
         const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
-        const bool take = keep_min ? (ok < key[r]) : (ok > key[r]);
-        key[r] = take ? ok : key[r];  // selects, not branches
-        idx[r] = take ? oi : idx[r];
+        // take the partner's element iff it is strictly better in this lane's direction
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.lt.u64 p, %4, %5;\n\t"
+            "selp.b64 %0, %2, %0, p;\n\t"
+            "selp.b32 %1, %3, %1, p;\n\t}"
+            : "+l"(key[r]), "+r"(idx[r])
+            : "l"(ok), "r"(oi), "l"(ok ^ flip), "l"(key[r] ^ flip));
       }
     }
 #pragma unroll
@@ -360,13 +367,18 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
           if ((r & jj) == 0) {
             const int l = r | jj;
             const bool up = (k < E) ? ((r & k) == 0) : up_lane;
+            const uint64_t flip = up ? 0ull : ~0ull;
             const uint64_t ka = key[r], kb = key[l];
             const uint32_t ia = idx[r], ib = idx[l];
-            const bool sw = (ka > kb) == up;  // equal keys may swap: harmless inside one thread
-            key[r] = sw ? kb : ka;            // selects, not branches
-            key[l] = sw ? ka : kb;
-            idx[r] = sw ? ib : ia;
-            idx[l] = sw ? ia : ib;
+            // swap iff (ka > kb) in the stage direction; equal keys never swap
+            asm("{\n\t.reg .pred p;\n\t"
+                "setp.gt.u64 p, %8, %9;\n\t"
+                "selp.b64 %0, %5, %4, p;\n\t"
+                "selp.b64 %1, %4, %5, p;\n\t"
+                "selp.b32 %2, %7, %6, p;\n\t"
+                "selp.b32 %3, %6, %7, p;\n\t}"
+                : "=l"(key[r]), "=l"(key[l]), "=r"(idx[r]), "=r"(idx[l])
+                : "l"(ka), "l"(kb), "r"(ia), "r"(ib), "l"(ka ^ flip), "l"(kb ^ flip));
           }
         }
       }
