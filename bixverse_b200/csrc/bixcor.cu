@@ -332,49 +332,74 @@ static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, c
   return BIXCOR_OK;
 }
 
-// d_x: device n x p column-major.  Builds the operand in ctx slot `slot`.
-static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int slot,
-                           Operand* op) {
+static int64_t operand_row_bytes(int64_t n, int precision) {
+  const int64_t K = round_up((int)n, k_padding(precision));
+  return precision == BIXCOR_PREC_F64 ? 8 * K : (precision == BIXCOR_PREC_I8EXACT ? 2 * K : 8 * K);
+}
+
+// Gene-major operand layout (one contiguous record per gene, so gene slabs built on different
+// ranks can be all-gathered):  F64 [K f64] | I8EXACT [K int8 h][K int8 l] | TF32X3 [K f32 hi][K f32 lo].
+static void bind_operand(Operand* op, int64_t n, int64_t p, int precision, const void* base, const double* inv) {
+  op->precision = precision;
+  op->K = round_up((int)n, k_padding(precision));
+  op->p = p;
+  op->z64 = nullptr;
+  op->i8 = nullptr;
+  op->f32 = nullptr;
+  op->inv_norm = inv;
+  if (precision == BIXCOR_PREC_F64) op->z64 = (const double*)base;
+  else if (precision == BIXCOR_PREC_I8EXACT) op->i8 = (const int8_t*)base;
+  else op->f32 = (const float*)base;
+}
+
+// d_x: device n x p column-major.  Writes the operand records of genes [g0, g1) into `dst`
+// (base pointer of the full p-gene operand) and their 1/|d| into inv (I8EXACT).
+static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int64_t g0,
+                         int64_t g1, void* dst, double* inv) {
   if (n < 2) return fail(BIXCOR_ERR_INVALID, "need at least 2 samples (n = %lld)", (long long)n);
   if (n > (spearman ? 16384 : (1 << 30)))
     return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman rank kernel supports n <= 16384 samples (got %lld)", (long long)n);
   RC_TRY(check_precision(precision, spearman, n));
+  if (g0 < 0 || g1 > p || g0 > g1) return fail(BIXCOR_ERR_INVALID, "bad gene range");
+  if (g0 == g1) return BIXCOR_OK;
   const int K = round_up((int)n, k_padding(precision));
   ColumnOut co;
   memset(&co, 0, sizeof co);
   co.kpad = K;
-  op->precision = precision;
-  op->K = K;
-  op->p = p;
   if (precision == BIXCOR_PREC_F64) {
-    RC_TRY(c->op[slot].reserve(sizeof(double) * (size_t)K * p));
     co.mode = COL_Z64;
-    co.f64 = (double*)c->op[slot].ptr;
+    co.f64 = (double*)dst + g0 * K;
     co.ld64 = K;
-    op->z64 = co.f64;
   } else if (precision == BIXCOR_PREC_I8EXACT) {
-    RC_TRY(c->op[slot].reserve((size_t)2 * K * p));
-    RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
     co.mode = COL_I8;
-    co.i8 = (int8_t*)c->op[slot].ptr;
-    co.ld8 = K;
-    co.plane8 = (int64_t)K * p;
-    co.inv_norm = (double*)c->aux[slot].ptr;
-    op->i8 = co.i8;
-    op->inv_norm = co.inv_norm;
+    co.i8 = (int8_t*)dst + g0 * 2 * K;
+    co.ld8 = 2 * K;
+    co.plane8 = K;
+    co.inv_norm = inv + g0;
   } else {
-    RC_TRY(c->op[slot].reserve(sizeof(float) * 2 * (size_t)K * p));
     co.mode = COL_TF32;
-    co.f32 = (float*)c->op[slot].ptr;
-    co.ld32 = K;
-    co.plane32 = (int64_t)K * p;
-    op->f32 = co.f32;
+    co.f32 = (float*)dst + g0 * 2 * K;
+    co.ld32 = 2 * K;
+    co.plane32 = K;
   }
+  const double* xs = d_x + g0 * n;
+  const int64_t cnt = g1 - g0;
   Timed tm(c, T_COLS);
-  if (spearman) return launch_rank_kernel(c, d_x, n, p, co);
-  standardise_columns_kernel<<<(unsigned)p, 128, 0, c->compute>>>(d_x, n, (int)n, co);
+  if (spearman) return launch_rank_kernel(c, xs, n, cnt, co);
+  standardise_columns_kernel<<<(unsigned)cnt, 128, 0, c->compute>>>(xs, n, (int)n, co);
   g_launches++;
   CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
+// Builds the full operand in ctx slot `slot`.
+static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int slot,
+                           Operand* op) {
+  RC_TRY(check_precision(precision, spearman, n));
+  RC_TRY(c->op[slot].reserve((size_t)operand_row_bytes(n, precision) * p));
+  RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
+  RC_TRY(build_operand(c, d_x, n, p, spearman, precision, 0, p, c->op[slot].ptr, (double*)c->aux[slot].ptr));
+  bind_operand(op, n, p, precision, c->op[slot].ptr, (const double*)c->aux[slot].ptr);
   return BIXCOR_OK;
 }
 
@@ -578,13 +603,8 @@ static int validate_rows(int64_t p, int64_t row_begin, int64_t row_end) {
 
 // Packed correlation of rows [row_begin,row_end).  If `pipe` is given, every
 // finished band is copied to h_out (host slice) while later bands compute.
-static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
-                              int precision, int64_t row_begin, int64_t row_end, double* d_out, D2HPipe* pipe,
-                              double* h_out) {
-  RC_TRY(validate_rows(p, row_begin, row_end));
-  if (row_begin == row_end) return BIXCOR_OK;
-  Operand op;
-  RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
+static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift, double beta, int64_t row_begin,
+                                 int64_t row_end, double* d_out, D2HPipe* pipe, double* h_out) {
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
   EpiParams e = make_epi(p);
@@ -598,15 +618,23 @@ static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, i
   for (int g = 0; g < ngroups; ++g) {
     const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
     RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e));
-    if (pipe) {
-      cudaEvent_t ev = ctx_event(c);
-      CU_TRY(cudaEventRecord(ev, c->compute));
-      const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - e.out_base;
-      const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - e.out_base;
-      RC_TRY(pipe->push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev));
-    }
+    cudaEvent_t ev = ctx_event(c);
+    CU_TRY(cudaEventRecord(ev, c->compute));
+    const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - e.out_base;
+    const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - e.out_base;
+    RC_TRY(pipe->push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev));
   }
   return BIXCOR_OK;
+}
+
+static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                              int precision, int64_t row_begin, int64_t row_end, double* d_out, D2HPipe* pipe,
+                              double* h_out) {
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (row_begin == row_end) return BIXCOR_OK;
+  Operand op;
+  RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
+  return dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, d_out, pipe, h_out);
 }
 
 static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
@@ -721,8 +749,8 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
     co.mode = COL_TF32;
     co.kpad = K;
     co.f32 = (float*)c->op[1].ptr;
-    co.ld32 = K;
-    co.plane32 = (int64_t)K * p;
+    co.ld32 = 2 * K;
+    co.plane32 = K;
     Timed tm(c, T_COLS);
     split_tf32_kernel<<<(unsigned)p, 256, 0, c->compute>>>(d_a, p, (int)p, co);
     g_launches++;
@@ -1021,6 +1049,31 @@ int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spear
   DEV_PROLOGUE();
   RC_TRY(dev_cor_upper_rows(c, d_x, n, p, spearman, shift ? 1 : 0, beta, precision, row_begin, row_end, d_out, nullptr,
                             nullptr));
+  return finish_dev(c);
+}
+
+int64_t bixcor_dev_operand_row_bytes(int64_t n, int precision) {
+  if (n < 1 || precision < 0 || precision > 2) return -1;
+  return operand_row_bytes(n, precision);
+}
+
+int bixcor_dev_build_operand(const double* d_x, int64_t n, int64_t p, int spearman, int precision, int64_t gene_begin,
+                             int64_t gene_end, void* d_operand, double* d_inv_norm) {
+  DEV_PROLOGUE();
+  RC_TRY(build_operand(c, d_x, n, p, spearman, precision, gene_begin, gene_end, d_operand, d_inv_norm));
+  return finish_dev(c);
+}
+
+int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p, int precision,
+                                 int shift, double beta, int64_t row_begin, int64_t row_end, double* d_out) {
+  DEV_PROLOGUE();
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (precision < 0 || precision > 2) return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
+  if (row_begin < row_end) {
+    Operand op;
+    bind_operand(&op, n, p, precision, d_operand, d_inv_norm);
+    RC_TRY(dev_cor_upper_rows_op(c, op, p, shift ? 1 : 0, beta, row_begin, row_end, d_out, nullptr, nullptr));
+  }
   return finish_dev(c);
 }
 

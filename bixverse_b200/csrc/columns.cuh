@@ -377,7 +377,7 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
                 "selp.b64 %1, %4, %5, p;\n\t"
                 "selp.b32 %2, %7, %6, p;\n\t"
                 "selp.b32 %3, %6, %7, p;\n\t}"
-                : "=l"(key[r]), "=l"(key[l]), "=r"(idx[r]), "=r"(idx[l])
+                : "=&l"(key[r]), "=&l"(key[l]), "=&r"(idx[r]), "=&r"(idx[l])
                 : "l"(ka), "l"(kb), "r"(ia), "r"(ib), "l"(ka ^ flip), "l"(kb ^ flip));
           }
         }

@@ -238,10 +238,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
             const uint32_t s0 = base + stage * STAGE_BYTES;
-            tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.x * BM, 0);
-            tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.x * BM, 1);
-            tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.y * BN, 0);
-            tma_load_3d(s0 + 3 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, tile.y * BN, 1);
+            tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.x * BM);
+            tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.x * BM);
+            tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.y * BN);
+            tma_load_3d(s0 + 3 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.y * BN);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -521,8 +521,8 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 3-D map over [plane][row][K]: dims (K, rows, 2), box (128 bytes of K, 128 rows, 1 plane), SWIZZLE_128B,
-// out-of-range rows are zero filled (ragged last tile).
+// 3-D map over the gene-major operand [row][plane][K]: dims (K, 2 planes, rows), box (128 bytes of K,
+// 1 plane, 128 rows), SWIZZLE_128B; out-of-range rows are zero filled (ragged last tile).
 inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, int K) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
@@ -530,9 +530,9 @@ inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, i
     return -1;
   }
   const int es = kind == KIND_TF32 ? 4 : 1;
-  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
-  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)BM, 1};
+  cuuint64_t dims[3] = {(cuuint64_t)K, 2, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * 2};
+  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), 1, (cuuint32_t)BM};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -563,7 +563,7 @@ inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, 
   return 0;
 }
 
-// operand set s: planes pointer (2 planes, [plane][rows][K]), K elements (padded), inv_norm (KIND_I8)
+// operand set s: gene-major digit planes ([row][plane][K]), K elements (padded), inv_norm (KIND_I8)
 inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int64_t rows, const void* planes0,
                             int K0, const double* inv0, const void* planes1, int K1, const double* inv1,
                             const int2* tiles, int ntiles, const EpiParams& E) {

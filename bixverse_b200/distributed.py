@@ -69,6 +69,25 @@ class DeviceBackend:
                                                  r0, r1, out.data_ptr()))
         return out
 
+    def operand_row_bytes(self, n, precision):
+        return int(self.lib.bixcor_dev_operand_row_bytes(n, precision))
+
+    def empty_bytes(self, nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def build_operand(self, x, n, p, spearman, precision, g0, g1, operand, inv_norm):
+        self._sync_in()
+        check(self.lib.bixcor_dev_build_operand(x.data_ptr(), n, p, int(spearman), precision, g0, g1,
+                                                operand.data_ptr(), inv_norm.data_ptr()))
+
+    def cor_upper_rows_op(self, operand, inv_norm, n, p, precision, shift, beta, r0, r1):
+        ln = packed_offset(r1, p, shift) - packed_offset(r0, p, shift)
+        out = self.empty(max(ln, 1))[:ln]
+        self._sync_in()
+        check(self.lib.bixcor_dev_cor_upper_rows_op(operand.data_ptr(), inv_norm.data_ptr(), n, p, precision, int(shift),
+                                                    float(beta), r0, r1, out.data_ptr()))
+        return out
+
     def diffcor_rows(self, xa, na, xb, nb, p, spearman, precision, r0, r1):
         ln = packed_offset(r1, p, 1) - packed_offset(r0, p, 1)
         outs = [self.empty(max(ln, 1))[:ln] for _ in range(4)]
@@ -113,11 +132,39 @@ def _world(group=None) -> tuple[int, int]:
     return 0, 1
 
 
+def gene_slab(p: int, world: int) -> int:
+    """Equal 128-aligned gene slab width of the operand exchange (the last slab may be ragged)."""
+    return ((p + world - 1) // world + TILE - 1) // TILE * TILE
+
+
+def exchange_operand(backend, x, n, p, spearman, precision, group=None):
+    """Every rank rank-transforms / standardises only its gene slab; the gene-major operand records
+    (and the per-gene norms) are all-gathered, so the column kernel scales with the number of GPUs."""
+    rank, world = _world(group)
+    slab = gene_slab(p, world)
+    rb = backend.operand_row_bytes(n, precision)
+    operand = backend.empty_bytes(world * slab * rb)
+    inv = backend.zeros(world * slab)
+    g0, g1 = min(p, rank * slab), min(p, (rank + 1) * slab)
+    backend.build_operand(x, n, p, spearman, precision, g0, g1, operand, inv)
+    if world > 1:
+        dist.all_gather_into_tensor(operand, operand[rank * slab * rb : (rank + 1) * slab * rb], group=group)
+        dist.all_gather_into_tensor(inv, inv[rank * slab : (rank + 1) * slab], group=group)
+    return operand, inv
+
+
 def sharded_cor_upper(backend, x, n, p, spearman, shift=1, beta=1.0, precision=PREC_F64, group=None):
-    """Rank-local slice of the packed correlation vector and its [o0,o1) range."""
+    """Rank-local slice of the packed correlation vector and its [o0,o1) range.
+
+    world == 1: one fused call.  world > 1: gene-sharded column kernel + operand all-gather over
+    NCCL, then the pair-balanced block rows of the Gram (no further collective)."""
     rank, world = _world(group)
     r0, r1 = pair_balanced_rows(p, shift, world, rank)
-    out = backend.cor_upper_rows(x, n, p, spearman, shift, beta, precision, r0, r1)
+    if world == 1:
+        out = backend.cor_upper_rows(x, n, p, spearman, shift, beta, precision, r0, r1)
+    else:
+        operand, inv = exchange_operand(backend, x, n, p, spearman, precision, group)
+        out = backend.cor_upper_rows_op(operand, inv, n, p, precision, shift, beta, r0, r1)
     return out, (packed_offset(r0, p, shift), packed_offset(r1, p, shift))
 
 

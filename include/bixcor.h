@@ -127,6 +127,16 @@ int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const 
 int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_out_np);
 int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
                               int precision, int64_t row_begin, int64_t row_end, double* d_out_slice);
+/* Operand exchange for multi-process drivers.  The Gram operand (standardised columns, TF32 hi/lo or
+ * int8 digit planes) is gene-major: bixcor_dev_operand_row_bytes(n, precision) contiguous bytes per gene,
+ * so a gene slab is one contiguous range that ranks can build independently and all-gather over NVLink.
+ * d_operand / d_inv_norm (p doubles, written for BIXCOR_PREC_I8EXACT) are base pointers of the full buffers. */
+int64_t bixcor_dev_operand_row_bytes(int64_t n, int precision);
+int bixcor_dev_build_operand(const double* d_x, int64_t n, int64_t p, int spearman, int precision,
+                             int64_t gene_begin, int64_t gene_end, void* d_operand, double* d_inv_norm);
+int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
+                                 int precision, int shift, double beta, int64_t row_begin, int64_t row_end,
+                                 double* d_out_slice);
 int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out_pp);
 int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
                             int spearman, int precision, int64_t row_begin, int64_t row_end, double* d_r_a,

@@ -22,6 +22,26 @@ class OracleBackend:
         full = o.soft_threshold(o.cor_upper_triangle(x.numpy().T, spearman, bool(shift)), beta)
         return torch.from_numpy(np.ascontiguousarray(self._slice(full, p, shift, r0, r1)))
 
+    # operand exchange: the stand-in operand record of a gene is its standardised column (n doubles)
+    def operand_row_bytes(self, n, precision):
+        return 8 * n
+
+    def empty_bytes(self, nbytes):
+        return torch.zeros(nbytes, dtype=torch.uint8)
+
+    def build_operand(self, x, n, p, spearman, precision, g0, g1, operand, inv_norm):
+        xs = x.numpy()[g0:g1].T  # n x (g1-g0)
+        z = o._standardise(o.rank_matrix_col(xs) if spearman else xs)
+        view = operand.numpy().view(np.float64).reshape(-1, n)
+        view[g0:g1] = z.T
+        inv_norm[g0:g1] = 1.0
+
+    def cor_upper_rows_op(self, operand, inv_norm, n, p, precision, shift, beta, r0, r1):
+        z = operand.numpy().view(np.float64).reshape(-1, n)[:p].T
+        assert float(inv_norm[:p].sum()) == p  # every slab arrived
+        full = o.soft_threshold(o.dense_to_upper_triangle(z.T @ z, bool(shift)), beta)
+        return torch.from_numpy(np.ascontiguousarray(self._slice(full, p, shift, r0, r1)))
+
     def diffcor_rows(self, xa, na, xb, nb, p, spearman, precision, r0, r1):
         res = o.differential_cor(xa.numpy().T, xb.numpy().T, spearman)
         return {k: torch.from_numpy(np.ascontiguousarray(self._slice(v, p, 1, r0, r1))) for k, v in res.items()}

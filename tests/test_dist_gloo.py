@@ -29,7 +29,7 @@ def _worker(rank, world, port, tmpdir):
         # --- bulk correlation: contiguous, disjoint, complete packed ranges
         sl, (o0, o1) = D.sharded_cor_upper(be, xt, n, p, True, 1, 6.0)
         full = o.soft_threshold(o.cor_upper_triangle(x, True, True), 6.0)
-        assert np.array_equal(sl.numpy(), full[o0:o1])
+        assert np.abs(sl.numpy() - full[o0:o1]).max() < 1e-14  # gene-sharded ranks + operand all-gather
         rng = [None] * world
         dist.all_gather_object(rng, (o0, o1))
         assert rng[0][0] == 0 and rng[-1][1] == full.shape[0] and all(a[1] == b[0] for a, b in zip(rng[:-1], rng[1:]))
