@@ -40,6 +40,10 @@ SIGNATURES = {
     "bixcor_diffcor_rows": (i32, [ptr, i64, ptr, i64, i64, i32, i32, i64, i64, ptr, ptr, ptr, ptr]),
     "bixcor_tom": (i32, [ptr, i64, i32, i32, i32, ptr]),
     "bixcor_tom_from_exp": (i32, [ptr, i64, i64, i32, i32, i32, f64, i32, i32, ptr]),
+    "bixcor_covariance": (i32, [ptr, i64, i64, ptr]),
+    "bixcor_cos": (i32, [ptr, i64, i64, ptr]),
+    "bixcor_cor2": (i32, [ptr, i64, i64, ptr, i64, i32, ptr]),
+    "bixcor_cov2cor": (i32, [ptr, i64, ptr]),
     "bixcor_sparse_gram_cor": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr]),
     "bixcor_dev_rank_columns": (i32, [ptr, i64, i64, ptr]),
     "bixcor_dev_cor_upper_rows": (i32, [ptr, i64, i64, i32, i32, f64, i32, i64, i64, ptr]),

@@ -33,7 +33,7 @@ from . import _lib
 from ._lib import PREC_F64, PREC_I8EXACT, PREC_TF32X3, TOM_V1, TOM_V2, BixcorError, check
 
 __all__ = [
-    "rs_cor", "rs_cor_upper_triangle", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
+    "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
     "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "calculate_tom", "calculate_tom_from_exp",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
     "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "BixcorError",
@@ -84,6 +84,44 @@ def rs_cor(x, spearman: bool, precision: int = PREC_F64) -> np.ndarray:
     n, p = a.shape
     out = np.empty((p, p), dtype=np.float64, order="F")
     check(_lib.load().bixcor_cor_dense(_p(a), n, p, int(bool(spearman)), precision, _p(out)))
+    return out
+
+
+def rs_covariance(x) -> np.ndarray:
+    """src/rust/src/base/r_cors_similarity.rs:49-55 (== base R cov)."""
+    a = _fmat(x)
+    n, p = a.shape
+    out = np.empty((p, p), dtype=np.float64, order="F")
+    check(_lib.load().bixcor_covariance(_p(a), n, p, _p(out)))
+    return out
+
+
+def rs_cos(x) -> np.ndarray:
+    """src/rust/src/base/r_cors_similarity.rs:90-97."""
+    a = _fmat(x)
+    n, p = a.shape
+    out = np.empty((p, p), dtype=np.float64, order="F")
+    check(_lib.load().bixcor_cos(_p(a), n, p, _p(out)))
+    return out
+
+
+def rs_cor2(x, y, spearman: bool) -> np.ndarray:
+    """src/rust/src/base/r_cors_similarity.rs:114-122 (== base R cor(x, y)); rows must match."""
+    a, b = _fmat(x), _fmat(y, "y")
+    if a.shape[0] != b.shape[0]:
+        raise ValueError("x and y need the same number of rows")
+    out = np.empty((a.shape[1], b.shape[1]), dtype=np.float64, order="F")
+    check(_lib.load().bixcor_cor2(_p(a), a.shape[0], a.shape[1], _p(b), b.shape[1], int(bool(spearman)), _p(out)))
+    return out
+
+
+def rs_cov2cor(x) -> np.ndarray:
+    """src/rust/src/base/r_cors_similarity.rs:135-142."""
+    a = _fmat(x)
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("x must be a square covariance matrix")
+    out = np.empty(a.shape, dtype=np.float64, order="F")
+    check(_lib.load().bixcor_cov2cor(_p(a), a.shape[0], _p(out)))
     return out
 
 

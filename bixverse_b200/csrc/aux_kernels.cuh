@@ -30,6 +30,15 @@ __global__ void extract_diag_kernel(const double* __restrict__ a, int64_t p, dou
   if (i < p) d[i] = a[i * p + i];
 }
 
+// rs_cov2cor (src/rust/src/base/r_cors_similarity.rs:135-142): r_ij = c_ij / sqrt(c_ii c_jj), column-major.
+__global__ void __launch_bounds__(256)
+cov2cor_kernel(const double* __restrict__ cov, int64_t p, double* __restrict__ out) {
+  const int64_t j = blockIdx.y;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  out[i + j * p] = cov[i + j * p] / sqrt(cov[i + i * p] * cov[j + j * p]);
+}
+
 __global__ void fill_kernel(double* __restrict__ x, int64_t n, double v) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;

@@ -355,7 +355,7 @@ static void bind_operand(Operand* op, int64_t n, int64_t p, int precision, const
 // d_x: device n x p column-major.  Writes the operand records of genes [g0, g1) into `dst`
 // (base pointer of the full p-gene operand) and their 1/|d| into inv (I8EXACT).
 static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int64_t g0,
-                         int64_t g1, void* dst, double* inv) {
+                         int64_t g1, void* dst, double* inv, int norm_mode = 0) {
   if (n < 2) return fail(BIXCOR_ERR_INVALID, "need at least 2 samples (n = %lld)", (long long)n);
   if (n > (spearman ? 16384 : (1 << 30)))
     return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman rank kernel supports n <= 16384 samples (got %lld)", (long long)n);
@@ -386,7 +386,7 @@ static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int sp
   const int64_t cnt = g1 - g0;
   Timed tm(c, T_COLS);
   if (spearman) return launch_rank_kernel(c, xs, n, cnt, co);
-  standardise_columns_kernel<<<(unsigned)cnt, 128, 0, c->compute>>>(xs, n, (int)n, co);
+  standardise_columns_kernel<<<(unsigned)cnt, 128, 0, c->compute>>>(xs, n, (int)n, co, norm_mode);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return BIXCOR_OK;
@@ -394,11 +394,11 @@ static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int sp
 
 // Builds the full operand in ctx slot `slot`.
 static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int slot,
-                           Operand* op) {
+                           Operand* op, int norm_mode = 0) {
   RC_TRY(check_precision(precision, spearman, n));
   RC_TRY(c->op[slot].reserve((size_t)operand_row_bytes(n, precision) * p));
   RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
-  RC_TRY(build_operand(c, d_x, n, p, spearman, precision, 0, p, c->op[slot].ptr, (double*)c->aux[slot].ptr));
+  RC_TRY(build_operand(c, d_x, n, p, spearman, precision, 0, p, c->op[slot].ptr, (double*)c->aux[slot].ptr, norm_mode));
   bind_operand(op, n, p, precision, c->op[slot].ptr, (const double*)c->aux[slot].ptr);
   return BIXCOR_OK;
 }
@@ -435,6 +435,7 @@ static EpiParams make_epi(int64_t p) {
   e.p = p;
   e.shift = 1;
   e.beta = 1.0;
+  e.scale = 1.0;
   return e;
 }
 
@@ -446,12 +447,19 @@ static void set_beta(EpiParams& e, double beta, int keep_sign) {
 }
 
 static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, const int2* tiles, int ntiles, int epi,
-                       const EpiParams& e) {
+                       const EpiParams& e, const Operand* cols = nullptr) {
   if (ntiles <= 0) return BIXCOR_OK;
+  if (cols && a.precision != BIXCOR_PREC_F64)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "two-matrix correlation runs on the FP64 path only");
   if (a.precision == BIXCOR_PREC_F64) {
     dmma::Params P;
     memset(&P, 0, sizeof P);
     P.R0 = P.C0 = a.z64;
+    P.pc = (int)p;
+    if (cols) {
+      P.C0 = cols->z64;
+      P.pc = (int)cols->p;
+    }
     P.ld0 = a.K;
     P.K0 = a.K;
     if (b) {
@@ -1297,6 +1305,99 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
                       (double*)c->out2.ptr));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, packed, out);
+}
+
+// ---- sibling Gram kernels ("next" rows of SURVEY 8f) ---------------------------------------------
+static int dense_symmetric(const double* x, int64_t n, int64_t p, int norm_mode, double scale, int diag_one,
+                           double* out_pp) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out_pp));
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t in_bytes = sizeof(double) * (size_t)n * p, out_bytes = sizeof(double) * (size_t)p * p;
+  RC_TRY(c->x[0].reserve(in_bytes));
+  RC_TRY(c->out.reserve(out_bytes));
+  RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
+  Operand op;
+  RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, n, p, 0, BIXCOR_PREC_F64, 0, &op, norm_mode));
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, 0, p, 1, 8, &tl));
+  EpiParams e = make_epi(p);
+  e.out = (double*)c->out.ptr;
+  e.ldo = p;
+  e.mirror = 1;
+  e.diag_one = diag_one;
+  e.scale = scale;
+  RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_DENSE, e));
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out_pp);
+  RC_TRY(pipe.push(out_pp, c->out.ptr, out_bytes, nullptr));
+  return pipe.finish();
+}
+
+int bixcor_covariance(const double* x, int64_t n, int64_t p, double* out_pp) {
+  return dense_symmetric(x, n, p, 1, 1.0 / (double)(n - 1), 0, out_pp);
+}
+
+int bixcor_cos(const double* x, int64_t n, int64_t p, double* out_pp) {
+  return dense_symmetric(x, n, p, 2, 1.0, 0, out_pp);
+}
+
+int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out_pq));
+  RC_TRY(host_shape_check(y, n, q, out_pq));
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
+  RC_TRY(c->x[1].reserve(sizeof(double) * (size_t)n * q));
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)p * q));
+  RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
+  RC_TRY(h2d(c, c->x[1].ptr, y, sizeof(double) * (size_t)n * q, c->compute));
+  Operand ox, oy;
+  RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, n, p, spearman, BIXCOR_PREC_F64, 0, &ox));
+  RC_TRY(prepare_operand(c, (const double*)c->x[1].ptr, n, q, spearman, BIXCOR_PREC_F64, 1, &oy));
+  // rows of the kernel = genes of y, cols = genes of x: out[iy * p + jx] is the column-major p x q result
+  std::vector<int2> tiles;
+  for (int bi = 0; bi < (int)((q + kTile - 1) / kTile); ++bi)
+    for (int bj = 0; bj < (int)((p + kTile - 1) / kTile); ++bj) tiles.push_back(make_int2(bi, bj));
+  RC_TRY(c->vec.reserve(sizeof(int2) * tiles.size() + 64));
+  CU_TRY(cudaMemcpyAsync(c->vec.ptr, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->compute));
+  CU_TRY(cudaStreamSynchronize(c->compute));  // `tiles` is a stack-owned staging vector
+  EpiParams e = make_epi(q);
+  e.out = (double*)c->out.ptr;
+  e.ldo = p;
+  RC_TRY(launch_gram(c, oy, nullptr, q, (const int2*)c->vec.ptr, (int)tiles.size(), EPI_DENSE, e, &ox));
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out_pq);
+  RC_TRY(pipe.push(out_pq, c->out.ptr, sizeof(double) * (size_t)p * q, nullptr));
+  return pipe.finish();
+}
+
+int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp) {
+  RC_TRY(ensure_init());
+  if (!cov_pp || !out_pp) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (p < 1) return fail(BIXCOR_ERR_INVALID, "p must be >= 1");
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t bytes = sizeof(double) * (size_t)p * p;
+  RC_TRY(c->out2.reserve(bytes));
+  RC_TRY(c->out.reserve(bytes));
+  RC_TRY(h2d(c, c->out2.ptr, cov_pp, bytes, c->compute));
+  {
+    Timed tm(c, T_OTHER);
+    dim3 grid((unsigned)((p + 255) / 256), (unsigned)p);
+    cov2cor_kernel<<<grid, 256, 0, c->compute>>>((const double*)c->out2.ptr, p, (double*)c->out.ptr);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out_pp);
+  RC_TRY(pipe.push(out_pp, c->out.ptr, bytes, nullptr));
+  return pipe.finish();
 }
 
 int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,

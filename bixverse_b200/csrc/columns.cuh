@@ -442,21 +442,23 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
 
 // Pearson: centre and scale one gene per CTA to unit Euclidean norm, so that
 // Z'Z is the correlation matrix (sd == 0 -> 0/0 = NaN column, IEEE propagation).
+// norm_mode: 0 = centre + unit norm (correlation), 1 = centre only (covariance),
+//            2 = unit norm without centring (cosine)
 __global__ void __launch_bounds__(128)
-standardise_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, ColumnOut out) {
+standardise_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, ColumnOut out, int norm_mode) {
   __shared__ double scr[32];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int64_t j = blockIdx.x;
   const double* col = x + j * ldx;
   double s = 0.0;
   for (int i = tid; i < n; i += nt) s += col[i];
-  const double mean = block_sum(s, scr) / (double)n;
+  const double mean = (norm_mode == 2) ? 0.0 : block_sum(s, scr) / (double)n;
   double q = 0.0;
   for (int i = tid; i < n; i += nt) {
     const double c = col[i] - mean;
     q += c * c;
   }
-  const double norm = sqrt(block_sum(q, scr));
+  const double norm = (norm_mode == 1) ? 1.0 : sqrt(block_sum(q, scr));
   for (int i = tid; i < out.kpad; i += nt) {
     double z = 0.0;
     if (i < n) z = (col[i] - mean) / norm;

@@ -26,6 +26,7 @@ struct EpiParams {
   int shift;
   int mirror;        // dense: also write the transposed element
   int diag_one;      // dense: force 1.0 on the diagonal
+  double scale;      // dense / packed: value multiplier applied first (1/(n-1) for covariance); 1 = none
   double beta;
   int beta_int;      // > 0: beta is this small integer (multiplication chain instead of pow)
   int keep_sign;
@@ -105,11 +106,11 @@ template <int EPI, bool MIRROR_INLINE = true>
 __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R, int j, double v, int pass) {
   const int i = R.i;
   if (EPI == EPI_PACKED) {
-    const double w = epi_power(E, v);
+    const double w = epi_power(E, v * E.scale);
     if (j >= i + E.shift) E.out[R.ro + j] = w;
     return w;
   } else if (EPI == EPI_DENSE) {
-    double w = epi_power(E, v);
+    double w = epi_power(E, v * E.scale);
     if (i == j && E.diag_one) w = 1.0;
     if (E.mirror && j < i) return w;  // lower half of a diagonal tile: filled by the mirror write
     E.out[(int64_t)i * E.ldo + j] = w;

@@ -62,7 +62,8 @@ struct Params {
   const double* C1;
   int64_t ld1;
   int K1;
-  int p;              // number of genes (rows and cols of G)
+  int p;              // number of row genes of G
+  int pc;             // number of column genes of G (== p for the symmetric Gram)
   const int2* tiles;  // (block row, block col) list of 128 x 128 tiles
   EpiParams E;
 };
@@ -88,7 +89,7 @@ __device__ __forceinline__ void mma_8x8x4(double (&c)[2], double a, double b) {
 // Shared layout per operand: [k8 group (2)][row][8 doubles].
 template <int CFG>
 __device__ __forceinline__ void load_stage(double* stage, const double* __restrict__ R, const double* __restrict__ C,
-                                           int64_t ld, int row0, int col0, int k0, int p, int tid) {
+                                           int64_t ld, int row0, int col0, int k0, int p, int pc, int tid) {
   constexpr int BN = Shape<CFG>::BN, THREADS = threads_of<CFG>();
   constexpr int CHUNKS = (BM + BN) * 8;  // 16-byte chunks of one stage
 #pragma unroll
@@ -98,7 +99,7 @@ __device__ __forceinline__ void load_stage(double* stage, const double* __restri
     const int cc = isB ? c - BM * 8 : c;
     const int row = cc >> 3, q = cc & 7;
     const int grow = (isB ? col0 : row0) + row;
-    const bool valid = grow < p;
+    const bool valid = grow < (isB ? pc : p);
     const double* src = (isB ? C : R) + (int64_t)(valid ? grow : 0) * ld + k0 + q * 2;
     double* dst = stage + (isB ? BM * BK : 0) + (q >> 2) * ((isB ? BN : BM) * 8) + row * 8 + (q & 3) * 2;
     cp_async16(dst, src, valid);
@@ -108,7 +109,7 @@ __device__ __forceinline__ void load_stage(double* stage, const double* __restri
 template <int CFG>
 __device__ __forceinline__ void gram_mainloop(double (&acc)[(BM / Shape<CFG>::WM) / 8][(Shape<CFG>::BN / Shape<CFG>::WN) / 8][2],
                                               double* smem, const double* __restrict__ R, const double* __restrict__ C,
-                                              int64_t ld, int K, int row0, int col0, int p, int tid) {
+                                              int64_t ld, int K, int row0, int col0, int p, int pc, int tid) {
   constexpr int WN = Shape<CFG>::WN, BN = Shape<CFG>::BN;
   constexpr int WTM = BM / Shape<CFG>::WM, WTN = BN / WN, MT = WTM / 8, NT = WTN / 8;
   constexpr int STAGE_DOUBLES = (BM + BN) * BK;
@@ -119,7 +120,7 @@ __device__ __forceinline__ void gram_mainloop(double (&acc)[(BM / Shape<CFG>::WM
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_stage<CFG>(smem + s * STAGE_DOUBLES, R, C, ld, row0, col0, s * BK, p, tid);
+    if (s < KT) load_stage<CFG>(smem + s * STAGE_DOUBLES, R, C, ld, row0, col0, s * BK, p, pc, tid);
     cp_async_commit();
   }
   for (int kt = 0; kt < KT; ++kt) {
@@ -127,7 +128,7 @@ __device__ __forceinline__ void gram_mainloop(double (&acc)[(BM / Shape<CFG>::WM
     __syncthreads();
     {
       const int kn = kt + STAGES - 1;
-      if (kn < KT) load_stage<CFG>(smem + (kn % STAGES) * STAGE_DOUBLES, R, C, ld, row0, col0, kn * BK, p, tid);
+      if (kn < KT) load_stage<CFG>(smem + (kn % STAGES) * STAGE_DOUBLES, R, C, ld, row0, col0, kn * BK, p, pc, tid);
       cp_async_commit();
     }
     const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(threads_of<CFG>(), Shape<CFG>::MIN_CTAS) gram_
   const int g = lane >> 2, t = lane & 3;
   const int64_t p = P.p;
   const EpiParams& E = P.E;
-  if (col0 >= p) return;  // right half of a ragged last tile
+  if (col0 >= P.pc) return;  // right half of a ragged last tile
 
   double acc[MT][NT][2];
 #pragma unroll
@@ -182,9 +183,9 @@ __global__ void __launch_bounds__(threads_of<CFG>(), Shape<CFG>::MIN_CTAS) gram_
 #pragma unroll 1
   for (int pass = 0; pass < NPASS; ++pass) {
     if (pass == 0)
-      gram_mainloop<CFG>(acc, smem, P.R0, P.C0, P.ld0, P.K0, row0, col0, P.p, tid);
+      gram_mainloop<CFG>(acc, smem, P.R0, P.C0, P.ld0, P.K0, row0, col0, P.p, P.pc, tid);
     else
-      gram_mainloop<CFG>(acc, smem, P.R1, P.C1, P.ld1, P.K1, row0, col0, P.p, tid);
+      gram_mainloop<CFG>(acc, smem, P.R1, P.C1, P.ld1, P.K1, row0, col0, P.p, P.pc, tid);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int64_t i = row0 + wm * WTM + mt * 8 + g;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(threads_of<CFG>(), Shape<CFG>::MIN_CTAS) gram_
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int j = col0 + wn * WTN + nt * 8 + 2 * t + e;
-            if (j < P.p) epi_store<EPI>(E, R, j, acc[mt][nt][e], pass);
+            if (j < P.pc) epi_store<EPI>(E, R, j, acc[mt][nt][e], pass);
           }
       }
 #pragma unroll

@@ -322,6 +322,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int shift = E.shift;
     const int diag_one = E.diag_one;
     const int keep_sign = E.keep_sign;
+    const double scale = E.scale;
     const int pw_mode = (E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0);  // 1 identity, 6 = WGCNA default, 0 generic
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
       const int2 tile = P.tiles[t];
@@ -406,6 +407,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= (jb + q < pp) ? __ldg(inv_col + jb + q) : 0.0;
           }
+          if ((EPI == EPI_PACKED || EPI == EPI_DENSE) && scale != 1.0) {
+#pragma unroll
+            for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= scale;
+          }
           if ((EPI == EPI_PACKED || EPI == EPI_DENSE) && pw_mode == 6) {
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) {
@@ -421,7 +426,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll 1
             for (int q = 0; q < EPI_CHUNK; ++q) {
               double* sp = stg + lane * EPI_CHUNK + (q ^ (lane & 15));
-              *sp = epi_power(E, *sp);
+              *sp = epi_power(E, *sp);  // (scale already applied above)
             }
           }
           __syncwarp();

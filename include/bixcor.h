@@ -115,6 +115,16 @@ int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int prec
 int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int signed_, int version,
                         double beta, int precision, int packed, double* out);
 
+/* Sibling Gram kernels sharing the same GEMM (FP64 path):
+ *   rs_covariance  src/rust/src/base/r_cors_similarity.rs:49-55   == base R cov()
+ *   rs_cos         src/rust/src/base/r_cors_similarity.rs:90-97   column cosine similarity
+ *   rs_cor2        src/rust/src/base/r_cors_similarity.rs:114-122 == base R cor(x, y): p x q, column-major
+ *   rs_cov2cor     src/rust/src/base/r_cors_similarity.rs:135-142 */
+int bixcor_covariance(const double* x, int64_t n, int64_t p, double* out_pp);
+int bixcor_cos(const double* x, int64_t n, int64_t p, double* out_pp);
+int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq);
+int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp);
+
 /* cells x genes CSR (int64 indptr[cells+1], int32 indices, float data) -> packed shift=1 Pearson */
 int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                            int64_t genes, int precision, double* out_packed);

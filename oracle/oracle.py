@@ -38,6 +38,9 @@ __all__ = [
     "rank_matrix_col",
     "column_pairwise_cor",
     "column_pairwise_cov",
+    "column_pairwise_cos",
+    "cor_two_matrices",
+    "cov2cor",
     "upper_triangle_indices",
     "dense_to_upper_triangle",
     "upper_triangle_to_dense",
@@ -127,6 +130,32 @@ def column_pairwise_cov(x: np.ndarray) -> np.ndarray:
     x = np.asarray(x, dtype=np.float64)
     xc = x - x.mean(axis=0)
     return (xc.T @ xc) / (x.shape[0] - 1)
+
+
+def column_pairwise_cos(x: np.ndarray) -> np.ndarray:
+    """Column cosine similarity (rs_cos, r_cors_similarity.rs:90-97)."""
+    x = np.asarray(x, dtype=np.float64)
+    xn = x / np.sqrt((x * x).sum(axis=0))
+    return xn.T @ xn
+
+
+def cor_two_matrices(x: np.ndarray, y: np.ndarray, spearman: bool = False) -> np.ndarray:
+    """p x q correlation between the columns of x and of y (rs_cor2, r_cors_similarity.rs:114-122;
+    == base R cor(x, y), inst/tinytest/test_R_rust_equality.R:39-55)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if x.shape[0] != y.shape[0]:
+        raise ValueError("x and y need the same number of rows")
+    if spearman:
+        x, y = rank_matrix_col(x), rank_matrix_col(y)
+    return _standardise(x).T @ _standardise(y)
+
+
+def cov2cor(c: np.ndarray) -> np.ndarray:
+    """rs_cov2cor (r_cors_similarity.rs:135-142; test_R_rust_equality.R:76-82)."""
+    c = np.asarray(c, dtype=np.float64)
+    d = np.sqrt(np.diag(c))
+    return c / np.outer(d, d)
 
 
 # --------------------------------------------------------------------------

@@ -359,3 +359,29 @@ def test_operand_exchange_api(api, prec_name):
         assert torch.equal(via, direct[o0 : o0 + via.numel()])
     ref = o.soft_threshold(o.cor_upper_triangle(x, True, True), 6.0)
     assert _maxerr(direct.cpu().numpy(), ref) < (TOL32 if prec_name == "tf32" else TOL64)
+
+
+# ----------------------------------------------------------------------------- sibling Gram kernels
+def test_covariance_cor2_cov2cor_golden(api, golden_dir):
+    """inst/tinytest/test_R_rust_equality.R:23-55,76-82 on the reference's own matrices."""
+    g = json.load(open(os.path.join(golden_dir, "r_equality_seed123.json")))
+    mat, mat2 = np.array(g["mat"]), np.array(g["mat_2"])
+    cov = api.rs_covariance(mat)
+    assert _maxerr(cov, np.array(g["cov"])) < 1e-13
+    assert _maxerr(api.rs_cor2(mat, mat2, False), np.array(g["pearson_2"])) < 1e-13
+    assert _maxerr(api.rs_cor2(mat, mat2, True), np.array(g["spearman_2"])) < 1e-13
+    assert _maxerr(api.rs_cov2cor(cov), np.array(g["pearson"])) < 1e-13
+
+
+def test_siblings_larger_shapes(api):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(120, 390, seed=41)
+    y = synthetic_bulk(120, 200, seed=42)
+    assert _maxerr(api.rs_covariance(x), o.column_pairwise_cov(x)) < 1e-10
+    c2 = api.rs_cor2(x, y, True)
+    rx, ry = o.rank_matrix_col(x), o.rank_matrix_col(y)
+    ref = np.corrcoef(rx.T, ry.T)[:390, 390:]
+    assert c2.shape == (390, 200) and _maxerr(c2, ref) < 1e-10
+    xn = x / np.sqrt((x * x).sum(axis=0))
+    assert _maxerr(api.rs_cos(x), xn.T @ xn) < 1e-10

@@ -75,6 +75,16 @@ def test_pearson_spearman_cov_equal_base_r_standin(req):
     assert np.abs(o.upper_triangle_to_dense(packed, True, 14) - req["pearson"]).max() < 1e-14
 
 
+def test_two_matrix_cor_and_cov2cor_equal_base_r_standin(req):
+    """inst/tinytest/test_R_rust_equality.R:37-55,76-82."""
+    mat, mat2 = req["mat"], req["mat_2"]
+    assert np.abs(o.cor_two_matrices(mat, mat2, False) - req["pearson_2"]).max() < 1e-14
+    assert np.abs(o.cor_two_matrices(mat, mat2, True) - req["spearman_2"]).max() < 1e-14
+    assert np.abs(o.cov2cor(o.column_pairwise_cov(mat)) - req["pearson"]).max() < 1e-14
+    c = o.column_pairwise_cos(mat)
+    assert np.allclose(np.diag(c), 1.0) and np.allclose(c, c.T)
+
+
 def test_rank_average_ties_signed_zero_nan():
     rng = np.random.default_rng(7)
     x = np.round(rng.normal(size=(257, 11)), 1)
