@@ -287,6 +287,37 @@ __device__ __forceinline__ void emit_ranked_column_warp(const ColumnOut& out, in
   }
 }
 
+// Compare-exchange primitives of the register sort.  Keys are the raw doubles (no NaN reaches the
+// sort; -0.0 == +0.0 under DSETP, which is the base-R tie semantics), so the comparison runs on the
+// FP64 pipe and only the selects occupy the integer ALU pipe, which is what bounds this kernel.
+// Inline setp/selp: ptxas otherwise turns the conditional swaps into branches.
+__device__ __forceinline__ void ce_asc(double& ka, double& kb, uint32_t& ia, uint32_t& ib) {
+  // afterwards ka <= kb; equal keys never swap
+  const double a = ka, b = kb;
+  const uint32_t x = ia, y = ib;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.lt.f64 p, %5, %4;\n\t"
+      "selp.f64 %0, %5, %4, p;\n\t"
+      "selp.f64 %1, %4, %5, p;\n\t"
+      "selp.b32 %2, %7, %6, p;\n\t"
+      "selp.b32 %3, %6, %7, p;\n\t}"
+      : "=&d"(ka), "=&d"(kb), "=&r"(ia), "=&r"(ib)
+      : "d"(a), "d"(b), "r"(x), "r"(y));
+}
+// Lane exchange: this lane keeps the smaller (keep_min != 0) or the larger of (own, partner's);
+// on equal keys both lanes keep their own element, so no index is lost or duplicated.
+__device__ __forceinline__ void ce_lane(double& k, uint32_t& i, double ok, uint32_t oi, int keep_min) {
+  // take = keep_min ? (partner < own) : (partner > own) = lt XOR (ne AND !keep_min): two DSETP, no predicate logic op
+  asm("{\n\t.reg .pred m, q, t;\n\t"
+      "setp.eq.s32 m, %4, 0;\n\t"
+      "setp.neu.and.f64 q, %2, %0, m;\n\t"
+      "setp.lt.xor.f64 t, %2, %0, q;\n\t"
+      "selp.f64 %0, %2, %0, t;\n\t"
+      "selp.b32 %1, %3, %1, t;\n\t}"
+      : "+d"(k), "+r"(i)
+      : "d"(ok), "r"(oi), "r"(keep_min));
+}
+
 template <int E>
 __global__ void __launch_bounds__(128)
 rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out) {
@@ -297,19 +328,20 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
   if (j >= p) return;  // whole warp leaves; no block-level barrier below
   const double* col = x + j * ldx;
 
-  uint64_t key[E];
+  // Padding slots hold +inf with an index >= n.  A real +inf ties with the padding, which is
+  // harmless: the tie run then starts at the first real +inf and its end is clamped to n - 1.
+  double key[E];
   uint32_t idx[E];
   bool has_nan = false;
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const int i = r * 32 + lane;  // coalesced load; the initial order is irrelevant to a sort
-    uint64_t k = ~0ull;
+    double v = __longlong_as_double(0x7ff0000000000000ll);
     if (i < n) {
-      const double v = col[i];
+      v = col[i];
       if (v != v) has_nan = true;
-      k = sortable_key(v);
     }
-    key[r] = k;
+    key[r] = v;
     idx[r] = (uint32_t)i;
   }
   if (__any_sync(0xffffffffu, has_nan)) {
@@ -333,67 +365,74 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
     return;
   }
 
-  // ---- bitonic sort, position s = lane*E + r --------------------------------
-  // The merge level k is a RUNTIME loop: the fully unrolled network is ~190 KB of code and
-  // is instruction-fetch bound; this form is one lane-exchange body plus log2(E) register stages.
-  // Compare-exchanges are inline setp/selp (ptxas otherwise turns the selects into branches); a
-  // descending exchange is the ascending one on keys XORed with all-ones.
+  // ---- bitonic sort, position s = lane*E + r, ascending everywhere ---------------------------
+  // Each merge of size k opens with the MIRROR stage (s <-> s ^ (k-1)), after which every
+  // half-cleaner stage (s <-> s ^ jj) sorts upwards: no direction flags, no key flipping.
+  // Merges inside one lane (k <= E) are fully unrolled register networks; merges across lanes
+  // run in a RUNTIME loop over k (the fully unrolled network is instruction-fetch bound).
+#pragma unroll
+  for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const int l = r ^ (k - 1);
+      if (r < l) ce_asc(key[r], key[l], idx[r], idx[l]);
+    }
+#pragma unroll
+    for (int jj = k >> 2; jj > 0; jj >>= 1) {
+#pragma unroll
+      for (int r = 0; r < E; ++r)
+        if ((r & jj) == 0) ce_asc(key[r], key[r | jj], idx[r], idx[r | jj]);
+    }
+  }
 #pragma unroll 1
-  for (int k = 2; k <= NP; k <<= 1) {
-    const bool up_lane = ((lane * E) & k) == 0;  // direction bit when it is a lane bit (k >= E)
+  for (int k = 2 * E; k <= NP; k <<= 1) {
+    {  // mirror stage: partner lane = lane ^ (k/E - 1), partner register = E-1-r
+      const int lm = k / E - 1;
+      const int keep_min = ((lane & (k / (2 * E))) == 0) ? 1 : 0;
+      if (E == 1) {
+        const double ok = __shfl_xor_sync(0xffffffffu, key[0], lm);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[0], lm);
+        ce_lane(key[0], idx[0], ok, oi, keep_min);
+      }
+#pragma unroll
+      for (int r = 0; r < E / 2; ++r) {  // registers r and E-1-r trade places across the lane pair
+        const int m = E - 1 - r;
+        const double oka = __shfl_xor_sync(0xffffffffu, key[m], lm);
+        const uint32_t oia = __shfl_xor_sync(0xffffffffu, idx[m], lm);
+        const double okb = __shfl_xor_sync(0xffffffffu, key[r], lm);
+        const uint32_t oib = __shfl_xor_sync(0xffffffffu, idx[r], lm);
+        ce_lane(key[r], idx[r], oka, oia, keep_min);
+        ce_lane(key[m], idx[m], okb, oib, keep_min);
+      }
+    }
 #pragma unroll 1
-    for (int jj = k >> 1; jj >= E; jj >>= 1) {
-      const int lm = jj / E;  // partner lane = lane ^ lm
-      const bool keep_min = ((lane & lm) == 0) == up_lane;
-      const uint64_t flip = keep_min ? 0ull : ~0ull;
+    for (int jj = k >> 2; jj >= E; jj >>= 1) {
+      const int lm = jj / E;  // partner lane = lane ^ lm, same register
+      const int keep_min = ((lane & lm) == 0) ? 1 : 0;
 #pragma unroll
       for (int r = 0; r < E; ++r) {
-        const uint64_t ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
+        const double ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
         const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
-        // take the partner's element iff it is strictly better in this lane's direction
-        asm("{\n\t.reg .pred p;\n\t"
-            "setp.lt.u64 p, %4, %5;\n\t"
-            "selp.b64 %0, %2, %0, p;\n\t"
-            "selp.b32 %1, %3, %1, p;\n\t}"
-            : "+l"(key[r]), "+r"(idx[r])
-            : "l"(ok), "r"(oi), "l"(ok ^ flip), "l"(key[r] ^ flip));
+        ce_lane(key[r], idx[r], ok, oi, keep_min);
       }
     }
 #pragma unroll
     for (int jj = E / 2; jj > 0; jj >>= 1) {
-      if (jj < k) {  // warp uniform
 #pragma unroll
-        for (int r = 0; r < E; ++r) {
-          if ((r & jj) == 0) {
-            const int l = r | jj;
-            const bool up = (k < E) ? ((r & k) == 0) : up_lane;
-            const uint64_t flip = up ? 0ull : ~0ull;
-            const uint64_t ka = key[r], kb = key[l];
-            const uint32_t ia = idx[r], ib = idx[l];
-            // swap iff (ka > kb) in the stage direction; equal keys never swap
-            asm("{\n\t.reg .pred p;\n\t"
-                "setp.gt.u64 p, %8, %9;\n\t"
-                "selp.b64 %0, %5, %4, p;\n\t"
-                "selp.b64 %1, %4, %5, p;\n\t"
-                "selp.b32 %2, %7, %6, p;\n\t"
-                "selp.b32 %3, %6, %7, p;\n\t}"
-                : "=&l"(key[r]), "=&l"(key[l]), "=&r"(idx[r]), "=&r"(idx[l])
-                : "l"(ka), "l"(kb), "r"(ia), "r"(ib), "l"(ka ^ flip), "l"(kb ^ flip));
-          }
-        }
-      }
+      for (int r = 0; r < E; ++r)
+        if ((r & jj) == 0) ce_asc(key[r], key[r | jj], idx[r], idx[r | jj]);
     }
   }
 
   // ---- tie runs -> 2 * average rank ------------------------------------------
-  const uint64_t prev_last = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
+  const double prev_last = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
   uint32_t start_mask = 0;  // bit r: position lane*E + r starts a run of equal keys
   int last = -1;
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const int s = lane * E + r;
-    const uint64_t prev = (r == 0) ? prev_last : key[r - 1];
-    const bool st = (s >= n) || (s == 0) || (key[r] != prev);
+    const double prev = (r == 0) ? prev_last : key[r - 1];
+    const bool st = (s == 0) || (key[r] != prev);
     if (st) {
       start_mask |= 1u << r;
       last = s;
@@ -434,7 +473,8 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
   for (int r = E - 1; r >= 0; --r) {
     const int s = lane * E + r;
     if (end_mask & (1u << r)) cur = s;
-    if (s < n) rk2[idx[r]] = (uint16_t)(lo[r] + (uint32_t)cur + 2u);  // lo + hi + 2 == 2 * average rank
+    // lo + hi + 2 == 2 * average 1-based rank; hi is clamped to the last real slot (+inf ties with padding)
+    if (idx[r] < (uint32_t)n) rk2[idx[r]] = (uint16_t)(lo[r] + (uint32_t)min(cur, n - 1) + 2u);
   }
   __syncwarp();
   emit_ranked_column_warp(out, j, n, rk2, lane);

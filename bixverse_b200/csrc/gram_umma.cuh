@@ -51,7 +51,9 @@ struct Params {
   int npass;         // 2 for the differential correlation (operand set 1 in pass 1)
   int kblocks[2];    // 128-byte K blocks per pass
   const double* inv_norm[2];  // KIND_I8: 1/|d| per gene and pass
-  int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = no global stores, 3 = no MMA issue
+  int zero;  // always 0; opaque to the compiler (scheduling fence, see the epilogue drain)
+  int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = generic path without global stores, 3 = no MMA issue,
+            // 4 = lean path without global stores, 5 = lean path without phase B, 6 = no TMA and no MMA (epilogue alone)
   EpiParams E;
 };
 
@@ -178,6 +180,80 @@ struct KindTraits<KIND_I8> {
   static constexpr int CHUNK_KB = 1 << 30;  // integer accumulation is exact: one chunk = whole K
 };
 
+
+// Lean epilogue of one interior tile of the packed correlation for one epilogue warp: 32 rows x
+// EPI_COLS columns, nothing predicated.  racc holds the drained accumulators (lane = row).  Row-side
+// factors are applied with lane = row, column-side factors and the power after the shared-memory
+// transpose with lane = (row parity, column); the 16 row offsets of a lane are 32-bit, computed once
+// per tile and pinned in registers, so a store costs one 64-bit add.
+template <int KIND, bool PW6>
+__device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS], double* stg, int lane, double rowf,
+                                                bool tf32_scaled, const double* colv, char* wbase, int a, int dbg) {
+  const int rr = lane >> 4, cc = lane & 15;
+  uint32_t roff[16];
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const int m = 2 * k2 + rr;
+    roff[k2] = (uint32_t)(m * a - (m * (m - 1)) / 2 + cc) << 3;
+    asm volatile("" : "+r"(roff[k2]));  // keep it: ptxas otherwise rematerialises the product per store
+  }
+  double colf[EPI_COLS / EPI_CHUNK];
+#pragma unroll
+  for (int c = 0; c < EPI_COLS / EPI_CHUNK; ++c) colf[c] = (KIND == KIND_I8) ? __ldg(colv + c * EPI_CHUNK + cc) : 1.0;
+  const uint32_t stg_s = smem_u32(stg);
+  uint32_t st_addr[EPI_CHUNK / 2];  // 16-byte unit u of row `lane` lives at unit u ^ (lane & 7)
+#pragma unroll
+  for (int u = 0; u < EPI_CHUNK / 2; ++u)
+    st_addr[u] = stg_s + (uint32_t)lane * (EPI_CHUNK * 8) + ((((uint32_t)u) ^ ((uint32_t)lane & 7u)) << 4);
+  // row r = 2*k2 + rr keeps unit (cc >> 1) at (cc >> 1) ^ (r & 7) = xq ^ ((2*k2) & 7)
+  const uint32_t xq = (uint32_t)((cc >> 1) ^ rr);
+  uint32_t ld_off[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    ld_off[t] = (uint32_t)rr * (EPI_CHUNK * 8) + (uint32_t)(cc & 1) * 8 + ((xq ^ (uint32_t)(2 * t)) << 4);
+  const char* const sb = reinterpret_cast<const char*>(stg);
+#pragma unroll
+  for (int c = 0; c < EPI_COLS; c += EPI_CHUNK) {
+#pragma unroll
+    for (int q = 0; q < EPI_CHUNK; q += 2) {  // phase A (lane = row)
+      double v0, v1;
+      if (KIND == KIND_I8) {
+        v0 = (double)(int)racc[c + q] * rowf;
+        v1 = (double)(int)racc[c + q + 1] * rowf;
+      } else {
+        v0 = (double)__uint_as_float(racc[c + q]);
+        v1 = (double)__uint_as_float(racc[c + q + 1]);
+        if (tf32_scaled) {
+          v0 *= rowf;
+          v1 *= rowf;
+        }
+      }
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(st_addr[q >> 1]), "d"(v0), "d"(v1) : "memory");
+    }
+    __syncwarp();
+    const double cf = colf[c / EPI_CHUNK];
+    if (dbg == 5) {  // profiling: no phase B at all
+      __syncwarp();
+      continue;
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {  // phase B (lane = 2 rows x 16 columns): two 128-byte runs per store
+      double v = *reinterpret_cast<const double*>(sb + ld_off[k2 & 3] + k2 * (2 * EPI_CHUNK * 8));
+      if (KIND == KIND_I8) v *= cf;
+      if (PW6) {
+        const double sq = v * v;
+        v = sq * sq * sq;
+      }
+      if (dbg == 4) {  // profiling: everything but the global store
+        asm volatile("" ::"d"(v));
+        continue;
+      }
+      *reinterpret_cast<double*>(wbase + roff[k2] + (uint32_t)(c * 8)) = v;
+    }
+    __syncwarp();
+  }
+}
+
 template <int KIND, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
@@ -236,12 +312,16 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           const int kelems = (KIND == KIND_TF32) ? 32 : 128;
           for (int kb = 0; kb < kb_n; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            const uint32_t s0 = base + stage * STAGE_BYTES;
-            tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.x * BM);
-            tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.x * BM);
-            tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.y * BN);
-            tma_load_3d(s0 + 3 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.y * BN);
+            if (P.dbg == 6) {  // profiling: no operand traffic at all
+              mbar_arrive(full_bar(stage));
+            } else {
+              mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+              const uint32_t s0 = base + stage * STAGE_BYTES;
+              tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.x * BM);
+              tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.x * BM);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.y * BN);
+              tma_load_3d(s0 + 3 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.y * BN);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -276,7 +356,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               for (int k = 0; k < 4; ++k) {             // 4 x 32-byte K steps inside the 128-byte swizzle row
                 const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes, in 16-byte descriptor units
                 const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
-                if (P.dbg == 3) continue;
+                if (P.dbg == 3 || P.dbg == 6) continue;
                 if (KIND == KIND_TF32) {
                   tc_mma<KIND>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
                   tc_mma<KIND>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
@@ -307,6 +387,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     // ============================ epilogue ================================
     // Warp e = warp - 4 owns TMEM lanes [32*(e%4), +32) (its hardware lane quarter) and the
     // accumulator columns [EPI_COLS*(e/4), +EPI_COLS) of every tile.
+    constexpr bool DIRECT = (KIND == KIND_I8 && EPI == EPI_PACKED);
+    static_assert(EPI_CHUNK == 16, "the direct path loads 16 accumulator columns per step");
     const int ew = (warp - 4) & 3;
     const int ch = (warp - 4) >> 2;
     int acc_stage = 0;
@@ -330,51 +412,98 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       const int i = row_base + lane;
       const int col_base = tile.y * BN + ch * EPI_COLS;
       for (int pass = 0; pass < P.npass; ++pass) {
-        // ---- drain: TMEM -> registers, chunk by chunk (FP32 round-to-nearest / exact int32 sums)
+        // Interior tiles of the packed correlation (97% of the tiles at p = 20000) lie strictly above the
+        // diagonal and fully inside the matrix: nothing is predicated and they take the lean path below.
+        const bool interior = (EPI == EPI_PACKED) && tile.x < tile.y && tile.y * BN + BN <= pp && pw_mode != 0 && !keep_sign && (dbg == 0 || dbg >= 3);
+        // DIRECT kernels keep the accumulators of the few non-interior tiles in TMEM and finish them chunk
+        // by chunk (the MMA warp waits a little longer on 3% of the tiles); in exchange the 64-register
+        // drain array only lives on the lean path and the kernel stays free of local-memory spills.
+        const bool direct = DIRECT && !interior;
         uint32_t racc[EPI_COLS];
         const int kb_n = P.kblocks[pass];
-        for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
+        uint32_t tacc_direct = 0;
+        if (direct) {
           mbar_wait(tfull_bar(acc_stage), acc_phase);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) +
-                                (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
-          if (KIND == KIND_I8) {
+          tacc_direct = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
+        } else {
+          // ---- drain: TMEM -> registers, chunk by chunk (FP32 round-to-nearest / exact int32 sums)
+          for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
+            mbar_wait(tfull_bar(acc_stage), acc_phase);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                  (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
+            if (KIND == KIND_I8) {
+              // `dep` is always 0 (P.zero is a runtime 0): it chains each batch of loads to the previous
+              // batch's sums (all 16 of them, or ptxas only hurries the one it needs), otherwise ptxas hoists all 12 tcgen05.ld (192 registers) and spills.
+              uint32_t dep = 0;
 #pragma unroll
-            for (int c = 0; c < EPI_COLS; c += 16) {
-              uint32_t r0[16], r1[16], r2[16];
-              tmem_ld16(tacc + c, r0);
-              tmem_ld16(tacc + BN + c, r1);
-              tmem_ld16(tacc + 2 * BN + c, r2);
-              tmem_ld_wait();
+              for (int c = 0; c < EPI_COLS; c += 16) {
+                uint32_t r0[16], r1[16], r2[16];
+                tmem_ld16(tacc + c + dep, r0);
+                tmem_ld16(tacc + BN + c + dep, r1);
+                tmem_ld16(tacc + 2 * BN + c + dep, r2);
+                tmem_ld_wait();
 #pragma unroll
-              for (int q = 0; q < 16; ++q)  // S = 256*hh + 16*(hl+lh) + ll, exact in int32 for n <= 1860
-                racc[c + q] = (uint32_t)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]);
-            }
-          } else {
+                for (int q = 0; q < 16; ++q)  // S = 256*hh + 16*(hl+lh) + ll, exact in int32 for n <= 1860
+                  racc[c + q] = (uint32_t)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]);
+                uint32_t any = 0;
 #pragma unroll
-            for (int c = 0; c < EPI_COLS; c += 32) {
-              uint32_t r0[32];
-              tmem_ld32(tacc + c, r0);
-              tmem_ld_wait();
-              if (kb0 == 0) {
+                for (int q = 0; q < 16; ++q) any |= racc[c + q];
+                dep = any & (uint32_t)P.zero;
+              }
+            } else {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) racc[c + q] = r0[q];
-              } else {
+              for (int c = 0; c < EPI_COLS; c += 32) {
+                uint32_t r0[32];
+                tmem_ld32(tacc + c, r0);
+                tmem_ld_wait();
+                if (kb0 == 0) {
 #pragma unroll
-                for (int q = 0; q < 32; ++q)
-                  racc[c + q] = __float_as_uint(__uint_as_float(racc[c + q]) + __uint_as_float(r0[q]));
+                  for (int q = 0; q < 32; ++q) racc[c + q] = r0[q];
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 32; ++q)
+                    racc[c + q] = __float_as_uint(__uint_as_float(racc[c + q]) + __uint_as_float(r0[q]));
+                }
               }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc_stage));  // TMEM buffer free: the MMA warp moves on
+            if (++acc_stage == T::ACC_STAGES) {
+              acc_stage = 0;
+              acc_phase ^= 1u;
+            }
           }
+        }
+        auto release_direct = [&]() {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc_stage));  // TMEM buffer free: the MMA warp moves on
+          if (lane == 0) mbar_arrive(tempty_bar(acc_stage));
           if (++acc_stage == T::ACC_STAGES) {
             acc_stage = 0;
             acc_phase ^= 1u;
           }
+        };
+        if (dbg == 1) {
+          if (direct) release_direct();
+          continue;
         }
-        if (dbg == 1) continue;
+        // ---- lean path: row-side factors are applied with lane = row, column-side factors and the power
+        //      after the transpose with lane = column; the 16 row offsets of a lane are 32-bit and computed
+        //      once per tile, so a store costs one address add.
+        if (interior) {
+          const EpiRow R0 = epi_row<EPI>(E, row_base);  // warp uniform
+          double rowf = scale;
+          if (KIND == KIND_I8) rowf *= P.inv_norm[pass][i];
+          const double* colv = (KIND == KIND_I8) ? P.inv_norm[pass] + col_base : nullptr;
+          char* const wbase = reinterpret_cast<char*>(out + (R0.ro + col_base));
+          const int a = pp - row_base - shift - 1;  // ro(i + 1) - ro(i) = p - i - shift - 1
+          if (pw_mode == 6) packed_interior<KIND, true>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
+          else packed_interior<KIND, false>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
+          continue;
+        }
         // ---- fused epilogue from registers.  Each 32 x 16 block is transposed through shared
         //      memory (XOR-swizzled, conflict free) so that one store instruction writes two
         //      contiguous 128-byte runs of the packed rows instead of 32 scattered doubles.
@@ -400,9 +529,20 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           // phase A (lane = row): finish the Gram value.  All mode decisions are warp uniform and sit
           // OUTSIDE the element loops, so each loop body is a handful of FP64 instructions.
           double vals[EPI_CHUNK];
+          if (DIRECT) {  // (KIND_I8) straight from TMEM
+            uint32_t r0[16], r1[16], r2[16];
+            tmem_ld16(tacc_direct + c, r0);
+            tmem_ld16(tacc_direct + BN + c, r1);
+            tmem_ld16(tacc_direct + 2 * BN + c, r2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < EPI_CHUNK; ++q)
-            vals[q] = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
+            for (int q = 0; q < EPI_CHUNK; ++q)
+              vals[q] = (double)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]) * inv_i;
+          } else {
+#pragma unroll
+            for (int q = 0; q < EPI_CHUNK; ++q)
+              vals[q] = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
+          }
           if (KIND == KIND_I8) {
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= (jb + q < pp) ? __ldg(inv_col + jb + q) : 0.0;
@@ -434,21 +574,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           // shared loads are issued for all 16 row pairs before the predicated stores (no branches).
           const int j = jb + cc;
           const bool col_ok = (j < pp) && (dbg != 2);
-          if (EPI == EPI_PACKED) {
-            int64_t ro_r[16];
-            double vv[16];
-#pragma unroll
+          if (EPI == EPI_PACKED) {  // diagonal / ragged tiles only (interior tiles took the path above)
+#pragma unroll 2
             for (int k2 = 0; k2 < 16; ++k2) {
               const int r = 2 * k2 + rr;
-              ro_r[k2] = __shfl_sync(0xffffffffu, R.ro, r);
-              vv[k2] = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
-            }
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) {
-              const int ir = row_base + 2 * k2 + rr;
-              const bool ok = col_ok && (ir < pp) && (j >= ir + shift);
-              double* dst = out + (ro_r[k2] + j);
-              if (ok) *dst = vv[k2];
+              const int ir = row_base + r;
+              const int64_t ro_r = __shfl_sync(0xffffffffu, R.ro, r);
+              const double v = stg[r * EPI_CHUNK + (cc ^ (r & 15))];
+              if (col_ok && (ir < pp) && (j >= ir + shift)) out[ro_r + j] = v;
             }
           } else if (EPI == EPI_DENSE) {
 #pragma unroll 8
@@ -491,6 +624,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             __syncwarp();
           }
         }
+        if (direct) release_direct();
       }
     }
   }
@@ -594,6 +728,7 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   P.inv_norm[0] = inv0;
   P.inv_norm[1] = inv1;
   P.E = E;
+  P.zero = 0;
   {
     const char* d = getenv("BIXCOR_UMMA_DEBUG");
     P.dbg = d ? atoi(d) : 0;

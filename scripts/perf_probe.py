@@ -12,11 +12,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     xd = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
     out = torch.empty(p * (p - 1) // 2, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    beta = float(os.environ.get("PROBE_BETA", "6.0"))
     for _ in range(3):
-        _lib.check(lib.bixcor_dev_cor_upper_rows(xd.data_ptr(), n, p, spearman, 1, 6.0, prec, 0, p, out.data_ptr()))
+        _lib.check(lib.bixcor_dev_cor_upper_rows(xd.data_ptr(), n, p, spearman, 1, beta, prec, 0, p, out.data_ptr()))
     _lib.check(lib.bixcor_timing_enable(1))
     for _ in range(5):
-        _lib.check(lib.bixcor_dev_cor_upper_rows(xd.data_ptr(), n, p, spearman, 1, 6.0, prec, 0, p, out.data_ptr()))
+        _lib.check(lib.bixcor_dev_cor_upper_rows(xd.data_ptr(), n, p, spearman, 1, beta, prec, 0, p, out.data_ptr()))
     t = _lib.last_timing()
     print(json.dumps({"gemm_ms": t["gemm_ms"] / 5, "cols_ms": t["cols_ms"] / 5}))
     sys.exit(0)
@@ -28,5 +29,6 @@ def run(tag, prec, spearman=1, n=1000, p=20000, **env):
 
 probes = sys.argv[1:] or ["i8:0", "i8:1", "i8:2", "i8:3", "tf32:0", "tf32:1"]
 for pr in probes:
-    kind, d = pr.split(":")
-    run(f"umma {kind} dbg {d}", 2 if kind == "i8" else 1, BIXCOR_UMMA_DEBUG=d)
+    kind, d, *rest = pr.split(":")
+    beta = rest[0] if rest else "6.0"
+    run(f"umma {kind} dbg {d} beta {beta}", 2 if kind == "i8" else 1, BIXCOR_UMMA_DEBUG=d, PROBE_BETA=beta)
