@@ -53,15 +53,56 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region.  NVML is polled from a thread every
+    ~1 ms (the timed region of the default run is ~10 ms, shorter than one nvidia-smi -lms period);
+    nvidia-smi is the fallback when the NVML binding is missing."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.smax, self.reasons, self.stop_flag, self.thread = [], None, set(), False, None
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                pass
+        return index
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for bit, name in self.NVML_REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
@@ -75,6 +116,11 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -94,7 +140,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_input():
@@ -125,10 +171,23 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm is a CPU job and takes every host core."""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=ncpu)
+    except Exception:
+        pass
+    return ncpu
+
+
 def run_reference(args):
     rank = _env_int("RANK", 0)
     if rank != 0:
         return 0
+    use_all_host_threads()
     x = make_input()[:, :CPU_SAMPLE_GENES]
     x = np.asfortranarray(x)
     for _ in range(args.warmup):
@@ -297,8 +356,15 @@ def run_ours(args):
             note = f"0.5 x {peaks['src']} dense bf16 (= tf32 tensor rate); the kernel issues 3 tf32 MMAs per algorithmic flop pair"
             mmas = 3
         out_bytes = 8.0 * my_pairs
+        traffic = None
+        if world == 1:
+            try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                traffic = tr.get("gram_dmma_kernel" if pname == "f64" else f"gram_umma_kernel_{pname}", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         roof = {"bound": "tensor", "kernel": "gram_dmma_kernel" if pname == "f64" else "gram_umma_kernel",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": traffic,
                 "peak_source": note, "mma_issue_frac": mmas * ach / peak if peak else None,
                 "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / ms_step if ms_step else None,
                 "launches_per_step": tm["gemm_launches"] / k_steps,
@@ -328,8 +394,25 @@ def run_ours(args):
     x_pin = torch.from_numpy(np.ascontiguousarray(x_host.T)).pin_memory()
     out_pin = torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
 
-    def step_e2e():
-        _lib.check(lib.bixcor_cor_upper_rows(x_pin.data_ptr(), n, p, 1, 1, BETA, PREC[primary], r0, r1, out_pin.data_ptr()))
+    if world == 1:
+        e2e_note = "bixcor_cor_upper_rows through the C ABI with pinned host buffers"
+        h2d_bytes = int(8 * n * p)
+
+        def step_e2e():
+            _lib.check(lib.bixcor_cor_upper_rows(x_pin.data_ptr(), n, p, 1, 1, BETA, PREC[primary], r0, r1, out_pin.data_ptr()))
+    else:
+        # host -> host multi-process driver: only this rank's gene slab crosses PCIe, operand records are
+        # all-gathered over NCCL, the rank's packed rows come back with the D2H of finished bands overlapped
+        from bixverse_b200.distributed import DeviceBackend, gene_slab, host_sharded_cor_upper
+
+        be_e2e, ws_e2e = DeviceBackend(dev), {}
+        slab_e2e = gene_slab(p, world)
+        h2d_bytes = int(8 * n * max(0, min(p, (rank + 1) * slab_e2e) - min(p, rank * slab_e2e)))
+        e2e_note = ("bixverse_b200.distributed.host_sharded_cor_upper (C ABI underneath) with pinned host buffers: gene-slab "
+                    "H2D, operand all-gather over NCCL, band-pipelined D2H")
+
+        def step_e2e():
+            host_sharded_cor_upper(be_e2e, x_pin, n, p, True, out_pin, 1, BETA, PREC[primary], workspace=ws_e2e)
 
     e2e_steps = max(1, min(steps, 5))
     for _ in range(2):
@@ -392,9 +475,9 @@ def run_ours(args):
                                     "slab, operand records all-gathered over NCCL" if world > 1 else "single GPU"),
                        "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
             "clocks": main["clocks"],
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(8 * n * p),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps,
-                    "note": "bixcor_cor_upper_rows through the C ABI with pinned host buffers; per-rank bytes"},
+                    "note": e2e_note + "; bytes are rank 0's"},
             "gpu_launches": main["gpu_launches"],
             "roofline": main["roofline"],
             "cpu_baseline": cpu_baseline,

@@ -1085,6 +1085,25 @@ int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm
   return finish_dev(c);
 }
 
+int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
+                                         int precision, int shift, double beta, int64_t row_begin,
+                                         int64_t row_end, double* h_out_slice) {
+  DEV_PROLOGUE();
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (!d_operand || !h_out_slice) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (precision < 0 || precision > 2) return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
+  if (row_begin == row_end) return BIXCOR_OK;
+  shift = shift ? 1 : 0;
+  Operand op;
+  bind_operand(&op, n, p, precision, d_operand, d_inv_norm);
+  const int64_t o0 = packed_row_offset(row_begin, p, shift), o1 = packed_row_offset(row_end, p, shift);
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o1 - o0)));
+  D2HPipe pipe(c, h_out_slice);
+  RC_TRY(dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, (double*)c->out.ptr, &pipe, h_out_slice));
+  RC_TRY(finish(c));
+  return pipe.finish();
+}
+
 int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out) {
   DEV_PROLOGUE();
   RC_TRY(dev_affinity(c, d_x, n, p, spearman, 1.0, 1, precision, 0, p, d_out));

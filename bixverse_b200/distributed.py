@@ -88,6 +88,22 @@ class DeviceBackend:
                                                     float(beta), r0, r1, out.data_ptr()))
         return out
 
+    def to_device(self, host_tensor):
+        return host_tensor.to(self.device, non_blocking=True)
+
+    def build_operand_slab(self, x_slab, n, spearman, precision, g0, g1, operand, inv_norm):
+        """x_slab holds only genes [g0,g1) (rows of the gene-major matrix); their records land at [g0,g1)."""
+        rb = self.operand_row_bytes(n, precision)
+        self._sync_in()
+        check(self.lib.bixcor_dev_build_operand(x_slab.data_ptr(), n, g1 - g0, int(spearman), precision, 0, g1 - g0,
+                                                operand.data_ptr() + g0 * rb, inv_norm.data_ptr() + 8 * g0))
+
+    def cor_upper_rows_op_to_host(self, operand, inv_norm, n, p, precision, shift, beta, r0, r1, out_host):
+        """Gram rows [r0,r1) straight into host memory; finished bands are copied while later ones compute."""
+        self._sync_in()
+        check(self.lib.bixcor_dev_cor_upper_rows_op_to_host(operand.data_ptr(), inv_norm.data_ptr(), n, p, precision,
+                                                            int(shift), float(beta), r0, r1, out_host.data_ptr()))
+
     def diffcor_rows(self, xa, na, xb, nb, p, spearman, precision, r0, r1):
         ln = packed_offset(r1, p, 1) - packed_offset(r0, p, 1)
         outs = [self.empty(max(ln, 1))[:ln] for _ in range(4)]
@@ -166,6 +182,36 @@ def sharded_cor_upper(backend, x, n, p, spearman, shift=1, beta=1.0, precision=P
         operand, inv = exchange_operand(backend, x, n, p, spearman, precision, group)
         out = backend.cor_upper_rows_op(operand, inv, n, p, precision, shift, beta, r0, r1)
     return out, (packed_offset(r0, p, shift), packed_offset(r1, p, shift))
+
+
+def host_sharded_cor_upper(backend, x_host, n, p, spearman, out_host, shift=1, beta=1.0, precision=PREC_F64,
+                           group=None, workspace=None):
+    """End-to-end packed correlation of one rank, host memory to host memory.
+
+    x_host: the p x n gene-major host tensor (== R's column-major n x p matrix), ideally pinned; only
+    this rank's gene slab crosses PCIe.  The slab is rank-transformed / standardised on the device, the
+    operand records are all-gathered over NCCL (NVLink), and the rank's pair-balanced block rows are
+    written into out_host (its packed slice, length o1 - o0) with the device-to-host copy of finished
+    bands overlapped with the Gram of later bands.  `workspace` (dict) caches the device buffers."""
+    rank, world = _world(group)
+    r0, r1 = pair_balanced_rows(p, shift, world, rank)
+    slab = gene_slab(p, world)
+    rb = backend.operand_row_bytes(n, precision)
+    ws = workspace if workspace is not None else {}
+    key = (n, p, precision, world)
+    if ws.get("key") != key:
+        ws.clear()
+        ws.update(key=key, operand=backend.empty_bytes(world * slab * rb), inv=backend.zeros(world * slab))
+    operand, inv = ws["operand"], ws["inv"]
+    g0, g1 = min(p, rank * slab), min(p, (rank + 1) * slab)
+    if g1 > g0:
+        x_slab = backend.to_device(x_host[g0:g1])
+        backend.build_operand_slab(x_slab, n, spearman, precision, g0, g1, operand, inv)
+    if world > 1:
+        dist.all_gather_into_tensor(operand, operand[rank * slab * rb : (rank + 1) * slab * rb], group=group)
+        dist.all_gather_into_tensor(inv, inv[rank * slab : (rank + 1) * slab], group=group)
+    backend.cor_upper_rows_op_to_host(operand, inv, n, p, precision, shift, beta, r0, r1, out_host)
+    return packed_offset(r0, p, shift), packed_offset(r1, p, shift)
 
 
 def sharded_diffcor(backend, xa, na, xb, nb, p, spearman, precision=PREC_F64, group=None):

@@ -147,6 +147,12 @@ int bixcor_dev_build_operand(const double* d_x, int64_t n, int64_t p, int spearm
 int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
                                  int precision, int shift, double beta, int64_t row_begin, int64_t row_end,
                                  double* d_out_slice);
+/* Same Gram, but the packed rows land in HOST memory: every finished band of block rows is copied
+ * device-to-host while later bands compute (the multi-process end-to-end path: H2D of one gene slab,
+ * operand all-gather over NVLink, then this call). h_out_slice may be pinned or pageable. */
+int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
+                                         int precision, int shift, double beta, int64_t row_begin,
+                                         int64_t row_end, double* h_out_slice);
 int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out_pp);
 int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
                             int spearman, int precision, int64_t row_begin, int64_t row_end, double* d_r_a,

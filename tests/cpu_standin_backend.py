@@ -42,6 +42,18 @@ class OracleBackend:
         full = o.soft_threshold(o.dense_to_upper_triangle(z.T @ z, bool(shift)), beta)
         return torch.from_numpy(np.ascontiguousarray(self._slice(full, p, shift, r0, r1)))
 
+    def to_device(self, host_tensor):
+        return host_tensor.clone()
+
+    def build_operand_slab(self, x_slab, n, spearman, precision, g0, g1, operand, inv_norm):
+        xs = x_slab.numpy().T  # n x (g1-g0)
+        z = o._standardise(o.rank_matrix_col(xs) if spearman else xs)
+        operand.numpy().view(np.float64).reshape(-1, n)[g0:g1] = z.T
+        inv_norm[g0:g1] = 1.0
+
+    def cor_upper_rows_op_to_host(self, operand, inv_norm, n, p, precision, shift, beta, r0, r1, out_host):
+        out_host.copy_(self.cor_upper_rows_op(operand, inv_norm, n, p, precision, shift, beta, r0, r1))
+
     def diffcor_rows(self, xa, na, xb, nb, p, spearman, precision, r0, r1):
         res = o.differential_cor(xa.numpy().T, xb.numpy().T, spearman)
         return {k: torch.from_numpy(np.ascontiguousarray(self._slice(v, p, 1, r0, r1))) for k, v in res.items()}

@@ -33,6 +33,11 @@ def _worker(rank, world, port, tmpdir):
         rng = [None] * world
         dist.all_gather_object(rng, (o0, o1))
         assert rng[0][0] == 0 and rng[-1][1] == full.shape[0] and all(a[1] == b[0] for a, b in zip(rng[:-1], rng[1:]))
+        # --- host-to-host driver: only the rank's gene slab is uploaded
+        r0, r1 = D.pair_balanced_rows(p, 1, world, rank)
+        out_host = torch.empty(D.packed_offset(r1, p, 1) - D.packed_offset(r0, p, 1), dtype=torch.float64)
+        h0, h1 = D.host_sharded_cor_upper(be, xt, n, p, True, out_host, 1, 6.0)
+        assert (h0, h1) == (o0, o1) and np.abs(out_host.numpy() - full[o0:o1]).max() < 1e-14
         # --- diffcor
         xb = synthetic_bulk(n + 7, p, seed=6)
         res, (d0, d1) = D.sharded_diffcor(be, xt, n, torch.from_numpy(np.ascontiguousarray(xb.T)), n + 7, p, False)

@@ -361,6 +361,31 @@ def test_operand_exchange_api(api, prec_name):
     assert _maxerr(direct.cpu().numpy(), ref) < (TOL32 if prec_name == "tf32" else TOL64)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_sharded_driver_single_rank(api, pinned):
+    """host -> host driver of the multi-process path (slab upload, operand build, band-pipelined D2H), world = 1."""
+    import torch
+
+    from bixverse_b200 import _lib
+    from bixverse_b200.distributed import DeviceBackend, host_sharded_cor_upper
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    n, p = 120, 1500
+    x = synthetic_bulk(n, p, seed=21, tie_heavy=True)
+    xt = torch.from_numpy(np.ascontiguousarray(x.T))
+    out = torch.empty(p * (p - 1) // 2, dtype=torch.float64)
+    if pinned:
+        xt, out = xt.pin_memory(), out.pin_memory()
+    be = DeviceBackend(torch.device("cuda", 0))
+    ws = {}
+    for _ in range(2):  # second call reuses the cached workspace
+        out.fill_(-7.0)
+        o0, o1 = host_sharded_cor_upper(be, xt, n, p, True, out, 1, 6.0, _lib.PREC_I8EXACT, workspace=ws)
+        assert (o0, o1) == (0, out.numel())
+        ref = o.soft_threshold(o.cor_upper_triangle(x, True, True), 6.0)
+        assert _maxerr(out.numpy(), ref) < TOL64
+
+
 # ----------------------------------------------------------------------------- sibling Gram kernels (SURVEY 8f row 3)
 def test_covariance_cor2_cov2cor_golden(api, golden_dir):
     """inst/tinytest/test_R_rust_equality.R:23-55,76-82 on the reference's own matrices."""
