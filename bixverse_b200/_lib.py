@@ -15,6 +15,7 @@ OK = 0
 ERR_NO_GPU, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 PREC_F64, PREC_TF32X3, PREC_I8EXACT = 0, 1, 2
 TOM_V1, TOM_V2 = 1, 2
+RBF_GAUSSIAN, RBF_BUMP, RBF_INVERSE_QUADRATIC = 1, 2, 3
 
 i64, i32, f64 = C.c_int64, C.c_int, C.c_double
 ptr = C.c_void_p
@@ -44,7 +45,12 @@ SIGNATURES = {
     "bixcor_cos": (i32, [ptr, i64, i64, ptr]),
     "bixcor_cor2": (i32, [ptr, i64, i64, ptr, i64, i32, ptr]),
     "bixcor_cov2cor": (i32, [ptr, i64, ptr]),
+    "bixcor_rbf": (i32, [ptr, i64, f64, i32, ptr]),
+    "bixcor_rbf_iterate_epsilons": (i32, [ptr, i64, i32, ptr, i32, i32, ptr]),
+    "bixcor_cor_upper_rbf": (i32, [ptr, i64, i64, i32, i32, f64, i32, i32, i32, ptr]),
+    "bixcor_coremo_stability": (i32, [ptr, i64, i64, ptr, i32, f64, i32, i32, i32, ptr]),
     "bixcor_sparse_gram_cor": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr]),
+    "bixcor_sparse_pairwise_cor": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr, ptr, i64, i32, ptr]),
     "bixcor_dev_rank_columns": (i32, [ptr, i64, i64, ptr]),
     "bixcor_dev_cor_upper_rows": (i32, [ptr, i64, i64, i32, i32, f64, i32, i64, i64, ptr]),
     "bixcor_dev_operand_row_bytes": (i64, [i64, i32]),

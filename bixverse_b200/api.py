@@ -12,6 +12,10 @@ rs_cor_upper_triangle       src/rust/src/base/r_cors_similarity.rs:251-268
 rs_differential_cor         src/rust/src/methods/r_diffcor.rs:45-74
 rs_tom                      src/rust/src/methods/r_coremo.rs:46-59
 rs_rank_matrix_col          src/rust/src/enrichment/r_singscore.rs:89-95
+rs_rbf_function[_mat]       src/rust/src/base/r_rbf.rs:36-83
+rs_rbf_iterate_epsilons     src/rust/src/base/r_rbf.rs:118-131
+rs_coremo_stability         src/rust/src/methods/r_coremo.rs:191-235
+rs_pairwise_gene_cors_mc    src/rust/src/meta_cell/r_mc_processing.rs:258-283
 rs_upper_triangle_to_dense  src/rust/src/base/r_helpers.rs:75-94
 rs_dense_to_upper_triangle  src/rust/src/base/r_helpers.rs:113-134
 calculate_tom               R/functions_stats.R:43-59
@@ -35,6 +39,7 @@ from ._lib import PREC_F64, PREC_I8EXACT, PREC_TF32X3, TOM_V1, TOM_V2, BixcorErr
 __all__ = [
     "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
     "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "calculate_tom", "calculate_tom_from_exp",
+    "rs_rbf_function", "rs_rbf_function_mat", "rs_rbf_iterate_epsilons", "rs_coremo_stability", "cor_upper_triangle_rbf", "rs_pairwise_gene_cors_mc",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
     "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "BixcorError",
 ]
@@ -212,6 +217,75 @@ def rs_dense_to_upper_triangle(x, shift: bool) -> np.ndarray:
     return out
 
 
+def _parse_rbf_types(rbf_type: str) -> int:
+    # crate parse_rbf_types; anything else is "Invalid RBF function" (r_rbf.rs:37-38)
+    try:
+        return {"gaussian": _lib.RBF_GAUSSIAN, "bump": _lib.RBF_BUMP, "inverse_quadratic": _lib.RBF_INVERSE_QUADRATIC}[rbf_type]
+    except KeyError:
+        raise ValueError(f"Invalid RBF function: {rbf_type}") from None
+
+
+def rs_rbf_function(x, epsilon: float, rbf_type: str) -> np.ndarray:
+    """src/rust/src/base/r_rbf.rs:36-48."""
+    mode = _parse_rbf_types(rbf_type)
+    v = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    out = np.empty_like(v)
+    check(_lib.load().bixcor_rbf(_p(v), v.shape[0], float(epsilon), mode, _p(out)))
+    return out
+
+
+def rs_rbf_function_mat(x, epsilon: float, rbf_type: str) -> np.ndarray:
+    """src/rust/src/base/r_rbf.rs:66-83."""
+    mode = _parse_rbf_types(rbf_type)
+    a = _fmat(x)
+    out = np.empty(a.shape, dtype=np.float64, order="F")
+    check(_lib.load().bixcor_rbf(_p(a), a.size, float(epsilon), mode, _p(out)))
+    return out
+
+
+def rs_rbf_iterate_epsilons(dist, epsilon_vec, original_dim: int, shift: bool, rbf_type: str) -> np.ndarray:
+    """src/rust/src/base/r_rbf.rs:118-131; an unknown rbf_type falls back to gaussian like the reference doc says."""
+    mode = {"bump": _lib.RBF_BUMP, "inverse_quadratic": _lib.RBF_INVERSE_QUADRATIC}.get(rbf_type, _lib.RBF_GAUSSIAN)
+    v = np.ascontiguousarray(dist, dtype=np.float64)
+    eps = np.ascontiguousarray(epsilon_vec, dtype=np.float64)
+    lib = _lib.load()
+    if v.shape[0] != lib.bixcor_packed_len(original_dim, int(bool(shift))):
+        raise ValueError("packed length does not match original_dim")
+    out = np.empty((original_dim, eps.shape[0]), dtype=np.float64, order="F")
+    check(lib.bixcor_rbf_iterate_epsilons(_p(v), original_dim, int(bool(shift)), _p(eps), eps.shape[0], mode, _p(out)))
+    return out
+
+
+def rs_coremo_stability(data, indices, epsilon: float, rbf_type: str, spearman: bool,
+                        precision: int = PREC_F64) -> list[np.ndarray]:
+    """src/rust/src/methods/r_coremo.rs:191-235: one packed distance vector per left-out (1-based) sample."""
+    import ctypes as C
+
+    mode = _parse_rbf_types(rbf_type)
+    a = _fmat(data)
+    n, p = a.shape
+    idx = np.ascontiguousarray(indices, dtype=np.int32)
+    lib = _lib.load()
+    outs = [np.empty(lib.bixcor_packed_len(p, 1), dtype=np.float64) for _ in range(idx.shape[0])]
+    ptrs = (C.c_void_p * max(1, idx.shape[0]))(*[o.ctypes.data for o in outs])
+    check(lib.bixcor_coremo_stability(_p(a), n, p, _p(idx), idx.shape[0], float(epsilon), mode, int(bool(spearman)),
+                                      precision, C.cast(ptrs, C.c_void_p)))
+    return outs
+
+
+def cor_upper_triangle_rbf(x, spearman: bool, epsilon: float, rbf_type: str, shift: bool = True,
+                           complement: bool = False, precision: int = PREC_F64) -> np.ndarray:
+    """Fused rs_cor_upper_triangle -> 1 - |r| -> rs_rbf_function (R/methods_coexp_cor.R:357-370) in one Gram pass."""
+    mode = _parse_rbf_types(rbf_type)
+    a = _fmat(x)
+    n, p = a.shape
+    lib = _lib.load()
+    out = np.empty(lib.bixcor_packed_len(p, int(bool(shift))), dtype=np.float64)
+    check(lib.bixcor_cor_upper_rbf(_p(a), n, p, int(bool(spearman)), int(bool(shift)), float(epsilon), mode,
+                                   int(bool(complement)), precision, _p(out)))
+    return out
+
+
 def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int, precision: int = PREC_F64) -> np.ndarray:
     """All-pairs Pearson over a cells x genes CSR matrix (north-star extension of
     rs_pairwise_gene_cors_mc, src/rust/src/meta_cell/r_mc_processing.rs:258-283)."""
@@ -223,6 +297,32 @@ def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int
     lib = _lib.load()
     out = np.empty(lib.bixcor_packed_len(genes, 1), dtype=np.float64)
     check(lib.bixcor_sparse_gram_cor(_p(ip), _p(ix), _p(dt), cells, genes, precision, _p(out)))
+    return out
+
+
+def rs_pairwise_gene_cors_mc(sparse_data: dict, gene_indices_1, gene_indices_2, spearman: bool) -> np.ndarray:
+    """src/rust/src/meta_cell/r_mc_processing.rs:258-283.  `sparse_data` is the reference's sparse list:
+    ``data``, ``indptr``, ``indices`` (0-based), ``nrow`` (cells), ``ncol`` (genes) and ``format`` ("csr"/"csc");
+    gene indices are 0-based, like the reference demands."""
+    for k in ("data", "indptr", "indices", "nrow", "ncol", "format"):
+        if k not in sparse_data:
+            raise ValueError(f"sparse_data is missing '{k}'")
+    fmt = str(sparse_data["format"]).lower()
+    if fmt not in ("csr", "csc"):
+        raise ValueError(f"unknown sparse format: {sparse_data['format']}")
+    cells, genes = int(sparse_data["nrow"]), int(sparse_data["ncol"])
+    ip = np.ascontiguousarray(sparse_data["indptr"], dtype=np.int64)
+    ix = np.ascontiguousarray(sparse_data["indices"], dtype=np.int32)
+    dt = np.ascontiguousarray(sparse_data["data"], dtype=np.float32)  # the reference casts to f32 (:267-269)
+    if ip.shape[0] != (cells if fmt == "csr" else genes) + 1:
+        raise ValueError("indptr length does not match the sparse format")
+    g1 = np.ascontiguousarray(gene_indices_1, dtype=np.int32)
+    g2 = np.ascontiguousarray(gene_indices_2, dtype=np.int32)
+    if g1.shape != g2.shape:
+        raise ValueError("gene_indices_1 and gene_indices_2 need the same length")
+    out = np.empty(g1.shape[0], dtype=np.float64)
+    check(_lib.load().bixcor_sparse_pairwise_cor(_p(ip), _p(ix), _p(dt), cells, genes, int(fmt == "csr"), _p(g1), _p(g2),
+                                                 g1.shape[0], int(bool(spearman)), _p(out)))
     return out
 
 

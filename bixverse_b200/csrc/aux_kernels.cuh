@@ -3,6 +3,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace bixcor {
 
@@ -37,6 +38,142 @@ cov2cor_kernel(const double* __restrict__ cov, int64_t p, double* __restrict__ o
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= p) return;
   out[i + j * p] = cov[i + j * p] / sqrt(cov[i + i * p] * cov[j + j * p]);
+}
+
+// rs_rbf_function / rs_rbf_function_mat (src/rust/src/base/r_rbf.rs:36-83): elementwise phi(d).
+__global__ void __launch_bounds__(256)
+rbf_elementwise_kernel(const double* __restrict__ d, int64_t len, int mode, double eps, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += stride)
+    out[i] = rbf_apply(mode, eps, d[i]);
+}
+
+// rs_rbf_iterate_epsilons (r_rbf.rs:118-131): for every epsilon the column sums of the symmetric affinity
+// matrix rebuilt from the packed distance vector (diagonal := 1 when shift, as rs_upper_triangle_to_dense does).
+// Two deterministic passes over the packed vector, all epsilons at once (NE_MAX accumulators per thread):
+//   rows:    k[i] += sum_{j > i} phi(d_ij)   one warp per row, contiguous run
+//   columns: k[j] += sum_{i < j} phi(d_ij)   one thread per column, consecutive threads read consecutive words,
+//            rows split into chunks whose partial sums are reduced in a fixed order by the caller.
+constexpr int kRbfMaxEps = 32;
+struct RbfEps {
+  int n;
+  double eps[kRbfMaxEps];
+};
+
+__global__ void __launch_bounds__(256)
+rbf_rowsum_kernel(const double* __restrict__ packed, int64_t p, int shift, int mode, RbfEps E, double* __restrict__ k) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= p) return;
+  const double* row = packed + packed_row_offset(i, p, shift);
+  const int64_t len = p - i - shift;  // elements (i, j) for j >= i + shift
+  double acc[kRbfMaxEps];
+#pragma unroll
+  for (int e = 0; e < kRbfMaxEps; ++e) acc[e] = 0.0;
+  for (int64_t q = lane; q < len; q += 32) {
+    const double d = row[q];
+    const bool diag = (shift == 0 && q == 0);  // the stored diagonal is counted once, by the column pass
+#pragma unroll
+    for (int e = 0; e < kRbfMaxEps; ++e)
+      if (e < E.n && !diag) acc[e] += rbf_apply(mode, E.eps[e], d);
+  }
+#pragma unroll
+  for (int e = 0; e < kRbfMaxEps; ++e) {
+    if (e < E.n) {
+      const double s = warp_sum(acc[e]);
+      if (lane == 0) k[(int64_t)e * p + i] = s + (shift ? 1.0 : 0.0);
+    }
+  }
+}
+
+// partial[(chunk * ne + e) * p + j] = sum over rows i in [chunk*rows_per_chunk, ...) with i < j (i <= j if !shift)
+__global__ void __launch_bounds__(128)
+rbf_colsum_kernel(const double* __restrict__ packed, int64_t p, int shift, int mode, RbfEps E, int rows_per_chunk,
+                  double* __restrict__ partial) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int64_t i0 = (int64_t)chunk * rows_per_chunk;
+  if (j >= p) return;
+  const int64_t i1 = min((int64_t)(i0 + rows_per_chunk), shift ? j : j + 1);
+  double acc[kRbfMaxEps];
+#pragma unroll
+  for (int e = 0; e < kRbfMaxEps; ++e) acc[e] = 0.0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const double d = packed[packed_row_offset(i, p, shift) + (j - i - shift)];
+#pragma unroll
+    for (int e = 0; e < kRbfMaxEps; ++e)
+      if (e < E.n) acc[e] += rbf_apply(mode, E.eps[e], d);
+  }
+#pragma unroll
+  for (int e = 0; e < kRbfMaxEps; ++e)
+    if (e < E.n) partial[((int64_t)chunk * E.n + e) * p + j] = acc[e];
+}
+
+// k[e][j] += sum_chunk partial[chunk][e][j] in chunk order (deterministic)
+__global__ void rbf_reduce_kernel(const double* __restrict__ partial, int64_t p, int ne, int nchunks, double* __restrict__ k) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (j >= p) return;
+  double s = k[(int64_t)e * p + j];
+  for (int c = 0; c < nchunks; ++c) s += partial[((int64_t)c * ne + e) * p + j];
+  k[(int64_t)e * p + j] = s;
+}
+
+// rs_coremo_stability: drop sample `s` from every gene's column (column-major n x p -> (n-1) x p).
+__global__ void __launch_bounds__(128)
+remove_row_kernel(const double* __restrict__ x, int64_t n, int64_t s, double* __restrict__ out) {
+  const int64_t j = blockIdx.x;
+  for (int64_t i = threadIdx.x; i < n - 1; i += blockDim.x) out[j * (n - 1) + i] = x[j * n + (i < s ? i : i + 1)];
+}
+
+// Pair-list path (rs_pairwise_gene_cors_mc, src/rust/src/meta_cell/r_mc_processing.rs:258-283): only the genes
+// that occur in the pair lists are densified, gene-major (slot s holds its `cells` values contiguously).
+// slot_of[g] = dense slot of gene g or -1.  CSR (rows = cells): one warp per cell.
+__global__ void __launch_bounds__(256)
+csr_gather_genes_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const float* __restrict__ data, int64_t cells, int64_t genes,
+                        const int32_t* __restrict__ slot_of, double* __restrict__ dense, int64_t ld) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= cells) return;
+  const int64_t b = indptr[warp], e = indptr[warp + 1];
+  for (int64_t q = b + lane; q < e; q += 32) {
+    const int64_t g = indices[q];
+    if (g < 0 || g >= genes) continue;
+    const int s = slot_of[g];
+    if (s >= 0) dense[(int64_t)s * ld + warp] = (double)data[q];
+  }
+}
+// CSC (columns = genes): one CTA per used gene (gene_of_slot[s]).
+__global__ void __launch_bounds__(256)
+csc_gather_genes_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const float* __restrict__ data, int64_t cells, const int32_t* __restrict__ gene_of_slot,
+                        double* __restrict__ dense, int64_t ld) {
+  const int64_t s = blockIdx.x;
+  const int64_t g = gene_of_slot[s];
+  const int64_t b = indptr[g], e = indptr[g + 1];
+  for (int64_t q = b + threadIdx.x; q < e; q += blockDim.x) {
+    const int64_t cidx = indices[q];
+    if (cidx >= 0 && cidx < cells) dense[s * ld + cidx] = (double)data[q];
+  }
+}
+// out[k] = <Z[slot1[k]], Z[slot2[k]]> over K (unit-norm centred columns -> the correlation).  One warp per pair.
+__global__ void __launch_bounds__(256)
+pair_dot_kernel(const double* __restrict__ z, int64_t K, const int32_t* __restrict__ s1, const int32_t* __restrict__ s2,
+                int64_t npairs, double* __restrict__ out) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= npairs) return;
+  const double2* a = reinterpret_cast<const double2*>(z + (int64_t)s1[warp] * K);
+  const double2* b = reinterpret_cast<const double2*>(z + (int64_t)s2[warp] * K);
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int64_t i = lane; i < K / 2; i += 32) {
+    const double2 u = a[i], v = b[i];
+    acc0 = fma(u.x, v.x, acc0);
+    acc1 = fma(u.y, v.y, acc1);
+  }
+  const double sum = warp_sum(acc0 + acc1);
+  if (lane == 0) out[warp] = sum;
 }
 
 __global__ void fill_kernel(double* __restrict__ x, int64_t n, double v) {

@@ -611,8 +611,17 @@ static int validate_rows(int64_t p, int64_t row_begin, int64_t row_end) {
 
 // Packed correlation of rows [row_begin,row_end).  If `pipe` is given, every
 // finished band is copied to h_out (host slice) while later bands compute.
+// optional RBF transform of the correlation in the epilogue
+struct RbfSpec {
+  int mode = 0;
+  double eps = 1.0;
+  int from_cor = 1;
+  int complement = 0;
+};
+
 static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift, double beta, int64_t row_begin,
-                                 int64_t row_end, double* d_out, D2HPipe* pipe, double* h_out) {
+                                 int64_t row_end, double* d_out, D2HPipe* pipe, double* h_out,
+                                 const RbfSpec* rbf = nullptr) {
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
   EpiParams e = make_epi(p);
@@ -620,6 +629,12 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
   e.out_base = packed_row_offset(row_begin, p, shift);
   e.shift = shift;
   set_beta(e, beta, 0);
+  if (rbf && rbf->mode) {
+    e.rbf_mode = rbf->mode;
+    e.rbf_eps = rbf->eps;
+    e.rbf_from_cor = rbf->from_cor;
+    e.rbf_complement = rbf->complement;
+  }
   if (!pipe)  // results stay in HBM: one launch over all tiles (no per-band tail)
     return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_PACKED, e);
   const int ngroups = (int)tl->group_tile.size() - 1;
@@ -637,12 +652,19 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
 
 static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
                               int precision, int64_t row_begin, int64_t row_end, double* d_out, D2HPipe* pipe,
-                              double* h_out) {
+                              double* h_out, const RbfSpec* rbf = nullptr) {
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (row_begin == row_end) return BIXCOR_OK;
   Operand op;
   RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
-  return dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, d_out, pipe, h_out);
+  return dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, d_out, pipe, h_out, rbf);
+}
+
+static int check_rbf(int rbf_type, double epsilon) {
+  if (rbf_type != BIXCOR_RBF_GAUSSIAN && rbf_type != BIXCOR_RBF_BUMP && rbf_type != BIXCOR_RBF_INVERSE_QUADRATIC)
+    return fail(BIXCOR_ERR_INVALID, "Invalid RBF function: %d", rbf_type);
+  if (!(epsilon > 0.0)) return fail(BIXCOR_ERR_INVALID, "epsilon must be positive");
+  return BIXCOR_OK;
 }
 
 static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
@@ -1416,6 +1438,234 @@ int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp) {
   RC_TRY(finish(c));
   D2HPipe pipe(c, out_pp);
   RC_TRY(pipe.push(out_pp, c->out.ptr, bytes, nullptr));
+  return pipe.finish();
+}
+
+// ---- RBF affinities and CoReMo stability ("next" rows 1-2 of SURVEY 8f) --------------------------
+int bixcor_rbf(const double* x, int64_t len, double epsilon, int rbf_type, double* out) {
+  RC_TRY(ensure_init());
+  if (len < 0 || (len > 0 && (!x || !out))) return fail(BIXCOR_ERR_INVALID, "null pointer / bad length");
+  RC_TRY(check_rbf(rbf_type, epsilon));
+  if (len == 0) return BIXCOR_OK;
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t bytes = sizeof(double) * (size_t)len;
+  RC_TRY(c->out2.reserve(bytes));
+  RC_TRY(c->out.reserve(bytes));
+  RC_TRY(h2d(c, c->out2.ptr, x, bytes, c->compute));
+  {
+    Timed tm(c, T_OTHER);
+    const unsigned grid = (unsigned)std::min<int64_t>((len + 255) / 256, (int64_t)c->sm_count * 16);
+    rbf_elementwise_kernel<<<grid, 256, 0, c->compute>>>((const double*)c->out2.ptr, len, rbf_type, epsilon,
+                                                          (double*)c->out.ptr);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out);
+  RC_TRY(pipe.push(out, c->out.ptr, bytes, nullptr));
+  return pipe.finish();
+}
+
+int bixcor_rbf_iterate_epsilons(const double* dist_packed, int64_t p, int shift, const double* epsilons, int n_eps,
+                                int rbf_type, double* out_p_x_neps) {
+  RC_TRY(ensure_init());
+  if (!dist_packed || !epsilons || !out_p_x_neps) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (p < 1 || n_eps < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
+  for (int e = 0; e < n_eps; ++e) RC_TRY(check_rbf(rbf_type, epsilons[e]));
+  shift = shift ? 1 : 0;
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const int64_t len = shift ? p * (p - 1) / 2 : p * (p + 1) / 2;
+  const int rows_per_chunk = 512;
+  const int nchunks = (int)((p + rows_per_chunk - 1) / rows_per_chunk);
+  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, len)));
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)p * n_eps));
+  RC_TRY(c->panel.reserve(sizeof(double) * (size_t)p * kRbfMaxEps * nchunks));
+  RC_TRY(h2d(c, c->out2.ptr, dist_packed, sizeof(double) * (size_t)len, c->compute));
+  for (int e0 = 0; e0 < n_eps; e0 += kRbfMaxEps) {
+    RbfEps E;
+    E.n = std::min(kRbfMaxEps, n_eps - e0);
+    for (int e = 0; e < kRbfMaxEps; ++e) E.eps[e] = e < E.n ? epsilons[e0 + e] : 1.0;
+    double* k = (double*)c->out.ptr + (size_t)e0 * p;
+    Timed tm(c, T_OTHER);
+    rbf_rowsum_kernel<<<(unsigned)((p + 7) / 8), 256, 0, c->compute>>>((const double*)c->out2.ptr, p, shift, rbf_type, E, k);
+    dim3 gc((unsigned)((p + 127) / 128), (unsigned)nchunks);
+    rbf_colsum_kernel<<<gc, 128, 0, c->compute>>>((const double*)c->out2.ptr, p, shift, rbf_type, E, rows_per_chunk,
+                                                  (double*)c->panel.ptr);
+    dim3 gr((unsigned)((p + 255) / 256), (unsigned)E.n);
+    rbf_reduce_kernel<<<gr, 256, 0, c->compute>>>((const double*)c->panel.ptr, p, E.n, nchunks, k);
+    g_launches += 3;
+  }
+  CU_TRY(cudaGetLastError());
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out_p_x_neps);
+  RC_TRY(pipe.push(out_p_x_neps, c->out.ptr, sizeof(double) * (size_t)p * n_eps, nullptr));
+  return pipe.finish();
+}
+
+int bixcor_cor_upper_rbf(const double* x, int64_t n, int64_t p, int spearman, int shift, double epsilon, int rbf_type,
+                         int complement, int precision, double* out_packed) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out_packed));
+  RC_TRY(check_rbf(rbf_type, epsilon));
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  shift = shift ? 1 : 0;
+  const int64_t len = shift ? p * (p - 1) / 2 : p * (p + 1) / 2;
+  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, len)));
+  RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
+  RbfSpec rbf;
+  rbf.mode = rbf_type;
+  rbf.eps = epsilon;
+  rbf.complement = complement ? 1 : 0;
+  D2HPipe pipe(c, out_packed);
+  RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[0].ptr, n, p, spearman, shift, 1.0, precision, 0, p,
+                            (double*)c->out.ptr, &pipe, out_packed, &rbf));
+  RC_TRY(finish(c));
+  return pipe.finish();
+}
+
+int bixcor_coremo_stability(const double* x, int64_t n, int64_t p, const int32_t* indices_1based, int n_idx,
+                            double epsilon, int rbf_type, int spearman, int precision, double* const* outs) {
+  RC_TRY(ensure_init());
+  if (!x || !indices_1based || !outs) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (n < 3) return fail(BIXCOR_ERR_INVALID, "need at least 3 samples to leave one out (n = %lld)", (long long)n);
+  if (p < 1 || n_idx < 0) return fail(BIXCOR_ERR_INVALID, "bad shape");
+  RC_TRY(check_rbf(rbf_type, epsilon));
+  for (int k = 0; k < n_idx; ++k) {
+    if (indices_1based[k] < 1 || indices_1based[k] > n)
+      return fail(BIXCOR_ERR_INVALID, "sample index %d out of range 1..%lld", indices_1based[k], (long long)n);
+    if (!outs[k]) return fail(BIXCOR_ERR_INVALID, "null output vector %d", k);
+  }
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const int64_t len = p * (p - 1) / 2;
+  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
+  RC_TRY(c->x[1].reserve(sizeof(double) * (size_t)(n - 1) * p));
+  RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
+  RbfSpec rbf;
+  rbf.mode = rbf_type;
+  rbf.eps = epsilon;
+  rbf.complement = 1;  // 1 - phi(1 - |r|)
+  // two result buffers: the D2H of sample k overlaps the kernels of sample k + 1
+  Buffer* res[2] = {&c->out, &c->out2};
+  for (auto* b : res) RC_TRY(b->reserve(sizeof(double) * (size_t)std::max<int64_t>(1, len)));
+  D2HPipe pipe(c, n_idx ? outs[0] : nullptr);
+  cudaEvent_t reuse[2] = {nullptr, nullptr};
+  for (int k = 0; k < n_idx; ++k) {
+    const int b = k & 1;
+    if (reuse[b]) CU_TRY(cudaStreamWaitEvent(c->compute, reuse[b], 0));  // its previous D2H has drained
+    {
+      Timed tm(c, T_OTHER);
+      remove_row_kernel<<<(unsigned)p, 128, 0, c->compute>>>((const double*)c->x[0].ptr, n, indices_1based[k] - 1,
+                                                             (double*)c->x[1].ptr);
+      g_launches++;
+    }
+    RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[1].ptr, n - 1, p, spearman, 1, 1.0, precision, 0, p,
+                              (double*)res[b]->ptr, nullptr, nullptr, &rbf));
+    cudaEvent_t ev = ctx_event(c);
+    CU_TRY(cudaEventRecord(ev, c->compute));
+    RC_TRY(pipe.push(outs[k], res[b]->ptr, sizeof(double) * (size_t)len, ev));
+    if (!pipe.pinned_dst) {
+      RC_TRY(pipe.finish());  // pageable destinations go through the staging ring synchronously
+      reuse[b] = nullptr;
+    } else {
+      reuse[b] = ctx_event(c);
+      CU_TRY(cudaEventRecord(reuse[b], c->copy_out));
+    }
+  }
+  RC_TRY(finish(c));
+  return pipe.finish();
+}
+
+// rs_pairwise_gene_cors_mc (src/rust/src/meta_cell/r_mc_processing.rs:258-283)
+int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                               int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
+                               int64_t n_pairs, int spearman, double* out) {
+  RC_TRY(ensure_init());
+  if (!indptr || n_pairs < 0 || (n_pairs > 0 && (!gene_idx1 || !gene_idx2 || !out)))
+    return fail(BIXCOR_ERR_INVALID, "null pointer / bad pair count");
+  if (cells < 2 || genes < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
+  if (n_pairs == 0) return BIXCOR_OK;
+  const int64_t nptr = (is_csr ? cells : genes) + 1;
+  const int64_t nnz = indptr[nptr - 1];
+  if (nnz < 0 || (nnz > 0 && (!indices || !data))) return fail(BIXCOR_ERR_INVALID, "bad sparse arrays");
+  if (spearman && cells > 16384)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman pair correlations support <= 16384 cells (got %lld)", (long long)cells);
+  // dense slots for the genes that actually occur
+  std::vector<int32_t> slot_of((size_t)genes, -1), gene_of_slot, s1((size_t)n_pairs), s2((size_t)n_pairs);
+  for (int64_t k = 0; k < n_pairs; ++k) {
+    const int32_t ga = gene_idx1[k], gb = gene_idx2[k];
+    if (ga < 0 || ga >= genes || gb < 0 || gb >= genes)
+      return fail(BIXCOR_ERR_INVALID, "gene index out of range at pair %lld (0-based indices expected)", (long long)k);
+    for (int32_t g : {ga, gb})
+      if (slot_of[g] < 0) {
+        slot_of[g] = (int32_t)gene_of_slot.size();
+        gene_of_slot.push_back(g);
+      }
+    s1[k] = slot_of[ga];
+    s2[k] = slot_of[gb];
+  }
+  const int64_t u = (int64_t)gene_of_slot.size();
+  const int K = round_up((int)cells, dmma::BK);
+  if ((double)u * (double)(cells + K) * 8.0 > 120e9)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "pair list touches %lld genes x %lld cells: split the pair list", (long long)u,
+                (long long)cells);
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const size_t b_ptr = sizeof(int64_t) * (size_t)nptr, b_idx = sizeof(int32_t) * (size_t)nnz,
+               b_dat = sizeof(float) * (size_t)nnz, b_map = sizeof(int32_t) * (size_t)genes,
+               b_gos = sizeof(int32_t) * (size_t)u, b_pair = sizeof(int32_t) * (size_t)n_pairs;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + al(b_map) + al(b_gos) + 2 * al(b_pair) + 256));
+  char* base = (char*)c->sparse_in.ptr;
+  int64_t* d_ptr = (int64_t*)base;
+  int32_t* d_idx = (int32_t*)(base + al(b_ptr));
+  float* d_dat = (float*)((char*)d_idx + al(b_idx));
+  int32_t* d_map = (int32_t*)((char*)d_dat + al(b_dat));
+  int32_t* d_gos = (int32_t*)((char*)d_map + al(b_map));
+  int32_t* d_s1 = (int32_t*)((char*)d_gos + al(b_gos));
+  int32_t* d_s2 = (int32_t*)((char*)d_s1 + al(b_pair));
+  RC_TRY(h2d(c, d_ptr, indptr, b_ptr, c->compute));
+  RC_TRY(h2d(c, d_idx, indices, b_idx, c->compute));
+  RC_TRY(h2d(c, d_dat, data, b_dat, c->compute));
+  RC_TRY(h2d(c, d_map, slot_of.data(), b_map, c->compute));
+  RC_TRY(h2d(c, d_gos, gene_of_slot.data(), b_gos, c->compute));
+  RC_TRY(h2d(c, d_s1, s1.data(), b_pair, c->compute));
+  RC_TRY(h2d(c, d_s2, s2.data(), b_pair, c->compute));
+  CU_TRY(cudaStreamSynchronize(c->compute));  // the index vectors above are stack/heap temporaries
+  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)u * cells));
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)n_pairs));
+  CU_TRY(cudaMemsetAsync(c->x[0].ptr, 0, sizeof(double) * (size_t)u * cells, c->compute));
+  {
+    Timed tm(c, T_OTHER);
+    if (is_csr)
+      csr_gather_genes_kernel<<<(unsigned)((cells * 32 + 255) / 256), 256, 0, c->compute>>>(
+          d_ptr, d_idx, d_dat, cells, genes, d_map, (double*)c->x[0].ptr, cells);
+    else
+      csc_gather_genes_kernel<<<(unsigned)u, 256, 0, c->compute>>>(d_ptr, d_idx, d_dat, cells, d_gos,
+                                                                   (double*)c->x[0].ptr, cells);
+    g_launches++;
+  }
+  Operand op;
+  RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, cells, u, spearman, BIXCOR_PREC_F64, 0, &op));
+  {
+    Timed tm(c, T_OTHER);
+    pair_dot_kernel<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, c->compute>>>(op.z64, op.K, d_s1, d_s2, n_pairs,
+                                                                                   (double*)c->out.ptr);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  RC_TRY(finish(c));
+  D2HPipe pipe(c, out);
+  RC_TRY(pipe.push(out, c->out.ptr, sizeof(double) * (size_t)n_pairs, nullptr));
   return pipe.finish();
 }
 

@@ -40,9 +40,32 @@ struct EpiParams {
   const double* dvec;  // TOM: diagonal of A
   int tom_v2;
   int tom_packed;
+  // RBF affinity transform (crate core::math::rbf behind src/rust/src/base/r_rbf.rs and the
+  // distance -> affinity step of rs_coremo_stability, src/rust/src/methods/r_coremo.rs:211-226)
+  int rbf_mode;        // 0 none, BIXCOR_RBF_GAUSSIAN / _BUMP / _INVERSE_QUADRATIC
+  double rbf_eps;
+  int rbf_from_cor;    // input is a correlation: distance d = 1 - |r| first
+  int rbf_complement;  // write 1 - phi(d) (rs_coremo_stability returns the RBF *distance*)
 };
 
+enum RbfMode : int { RBF_NONE = 0, RBF_GAUSSIAN = 1, RBF_BUMP = 2, RBF_INVERSE_QUADRATIC = 3 };
+
+// phi(d) for the three kernels of the reference (rs_rbf_function): gaussian exp(-(eps d)^2), bump
+// exp(-1 / (1 - (eps d)^2) + 1) for d < 1/eps and 0 beyond, inverse quadratic 1 / (1 + (eps d)^2).
+__device__ __forceinline__ double rbf_apply(int mode, double eps, double d) {
+  const double t = eps * d;
+  const double t2 = t * t;
+  if (mode == RBF_GAUSSIAN) return exp(-t2);
+  if (mode == RBF_BUMP) return (d < 1.0 / eps) ? exp(-1.0 / (1.0 - t2) + 1.0) : 0.0;
+  return 1.0 / (1.0 + t2);
+}
+
 __device__ __forceinline__ double epi_power(const EpiParams& E, double r) {
+  if (E.rbf_mode) {  // warp uniform
+    const double d = E.rbf_from_cor ? 1.0 - fabs(r) : r;
+    const double a = rbf_apply(E.rbf_mode, E.rbf_eps, d);
+    return E.rbf_complement ? 1.0 - a : a;
+  }
   if (E.beta == 1.0) return r;
   double a = fabs(r);
   const int bi = E.beta_int;  // warp-uniform: the branches below never diverge

@@ -405,7 +405,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int diag_one = E.diag_one;
     const int keep_sign = E.keep_sign;
     const double scale = E.scale;
-    const int pw_mode = (E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0);  // 1 identity, 6 = WGCNA default, 0 generic
+    // 1 identity, 6 = WGCNA default, 0 generic (any other exponent, or an RBF transform)
+    const int pw_mode = E.rbf_mode ? 0 : ((E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0));
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
       const int2 tile = P.tiles[t];
       const int row_base = tile.x * BM + ew * 32;

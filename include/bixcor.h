@@ -125,9 +125,41 @@ int bixcor_cos(const double* x, int64_t n, int64_t p, double* out_pp);
 int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq);
 int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp);
 
+/* RBF affinities.  `rbf_type` mirrors parse_rbf_types ("gaussian", "bump", "inverse_quadratic"):
+ *   rs_rbf_function / rs_rbf_function_mat  src/rust/src/base/r_rbf.rs:36-83  -> bixcor_rbf (a matrix is its flat storage)
+ *   rs_rbf_iterate_epsilons                src/rust/src/base/r_rbf.rs:118-131 -> bixcor_rbf_iterate_epsilons:
+ *     out is p x n_eps column-major, column e = column sums of the symmetric affinity matrix rebuilt from the
+ *     packed distances with epsilons[e] (diagonal := 1 when shift, as rs_upper_triangle_to_dense)
+ *   bixcor_cor_upper_rbf: fused correlation -> d = 1 - |r| -> phi(d) (or 1 - phi(d) when complement) in the Gram epilogue,
+ *     packed output; the R side computes this as rs_cor_upper_triangle + rs_rbf_function (R/methods_coexp_cor.R:357-370). */
+#define BIXCOR_RBF_GAUSSIAN 1
+#define BIXCOR_RBF_BUMP 2
+#define BIXCOR_RBF_INVERSE_QUADRATIC 3
+int bixcor_rbf(const double* x, int64_t len, double epsilon, int rbf_type, double* out);
+int bixcor_rbf_iterate_epsilons(const double* dist_packed, int64_t p, int shift, const double* epsilons, int n_eps,
+                                int rbf_type, double* out_p_x_neps);
+int bixcor_cor_upper_rbf(const double* x, int64_t n, int64_t p, int spearman, int shift, double epsilon, int rbf_type,
+                         int complement, int precision, double* out_packed);
+/* rs_coremo_stability (src/rust/src/methods/r_coremo.rs:191-235): for every 1-based sample index
+ * the packed (shift = 1) vector 1 - phi(1 - |r|) of the correlation without that sample; outs[k] receives
+ * p(p-1)/2 doubles for indices_1based[k].  Each leave-one-out pass re-ranks / re-standardises on the device and
+ * runs the Gram with the transform fused; the device-to-host copy of pass k overlaps the kernels of pass k + 1. */
+int bixcor_coremo_stability(const double* x, int64_t n, int64_t p, const int32_t* indices_1based, int n_idx,
+                            double epsilon, int rbf_type, int spearman, int precision, double* const* outs);
+
 /* cells x genes CSR (int64 indptr[cells+1], int32 indices, float data) -> packed shift=1 Pearson */
 int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                            int64_t genes, int precision, double* out_packed);
+
+/* Pair-list gene-gene correlations over a sparse cells x genes matrix:
+ *   rs_pairwise_gene_cors_mc  src/rust/src/meta_cell/r_mc_processing.rs:258-283
+ * The sparse list {indptr, indices (0-based), data} is CSR with rows = cells (is_csr != 0) or CSC with
+ * columns = genes (is_csr == 0).  gene_idx1/2 are 0-based (as the reference requires); out[k] is the Pearson
+ * (or Spearman: average-tie ranks over ALL cells, zeros tie) correlation of the two genes of pair k over all
+ * cells including the implicit zeros.  Only the genes named in the pair lists are densified on the device. */
+int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                               int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
+                               int64_t n_pairs, int spearman, double* out);
 
 /* ---- device-pointer entry points (inputs/outputs resident in HBM) ------ */
 /* All pointers are device pointers on the library's current device; work is

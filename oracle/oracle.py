@@ -53,6 +53,10 @@ __all__ = [
     "tom_from_exp",
     "sparse_gram_cor",
     "pairwise_gene_cors",
+    "pairwise_gene_cors_spearman",
+    "rbf_function",
+    "rbf_iterate_epsilons",
+    "coremo_stability",
     "shard_rows",
 ]
 
@@ -324,6 +328,59 @@ def pairwise_gene_cors(indptr, indices, data, cells: int, genes: int, idx1, idx2
     for t, (i, j) in enumerate(zip(idx1, idx2)):
         out[t] = np.corrcoef(dense[:, i], dense[:, j])[0, 1]
     return out
+
+
+def pairwise_gene_cors_spearman(indptr, indices, data, cells: int, genes: int, idx1, idx2) -> np.ndarray:
+    """Spearman flavour of the pair list: Pearson of the average-tie ranks over ALL cells (zeros tie)."""
+    dense = _csr_to_dense(indptr, indices, data, cells, genes)
+    out = np.empty(len(idx1), dtype=np.float64)
+    for t, (i, j) in enumerate(zip(idx1, idx2)):
+        out[t] = np.corrcoef(rank_average(dense[:, i]), rank_average(dense[:, j]))[0, 1]
+    return out
+
+
+# --------------------------------------------------------------------------
+# RBF affinities (crate core::math::rbf behind src/rust/src/base/r_rbf.rs:36-131) and the
+# leave-one-out CoReMo stability distances (src/rust/src/methods/r_coremo.rs:191-235).
+# The kernel formulas are not in the reference tree; they are the textbook definitions the
+# crate documents (gaussian exp(-(eps d)^2), inverse quadratic 1/(1+(eps d)^2), bump
+# exp(-1/(1-(eps d)^2) + 1) inside d < 1/eps, 0 outside).  PARITY UNPINNED: no reference test
+# holds values of these functions (they only feed hclust / Leiden fixtures).
+# --------------------------------------------------------------------------
+def rbf_function(d, epsilon: float, rbf_type: str) -> np.ndarray:
+    d = np.asarray(d, dtype=np.float64)
+    t2 = (epsilon * d) ** 2
+    if rbf_type == "gaussian":
+        return np.exp(-t2)
+    if rbf_type == "inverse_quadratic":
+        return 1.0 / (1.0 + t2)
+    if rbf_type == "bump":
+        out = np.zeros_like(d)
+        inside = d < 1.0 / epsilon
+        out[inside] = np.exp(-1.0 / (1.0 - t2[inside]) + 1.0)
+        return out
+    raise ValueError(f"Invalid RBF function: {rbf_type}")
+
+
+def rbf_iterate_epsilons(dist, epsilons, original_dim: int, shift: bool, rbf_type: str) -> np.ndarray:
+    """original_dim x len(epsilons): column sums of the symmetric affinity matrix rebuilt from the packed
+    distances (diagonal := 1 when shift, as rs_upper_triangle_to_dense, r_helpers.rs:83-84)."""
+    out = np.empty((original_dim, len(epsilons)), dtype=np.float64)
+    for e, eps in enumerate(epsilons):
+        aff = upper_triangle_to_dense(rbf_function(dist, eps, rbf_type), shift, original_dim)
+        out[:, e] = aff.sum(axis=0)
+    return out
+
+
+def coremo_stability(x, indices_1based, epsilon: float, rbf_type: str, spearman: bool) -> list[np.ndarray]:
+    """r_coremo.rs:204-226: drop one sample, correlate, d = 1 - |r| (packed, shift 1), return 1 - phi(d)."""
+    x = np.asarray(x, dtype=np.float64)
+    res = []
+    for idx in indices_1based:
+        red = np.delete(x, int(idx) - 1, axis=0)
+        d = 1.0 - np.abs(cor_upper_triangle(red, spearman, True))
+        res.append(1.0 - rbf_function(d, epsilon, rbf_type))
+    return res
 
 
 # --------------------------------------------------------------------------

@@ -410,3 +410,82 @@ def test_siblings_larger_shapes(api):
     assert c2.shape == (390, 200) and _maxerr(c2, ref) < 1e-10
     xn = x / np.sqrt((x * x).sum(axis=0))
     assert _maxerr(api.rs_cos(x), xn.T @ xn) < 1e-10
+
+
+# ----------------------------------------------------------------------------- RBF affinities + CoReMo stability
+@pytest.mark.parametrize("rbf_type", ["gaussian", "bump", "inverse_quadratic"])
+def test_rbf_function_and_epsilon_sweep(api, rbf_type):
+    rng = np.random.default_rng(5)
+    d = np.concatenate([np.linspace(0.0, 1.0, 101), rng.uniform(0, 1, 5000)])
+    for eps in (0.25, 1.0, 2.0, 7.5):
+        assert _maxerr(api.rs_rbf_function(d, eps, rbf_type), o.rbf_function(d, eps, rbf_type)) < 1e-14
+    m = rng.uniform(0, 1, size=(37, 11))
+    assert _maxerr(api.rs_rbf_function_mat(m, 2.0, rbf_type), o.rbf_function(m, 2.0, rbf_type)) < 1e-14
+    eps_vec = np.sort(np.array([0.25] + list(np.arange(0.5, 10.5, 0.5))))[::-1]  # R/methods_coexp_cor.R:314,353
+    for p, shift in ((300, True), (131, False), (1100, True)):
+        x = rng.normal(size=(40, p))
+        dist = 1.0 - np.abs(o.cor_upper_triangle(x, False, shift))
+        dist[dist < 0] = 0.0
+        got = api.rs_rbf_iterate_epsilons(dist, eps_vec, p, shift, rbf_type)
+        ref = o.rbf_iterate_epsilons(dist, eps_vec, p, shift, rbf_type)
+        assert got.shape == (p, eps_vec.shape[0])
+        assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+    with pytest.raises(ValueError):
+        api.rs_rbf_function(d, 1.0, "laplace")
+
+
+@pytest.mark.parametrize("spearman", [False, True])
+@pytest.mark.parametrize("rbf_type", ["gaussian", "bump"])
+def test_coremo_stability(api, spearman, rbf_type):
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    n, p = 60, 400
+    x = synthetic_bulk(n, p, seed=31, tie_heavy=spearman)
+    idx = [1, 2, 17, n]
+    got = api.rs_coremo_stability(x, idx, 2.0, rbf_type, spearman)
+    ref = o.coremo_stability(x, idx, 2.0, rbf_type, spearman)
+    assert len(got) == len(idx)
+    for g, r in zip(got, ref):
+        assert _maxerr(g, r) < TOL64
+    if spearman:
+        _, i8 = _precisions()
+        got8 = api.rs_coremo_stability(x, idx, 2.0, rbf_type, True, precision=i8)
+        for g, r in zip(got8, ref):
+            assert _maxerr(g, r) < 1e-12
+    fused = api.cor_upper_triangle_rbf(x, spearman, 2.0, rbf_type)
+    assert _maxerr(fused, o.rbf_function(1.0 - np.abs(o.cor_upper_triangle(x, spearman, True)), 2.0, rbf_type)) < TOL64
+    tf32, _ = _precisions()
+    fused32 = api.cor_upper_triangle_rbf(x, spearman, 2.0, rbf_type, precision=tf32)
+    assert _maxerr(fused32, fused) < 2e-5
+    with pytest.raises(api.BixcorError):
+        api.rs_coremo_stability(x, [0], 2.0, rbf_type, spearman)
+
+
+# ----------------------------------------------------------------------------- sparse pair list
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+@pytest.mark.parametrize("spearman", [False, True])
+def test_pairwise_gene_cors_mc(api, fmt, spearman):
+    import scipy.sparse as sp
+
+    from bixverse_b200.synthetic import synthetic_sparse_cells
+
+    cells, genes = 900, 60
+    ip, ix, d = synthetic_sparse_cells(cells, genes, 11, density=0.15)
+    rng = np.random.default_rng(3)
+    g1 = rng.integers(0, genes, size=200).astype(np.int32)
+    g2 = rng.integers(0, genes, size=200).astype(np.int32)
+    m = sp.csr_matrix((d, ix, ip), shape=(cells, genes))
+    if fmt == "csc":
+        m = m.tocsc()
+    sparse_list = {"data": m.data, "indptr": m.indptr, "indices": m.indices, "nrow": cells, "ncol": genes, "format": fmt}
+    got = api.rs_pairwise_gene_cors_mc(sparse_list, g1, g2, spearman)
+    ref = (o.pairwise_gene_cors_spearman if spearman else o.pairwise_gene_cors)(ip, ix, d, cells, genes, g1, g2)
+    ok = ~np.isnan(ref)
+    assert ok.sum() > 150 and np.abs(got[ok] - ref[ok]).max() < 1e-10
+    if not spearman:  # the pair list is the all-pairs Gram restricted to the listed pairs (finding 3)
+        allp = api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes)
+        dense = o.upper_triangle_to_dense(allp, True, genes)
+        off = (g1 != g2) & ok
+        assert np.abs(got[off] - dense[g1[off], g2[off]]).max() < 1e-10
+    with pytest.raises(api.BixcorError):
+        api.rs_pairwise_gene_cors_mc(sparse_list, [genes], [0], spearman)

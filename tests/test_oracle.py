@@ -182,3 +182,21 @@ def test_shard_rows_partition_properties():
                 if p >= 20000:
                     pairs = [o.packed_offset(b, p, shift) - o.packed_offset(a, p, shift) for a, b in bounds]
                     assert max(pairs) / (sum(pairs) / world) < 1.06  # balanced by pair count
+
+
+def test_rbf_and_stability_restatement():
+    """Internal consistency of the RBF / leave-one-out restatement (parity unpinned, see oracle.py)."""
+    d = np.linspace(0.0, 1.0, 11)
+    assert o.rbf_function(d, 2.0, "gaussian")[0] == 1.0 and o.rbf_function(d, 2.0, "bump")[0] == 1.0
+    assert o.rbf_function(d, 2.0, "inverse_quadratic")[5] == pytest.approx(1.0 / (1.0 + 1.0))
+    assert np.all(o.rbf_function(d, 2.0, "bump")[d >= 0.5] == 0.0)
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(20, 9))
+    dist = 1.0 - np.abs(o.cor_upper_triangle(x, False, True))
+    k = o.rbf_iterate_epsilons(dist, [1.0, 3.0], 9, True, "gaussian")
+    dense = o.upper_triangle_to_dense(o.rbf_function(dist, 3.0, "gaussian"), True, 9)
+    assert np.allclose(k[:, 1], dense.sum(axis=0)) and np.allclose(np.diag(dense), 1.0)
+    res = o.coremo_stability(x, [1, 20], 2.0, "gaussian", True)
+    red = x[1:]
+    ref = 1.0 - np.exp(-((2.0 * (1.0 - np.abs(o.cor_upper_triangle(red, True, True)))) ** 2))
+    assert np.allclose(res[0], ref) and len(res) == 2 and res[1].shape == ref.shape
