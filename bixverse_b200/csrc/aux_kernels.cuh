@@ -196,6 +196,36 @@ csr_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
   }
 }
 
+// Same scatter into the TF32 hi / lo planes of the fast path (gene-major record [K hi][K lo], pre-zeroed):
+// hi = tf32(v), lo = tf32(v - hi).  The column sums are accumulated from the exact f32 values (one atomic per
+// nonzero would be order dependent, so they are taken from the planes by panel_rowsum_tf32_kernel instead).
+__global__ void __launch_bounds__(256)
+csr_densify_tf32_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const float* __restrict__ data, int64_t c0, int ncell, int64_t genes, float* __restrict__ planes,
+                        int64_t K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= ncell) return;
+  const int64_t b = indptr[c0 + warp], e = indptr[c0 + warp + 1];
+  for (int64_t q = b + lane; q < e; q += 32) {
+    const int64_t g = indices[q];
+    if (g < 0 || g >= genes) continue;
+    const float v = data[q];
+    const float hi = to_tf32(v);
+    planes[g * 2 * K + warp] = hi;
+    planes[g * 2 * K + K + warp] = to_tf32(v - hi);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+panel_rowsum_tf32_kernel(const float* __restrict__ planes, int64_t K, int ncell, double* __restrict__ colsum) {
+  __shared__ double scr[32];
+  const int64_t g = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < ncell; i += blockDim.x) s += (double)planes[g * 2 * K + i] + (double)planes[g * 2 * K + K + i];
+  s = block_sum(s, scr);
+  if (threadIdx.x == 0) colsum[g] += s;
+}
+
 // colsum[g] += sum over the panel row g.  One CTA per gene.
 __global__ void __launch_bounds__(128)
 panel_rowsum_kernel(const double* __restrict__ panel, int64_t ldk, int ncell, double* __restrict__ colsum) {

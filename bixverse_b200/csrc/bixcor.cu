@@ -810,28 +810,36 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
 
 static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
                                  int64_t cells, int64_t genes, int precision, double* d_gram, double* d_colsum) {
-  if (precision != BIXCOR_PREC_F64)
-    return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram currently runs on the FP64 path only");
+  if (precision != BIXCOR_PREC_F64 && precision != BIXCOR_PREC_TF32X3)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram runs on BIXCOR_PREC_F64 or BIXCOR_PREC_TF32X3");
+  const bool fast = precision == BIXCOR_PREC_TF32X3;
   const int chunk = 8192;  // cells per dense panel (K of one Gram accumulation pass)
-  RC_TRY(c->panel.reserve(sizeof(double) * (size_t)chunk * genes));
+  RC_TRY(c->panel.reserve(sizeof(double) * (size_t)chunk * genes));  // f64 panel == two f32 planes
   TileList* tl;
   RC_TRY(get_tiles(c, genes, 0, genes, 1, 8, &tl));
   for (int64_t c0 = 0; c0 < cells; c0 += chunk) {
     const int nc = (int)std::min<int64_t>(chunk, cells - c0);
-    const int K = round_up(nc, dmma::BK);
+    const int K = round_up(nc, fast ? 32 : dmma::BK);
+    Operand op;
+    op.precision = precision;
+    op.K = K;
+    op.p = genes;
     {
       Timed tm(c, T_OTHER);
       CU_TRY(cudaMemsetAsync(c->panel.ptr, 0, sizeof(double) * (size_t)K * genes, c->compute));
-      csr_densify_kernel<<<(nc * 32 + 255) / 256, 256, 0, c->compute>>>(d_indptr, d_indices, d_data, c0, nc, genes,
-                                                                         (double*)c->panel.ptr, K);
-      panel_rowsum_kernel<<<(unsigned)genes, 128, 0, c->compute>>>((const double*)c->panel.ptr, K, nc, d_colsum);
+      if (fast) {
+        csr_densify_tf32_kernel<<<(nc * 32 + 255) / 256, 256, 0, c->compute>>>(d_indptr, d_indices, d_data, c0, nc, genes,
+                                                                                (float*)c->panel.ptr, K);
+        panel_rowsum_tf32_kernel<<<(unsigned)genes, 128, 0, c->compute>>>((const float*)c->panel.ptr, K, nc, d_colsum);
+        op.f32 = (const float*)c->panel.ptr;
+      } else {
+        csr_densify_kernel<<<(nc * 32 + 255) / 256, 256, 0, c->compute>>>(d_indptr, d_indices, d_data, c0, nc, genes,
+                                                                           (double*)c->panel.ptr, K);
+        panel_rowsum_kernel<<<(unsigned)genes, 128, 0, c->compute>>>((const double*)c->panel.ptr, K, nc, d_colsum);
+        op.z64 = (const double*)c->panel.ptr;
+      }
       g_launches += 2;
     }
-    Operand op;
-    op.precision = BIXCOR_PREC_F64;
-    op.K = K;
-    op.p = genes;
-    op.z64 = (const double*)c->panel.ptr;
     EpiParams e = make_epi(genes);
     e.out = d_gram;
     e.ldo = genes;

@@ -740,6 +740,7 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_DIFFCOR)
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_TOM)
+  BIXCOR_UMMA_CASE(KIND_TF32, EPI_ACCUM)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_PACKED)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DIFFCOR)

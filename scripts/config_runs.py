@@ -118,7 +118,6 @@ cells, genes = 1_000_000, 5000
 t0 = time.perf_counter()
 ip, ix, d = synthetic_sparse_cells_fast(cells, genes, seed=2027)
 tgen = time.perf_counter() - t0
-got, t = timed(lambda: api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes), 1)
 # oracle on the first 250 genes (dense 1M x 250)
 gsub = 250
 sel = ix < gsub
@@ -126,12 +125,14 @@ rows = np.repeat(np.arange(cells, dtype=np.int64), np.diff(ip))[sel]
 dense = np.zeros((cells, gsub))
 dense[rows, ix[sel]] = d[sel].astype(np.float64)
 ref = np.corrcoef(dense.T)
-err = 0.0
-for i in range(gsub - 1):
-    off = int(o.packed_offset(i, genes, 1))
-    err = max(err, float(np.nanmax(np.abs(got[off: off + gsub - 1 - i] - ref[i, i + 1: gsub]))))
-emit({"config": "C5 sparse CSR 1M cells x 5000 genes (5% density)", "nnz": int(ip[-1]), "pairs": int(got.shape[0]), "wall_ms": 1e3 * t,
-      "pairs_per_s": got.shape[0] / t, "max_err_first_250_genes": err, "gen_s": tgen, "precision": "f64 (dense-panel DMMA)"})
+for pname, prec in (("f64 (dense-panel DMMA)", _lib.PREC_F64), ("tf32 (dense-panel 3xTF32 tcgen05)", _lib.PREC_TF32X3)):
+    got, t = timed(lambda: api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes, precision=prec), 1)
+    err = 0.0
+    for i in range(gsub - 1):
+        off = int(o.packed_offset(i, genes, 1))
+        err = max(err, float(np.nanmax(np.abs(got[off: off + gsub - 1 - i] - ref[i, i + 1: gsub]))))
+    emit({"config": "C5 sparse CSR 1M cells x 5000 genes (5% density)", "nnz": int(ip[-1]), "pairs": int(got.shape[0]), "wall_ms": 1e3 * t,
+          "pairs_per_s": got.shape[0] / t, "max_err_first_250_genes": err, "gen_s": tgen, "precision": pname})
 
 with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "configs_r01.json"), "w") as f:
     for d_ in OUT:

@@ -226,6 +226,17 @@ def test_sparse_gram_cor(api):
     assert np.abs(pl[ok] - got[sel][ok]).max() < 1e-9
 
 
+def test_sparse_gram_cor_tf32_fast_path(api):
+    from bixverse_b200.synthetic import synthetic_sparse_cells
+
+    tf32, _ = _precisions()
+    cells, genes = 20000, 300  # three 8192-cell panels
+    ip, ix, d = synthetic_sparse_cells(cells, genes, 2028, density=0.05)
+    got = api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes, precision=tf32)
+    ref = o.sparse_gram_cor(ip, ix, d, cells, genes)
+    assert _maxerr(got, ref) < TOL32
+
+
 # ----------------------------------------------------------------------------- fast / exact tensor paths
 def _precisions():
     from bixverse_b200 import _lib
