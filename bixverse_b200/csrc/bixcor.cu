@@ -136,6 +136,7 @@ struct Ctx {
 static std::vector<Ctx*> g_ctx;
 static std::mutex g_init_mu;
 static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM: measured fastest), env BIXCOR_DMMA_VARIANT
+static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
 
@@ -238,8 +239,12 @@ static void timing_collect(Ctx* c) {
 // one wave share operand rows in L2 and every band completes one contiguous
 // packed range (the unit of the D2H pipeline).
 // ----------------------------------------------------------------------------
-static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int upper_only, int band, TileList** out) {
-  auto key = std::make_tuple(p, row_begin, row_end, upper_only, band);
+// pairs != 0: entries are CTA-pair super-tiles of the 2-CTA tcgen05 kernels, (first block row, block col) with the
+// second block row = first + 1 and umma::TILE_SECOND_INVALID set on the column when that row holds nothing to
+// compute (outside [row_begin,row_end) or entirely below the diagonal).
+static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int upper_only, int band, int pairs,
+                     TileList** out) {
+  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs ? 1 : 0), band);
   auto it = c->tile_cache.find(key);
   if (it != c->tile_cache.end()) {
     *out = &it->second;
@@ -259,9 +264,18 @@ static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int 
     tl.group_tile.push_back((int)tiles.size());
     tl.group_row.push_back(std::max<int64_t>(row_begin, (int64_t)bb * kTile));
     const int j0 = upper_only ? bb : 0;
-    for (int bj = j0; bj < nb; ++bj)
-      for (int bi = bb; bi < be; ++bi)
-        if (!upper_only || bi <= bj) tiles.push_back(make_int2(bi, bj));
+    for (int bj = j0; bj < nb; ++bj) {
+      if (!pairs) {
+        for (int bi = bb; bi < be; ++bi)
+          if (!upper_only || bi <= bj) tiles.push_back(make_int2(bi, bj));
+      } else {
+        for (int bi = bb; bi < be; bi += 2) {  // bands start at b0 and hold an even number of block rows
+          if (upper_only && bi > bj) continue;
+          const bool second_ok = (bi + 1 < b1) && (!upper_only || bi + 1 <= bj);
+          tiles.push_back(make_int2(bi, second_ok ? bj : (bj | umma::TILE_SECOND_INVALID)));
+        }
+      }
+    }
   }
   tl.group_tile.push_back((int)tiles.size());
   tl.group_row.push_back(row_end);
@@ -290,6 +304,15 @@ struct Operand {
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Does this (precision, epilogue) run on the CTA-pair tcgen05 kernels (=> pair tile lists)?  g_umma_ctas: 1 = never,
+// 3 = always, 2 (default) = where it measured faster on B200: the packed correlation (short K; -3 %).  With the
+// chunked FP32 promotion of the long-K TOM / sparse Grams the cross-CTA drain handshake costs more than the
+// halved B traffic saves (TOM 20k: 54 ms vs 43 ms), see profiles/umma_probe_r01.txt.
+static int umma_pairs(int precision, int epi) {
+  if (precision == BIXCOR_PREC_F64 || g_umma_ctas == 1) return 0;
+  return (g_umma_ctas == 3 || epi == EPI_PACKED) ? 1 : 0;
+}
 
 static int k_padding(int precision) {
   return precision == BIXCOR_PREC_F64 ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
@@ -483,7 +506,7 @@ static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, co
   const void* pl0 = kind == umma::KIND_I8 ? (const void*)a.i8 : (const void*)a.f32;
   const void* pl1 = b ? (kind == umma::KIND_I8 ? (const void*)b->i8 : (const void*)b->f32) : nullptr;
   Timed tm(c, T_GEMM);
-  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
+  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, umma_pairs(a.precision, epi) ? 2 : 1, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
                              b ? b->inv_norm : nullptr, tiles, ntiles, e) != 0)
     return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
   g_launches++;
@@ -623,7 +646,7 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
                                  int64_t row_end, double* d_out, D2HPipe* pipe, double* h_out,
                                  const RbfSpec* rbf = nullptr) {
   TileList* tl;
-  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(op.precision, EPI_PACKED), &tl));
   EpiParams e = make_epi(p);
   e.out = d_out;
   e.out_base = packed_row_offset(row_begin, p, shift);
@@ -678,7 +701,7 @@ static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double
   RC_TRY(prepare_operand(c, d_xa, na, p, spearman, precision, 0, &a));
   RC_TRY(prepare_operand(c, d_xb, nb, p, spearman, precision, 1, &b));
   TileList* tl;
-  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, &tl));
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(precision, EPI_DIFFCOR), &tl));
   const double cf = spearman ? g_fieller : 1.0;
   EpiParams e = make_epi(p);
   e.out_base = packed_row_offset(row_begin, p, 1);
@@ -718,7 +741,7 @@ static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spe
   RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
   const bool full = (row_begin == 0 && row_end == p);
   TileList* tl;
-  RC_TRY(get_tiles(c, p, row_begin, row_end, full ? 1 : 0, 8, &tl));
+  RC_TRY(get_tiles(c, p, row_begin, row_end, full ? 1 : 0, 8, umma_pairs(precision, EPI_DENSE), &tl));
   EpiParams e = make_epi(p);
   e.out = d_app;
   e.ldo = p;
@@ -792,7 +815,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   const bool full = (row_begin == 0 && row_end == p);
   const int upper = (packed || full) ? 1 : 0;
   TileList* tl;
-  RC_TRY(get_tiles(c, p, row_begin, row_end, upper, 8, &tl));
+  RC_TRY(get_tiles(c, p, row_begin, row_end, upper, 8, umma_pairs(precision, EPI_TOM), &tl));
   EpiParams e = make_epi(p);
   e.out = d_out;
   e.ldo = p;
@@ -816,7 +839,7 @@ static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t*
   const int chunk = 8192;  // cells per dense panel (K of one Gram accumulation pass)
   RC_TRY(c->panel.reserve(sizeof(double) * (size_t)chunk * genes));  // f64 panel == two f32 planes
   TileList* tl;
-  RC_TRY(get_tiles(c, genes, 0, genes, 1, 8, &tl));
+  RC_TRY(get_tiles(c, genes, 0, genes, 1, 8, umma_pairs(precision, EPI_ACCUM), &tl));
   for (int64_t c0 = 0; c0 < cells; c0 += chunk) {
     const int nc = (int)std::min<int64_t>(chunk, cells - c0);
     const int K = round_up(nc, fast ? 32 : dmma::BK);
@@ -951,6 +974,7 @@ int bixcor_init_devices(int first_device, int n_gpus) {
     return fail(BIXCOR_ERR_INVALID, "requested devices [%d,%d) but %d visible", first_device, first_device + n_gpus,
                 count);
   if (const char* v = getenv("BIXCOR_DMMA_VARIANT")) g_dmma_variant = atoi(v);
+  if (const char* v = getenv("BIXCOR_UMMA_CTAS")) g_umma_ctas = (atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 2;
   for (int d = 0; d < n_gpus; ++d) {
     Ctx* c = nullptr;
     int rc = ctx_create(first_device + d, &c);
@@ -1371,7 +1395,7 @@ static int dense_symmetric(const double* x, int64_t n, int64_t p, int norm_mode,
   Operand op;
   RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, n, p, 0, BIXCOR_PREC_F64, 0, &op, norm_mode));
   TileList* tl;
-  RC_TRY(get_tiles(c, p, 0, p, 1, 8, &tl));
+  RC_TRY(get_tiles(c, p, 0, p, 1, 8, 0, &tl));
   EpiParams e = make_epi(p);
   e.out = (double*)c->out.ptr;
   e.ldo = p;

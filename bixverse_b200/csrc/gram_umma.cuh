@@ -25,6 +25,8 @@
 
 #include <cuda.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -33,24 +35,56 @@ namespace umma {
 
 enum Kind : int { KIND_TF32 = 0, KIND_I8 = 1 };
 
+// Developer instrumentation (ablation modes of Params::dbg inside the lean epilogue, clock64 phase counters)
+// costs registers in the hot loops, so it is compiled in only with -DBIXCOR_UMMA_PROFILE (scripts/perf_probe.py,
+// profiles/umma_probe_r01.txt were produced that way).
+// Lean epilogue of interior packed tiles: through the swizzled shared-memory transpose (default: every store
+// instruction writes two full 128-byte runs) or straight from the tcgen05.ld.16x256b fragment layout
+// (-DBIXCOR_UMMA_LEAN_FRAG: no STS/LDS, but a store instruction then touches 8 rows x 64 bytes and the kernel
+// is 17% slower - measured, profiles/umma_probe_r01.txt; kept for that ablation).
+#ifdef BIXCOR_UMMA_LEAN_FRAG
+constexpr bool kFragEpilogue = true;
+#else
+constexpr bool kFragEpilogue = false;
+#endif
+#ifdef BIXCOR_UMMA_PROFILE
+constexpr bool kProfile = true;
+#else
+constexpr bool kProfile = false;
+#endif
+
 constexpr int BM = 128, BN = 128;
 constexpr int ROW_BYTES = 128;                    // one SWIZZLE_128B row: 32 tf32 or 128 int8
 constexpr int PLANE_TILE_BYTES = BM * ROW_BYTES;  // 16 KB
-constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;  // A hi, A lo, B hi, B lo
-constexpr int STAGES = 3;
+// CTAS = 1: one CTA per 128 x 128 tile (cta_group::1).  CTAS = 2: a CTA pair (one TPC) shares a 256 x 128
+// super-tile with tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the B tile, the
+// tensor cores of both SMs read both halves.  Per-SM operand traffic through shared memory drops from
+// 32 KB to 24 KB per MMA and the TMA fill from 64 KB to 48 KB per K block - the K loop of the 1-CTA kernel is
+// bound by exactly that traffic (profiles/README_r01.md).
+template <int CTAS>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = PLANE_TILE_BYTES / CTAS;
+  static constexpr int STAGE_BYTES = 2 * PLANE_TILE_BYTES + 2 * B_TILE_BYTES;  // A hi, A lo, B hi, B lo
+  static constexpr int STAGES = CTAS == 1 ? 3 : 4;
+};
 constexpr int EPI_WARPS = 8;                                  // two per scheduler: (TMEM lane quarter) x (column half)
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr int EPI_COLS = BN / (EPI_WARPS / 4);                // accumulator columns owned by one epilogue warp
 constexpr int EPI_CHUNK = 16;                                 // columns transposed per step
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_CHUNK * 8;  // one 32 x 16 double transpose buffer per warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+template <int CTAS>
+constexpr int smem_bytes_of() {
+  return Cfg<CTAS>::STAGES * Cfg<CTAS>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+}
+constexpr int TILE_SECOND_INVALID = 1 << 30;  // CTAS = 2: flag on tile.y, the pair's second block row holds nothing
 
 struct Params {
   int ntiles;
-  const int2* tiles;
+  const int2* tiles;  // CTAS = 1: (block row, block col); CTAS = 2: (first block row of the pair, block col | flags)
   int npass;         // 2 for the differential correlation (operand set 1 in pass 1)
   int kblocks[2];    // 128-byte K blocks per pass
   const double* inv_norm[2];  // KIND_I8: 1/|d| per gene and pass
+  unsigned long long* prof;  // optional (env BIXCOR_UMMA_PROF): per epilogue warp cycles {wait, drain, lean epilogue, tiles}
   int zero;  // always 0; opaque to the compiler (scheduling fence, see the epilogue drain)
   int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = generic path without global stores, 3 = no MMA issue,
             // 4 = lean path without global stores, 5 = lean path without phase B, 6 = no TMA and no MMA (epilogue alone)
@@ -89,6 +123,62 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---- cluster variants used by the CTA-pair kernel ----
+// Default (.release.cta / .acquire.cta) semantics on purpose, like CUTLASS' ClusterBarrier: a .cluster-scope
+// release compiles to MEMBAR.ALL.GPU in front of every arrive and an acquire to CCTL.IVALL after every wait,
+// which cost the producer more than a K block.  What these barriers order is async-proxy traffic (TMA bytes,
+// tcgen05 reads/writes), which complete_tx and the tcgen05 fences cover.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of a CTA pair member: data lands in the executing CTA's shared memory, the completion bytes are
+// signalled on `bar_cluster`, a shared::cluster address that may belong to the peer (leader) CTA.
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -103,8 +193,24 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int KIND>
+template <int KIND, int CTAS = 1>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (CTAS == 2) {
+    if (KIND == KIND_TF32) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
+    return;
+  }
   if (KIND == KIND_TF32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -140,6 +246,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bits, 4 repeats = 16 lanes x 32 columns.  Thread t receives, for repeat n, r[4n+0..1] =
+// (lane t/4, columns 8n + 2(t%4) + {0,1}) and r[4n+2..3] = (lane t/4 + 8, same columns): the accumulator
+// fragment layout of mma, i.e. every quad holds 8 consecutive columns of a row.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// two consecutive doubles of one packed row: one 16-byte store when the pair is 16-byte aligned, two 8-byte
+// stores otherwise (predicated, no branch: rows of one warp instruction have mixed parity)
+__device__ __forceinline__ void store_pair(char* addr, double v0, double v1, uint32_t odd) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "@!p st.global.v2.f64 [%0], {%1, %2};\n\t"
+      "@p st.global.f64 [%0], %1;\n\t"
+      "@p st.global.f64 [%0+8], %2;\n\t}"
+      ::"l"(addr), "d"(v0), "d"(v1), "r"(odd)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4,
@@ -154,11 +282,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // instruction descriptor: dense, K-major A and B, M = 128, N = 128
-template <int KIND>
+template <int KIND, int CTAS = 1>
 __host__ __device__ constexpr uint32_t make_idesc() {
   return (KIND == KIND_TF32 ? (1u << 4) | (2u << 7) | (2u << 10)    // D = F32, A = B = TF32
                             : (2u << 4) | (1u << 7) | (1u << 10))   // D = S32, A = B = signed int8
-         | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);  // M = 256 across the CTA pair
 }
 
 template <int KIND>
@@ -217,7 +345,10 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
 #pragma unroll
     for (int q = 0; q < EPI_CHUNK; q += 2) {  // phase A (lane = row)
       double v0, v1;
-      if (KIND == KIND_I8) {
+      if (kProfile && KIND == KIND_I8 && dbg == 7) {  // profiling: no FP64 instruction at all (values are garbage)
+        v0 = __hiloint2double(0x43300000, (int)racc[c + q]);
+        v1 = __hiloint2double(0x43300000, (int)racc[c + q + 1]);
+      } else if (KIND == KIND_I8) {
         v0 = (double)(int)racc[c + q] * rowf;
         v1 = (double)(int)racc[c + q + 1] * rowf;
       } else {
@@ -232,19 +363,19 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
     }
     __syncwarp();
     const double cf = colf[c / EPI_CHUNK];
-    if (dbg == 5) {  // profiling: no phase B at all
+    if (kProfile && dbg == 5) {  // profiling: no phase B at all
       __syncwarp();
       continue;
     }
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {  // phase B (lane = 2 rows x 16 columns): two 128-byte runs per store
       double v = *reinterpret_cast<const double*>(sb + ld_off[k2 & 3] + k2 * (2 * EPI_CHUNK * 8));
-      if (KIND == KIND_I8) v *= cf;
-      if (PW6) {
+      if (KIND == KIND_I8 && !(kProfile && dbg == 7)) v *= cf;
+      if (PW6 && !(kProfile && dbg == 7)) {
         const double sq = v * v;
         v = sq * sq * sq;
       }
-      if (dbg == 4) {  // profiling: everything but the global store
+      if (kProfile && dbg == 4) {  // profiling: everything but the global store
         asm volatile("" ::"d"(v));
         continue;
       }
@@ -254,11 +385,20 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
   }
 }
 
-template <int KIND, int EPI>
+// map0 / map1: 128-row boxes (A operand of pass 0 / 1); mapb0 / mapb1: the B operand boxes (128 rows for CTAS = 1,
+// 64 rows = this CTA's half of the B tile for CTAS = 2).
+template <int KIND, int EPI, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
-gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
+gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                 const __grid_constant__ CUtensorMap mapb0, const __grid_constant__ CUtensorMap mapb1, const Params P) {
   using T = KindTraits<KIND>;
   constexpr int TMEM_COLS = (T::NACC * T::ACC_STAGES * BN <= 256) ? 256 : 512;
+  constexpr int STAGES = Cfg<CTAS>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<CTAS>::STAGE_BYTES;
+  constexpr int B_TILE_BYTES = Cfg<CTAS>::B_TILE_BYTES;
+  uint32_t cta_rank = 0;
+  if (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int unit0 = (int)blockIdx.x / CTAS, unit_stride = (int)gridDim.x / CTAS;  // tile (pair) scheduling units
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -280,22 +420,29 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CTAS);  // one expect_tx arrive per CTA of the pair (the leader's barrier collects both)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {  // one warp of EACH CTA of the pair takes part in the collective allocation
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -304,23 +451,37 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
-        const int2 tile = P.tiles[t];
+      for (int t = unit0; t < P.ntiles; t += unit_stride) {
+        int2 tile = P.tiles[t];
+        if (CTAS == 2) {
+          tile.x += (int)cta_rank;  // this CTA's block row of the pair
+          tile.y &= ~TILE_SECOND_INVALID;
+        }
         for (int pass = 0; pass < P.npass; ++pass) {
           const CUtensorMap* map = pass ? &map1 : &map0;
+          const CUtensorMap* mapb = pass ? &mapb1 : &mapb0;
           const int kb_n = P.kblocks[pass];
           const int kelems = (KIND == KIND_TF32) ? 32 : 128;
           for (int kb = 0; kb < kb_n; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (P.dbg == 6) {  // profiling: no operand traffic at all
+            const uint32_t s0 = base + stage * STAGE_BYTES;
+            if (CTAS == 2) {
+              // the leader's full barrier counts the bytes of both CTAs; B rows: this CTA's half of the tile
+              const uint32_t fb = mapa_rank(full_bar(stage), 0);
+              mbar_expect_tx_cluster(fb, STAGE_BYTES);
+              const int brow = tile.y * BN + (int)cta_rank * (BN / 2);
+              tma_load_3d_pair(s0 + 0 * PLANE_TILE_BYTES, map, fb, kb * kelems, 0, tile.x * BM);
+              tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, 1, tile.x * BM);
+              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, 0, brow);
+              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, 1, brow);
+            } else if (kProfile && P.dbg == 6) {  // profiling: no operand traffic at all
               mbar_arrive(full_bar(stage));
             } else {
               mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-              const uint32_t s0 = base + stage * STAGE_BYTES;
               tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.x * BM);
               tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.x * BM);
-              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.y * BN);
-              tma_load_3d(s0 + 3 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.y * BN);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, mapb, full_bar(stage), kb * kelems, 0, tile.y * BN);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, full_bar(stage), kb * kelems, 1, tile.y * BN);
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -331,50 +492,58 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<KIND>();
+    // ============================ MMA issuer (leader CTA of a pair only) ===
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc<KIND, CTAS>();
       int stage = 0, acc_stage = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+      for (int t = unit0; t < P.ntiles; t += unit_stride) {
         for (int pass = 0; pass < P.npass; ++pass) {
           const int kb_n = P.kblocks[pass];
-          for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
-            const int kb1 = (kb_n - kb0 > T::CHUNK_KB) ? kb0 + T::CHUNK_KB : kb_n;
-            mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);  // epilogue has drained this accumulator set
+          const int chunk_kb = (kProfile && P.dbg == 8) ? (1 << 30) : T::CHUNK_KB;  // dbg 8: profiling, no chunked promotion
+          for (int kb0 = 0; kb0 < kb_n; kb0 += chunk_kb) {
+            const int kb1 = (kb_n - kb0 > chunk_kb) ? kb0 + chunk_kb : kb_n;
+            // epilogue (of both CTAs) has drained this accumulator set
+            if (CTAS == 2) mbar_wait_cluster(tempty_bar(acc_stage), acc_phase ^ 1u);
+            else mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * T::NACC * BN);
             for (int kb = kb0; kb < kb1; ++kb) {
-              mbar_wait(full_bar(stage), phase);
+              if (CTAS == 2) mbar_wait_cluster(full_bar(stage), phase);
+              else mbar_wait(full_bar(stage), phase);
               tc_fence_after();
               const uint32_t s0 = base + stage * STAGE_BYTES;
               const uint64_t dA0 = make_smem_desc(s0 + 0 * PLANE_TILE_BYTES);
               const uint64_t dA1 = make_smem_desc(s0 + 1 * PLANE_TILE_BYTES);
               const uint64_t dB0 = make_smem_desc(s0 + 2 * PLANE_TILE_BYTES);
-              const uint64_t dB1 = make_smem_desc(s0 + 3 * PLANE_TILE_BYTES);
+              const uint64_t dB1 = make_smem_desc(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {             // 4 x 32-byte K steps inside the 128-byte swizzle row
                 const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes, in 16-byte descriptor units
                 const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
-                if (P.dbg == 3 || P.dbg == 6) continue;
+                if (kProfile && (P.dbg == 3 || P.dbg == 6)) continue;
                 if (KIND == KIND_TF32) {
-                  tc_mma<KIND>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
-                  tc_mma<KIND>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
-                  tc_mma<KIND>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
+                  tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
+                  tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
+                  tc_mma<KIND, CTAS>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
                 } else {
-                  tc_mma<KIND>(acc0 + 0 * BN, dA0 + ko, dB0 + ko, idesc, first);  // h*h
-                  tc_mma<KIND>(acc0 + 1 * BN, dA0 + ko, dB1 + ko, idesc, first);  // h*l
-                  tc_mma<KIND>(acc0 + 1 * BN, dA1 + ko, dB0 + ko, idesc, 1u);     // l*h
-                  tc_mma<KIND>(acc0 + 2 * BN, dA1 + ko, dB1 + ko, idesc, first);  // l*l
+                  tc_mma<KIND, CTAS>(acc0 + 0 * BN, dA0 + ko, dB0 + ko, idesc, first);  // h*h
+                  tc_mma<KIND, CTAS>(acc0 + 1 * BN, dA0 + ko, dB1 + ko, idesc, first);  // h*l
+                  tc_mma<KIND, CTAS>(acc0 + 1 * BN, dA1 + ko, dB0 + ko, idesc, 1u);     // l*h
+                  tc_mma<KIND, CTAS>(acc0 + 2 * BN, dA1 + ko, dB1 + ko, idesc, first);  // l*l
                 }
               }
-              tc_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+              // smem stage reusable (in both CTAs) once these MMAs have read it
+              if (CTAS == 2) tc_commit_pair(empty_bar(stage));
+              else tc_commit(empty_bar(stage));
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
               }
             }
-            tc_commit(tfull_bar(acc_stage));  // chunk accumulators complete -> epilogue warps
+            // chunk accumulators complete -> epilogue warps (of both CTAs)
+            if (CTAS == 2) tc_commit_pair(tfull_bar(acc_stage));
+            else tc_commit(tfull_bar(acc_stage));
             if (++acc_stage == T::ACC_STAGES) {
               acc_stage = 0;
               acc_phase ^= 1u;
@@ -397,7 +566,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     double* stg = epi_stage_all + (warp - 4) * (32 * EPI_CHUNK);
     const bool want_mirror = epi_wants_mirror<EPI>(E);
     const int pp = (int)E.p;
-    const int dbg = P.dbg;
+    const int dbg = kProfile ? P.dbg : 0;
     // loop invariants pulled out of the constant bank once
     double* const out = E.out;
     const int64_t ldo = E.ldo;
@@ -407,30 +576,149 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const double scale = E.scale;
     // 1 identity, 6 = WGCNA default, 0 generic (any other exponent, or an RBF transform)
     const int pw_mode = E.rbf_mode ? 0 : ((E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0));
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
-      const int2 tile = P.tiles[t];
+    long long prof_acc[4] = {0, 0, 0, 0};
+    // tempty arrives go to the leader CTA's barrier (its MMA warp is the only consumer)
+    auto arrive_tempty = [&](int st) {
+      if (CTAS == 2) mbar_arrive_cluster(mapa_rank(tempty_bar(st), 0));
+      else mbar_arrive(tempty_bar(st));
+    };
+    for (int t = unit0; t < P.ntiles; t += unit_stride) {
+      int2 tile = P.tiles[t];
+      bool tile_valid = true;
+      if (CTAS == 2) {
+        tile_valid = !(cta_rank == 1 && (tile.y & TILE_SECOND_INVALID));
+        tile.x += (int)cta_rank;
+        tile.y &= ~TILE_SECOND_INVALID;
+      }
       const int row_base = tile.x * BM + ew * 32;
       const int i = row_base + lane;
       const int col_base = tile.y * BN + ch * EPI_COLS;
       for (int pass = 0; pass < P.npass; ++pass) {
         // Interior tiles of the packed correlation (97% of the tiles at p = 20000) lie strictly above the
         // diagonal and fully inside the matrix: nothing is predicated and they take the lean path below.
-        const bool interior = (EPI == EPI_PACKED) && tile.x < tile.y && tile.y * BN + BN <= pp && pw_mode != 0 && !keep_sign && (dbg == 0 || dbg >= 3);
+        const bool interior = tile_valid && (EPI == EPI_PACKED) && tile.x < tile.y && tile.y * BN + BN <= pp && pw_mode != 0 && !keep_sign && (dbg == 0 || dbg >= 3);
         // DIRECT kernels keep the accumulators of the few non-interior tiles in TMEM and finish them chunk
         // by chunk (the MMA warp waits a little longer on 3% of the tiles); in exchange the 64-register
         // drain array only lives on the lean path and the kernel stays free of local-memory spills.
+        const int kb_n = P.kblocks[pass];
+        if (kFragEpilogue && interior) {
+          // ---- (ablation) lean path without a shared-memory transpose: the accumulators are read in the
+          //      16x256b fragment layout, a quad holds 8 consecutive columns of a row and stores them as
+          //      16-byte pairs straight to the packed row.
+          uint32_t sf[EPI_COLS];  // [(h*2 + g)*16 + 4n + 2k + e]: row 16h + 8k + lane/4, column 32g + 8n + 2(lane%4) + e
+          for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
+            mbar_wait(tfull_bar(acc_stage), acc_phase);
+            tc_fence_after();
+            const uint32_t tcol = (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
+            uint32_t dep = 0;
+#pragma unroll
+            for (int hg = 0; hg < 4; ++hg) {
+              const int h = hg >> 1, g = hg & 1;
+              const uint32_t ta = tmem_base + ((uint32_t)(ew * 32 + h * 16) << 16) + tcol + (uint32_t)(g * 32) + dep;
+              if (KIND == KIND_I8) {
+                uint32_t r0[16], r1[16], r2[16];
+                tmem_ld_16x256b_x4(ta, r0);
+                tmem_ld_16x256b_x4(ta + BN, r1);
+                tmem_ld_16x256b_x4(ta + 2 * BN, r2);
+                tmem_ld_wait();
+                uint32_t any = 0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {  // S = 256*hh + 16*(hl+lh) + ll, exact in int32 for n <= 1860
+                  sf[hg * 16 + q] = (uint32_t)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]);
+                  any |= sf[hg * 16 + q];
+                }
+                dep = any & (uint32_t)P.zero;  // (scheduling fence, see the generic drain below)
+              } else {
+                uint32_t r0[16];
+                tmem_ld_16x256b_x4(ta, r0);
+                tmem_ld_wait();
+                uint32_t any = 0;
+                if (kb0 == 0) {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) sf[hg * 16 + q] = r0[q];
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q)
+                    sf[hg * 16 + q] = __float_as_uint(__uint_as_float(sf[hg * 16 + q]) + __uint_as_float(r0[q]));
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) any |= sf[hg * 16 + q];
+                dep = any & (uint32_t)P.zero;
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_tempty(acc_stage);
+            if (++acc_stage == T::ACC_STAGES) {
+              acc_stage = 0;
+              acc_phase ^= 1u;
+            }
+          }
+          const int q4 = lane & 3, rl = lane >> 2;
+          const double* inv = (KIND == KIND_I8) ? P.inv_norm[pass] : nullptr;
+          double rowf[4];
+          char* rptr[4];
+          uint32_t odd[4];
+#pragma unroll
+          for (int hk = 0; hk < 4; ++hk) {
+            const int r = row_base + 16 * (hk >> 1) + 8 * (hk & 1) + rl;
+            const int64_t idx0 = packed_row_offset(r, E.p, shift) - E.out_base - r - shift + col_base + 2 * q4;
+            rptr[hk] = reinterpret_cast<char*>(out + idx0);
+            odd[hk] = (uint32_t)(idx0 & 1);
+            rowf[hk] = (KIND == KIND_I8) ? scale * __ldg(inv + r) : scale;
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              double c0 = 1.0, c1 = 1.0;
+              if (KIND == KIND_I8) {
+                const double2 cf = __ldg(reinterpret_cast<const double2*>(inv + col_base + 32 * g + 8 * n + 2 * q4));
+                c0 = cf.x;
+                c1 = cf.y;
+              }
+#pragma unroll
+              for (int hk = 0; hk < 4; ++hk) {
+                const int h = hk >> 1, k = hk & 1;
+                const uint32_t s0 = sf[(h * 2 + g) * 16 + 4 * n + 2 * k], s1 = sf[(h * 2 + g) * 16 + 4 * n + 2 * k + 1];
+                double v0, v1;
+                if (KIND == KIND_I8) {
+                  v0 = (double)(int)s0 * rowf[hk] * c0;
+                  v1 = (double)(int)s1 * rowf[hk] * c1;
+                } else {
+                  v0 = (double)__uint_as_float(s0);
+                  v1 = (double)__uint_as_float(s1);
+                  if (scale != 1.0) {
+                    v0 *= scale;
+                    v1 *= scale;
+                  }
+                }
+                if (pw_mode == 6) {
+                  const double a0 = v0 * v0, a1 = v1 * v1;
+                  v0 = a0 * a0 * a0;
+                  v1 = a1 * a1 * a1;
+                }
+                store_pair(rptr[hk] + (32 * g + 8 * n) * 8, v0, v1, odd[hk]);
+              }
+            }
+          }
+          continue;
+        }
         const bool direct = DIRECT && !interior;
         uint32_t racc[EPI_COLS];
-        const int kb_n = P.kblocks[pass];
         uint32_t tacc_direct = 0;
+        const long long pt0 = (kProfile && P.prof) ? clock64() : 0;
+        long long pt1 = pt0;
         if (direct) {
           mbar_wait(tfull_bar(acc_stage), acc_phase);
           tc_fence_after();
           tacc_direct = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
         } else {
           // ---- drain: TMEM -> registers, chunk by chunk (FP32 round-to-nearest / exact int32 sums)
-          for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
+          const int chunk_kb = (kProfile && dbg == 8) ? (1 << 30) : T::CHUNK_KB;
+          for (int kb0 = 0; kb0 < kb_n; kb0 += chunk_kb) {
             mbar_wait(tfull_bar(acc_stage), acc_phase);
+            if (kProfile && P.prof && kb0 == 0) pt1 = clock64();
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                   (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
@@ -455,23 +743,23 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               }
             } else {
 #pragma unroll
-              for (int c = 0; c < EPI_COLS; c += 32) {
-                uint32_t r0[32];
-                tmem_ld32(tacc + c, r0);
+              for (int c = 0; c < EPI_COLS; c += 16) {
+                uint32_t r0[16];
+                tmem_ld16(tacc + c, r0);
                 tmem_ld_wait();
                 if (kb0 == 0) {
 #pragma unroll
-                  for (int q = 0; q < 32; ++q) racc[c + q] = r0[q];
+                  for (int q = 0; q < 16; ++q) racc[c + q] = r0[q];
                 } else {
 #pragma unroll
-                  for (int q = 0; q < 32; ++q)
+                  for (int q = 0; q < 16; ++q)
                     racc[c + q] = __float_as_uint(__uint_as_float(racc[c + q]) + __uint_as_float(r0[q]));
                 }
               }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc_stage));  // TMEM buffer free: the MMA warp moves on
+            if (lane == 0) arrive_tempty(acc_stage);  // TMEM buffer free: the MMA warp moves on
             if (++acc_stage == T::ACC_STAGES) {
               acc_stage = 0;
               acc_phase ^= 1u;
@@ -481,28 +769,36 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         auto release_direct = [&]() {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc_stage));
+          if (lane == 0) arrive_tempty(acc_stage);
           if (++acc_stage == T::ACC_STAGES) {
             acc_stage = 0;
             acc_phase ^= 1u;
           }
         };
-        if (dbg == 1) {
+        if (dbg == 1 || !tile_valid) {  // (a pair's second block row that holds nothing: protocol only)
           if (direct) release_direct();
           continue;
         }
         // ---- lean path: row-side factors are applied with lane = row, column-side factors and the power
         //      after the transpose with lane = column; the 16 row offsets of a lane are 32-bit and computed
         //      once per tile, so a store costs one address add.
-        if (interior) {
+        if (!kFragEpilogue && interior) {
           const EpiRow R0 = epi_row<EPI>(E, row_base);  // warp uniform
           double rowf = scale;
           if (KIND == KIND_I8) rowf *= P.inv_norm[pass][i];
           const double* colv = (KIND == KIND_I8) ? P.inv_norm[pass] + col_base : nullptr;
           char* const wbase = reinterpret_cast<char*>(out + (R0.ro + col_base));
           const int a = pp - row_base - shift - 1;  // ro(i + 1) - ro(i) = p - i - shift - 1
+          const long long pt2 = (kProfile && P.prof) ? clock64() : 0;
           if (pw_mode == 6) packed_interior<KIND, true>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
           else packed_interior<KIND, false>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
+          if (kProfile && P.prof) {
+            const long long pt3 = clock64();
+            prof_acc[0] += pt1 - pt0;
+            prof_acc[1] += pt2 - pt1;
+            prof_acc[2] += pt3 - pt2;
+            prof_acc[3] += 1;
+          }
           continue;
         }
         // ---- fused epilogue from registers.  Each 32 x 16 block is transposed through shared
@@ -628,13 +924,21 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         if (direct) release_direct();
       }
     }
+    if (kProfile && P.prof && lane == 0) {
+      unsigned long long* dst = P.prof + ((size_t)blockIdx.x * EPI_WARPS + (warp - 4)) * 4;
+      for (int q = 0; q < 4; ++q) dst[q] = (unsigned long long)prof_acc[q];
+    }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the peer's shared memory / TMEM stay alive until both CTAs are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (CTAS == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -663,7 +967,7 @@ inline EncodeTiledFn encode_fn() {
 
 // 3-D map over the gene-major operand [row][plane][K]: dims (K, 2 planes, rows), box (128 bytes of K,
 // 1 plane, 128 rows), SWIZZLE_128B; out-of-range rows are zero filled (ragged last tile).
-inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, int K) {
+inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, int K, int box_rows = BM) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     snprintf(err_buf(), 512, "cuTensorMapEncodeTiled entry point not available");
@@ -672,7 +976,7 @@ inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, i
   const int es = kind == KIND_TF32 ? 4 : 1;
   cuuint64_t dims[3] = {(cuuint64_t)K, 2, (cuuint64_t)rows};
   cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * 2};
-  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), 1, (cuuint32_t)BM};
+  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), 1, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -685,40 +989,58 @@ inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, i
   return 0;
 }
 
-template <int KIND, int EPI>
-inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, const CUtensorMap& m1, const Params& P) {
-  auto kern = gram_umma_kernel<KIND, EPI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+template <int KIND, int EPI, int CTAS>
+inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& b0,
+                      const CUtensorMap& b1, const Params& P) {
+  auto kern = gram_umma_kernel<KIND, EPI, CTAS>;
+  constexpr int smem = smem_bytes_of<CTAS>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     snprintf(err_buf(), 512, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return -1;
   }
-  const int grid = P.ntiles < sm_count ? P.ntiles : sm_count;
-  kern<<<grid, THREADS, SMEM_BYTES, stream>>>(m0, m1, P);
-  e = cudaGetLastError();
+  const int units = sm_count / CTAS;  // persistent: one CTA (pair) per SM (TPC)
+  const int grid = CTAS * (P.ntiles < units ? P.ntiles : units);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, m0, m1, b0, b1, P);
   if (e != cudaSuccess) {
-    snprintf(err_buf(), 512, "gram_umma_kernel launch: %s", cudaGetErrorString(e));
+    snprintf(err_buf(), 512, "gram_umma_kernel launch (CTAS = %d): %s", CTAS, cudaGetErrorString(e));
     return -1;
   }
   return 0;
 }
 
-// operand set s: gene-major digit planes ([row][plane][K]), K elements (padded), inv_norm (KIND_I8)
-inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int64_t rows, const void* planes0,
-                            int K0, const double* inv0, const void* planes1, int K1, const double* inv1,
-                            const int2* tiles, int ntiles, const EpiParams& E) {
+// operand set s: gene-major digit planes ([row][plane][K]), K elements (padded), inv_norm (KIND_I8).
+// ctas = 2: `tiles` is a pair list (first block row of the pair, block col | TILE_SECOND_INVALID).
+inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int ctas, int64_t rows,
+                            const void* planes0, int K0, const double* inv0, const void* planes1, int K1,
+                            const double* inv1, const int2* tiles, int ntiles, const EpiParams& E) {
   if (ntiles <= 0) return 0;
   const int kelems = kind == KIND_TF32 ? 32 : 128;
   if (K0 % kelems != 0 || (planes1 && K1 % kelems != 0)) {
     snprintf(err_buf(), 512, "operand K must be padded to %d elements", kelems);
     return -1;
   }
-  CUtensorMap m0, m1;
+  CUtensorMap m0, m1, b0, b1;
   if (make_map(&m0, kind, planes0, rows, K0)) return -1;
+  if (make_map(&b0, kind, planes0, rows, K0, BN / ctas)) return -1;
   if (planes1) {
     if (make_map(&m1, kind, planes1, rows, K1)) return -1;
+    if (make_map(&b1, kind, planes1, rows, K1, BN / ctas)) return -1;
   } else {
     m1 = m0;
+    b1 = b0;
   }
   Params P;
   P.ntiles = ntiles;
@@ -730,12 +1052,43 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   P.inv_norm[1] = inv1;
   P.E = E;
   P.zero = 0;
+  P.prof = nullptr;
   {
     const char* d = getenv("BIXCOR_UMMA_DEBUG");
     P.dbg = d ? atoi(d) : 0;
   }
-#define BIXCOR_UMMA_CASE(KIND, EPI) \
-  if (kind == KIND && epi == EPI) return launch_one<KIND, EPI>(stream, sm_count, m0, m1, P);
+  static unsigned long long* d_prof = nullptr;
+  const bool want_prof = getenv("BIXCOR_UMMA_PROF") != nullptr;
+  if (want_prof) {  // developer aid: per-warp cycle counters of the lean epilogue, printed after the launch
+    if (!d_prof) cudaMalloc(&d_prof, sizeof(unsigned long long) * 4 * EPI_WARPS * 1024);
+    cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 4 * EPI_WARPS * 1024, stream);
+    P.prof = d_prof;
+  }
+  struct ProfDump {
+    cudaStream_t st;
+    unsigned long long* d;
+    int nblk;
+    ~ProfDump() {
+      if (!d) return;
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> h((size_t)4 * EPI_WARPS * nblk);
+      cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+      double w = 0, dr = 0, ep = 0, nt = 0;
+      for (size_t i = 0; i < h.size(); i += 4) {
+        w += (double)h[i];
+        dr += (double)h[i + 1];
+        ep += (double)h[i + 2];
+        nt += (double)h[i + 3];
+      }
+      if (nt > 0)
+        fprintf(stderr, "[umma prof] per warp-tile cycles: wait %.0f  drain %.0f  lean epilogue %.0f  (warp-tiles %.0f)\n", w / nt,
+                dr / nt, ep / nt, nt);
+    }
+  } prof_dump{stream, want_prof ? d_prof : nullptr, sm_count};
+#define BIXCOR_UMMA_CASE(KIND, EPI)                                                          \
+  if (kind == KIND && epi == EPI)                                                            \
+    return ctas == 2 ? launch_one<KIND, EPI, 2>(stream, sm_count, m0, m1, b0, b1, P)          \
+                     : launch_one<KIND, EPI, 1>(stream, sm_count, m0, m1, b0, b1, P);
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_PACKED)
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_DIFFCOR)

@@ -26,9 +26,14 @@ def run(tag, prec, spearman=1, n=1000, p=20000, **env):
     e = dict(os.environ); e.update({k: str(v) for k, v in env.items()})
     r = subprocess.run([sys.executable, __file__, "child", str(prec), str(spearman), str(n), str(p)], env=e, capture_output=True, text=True, timeout=600)
     print(tag, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ("ERR " + r.stderr[-300:]), flush=True)
+    prof = [ln for ln in r.stderr.splitlines() if "[umma prof]" in ln]
+    if prof:
+        print("   ", prof[-1], flush=True)
 
 probes = sys.argv[1:] or ["i8:0", "i8:1", "i8:2", "i8:3", "tf32:0", "tf32:1"]
 for pr in probes:
     kind, d, *rest = pr.split(":")
     beta = rest[0] if rest else "6.0"
-    run(f"umma {kind} dbg {d} beta {beta}", 2 if kind == "i8" else 1, BIXCOR_UMMA_DEBUG=d, PROBE_BETA=beta)
+    nn = int(rest[1]) if len(rest) > 1 else 1000
+    run(f"umma {kind} dbg {d} beta {beta} n {nn} ctas {os.environ.get('BIXCOR_UMMA_CTAS', '2')}", 2 if kind == "i8" else 1, n=nn,
+        BIXCOR_UMMA_DEBUG=d, PROBE_BETA=beta)
