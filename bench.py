@@ -313,7 +313,7 @@ def run_ours(args):
             def step():
                 _lib.check(lib.bixcor_dev_build_operand(x_dev.data_ptr(), n, p, 1, prec, g0, g1, operand.data_ptr(), inv.data_ptr()))
                 dist.all_gather_into_tensor(operand, operand[rank * slab * rb:(rank + 1) * slab * rb])
-                dist.all_gather_into_tensor(inv, inv[rank * slab:(rank + 1) * slab])
+                _lib.check(lib.bixcor_dev_operand_inv_norm(operand.data_ptr(), n, p, prec, inv.data_ptr()))  # no second collective
                 _lib.check(lib.bixcor_dev_cor_upper_rows_op(operand.data_ptr(), inv.data_ptr(), n, p, prec, 1, BETA, r0, r1,
                                                             out_dev.data_ptr()))
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "bixcor_dev_cor_upper_rows": (i32, [ptr, i64, i64, i32, i32, f64, i32, i64, i64, ptr]),
     "bixcor_dev_operand_row_bytes": (i64, [i64, i32]),
     "bixcor_dev_build_operand": (i32, [ptr, i64, i64, i32, i32, i64, i64, ptr, ptr]),
+    "bixcor_dev_operand_inv_norm": (i32, [ptr, i64, i64, i32, ptr]),
     "bixcor_dev_cor_upper_rows_op": (i32, [ptr, ptr, i64, i64, i32, i32, f64, i64, i64, ptr]),
     "bixcor_dev_cor_upper_rows_op_to_host": (i32, [ptr, ptr, i64, i64, i32, i32, f64, i64, i64, ptr]),
     "bixcor_dev_cor_dense": (i32, [ptr, i64, i64, i32, i32, ptr]),

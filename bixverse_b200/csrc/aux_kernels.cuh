@@ -176,6 +176,28 @@ pair_dot_kernel(const double* __restrict__ z, int64_t K, const int32_t* __restri
   if (lane == 0) out[warp] = sum;
 }
 
+// 1/|d| of every gene straight from its int8 digit record [K h][K l] (d = 16h + l, exact in int64): lets a
+// multi-process driver all-gather only the operand records and rebuild the norms locally.  One warp per gene.
+__global__ void __launch_bounds__(256)
+inv_norm_from_digits_kernel(const int8_t* __restrict__ rec, int64_t K, int64_t p, double* __restrict__ inv) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= p) return;
+  const int* h = reinterpret_cast<const int*>(rec + g * 2 * K);
+  const int* l = reinterpret_cast<const int*>(rec + g * 2 * K + K);
+  long long ss = 0;
+  for (int64_t i = lane; i < K / 4; i += 32) {
+    const int hw = h[i], lw = l[i];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int d = 16 * (int)(int8_t)(hw >> (8 * b)) + (int)(int8_t)(lw >> (8 * b));
+      ss += (long long)d * d;
+    }
+  }
+  ss = warp_sum_ll(ss);
+  if (lane == 0) inv[g] = 1.0 / sqrt((double)ss);
+}
+
 __global__ void fill_kernel(double* __restrict__ x, int64_t n, double v) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;

@@ -1126,6 +1126,21 @@ int bixcor_dev_build_operand(const double* d_x, int64_t n, int64_t p, int spearm
   return finish_dev(c);
 }
 
+int bixcor_dev_operand_inv_norm(const void* d_operand, int64_t n, int64_t p, int precision, double* d_inv_norm) {
+  DEV_PROLOGUE();
+  if (!d_operand || !d_inv_norm) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (precision != BIXCOR_PREC_I8EXACT) return finish_dev(c);  // the other operands are unit-norm already
+  const int K = round_up((int)n, k_padding(precision));
+  {
+    Timed tm(c, T_COLS);
+    inv_norm_from_digits_kernel<<<(unsigned)((p * 32 + 255) / 256), 256, 0, c->compute>>>((const int8_t*)d_operand, K, p,
+                                                                                       d_inv_norm);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  return finish_dev(c);
+}
+
 int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p, int precision,
                                  int shift, double beta, int64_t row_begin, int64_t row_end, double* d_out) {
   DEV_PROLOGUE();

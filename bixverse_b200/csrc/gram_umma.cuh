@@ -56,6 +56,10 @@ constexpr bool kProfile = false;
 constexpr int BM = 128, BN = 128;
 constexpr int ROW_BYTES = 128;                    // one SWIZZLE_128B row: 32 tf32 or 128 int8
 constexpr int PLANE_TILE_BYTES = BM * ROW_BYTES;  // 16 KB
+#ifndef BIXCOR_UMMA_EPI_WARPS
+#define BIXCOR_UMMA_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = BIXCOR_UMMA_EPI_WARPS;              // 8: two per scheduler, (TMEM lane quarter) x (column half); 16: four
 // CTAS = 1: one CTA per 128 x 128 tile (cta_group::1).  CTAS = 2: a CTA pair (one TPC) shares a 256 x 128
 // super-tile with tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the B tile, the
 // tensor cores of both SMs read both halves.  Per-SM operand traffic through shared memory drops from
@@ -65,9 +69,8 @@ template <int CTAS>
 struct Cfg {
   static constexpr int B_TILE_BYTES = PLANE_TILE_BYTES / CTAS;
   static constexpr int STAGE_BYTES = 2 * PLANE_TILE_BYTES + 2 * B_TILE_BYTES;  // A hi, A lo, B hi, B lo
-  static constexpr int STAGES = CTAS == 1 ? 3 : 4;
+  static constexpr int STAGES = (EPI_WARPS == 8) ? (CTAS == 1 ? 3 : 4) : (CTAS == 1 ? 2 : 3);  // smem left after the epilogue staging
 };
-constexpr int EPI_WARPS = 8;                                  // two per scheduler: (TMEM lane quarter) x (column half)
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr int EPI_COLS = BN / (EPI_WARPS / 4);                // accumulator columns owned by one epilogue warp
 constexpr int EPI_CHUNK = 16;                                 // columns transposed per step
@@ -601,7 +604,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         // by chunk (the MMA warp waits a little longer on 3% of the tiles); in exchange the 64-register
         // drain array only lives on the lean path and the kernel stays free of local-memory spills.
         const int kb_n = P.kblocks[pass];
-        if (kFragEpilogue && interior) {
+        if (kFragEpilogue && EPI_COLS == 64 && interior) {
           // ---- (ablation) lean path without a shared-memory transpose: the accumulators are read in the
           //      16x256b fragment layout, a quad holds 8 consecutive columns of a row and stores them as
           //      16-byte pairs straight to the packed row.

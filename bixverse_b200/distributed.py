@@ -80,6 +80,11 @@ class DeviceBackend:
         check(self.lib.bixcor_dev_build_operand(x.data_ptr(), n, p, int(spearman), precision, g0, g1,
                                                 operand.data_ptr(), inv_norm.data_ptr()))
 
+    def operand_inv_norm(self, operand, n, p, precision, inv_norm):
+        """Per-gene norms from the (all-gathered) operand records: saves the second collective."""
+        self._sync_in()
+        check(self.lib.bixcor_dev_operand_inv_norm(operand.data_ptr(), n, p, precision, inv_norm.data_ptr()))
+
     def cor_upper_rows_op(self, operand, inv_norm, n, p, precision, shift, beta, r0, r1):
         ln = packed_offset(r1, p, shift) - packed_offset(r0, p, shift)
         out = self.empty(max(ln, 1))[:ln]
@@ -165,7 +170,7 @@ def exchange_operand(backend, x, n, p, spearman, precision, group=None):
     backend.build_operand(x, n, p, spearman, precision, g0, g1, operand, inv)
     if world > 1:
         dist.all_gather_into_tensor(operand, operand[rank * slab * rb : (rank + 1) * slab * rb], group=group)
-        dist.all_gather_into_tensor(inv, inv[rank * slab : (rank + 1) * slab], group=group)
+        backend.operand_inv_norm(operand, n, p, precision, inv)  # instead of a second all-gather
     return operand, inv
 
 
@@ -209,7 +214,7 @@ def host_sharded_cor_upper(backend, x_host, n, p, spearman, out_host, shift=1, b
         backend.build_operand_slab(x_slab, n, spearman, precision, g0, g1, operand, inv)
     if world > 1:
         dist.all_gather_into_tensor(operand, operand[rank * slab * rb : (rank + 1) * slab * rb], group=group)
-        dist.all_gather_into_tensor(inv, inv[rank * slab : (rank + 1) * slab], group=group)
+        backend.operand_inv_norm(operand, n, p, precision, inv)  # instead of a second all-gather
     backend.cor_upper_rows_op_to_host(operand, inv, n, p, precision, shift, beta, r0, r1, out_host)
     return packed_offset(r0, p, shift), packed_offset(r1, p, shift)
 

@@ -176,6 +176,9 @@ int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spear
 int64_t bixcor_dev_operand_row_bytes(int64_t n, int precision);
 int bixcor_dev_build_operand(const double* d_x, int64_t n, int64_t p, int spearman, int precision,
                              int64_t gene_begin, int64_t gene_end, void* d_operand, double* d_inv_norm);
+/* Rebuilds the p per-gene norms of a BIXCOR_PREC_I8EXACT operand from its digit records (exact integer sums), so a
+ * multi-process driver only all-gathers the operand; a no-op for the other precisions. */
+int bixcor_dev_operand_inv_norm(const void* d_operand, int64_t n, int64_t p, int precision, double* d_inv_norm);
 int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
                                  int precision, int shift, double beta, int64_t row_begin, int64_t row_end,
                                  double* d_out_slice);

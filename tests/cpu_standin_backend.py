@@ -36,6 +36,10 @@ class OracleBackend:
         view[g0:g1] = z.T
         inv_norm[g0:g1] = 1.0
 
+    def operand_inv_norm(self, operand, n, p, precision, inv_norm):
+        z = operand.numpy().view(np.float64).reshape(-1, n)[:p]
+        inv_norm[:p] = torch.from_numpy((np.abs(z).sum(axis=1) > 0).astype(np.float64))  # 1 where a record arrived
+
     def cor_upper_rows_op(self, operand, inv_norm, n, p, precision, shift, beta, r0, r1):
         z = operand.numpy().view(np.float64).reshape(-1, n)[:p].T
         assert float(inv_norm[:p].sum()) == p  # every slab arrived

@@ -363,6 +363,10 @@ def test_operand_exchange_api(api, prec_name):
     inv = be.zeros(p)
     for g0, g1 in ((0, 256), (256, 640), (640, p)):
         be.build_operand(xd, n, p, True, prec, g0, g1, operand, inv)
+    inv2 = be.zeros(p)
+    be.operand_inv_norm(operand, n, p, prec, inv2)  # norms rebuilt from the records == norms written by the rank kernel
+    if prec_name == "i8":
+        assert torch.equal(inv2, inv)
     direct = be.cor_upper_rows(xd, n, p, True, 1, 6.0, prec, 0, p)
     for r0, r1 in ((0, p), (128, 512)):
         via = be.cor_upper_rows_op(operand, inv, n, p, prec, 1, 6.0, r0, r1)
