@@ -1,0 +1,93 @@
+"""Every BASELINE.json shape at full size on N GPUs (torchrun, one process per GPU), inputs resident in HBM:
+CUDA-event time of the whole sharded job, max over ranks.  Run it at N = 1, 2, 4, 8; one JSON object per config.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/scale_runs.py
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from bixverse_b200 import _lib, api
+from bixverse_b200 import distributed as D
+from bixverse_b200.synthetic import synthetic_bulk, synthetic_pair, synthetic_sparse_cells_fast
+
+world = int(os.environ.get("WORLD_SIZE", 1))
+rank = int(os.environ.get("RANK", 0))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+api.init(1, local)
+be = D.DeviceBackend(dev)
+OUT = []
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def timed(fn, reps=3):
+    fn()  # warm-up (allocations, tile lists, NCCL channels)
+    ts = []
+    for _ in range(reps):
+        barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        barrier()
+        ts.append(time.perf_counter() - t0)
+        del r
+    t = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def emit(d):
+    d["n_gpus"] = world
+    if rank == 0:
+        OUT.append(d)
+        print(json.dumps(d), flush=True)
+
+
+P = 199_990_000
+n, p = 1000, 20000
+x = torch.from_numpy(np.ascontiguousarray(synthetic_bulk(n, p, seed=2024, tie_heavy=True).T)).to(dev)
+for name, prec in (("i8", _lib.PREC_I8EXACT), ("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
+    t = timed(lambda: D.sharded_cor_upper(be, x, n, p, True, 1, 6.0, prec))
+    emit({"config": "C2 Spearman 20000x1000 |r|^6 packed", "precision": name, "ms": 1e3 * t, "pairs_per_s": P / t})
+for name, prec in (("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
+    t = timed(lambda: D.sharded_tom_from_exp(be, x, n, p, False, True, "v1", beta=6.0, precision=prec), reps=2)
+    emit({"config": "C4 TOM-from-exp signed v1 beta=6 20000x1000 packed", "precision": name, "ms": 1e3 * t, "alg_tflops": 8.4e12 / t / 1e12})
+del x
+xa, xb = synthetic_pair(500, 500, p, seed=2025)
+xa = torch.from_numpy(np.ascontiguousarray(xa.T)).to(dev)
+xb = torch.from_numpy(np.ascontiguousarray(xb.T)).to(dev)
+for name, prec, sp in (("f64-pearson", _lib.PREC_F64, False), ("i8-spearman", _lib.PREC_I8EXACT, True), ("tf32-pearson", _lib.PREC_TF32X3, False)):
+    t = timed(lambda: D.sharded_diffcor(be, xa, 500, xb, 500, p, sp, prec), reps=2)
+    emit({"config": "C3 diffcor 20000 genes 500 vs 500", "precision": name, "ms": 1e3 * t, "pairs_per_s": P / t})
+del xa, xb
+cells, genes = 1_000_000, 5000
+c0, c1 = cells * rank // world, cells * (rank + 1) // world
+ip, ix, dd = synthetic_sparse_cells_fast(c1 - c0, genes, seed=2027 + rank)  # this rank's cell shard
+lp, li, ld = torch.from_numpy(ip).to(dev), torch.from_numpy(ix).to(dev), torch.from_numpy(dd).to(dev)
+for name, prec in (("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
+    t = timed(lambda: D.sharded_sparse_gram_cor(be, lp, li, ld, c1 - c0, genes, prec), reps=2)
+    emit({"config": "C5 sparse CSR 1M cells x 5000 genes, cell shards + Gram all-reduce", "precision": name, "ms": 1e3 * t,
+          "pairs_per_s": genes * (genes - 1) // 2 / t})
+if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/scale_r01_n{world}.json", "w") as f:
+        for d_ in OUT:
+            f.write(json.dumps(d_) + "\n")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
