@@ -67,7 +67,23 @@ for name, prec in (("i8", _lib.PREC_I8EXACT), ("tf32", _lib.PREC_TF32X3), ("f64"
 for name, prec in (("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
     t = timed(lambda: D.sharded_tom_from_exp(be, x, n, p, False, True, "v1", beta=6.0, precision=prec), reps=2)
     emit({"config": "C4 TOM-from-exp signed v1 beta=6 20000x1000 packed", "precision": name, "ms": 1e3 * t, "alg_tflops": 8.4e12 / t / 1e12})
-del x
+# north-star target: upper-triangle correlation + 20k-gene TOM from a HOST expression matrix, results back on the host
+x_pin = x.cpu().pin_memory()
+r0, r1 = D.pair_balanced_rows(p, 1, world, rank)
+my_len = D.packed_offset(r1, p, 1) - D.packed_offset(r0, p, 1)
+cor_pin = torch.empty(max(my_len, 1), dtype=torch.float64).pin_memory()
+tom_pin = torch.empty(max(my_len, 1), dtype=torch.float64).pin_memory()
+ws = {}
+for name, prec, tprec in (("f64 (FP64 DMMA Gram + TOM)", _lib.PREC_F64, _lib.PREC_F64), ("fast (exact int8 Gram, 3xTF32 TOM)", _lib.PREC_I8EXACT, _lib.PREC_TF32X3)):
+    def job():
+        D.host_sharded_cor_upper(be, x_pin, n, p, prec == _lib.PREC_I8EXACT, cor_pin, 1, 1.0, prec, workspace=ws)
+        xd = x_pin.to(dev, non_blocking=True)
+        t_out, _ = D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=6.0, precision=tprec)
+        tom_pin[: t_out.numel()].copy_(t_out)
+        torch.cuda.synchronize(dev)
+    t = timed(job, reps=2)
+    emit({"config": "north-star: packed correlation + signed TOM (beta 6) of 20000x1000, host -> host", "precision": name, "ms": 1e3 * t})
+del x, x_pin, cor_pin, tom_pin
 xa, xb = synthetic_pair(500, 500, p, seed=2025)
 xa = torch.from_numpy(np.ascontiguousarray(xa.T)).to(dev)
 xb = torch.from_numpy(np.ascontiguousarray(xb.T)).to(dev)
