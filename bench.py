@@ -240,7 +240,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     api.init(1, local)
-    PREC = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3}
+    PREC = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3, "ozaki": _lib.PREC_OZAKI}
     peaks = load_peaks()
     steps, warmup = args.steps, max(args.warmup, 3)
 
@@ -433,7 +433,7 @@ def run_ours(args):
 
             be = DeviceBackend(dev)
             tom = {}
-            for tname in (("tf32", "f64") if not args.no_alt else ("tf32",)):
+            for tname in (("tf32", "ozaki", "f64") if not args.no_alt else ("tf32",)):
                 tprec = PREC[tname]
                 t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)  # warm-up
                 del t_out
@@ -450,7 +450,8 @@ def run_ours(args):
                               "achieved_tflops": 8.4e12 / t_tom / 1e12,
                               "kernel_ms_rank0": {"gemm": ttm["gemm_ms"], "columns": ttm["cols_ms"], "other": ttm["other_ms"]}}
             tom["config"] = ("config4: signed TOM v1 from expression, 20000 genes x 1000 samples, Pearson, beta=6, packed "
-                             "output, HBM resident; slabs exchanged + k all-reduced over NCCL when N > 1")
+                             "output, HBM resident; slabs exchanged + k all-reduced over NCCL when N > 1; tf32 = 3xTF32 tcgen05 "
+                             "(<=1e-5), ozaki = 6-slice int8 tcgen05 with FP64 recombination (<=1e-10), f64 = FP64 DMMA")
         except Exception as ex:  # report, do not hide
             tom = {"error": str(ex)}
 

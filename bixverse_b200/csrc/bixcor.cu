@@ -118,6 +118,8 @@ struct Ctx {
   Buffer x[2];          // staged expression matrices
   Buffer op[2];         // Gram operands (Z / digit planes / TF32 planes)
   Buffer aux[2];        // per-gene vectors (inv norm)
+  Buffer oz[2];         // Ozaki digit planes (+ per-row scale at the end)
+  Buffer ozg;           // Ozaki FP64 accumulation matrix (p x p)
   Buffer out;           // packed / dense result
   Buffer out2;          // affinity matrix for TOM
   Buffer vec;           // k, diag, colsum
@@ -166,6 +168,8 @@ static void ctx_destroy(Ctx* c) {
   for (auto& b : c->x) b.release();
   for (auto& b : c->op) b.release();
   for (auto& b : c->aux) b.release();
+  for (auto& b : c->oz) b.release();
+  c->ozg.release();
   c->out.release();
   c->out2.release();
   c->vec.release();
@@ -301,6 +305,9 @@ struct Operand {
   const int8_t* i8 = nullptr;   // I8EXACT: 2 planes (h, l) p x K
   const float* f32 = nullptr;   // TF32X3: 2 planes p x K
   const double* inv_norm = nullptr;
+  const int8_t* oz = nullptr;        // OZAKI: OZ_SLICES digit planes per row, p x OZ_SLICES x ozK
+  const double* oz_scale = nullptr;  // OZAKI: power-of-two row scales
+  int ozK = 0;
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -311,15 +318,35 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // halved B traffic saves (TOM 20k: 54 ms vs 43 ms), see profiles/umma_probe_r01.txt.
 static int umma_pairs(int precision, int epi) {
   if (precision == BIXCOR_PREC_F64 || g_umma_ctas == 1) return 0;
+  if (precision == BIXCOR_PREC_OZAKI) return 1;  // long-K digit passes stream their operands from HBM / L2: half the B traffic pays
   return (g_umma_ctas == 3 || epi == EPI_PACKED) ? 1 : 0;
 }
 
 static int k_padding(int precision) {
-  return precision == BIXCOR_PREC_F64 ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
+  return (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_OZAKI) ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
+}
+
+// Slice an f64 operand (rows x K, ld = ldz) into the Ozaki digit planes of ctx slot `slot`.
+static int ozaki_slice(Ctx* c, const double* d_z, int64_t ldz, int64_t k, int64_t rows, int slot, Operand* op) {
+  const int ozK = round_up((int)k, 128);
+  const size_t plane_bytes = (size_t)OZ_SLICES * ozK * rows;
+  RC_TRY(c->oz[slot].reserve(plane_bytes + 256 + sizeof(double) * (size_t)rows));
+  int8_t* planes = (int8_t*)c->oz[slot].ptr;
+  double* scale = (double*)((char*)c->oz[slot].ptr + ((plane_bytes + 255) & ~size_t(255)));
+  {
+    Timed tm(c, T_COLS);
+    ozaki_slice_kernel<<<(unsigned)rows, 128, 0, c->compute>>>(d_z, ldz, (int)k, ozK, planes, scale);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  op->oz = planes;
+  op->oz_scale = scale;
+  op->ozK = ozK;
+  return BIXCOR_OK;
 }
 
 static int check_precision(int precision, int spearman, int64_t n) {
-  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3) return BIXCOR_OK;
+  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_OZAKI) return BIXCOR_OK;
   if (precision == BIXCOR_PREC_I8EXACT) {
     if (!spearman) return fail(BIXCOR_ERR_INVALID, "BIXCOR_PREC_I8EXACT is defined for Spearman only");
     // sum d_i d_j <= n(n^2-1)/3 must fit the int32 recombination of the three digit accumulators
@@ -357,7 +384,7 @@ static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, c
 
 static int64_t operand_row_bytes(int64_t n, int precision) {
   const int64_t K = round_up((int)n, k_padding(precision));
-  return precision == BIXCOR_PREC_F64 ? 8 * K : (precision == BIXCOR_PREC_I8EXACT ? 2 * K : 8 * K);
+  return precision == BIXCOR_PREC_I8EXACT ? 2 * K : 8 * K;
 }
 
 // Gene-major operand layout (one contiguous record per gene, so gene slabs built on different
@@ -370,7 +397,7 @@ static void bind_operand(Operand* op, int64_t n, int64_t p, int precision, const
   op->i8 = nullptr;
   op->f32 = nullptr;
   op->inv_norm = inv;
-  if (precision == BIXCOR_PREC_F64) op->z64 = (const double*)base;
+  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_OZAKI) op->z64 = (const double*)base;
   else if (precision == BIXCOR_PREC_I8EXACT) op->i8 = (const int8_t*)base;
   else op->f32 = (const float*)base;
 }
@@ -389,7 +416,7 @@ static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int sp
   ColumnOut co;
   memset(&co, 0, sizeof co);
   co.kpad = K;
-  if (precision == BIXCOR_PREC_F64) {
+  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_OZAKI) {
     co.mode = COL_Z64;
     co.f64 = (double*)dst + g0 * K;
     co.ld64 = K;
@@ -409,7 +436,10 @@ static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int sp
   const int64_t cnt = g1 - g0;
   Timed tm(c, T_COLS);
   if (spearman) return launch_rank_kernel(c, xs, n, cnt, co);
-  standardise_columns_kernel<<<(unsigned)cnt, 128, 0, c->compute>>>(xs, n, (int)n, co, norm_mode);
+  // register-resident single-pass kernel when the column fits (n <= 2048, even, 16-byte aligned columns / records)
+  const bool reg_ok = n <= 2048 && (n % 2 == 0) && ((uintptr_t)xs % 16 == 0) && (K % 2 == 0) && (K - n <= 256);
+  if (reg_ok) standardise_columns_reg_kernel<<<(unsigned)cnt, 128, 0, c->compute>>>(xs, n, (int)n, co, norm_mode);
+  else standardise_columns_kernel<<<(unsigned)cnt, 128, 0, c->compute>>>(xs, n, (int)n, co, norm_mode);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return BIXCOR_OK;
@@ -423,6 +453,7 @@ static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int 
   RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
   RC_TRY(build_operand(c, d_x, n, p, spearman, precision, 0, p, c->op[slot].ptr, (double*)c->aux[slot].ptr, norm_mode));
   bind_operand(op, n, p, precision, c->op[slot].ptr, (const double*)c->aux[slot].ptr);
+  if (precision == BIXCOR_PREC_OZAKI) RC_TRY(ozaki_slice(c, op->z64, op->K, n, p, slot, op));
   return BIXCOR_OK;
 }
 
@@ -469,9 +500,49 @@ static void set_beta(EpiParams& e, double beta, int keep_sign) {
   if (beta > 1.0 && beta <= 64.0 && beta == std::floor(beta)) e.beta_int = (int)beta;
 }
 
+// FP64-class Gram on the int8 tensor cores.  G (p x p f64, ctx->ozg) accumulates the digit-pair Grams of the
+// six (group a, group b) combinations with s + t <= 5; each pass is the exact int8 kernel with EPI_ACCUM and the
+// weight 128^-(2a + 2b + 4); a finisher applies the row scales and the requested epilogue for rows [row0,row1).
+static int launch_gram_ozaki(Ctx* c, const Operand& a, int64_t p, const int2* tiles, int ntiles, int epi,
+                             const EpiParams& e, int64_t row0, int64_t row1) {
+  if (!a.oz || row0 < 0) return fail(BIXCOR_ERR_INVALID, "Ozaki path: operand not sliced / row range missing");
+  if (epi != EPI_PACKED && epi != EPI_DENSE && epi != EPI_TOM)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_OZAKI supports the correlation and TOM entry points");
+  if ((int64_t)a.ozK > 60000) return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_OZAKI supports K <= 60000 (int32 digit sums)");
+  RC_TRY(c->ozg.reserve(sizeof(double) * (size_t)p * p));
+  double* G = (double*)c->ozg.ptr;
+  CU_TRY(cudaMemsetAsync(G + row0 * p, 0, sizeof(double) * (size_t)(row1 - row0) * p, c->compute));
+  static const int kPass[6][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}, {0, 2}, {2, 0}};
+  for (auto& ab : kPass) {
+    EpiParams ea = make_epi(p);
+    ea.out = G;
+    ea.ldo = p;
+    ea.scale = std::ldexp(1.0, -7 * (2 * ab[0] + 2 * ab[1] + 4));
+    Timed tm(c, T_GEMM);
+    if (umma::launch_gram_umma(c->compute, c->sm_count, umma::KIND_I8, EPI_ACCUM, umma_pairs(BIXCOR_PREC_OZAKI, epi) ? 2 : 1, p, a.oz, a.ozK, nullptr, nullptr, 0,
+                               nullptr, tiles, ntiles, ea, OZ_SLICES, 2 * ab[0], 2 * ab[1]) != 0)
+      return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
+    g_launches++;
+  }
+  {
+    Timed tm(c, T_OTHER);
+    const dim3 grid(8, (unsigned)(row1 - row0));
+    if (epi == EPI_PACKED) ozaki_finish_packed_kernel<<<grid, 256, 0, c->compute>>>(G, a.oz_scale, e, row0, row1);
+    else if (epi == EPI_DENSE) ozaki_finish_dense_kernel<<<grid, 256, 0, c->compute>>>(G, a.oz_scale, e, row0, row1);
+    else ozaki_finish_tom_kernel<<<grid, 256, 0, c->compute>>>(G, a.oz_scale, e, row0, row1);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
 static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, const int2* tiles, int ntiles, int epi,
-                       const EpiParams& e, const Operand* cols = nullptr) {
+                       const EpiParams& e, const Operand* cols = nullptr, int64_t row0 = -1, int64_t row1 = -1) {
   if (ntiles <= 0) return BIXCOR_OK;
+  if (a.precision == BIXCOR_PREC_OZAKI) {
+    if (b || cols) return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_OZAKI supports the correlation and TOM entry points");
+    return launch_gram_ozaki(c, a, p, tiles, ntiles, epi, e, row0, row1);
+  }
   if (cols && a.precision != BIXCOR_PREC_F64)
     return fail(BIXCOR_ERR_UNSUPPORTED, "two-matrix correlation runs on the FP64 path only");
   if (a.precision == BIXCOR_PREC_F64) {
@@ -659,11 +730,12 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
     e.rbf_complement = rbf->complement;
   }
   if (!pipe)  // results stay in HBM: one launch over all tiles (no per-band tail)
-    return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_PACKED, e);
+    return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_PACKED, e, nullptr, row_begin, row_end);
   const int ngroups = (int)tl->group_tile.size() - 1;
   for (int g = 0; g < ngroups; ++g) {
     const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
-    RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e));
+    RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e, nullptr, tl->group_row[g],
+                       tl->group_row[g + 1]));
     cudaEvent_t ev = ctx_event(c);
     CU_TRY(cudaEventRecord(ev, c->compute));
     const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - e.out_base;
@@ -748,7 +820,7 @@ static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spe
   e.mirror = full ? 1 : 0;
   e.diag_one = 1;
   set_beta(e, beta, keep_sign);
-  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_DENSE, e);
+  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_DENSE, e, nullptr, row_begin, row_end);
 }
 
 static int dev_tom_connectivity(Ctx* c, double* d_a, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
@@ -809,8 +881,12 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
     g_launches++;
     op.K = K;
     op.f32 = co.f32;
+  } else if (precision == BIXCOR_PREC_OZAKI) {
+    op.K = (int)p;
+    op.z64 = d_a;
+    RC_TRY(ozaki_slice(c, d_a, p, p, p, 1, &op));  // rows of A are its columns (symmetric): digit planes of every gene
   } else {
-    return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64 and BIXCOR_PREC_TF32X3");
+    return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3 and BIXCOR_PREC_OZAKI");
   }
   const bool full = (row_begin == 0 && row_end == p);
   const int upper = (packed || full) ? 1 : 0;
@@ -828,7 +904,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   e.tom_v2 = (version == BIXCOR_TOM_V2);
   e.tom_packed = packed ? 1 : 0;
   // non-packed strip mode writes into out + 0 with absolute (i*p + j) addressing
-  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_TOM, e);
+  return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_TOM, e, nullptr, row_begin, row_end);
 }
 
 static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
@@ -1145,7 +1221,7 @@ int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm
                                  int shift, double beta, int64_t row_begin, int64_t row_end, double* d_out) {
   DEV_PROLOGUE();
   RC_TRY(validate_rows(p, row_begin, row_end));
-  if (precision < 0 || precision > 2) return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
+  if (precision < 0 || precision > 2) return fail(BIXCOR_ERR_INVALID, "operand exchange supports precisions 0..2 (got %d)", precision);
   if (row_begin < row_end) {
     Operand op;
     bind_operand(&op, n, p, precision, d_operand, d_inv_norm);
@@ -1389,6 +1465,7 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
   RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
   // the correlation feeding the TOM is always the exact / requested-precision Gram
+  // (Ozaki pays off on the long-K A*A product; at K = n the FP64 DMMA Gram is faster, so it feeds the TOM)
   const int cor_prec = (precision == BIXCOR_PREC_TF32X3) ? BIXCOR_PREC_TF32X3 : BIXCOR_PREC_F64;
   RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
                       (double*)c->out2.ptr));

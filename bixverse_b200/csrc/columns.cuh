@@ -12,6 +12,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace bixcor {
 
@@ -505,6 +506,160 @@ standardise_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, Col
     if (out.mode == COL_Z64) out.f64[j * out.ld64 + i] = z;
     else emit_tf32(out, j, i, z);
   }
+}
+
+// Same for n <= 2048 with one trip through HBM: the column is read ONCE with 128-bit loads (16 bytes per lane,
+// coalesced), kept in registers (up to 8 double2 per thread), reduced by warp shuffles + a block step, and the
+// operand is written with 128-bit stores.  Requires n even and 16-byte aligned columns (host checks).
+__global__ void __launch_bounds__(128)
+standardise_columns_reg_kernel(const double* __restrict__ x, int64_t ldx, int n, ColumnOut out, int norm_mode) {
+  __shared__ double scr[32];
+  const int tid = threadIdx.x;
+  const int64_t j = blockIdx.x;
+  const double2* col = reinterpret_cast<const double2*>(x + j * ldx);
+  const int n2 = n >> 1;
+  double2 v[8];
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i2 = r * 128 + tid;
+    v[r] = (i2 < n2) ? __ldg(col + i2) : make_double2(0.0, 0.0);
+    s += v[r].x + v[r].y;
+  }
+  const double mean = (norm_mode == 2) ? 0.0 : block_sum(s, scr) / (double)n;
+  double q = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i2 = r * 128 + tid;
+    if (i2 < n2) {
+      v[r].x -= mean;
+      v[r].y -= mean;
+      q += v[r].x * v[r].x + v[r].y * v[r].y;
+    }
+  }
+  const double norm = (norm_mode == 1) ? 1.0 : sqrt(block_sum(q, scr));
+  const int k2 = out.kpad >> 1;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {  // kpad <= n + 31: one extra trip covers the zero padding
+    const int i2 = r * 128 + tid;
+    if (i2 >= k2) break;
+    double2 z = make_double2(0.0, 0.0);
+    if (r < 8 && i2 < n2) z = make_double2(v[r].x / norm, v[r].y / norm);
+    if (out.mode == COL_Z64) {
+      reinterpret_cast<double2*>(out.f64 + j * out.ld64)[i2] = z;
+    } else {
+      const float h0 = to_tf32((float)z.x), h1 = to_tf32((float)z.y);
+      const float l0 = to_tf32((float)(z.x - (double)h0)), l1 = to_tf32((float)(z.y - (double)h1));
+      reinterpret_cast<float2*>(out.f32 + j * out.ld32)[i2] = make_float2(h0, h1);
+      reinterpret_cast<float2*>(out.f32 + out.plane32 + j * out.ld32)[i2] = make_float2(l0, l1);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Ozaki-style operand for the FP64-accurate Gram on the int8 tensor cores (BIXCOR_PREC_OZAKI).
+// Row g of an f64 matrix becomes scale[g] = 2^e with |z / scale| < 0.5 and OZ_SLICES balanced base-128 digits per
+// element, z / scale = sum_t d_t 128^-(t+1) + O(128^-6), d_t in [-64, 64] (int8).  Record layout: [OZ_SLICES][kpad]
+// int8 per row, so planes (2a, 2a+1) form the digit pair "group a" that one pass of the int8 kernel multiplies.
+// All arithmetic here is exact in FP64 (scaling by powers of two, rint, subtraction of the rounded part).
+// ----------------------------------------------------------------------------
+constexpr int OZ_SLICES = 6;
+
+__global__ void __launch_bounds__(128)
+ozaki_slice_kernel(const double* __restrict__ z, int64_t ld, int k, int kpad, int8_t* __restrict__ planes,
+                   double* __restrict__ scale) {
+  __shared__ double scr[4];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t g = blockIdx.x;
+  const double* src = z + g * ld;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  double amax = 0.0;
+  bool bad = false;
+  for (int i = tid; i < k; i += 128) {
+    const double v = src[i];
+    if (!(fabs(v) <= 1.7976931348623157e308)) bad = true;  // NaN or inf
+    amax = fmax(amax, fabs(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) scr[warp] = amax;
+  if (bad) s_bad = 1;
+  __syncthreads();
+  amax = fmax(fmax(scr[0], scr[1]), fmax(scr[2], scr[3]));
+  double s = 0.0, inv_s = 0.0;
+  if (amax > 0.0 && !s_bad) {
+    int ex;
+    frexp(amax, &ex);        // amax = m * 2^ex, m in [0.5, 1)
+    s = ldexp(1.0, ex + 1);  // |z| / s < 0.5
+    inv_s = ldexp(1.0, -(ex + 1));
+  }
+  if (tid == 0) scale[g] = s_bad ? __longlong_as_double(0x7ff8000000000000ll) : s;
+  int8_t* rec = planes + g * (int64_t)OZ_SLICES * kpad;
+  for (int i4 = tid * 4; i4 < kpad; i4 += 512) {  // four elements per thread: one 32-bit store per plane
+    uint32_t w[OZ_SLICES];
+#pragma unroll
+    for (int t = 0; t < OZ_SLICES; ++t) w[t] = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i4 + q;
+      double v = (i < k && inv_s != 0.0) ? src[i] * inv_s : 0.0;
+#pragma unroll
+      for (int t = 0; t < OZ_SLICES; ++t) {
+        const double tt = v * 128.0;
+        const double d = rint(tt);
+        v = tt - d;
+        w[t] |= ((uint32_t)(int)d & 0xffu) << (8 * q);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < OZ_SLICES; ++t) *reinterpret_cast<uint32_t*>(rec + (int64_t)t * kpad + i4) = w[t];
+  }
+}
+
+// Finishers of the Ozaki path: G holds sum_ab w_ab * (digit-pair Gram) for the upper triangle (dense, ld = p);
+// the true Gram value is scale[i] * scale[j] * G[i][j].
+__global__ void __launch_bounds__(256)
+ozaki_finish_packed_kernel(const double* __restrict__ G, const double* __restrict__ scale, EpiParams E, int64_t row0,
+                           int64_t row1) {
+  const int64_t i = row0 + blockIdx.y;
+  if (i >= row1) return;
+  const double si = scale[i];
+  const int64_t ro = packed_row_offset(i, E.p, E.shift) - E.out_base - i - E.shift;
+  for (int64_t j = i + E.shift + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < E.p; j += (int64_t)gridDim.x * blockDim.x)
+    E.out[ro + j] = epi_power(E, G[i * E.p + j] * si * scale[j] * E.scale);
+}
+
+__global__ void __launch_bounds__(256)
+ozaki_finish_dense_kernel(const double* __restrict__ G, const double* __restrict__ scale, EpiParams E, int64_t row0,
+                          int64_t row1) {
+  const int64_t i = row0 + blockIdx.y;
+  if (i >= row1) return;
+  const double si = scale[i];
+  const int64_t jstart = E.mirror ? i : 0;
+  for (int64_t j = jstart + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < E.p; j += (int64_t)gridDim.x * blockDim.x) {
+    double w = epi_power(E, G[i * E.p + j] * si * scale[j] * E.scale);
+    if (i == j && E.diag_one) w = 1.0;
+    E.out[i * E.ldo + j] = w;
+    if (E.mirror && j != i) E.out[j * E.ldo + i] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ozaki_finish_tom_kernel(const double* __restrict__ G, const double* __restrict__ scale, EpiParams E, int64_t row0,
+                        int64_t row1) {
+  const int64_t i = row0 + blockIdx.y;
+  if (i >= row1) return;
+  EpiRow R;
+  R.i = (int)i;
+  R.ro = packed_row_offset(i, E.p, 1) - E.out_base - i - 1;
+  R.k_i = E.kvec[i];
+  R.d_i = E.dvec[i];
+  const double si = scale[i];
+  const int64_t jstart = (E.tom_packed || E.mirror) ? i : 0;
+  for (int64_t j = jstart + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < E.p; j += (int64_t)gridDim.x * blockDim.x)
+    epi_store<EPI_TOM>(E, R, (int)j, G[i * E.p + j] * si * scale[j], 0);
 }
 
 // Split an existing f64 matrix (ld = ldin, `rows` x `k`) into TF32 hi/lo planes

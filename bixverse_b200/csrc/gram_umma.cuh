@@ -88,6 +88,7 @@ struct Params {
   int kblocks[2];    // 128-byte K blocks per pass
   const double* inv_norm[2];  // KIND_I8: 1/|d| per gene and pass
   unsigned long long* prof;  // optional (env BIXCOR_UMMA_PROF): per epilogue warp cycles {wait, drain, lean epilogue, tiles}
+  int plane_a0, plane_b0;  // first digit plane of the row / column operand inside the gene record (0 unless Ozaki groups)
   int zero;  // always 0; opaque to the compiler (scheduling fence, see the epilogue drain)
   int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = generic path without global stores, 3 = no MMA issue,
             // 4 = lean path without global stores, 5 = lean path without phase B, 6 = no TMA and no MMA (epilogue alone)
@@ -473,18 +474,18 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               const uint32_t fb = mapa_rank(full_bar(stage), 0);
               mbar_expect_tx_cluster(fb, STAGE_BYTES);
               const int brow = tile.y * BN + (int)cta_rank * (BN / 2);
-              tma_load_3d_pair(s0 + 0 * PLANE_TILE_BYTES, map, fb, kb * kelems, 0, tile.x * BM);
-              tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, 1, tile.x * BM);
-              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, 0, brow);
-              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, 1, brow);
+              tma_load_3d_pair(s0 + 0 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0, tile.x * BM);
+              tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0 + 1, tile.x * BM);
+              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0, brow);
+              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0 + 1, brow);
             } else if (kProfile && P.dbg == 6) {  // profiling: no operand traffic at all
               mbar_arrive(full_bar(stage));
             } else {
               mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-              tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 0, tile.x * BM);
-              tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, 1, tile.x * BM);
-              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, mapb, full_bar(stage), kb * kelems, 0, tile.y * BN);
-              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, full_bar(stage), kb * kelems, 1, tile.y * BN);
+              tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, P.plane_a0, tile.x * BM);
+              tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, P.plane_a0 + 1, tile.x * BM);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, mapb, full_bar(stage), kb * kelems, P.plane_b0, tile.y * BN);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, full_bar(stage), kb * kelems, P.plane_b0 + 1, tile.y * BN);
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -559,7 +560,9 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     // ============================ epilogue ================================
     // Warp e = warp - 4 owns TMEM lanes [32*(e%4), +32) (its hardware lane quarter) and the
     // accumulator columns [EPI_COLS*(e/4), +EPI_COLS) of every tile.
-    constexpr bool DIRECT = (KIND == KIND_I8 && EPI == EPI_PACKED);
+    // Ozaki pass: int8 digit-pair Gram accumulated into an FP64 matrix, G += w * (128^2 hh + 128 (hl + lh) + ll)
+    constexpr bool OZAKI = (KIND == KIND_I8 && EPI == EPI_ACCUM);
+    constexpr bool DIRECT = (KIND == KIND_I8 && (EPI == EPI_PACKED || EPI == EPI_ACCUM));
     static_assert(EPI_CHUNK == 16, "the direct path loads 16 accumulator columns per step");
     const int ew = (warp - 4) & 3;
     const int ch = (warp - 4) >> 2;
@@ -815,10 +818,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         double inv_i = 0.0;
         if (row_ok) {
           R = epi_row<EPI>(E, i);
-          if (KIND == KIND_I8) inv_i = P.inv_norm[pass][i];
+          if (KIND == KIND_I8 && !OZAKI) inv_i = P.inv_norm[pass][i];
         }
         const int rr = lane >> 4, cc = lane & 15;
-        const double* inv_col = (KIND == KIND_I8) ? P.inv_norm[pass] : nullptr;
+        const double* inv_col = (KIND == KIND_I8 && !OZAKI) ? P.inv_norm[pass] : nullptr;
 #pragma unroll
         for (int c = 0; c < EPI_COLS; c += EPI_CHUNK) {
           const int jb = col_base + c;
@@ -835,15 +838,21 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             tmem_ld16(tacc_direct + BN + c, r1);
             tmem_ld16(tacc_direct + 2 * BN + c, r2);
             tmem_ld_wait();
+            if (OZAKI) {
 #pragma unroll
-            for (int q = 0; q < EPI_CHUNK; ++q)
-              vals[q] = (double)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]) * inv_i;
+              for (int q = 0; q < EPI_CHUNK; ++q)  // exact: every term is an integer below 2^53
+                vals[q] = (16384.0 * (double)(int)r0[q] + 128.0 * (double)(int)r1[q] + (double)(int)r2[q]) * scale;
+            } else {
+#pragma unroll
+              for (int q = 0; q < EPI_CHUNK; ++q)
+                vals[q] = (double)(256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q]) * inv_i;
+            }
           } else {
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q)
               vals[q] = (KIND == KIND_I8) ? (double)(int)racc[c + q] * inv_i : (double)__uint_as_float(racc[c + q]);
           }
-          if (KIND == KIND_I8) {
+          if (KIND == KIND_I8 && !OZAKI) {
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= (jb + q < pp) ? __ldg(inv_col + jb + q) : 0.0;
           }
@@ -970,15 +979,15 @@ inline EncodeTiledFn encode_fn() {
 
 // 3-D map over the gene-major operand [row][plane][K]: dims (K, 2 planes, rows), box (128 bytes of K,
 // 1 plane, 128 rows), SWIZZLE_128B; out-of-range rows are zero filled (ragged last tile).
-inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, int K, int box_rows = BM) {
+inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, int K, int box_rows = BM, int nplanes = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     snprintf(err_buf(), 512, "cuTensorMapEncodeTiled entry point not available");
     return -1;
   }
   const int es = kind == KIND_TF32 ? 4 : 1;
-  cuuint64_t dims[3] = {(cuuint64_t)K, 2, (cuuint64_t)rows};
-  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * 2};
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)nplanes, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * nplanes};
   cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), 1, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
@@ -1028,7 +1037,8 @@ inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, 
 // ctas = 2: `tiles` is a pair list (first block row of the pair, block col | TILE_SECOND_INVALID).
 inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int ctas, int64_t rows,
                             const void* planes0, int K0, const double* inv0, const void* planes1, int K1,
-                            const double* inv1, const int2* tiles, int ntiles, const EpiParams& E) {
+                            const double* inv1, const int2* tiles, int ntiles, const EpiParams& E, int nplanes = 2,
+                            int plane_a0 = 0, int plane_b0 = 0) {
   if (ntiles <= 0) return 0;
   const int kelems = kind == KIND_TF32 ? 32 : 128;
   if (K0 % kelems != 0 || (planes1 && K1 % kelems != 0)) {
@@ -1036,8 +1046,8 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
     return -1;
   }
   CUtensorMap m0, m1, b0, b1;
-  if (make_map(&m0, kind, planes0, rows, K0)) return -1;
-  if (make_map(&b0, kind, planes0, rows, K0, BN / ctas)) return -1;
+  if (make_map(&m0, kind, planes0, rows, K0, BM, nplanes)) return -1;
+  if (make_map(&b0, kind, planes0, rows, K0, BN / ctas, nplanes)) return -1;
   if (planes1) {
     if (make_map(&m1, kind, planes1, rows, K1)) return -1;
     if (make_map(&b1, kind, planes1, rows, K1, BN / ctas)) return -1;
@@ -1055,6 +1065,8 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   P.inv_norm[1] = inv1;
   P.E = E;
   P.zero = 0;
+  P.plane_a0 = plane_a0;
+  P.plane_b0 = plane_b0;
   P.prof = nullptr;
   {
     const char* d = getenv("BIXCOR_UMMA_DEBUG");
@@ -1100,6 +1112,7 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   BIXCOR_UMMA_CASE(KIND_I8, EPI_PACKED)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DIFFCOR)
+  BIXCOR_UMMA_CASE(KIND_I8, EPI_ACCUM)
 #undef BIXCOR_UMMA_CASE
   snprintf(err_buf(), 512, "no tcgen05 kernel for kind %d / epilogue %d", kind, epi);
   return -1;

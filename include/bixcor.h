@@ -62,6 +62,8 @@ extern "C" {
 #define BIXCOR_PREC_F64 0    /* FP64 tensor-core (DMMA) Gram: exact path, <=1e-10 */
 #define BIXCOR_PREC_TF32X3 1 /* tcgen05 3xTF32 split, FP32 accumulate in TMEM: fast path, <=1e-5 */
 #define BIXCOR_PREC_I8EXACT 2 /* Spearman only: exact integer Gram of centred ranks on tcgen05 kind::i8 */
+#define BIXCOR_PREC_OZAKI 3   /* FP64-class Gram on the int8 tensor cores: 6 balanced base-128 digit slices per operand
+                               * (Ozaki splitting), 24 exact kind::i8 MMAs per product, FP64 recombination; <=1e-10 */
 
 /* `version` argument of the TOM entry points ("v1"/"v2" of parse_tom_types) */
 #define BIXCOR_TOM_V1 1

@@ -94,7 +94,7 @@ a = o.soft_threshold(r, 6.0, signed=True)
 np.fill_diagonal(a, 1.0)
 k = np.abs(a).sum(axis=1)
 t_cpu_cor = time.perf_counter() - t0
-for name, prec in (("f64", _lib.PREC_F64), ("tf32", _lib.PREC_TF32X3)):
+for name, prec in (("f64", _lib.PREC_F64), ("ozaki-int8", _lib.PREC_OZAKI), ("tf32", _lib.PREC_TF32X3)):
     for packed in (True, False):
         got, t = timed(lambda: api.calculate_tom_from_exp(x, True, "v1", "pearson", beta=6.0, precision=prec, packed=packed), 2)
         err = 0.0

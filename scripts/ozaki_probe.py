@@ -1,0 +1,45 @@
+"""Ozaki int8 path at full size on one GPU: time and accuracy against the FP64 DMMA path (config 2 Pearson Gram, config 4 TOM)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from bixverse_b200 import _lib, api
+from bixverse_b200 import distributed as D
+from bixverse_b200.synthetic import synthetic_bulk
+
+api.init(1, 0); lib = _lib.load()
+dev = torch.device("cuda", 0); be = D.DeviceBackend(dev)
+n, p = 1000, 20000
+x = synthetic_bulk(n, p, seed=2026)
+xd = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
+res = {}
+for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI)):
+    for spearman in (0, 1):
+        out = be.cor_upper_rows(xd, n, p, spearman, 1, 1.0, prec, 0, p)
+        _lib.check(lib.bixcor_timing_enable(1))
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        out = be.cor_upper_rows(xd, n, p, spearman, 1, 1.0, prec, 0, p)
+        torch.cuda.synchronize(); t = time.perf_counter() - t0
+        tm = _lib.last_timing(); _lib.check(lib.bixcor_timing_enable(0))
+        print(f"cor_upper {name} spearman={spearman}: wall {1e3*t:.2f} ms  kernels {tm}", flush=True)
+        res[(name, spearman)] = out
+for spearman in (0, 1):
+    d = (res[("f64", spearman)] - res[("ozaki", spearman)]).abs().max().item()
+    print(f"max |f64 - ozaki| packed correlation, spearman={spearman}: {d:.3e}", flush=True)
+del res
+toms = {}
+for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI), ("tf32", _lib.PREC_TF32X3)):
+    D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=6.0, precision=prec)
+    _lib.check(lib.bixcor_timing_enable(1))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out, _ = D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=6.0, precision=prec)
+    torch.cuda.synchronize(); t = time.perf_counter() - t0
+    tm = _lib.last_timing(); _lib.check(lib.bixcor_timing_enable(0))
+    print(f"TOM {name}: wall {1e3*t:.2f} ms  kernels {tm}", flush=True)
+    toms[name] = out
+print("max |f64 - ozaki| TOM:", (toms["f64"] - toms["ozaki"]).abs().max().item(), " max |f64 - tf32| TOM:", (toms["f64"] - toms["tf32"]).abs().max().item())
+# beta = 1 TOM (reference semantics, dense affinities: the hard case for fixed-point slices)
+t1 = {}
+for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI)):
+    out, _ = D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=1.0, precision=prec)
+    t1[name] = out
+print("max |f64 - ozaki| TOM beta=1:", (t1["f64"] - t1["ozaki"]).abs().max().item())

@@ -64,7 +64,7 @@ x = torch.from_numpy(np.ascontiguousarray(synthetic_bulk(n, p, seed=2024, tie_he
 for name, prec in (("i8", _lib.PREC_I8EXACT), ("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
     t = timed(lambda: D.sharded_cor_upper(be, x, n, p, True, 1, 6.0, prec))
     emit({"config": "C2 Spearman 20000x1000 |r|^6 packed", "precision": name, "ms": 1e3 * t, "pairs_per_s": P / t})
-for name, prec in (("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
+for name, prec in (("tf32", _lib.PREC_TF32X3), ("ozaki-int8", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
     t = timed(lambda: D.sharded_tom_from_exp(be, x, n, p, False, True, "v1", beta=6.0, precision=prec), reps=2)
     emit({"config": "C4 TOM-from-exp signed v1 beta=6 20000x1000 packed", "precision": name, "ms": 1e3 * t, "alg_tflops": 8.4e12 / t / 1e12})
 # north-star target: upper-triangle correlation + 20k-gene TOM from a HOST expression matrix, results back on the host
@@ -74,7 +74,9 @@ my_len = D.packed_offset(r1, p, 1) - D.packed_offset(r0, p, 1)
 cor_pin = torch.empty(max(my_len, 1), dtype=torch.float64).pin_memory()
 tom_pin = torch.empty(max(my_len, 1), dtype=torch.float64).pin_memory()
 ws = {}
-for name, prec, tprec in (("f64 (FP64 DMMA Gram + TOM)", _lib.PREC_F64, _lib.PREC_F64), ("fast (exact int8 Gram, 3xTF32 TOM)", _lib.PREC_I8EXACT, _lib.PREC_TF32X3)):
+for name, prec, tprec in (("f64 (FP64 DMMA Gram + TOM)", _lib.PREC_F64, _lib.PREC_F64),
+                          ("exact-class (FP64 DMMA Gram, Ozaki int8 TOM)", _lib.PREC_F64, _lib.PREC_OZAKI),
+                          ("fast (exact int8 Gram, 3xTF32 TOM)", _lib.PREC_I8EXACT, _lib.PREC_TF32X3)):
     def job():
         D.host_sharded_cor_upper(be, x_pin, n, p, prec == _lib.PREC_I8EXACT, cor_pin, 1, 1.0, prec, workspace=ws)
         xd = x_pin.to(dev, non_blocking=True)
@@ -99,6 +101,35 @@ for name, prec in (("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
     t = timed(lambda: D.sharded_sparse_gram_cor(be, lp, li, ld, c1 - c0, genes, prec), reps=2)
     emit({"config": "C5 sparse CSR 1M cells x 5000 genes, cell shards + Gram all-reduce", "precision": name, "ms": 1e3 * t,
           "pairs_per_s": genes * (genes - 1) // 2 / t})
+# ---- CPU baseline of every shape on the box's host cores (N = 1 run only, bounded samples of the same workloads):
+# the NumPy/OpenBLAS oracle port following the reference's algorithm shape (the Rust crate cannot be built here)
+if world == 1 and os.environ.get("SCALE_CPU", "1") != "0":
+    from oracle import oracle as o
+
+    try:
+        from threadpoolctl import threadpool_info
+
+        cores = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    gs = 6000
+    xs = synthetic_bulk(1000, gs, seed=2024, tie_heavy=True)
+    t0 = time.perf_counter(); o.soft_threshold(o.cor_upper_triangle(xs, True, True), 6.0); t = time.perf_counter() - t0
+    emit({"config": "C2 Spearman 20000x1000 |r|^6 packed", "precision": "cpu oracle port", "cores": cores, "sample": f"first {gs} genes",
+          "ms": 1e3 * t, "pairs_per_s": gs * (gs - 1) / 2 / t})
+    xa_s, xb_s = synthetic_pair(500, 500, gs, seed=2025)
+    t0 = time.perf_counter(); o.differential_cor(xa_s, xb_s, False); t = time.perf_counter() - t0
+    emit({"config": "C3 diffcor 20000 genes 500 vs 500", "precision": "cpu oracle port", "cores": cores, "sample": f"first {gs} genes",
+          "ms": 1e3 * t, "pairs_per_s": gs * (gs - 1) / 2 / t})
+    t0 = time.perf_counter(); o.tom_from_exp(xs, True, "v1", False, 6.0); t = time.perf_counter() - t0
+    emit({"config": "C4 TOM-from-exp signed v1 beta=6 20000x1000 packed", "precision": "cpu oracle port", "cores": cores,
+          "sample": f"first {gs} genes (full square A*A as the reference does)", "ms": 1e3 * t,
+          "alg_tflops": (2.0 * 1000 * gs * (gs - 1) / 2 + 2.0 * gs * gs * (gs - 1) / 2) / t / 1e12})
+    cs, gsp = 100_000, 2000
+    ip_s, ix_s, d_s = synthetic_sparse_cells_fast(cs, gsp, seed=2027)
+    t0 = time.perf_counter(); o.sparse_gram_cor(ip_s, ix_s, d_s, cs, gsp); t = time.perf_counter() - t0
+    emit({"config": "C5 sparse CSR 1M cells x 5000 genes, cell shards + Gram all-reduce", "precision": "cpu oracle port", "cores": cores,
+          "sample": f"{cs} cells x {gsp} genes", "ms": 1e3 * t, "pairs_per_s": gsp * (gsp - 1) / 2 / t, "pair_cells_per_s": gsp * (gsp - 1) / 2 * cs / t})
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/scale_r01_n{world}.json", "w") as f:

@@ -504,3 +504,68 @@ def test_pairwise_gene_cors_mc(api, fmt, spearman):
         assert np.abs(got[off] - dense[g1[off], g2[off]]).max() < 1e-10
     with pytest.raises(api.BixcorError):
         api.rs_pairwise_gene_cors_mc(sparse_list, [genes], [0], spearman)
+
+
+# ----------------------------------------------------------------------------- FP64-class Gram on the int8 tensor cores (Ozaki slices)
+@pytest.mark.parametrize("n,p", [(12, 14), (200, 2000), (57, 129), (1000, 257), (1500, 300)])
+@pytest.mark.parametrize("spearman", [False, True])
+def test_ozaki_int8_fp64_class_correlation(api, n, p, spearman):
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    oz = _lib.PREC_OZAKI
+    x = synthetic_bulk(n, p, seed=7 * n + p) if n >= 50 else np.random.default_rng(n + p).normal(size=(n, p))
+    dense_ref = o.column_pairwise_cor(x, spearman)
+    for shift in (True, False):
+        got = api.rs_cor_upper_triangle(x, spearman, shift, precision=oz)
+        assert _maxerr(got, o.dense_to_upper_triangle(dense_ref, shift)) < TOL64
+    got6 = api.rs_cor_upper_triangle(x, spearman, True, beta=6.0, precision=oz)
+    assert _maxerr(got6, o.soft_threshold(o.dense_to_upper_triangle(dense_ref, True), 6.0)) < TOL64
+    dense = api.rs_cor(x, spearman, precision=oz)
+    ref = dense_ref.copy()
+    np.fill_diagonal(ref, 1.0)
+    assert _maxerr(dense, ref) < TOL64
+    assert np.array_equal(dense, dense.T, equal_nan=True)
+    r0, r1 = 128, min(p, 256)
+    if p > 128:
+        part = api.rs_cor_upper_triangle(x, spearman, True, precision=oz, rows=(r0, r1))
+        full = api.rs_cor_upper_triangle(x, spearman, True, precision=oz)
+        assert np.array_equal(part, full[int(o.packed_offset(r0, p, 1)) : int(o.packed_offset(r1, p, 1))])
+
+
+@pytest.mark.parametrize("p", [5, 130, 400])
+@pytest.mark.parametrize("signed", [True, False])
+def test_ozaki_tom(api, p, signed):
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    rng = np.random.default_rng(p)
+    cor = np.corrcoef(rng.normal(size=(3 * p, p)).T)
+    for version in ("v1", "v2"):
+        got = api.calculate_tom(cor, signed, version, precision=_lib.PREC_OZAKI)
+        ref = o.calc_tom(cor if signed else np.abs(cor), signed, version)
+        off = ~np.eye(p, dtype=bool)
+        assert np.abs(got - ref)[off].max() < TOL64
+    x = synthetic_bulk(150, 500, seed=9)
+    for packed in (False, True):
+        got = api.calculate_tom_from_exp(x, signed, "v1", "pearson", beta=2.0, precision=_lib.PREC_OZAKI, packed=packed)
+        ref = o.tom_from_exp(x, signed, "v1", False, 2.0)
+        if packed:
+            assert _maxerr(got, o.dense_to_upper_triangle(ref, True)) < TOL64
+        else:
+            off = ~np.eye(500, dtype=bool)
+            assert np.abs(got - ref)[off].max() < TOL64
+
+
+def test_ozaki_nan_and_constant_columns(api):
+    from bixverse_b200 import _lib
+
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(40, 200))
+    x[:, 3] = 2.0
+    x[5, 7] = np.nan
+    got = api.rs_cor(x, False, precision=_lib.PREC_OZAKI)
+    ref = api.rs_cor(x, False)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max() < TOL64
