@@ -1465,8 +1465,7 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
   RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
   // the correlation feeding the TOM is always the exact / requested-precision Gram
-  // (Ozaki pays off on the long-K A*A product; at K = n the FP64 DMMA Gram is faster, so it feeds the TOM)
-  const int cor_prec = (precision == BIXCOR_PREC_TF32X3) ? BIXCOR_PREC_TF32X3 : BIXCOR_PREC_F64;
+  const int cor_prec = (precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_OZAKI) ? precision : BIXCOR_PREC_F64;
   RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
                       (double*)c->out2.ptr));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, packed, out);

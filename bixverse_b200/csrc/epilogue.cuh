@@ -140,7 +140,9 @@ __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R,
     if (MIRROR_INLINE && E.mirror && i != j) E.out[(int64_t)j * E.ldo + i] = w;
     return w;
   } else if (EPI == EPI_ACCUM) {
-    E.out[(int64_t)i * E.ldo + j] += v;
+    // One thread owns an element within a launch and launches are stream ordered, so the fire-and-forget
+    // reduction (RED.ADD.F64 at the L2) is deterministic; it saves the load round trip of a read-modify-write.
+    atomicAdd(&E.out[(int64_t)i * E.ldo + j], v);
     return v;
   } else if (EPI == EPI_DIFFCOR) {
     if (j > i) {

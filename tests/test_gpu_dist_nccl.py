@@ -45,7 +45,7 @@ def _worker(rank, world, port, tmpdir):
         ref = o.differential_cor(x, xb, False)
         assert np.abs(res["r_a"].cpu().numpy() - ref["r_a"][d0:d1]).max() < 1e-10
         assert np.abs(res["z_score"].cpu().numpy() - ref["z_score"][d0:d1]).max() < 1e-9
-        for prec, tol in ((_lib.PREC_F64, 1e-10), (_lib.PREC_TF32X3, 1e-5)):
+        for prec, tol in ((_lib.PREC_F64, 1e-10), (_lib.PREC_OZAKI, 1e-10), (_lib.PREC_TF32X3, 1e-5)):
             for signed in (True, False):
                 t, (t0, t1) = D.sharded_tom_from_exp(be, xd, n, p, False, signed, "v1", beta=2.0, precision=prec)
                 tref = o.dense_to_upper_triangle(o.tom_from_exp(x, signed, "v1", False, 2.0), True)
