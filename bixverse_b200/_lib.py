@@ -32,6 +32,8 @@ SIGNATURES = {
     "bixcor_packed_offset": (i64, [i64, i64, i32]),
     "bixcor_upper_to_dense": (i32, [ptr, i32, i64, ptr]),
     "bixcor_dense_to_upper": (i32, [ptr, i32, i64, ptr]),
+    "bixcor_upper_to_sparse_nnz": (i64, [ptr, i32, i64]),
+    "bixcor_upper_to_sparse": (i32, [ptr, i32, i64, ptr, ptr, ptr]),
     "bixcor_shard_rows": (i32, [i64, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
     "bixcor_rank_columns": (i32, [ptr, i64, i64, ptr]),
     "bixcor_cor_dense": (i32, [ptr, i64, i64, i32, i32, ptr]),

@@ -18,6 +18,7 @@ rs_coremo_stability         src/rust/src/methods/r_coremo.rs:191-235
 rs_pairwise_gene_cors_mc    src/rust/src/meta_cell/r_mc_processing.rs:258-283
 rs_upper_triangle_to_dense  src/rust/src/base/r_helpers.rs:75-94
 rs_dense_to_upper_triangle  src/rust/src/base/r_helpers.rs:113-134
+rs_upper_triangle_to_sparse src/rust/src/data/r_sparse.rs:43-55
 calculate_tom               R/functions_stats.R:43-59
 calculate_tom_from_exp      R/functions_stats.R:103-121
 UpperTriangularSymMat       R/classes_triangular_mat.R:10-211
@@ -38,7 +39,7 @@ from ._lib import PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_TF32X3, TOM_V1, TOM_V
 
 __all__ = [
     "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
-    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "calculate_tom", "calculate_tom_from_exp",
+    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp",
     "rs_rbf_function", "rs_rbf_function_mat", "rs_rbf_iterate_epsilons", "rs_coremo_stability", "cor_upper_triangle_rbf", "rs_pairwise_gene_cors_mc",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
     "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "BixcorError",
@@ -286,6 +287,22 @@ def cor_upper_triangle_rbf(x, spearman: bool, epsilon: float, rbf_type: str, shi
     return out
 
 
+def rs_upper_triangle_to_sparse(value, shift: bool, n: int, cs_type: str = "csc") -> dict:
+    """src/rust/src/data/r_sparse.rs:43-55: the reference's sparse list (data, indices 0-based, indptr, nrow, ncol, cs_type)."""
+    if cs_type not in ("csr", "csc"):
+        raise ValueError("Invalid cs_type")
+    v = np.ascontiguousarray(value, dtype=np.float64)
+    lib = _lib.load()
+    if v.shape[0] != lib.bixcor_packed_len(n, int(bool(shift))):
+        raise ValueError("packed length does not match n")
+    nnz = lib.bixcor_upper_to_sparse_nnz(_p(v), int(bool(shift)), n)
+    indptr = np.empty(n + 1, dtype=np.int64)
+    indices = np.empty(max(nnz, 1), dtype=np.int32)
+    data = np.empty(max(nnz, 1), dtype=np.float64)
+    check(lib.bixcor_upper_to_sparse(_p(v), int(bool(shift)), n, _p(indptr), _p(indices), _p(data)))
+    return {"data": data[:nnz], "indices": indices[:nnz], "indptr": indptr, "nrow": n, "ncol": n, "cs_type": cs_type}
+
+
 def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int, precision: int = PREC_F64) -> np.ndarray:
     """All-pairs Pearson over a cells x genes CSR matrix (north-star extension of
     rs_pairwise_gene_cors_mc, src/rust/src/meta_cell/r_mc_processing.rs:258-283)."""
@@ -340,6 +357,10 @@ class UpperTriangularSymMat:
 
     def get_sym_matrix(self) -> np.ndarray:
         return rs_upper_triangle_to_dense(self.values, self.shift, len(self.features))
+
+    def get_sparse_matrix(self) -> dict:
+        """R/classes_triangular_mat.R:125-140 (the sparse list; Matrix::sparseMatrix is the R side's business)."""
+        return rs_upper_triangle_to_sparse(self.values, self.shift, len(self.features), "csc")
 
 
 class UpperTriangleDiffcorMat:

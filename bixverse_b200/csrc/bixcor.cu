@@ -1151,6 +1151,49 @@ int bixcor_dense_to_upper(const double* dense, int shift, int64_t p, double* out
   return BIXCOR_OK;
 }
 
+int64_t bixcor_upper_to_sparse_nnz(const double* packed, int shift, int64_t p) {
+  if (!packed || p < 0) return -1;
+  const int64_t len = shift ? p * (p - 1) / 2 : p * (p + 1) / 2;
+  int64_t nnz = shift ? p : 0;  // unit diagonal
+  int64_t idx = 0;
+  for (int64_t i = 0; i < p; ++i)
+    for (int64_t j = i + (shift ? 1 : 0); j < p; ++j, ++idx)
+      if (packed[idx] != 0.0) nnz += (i == j) ? 1 : 2;
+  (void)len;
+  return nnz;
+}
+
+int bixcor_upper_to_sparse(const double* packed, int shift, int64_t p, int64_t* indptr, int32_t* indices, double* data) {
+  if (!packed || !indptr || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
+  const int s = shift ? 1 : 0;
+  int64_t pos = 0;
+  for (int64_t c = 0; c < p; ++c) {
+    indptr[c] = pos;
+    for (int64_t r = 0; r < c; ++r) {  // rows above the diagonal: element (r, c) of the packed rows r
+      const double v = packed[packed_row_offset(r, p, s) + (c - r - s)];
+      if (v != 0.0) {
+        indices[pos] = (int32_t)r;
+        data[pos++] = v;
+      }
+    }
+    const double d = s ? 1.0 : packed[packed_row_offset(c, p, 0)];
+    if (d != 0.0) {
+      indices[pos] = (int32_t)c;
+      data[pos++] = d;
+    }
+    const double* row = packed + packed_row_offset(c, p, s);  // rows below: the contiguous run of packed row c
+    for (int64_t r = c + 1; r < p; ++r) {
+      const double v = row[r - c - s];
+      if (v != 0.0) {
+        indices[pos] = (int32_t)r;
+        data[pos++] = v;
+      }
+    }
+  }
+  indptr[p] = pos;
+  return BIXCOR_OK;
+}
+
 int bixcor_shard_rows(int64_t p, int shift, int world, int rank, int64_t* row_begin, int64_t* row_end) {
   if (world < 1 || rank < 0 || rank >= world || p < 0 || !row_begin || !row_end)
     return fail(BIXCOR_ERR_INVALID, "bad shard arguments");

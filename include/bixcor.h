@@ -88,6 +88,13 @@ int64_t bixcor_packed_len(int64_t p, int shift);
 int64_t bixcor_packed_offset(int64_t i, int64_t p, int shift);
 int bixcor_upper_to_dense(const double* packed, int shift, int64_t p, double* out_pp);
 int bixcor_dense_to_upper(const double* dense_pp, int shift, int64_t p, double* out_packed);
+/* rs_upper_triangle_to_sparse (src/rust/src/data/r_sparse.rs:43-55; crate CompressedSparseData2::from_upper_triangle_sym)
+ * behind upper_triangular_sym_mat$get_sparse_matrix() (R/classes_triangular_mat.R:125-140): the symmetric matrix of a
+ * packed vector as compressed sparse columns (== rows, it is symmetric): exact zeros dropped, diagonal := 1 when shift,
+ * row indices ascending inside a column, 0-based (inst/tinytest/test_sparse.R:5-50 compares with Matrix's @i/@p/@x).
+ * Two calls: the count, then the fill into caller-allocated indptr[p+1] / indices[nnz] / data[nnz]. */
+int64_t bixcor_upper_to_sparse_nnz(const double* packed, int shift, int64_t p);
+int bixcor_upper_to_sparse(const double* packed, int shift, int64_t p, int64_t* indptr, int32_t* indices, double* data);
 /* Block-row range [row_begin,row_end) of rank `rank` of `world`: equal pair-count
  * quantiles rounded to 128 rows, so every rank owns one contiguous packed range. */
 int bixcor_shard_rows(int64_t p, int shift, int world, int rank, int64_t* row_begin, int64_t* row_end);

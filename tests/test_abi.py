@@ -60,6 +60,35 @@ def test_reference_sparse_vector(lib_built, golden_dir):
     assert np.array_equal(d, np.array(kat["sparse_dense_expected"]))
 
 
+def test_upper_triangle_to_sparse_matches_reference_test(lib_built):
+    """inst/tinytest/test_sparse.R:5-50: the packed vector c(0.3, 0, 1, 0, 0.2, -0.5), n = 4, shift TRUE as CSC equals
+    Matrix's sparse form of rs_upper_triangle_to_dense(...) (scipy.sparse is the Matrix stand-in)."""
+    import scipy.sparse as sp
+
+    from bixverse_b200 import api
+
+    data = np.array([0.3, 0.0, 1.0, 0.0, 0.2, -0.5])
+    got = api.rs_upper_triangle_to_sparse(data, True, 4, "csc")
+    dense = api.rs_upper_triangle_to_dense(data, True, 4)
+    ref = sp.csc_matrix(dense)
+    ref.sort_indices()
+    assert got["nrow"] == 4 and got["ncol"] == 4 and got["cs_type"] == "csc"
+    assert np.array_equal(got["indptr"], ref.indptr) and np.array_equal(got["indices"], ref.indices)
+    assert np.array_equal(got["data"], ref.data)
+    assert list(got["indptr"]) == [0, 3, 6, 8, 12]
+    rng = np.random.default_rng(0)
+    for p, shift in ((1, True), (7, True), (9, False), (40, True)):
+        v = rng.normal(size=p * (p - 1) // 2 if shift else p * (p + 1) // 2)
+        v[rng.uniform(size=v.shape) < 0.4] = 0.0
+        got = api.rs_upper_triangle_to_sparse(v, shift, p, "csr")
+        ref = sp.csc_matrix(o.upper_triangle_to_dense(v, shift, p))
+        ref.sort_indices()
+        assert np.array_equal(got["indptr"], ref.indptr) and np.array_equal(got["indices"], ref.indices)
+        assert np.array_equal(got["data"], ref.data)
+    with pytest.raises(ValueError):
+        api.rs_upper_triangle_to_sparse(data, True, 4, "coo")
+
+
 def test_shard_rows_matches_oracle(lib_built):
     from bixverse_b200 import api
 
