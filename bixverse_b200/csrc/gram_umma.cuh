@@ -1,4 +1,5 @@
-// tcgen05 / TMEM Gram kernels: the fast 3xTF32 path and the exact int8 Spearman path.
+// tcgen05 / TMEM Gram kernels: the fast 3xTF32 path, the exact int8 Spearman path and the int8 passes of the
+// FP64-class Ozaki path.
 //
 //   G[i][j] = sum_k R[i][k] * C[j][k]   with both operands K-major, exactly the shape of
 //   Z'Z (column_pairwise_cor, src/rust/src/base/r_cors_similarity.rs:74) and of the A*A of
@@ -11,12 +12,16 @@
 //              l in [-8,7]; plane 0 = h, plane 1 = l (int8).  Three exact int32 accumulators
 //              hh, hl+lh, ll; the epilogue recombines S = 256*hh + 16*(hl+lh) + ll exactly in
 //              FP64 and scales by 1/(|d_i||d_j|): an integer-exact Gram at int8 tensor rate.
+//              The same kind runs the Ozaki passes (BIXCOR_PREC_OZAKI): operand records hold six base-128
+//              digit planes, a pass multiplies two plane pairs and adds w * (128^2 hh + 128 (hl+lh) + ll)
+//              into an FP64 matrix (EPI_ACCUM, RED.ADD.F64).
 //
 // Structure (persistent, warp specialised, one CTA per SM):
 //   warp 0   TMA producer: 4 x cp.async.bulk.tensor (A hi/lo, B hi/lo tiles of 128 rows x 128 B,
 //            SWIZZLE_128B) per pipeline stage, completion on an mbarrier (complete_tx)
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1 (M=128, N=128) with
-//            shared-memory descriptors; tcgen05.commit releases smem stages / publishes accumulators
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1 (M=128, N=128) - or, as the leader of a
+//            CTA pair, cta_group::2 (M=256) - with shared-memory descriptors; tcgen05.commit releases smem
+//            stages / publishes accumulators
 //   warp 2   TMEM allocator
 //   warps 4-11 epilogue (two per scheduler): drain the accumulators with tcgen05.ld into registers
 //            (releasing TMEM to the MMA warp at once), then run the fused epilogue (epilogue.cuh)
@@ -62,9 +67,9 @@ constexpr int PLANE_TILE_BYTES = BM * ROW_BYTES;  // 16 KB
 constexpr int EPI_WARPS = BIXCOR_UMMA_EPI_WARPS;              // 8: two per scheduler, (TMEM lane quarter) x (column half); 16: four
 // CTAS = 1: one CTA per 128 x 128 tile (cta_group::1).  CTAS = 2: a CTA pair (one TPC) shares a 256 x 128
 // super-tile with tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the B tile, the
-// tensor cores of both SMs read both halves.  Per-SM operand traffic through shared memory drops from
-// 32 KB to 24 KB per MMA and the TMA fill from 64 KB to 48 KB per K block - the K loop of the 1-CTA kernel is
-// bound by exactly that traffic (profiles/README_r01.md).
+// tensor cores of both SMs read both halves.  Per-SM operand staging drops from 64 KB to 48 KB per K block (L2
+// and TMA traffic -25 %).  Measured (profiles/umma_probe_r01.txt): +3 % on the packed correlation, a win on the
+// Ozaki passes whose operands stream from HBM/L2, a loss on the long-K TF32 TOM (cross-CTA drain handshake).
 template <int CTAS>
 struct Cfg {
   static constexpr int B_TILE_BYTES = PLANE_TILE_BYTES / CTAS;
