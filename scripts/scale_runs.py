@@ -91,7 +91,7 @@ del x, x_pin, cor_pin, tom_pin
 xa, xb = synthetic_pair(500, 500, p, seed=2025)
 xa = torch.from_numpy(np.ascontiguousarray(xa.T)).to(dev)
 xb = torch.from_numpy(np.ascontiguousarray(xb.T)).to(dev)
-for name, prec, sp in (("f64-pearson", _lib.PREC_F64, False), ("i8-spearman", _lib.PREC_I8EXACT, True), ("tf32-pearson", _lib.PREC_TF32X3, False)):
+for name, prec, sp in (("f64-pearson", _lib.PREC_F64, False), ("i8-spearman", _lib.PREC_I8EXACT, True), ("tf32-pearson", _lib.PREC_TF32X3, False), ("ozaki-pearson", _lib.PREC_OZAKI, False)):
     t = timed(lambda: D.sharded_diffcor(be, xa, 500, xb, 500, p, sp, prec), reps=2)
     emit({"config": "C3 diffcor 20000 genes 500 vs 500", "precision": name, "ms": 1e3 * t, "pairs_per_s": P / t})
 del xa, xb

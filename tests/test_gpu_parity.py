@@ -557,6 +557,20 @@ def test_ozaki_tom(api, p, signed):
             assert np.abs(got - ref)[off].max() < TOL64
 
 
+def test_ozaki_diffcor(api):
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_pair
+
+    xa, xb = synthetic_pair(60, 75, 333, seed=2025)
+    for spearman in (False, True):
+        ref = o.differential_cor(xa, xb, spearman)
+        got = api.rs_differential_cor(xa, xb, spearman, precision=_lib.PREC_OZAKI)
+        assert _maxerr(got["r_a"], ref["r_a"]) < TOL64 and _maxerr(got["r_b"], ref["r_b"]) < TOL64
+        assert _maxerr(got["z_score"], ref["z_score"]) < 1e-8
+        ok = ref["p_val"] > 1e-280
+        assert np.abs(got["p_val"][ok] / ref["p_val"][ok] - 1.0).max() < 1e-6
+
+
 def test_ozaki_nan_and_constant_columns(api):
     from bixverse_b200 import _lib
 
