@@ -311,6 +311,7 @@ struct Operand {
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static bool is_ozaki(int precision) { return precision == BIXCOR_PREC_OZAKI || precision == BIXCOR_PREC_OZAKI4; }
 
 // Does this (precision, epilogue) run on the CTA-pair tcgen05 kernels (=> pair tile lists)?  g_umma_ctas: 1 = never,
 // 3 = always, 2 (default) = where it measured faster on B200: the packed correlation (short K; -3 %).  With the
@@ -318,12 +319,12 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // halved B traffic saves (TOM 20k: 54 ms vs 43 ms), see profiles/umma_probe_r01.txt.
 static int umma_pairs(int precision, int epi) {
   if (precision == BIXCOR_PREC_F64 || g_umma_ctas == 1) return 0;
-  if (precision == BIXCOR_PREC_OZAKI) return 1;  // long-K digit passes stream their operands from HBM / L2: half the B traffic pays
+  if (is_ozaki(precision)) return 1;  // long-K digit passes stream their operands from HBM / L2: half the B traffic pays
   return (g_umma_ctas == 3 || epi == EPI_PACKED) ? 1 : 0;
 }
 
 static int k_padding(int precision) {
-  return (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_OZAKI) ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
+  return (precision == BIXCOR_PREC_F64 || is_ozaki(precision)) ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
 }
 
 // Slice an f64 operand (rows x K, ld = ldz) into the Ozaki digit planes of ctx slot `slot`.
@@ -346,7 +347,7 @@ static int ozaki_slice(Ctx* c, const double* d_z, int64_t ldz, int64_t k, int64_
 }
 
 static int check_precision(int precision, int spearman, int64_t n) {
-  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_OZAKI) return BIXCOR_OK;
+  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3 || is_ozaki(precision)) return BIXCOR_OK;
   if (precision == BIXCOR_PREC_I8EXACT) {
     if (!spearman) return fail(BIXCOR_ERR_INVALID, "BIXCOR_PREC_I8EXACT is defined for Spearman only");
     // sum d_i d_j <= n(n^2-1)/3 must fit the int32 recombination of the three digit accumulators
@@ -397,7 +398,7 @@ static void bind_operand(Operand* op, int64_t n, int64_t p, int precision, const
   op->i8 = nullptr;
   op->f32 = nullptr;
   op->inv_norm = inv;
-  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_OZAKI) op->z64 = (const double*)base;
+  if (precision == BIXCOR_PREC_F64 || is_ozaki(precision)) op->z64 = (const double*)base;
   else if (precision == BIXCOR_PREC_I8EXACT) op->i8 = (const int8_t*)base;
   else op->f32 = (const float*)base;
 }
@@ -416,7 +417,7 @@ static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int sp
   ColumnOut co;
   memset(&co, 0, sizeof co);
   co.kpad = K;
-  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_OZAKI) {
+  if (precision == BIXCOR_PREC_F64 || is_ozaki(precision)) {
     co.mode = COL_Z64;
     co.f64 = (double*)dst + g0 * K;
     co.ld64 = K;
@@ -453,7 +454,7 @@ static int prepare_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int 
   RC_TRY(c->aux[slot].reserve(sizeof(double) * p));
   RC_TRY(build_operand(c, d_x, n, p, spearman, precision, 0, p, c->op[slot].ptr, (double*)c->aux[slot].ptr, norm_mode));
   bind_operand(op, n, p, precision, c->op[slot].ptr, (const double*)c->aux[slot].ptr);
-  if (precision == BIXCOR_PREC_OZAKI) RC_TRY(ozaki_slice(c, op->z64, op->K, n, p, slot, op));
+  if (is_ozaki(precision)) RC_TRY(ozaki_slice(c, op->z64, op->K, n, p, slot, op));
   return BIXCOR_OK;
 }
 
@@ -512,14 +513,17 @@ static int launch_gram_ozaki(Ctx* c, const Operand& a, int64_t p, const int2* ti
   RC_TRY(c->ozg.reserve(sizeof(double) * (size_t)p * p));
   double* G = (double*)c->ozg.ptr;
   CU_TRY(cudaMemsetAsync(G + row0 * p, 0, sizeof(double) * (size_t)(row1 - row0) * p, c->compute));
+  // six slices: all digit products with s + t <= 5; four slices (BIXCOR_PREC_OZAKI4): s + t <= 3, the first three passes
   static const int kPass[6][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}, {0, 2}, {2, 0}};
-  for (auto& ab : kPass) {
+  const int npass = a.precision == BIXCOR_PREC_OZAKI4 ? 3 : 6;
+  for (int ps = 0; ps < npass; ++ps) {
+    const int* ab = kPass[ps];
     EpiParams ea = make_epi(p);
     ea.out = G;
     ea.ldo = p;
     ea.scale = std::ldexp(1.0, -7 * (2 * ab[0] + 2 * ab[1] + 4));
     Timed tm(c, T_GEMM);
-    if (umma::launch_gram_umma(c->compute, c->sm_count, umma::KIND_I8, EPI_ACCUM, umma_pairs(BIXCOR_PREC_OZAKI, epi) ? 2 : 1, p, a.oz, a.ozK, nullptr, nullptr, 0,
+    if (umma::launch_gram_umma(c->compute, c->sm_count, umma::KIND_I8, EPI_ACCUM, umma_pairs(a.precision, epi) ? 2 : 1, p, a.oz, a.ozK, nullptr, nullptr, 0,
                                nullptr, tiles, ntiles, ea, OZ_SLICES, 2 * ab[0], 2 * ab[1]) != 0)
       return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
     g_launches++;
@@ -539,7 +543,7 @@ static int launch_gram_ozaki(Ctx* c, const Operand& a, int64_t p, const int2* ti
 static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, const int2* tiles, int ntiles, int epi,
                        const EpiParams& e, const Operand* cols = nullptr, int64_t row0 = -1, int64_t row1 = -1) {
   if (ntiles <= 0) return BIXCOR_OK;
-  if (a.precision == BIXCOR_PREC_OZAKI) {
+  if (is_ozaki(a.precision)) {
     if (b || cols) return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_OZAKI supports the correlation and TOM entry points");
     return launch_gram_ozaki(c, a, p, tiles, ntiles, epi, e, row0, row1);
   }
@@ -889,7 +893,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
     g_launches++;
     op.K = K;
     op.f32 = co.f32;
-  } else if (precision == BIXCOR_PREC_OZAKI) {
+  } else if (is_ozaki(precision)) {
     op.K = (int)p;
     op.z64 = d_a;
     RC_TRY(ozaki_slice(c, d_a, p, p, p, 1, &op));  // rows of A are its columns (symmetric): digit planes of every gene
@@ -1516,7 +1520,7 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
   RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
   // the correlation feeding the TOM is always the exact / requested-precision Gram
-  const int cor_prec = (precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_OZAKI) ? precision : BIXCOR_PREC_F64;
+  const int cor_prec = (precision == BIXCOR_PREC_TF32X3 || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
   RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
                       (double*)c->out2.ptr));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, packed, out);

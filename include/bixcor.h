@@ -64,6 +64,9 @@ extern "C" {
 #define BIXCOR_PREC_I8EXACT 2 /* Spearman only: exact integer Gram of centred ranks on tcgen05 kind::i8 */
 #define BIXCOR_PREC_OZAKI 3   /* FP64-class Gram on the int8 tensor cores: 6 balanced base-128 digit slices per operand
                                * (Ozaki splitting), 24 exact kind::i8 MMAs per product, FP64 recombination; <=1e-10 */
+#define BIXCOR_PREC_OZAKI4 4  /* same with the four leading slices (three passes, 12 MMAs per product): the dropped digit
+                               * products grow with sqrt(K): <=1e-7 at K = 1000, 5e-6 on the 20k TOM (the 3xTF32 class,
+                               * 10 % faster there and free of the chunked FP32 promotion) */
 
 /* `version` argument of the TOM entry points ("v1"/"v2" of parse_tom_types) */
 #define BIXCOR_TOM_V1 1

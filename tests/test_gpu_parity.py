@@ -557,6 +557,21 @@ def test_ozaki_tom(api, p, signed):
             assert np.abs(got - ref)[off].max() < TOL64
 
 
+def test_ozaki4_medium_precision(api):
+    """Four leading Ozaki slices (three int8 passes): the cost class of 3xTF32, errors around 1e-8."""
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    oz4 = _lib.PREC_OZAKI4
+    x = synthetic_bulk(300, 700, seed=77)
+    for spearman in (False, True):
+        got = api.rs_cor_upper_triangle(x, spearman, True, precision=oz4)
+        assert _maxerr(got, o.cor_upper_triangle(x, spearman, True)) < 1e-7
+    for signed in (True, False):
+        got = api.calculate_tom_from_exp(x, signed, "v1", "pearson", beta=2.0, precision=oz4, packed=True)
+        assert _maxerr(got, o.dense_to_upper_triangle(o.tom_from_exp(x, signed, "v1", False, 2.0), True)) < 1e-7
+
+
 def test_ozaki_diffcor(api):
     from bixverse_b200 import _lib
     from bixverse_b200.synthetic import synthetic_pair
