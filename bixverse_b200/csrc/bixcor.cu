@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1073,6 +1074,17 @@ int bixcor_init_devices(int first_device, int n_gpus) {
     }
     g_ctx.push_back(c);
   }
+  // NVLink peer access between the devices of the process (slab exchange of the multi-device TOM)
+  for (auto* a : g_ctx)
+    for (auto* b : g_ctx) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a->device, b->device) == cudaSuccess && can) {
+        cudaSetDevice(a->device);
+        cudaDeviceEnablePeerAccess(b->device, 0);
+      }
+      cudaGetLastError();  // "already enabled" is fine
+    }
   return BIXCOR_OK;
 }
 
@@ -1491,12 +1503,114 @@ static int tom_common(Ctx* c, double* d_a, int64_t p, int signed_, int version, 
   return pipe.finish();
 }
 
+// Reusable barrier of the per-device host threads; a failed thread makes every thread leave with its code.
+struct PhaseBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, count = 0, gen = 0, rc = BIXCOR_OK;
+  explicit PhaseBarrier(int n_) : n(n_) {}
+  int arrive(int my_rc) {
+    std::unique_lock<std::mutex> lk(m);
+    if (my_rc != BIXCOR_OK && rc == BIXCOR_OK) rc = my_rc;
+    const int g = gen;
+    if (++count == n) {
+      count = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != g; });
+    }
+    return rc;
+  }
+};
+
+static void even_slab(int64_t p, int nd, int d, int64_t* c0, int64_t* c1) {
+  const int64_t nb = (p + kTile - 1) / kTile;
+  *c0 = std::min<int64_t>(p, nb * d / nd * kTile);
+  *c1 = std::min<int64_t>(p, nb * (d + 1) / nd * kTile);
+}
+
+// TOM on every device of the process (bixcor_init(n), n > 1): the same three phases as the one-process-per-GPU
+// driver (bixverse_b200/distributed.py), with cudaMemcpyPeer over NVLink for the slab exchange and the host for k.
+//   phase 1  device d: affinity columns of gene slab d (from x, or uploaded from a_pp) + their connectivity
+//   exchange every device pulls the other slabs into its copy of A; k is gathered through the host
+//   phase 3  device d: TOM rows of its share (pair-balanced when packed, equal strips when dense) -> caller's buffer
+static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int64_t p, int spearman, int signed_,
+                            int version, double beta, int precision, int packed, double* out) {
+  const int nd_all = (int)g_ctx.size();
+  PhaseBarrier bar(nd_all);
+  std::vector<double> k_host((size_t)p, 0.0);
+  const int cor_prec = (precision == BIXCOR_PREC_TF32X3 || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
+  return for_each_device([&](Ctx* c, int d, int nd) -> int {
+    int64_t c0, c1;
+    even_slab(p, nd, d, &c0, &c1);
+    double* d_a = nullptr;
+    double* d_k = nullptr;
+    int rc = [&]() -> int {
+      RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
+      RC_TRY(c->vec.reserve(sizeof(double) * (size_t)p * 4));
+      d_a = (double*)c->out2.ptr;
+      d_k = (double*)c->vec.ptr + p;
+      if (c1 > c0) {
+        if (x) {
+          RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
+          RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
+          RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, c0, c1, d_a));
+        } else {
+          RC_TRY(h2d(c, d_a + c0 * p, a_pp + c0 * p, sizeof(double) * (size_t)(c1 - c0) * p, c->compute));
+        }
+        RC_TRY(dev_tom_connectivity(c, d_a, p, signed_, c0, c1, d_k));
+        RC_TRY(finish(c));
+        CU_TRY(cudaMemcpy(k_host.data() + c0, d_k + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost));
+      }
+      return BIXCOR_OK;
+    }();
+    rc = bar.arrive(rc);
+    if (rc != BIXCOR_OK) return rc;
+    rc = [&]() -> int {
+      for (int s_ = 0; s_ < nd; ++s_) {
+        if (s_ == d) continue;
+        int64_t s0, s1;
+        even_slab(p, nd, s_, &s0, &s1);
+        if (s1 > s0)
+          CU_TRY(cudaMemcpyPeerAsync(d_a + s0 * p, c->device, (const double*)g_ctx[s_]->out2.ptr + s0 * p, g_ctx[s_]->device,
+                                     sizeof(double) * (size_t)(s1 - s0) * p, c->compute));
+      }
+      CU_TRY(cudaMemcpyAsync(d_k, k_host.data(), sizeof(double) * (size_t)p, cudaMemcpyHostToDevice, c->compute));
+      return finish(c);
+    }();
+    rc = bar.arrive(rc);  // nobody reuses a slab buffer while a peer may still be reading it
+    if (rc != BIXCOR_OK) return rc;
+    int64_t r0, r1;
+    if (packed) shard_rows_impl(p, 1, nd, d, &r0, &r1);
+    else even_slab(p, nd, d, &r0, &r1);
+    if (r1 <= r0) return BIXCOR_OK;
+    if (packed) {
+      const int64_t o0 = packed_row_offset(r0, p, 1), o1 = packed_row_offset(r1, p, 1);
+      RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o1 - o0)));
+      RC_TRY(dev_tom_rows(c, d_a, d_k, p, signed_, version, precision, 1, r0, r1, (double*)c->out.ptr));
+      RC_TRY(finish(c));
+      D2HPipe pipe(c, out);
+      RC_TRY(pipe.push(out + o0, c->out.ptr, sizeof(double) * (size_t)(o1 - o0), nullptr));
+      return pipe.finish();
+    }
+    RC_TRY(c->out.reserve(sizeof(double) * (size_t)p * p));  // strip mode addresses the full matrix
+    RC_TRY(dev_tom_rows(c, d_a, d_k, p, signed_, version, precision, 0, r0, r1, (double*)c->out.ptr));
+    RC_TRY(finish(c));
+    D2HPipe pipe(c, out);
+    RC_TRY(pipe.push(out + r0 * p, (double*)c->out.ptr + r0 * p, sizeof(double) * (size_t)(r1 - r0) * p, nullptr));
+    return pipe.finish();
+  });
+}
+
 int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int precision, double* out_pp) {
   RC_TRY(ensure_init());
   if (!a_pp || !out_pp) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (p < 1) return fail(BIXCOR_ERR_INVALID, "p must be >= 1");
   if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
     return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
+  if (g_ctx.size() > 1 && p >= 2 * kTile)
+    return tom_multi_device(nullptr, 0, a_pp, p, 0, signed_, version, 1.0, precision, 0, out_pp);
   Ctx* c = g_ctx[0];
   CU_TRY(cudaSetDevice(c->device));
   call_begin(c);
@@ -1512,6 +1626,8 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(host_shape_check(x, n, p, out));
   if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
     return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
+  if (g_ctx.size() > 1 && p >= 2 * kTile)
+    return tom_multi_device(x, n, nullptr, p, spearman, signed_, version, beta, precision, packed, out);
   Ctx* c = g_ctx[0];
   CU_TRY(cudaSetDevice(c->device));
   call_begin(c);

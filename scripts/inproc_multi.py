@@ -37,6 +37,20 @@ for nd in [d for d in (1, 2, 4, 8) if d <= ndev_max]:
     t = float(np.median(ts[1:]))
     rows.append({"config": "C3 diffcor host->host, one process", "devices": nd, "precision": "f64", "ms": 1e3 * t, "pairs_per_s": P / t})
     print(json.dumps(rows[-1]), flush=True)
+# multi-device TOM from a host matrix (packed result on the host): FP64 DMMA / Ozaki int8 / 3xTF32
+tom_out = torch.empty(P, dtype=torch.float64).pin_memory()
+for nd in [d for d in (1, 2, 4, 8) if d <= ndev_max]:
+    api.init(nd, 0)
+    for name, prec in (("tf32", _lib.PREC_TF32X3), ("ozaki", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
+        ts = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            _lib.check(lib.bixcor_tom_from_exp(x.data_ptr(), n, p, 0, 1, _lib.TOM_V1, 6.0, prec, 1, tom_out.data_ptr()))
+            ts.append(time.perf_counter() - t0)
+        t = float(np.median(ts[1:]))
+        rows.append({"config": "C4 TOM-from-exp host->host, one process", "devices": nd, "precision": name, "ms": 1e3 * t,
+                     "checksum": float(tom_out[:1000000].sum())})
+        print(json.dumps(rows[-1]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/inproc_multi_r01.json", "w") as f:
     for r in rows:

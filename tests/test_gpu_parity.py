@@ -343,6 +343,36 @@ def test_in_process_multi_device(api):
         assert np.array_equal(dsingle[k], dmulti[k], equal_nan=True)
 
 
+@pytest.mark.parametrize("prec_name", ["f64", "tf32", "ozaki"])
+def test_in_process_multi_device_tom(api, prec_name):
+    """bixcor_init(n) with n > 1: slab affinities per device, NVLink peer exchange, k through the host, TOM rows per device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    prec = {"f64": _lib.PREC_F64, "tf32": _lib.PREC_TF32X3, "ozaki": _lib.PREC_OZAKI}[prec_name]
+    tol = TOL32 if prec_name == "tf32" else TOL64
+    x = synthetic_bulk(90, 900, seed=41)
+    cor = np.corrcoef(x.T)
+    try:
+        api.init(2, 0)
+        for signed in (True, False):
+            ref = o.tom_from_exp(x, signed, "v1", False, 2.0)
+            off = ~np.eye(900, dtype=bool)
+            dense = api.calculate_tom_from_exp(x, signed, "v1", "pearson", beta=2.0, precision=prec, packed=False)
+            assert np.abs(dense - ref)[off].max() < tol
+            packed = api.calculate_tom_from_exp(x, signed, "v1", "pearson", beta=2.0, precision=prec, packed=True)
+            assert _maxerr(packed, o.dense_to_upper_triangle(ref, True)) < tol
+            got = api.calculate_tom(cor, signed, "v2", precision=prec)
+            ref2 = o.calc_tom(cor if signed else np.abs(cor), signed, "v2")
+            assert np.abs(got - ref2)[off].max() < tol
+    finally:
+        api.init(1, 0)
+
+
 @pytest.mark.parametrize("prec_name", ["f64", "i8", "tf32"])
 def test_operand_exchange_api(api, prec_name):
     """Gene slabs of the Gram operand built separately (as different ranks would) give the same packed result."""
