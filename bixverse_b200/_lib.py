@@ -42,6 +42,7 @@ SIGNATURES = {
     "bixcor_diffcor": (i32, [ptr, i64, ptr, i64, i64, i32, i32, ptr, ptr, ptr, ptr]),
     "bixcor_diffcor_rows": (i32, [ptr, i64, ptr, i64, i64, i32, i32, i64, i64, ptr, ptr, ptr, ptr]),
     "bixcor_tom": (i32, [ptr, i64, i32, i32, i32, ptr]),
+    "bixcor_tom_packed": (i32, [ptr, i32, i64, i32, i32, i32, ptr]),
     "bixcor_tom_from_exp": (i32, [ptr, i64, i64, i32, i32, i32, f64, i32, i32, ptr]),
     "bixcor_covariance": (i32, [ptr, i64, i64, ptr]),
     "bixcor_cos": (i32, [ptr, i64, i64, ptr]),

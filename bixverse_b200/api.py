@@ -21,6 +21,7 @@ rs_dense_to_upper_triangle  src/rust/src/base/r_helpers.rs:113-134
 rs_upper_triangle_to_sparse src/rust/src/data/r_sparse.rs:43-55
 calculate_tom               R/functions_stats.R:43-59
 calculate_tom_from_exp      R/functions_stats.R:103-121
+cor_module_tom              R/methods_coexp_cor.R:118-164
 UpperTriangularSymMat       R/classes_triangular_mat.R:10-211
 UpperTriangleDiffcorMat     R/classes_triangular_mat.R:224-341
 =========================== =================================================
@@ -39,7 +40,7 @@ from ._lib import PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_TF32X3, 
 
 __all__ = [
     "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
-    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp",
+    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp", "cor_module_tom",
     "rs_rbf_function", "rs_rbf_function_mat", "rs_rbf_iterate_epsilons", "rs_coremo_stability", "cor_upper_triangle_rbf", "rs_pairwise_gene_cors_mc",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
     "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "PREC_OZAKI4", "BixcorError",
@@ -183,6 +184,18 @@ def calculate_tom(cor_mat, signed: bool, version: str = "v1", precision: int = P
     if not signed:
         cor_mat = np.abs(cor_mat)  # R/functions_stats.R:52-54
     return rs_tom(cor_mat, version, signed, precision)
+
+
+def cor_module_tom(cor_res: "UpperTriangularSymMat", signed: bool = True, version: str = "v2",
+                   precision: int = PREC_F64) -> "UpperTriangularSymMat":
+    """R/methods_coexp_cor.R:118-164 on the result container: get_sym_matrix -> rs_tom -> rs_dense_to_upper_triangle,
+    fused into one library call; returns the TOM as a new shift = 1 container (the R method stores it back)."""
+    ver = _parse_tom_types(version)
+    p = len(cor_res.features)
+    lib = _lib.load()
+    out = np.empty(lib.bixcor_packed_len(p, 1), dtype=np.float64)
+    check(lib.bixcor_tom_packed(_p(cor_res.values), int(cor_res.shift), p, int(bool(signed)), ver, precision, _p(out)))
+    return UpperTriangularSymMat(out, cor_res.features, True)
 
 
 def calculate_tom_from_exp(x, signed: bool, version: str, cor_method: str = "pearson", beta: float = 1.0,

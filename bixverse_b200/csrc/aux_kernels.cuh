@@ -217,6 +217,35 @@ diffcor_zp_kernel(const double* __restrict__ ra, const double* __restrict__ rb, 
   }
 }
 
+// cor_module_tom (R/methods_coexp_cor.R:118-164) unpacks the stored triangle before rs_tom
+// (rs_upper_triangle_to_dense, src/rust/src/base/r_helpers.rs:75-94: diagonal := 1 when shift, mirror).  On the
+// device: one CTA per row copies the contiguous packed run (upper part + diagonal), then a tiled transpose fills
+// the lower part with coalesced reads and writes.
+__global__ void __launch_bounds__(256)
+unpack_upper_rows_kernel(const double* __restrict__ packed, int64_t p, int shift, double* __restrict__ dense) {
+  const int64_t i = blockIdx.x;
+  const double* row = packed + packed_row_offset(i, p, shift);
+  double* dst = dense + i * p;
+  if (shift && threadIdx.x == 0) dst[i] = 1.0;
+  for (int64_t j = i + shift + threadIdx.x; j < p; j += blockDim.x) dst[j] = row[j - i - shift];
+}
+__global__ void __launch_bounds__(256)
+mirror_upper_kernel(double* __restrict__ dense, int64_t p) {  // dense[j][i] = dense[i][j] for j > i, 32 x 32 tiles
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = (int64_t)bi * 32 + r, j = (int64_t)bj * 32 + tx;
+    t[r][tx] = (i < p && j < p) ? dense[i * p + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t j = (int64_t)bj * 32 + r, i = (int64_t)bi * 32 + tx;  // write row j, column i
+    if (j < p && i < p && j > i) dense[j * p + i] = t[tx][r];
+  }
+}
+
 __global__ void fill_kernel(double* __restrict__ x, int64_t n, double v) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;

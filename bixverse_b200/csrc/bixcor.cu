@@ -1026,6 +1026,24 @@ static void shard_rows_impl(int64_t p, int shift, int world, int rank, int64_t* 
 // ============================================================================
 using namespace bixcor;
 
+// rows [0,p) split over host threads in blocks balanced by pair count (pure index logic, no GPU involved)
+template <class F>
+static void parallel_rows(int64_t p, F fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nthr = (p < 2048) ? 1 : (int)std::max(1u, std::min(hw ? hw : 4u, 16u));
+  if (nthr == 1) {
+    fn(0, p);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthr; ++t) {
+    int64_t r0, r1;
+    shard_rows_impl(p, 1, nthr, t, &r0, &r1);
+    if (r1 > r0) th.emplace_back([=] { fn(r0, r1); });
+  }
+  for (auto& t : th) t.join();
+}
+
 extern "C" {
 
 const char* bixcor_last_error(void) {
@@ -1152,26 +1170,30 @@ int64_t bixcor_packed_offset(int64_t i, int64_t p, int shift) { return packed_ro
 
 int bixcor_upper_to_dense(const double* packed, int shift, int64_t p, double* out) {
   if (!packed || !out || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
-  int64_t idx = 0;
-  for (int64_t i = 0; i < p; ++i)
-    for (int64_t j = i; j < p; ++j) {
-      if (shift && i == j) {
-        out[i + j * p] = 1.0;
-      } else {
-        out[i + j * p] = packed[idx];
-        out[j + i * p] = packed[idx];
-        ++idx;
+  const int s = shift ? 1 : 0;
+  parallel_rows(p, [=](int64_t r0, int64_t r1) {
+    for (int64_t i = r0; i < r1; ++i) {
+      const double* row = packed + packed_row_offset(i, p, s);
+      if (s) out[i + i * p] = 1.0;
+      for (int64_t j = i + s; j < p; ++j) {
+        const double v = row[j - i - s];
+        out[i + j * p] = v;
+        out[j + i * p] = v;
       }
     }
+  });
   return BIXCOR_OK;
 }
 
 int bixcor_dense_to_upper(const double* dense, int shift, int64_t p, double* out) {
   if (!dense || !out || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
-  int64_t idx = 0;
-  const int64_t s = shift ? 1 : 0;
-  for (int64_t i = 0; i < p; ++i)
-    for (int64_t j = i + s; j < p; ++j) out[idx++] = dense[i + j * p];
+  const int s = shift ? 1 : 0;
+  parallel_rows(p, [=](int64_t r0, int64_t r1) {
+    for (int64_t i = r0; i < r1; ++i) {
+      double* row = out + packed_row_offset(i, p, s);
+      for (int64_t j = i + s; j < p; ++j) row[j - i - s] = dense[i + j * p];
+    }
+  });
   return BIXCOR_OK;
 }
 
@@ -1618,6 +1640,34 @@ int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int prec
   RC_TRY(c->out2.reserve(bytes));
   RC_TRY(h2d(c, c->out2.ptr, a_pp, bytes, c->compute));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, 0, out_pp);
+}
+
+// cor_module_tom in one call (R/methods_coexp_cor.R:118-164: get_sym_matrix -> rs_tom -> rs_dense_to_upper_triangle):
+// packed correlation in, packed (shift = 1) TOM out; the dense matrices only ever exist in HBM.
+int bixcor_tom_packed(const double* packed_in, int shift_in, int64_t p, int signed_, int version, int precision,
+                      double* out_packed) {
+  RC_TRY(ensure_init());
+  if (!packed_in || !out_packed) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (p < 2) return fail(BIXCOR_ERR_INVALID, "p must be >= 2");
+  if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
+    return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  const int s = shift_in ? 1 : 0;
+  const size_t in_bytes = sizeof(double) * (size_t)(s ? p * (p - 1) / 2 : p * (p + 1) / 2);
+  RC_TRY(c->out.reserve(std::max(in_bytes, sizeof(double) * (size_t)(p * (p - 1) / 2))));
+  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
+  RC_TRY(h2d(c, c->out.ptr, packed_in, in_bytes, c->compute));
+  {
+    Timed tm(c, T_OTHER);
+    unpack_upper_rows_kernel<<<(unsigned)p, 256, 0, c->compute>>>((const double*)c->out.ptr, p, s, (double*)c->out2.ptr);
+    const unsigned nb = (unsigned)((p + 31) / 32);
+    mirror_upper_kernel<<<dim3(nb, nb), 256, 0, c->compute>>>((double*)c->out2.ptr, p);
+    g_launches += 2;
+  }
+  CU_TRY(cudaGetLastError());
+  return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, 1, out_packed);
 }
 
 int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int signed_, int version, double beta,

@@ -123,6 +123,10 @@ int bixcor_diffcor_rows(const double* xa, int64_t na, const double* xb, int64_t 
 
 int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int precision, double* out_pp);
 
+/* cor_module_tom (R/methods_coexp_cor.R:118-164) in one call: the stored packed correlation (shift as stored) in,
+ * the packed shift = 1 TOM out; replaces rs_upper_triangle_to_dense + rs_tom + rs_dense_to_upper_triangle. */
+int bixcor_tom_packed(const double* packed_in, int shift_in, int64_t p, int signed_, int version, int precision,
+                      double* out_packed);
 /* packed != 0: out is the shift=1 packed vector (cor_module_tom layout), else dense p x p. */
 int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int signed_, int version,
                         double beta, int precision, int packed, double* out);

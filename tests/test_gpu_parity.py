@@ -199,6 +199,23 @@ def test_tom_from_exp(api, cor_method):
         assert _maxerr(gotb, o.dense_to_upper_triangle(refb, True)) < TOL64
 
 
+@pytest.mark.parametrize("shift", [True, False])
+def test_cor_module_tom_fused(api, shift):
+    """cor_module_tom == unpack (diag := 1 when shift) -> rs_tom -> repack, in one call."""
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(80, 450, seed=13)
+    packed = api.rs_cor_upper_triangle(x, True, shift)
+    res = api.UpperTriangularSymMat(packed, [f"g{i}" for i in range(450)], shift)
+    for signed, version in ((True, "v2"), (False, "v1")):
+        got = api.cor_module_tom(res, signed, version)
+        dense = o.upper_triangle_to_dense(packed, shift, 450)
+        ref = o.dense_to_upper_triangle(o.calc_tom(dense if signed else np.abs(dense), signed, version), True)
+        assert got.shift and _maxerr(got.values, ref) < TOL64
+        chain = api.rs_dense_to_upper_triangle(api.rs_tom(api.rs_upper_triangle_to_dense(packed, shift, 450), version, signed), True)
+        assert _maxerr(got.values, chain) < 1e-13
+
+
 def test_tom_invalid_version_is_error(api):
     with pytest.raises(ValueError, match="Invalid TOM version type"):
         api.rs_tom(np.eye(4), "v9", True)
