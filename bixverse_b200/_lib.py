@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbixcor.so")
+# BIXCOR_LIB: developer override to load an ablation build (make -C csrc VARIANT=... EXTRA=...), see scripts/perf_probe.py
+LIB_PATH = os.environ.get("BIXCOR_LIB") or os.path.join(_HERE, "libbixcor.so")
 
 OK = 0
 ERR_NO_GPU, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5

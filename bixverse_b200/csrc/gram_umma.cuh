@@ -70,16 +70,40 @@ constexpr int EPI_WARPS = BIXCOR_UMMA_EPI_WARPS;              // 8: two per sche
 // tensor cores of both SMs read both halves.  Per-SM operand staging drops from 64 KB to 48 KB per K block (L2
 // and TMA traffic -25 %).  Measured (profiles/umma_probe_r01.txt): +3 % on the packed correlation, a win on the
 // Ozaki passes whose operands stream from HBM/L2, a loss on the long-K TF32 TOM (cross-CTA drain handshake).
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);                // accumulator columns owned by one epilogue warp
+constexpr int EPI_CHUNK = 16;                                 // columns transposed per step
+// Lean epilogue with bulk-async stores (-DBIXCOR_UMMA_BULK=<columns per store: 16 / 32 / 64>): every lane finishes
+// BULK_COLS values of ITS OWN row, parks them in shared memory and hands the run to the copy engine
+// (cp.async.bulk.global.shared::cta), so the warp issues neither the transposing LDS nor the STG of the
+// default lean epilogue.  Row layout in shared memory: 16 bytes of lead padding + the run; a row whose
+// global address is 8 (mod 16) sits 8 bytes earlier so that elements 1 .. BULK_COLS-2 are 16-byte aligned on
+// both sides, its first and last element go out as scalar stores.
+#ifdef BIXCOR_UMMA_BULK
+constexpr int BULK_COLS = BIXCOR_UMMA_BULK;
+#ifdef BIXCOR_UMMA_BULK_NBUF
+constexpr int BULK_NBUF = BIXCOR_UMMA_BULK_NBUF;
+#else
+constexpr int BULK_NBUF = 1;
+#endif
+#else
+constexpr int BULK_COLS = 0;
+constexpr int BULK_NBUF = 0;
+#endif
+constexpr int BULK_ROW_BYTES = BULK_COLS * 8 + 16;
+constexpr int BULK_BUF_BYTES = 32 * BULK_ROW_BYTES;
+constexpr int BULK_WARP_BYTES = BULK_COLS ? BULK_NBUF * BULK_BUF_BYTES + EPI_COLS * 8 /*column factors*/ : 0;
+constexpr int EPI_WARP_STAGE_BYTES = (BULK_WARP_BYTES > 32 * EPI_CHUNK * 8) ? BULK_WARP_BYTES : 32 * EPI_CHUNK * 8;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_WARP_STAGE_BYTES;  // one 32 x 16 double transpose buffer per warp (or the bulk rows)
+constexpr int SMEM_LIMIT = 232448;  // 227 KB per CTA
 template <int CTAS>
 struct Cfg {
   static constexpr int B_TILE_BYTES = PLANE_TILE_BYTES / CTAS;
   static constexpr int STAGE_BYTES = 2 * PLANE_TILE_BYTES + 2 * B_TILE_BYTES;  // A hi, A lo, B hi, B lo
-  static constexpr int STAGES = (EPI_WARPS == 8) ? (CTAS == 1 ? 3 : 4) : (CTAS == 1 ? 2 : 3);  // smem left after the epilogue staging
+  static constexpr int FIT = (SMEM_LIMIT - 1024 - 256 - EPI_STAGE_BYTES) / STAGE_BYTES;  // smem left after the epilogue staging
+  static constexpr int STAGES = FIT > 4 ? 4 : FIT;
 };
-constexpr int THREADS = 128 + 32 * EPI_WARPS;
-constexpr int EPI_COLS = BN / (EPI_WARPS / 4);                // accumulator columns owned by one epilogue warp
-constexpr int EPI_CHUNK = 16;                                 // columns transposed per step
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_CHUNK * 8;  // one 32 x 16 double transpose buffer per warp
+static_assert(Cfg<1>::STAGES >= 2 && Cfg<2>::STAGES >= 2, "operand pipeline needs two stages");
 template <int CTAS>
 constexpr int smem_bytes_of() {
   return Cfg<CTAS>::STAGES * Cfg<CTAS>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
@@ -394,6 +418,73 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
   }
 }
 
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Lean epilogue of one interior tile with bulk-async stores (see BULK_COLS above): lane = row for the whole tile.
+// stg_s: this warp's staging (BULK_NBUF row buffers, then EPI_COLS column factors); grow: this lane's packed row at
+// the warp's first column; buf: round-robin buffer index, kept across tiles.
+template <int KIND, bool PW6>
+__device__ __forceinline__ void packed_interior_bulk(const uint32_t (&racc)[EPI_COLS], uint32_t stg_s, int lane, double rowf,
+                                                     bool tf32_scaled, const double* colv, char* grow, uint32_t& buf) {
+  constexpr int BC = BULK_COLS ? BULK_COLS : 16;
+  const uint32_t colf_s = stg_s + (uint32_t)(BULK_NBUF * BULK_BUF_BYTES);
+  if (KIND == KIND_I8) {  // 1/|d_j| of the warp's 64 columns: two per lane, read back as broadcast LDS.128
+    const double2 cf = __ldg(reinterpret_cast<const double2*>(colv) + lane);
+    __syncwarp();
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(colf_s + (uint32_t)lane * 16u), "d"(cf.x), "d"(cf.y) : "memory");
+    __syncwarp();
+  }
+  const uint32_t odd = ((uint32_t)(uintptr_t)grow >> 3) & 1u;
+  const uint32_t row_s = stg_s + (uint32_t)lane * BULK_ROW_BYTES;
+#pragma unroll
+  for (int c = 0; c < EPI_COLS; c += BC) {
+    const uint32_t bs = row_s + buf * (uint32_t)BULK_BUF_BYTES;
+    // the copy that last read this buffer is done with it
+    if (BULK_NBUF <= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(BULK_NBUF > 1 ? BULK_NBUF - 1 : 0) : "memory");
+    const uint32_t st0 = bs + (odd ? 0u : 16u);
+    double carry = 0.0, first = 0.0;
+#pragma unroll
+    for (int q = 0; q < BC; q += 2) {
+      double v0, v1;
+      if (KIND == KIND_I8) {
+        double c0, c1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(colf_s + (uint32_t)((c + q) * 8)));
+        v0 = (double)(int)racc[c + q] * rowf * c0;
+        v1 = (double)(int)racc[c + q + 1] * rowf * c1;
+      } else {
+        v0 = (double)__uint_as_float(racc[c + q]);
+        v1 = (double)__uint_as_float(racc[c + q + 1]);
+        if (tf32_scaled) {
+          v0 *= rowf;
+          v1 *= rowf;
+        }
+      }
+      if (PW6) {
+        const double s0 = v0 * v0, s1 = v1 * v1;
+        v0 = s0 * s0 * s0;
+        v1 = s1 * s1 * s1;
+      }
+      if (q == 0) first = v0;
+      // even row: (v[q], v[q+1]) at 16 + 8q; odd row: (v[q-1], v[q]) at 8q (the q = 0 pair fills the lead padding)
+      const double a = odd ? carry : v0, b = odd ? v0 : v1;
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(st0 + (uint32_t)(q * 8)), "d"(a), "d"(b) : "memory");
+      carry = v1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    char* const g = grow + c * 8;
+    if (odd) {
+      *reinterpret_cast<double*>(g) = first;
+      *reinterpret_cast<double*>(g + (BC - 1) * 8) = carry;
+    }
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + (odd ? 8 : 0)), "r"(bs + 16u),
+                 "r"(odd ? (uint32_t)((BC - 2) * 8) : (uint32_t)(BC * 8))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (BULK_NBUF > 1) buf = (buf + 1 == (uint32_t)BULK_NBUF) ? 0u : buf + 1;
+  }
+}
+
 // map0 / map1: 128-row boxes (A operand of pass 0 / 1); mapb0 / mapb1: the B operand boxes (128 rows for CTAS = 1,
 // 64 rows = this CTA's half of the B tile for CTAS = 2).
 template <int KIND, int EPI, int CTAS>
@@ -574,7 +665,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     const EpiParams& E = P.E;
-    double* stg = epi_stage_all + (warp - 4) * (32 * EPI_CHUNK);
+    double* stg = epi_stage_all + (warp - 4) * (EPI_WARP_STAGE_BYTES / 8);
+    uint32_t bulk_buf = 0;
     const bool want_mirror = epi_wants_mirror<EPI>(E);
     const int pp = (int)E.p;
     const int dbg = kProfile ? P.dbg : 0;
@@ -801,7 +893,11 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           char* const wbase = reinterpret_cast<char*>(out + (R0.ro + col_base));
           const int a = pp - row_base - shift - 1;  // ro(i + 1) - ro(i) = p - i - shift - 1
           const long long pt2 = (kProfile && P.prof) ? clock64() : 0;
-          if (pw_mode == 6) packed_interior<KIND, true>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
+          if (BULK_COLS) {
+            char* const grow = wbase + ((int64_t)(lane * a - (lane * (lane - 1)) / 2) << 3);
+            if (pw_mode == 6) packed_interior_bulk<KIND, true>(racc, smem_u32(stg), lane, rowf, scale != 1.0, colv, grow, bulk_buf);
+            else packed_interior_bulk<KIND, false>(racc, smem_u32(stg), lane, rowf, scale != 1.0, colv, grow, bulk_buf);
+          } else if (pw_mode == 6) packed_interior<KIND, true>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
           else packed_interior<KIND, false>(racc, stg, lane, rowf, scale != 1.0, colv, wbase, a, dbg);
           if (kProfile && P.prof) {
             const long long pt3 = clock64();
@@ -812,6 +908,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           }
           continue;
         }
+        if (BULK_COLS) bulk_wait_read_all();  // the staging below is reused with plain stores
         // ---- fused epilogue from registers.  Each 32 x 16 block is transposed through shared
         //      memory (XOR-swizzled, conflict free) so that one store instruction writes two
         //      contiguous 128-byte runs of the packed rows instead of 32 scattered doubles.
@@ -941,6 +1038,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         if (direct) release_direct();
       }
     }
+    if (BULK_COLS) bulk_wait_read_all();  // shared memory stays valid until the copy engine has read it
     if (kProfile && P.prof && lane == 0) {
       unsigned long long* dst = P.prof + ((size_t)blockIdx.x * EPI_WARPS + (warp - 4)) * 4;
       for (int q = 0; q < 4; ++q) dst[q] = (unsigned long long)prof_acc[q];
