@@ -48,6 +48,7 @@ SIGNATURES = {
     "bixcor_covariance": (i32, [ptr, i64, i64, ptr]),
     "bixcor_cos": (i32, [ptr, i64, i64, ptr]),
     "bixcor_cor2": (i32, [ptr, i64, i64, ptr, i64, i32, ptr]),
+    "bixcor_rbh_cor": (i32, [ptr, i64, i64, ptr, i64, i32, i32, f64, ptr, ptr, ptr, i64, ptr]),
     "bixcor_cov2cor": (i32, [ptr, i64, ptr]),
     "bixcor_rbf": (i32, [ptr, i64, f64, i32, ptr]),
     "bixcor_rbf_iterate_epsilons": (i32, [ptr, i64, i32, ptr, i32, i32, ptr]),

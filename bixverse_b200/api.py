@@ -40,7 +40,7 @@ from ._lib import PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_TF32X3, 
 
 __all__ = [
     "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
-    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp", "cor_module_tom",
+    "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp", "cor_module_tom", "rs_rbh_cor",
     "rs_rbf_function", "rs_rbf_function_mat", "rs_rbf_iterate_epsilons", "rs_coremo_stability", "cor_upper_triangle_rbf", "rs_pairwise_gene_cors_mc",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
     "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "PREC_OZAKI4", "BixcorError",
@@ -120,6 +120,41 @@ def rs_cor2(x, y, spearman: bool) -> np.ndarray:
     out = np.empty((a.shape[1], b.shape[1]), dtype=np.float64, order="F")
     check(_lib.load().bixcor_cor2(_p(a), a.shape[0], a.shape[1], _p(b), b.shape[1], int(bool(spearman)), _p(out)))
     return out
+
+
+def rs_rbh_cor(module_matrices: dict, k_best: int, spearman: bool, min_similarity: float) -> dict:
+    """src/rust/src/methods/r_rbh.rs:187-272.  module_matrices: name -> (matrix features x modules, rownames, colnames)
+    (the named R matrices of the list).  Every origin is compared with every later target on their shared features;
+    returns the reference's list: origin, target, comparisons, origin_modules, target_modules, similarity."""
+    lib = _lib.load()
+    names = list(module_matrices)
+    res = {k: [] for k in ("origin", "target", "comparisons", "origin_modules", "target_modules", "similarity")}
+    for a, na in enumerate(names[:-1]):
+        xa, ra, ca = module_matrices[na]
+        xa = np.asarray(xa, dtype=np.float64)
+        for nb in names[a + 1:]:
+            xb, rb, cb = module_matrices[nb]
+            xb = np.asarray(xb, dtype=np.float64)
+            pos_b = {f: k for k, f in enumerate(rb)}
+            shared = [(k, pos_b[f]) for k, f in enumerate(ra) if f in pos_b]
+            n_hits = 0
+            if len(shared) >= 2:
+                ia, ib = (list(t) for t in zip(*shared))
+                sa, sb = _fmat(xa[ia]), _fmat(xb[ib], "y")
+                cap = sa.shape[1] * sb.shape[1]
+                oi, oj = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32)
+                sim = np.empty(cap, dtype=np.float64)
+                cnt = np.zeros(1, dtype=np.int64)
+                check(lib.bixcor_rbh_cor(_p(sa), sa.shape[0], sa.shape[1], _p(sb), sb.shape[1], int(k_best), int(bool(spearman)),
+                                         float(min_similarity), _p(oi), _p(oj), _p(sim), cap, _p(cnt)))
+                n_hits = int(cnt[0])
+                res["origin_modules"] += [ca[i] for i in oi[:n_hits]]
+                res["target_modules"] += [cb[j] for j in oj[:n_hits]]
+                res["similarity"] += sim[:n_hits].tolist()
+            res["origin"].append(na)
+            res["target"].append(nb)
+            res["comparisons"].append(n_hits)
+    return res
 
 
 def rs_cov2cor(x) -> np.ndarray:

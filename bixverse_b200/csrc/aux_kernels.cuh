@@ -246,6 +246,68 @@ mirror_upper_kernel(double* __restrict__ dense, int64_t p) {  // dense[j][i] = d
   }
 }
 
+// Reciprocal best hits on a correlation block (rs_rbh_cor, src/rust/src/methods/r_rbh.rs:187-272).  sim is the
+// column-major p x q matrix of cor2; one warp per line (a row i: stride p over j; a column j: contiguous) finds the
+// k-th largest |r| of the line (with multiplicity; NaN never counts; fewer than k values: -inf).
+__global__ void __launch_bounds__(256)
+rbh_kth_best_kernel(const double* __restrict__ sim, int64_t p, int64_t q, int k, double* __restrict__ row_thr,
+                    double* __restrict__ col_thr) {
+  const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (line >= p + q) return;
+  const bool is_row = line < p;
+  const double* base = is_row ? sim + line : sim + (line - p) * p;
+  const int64_t len = is_row ? q : p, stride = is_row ? p : 1;
+  double prev = INFINITY, thr = -INFINITY;
+  int remaining = k;
+  bool first = true;
+  while (remaining > 0) {
+    double m = -INFINITY;
+    int cnt = 0;
+    for (int64_t e = lane; e < len; e += 32) {
+      const double v = fabs(base[e * stride]);
+      if (v == v && (first || v < prev)) {
+        if (v > m) {
+          m = v;
+          cnt = 1;
+        } else if (v == m) {
+          ++cnt;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (om > m) {
+        m = om;
+        cnt = oc;
+      } else if (om == m) {
+        cnt += oc;
+      }
+    }
+    if (cnt == 0) break;  // line exhausted before the k-th value
+    if (cnt >= remaining) {
+      thr = m;
+      break;
+    }
+    remaining -= cnt;
+    prev = m;
+    first = false;
+  }
+  if (lane == 0) (is_row ? row_thr[line] : col_thr[line - p]) = thr;
+}
+// sim := |sim|; hit[i + j p] = |r_ij| is among the k best of row i AND of column j AND exceeds min_similarity
+__global__ void __launch_bounds__(256)
+rbh_mark_kernel(double* __restrict__ sim, int64_t p, int64_t q, const double* __restrict__ row_thr,
+                const double* __restrict__ col_thr, double min_similarity, unsigned char* __restrict__ hit) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p * q) return;
+  const int64_t i = e % p, j = e / p;
+  const double v = fabs(sim[e]);
+  sim[e] = v;
+  hit[e] = (v >= row_thr[i] && v >= col_thr[j] && v > min_similarity) ? 1 : 0;
+}
+
 __global__ void fill_kernel(double* __restrict__ x, int64_t n, double v) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;

@@ -1729,13 +1729,8 @@ int bixcor_cos(const double* x, int64_t n, int64_t p, double* out_pp) {
   return dense_symmetric(x, n, p, 2, 1.0, 0, out_pp);
 }
 
-int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq) {
-  RC_TRY(ensure_init());
-  RC_TRY(host_shape_check(x, n, p, out_pq));
-  RC_TRY(host_shape_check(y, n, q, out_pq));
-  Ctx* c = g_ctx[0];
-  CU_TRY(cudaSetDevice(c->device));
-  call_begin(c);
+// cor2 on the device: leaves the column-major p x q matrix cor(x_i, y_j) in c->out
+static int dev_cor2(Ctx* c, const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman) {
   RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
   RC_TRY(c->x[1].reserve(sizeof(double) * (size_t)n * q));
   RC_TRY(c->out.reserve(sizeof(double) * (size_t)p * q));
@@ -1754,11 +1749,70 @@ int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t 
   EpiParams e = make_epi(q);
   e.out = (double*)c->out.ptr;
   e.ldo = p;
-  RC_TRY(launch_gram(c, oy, nullptr, q, (const int2*)c->vec.ptr, (int)tiles.size(), EPI_DENSE, e, &ox));
+  return launch_gram(c, oy, nullptr, q, (const int2*)c->vec.ptr, (int)tiles.size(), EPI_DENSE, e, &ox);
+}
+
+int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq) {
+  RC_TRY(ensure_init());
+  RC_TRY(host_shape_check(x, n, p, out_pq));
+  RC_TRY(host_shape_check(y, n, q, out_pq));
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  RC_TRY(dev_cor2(c, x, n, p, y, q, spearman));
   RC_TRY(finish(c));
   D2HPipe pipe(c, out_pq);
   RC_TRY(pipe.push(out_pq, c->out.ptr, sizeof(double) * (size_t)p * q, nullptr));
   return pipe.finish();
+}
+
+// rs_rbh_cor for one (origin, target) pair of module matrices already restricted to their shared features
+// (src/rust/src/methods/r_rbh.rs:187-272; crate calculate_rbh_cor): |cor2| on the device, k-th best value of every
+// row and column, reciprocal hits above min_similarity compacted origin-major into the caller's arrays (0-based).
+int bixcor_rbh_cor(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int k_best, int spearman,
+                   double min_similarity, int32_t* out_origin, int32_t* out_target, double* out_sim, int64_t capacity,
+                   int64_t* n_hits) {
+  RC_TRY(ensure_init());
+  if (!n_hits) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  *n_hits = 0;
+  RC_TRY(host_shape_check(x, n, p, n_hits));
+  RC_TRY(host_shape_check(y, n, q, n_hits));
+  if (k_best < 1) return fail(BIXCOR_ERR_INVALID, "k_best must be >= 1");
+  if (capacity > 0 && (!out_origin || !out_target || !out_sim)) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  Ctx* c = g_ctx[0];
+  CU_TRY(cudaSetDevice(c->device));
+  call_begin(c);
+  RC_TRY(dev_cor2(c, x, n, p, y, q, spearman));
+  const size_t pq = (size_t)p * q;
+  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)(p + q) + pq));
+  double* thr = (double*)c->out2.ptr;
+  unsigned char* hit = (unsigned char*)(thr + p + q);
+  {
+    Timed tm(c, T_OTHER);
+    rbh_kth_best_kernel<<<(unsigned)((p + q + 7) / 8), 256, 0, c->compute>>>((const double*)c->out.ptr, p, q, k_best, thr, thr + p);
+    rbh_mark_kernel<<<(unsigned)((pq + 255) / 256), 256, 0, c->compute>>>((double*)c->out.ptr, p, q, thr, thr + p, min_similarity, hit);
+    g_launches += 2;
+  }
+  CU_TRY(cudaGetLastError());
+  std::vector<double> sim(pq);
+  std::vector<unsigned char> mask(pq);
+  CU_TRY(cudaMemcpyAsync(sim.data(), c->out.ptr, sizeof(double) * pq, cudaMemcpyDeviceToHost, c->compute));
+  CU_TRY(cudaMemcpyAsync(mask.data(), hit, pq, cudaMemcpyDeviceToHost, c->compute));
+  RC_TRY(finish(c));
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < p; ++i)
+    for (int64_t j = 0; j < q; ++j)
+      if (mask[(size_t)(i + j * p)]) {
+        if (cnt < capacity) {
+          out_origin[cnt] = (int32_t)i;
+          out_target[cnt] = (int32_t)j;
+          out_sim[cnt] = sim[(size_t)(i + j * p)];
+        }
+        ++cnt;
+      }
+  *n_hits = cnt;
+  if (cnt > capacity) return fail(BIXCOR_ERR_INVALID, "rbh: %lld hits exceed the capacity %lld", (long long)cnt, (long long)capacity);
+  return BIXCOR_OK;
 }
 
 int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp) {

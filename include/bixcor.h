@@ -139,6 +139,14 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
 int bixcor_covariance(const double* x, int64_t n, int64_t p, double* out_pp);
 int bixcor_cos(const double* x, int64_t n, int64_t p, double* out_pp);
 int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq);
+/* rs_rbh_cor (src/rust/src/methods/r_rbh.rs:187-272; crate calculate_rbh_cor) for ONE (origin, target) pair:
+ * x (n x p) and y (n x q) hold the two module matrices restricted to their n shared features (rows aligned).
+ * similarity = |cor(x_i, y_j)|; (i, j) is a hit when it is among the k_best largest of row i AND of column j and
+ * exceeds min_similarity.  Hits are written origin-major with 0-based indices; *n_hits is the number found (an
+ * error is returned when it exceeds capacity; p * q always suffices). */
+int bixcor_rbh_cor(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int k_best, int spearman,
+                   double min_similarity, int32_t* out_origin, int32_t* out_target, double* out_sim, int64_t capacity,
+                   int64_t* n_hits);
 int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp);
 
 /* RBF affinities.  `rbf_type` mirrors parse_rbf_types ("gaussian", "bump", "inverse_quadratic"):

@@ -17,7 +17,9 @@ tests and docs, and is pinned by ``tests/test_oracle.py`` against
 * base-R ``cor()`` equivalence (``inst/tinytest/test_R_rust_equality.R:5-72``)
   with numpy.corrcoef / scipy.stats as the base-R stand-in on the very matrix
   the reference test uses (R's ``set.seed(123); rnorm`` stream is reproduced in
-  ``tests/golden/make_golden.py``).
+  ``tests/golden/make_golden.py``),
+* the reciprocal-best-hit known answers of ``inst/tinytest/test_rbh.R:109-214``
+  (Pearson to 1e-7 and Spearman, on the test's own ``set.seed(42)`` matrices).
 
 PARITY UNPINNED (no reference test or golden vector exists): the Fisher-z
 z-score / p-value of ``rs_differential_cor`` (constants restated from the
@@ -57,6 +59,8 @@ __all__ = [
     "rbf_function",
     "rbf_iterate_epsilons",
     "coremo_stability",
+    "rbh_cor",
+    "rbh_cor_list",
     "shard_rows",
 ]
 
@@ -387,6 +391,59 @@ def coremo_stability(x, indices_1based, epsilon: float, rbf_type: str, spearman:
 # multi-GPU partition of the packed triangle (host logic; mirrored by
 # bixcor_shard_rows in include/bixcor.h)
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# reciprocal best hits on correlations (rs_rbh_cor,
+# src/rust/src/methods/r_rbh.rs:187-272; crate methods::rbh::calculate_rbh_cor)
+# Pinned by the known-answer test inst/tinytest/test_rbh.R:109-214 (k_best = 1,
+# Pearson 1e-7 and Spearman) on R's own set.seed(42) matrices.  Unpinned: the
+# use of |r| as the similarity (doc ":172-173": "Minimum (absolute)
+# correlations"; every KAT hit is positive), tie handling of the k-th best.
+# --------------------------------------------------------------------------
+def rbh_cor(x: np.ndarray, y: np.ndarray, k_best: int, spearman: bool, min_similarity: float = 0.0):
+    """x (features x p), y (same features x q) -> list of (i, j, |r_ij|), origin-major, for pairs that are among the
+    k_best largest of row i and of column j and exceed min_similarity."""
+    sim = np.abs(cor_two_matrices(np.asarray(x, float), np.asarray(y, float), spearman))
+    p, q = sim.shape
+
+    def kth(v):
+        v = np.sort(v[~np.isnan(v)])[::-1]
+        return v[k_best - 1] if v.size >= k_best else -np.inf
+
+    row_thr = np.array([kth(sim[i, :]) for i in range(p)])
+    col_thr = np.array([kth(sim[:, j]) for j in range(q)])
+    hits = []
+    for i in range(p):
+        for j in range(q):
+            v = sim[i, j]
+            if v >= row_thr[i] and v >= col_thr[j] and v > min_similarity:
+                hits.append((i, j, float(v)))
+    return hits
+
+
+def rbh_cor_list(module_matrices: dict, k_best: int, spearman: bool, min_similarity: float) -> dict:
+    """The list-level driver of r_rbh.rs:195-270: every origin against every later target, features intersected by
+    row name; module_matrices maps name -> (matrix, rownames, colnames)."""
+    names = list(module_matrices)
+    res = {k: [] for k in ("origin", "target", "comparisons", "origin_modules", "target_modules", "similarity")}
+    for a, na in enumerate(names[:-1]):
+        xa, ra, ca = module_matrices[na]
+        for nb in names[a + 1:]:
+            xb, rb, cb = module_matrices[nb]
+            pos_b = {f: k for k, f in enumerate(rb)}
+            shared = [(k, pos_b[f]) for k, f in enumerate(ra) if f in pos_b]
+            hits = []
+            if len(shared) >= 2:
+                ia, ib = zip(*shared)
+                hits = rbh_cor(np.asarray(xa, float)[list(ia)], np.asarray(xb, float)[list(ib)], k_best, spearman, min_similarity)
+            res["origin"].append(na)
+            res["target"].append(nb)
+            res["comparisons"].append(len(hits))
+            res["origin_modules"] += [ca[i] for i, _, _ in hits]
+            res["target_modules"] += [cb[j] for _, j, _ in hits]
+            res["similarity"] += [v for _, _, v in hits]
+    return res
+
+
 def shard_rows(p: int, shift: int, world: int, rank: int, align: int = 128) -> tuple[int, int]:
     """Contiguous block-row range [r0, r1) owned by `rank`: boundaries at
     equal-pair-count quantiles of the triangle, rounded to `align` rows."""

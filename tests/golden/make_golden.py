@@ -10,6 +10,8 @@
    normals); expected values come from numpy/scipy as the base-R `cor()`
    stand-in (R itself is not installed here).  The generator self-checks
    against the well-known first draws of set.seed(123).
+3. rbh_cor_seed42.json - the matrices and expected reciprocal best hits of
+   inst/tinytest/test_rbh.R:109-214 (set.seed(42) stream).
 """
 import json
 import os
@@ -108,6 +110,30 @@ def main():
     }
     with open(os.path.join(HERE, "r_equality_seed123.json"), "w") as f:
         json.dump(eq, f)
+    # 3. rbh_cor_seed42.json - inst/tinytest/test_rbh.R:109-146: set.seed(42); rnorm(16) 4x4, rnorm(15) 5x3, rnorm(20) 4x5
+    #    (one continued stream) and the expected reciprocal best hits typed into that test (tolerance 1e-7, :179-184).
+    g = RMersenne(42)
+    chk42 = g.rnorm(16)
+    assert np.allclose(chk42[:3], [1.37095845, -0.56469817, 0.36312841], atol=5e-9), chk42[:3]
+    rbh = {
+        "source": "inst/tinytest/test_rbh.R:109-214 (inputs via re-implemented R RNG, expected values typed in the test)",
+        "matrix_a": chk42.reshape(4, 4).T.tolist(),
+        "rownames_a": [f"gene_{i}" for i in range(1, 5)],
+        "colnames_a": [f"ic_{i}" for i in range(1, 5)],
+        "matrix_b": g.rnorm(15).reshape(3, 5).T.tolist(),
+        "rownames_b": [f"gene_{i}" for i in range(1, 6)],
+        "colnames_b": [f"ic_{i}" for i in range(1, 4)],
+        "matrix_c": g.rnorm(20).reshape(5, 4).T.tolist(),
+        "rownames_c": [f"gene_{i}" for i in range(10, 14)],
+        "colnames_c": [f"ic_{i}" for i in range(1, 6)],
+        "expected_origin_modules": ["ic_2", "ic_3", "ic_4"],
+        "expected_target_modules": ["ic_3", "ic_1", "ic_2"],
+        "expected_pearson": [0.8420369, 0.8487127, 0.9582737],
+        "expected_spearman": [1.0, 1.0, 1.0],
+        "tolerance": 1e-7,
+    }
+    with open(os.path.join(HERE, "rbh_cor_seed42.json"), "w") as f:
+        json.dump(rbh, f)
     print("golden fixtures written; set.seed(123) rnorm(3) =", chk)
 
 

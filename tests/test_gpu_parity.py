@@ -460,6 +460,40 @@ def test_covariance_cor2_cov2cor_golden(api, golden_dir):
     assert _maxerr(api.rs_cov2cor(cov), np.array(g["pearson"])) < 1e-13
 
 
+@pytest.mark.parametrize("spearman", [False, True])
+def test_rbh_cor_known_answer_and_oracle(api, golden_dir, spearman):
+    """rs_rbh_cor: the reference's own known answers (inst/tinytest/test_rbh.R:109-214) and larger seeded cases
+    against the oracle (k_best 1 / 3, thresholds, negative correlations, more than one tile per side)."""
+    import json, os
+
+    with open(os.path.join(golden_dir, "rbh_cor_seed42.json")) as f:
+        g = json.load(f)
+    mats = {
+        "origin_1": (np.array(g["matrix_a"]), g["rownames_a"], g["colnames_a"]),
+        "origin_2": (np.array(g["matrix_b"]), g["rownames_b"], g["colnames_b"]),
+        "origin_3": (np.array(g["matrix_c"]), g["rownames_c"], g["colnames_c"]),
+    }
+    res = api.rs_rbh_cor(mats, 1, spearman, 0.0)
+    assert res["origin"] == ["origin_1", "origin_1", "origin_2"] and res["target"] == ["origin_2", "origin_3", "origin_3"]
+    assert res["comparisons"] == [3, 0, 0]
+    assert res["origin_modules"] == g["expected_origin_modules"] and res["target_modules"] == g["expected_target_modules"]
+    np.testing.assert_allclose(res["similarity"], g["expected_spearman" if spearman else "expected_pearson"], atol=g["tolerance"])
+
+    rng = np.random.default_rng(77)
+    feats = [f"g{i}" for i in range(300)]
+    big = {}
+    for name, ncol, lo in (("ica", 150, 0), ("nmf", 140, 40), ("pca", 33, 100)):
+        m = rng.normal(size=(200, ncol))
+        big[name] = (m, feats[lo:lo + 200], [f"{name}_{k}" for k in range(ncol)])
+    big["nmf"][0][:160, 5] = -big["ica"][0][40:, 9]  # shared features line up: a strong NEGATIVE correlation must be a hit
+    for k_best, thr in ((1, 0.0), (3, 0.1), (2, 0.25)):
+        got = api.rs_rbh_cor(big, k_best, spearman, thr)
+        ref = o.rbh_cor_list(big, k_best, spearman, thr)
+        for key in ("origin", "target", "comparisons", "origin_modules", "target_modules"):
+            assert got[key] == ref[key], key
+        assert _maxerr(np.array(got["similarity"]), np.array(ref["similarity"])) < TOL64
+
+
 def test_siblings_larger_shapes(api):
     from bixverse_b200.synthetic import synthetic_bulk
 

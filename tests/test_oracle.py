@@ -200,3 +200,38 @@ def test_rbf_and_stability_restatement():
     red = x[1:]
     ref = 1.0 - np.exp(-((2.0 * (1.0 - np.abs(o.cor_upper_triangle(red, True, True)))) ** 2))
     assert np.allclose(res[0], ref) and len(res) == 2 and res[1].shape == ref.shape
+
+
+def _rbh_fixture(golden_dir):
+    with open(os.path.join(golden_dir, "rbh_cor_seed42.json")) as f:
+        g = json.load(f)
+    mats = {
+        "origin_1": (np.array(g["matrix_a"]), g["rownames_a"], g["colnames_a"]),
+        "origin_2": (np.array(g["matrix_b"]), g["rownames_b"], g["colnames_b"]),
+    }
+    disjoint = {"origin_1": mats["origin_1"], "origin_2": (np.array(g["matrix_c"]), g["rownames_c"], g["colnames_c"])}
+    return g, mats, disjoint
+
+
+@pytest.mark.parametrize("spearman", [False, True])
+def test_rbh_cor_known_answer(golden_dir, spearman):
+    """inst/tinytest/test_rbh.R:109-214: k_best = 1, minimum_similarity = 0, on the test's own set.seed(42) matrices."""
+    g, mats, disjoint = _rbh_fixture(golden_dir)
+    res = o.rbh_cor_list(mats, 1, spearman, 0.0)
+    assert res["origin"] == ["origin_1"] and res["target"] == ["origin_2"] and res["comparisons"] == [3]
+    assert res["origin_modules"] == g["expected_origin_modules"]
+    assert res["target_modules"] == g["expected_target_modules"]
+    np.testing.assert_allclose(res["similarity"], g["expected_spearman" if spearman else "expected_pearson"], atol=g["tolerance"])
+    none = o.rbh_cor_list(disjoint, 1, spearman, 0.0)  # no overlapping features (:196-214)
+    assert none["comparisons"] == [0] and none["similarity"] == []
+
+
+def test_rbh_cor_k_best_and_threshold():
+    rng = np.random.default_rng(5)
+    x, y = rng.normal(size=(40, 7)), rng.normal(size=(40, 9))
+    y[:, 2] = -x[:, 4] + 0.01 * rng.normal(size=40)  # strong negative hit: similarity is |r|
+    h1 = o.rbh_cor(x, y, 1, False, 0.0)
+    assert (4, 2) in [(i, j) for i, j, _ in h1] and all(v > 0 for _, _, v in h1)
+    h3 = o.rbh_cor(x, y, 3, False, 0.0)
+    assert set((i, j) for i, j, _ in h1) <= set((i, j) for i, j, _ in h3) and len(h3) > len(h1)
+    assert o.rbh_cor(x, y, 3, False, 0.9) == [h for h in h3 if h[2] > 0.9]
