@@ -56,6 +56,7 @@ SIGNATURES = {
     "bixcor_coremo_stability": (i32, [ptr, i64, i64, ptr, i32, f64, i32, i32, i32, ptr]),
     "bixcor_sparse_gram_cor": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr]),
     "bixcor_sparse_pairwise_cor": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr, ptr, i64, i32, ptr]),
+    "bixcor_sparse_pairwise_cor_cells": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr, i64, ptr, ptr, i64, i32, ptr]),
     "bixcor_dev_rank_columns": (i32, [ptr, i64, i64, ptr]),
     "bixcor_dev_cor_upper_rows": (i32, [ptr, i64, i64, i32, i32, f64, i32, i64, i64, ptr]),
     "bixcor_dev_operand_row_bytes": (i64, [i64, i32]),

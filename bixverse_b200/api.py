@@ -365,10 +365,13 @@ def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int
     return out
 
 
-def rs_pairwise_gene_cors_mc(sparse_data: dict, gene_indices_1, gene_indices_2, spearman: bool) -> np.ndarray:
+def rs_pairwise_gene_cors_mc(sparse_data: dict, gene_indices_1, gene_indices_2, spearman: bool,
+                             cells_to_keep=None) -> np.ndarray:
     """src/rust/src/meta_cell/r_mc_processing.rs:258-283.  `sparse_data` is the reference's sparse list:
     ``data``, ``indptr``, ``indices`` (0-based), ``nrow`` (cells), ``ncol`` (genes) and ``format`` ("csr"/"csc");
-    gene indices are 0-based, like the reference demands."""
+    gene indices are 0-based, like the reference demands.  With ``cells_to_keep`` (0-based cell indices) this is the
+    arithmetic of rs_pairwise_gene_cors (src/rust/src/single_cell/r_sc_processing.rs:474-499) on gene columns the
+    caller has read from ``counts_genes.bin``."""
     for k in ("data", "indptr", "indices", "nrow", "ncol", "format"):
         if k not in sparse_data:
             raise ValueError(f"sparse_data is missing '{k}'")
@@ -386,6 +389,12 @@ def rs_pairwise_gene_cors_mc(sparse_data: dict, gene_indices_1, gene_indices_2, 
     if g1.shape != g2.shape:
         raise ValueError("gene_indices_1 and gene_indices_2 need the same length")
     out = np.empty(g1.shape[0], dtype=np.float64)
+    if cells_to_keep is not None:
+        keep = np.ascontiguousarray(cells_to_keep, dtype=np.int32)
+        check(_lib.load().bixcor_sparse_pairwise_cor_cells(_p(ip), _p(ix), _p(dt), cells, genes, int(fmt == "csr"), _p(keep),
+                                                           keep.shape[0], _p(g1), _p(g2), g1.shape[0], int(bool(spearman)),
+                                                           _p(out)))
+        return out
     check(_lib.load().bixcor_sparse_pairwise_cor(_p(ip), _p(ix), _p(dt), cells, genes, int(fmt == "csr"), _p(g1), _p(g2),
                                                  g1.shape[0], int(bool(spearman)), _p(out)))
     return out

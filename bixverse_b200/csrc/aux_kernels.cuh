@@ -132,29 +132,34 @@ remove_row_kernel(const double* __restrict__ x, int64_t n, int64_t s, double* __
 __global__ void __launch_bounds__(256)
 csr_gather_genes_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const float* __restrict__ data, int64_t cells, int64_t genes,
-                        const int32_t* __restrict__ slot_of, double* __restrict__ dense, int64_t ld) {
+                        const int32_t* __restrict__ slot_of, const int32_t* __restrict__ cell_pos,
+                        double* __restrict__ dense, int64_t ld) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= cells) return;
+  const int64_t dst = cell_pos ? cell_pos[warp] : warp;  // cells_to_keep: position among the kept cells, -1 = dropped
+  if (dst < 0) return;
   const int64_t b = indptr[warp], e = indptr[warp + 1];
   for (int64_t q = b + lane; q < e; q += 32) {
     const int64_t g = indices[q];
     if (g < 0 || g >= genes) continue;
     const int s = slot_of[g];
-    if (s >= 0) dense[(int64_t)s * ld + warp] = (double)data[q];
+    if (s >= 0) dense[(int64_t)s * ld + dst] = (double)data[q];
   }
 }
 // CSC (columns = genes): one CTA per used gene (gene_of_slot[s]).
 __global__ void __launch_bounds__(256)
 csc_gather_genes_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const float* __restrict__ data, int64_t cells, const int32_t* __restrict__ gene_of_slot,
-                        double* __restrict__ dense, int64_t ld) {
+                        const int32_t* __restrict__ cell_pos, double* __restrict__ dense, int64_t ld) {
   const int64_t s = blockIdx.x;
   const int64_t g = gene_of_slot[s];
   const int64_t b = indptr[g], e = indptr[g + 1];
   for (int64_t q = b + threadIdx.x; q < e; q += blockDim.x) {
     const int64_t cidx = indices[q];
-    if (cidx >= 0 && cidx < cells) dense[s * ld + cidx] = (double)data[q];
+    if (cidx < 0 || cidx >= cells) continue;
+    const int64_t dst = cell_pos ? cell_pos[cidx] : cidx;
+    if (dst >= 0) dense[s * ld + dst] = (double)data[q];
   }
 }
 // out[k] = <Z[slot1[k]], Z[slot2[k]]> over K (unit-norm centred columns -> the correlation).  One warp per pair.

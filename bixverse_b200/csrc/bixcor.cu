@@ -1983,19 +1983,34 @@ int bixcor_coremo_stability(const double* x, int64_t n, int64_t p, const int32_t
 }
 
 // rs_pairwise_gene_cors_mc (src/rust/src/meta_cell/r_mc_processing.rs:258-283)
-int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
-                               int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
-                               int64_t n_pairs, int spearman, double* out) {
+// cells_to_keep == nullptr: every cell; else the correlation runs over the n_keep listed cells (0-based, unique)
+static int sparse_pairwise_impl(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                                int64_t genes, int is_csr, const int32_t* cells_to_keep, int64_t n_keep,
+                                const int32_t* gene_idx1, const int32_t* gene_idx2, int64_t n_pairs, int spearman,
+                                double* out) {
   RC_TRY(ensure_init());
   if (!indptr || n_pairs < 0 || (n_pairs > 0 && (!gene_idx1 || !gene_idx2 || !out)))
     return fail(BIXCOR_ERR_INVALID, "null pointer / bad pair count");
   if (cells < 2 || genes < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
   if (n_pairs == 0) return BIXCOR_OK;
-  const int64_t nptr = (is_csr ? cells : genes) + 1;
+  std::vector<int32_t> cell_pos;
+  const int64_t all_cells = cells;  // extent of the sparse arrays; `cells` below = cells the correlation runs over
+  if (cells_to_keep) {
+    if (n_keep < 2) return fail(BIXCOR_ERR_INVALID, "cells_to_keep needs at least 2 cells");
+    cell_pos.assign((size_t)all_cells, -1);
+    for (int64_t k = 0; k < n_keep; ++k) {
+      const int32_t ci = cells_to_keep[k];
+      if (ci < 0 || ci >= all_cells) return fail(BIXCOR_ERR_INVALID, "cells_to_keep[%lld] out of range (0-based)", (long long)k);
+      if (cell_pos[ci] >= 0) return fail(BIXCOR_ERR_INVALID, "cells_to_keep[%lld] is a duplicate", (long long)k);
+      cell_pos[ci] = (int32_t)k;
+    }
+    cells = n_keep;
+  }
+  const int64_t nptr = (is_csr ? all_cells : genes) + 1;
   const int64_t nnz = indptr[nptr - 1];
   if (nnz < 0 || (nnz > 0 && (!indices || !data))) return fail(BIXCOR_ERR_INVALID, "bad sparse arrays");
-  if (spearman && cells > 16384)
-    return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman pair correlations support <= 16384 cells (got %lld)", (long long)cells);
+  // Spearman beyond the 16384-cell limit of the dense rank kernel: ranks of the non-zeros only (rank_sparse_columns_kernel)
+  const bool sparse_ranks = spearman && cells > 16384;
   // dense slots for the genes that actually occur
   std::vector<int32_t> slot_of((size_t)genes, -1), gene_of_slot, s1((size_t)n_pairs), s2((size_t)n_pairs);
   for (int64_t k = 0; k < n_pairs; ++k) {
@@ -2020,9 +2035,10 @@ int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, co
   call_begin(c);
   const size_t b_ptr = sizeof(int64_t) * (size_t)nptr, b_idx = sizeof(int32_t) * (size_t)nnz,
                b_dat = sizeof(float) * (size_t)nnz, b_map = sizeof(int32_t) * (size_t)genes,
-               b_gos = sizeof(int32_t) * (size_t)u, b_pair = sizeof(int32_t) * (size_t)n_pairs;
+               b_gos = sizeof(int32_t) * (size_t)u, b_pair = sizeof(int32_t) * (size_t)n_pairs,
+               b_cpos = sizeof(int32_t) * cell_pos.size();
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + al(b_map) + al(b_gos) + 2 * al(b_pair) + 256));
+  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + al(b_map) + al(b_gos) + 2 * al(b_pair) + al(b_cpos) + 256));
   char* base = (char*)c->sparse_in.ptr;
   int64_t* d_ptr = (int64_t*)base;
   int32_t* d_idx = (int32_t*)(base + al(b_ptr));
@@ -2031,6 +2047,7 @@ int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, co
   int32_t* d_gos = (int32_t*)((char*)d_map + al(b_map));
   int32_t* d_s1 = (int32_t*)((char*)d_gos + al(b_gos));
   int32_t* d_s2 = (int32_t*)((char*)d_s1 + al(b_pair));
+  int32_t* d_cpos = cell_pos.empty() ? nullptr : (int32_t*)((char*)d_s2 + al(b_pair));
   RC_TRY(h2d(c, d_ptr, indptr, b_ptr, c->compute));
   RC_TRY(h2d(c, d_idx, indices, b_idx, c->compute));
   RC_TRY(h2d(c, d_dat, data, b_dat, c->compute));
@@ -2038,6 +2055,7 @@ int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, co
   RC_TRY(h2d(c, d_gos, gene_of_slot.data(), b_gos, c->compute));
   RC_TRY(h2d(c, d_s1, s1.data(), b_pair, c->compute));
   RC_TRY(h2d(c, d_s2, s2.data(), b_pair, c->compute));
+  if (d_cpos) RC_TRY(h2d(c, d_cpos, cell_pos.data(), b_cpos, c->compute));
   CU_TRY(cudaStreamSynchronize(c->compute));  // the index vectors above are stack/heap temporaries
   RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)u * cells));
   RC_TRY(c->out.reserve(sizeof(double) * (size_t)n_pairs));
@@ -2045,15 +2063,34 @@ int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, co
   {
     Timed tm(c, T_OTHER);
     if (is_csr)
-      csr_gather_genes_kernel<<<(unsigned)((cells * 32 + 255) / 256), 256, 0, c->compute>>>(
-          d_ptr, d_idx, d_dat, cells, genes, d_map, (double*)c->x[0].ptr, cells);
+      csr_gather_genes_kernel<<<(unsigned)((all_cells * 32 + 255) / 256), 256, 0, c->compute>>>(
+          d_ptr, d_idx, d_dat, all_cells, genes, d_map, d_cpos, (double*)c->x[0].ptr, cells);
     else
-      csc_gather_genes_kernel<<<(unsigned)u, 256, 0, c->compute>>>(d_ptr, d_idx, d_dat, cells, d_gos,
+      csc_gather_genes_kernel<<<(unsigned)u, 256, 0, c->compute>>>(d_ptr, d_idx, d_dat, all_cells, d_gos, d_cpos,
                                                                    (double*)c->x[0].ptr, cells);
     g_launches++;
   }
+  if (sparse_ranks) {
+    constexpr int kCap = 16384;
+    constexpr int kSmem = kCap * 12;
+    RC_TRY(c->vec.reserve(256));
+    CU_TRY(cudaMemsetAsync(c->vec.ptr, 0, sizeof(int), c->compute));
+    CU_TRY(cudaFuncSetAttribute(rank_sparse_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    {
+      Timed tm(c, T_COLS);
+      rank_sparse_columns_kernel<<<(unsigned)u, kSparseRankThreads, kSmem, c->compute>>>((double*)c->x[0].ptr, cells, cells, kCap,
+                                                                                        (int*)c->vec.ptr);
+      g_launches++;
+    }
+    int overflow = 0;
+    CU_TRY(cudaMemcpyAsync(&overflow, c->vec.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    CU_TRY(cudaStreamSynchronize(c->compute));
+    if (overflow)
+      return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman pair correlations over %lld cells support <= %d non-zero cells per gene",
+                  (long long)cells, kCap);
+  }
   Operand op;
-  RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, cells, u, spearman, BIXCOR_PREC_F64, 0, &op));
+  RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, cells, u, sparse_ranks ? 0 : spearman, BIXCOR_PREC_F64, 0, &op));
   {
     Timed tm(c, T_OTHER);
     pair_dot_kernel<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, c->compute>>>(op.z64, op.K, d_s1, d_s2, n_pairs,
@@ -2065,6 +2102,23 @@ int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, co
   D2HPipe pipe(c, out);
   RC_TRY(pipe.push(out, c->out.ptr, sizeof(double) * (size_t)n_pairs, nullptr));
   return pipe.finish();
+}
+
+int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                               int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
+                               int64_t n_pairs, int spearman, double* out) {
+  return sparse_pairwise_impl(indptr, indices, data, cells, genes, is_csr, nullptr, 0, gene_idx1, gene_idx2, n_pairs, spearman,
+                              out);
+}
+
+// rs_pairwise_gene_cors (src/rust/src/single_cell/r_sc_processing.rs:474-499): as above over the listed cells only
+int bixcor_sparse_pairwise_cor_cells(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                                     int64_t genes, int is_csr, const int32_t* cells_to_keep, int64_t n_keep,
+                                     const int32_t* gene_idx1, const int32_t* gene_idx2, int64_t n_pairs, int spearman,
+                                     double* out) {
+  if (!cells_to_keep) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  return sparse_pairwise_impl(indptr, indices, data, cells, genes, is_csr, cells_to_keep, n_keep, gene_idx1, gene_idx2, n_pairs,
+                              spearman, out);
 }
 
 int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,

@@ -90,6 +90,108 @@ __device__ __forceinline__ void emit_tf32(const ColumnOut& out, int64_t j, int i
   out.f32[out.plane32 + j * out.ld32 + i] = lo;
 }
 
+// Average-tie ranks of a mostly-zero column held dense (sparse single-cell genes, any number of cells): one CTA per
+// gene compacts the non-zero entries into shared memory (at most `cap`, a power of two; dynamic smem cap * 12
+// bytes), sorts them, and ranks the zeros analytically: with `neg` negative and `zc` zero entries the zeros share
+// rank neg + (zc + 1) / 2, the s-th smallest non-zero sits at full position s (negative) or s + zc (positive).
+// Ranks overwrite the column in place.  A column with more than `cap` non-zeros raises *overflow (nothing written).
+constexpr int kSparseRankThreads = 512;
+__global__ void __launch_bounds__(kSparseRankThreads)
+rank_sparse_columns_kernel(double* __restrict__ x, int64_t ldx, int64_t n, int cap, int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* idx = reinterpret_cast<uint32_t*>(key + cap);
+  __shared__ int s_cnt, s_neg, s_nan;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  double* col = x + (int64_t)blockIdx.x * ldx;
+  if (tid == 0) s_cnt = s_neg = s_nan = 0;
+  __syncthreads();
+  // ---- pass 1: compact the non-zeros (order is irrelevant, they are sorted next)
+  for (int64_t i0 = 0; i0 < n; i0 += nt) {
+    const int64_t i = i0 + tid;
+    const double v = (i < n) ? col[i] : 0.0;
+    const bool nz = (v != 0.0);  // NaN counts as non-zero here and poisons the column below
+    if (v != v) s_nan = 1;
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    const unsigned mneg = __ballot_sync(0xffffffffu, v < 0.0);
+    int base = 0;
+    if (lane == 0 && m) {
+      base = atomicAdd(&s_cnt, __popc(m));
+      if (mneg) atomicAdd(&s_neg, __popc(mneg));
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nz) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < cap) {
+        key[pos] = sortable_key(v);
+        idx[pos] = (uint32_t)i;
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_cnt, neg = s_neg;
+  if (s_nan) {  // base-R cor(): a column holding NA correlates to NA with everything
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int64_t i = tid; i < n; i += nt) col[i] = qnan;
+    return;
+  }
+  if (cnt > cap) {
+    if (tid == 0) atomicExch(overflow, 1);
+    return;
+  }
+  int npow2 = 2;
+  while (npow2 < cnt) npow2 <<= 1;
+  for (int i = cnt + tid; i < npow2; i += nt) {
+    key[i] = ~0ull;
+    idx[i] = 0xffffffffu;
+  }
+  __syncthreads();
+  const int half = npow2 >> 1;
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int t = tid; t < half; t += nt) {
+        const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+        const int l = i | jj;
+        const bool up = (i & k) == 0;
+        const uint64_t ki = key[i], kl = key[l];
+        if ((ki > kl) == up && ki != kl) {
+          key[i] = kl;
+          key[l] = ki;
+          const uint32_t ti = idx[i];
+          idx[i] = idx[l];
+          idx[l] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- zeros first (the sorted list lives in shared memory, the column can be overwritten)
+  const int64_t zc = n - cnt;
+  const double zero_rank = (double)neg + 0.5 * (double)(zc + 1);
+  for (int64_t i = tid; i < n; i += nt)
+    if (col[i] == 0.0) col[i] = zero_rank;
+  __syncthreads();
+  // ---- non-zeros: tie run [lo, hi] of equal keys by binary search, rank = mean of the full positions + 1
+  for (int s = tid; s < cnt; s += nt) {
+    const uint64_t k = key[s];
+    int a = 0, b = s;  // lower bound
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (key[mid] < k) a = mid + 1; else b = mid;
+    }
+    const int lo = a;
+    a = s;
+    b = cnt - 1;  // upper bound (last index with key == k)
+    while (a < b) {
+      const int mid = (a + b + 1) >> 1;
+      if (key[mid] > k) b = mid - 1; else a = mid;
+    }
+    const int hi = a;
+    const double shift = (s < neg) ? 0.0 : (double)zc;
+    col[idx[s]] = 0.5 * (double)(lo + hi) + 1.0 + shift;
+  }
+}
+
 // One CTA per gene.  Dynamic smem: npow2 * 12 bytes (u64 key + u32 index).
 // blockDim.x must be a power of two, a multiple of 32 and <= npow2.
 __global__ void __launch_bounds__(256)

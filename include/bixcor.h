@@ -180,10 +180,18 @@ int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const 
  * The sparse list {indptr, indices (0-based), data} is CSR with rows = cells (is_csr != 0) or CSC with
  * columns = genes (is_csr == 0).  gene_idx1/2 are 0-based (as the reference requires); out[k] is the Pearson
  * (or Spearman: average-tie ranks over ALL cells, zeros tie) correlation of the two genes of pair k over all
- * cells including the implicit zeros.  Only the genes named in the pair lists are densified on the device. */
+ * cells including the implicit zeros.  Only the genes named in the pair lists are densified on the device.
+ * Spearman over more than 16384 cells ranks the non-zero entries of a gene only (the zeros' shared rank follows
+ * analytically) and supports up to 16384 non-zero cells per gene. */
 int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                                int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
                                int64_t n_pairs, int spearman, double* out);
+/* rs_pairwise_gene_cors (src/rust/src/single_cell/r_sc_processing.rs:474-499): the same over the n_keep cells listed
+ * in cells_to_keep (0-based, unique; the Rust side keeps reading counts_genes.bin and hands over the gene columns). */
+int bixcor_sparse_pairwise_cor_cells(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
+                                     int64_t genes, int is_csr, const int32_t* cells_to_keep, int64_t n_keep,
+                                     const int32_t* gene_idx1, const int32_t* gene_idx2, int64_t n_pairs, int spearman,
+                                     double* out);
 
 /* ---- device-pointer entry points (inputs/outputs resident in HBM) ------ */
 /* All pointers are device pointers on the library's current device; work is

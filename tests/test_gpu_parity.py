@@ -587,6 +587,70 @@ def test_pairwise_gene_cors_mc(api, fmt, spearman):
         api.rs_pairwise_gene_cors_mc(sparse_list, [genes], [0], spearman)
 
 
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+@pytest.mark.parametrize("spearman", [False, True])
+def test_pairwise_gene_cors_cells_to_keep(api, fmt, spearman):
+    """rs_pairwise_gene_cors semantics: the correlation runs over the listed cells only (zeros included)."""
+    import scipy.sparse as sp
+
+    from bixverse_b200.synthetic import synthetic_sparse_cells
+
+    cells, genes = 1100, 40
+    ip, ix, d = synthetic_sparse_cells(cells, genes, 21, density=0.2)
+    rng = np.random.default_rng(8)
+    keep = rng.permutation(cells)[:613].astype(np.int32)  # unsorted on purpose
+    g1 = rng.integers(0, genes, size=120).astype(np.int32)
+    g2 = rng.integers(0, genes, size=120).astype(np.int32)
+    m = sp.csr_matrix((d, ix, ip), shape=(cells, genes))
+    sub = sp.csr_matrix(m[keep])
+    ref = (o.pairwise_gene_cors_spearman if spearman else o.pairwise_gene_cors)(
+        sub.indptr.astype(np.int64), sub.indices.astype(np.int32), sub.data, len(keep), genes, g1, g2)
+    mm = m.tocsc() if fmt == "csc" else m
+    sparse_list = {"data": mm.data, "indptr": mm.indptr, "indices": mm.indices, "nrow": cells, "ncol": genes, "format": fmt}
+    got = api.rs_pairwise_gene_cors_mc(sparse_list, g1, g2, spearman, cells_to_keep=keep)
+    ok = ~np.isnan(ref)
+    assert ok.sum() > 100 and np.abs(got[ok] - ref[ok]).max() < 1e-10
+    for bad in ([0, 0, 1], [cells, 1, 2], [5]):
+        with pytest.raises(api.BixcorError):
+            api.rs_pairwise_gene_cors_mc(sparse_list, g1, g2, spearman, cells_to_keep=bad)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_pairwise_spearman_many_cells(api, fmt):
+    """Spearman over more cells than the dense rank kernel takes: ranks of the non-zeros + analytic zero rank
+    (negative values, heavy ties and explicit zeros included) against dense rankdata."""
+    import scipy.sparse as sp
+
+    cells, genes = 40000, 24
+    rng = np.random.default_rng(31)
+    dense = np.zeros((cells, genes), dtype=np.float32)
+    for g in range(genes):
+        nnz = int(cells * rng.uniform(0.01, 0.12))
+        pos = rng.choice(cells, nnz, replace=False)
+        vals = np.round(rng.normal(0.5, 1.0, nnz), 1 if g % 2 else 3)  # ties; some values round to 0 and some are negative
+        dense[pos, g] = vals.astype(np.float32)
+    dense[:, 5] = np.abs(dense[:, 5])  # an all-non-negative gene
+    dense[:, 7] = 0.0                   # an all-zero gene: zero variance -> NaN
+    dense[:, 9] = 0.7 * dense[:, 3] + dense[:, 9] * (rng.random(cells) < 0.3)
+    m = sp.csr_matrix(dense)
+    g1, g2 = np.triu_indices(genes, 1)
+    g1, g2 = g1.astype(np.int32), g2.astype(np.int32)
+    ref = o.pairwise_gene_cors_spearman(m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data, cells, genes, g1, g2)
+    mm = m.tocsc() if fmt == "csc" else m
+    sparse_list = {"data": mm.data, "indptr": mm.indptr, "indices": mm.indices, "nrow": cells, "ncol": genes, "format": fmt}
+    got = api.rs_pairwise_gene_cors_mc(sparse_list, g1, g2, True)
+    ok = ~np.isnan(ref)
+    assert ok.sum() == len(g1) - (genes - 1) and np.isnan(got[~ok]).all()
+    assert np.abs(got[ok] - ref[ok]).max() < 1e-10
+    # more than 16384 non-zero cells in one gene: reported, not silently wrong
+    dense[:20000, 2] = 1.5
+    m2 = sp.csr_matrix(dense)
+    sl2 = {"data": m2.data, "indptr": m2.indptr, "indices": m2.indices, "nrow": cells, "ncol": genes, "format": "csr"}
+    with pytest.raises(api.BixcorError):
+        api.rs_pairwise_gene_cors_mc(sl2, g1, g2, True)
+    assert np.isfinite(api.rs_pairwise_gene_cors_mc(sl2, g1[:5], g2[:5], False)).all()  # Pearson has no such limit
+
+
 # ----------------------------------------------------------------------------- FP64-class Gram on the int8 tensor cores (Ozaki slices)
 @pytest.mark.parametrize("n,p", [(12, 14), (200, 2000), (57, 129), (1000, 257), (1500, 300)])
 @pytest.mark.parametrize("spearman", [False, True])
