@@ -400,6 +400,30 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
       __syncwarp();
       continue;
     }
+    if (kProfile && dbg == 9) {  // profiling: upper bound of a 128-bit phase B (LDS.128 + STG.128, addresses forced to
+                                 // 16-byte alignment, so the VALUES LAND IN THE WRONG PLACE for odd rows: timing only)
+      const int r4 = lane >> 3, u = lane & 7;
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const int m = 4 * k4 + r4;
+        double v0, v1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1)
+                     : "r"(stg_s + (uint32_t)(m * 128) + ((uint32_t)(u ^ (m & 7)) << 4)));
+        if (KIND == KIND_I8) {
+          v0 *= cf;
+          v1 *= cf;
+        }
+        if (PW6) {
+          const double s0 = v0 * v0, s1 = v1 * v1;
+          v0 = s0 * s0 * s0;
+          v1 = s1 * s1 * s1;
+        }
+        const uint64_t ga = ((uint64_t)(wbase + ((uint32_t)(m * a - (m * (m - 1)) / 2 + 2 * u) << 3) + (uint32_t)(c * 8))) & ~15ull;
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ga), "d"(v0), "d"(v1) : "memory");
+      }
+      __syncwarp();
+      continue;
+    }
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {  // phase B (lane = 2 rows x 16 columns): two 128-byte runs per store
       double v = *reinterpret_cast<const double*>(sb + ld_off[k2 & 3] + k2 * (2 * EPI_CHUNK * 8));
