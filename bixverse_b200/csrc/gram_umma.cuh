@@ -52,6 +52,14 @@ constexpr bool kFragEpilogue = true;
 #else
 constexpr bool kFragEpilogue = false;
 #endif
+// int8 kind with N = 256 MMAs (-DBIXCOR_UMMA_I8_WIDE=1): the B operand of one instruction is the hi plane AND the lo
+// plane of the column genes (they are adjacent in shared memory), so a K step takes two MMAs (h x [h|l], l x [h|l])
+// instead of four; every A plane is read from shared memory once instead of twice (-33 % operand reads per CTA of a
+// pair), at the price of a fourth accumulator (hl and lh no longer share one): all 512 TMEM columns.
+#ifndef BIXCOR_UMMA_I8_WIDE
+#define BIXCOR_UMMA_I8_WIDE 0
+#endif
+constexpr bool kI8Wide = BIXCOR_UMMA_I8_WIDE != 0;
 #ifdef BIXCOR_UMMA_PROFILE
 constexpr bool kProfile = true;
 #else
@@ -314,12 +322,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// instruction descriptor: dense, K-major A and B, M = 128, N = 128
-template <int KIND, int CTAS = 1>
+// instruction descriptor: dense, K-major A and B, M = 128, N = 128 (256 for the wide int8 form)
+template <int KIND, int CTAS = 1, int N = BN>
 __host__ __device__ constexpr uint32_t make_idesc() {
   return (KIND == KIND_TF32 ? (1u << 4) | (2u << 7) | (2u << 10)    // D = F32, A = B = TF32
                             : (2u << 4) | (1u << 7) | (1u << 10))   // D = S32, A = B = signed int8
-         | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);  // M = 256 across the CTA pair
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);  // M = 256 across the CTA pair
 }
 
 template <int KIND>
@@ -336,7 +344,7 @@ struct KindTraits<KIND_TF32> {
 };
 template <>
 struct KindTraits<KIND_I8> {
-  static constexpr int NACC = 3;  // hh, hl+lh, ll (exact int32)
+  static constexpr int NACC = kI8Wide ? 4 : 3;  // hh, hl+lh, ll (exact int32); wide form: hh, hl, lh, ll
   static constexpr int ACC_STAGES = 1;
   static constexpr int CHUNK_KB = 1 << 30;  // integer accumulation is exact: one chunk = whole K
 };
@@ -619,6 +627,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     // ============================ MMA issuer (leader CTA of a pair only) ===
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc<KIND, CTAS>();
+      constexpr uint32_t idesc_wide = make_idesc<KIND, CTAS, 2 * BN>();
       int stage = 0, acc_stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = unit0; t < P.ntiles; t += unit_stride) {
@@ -650,6 +659,9 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                   tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
                   tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
                   tc_mma<KIND, CTAS>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
+                } else if (kI8Wide) {  // B = [hi plane | lo plane] of the column genes in one N = 256 operand
+                  tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB0 + ko, idesc_wide, first);           // h * [h | l]
+                  tc_mma<KIND, CTAS>(acc0 + 2 * BN, dA1 + ko, dB0 + ko, idesc_wide, first);  // l * [h | l]
                 } else {
                   tc_mma<KIND, CTAS>(acc0 + 0 * BN, dA0 + ko, dB0 + ko, idesc, first);  // h*h
                   tc_mma<KIND, CTAS>(acc0 + 1 * BN, dA0 + ko, dB1 + ko, idesc, first);  // h*l
@@ -686,6 +698,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     static_assert(EPI_CHUNK == 16, "the direct path loads 16 accumulator columns per step");
     const int ew = (warp - 4) & 3;
     const int ch = (warp - 4) >> 2;
+    // TMEM columns (inside an accumulator stage) of this warp's hh / hl / lh / ll sums.  Three accumulators: hl and
+    // lh share one.  Wide form: the N = 256 result of h x [h|l] sits in columns [0, 256), l x [h|l] in [256, 512); a
+    // CTA pair splits B by column halves, so its result reads [hh(0:64) | hl(0:64) | hh(64:128) | hl(64:128)].
+    static_assert(!kI8Wide || EPI_COLS == 64, "wide int8 column mapping assumes two column halves");
+    const uint32_t o_hh = (KIND == KIND_I8 && kI8Wide && CTAS == 2) ? (uint32_t)(ch * 128) : (uint32_t)(ch * EPI_COLS);
+    const uint32_t o_hl = o_hh + ((KIND == KIND_I8 && kI8Wide) ? (CTAS == 2 ? 64u : (uint32_t)BN) : (uint32_t)BN);
+    const uint32_t o_lh = o_hh + 2u * BN;  // wide form only
+    const uint32_t o_ll = (KIND == KIND_I8 && kI8Wide) ? o_hl + 2u * BN : o_hh + 2u * BN;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     const EpiParams& E = P.E;
@@ -736,7 +756,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           for (int kb0 = 0; kb0 < kb_n; kb0 += T::CHUNK_KB) {
             mbar_wait(tfull_bar(acc_stage), acc_phase);
             tc_fence_after();
-            const uint32_t tcol = (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
+            const uint32_t tcol = (uint32_t)(acc_stage * T::NACC * BN);
             uint32_t dep = 0;
 #pragma unroll
             for (int hg = 0; hg < 4; ++hg) {
@@ -744,9 +764,15 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               const uint32_t ta = tmem_base + ((uint32_t)(ew * 32 + h * 16) << 16) + tcol + (uint32_t)(g * 32) + dep;
               if (KIND == KIND_I8) {
                 uint32_t r0[16], r1[16], r2[16];
-                tmem_ld_16x256b_x4(ta, r0);
-                tmem_ld_16x256b_x4(ta + BN, r1);
-                tmem_ld_16x256b_x4(ta + 2 * BN, r2);
+                tmem_ld_16x256b_x4(ta + o_hh, r0);
+                tmem_ld_16x256b_x4(ta + o_hl, r1);
+                if (kI8Wide) {
+                  tmem_ld_16x256b_x4(ta + o_lh, r2);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) r1[q] += r2[q];
+                }
+                tmem_ld_16x256b_x4(ta + o_ll, r2);
                 tmem_ld_wait();
                 uint32_t any = 0;
 #pragma unroll
@@ -757,7 +783,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 dep = any & (uint32_t)P.zero;  // (scheduling fence, see the generic drain below)
               } else {
                 uint32_t r0[16];
-                tmem_ld_16x256b_x4(ta, r0);
+                tmem_ld_16x256b_x4(ta + o_hh, r0);
                 tmem_ld_wait();
                 uint32_t any = 0;
                 if (kb0 == 0) {
@@ -839,7 +865,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         if (direct) {
           mbar_wait(tfull_bar(acc_stage), acc_phase);
           tc_fence_after();
-          tacc_direct = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
+          tacc_direct = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
         } else {
           // ---- drain: TMEM -> registers, chunk by chunk (FP32 round-to-nearest / exact int32 sums)
           const int chunk_kb = (kProfile && dbg == 8) ? (1 << 30) : T::CHUNK_KB;
@@ -847,8 +873,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             mbar_wait(tfull_bar(acc_stage), acc_phase);
             if (kProfile && P.prof && kb0 == 0) pt1 = clock64();
             tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) +
-                                  (uint32_t)(acc_stage * T::NACC * BN + ch * EPI_COLS);
+            const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
             if (KIND == KIND_I8) {
               // `dep` is always 0 (P.zero is a runtime 0): it chains each batch of loads to the previous
               // batch's sums (all 16 of them, or ptxas only hurries the one it needs), otherwise ptxas hoists all 12 tcgen05.ld (192 registers) and spills.
@@ -856,9 +881,15 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
               for (int c = 0; c < EPI_COLS; c += 16) {
                 uint32_t r0[16], r1[16], r2[16];
-                tmem_ld16(tacc + c + dep, r0);
-                tmem_ld16(tacc + BN + c + dep, r1);
-                tmem_ld16(tacc + 2 * BN + c + dep, r2);
+                tmem_ld16(tacc + o_hl + c + dep, r1);
+                if (kI8Wide) {  // hl + lh first, so that only three batches are ever live
+                  tmem_ld16(tacc + o_lh + c + dep, r2);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) r1[q] += r2[q];
+                }
+                tmem_ld16(tacc + o_hh + c + dep, r0);
+                tmem_ld16(tacc + o_ll + c + dep, r2);
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 16; ++q)  // S = 256*hh + 16*(hl+lh) + ll, exact in int32 for n <= 1860
@@ -872,7 +903,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
               for (int c = 0; c < EPI_COLS; c += 16) {
                 uint32_t r0[16];
-                tmem_ld16(tacc + c, r0);
+                tmem_ld16(tacc + o_hh + c, r0);
                 tmem_ld_wait();
                 if (kb0 == 0) {
 #pragma unroll
@@ -960,9 +991,15 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           double vals[EPI_CHUNK];
           if (DIRECT) {  // (KIND_I8) straight from TMEM
             uint32_t r0[16], r1[16], r2[16];
-            tmem_ld16(tacc_direct + c, r0);
-            tmem_ld16(tacc_direct + BN + c, r1);
-            tmem_ld16(tacc_direct + 2 * BN + c, r2);
+            tmem_ld16(tacc_direct + o_hl + c, r1);
+            if (kI8Wide) {
+              tmem_ld16(tacc_direct + o_lh + c, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) r1[q] += r2[q];
+            }
+            tmem_ld16(tacc_direct + o_hh + c, r0);
+            tmem_ld16(tacc_direct + o_ll + c, r2);
             tmem_ld_wait();
             if (OZAKI) {
 #pragma unroll
