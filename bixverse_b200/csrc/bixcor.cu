@@ -247,9 +247,13 @@ static void timing_collect(Ctx* c) {
 // pairs != 0: entries are CTA-pair super-tiles of the 2-CTA tcgen05 kernels, (first block row, block col) with the
 // second block row = first + 1 and umma::TILE_SECOND_INVALID set on the column when that row holds nothing to
 // compute (outside [row_begin,row_end) or entirely below the diagonal).
+// swap (packed correlation on the tcgen05 kernels, lean-eligible epilogue): interior tiles - strictly above the diagonal
+// and fully inside the matrix - are emitted transposed (umma::TILE_SWAPPED: one block row x one / two block columns),
+// the diagonal and ragged-edge tiles in the plain geometry.
 static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int upper_only, int band, int pairs,
-                     TileList** out) {
-  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs ? 1 : 0), band);
+                     TileList** out, int swap = 0) {
+  if (!upper_only) swap = 0;
+  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs ? 1 : 0) + (swap ? 4 : 0), band);
   auto it = c->tile_cache.find(key);
   if (it != c->tile_cache.end()) {
     *out = &it->second;
@@ -269,6 +273,21 @@ static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int 
     tl.group_tile.push_back((int)tiles.size());
     tl.group_row.push_back(std::max<int64_t>(row_begin, (int64_t)bb * kTile));
     const int j0 = upper_only ? bb : 0;
+    if (swap) {
+      const int nfull = (int)(p / kTile);  // block columns [0, nfull) are complete
+      for (int bi = bb; bi < be; ++bi) {
+        // plain geometry: the diagonal tile and, where the last block column is ragged, that column
+        tiles.push_back(make_int2(bi, pairs ? (bi | umma::TILE_SECOND_INVALID) : bi));
+        if (nfull < nb && bi < nb - 1) tiles.push_back(make_int2(bi, pairs ? ((nb - 1) | umma::TILE_SECOND_INVALID) : nb - 1));
+        // transposed geometry: block columns bi + 1 .. nfull - 1, two per CTA pair
+        for (int bj = bi + 1; bj < nfull; bj += pairs ? 2 : 1) {
+          int y = bj | umma::TILE_SWAPPED;
+          if (pairs && bj + 1 >= nfull) y |= umma::TILE_SECOND_INVALID;
+          tiles.push_back(make_int2(bi, y));
+        }
+      }
+      continue;
+    }
     for (int bj = j0; bj < nb; ++bj) {
       if (!pairs) {
         for (int bi = bb; bi < be; ++bi)
@@ -502,6 +521,12 @@ static void set_beta(EpiParams& e, double beta, int keep_sign) {
   if (beta > 1.0 && beta <= 64.0 && beta == std::floor(beta)) e.beta_int = (int)beta;
 }
 
+// Transposed interior tiles need the lean epilogue (identity or ^6, unsigned, no RBF) and a tcgen05 kind.
+static int swap_tiles(int precision, const EpiParams& e) {
+  if (!umma::kSwapInterior || (precision != BIXCOR_PREC_TF32X3 && precision != BIXCOR_PREC_I8EXACT)) return 0;
+  return (!e.rbf_mode && !e.keep_sign && (e.beta == 1.0 || e.beta_int == 6)) ? 1 : 0;
+}
+
 // FP64-class Gram on the int8 tensor cores.  G (p x p f64, ctx->ozg) accumulates the digit-pair Grams of the
 // six (group a, group b) combinations with s + t <= 5; each pass is the exact int8 kernel with EPI_ACCUM and the
 // weight 128^-(2a + 2b + 4); a finisher applies the row scales and the requested epilogue for rows [row0,row1).
@@ -721,8 +746,6 @@ struct RbfSpec {
 static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift, double beta, int64_t row_begin,
                                  int64_t row_end, double* d_out, D2HPipe* pipe, double* h_out,
                                  const RbfSpec* rbf = nullptr) {
-  TileList* tl;
-  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(op.precision, EPI_PACKED), &tl));
   EpiParams e = make_epi(p);
   e.out = d_out;
   e.out_base = packed_row_offset(row_begin, p, shift);
@@ -734,6 +757,8 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
     e.rbf_from_cor = rbf->from_cor;
     e.rbf_complement = rbf->complement;
   }
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(op.precision, EPI_PACKED), &tl, swap_tiles(op.precision, e)));
   if (!pipe)  // results stay in HBM: one launch over all tiles (no per-band tail)
     return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_PACKED, e, nullptr, row_begin, row_end);
   const int ngroups = (int)tl->group_tile.size() - 1;
@@ -777,8 +802,6 @@ static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double
   Operand a, b;
   RC_TRY(prepare_operand(c, d_xa, na, p, spearman, precision, 0, &a));
   RC_TRY(prepare_operand(c, d_xb, nb, p, spearman, precision, 1, &b));
-  TileList* tl;
-  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(precision, EPI_PACKED), &tl));
   const double cf = spearman ? g_fieller : 1.0;
   const double inv_se = 1.0 / std::sqrt(cf / (double)(na - 3) + cf / (double)(nb - 3));
   // Two packed Grams through the lean epilogue, then the Fisher-z step as a full-occupancy streaming kernel
@@ -788,6 +811,8 @@ static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double
   ea.shift = eb.shift = 1;
   ea.out = d_ra;
   eb.out = d_rb;
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(precision, EPI_PACKED), &tl, swap_tiles(precision, ea)));
   const int ngroups = pipe ? (int)tl->group_tile.size() - 1 : 1;
   for (int g = 0; g < ngroups; ++g) {
     const int t0 = pipe ? tl->group_tile[g] : 0, t1 = pipe ? tl->group_tile[g + 1] : tl->ntiles;

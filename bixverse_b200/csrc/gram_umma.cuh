@@ -116,7 +116,21 @@ template <int CTAS>
 constexpr int smem_bytes_of() {
   return Cfg<CTAS>::STAGES * Cfg<CTAS>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 }
-constexpr int TILE_SECOND_INVALID = 1 << 30;  // CTAS = 2: flag on tile.y, the pair's second block row holds nothing
+constexpr int TILE_SECOND_INVALID = 1 << 30;  // CTAS = 2: flag on tile.y, the pair's second tile holds nothing
+// Flag on tile.y (packed correlation, interior tiles): the tile is computed TRANSPOSED - the column genes are the M
+// operand (TMEM lanes), the row genes the N operand (TMEM columns).  A warp then holds, for one output row, 32
+// consecutive columns in its 32 lanes and writes 256 contiguous bytes per store straight from registers: no
+// shared-memory transpose at all.  A CTA pair covers one block row x TWO consecutive block columns (tile.y, tile.y + 1).
+constexpr int TILE_SWAPPED = 1 << 29;
+// Compile-time option (-DBIXCOR_UMMA_SWAP=1); the default keeps interior tiles untransposed with the shared-memory
+// transpose of packed_interior.  Measured (profiles/umma_probe_r01.txt, run 36): correct and bit-identical on the int8
+// path, but no faster (0.834 vs 0.814 ms) - the epilogue is not limited by its shared-memory traffic or LSU
+// instruction count.  Only one of the two lean paths is compiled so that the kernel stays within its registers.
+#ifndef BIXCOR_UMMA_SWAP
+#define BIXCOR_UMMA_SWAP 0
+#endif
+constexpr bool kSwapInterior = BIXCOR_UMMA_SWAP != 0;
+constexpr int TILE_FLAGS = TILE_SECOND_INVALID | TILE_SWAPPED;
 
 struct Params {
   int ntiles;
@@ -450,6 +464,44 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
   }
 }
 
+// Lean epilogue of one transposed (TILE_SWAPPED) interior tile for one epilogue warp: lane = output column, racc[q] =
+// output row rb + q.  rowv: 1/|d| of rows rb .. rb + EPI_COLS (KIND_I8), read as warp-uniform 16-byte loads; colf: the
+// lane's column factor; gp: the lane's element of row rb; a = packed length step ro(rb + 1) - ro(rb).
+template <int KIND, bool PW6>
+__device__ __forceinline__ void packed_swapped(const uint32_t (&racc)[EPI_COLS], double colf, double scale, bool scaled,
+                                               const double* rowv, char* gp, int a) {
+  uint32_t off = 0;  // byte offset of row rb + q relative to row rb (warp uniform, < 2^32: 64 rows of at most 2^24 columns)
+#pragma unroll
+  for (int q = 0; q < EPI_COLS; q += 2) {
+    double v0, v1;
+    uint32_t x0 = racc[q], x1 = racc[q + 1];
+    asm volatile("" : "+r"(x0), "+r"(x1));  // ordered against the offset chain below: conversions are not hoisted
+    if (KIND == KIND_I8) {
+      const double2 rf = __ldg(reinterpret_cast<const double2*>(rowv) + (q >> 1));
+      v0 = (double)(int)x0 * (scale * rf.x) * colf;  // same association as the untransposed paths: bit-identical
+      v1 = (double)(int)x1 * (scale * rf.y) * colf;
+    } else {
+      v0 = (double)__uint_as_float(x0);
+      v1 = (double)__uint_as_float(x1);
+      if (scaled) {
+        v0 *= scale;
+        v1 *= scale;
+      }
+    }
+    if (PW6) {
+      const double s0 = v0 * v0, s1 = v1 * v1;
+      v0 = s0 * s0 * s0;
+      v1 = s1 * s1 * s1;
+    }
+    *reinterpret_cast<double*>(gp + off) = v0;
+    off += (uint32_t)(a - q) << 3;
+    asm volatile("" : "+r"(off));  // keep the offsets a running sum: ptxas otherwise precomputes all 64 of them
+    *reinterpret_cast<double*>(gp + off) = v1;
+    off += (uint32_t)(a - q - 1) << 3;
+    asm volatile("" : "+r"(off));
+  }
+}
+
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // Lean epilogue of one interior tile with bulk-async stores (see BULK_COLS above): lane = row for the whole tile.
@@ -584,11 +636,11 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit0; t < P.ntiles; t += unit_stride) {
-        int2 tile = P.tiles[t];
-        if (CTAS == 2) {
-          tile.x += (int)cta_rank;  // this CTA's block row of the pair
-          tile.y &= ~TILE_SECOND_INVALID;
-        }
+        const int2 tile = P.tiles[t];
+        const int ty = tile.y & ~TILE_FLAGS;
+        // M operand rows (this CTA's 128) and N operand rows (the whole tile, or this CTA's half of it)
+        const int a_row = ((tile.y & TILE_SWAPPED) ? ty + (int)cta_rank : tile.x + (int)cta_rank) * BM;
+        const int b_row = ((tile.y & TILE_SWAPPED) ? tile.x : ty) * BN + (CTAS == 2 ? (int)cta_rank * (BN / 2) : 0);
         for (int pass = 0; pass < P.npass; ++pass) {
           const CUtensorMap* map = pass ? &map1 : &map0;
           const CUtensorMap* mapb = pass ? &mapb1 : &mapb0;
@@ -601,19 +653,18 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               // the leader's full barrier counts the bytes of both CTAs; B rows: this CTA's half of the tile
               const uint32_t fb = mapa_rank(full_bar(stage), 0);
               mbar_expect_tx_cluster(fb, STAGE_BYTES);
-              const int brow = tile.y * BN + (int)cta_rank * (BN / 2);
-              tma_load_3d_pair(s0 + 0 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0, tile.x * BM);
-              tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0 + 1, tile.x * BM);
-              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0, brow);
-              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0 + 1, brow);
+              tma_load_3d_pair(s0 + 0 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0, a_row);
+              tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0 + 1, a_row);
+              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0, b_row);
+              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0 + 1, b_row);
             } else if (kProfile && P.dbg == 6) {  // profiling: no operand traffic at all
               mbar_arrive(full_bar(stage));
             } else {
               mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-              tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, P.plane_a0, tile.x * BM);
-              tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, P.plane_a0 + 1, tile.x * BM);
-              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, mapb, full_bar(stage), kb * kelems, P.plane_b0, tile.y * BN);
-              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, full_bar(stage), kb * kelems, P.plane_b0 + 1, tile.y * BN);
+              tma_load_3d(s0 + 0 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, P.plane_a0, a_row);
+              tma_load_3d(s0 + 1 * PLANE_TILE_BYTES, map, full_bar(stage), kb * kelems, P.plane_a0 + 1, a_row);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES, mapb, full_bar(stage), kb * kelems, P.plane_b0, b_row);
+              tma_load_3d(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, full_bar(stage), kb * kelems, P.plane_b0 + 1, b_row);
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -731,19 +782,17 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     };
     for (int t = unit0; t < P.ntiles; t += unit_stride) {
       int2 tile = P.tiles[t];
-      bool tile_valid = true;
-      if (CTAS == 2) {
-        tile_valid = !(cta_rank == 1 && (tile.y & TILE_SECOND_INVALID));
-        tile.x += (int)cta_rank;
-        tile.y &= ~TILE_SECOND_INVALID;
-      }
+      const bool tile_valid = !(CTAS == 2 && cta_rank == 1 && (tile.y & TILE_SECOND_INVALID));
+      const bool swapped = kSwapInterior && (EPI == EPI_PACKED) && (tile.y & TILE_SWAPPED);
+      tile.y &= ~TILE_FLAGS;
+      if (CTAS == 2) (swapped ? tile.y : tile.x) += (int)cta_rank;  // this CTA's block column / block row of the pair
       const int row_base = tile.x * BM + ew * 32;
       const int i = row_base + lane;
       const int col_base = tile.y * BN + ch * EPI_COLS;
       for (int pass = 0; pass < P.npass; ++pass) {
         // Interior tiles of the packed correlation (97% of the tiles at p = 20000) lie strictly above the
         // diagonal and fully inside the matrix: nothing is predicated and they take the lean path below.
-        const bool interior = tile_valid && (EPI == EPI_PACKED) && tile.x < tile.y && tile.y * BN + BN <= pp && pw_mode != 0 && !keep_sign && (dbg == 0 || dbg >= 3);
+        const bool interior = !kSwapInterior && tile_valid && (EPI == EPI_PACKED) && tile.x < tile.y && tile.y * BN + BN <= pp && pw_mode != 0 && !keep_sign && (dbg == 0 || dbg >= 3);
         // DIRECT kernels keep the accumulators of the few non-interior tiles in TMEM and finish them chunk
         // by chunk (the MMA warp waits a little longer on 3% of the tiles); in exchange the 64-register
         // drain array only lives on the lean path and the kernel stays free of local-memory spills.
@@ -857,7 +906,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           }
           continue;
         }
-        const bool direct = DIRECT && !interior;
+        const bool direct = DIRECT && !interior && !(swapped && tile_valid);
         uint32_t racc[EPI_COLS];
         uint32_t tacc_direct = 0;
         const long long pt0 = (kProfile && P.prof) ? clock64() : 0;
@@ -935,6 +984,19 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         };
         if (dbg == 1 || !tile_valid) {  // (a pair's second block row that holds nothing: protocol only)
           if (direct) release_direct();
+          continue;
+        }
+        // ---- transposed interior tile: lane = output column, register = output row; coalesced stores from registers
+        if (swapped) {
+          const int rb = tile.x * BN + ch * EPI_COLS;      // first output row of this warp (TMEM columns = row genes)
+          const int cb = tile.y * BM + ew * 32 + lane;     // this lane's output column (TMEM lanes = column genes)
+          const EpiRow R0 = epi_row<EPI>(E, rb);           // warp uniform
+          const double colf = (KIND == KIND_I8) ? P.inv_norm[pass][cb] : 1.0;
+          const double* rowv = (KIND == KIND_I8) ? P.inv_norm[pass] + rb : nullptr;
+          char* const gp = reinterpret_cast<char*>(out + (R0.ro + cb));
+          const int a = pp - rb - shift - 1;  // ro(i + 1) - ro(i) = p - i - shift - 1
+          if (pw_mode == 6) packed_swapped<KIND, true>(racc, colf, scale, scale != 1.0, rowv, gp, a);
+          else packed_swapped<KIND, false>(racc, colf, scale, scale != 1.0, rowv, gp, a);
           continue;
         }
         // ---- lean path: row-side factors are applied with lane = row, column-side factors and the power
