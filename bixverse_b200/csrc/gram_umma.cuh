@@ -400,7 +400,7 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
 #pragma unroll
     for (int q = 0; q < EPI_CHUNK; q += 2) {  // phase A (lane = row)
       double v0, v1;
-      if (kProfile && KIND == KIND_I8 && dbg == 7) {  // profiling: no FP64 instruction at all (values are garbage)
+      if (kProfile && KIND == KIND_I8 && (dbg == 7 || dbg == 10)) {  // profiling: no FP64 instruction at all (values are garbage)
         v0 = __hiloint2double(0x43300000, (int)racc[c + q]);
         v1 = __hiloint2double(0x43300000, (int)racc[c + q + 1]);
       } else if (KIND == KIND_I8) {
@@ -449,12 +449,12 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {  // phase B (lane = 2 rows x 16 columns): two 128-byte runs per store
       double v = *reinterpret_cast<const double*>(sb + ld_off[k2 & 3] + k2 * (2 * EPI_CHUNK * 8));
-      if (KIND == KIND_I8 && !(kProfile && dbg == 7)) v *= cf;
-      if (PW6 && !(kProfile && dbg == 7)) {
+      if (KIND == KIND_I8 && !(kProfile && (dbg == 7 || dbg == 10))) v *= cf;
+      if (PW6 && !(kProfile && (dbg == 7 || dbg == 10))) {
         const double sq = v * v;
         v = sq * sq * sq;
       }
-      if (kProfile && dbg == 4) {  // profiling: everything but the global store
+      if (kProfile && (dbg == 4 || dbg == 10)) {  // profiling: everything but the global store (10: and no FP64)
         asm volatile("" ::"d"(v));
         continue;
       }
