@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("BIXCOR_LIB") or os.path.join(_HERE, "libbixcor.so")
 
 OK = 0
 ERR_NO_GPU, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
-PREC_F64, PREC_TF32X3, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4 = 0, 1, 2, 3, 4
+PREC_F64, PREC_TF32X3, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_F16X3 = 0, 1, 2, 3, 4, 5
 TOM_V1, TOM_V2 = 1, 2
 RBF_GAUSSIAN, RBF_BUMP, RBF_INVERSE_QUADRATIC = 1, 2, 3
 

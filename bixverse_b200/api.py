@@ -36,14 +36,14 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from ._lib import PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_TF32X3, TOM_V1, TOM_V2, BixcorError, check
+from ._lib import PREC_F16X3, PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_TF32X3, TOM_V1, TOM_V2, BixcorError, check
 
 __all__ = [
     "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
     "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp", "cor_module_tom", "rs_rbh_cor",
     "rs_rbf_function", "rs_rbf_function_mat", "rs_rbf_iterate_epsilons", "rs_coremo_stability", "cor_upper_triangle_rbf", "rs_pairwise_gene_cors_mc",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
-    "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "PREC_OZAKI4", "BixcorError",
+    "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "PREC_OZAKI4", "PREC_F16X3", "BixcorError",
 ]
 
 

@@ -323,7 +323,7 @@ struct Operand {
   int64_t p = 0;
   const double* z64 = nullptr;  // F64: p x K
   const int8_t* i8 = nullptr;   // I8EXACT: 2 planes (h, l) p x K
-  const float* f32 = nullptr;   // TF32X3: 2 planes p x K
+  const float* f32 = nullptr;   // TF32X3: 2 planes p x K (F16X3: the same slot holds 2 binary16 planes)
   const double* inv_norm = nullptr;
   const int8_t* oz = nullptr;        // OZAKI: OZ_SLICES digit planes per row, p x OZ_SLICES x ozK
   const double* oz_scale = nullptr;  // OZAKI: power-of-two row scales
@@ -344,8 +344,12 @@ static int umma_pairs(int precision, int epi) {
 }
 
 static int k_padding(int precision) {
+  if (precision == BIXCOR_PREC_F16X3) return 64;
   return (precision == BIXCOR_PREC_F64 || is_ozaki(precision)) ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
 }
+static bool is_split_float(int precision) { return precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_F16X3; }
+// precisions whose operand is ONE record per gene that ranks can exchange (F64, 3xTF32, int8 exact, 3xF16)
+static bool exchangeable(int precision) { return (precision >= 0 && precision <= 2) || precision == BIXCOR_PREC_F16X3; }
 
 // Slice an f64 operand (rows x K, ld = ldz) into the Ozaki digit planes of ctx slot `slot`.
 static int ozaki_slice(Ctx* c, const double* d_z, int64_t ldz, int64_t k, int64_t rows, int slot, Operand* op) {
@@ -367,7 +371,7 @@ static int ozaki_slice(Ctx* c, const double* d_z, int64_t ldz, int64_t k, int64_
 }
 
 static int check_precision(int precision, int spearman, int64_t n) {
-  if (precision == BIXCOR_PREC_F64 || precision == BIXCOR_PREC_TF32X3 || is_ozaki(precision)) return BIXCOR_OK;
+  if (precision == BIXCOR_PREC_F64 || is_split_float(precision) || is_ozaki(precision)) return BIXCOR_OK;
   if (precision == BIXCOR_PREC_I8EXACT) {
     if (!spearman) return fail(BIXCOR_ERR_INVALID, "BIXCOR_PREC_I8EXACT is defined for Spearman only");
     // sum d_i d_j <= n(n^2-1)/3 must fit the int32 recombination of the three digit accumulators
@@ -405,7 +409,7 @@ static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, c
 
 static int64_t operand_row_bytes(int64_t n, int precision) {
   const int64_t K = round_up((int)n, k_padding(precision));
-  return precision == BIXCOR_PREC_I8EXACT ? 2 * K : 8 * K;
+  return precision == BIXCOR_PREC_I8EXACT ? 2 * K : (precision == BIXCOR_PREC_F16X3 ? 4 * K : 8 * K);
 }
 
 // Gene-major operand layout (one contiguous record per gene, so gene slabs built on different
@@ -447,6 +451,12 @@ static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int sp
     co.ld8 = 2 * K;
     co.plane8 = K;
     co.inv_norm = inv + g0;
+  } else if (precision == BIXCOR_PREC_F16X3) {
+    co.mode = COL_TF32;
+    co.half_planes = 1;
+    co.f32 = (float*)((__half*)dst + g0 * 2 * K);
+    co.ld32 = 2 * K;
+    co.plane32 = K;
   } else {
     co.mode = COL_TF32;
     co.f32 = (float*)dst + g0 * 2 * K;
@@ -523,7 +533,7 @@ static void set_beta(EpiParams& e, double beta, int keep_sign) {
 
 // Transposed interior tiles need the lean epilogue (identity or ^6, unsigned, no RBF) and a tcgen05 kind.
 static int swap_tiles(int precision, const EpiParams& e) {
-  if (!umma::kSwapInterior || (precision != BIXCOR_PREC_TF32X3 && precision != BIXCOR_PREC_I8EXACT)) return 0;
+  if (!umma::kSwapInterior || (!is_split_float(precision) && precision != BIXCOR_PREC_I8EXACT)) return 0;
   return (!e.rbf_mode && !e.keep_sign && (e.beta == 1.0 || e.beta_int == 6)) ? 1 : 0;
 }
 
@@ -603,7 +613,7 @@ static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, co
     }
     return fail(BIXCOR_ERR_INVALID, "bad epilogue %d", epi);
   }
-  const int kind = a.precision == BIXCOR_PREC_I8EXACT ? umma::KIND_I8 : umma::KIND_TF32;
+  const int kind = a.precision == BIXCOR_PREC_I8EXACT ? umma::KIND_I8 : (a.precision == BIXCOR_PREC_F16X3 ? umma::KIND_F16 : umma::KIND_TF32);
   const void* pl0 = kind == umma::KIND_I8 ? (const void*)a.i8 : (const void*)a.f32;
   const void* pl1 = b ? (kind == umma::KIND_I8 ? (const void*)b->i8 : (const void*)b->f32) : nullptr;
   Timed tm(c, T_GEMM);
@@ -904,12 +914,13 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
       op.K = (int)p;
       op.z64 = d_a;
     }
-  } else if (precision == BIXCOR_PREC_TF32X3) {
-    const int K = round_up((int)p, 32);
+  } else if (is_split_float(precision)) {
+    const int K = round_up((int)p, k_padding(precision));
     RC_TRY(c->op[1].reserve(sizeof(float) * 2 * (size_t)K * p));
     ColumnOut co;
     memset(&co, 0, sizeof co);
     co.mode = COL_TF32;
+    co.half_planes = precision == BIXCOR_PREC_F16X3;
     co.kpad = K;
     co.f32 = (float*)c->op[1].ptr;
     co.ld32 = 2 * K;
@@ -924,7 +935,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
     op.z64 = d_a;
     RC_TRY(ozaki_slice(c, d_a, p, p, p, 1, &op));  // rows of A are its columns (symmetric): digit planes of every gene
   } else {
-    return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3 and BIXCOR_PREC_OZAKI");
+    return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3, BIXCOR_PREC_F16X3 and BIXCOR_PREC_OZAKI");
   }
   const bool full = (row_begin == 0 && row_end == p);
   const int upper = (packed || full) ? 1 : 0;
@@ -1305,7 +1316,7 @@ int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spear
 }
 
 int64_t bixcor_dev_operand_row_bytes(int64_t n, int precision) {
-  if (n < 1 || precision < 0 || precision > 2) return -1;
+  if (n < 1 || !exchangeable(precision)) return -1;
   return operand_row_bytes(n, precision);
 }
 
@@ -1335,7 +1346,7 @@ int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm
                                  int shift, double beta, int64_t row_begin, int64_t row_end, double* d_out) {
   DEV_PROLOGUE();
   RC_TRY(validate_rows(p, row_begin, row_end));
-  if (precision < 0 || precision > 2) return fail(BIXCOR_ERR_INVALID, "operand exchange supports precisions 0..2 (got %d)", precision);
+  if (!exchangeable(precision)) return fail(BIXCOR_ERR_INVALID, "operand exchange supports precisions 0..2 and 5 (got %d)", precision);
   if (row_begin < row_end) {
     Operand op;
     bind_operand(&op, n, p, precision, d_operand, d_inv_norm);
@@ -1350,7 +1361,7 @@ int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_
   DEV_PROLOGUE();
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (!d_operand || !h_out_slice) return fail(BIXCOR_ERR_INVALID, "null pointer");
-  if (precision < 0 || precision > 2) return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
+  if (!exchangeable(precision)) return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
   if (row_begin == row_end) return BIXCOR_OK;
   shift = shift ? 1 : 0;
   Operand op;
@@ -1587,7 +1598,7 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
   const int nd_all = (int)g_ctx.size();
   PhaseBarrier bar(nd_all);
   std::vector<double> k_host((size_t)p, 0.0);
-  const int cor_prec = (precision == BIXCOR_PREC_TF32X3 || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
+  const int cor_prec = (is_split_float(precision) || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
   return for_each_device([&](Ctx* c, int d, int nd) -> int {
     int64_t c0, c1;
     even_slab(p, nd, d, &c0, &c1);
@@ -1711,7 +1722,7 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
   RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
   // the correlation feeding the TOM is always the exact / requested-precision Gram
-  const int cor_prec = (precision == BIXCOR_PREC_TF32X3 || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
+  const int cor_prec = (is_split_float(precision) || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
   RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
                       (double*)c->out2.ptr));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, packed, out);

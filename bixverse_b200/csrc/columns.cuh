@@ -34,6 +34,9 @@ struct ColumnOut {
   float* f32;          // COL_TF32: 2 planes, plane stride `plane32` floats
   int64_t ld32;
   int64_t plane32;
+  int half_planes;     // COL_TF32 with binary16 planes instead (BIXCOR_PREC_F16X3): f32 / ld32 / plane32 then address
+                       // __half elements and the values are scaled by kF16Scale before the split
+
   double* inv_norm;    // COL_I8: 1/sqrt(sum d^2) per gene
 };
 
@@ -83,7 +86,21 @@ __device__ __forceinline__ int block_excl_suffix_min(int v, int* scr) {
 
 // Write one standardised column in the requested operand layout.
 // `val(i)` yields the centred value of sample i (double), `scale_div` the norm.
+constexpr double kF16Scale = 1024.0;  // keeps lo = f16(s z - hi) out of the subnormal range for |z| > 1e-4
+__device__ __forceinline__ void split_f16(double z, __half& hi, __half& lo) {
+  const double zs = z * kF16Scale;
+  hi = __float2half_rn((float)zs);
+  lo = __float2half_rn((float)(zs - (double)__half2float(hi)));
+}
 __device__ __forceinline__ void emit_tf32(const ColumnOut& out, int64_t j, int i, double z) {
+  if (out.half_planes) {
+    __half hi, lo;
+    split_f16(z, hi, lo);
+    __half* hp = reinterpret_cast<__half*>(out.f32);
+    hp[j * out.ld32 + i] = hi;
+    hp[out.plane32 + j * out.ld32 + i] = lo;
+    return;
+  }
   float hi = to_tf32((float)z);
   float lo = to_tf32((float)(z - (double)hi));
   out.f32[j * out.ld32 + i] = hi;
@@ -237,6 +254,10 @@ rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2,
       if (tid == 0) out.inv_norm[j] = qnan;
     } else {
       for (int i = tid; i < out.kpad; i += nt) {
+        if (out.half_planes) {
+          emit_tf32(out, j, i, (i < n) ? qnan : 0.0);
+          continue;
+        }
         float f = (i < n) ? __int_as_float(0x7fc00000) : 0.f;
         out.f32[j * out.ld32 + i] = f;
         out.f32[out.plane32 + j * out.ld32 + i] = 0.f;
@@ -461,6 +482,10 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
       if (lane == 0) out.inv_norm[j] = qnan;
     } else {
       for (int i = lane; i < out.kpad; i += 32) {
+        if (out.half_planes) {
+          emit_tf32(out, j, i, (i < n) ? qnan : 0.0);
+          continue;
+        }
         out.f32[j * out.ld32 + i] = (i < n) ? __int_as_float(0x7fc00000) : 0.f;
         out.f32[out.plane32 + j * out.ld32 + i] = 0.f;
       }
@@ -649,6 +674,13 @@ standardise_columns_reg_kernel(const double* __restrict__ x, int64_t ldx, int n,
     if (r < 8 && i2 < n2) z = make_double2(v[r].x / norm, v[r].y / norm);
     if (out.mode == COL_Z64) {
       reinterpret_cast<double2*>(out.f64 + j * out.ld64)[i2] = z;
+    } else if (out.half_planes) {
+      __half h0, l0, h1, l1;
+      split_f16(z.x, h0, l0);
+      split_f16(z.y, h1, l1);
+      __half* hp = reinterpret_cast<__half*>(out.f32);
+      reinterpret_cast<__half2*>(hp + j * out.ld32)[i2] = __halves2half2(h0, h1);
+      reinterpret_cast<__half2*>(hp + out.plane32 + j * out.ld32)[i2] = __halves2half2(l0, l1);
     } else {
       const float h0 = to_tf32((float)z.x), h1 = to_tf32((float)z.y);
       const float l0 = to_tf32((float)(z.x - (double)h0)), l1 = to_tf32((float)(z.y - (double)h1));

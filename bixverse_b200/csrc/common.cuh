@@ -1,6 +1,7 @@
 // Shared device/host helpers for libbixcor (sm_100a only).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 

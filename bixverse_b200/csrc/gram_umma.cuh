@@ -38,7 +38,11 @@
 namespace bixcor {
 namespace umma {
 
-enum Kind : int { KIND_TF32 = 0, KIND_I8 = 1 };
+enum Kind : int { KIND_TF32 = 0, KIND_I8 = 1, KIND_F16 = 2 };
+// KIND_F16: the same hi / lo split as KIND_TF32 on binary16 planes (hi = f16(s z), lo = f16(s z - hi), s = 2^10 so that
+// the low part stays out of the subnormal range; the epilogue unscales by 2^-20): 22 instead of 21 significant bits,
+// half the operand bytes and twice the MMA rate of the TF32 form.  FP32 accumulation with the same chunked promotion.
+constexpr double kF16Unscale = 1.0 / 1048576.0;
 
 // Developer instrumentation (ablation modes of Params::dbg inside the lean epilogue, clock64 phase counters)
 // costs registers in the hot loops, so it is compiled in only with -DBIXCOR_UMMA_PROFILE (scripts/perf_probe.py,
@@ -248,38 +252,24 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+#define BIXCOR_TC_MMA(GROUP, KINDSTR)                                                                  \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                       \
+               "tcgen05.mma.cta_group::" GROUP ".kind::" KINDSTR " [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), \
+               "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)                                   \
+               : "memory")
 template <int KIND, int CTAS = 1>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   if (CTAS == 2) {
-    if (KIND == KIND_TF32) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-          "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-          ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-          "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-          ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-          : "memory");
-    }
-    return;
-  }
-  if (KIND == KIND_TF32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (KIND == KIND_TF32) BIXCOR_TC_MMA("2", "tf32");
+    else if (KIND == KIND_F16) BIXCOR_TC_MMA("2", "f16");
+    else BIXCOR_TC_MMA("2", "i8");
   } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (KIND == KIND_TF32) BIXCOR_TC_MMA("1", "tf32");
+    else if (KIND == KIND_F16) BIXCOR_TC_MMA("1", "f16");
+    else BIXCOR_TC_MMA("1", "i8");
   }
 }
+#undef BIXCOR_TC_MMA
 
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -340,7 +330,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 template <int KIND, int CTAS = 1, int N = BN>
 __host__ __device__ constexpr uint32_t make_idesc() {
   return (KIND == KIND_TF32 ? (1u << 4) | (2u << 7) | (2u << 10)    // D = F32, A = B = TF32
-                            : (2u << 4) | (1u << 7) | (1u << 10))   // D = S32, A = B = signed int8
+          : KIND == KIND_F16 ? (1u << 4)                            // D = F32, A = B = F16 (format code 0)
+                             : (2u << 4) | (1u << 7) | (1u << 10))  // D = S32, A = B = signed int8
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);  // M = 256 across the CTA pair
 }
 
@@ -355,6 +346,15 @@ struct KindTraits<KIND_TF32> {
   // at a time; the epilogue warps drain every chunk from TMEM and sum the chunks in FP32 registers
   // with round-to-nearest (measured: 1e-5 -> <1e-6 at n = 1000, and independent of K).
   static constexpr int CHUNK_KB = 4;
+};
+#ifndef BIXCOR_F16_CHUNK_KB
+#define BIXCOR_F16_CHUNK_KB 2
+#endif
+template <>
+struct KindTraits<KIND_F16> {
+  static constexpr int NACC = 1;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int CHUNK_KB = BIXCOR_F16_CHUNK_KB;  // K blocks of 64 samples: 2 = the same 128 samples per promotion as TF32
 };
 template <>
 struct KindTraits<KIND_I8> {
@@ -645,7 +645,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           const CUtensorMap* map = pass ? &map1 : &map0;
           const CUtensorMap* mapb = pass ? &mapb1 : &mapb0;
           const int kb_n = P.kblocks[pass];
-          const int kelems = (KIND == KIND_TF32) ? 32 : 128;
+          const int kelems = (KIND == KIND_TF32) ? 32 : (KIND == KIND_F16 ? 64 : 128);
           for (int kb = 0; kb < kb_n; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t s0 = base + stage * STAGE_BYTES;
@@ -706,7 +706,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes, in 16-byte descriptor units
                 const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
                 if (kProfile && (P.dbg == 3 || P.dbg == 6)) continue;
-                if (KIND == KIND_TF32) {
+                if (KIND != KIND_I8) {
                   tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB0 + ko, idesc, first);  // hi*hi
                   tc_mma<KIND, CTAS>(acc0, dA0 + ko, dB1 + ko, idesc, 1u);     // hi*lo
                   tc_mma<KIND, CTAS>(acc0, dA1 + ko, dB0 + ko, idesc, 1u);     // lo*hi
@@ -771,7 +771,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int shift = E.shift;
     const int diag_one = E.diag_one;
     const int keep_sign = E.keep_sign;
-    const double scale = E.scale;
+    const double scale = E.scale * (KIND == KIND_F16 ? kF16Unscale : 1.0);  // f16 planes carry 2^10 each
     // 1 identity, 6 = WGCNA default, 0 generic (any other exponent, or an RBF transform)
     const int pw_mode = E.rbf_mode ? 0 : ((E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0));
     long long prof_acc[4] = {0, 0, 0, 0};
@@ -1081,7 +1081,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= (jb + q < pp) ? __ldg(inv_col + jb + q) : 0.0;
           }
-          if ((EPI == EPI_PACKED || EPI == EPI_DENSE) && scale != 1.0) {
+          if ((EPI == EPI_PACKED || EPI == EPI_DENSE || KIND == KIND_F16) && scale != 1.0) {
 #pragma unroll
             for (int q = 0; q < EPI_CHUNK; ++q) vals[q] *= scale;
           }
@@ -1211,12 +1211,12 @@ inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, i
     snprintf(err_buf(), 512, "cuTensorMapEncodeTiled entry point not available");
     return -1;
   }
-  const int es = kind == KIND_TF32 ? 4 : 1;
+  const int es = kind == KIND_TF32 ? 4 : (kind == KIND_F16 ? 2 : 1);
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)nplanes, (cuuint64_t)rows};
   cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * es * nplanes};
   cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), 1, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+  CUresult r = fn(map, kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (kind == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 3,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1266,7 +1266,7 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
                             const double* inv1, const int2* tiles, int ntiles, const EpiParams& E, int nplanes = 2,
                             int plane_a0 = 0, int plane_b0 = 0) {
   if (ntiles <= 0) return 0;
-  const int kelems = kind == KIND_TF32 ? 32 : 128;
+  const int kelems = kind == KIND_TF32 ? 32 : (kind == KIND_F16 ? 64 : 128);
   if (K0 % kelems != 0 || (planes1 && K1 % kelems != 0)) {
     snprintf(err_buf(), 512, "operand K must be padded to %d elements", kelems);
     return -1;
@@ -1335,6 +1335,9 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_DIFFCOR)
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_TOM)
   BIXCOR_UMMA_CASE(KIND_TF32, EPI_ACCUM)
+  BIXCOR_UMMA_CASE(KIND_F16, EPI_PACKED)
+  BIXCOR_UMMA_CASE(KIND_F16, EPI_DENSE)
+  BIXCOR_UMMA_CASE(KIND_F16, EPI_TOM)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_PACKED)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DIFFCOR)

@@ -239,7 +239,7 @@ def sharded_tom_from_exp(backend, x, n, p, spearman, signed, version, beta=1.0, 
     a_full = backend.empty(p, p)  # row i of this tensor == column i of the column-major matrix
     k = backend.zeros(p)
     c0, c1 = even_slab(p, world, rank)
-    cor_prec = precision if precision in (PREC_F64, _lib.PREC_TF32X3, _lib.PREC_OZAKI, _lib.PREC_OZAKI4) else PREC_F64
+    cor_prec = precision if precision in (PREC_F64, _lib.PREC_TF32X3, _lib.PREC_F16X3, _lib.PREC_OZAKI, _lib.PREC_OZAKI4) else PREC_F64
     backend.affinity_cols(x, n, p, spearman, signed, beta, cor_prec, c0, c1, a_full)
     backend.tom_connectivity(a_full, p, signed, c0, c1, k)
     if world > 1:

@@ -67,6 +67,8 @@ extern "C" {
 #define BIXCOR_PREC_OZAKI4 4  /* same with the four leading slices (three passes, 12 MMAs per product): the dropped digit
                                * products grow with sqrt(K): <=1e-7 at K = 1000, 5e-6 on the 20k TOM (the 3xTF32 class,
                                * 10 % faster there and free of the chunked FP32 promotion) */
+#define BIXCOR_PREC_F16X3 5   /* tcgen05 kind::f16 on binary16 hi / lo planes (3 MMAs per product like 3xTF32, 22 significant
+                               * bits, half the operand bytes, twice the MMA rate): fast path, <=1e-5; dense Grams and TOM */
 
 /* `version` argument of the TOM entry points ("v1"/"v2" of parse_tom_types) */
 #define BIXCOR_TOM_V1 1

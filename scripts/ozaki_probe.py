@@ -27,7 +27,7 @@ for spearman in (0, 1):
     print(f"max |f64 - ozaki| packed correlation, spearman={spearman}: {d:.3e}", flush=True)
 del res
 toms = {}
-for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI), ("ozaki4", _lib.PREC_OZAKI4), ("tf32", _lib.PREC_TF32X3)):
+for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI), ("ozaki4", _lib.PREC_OZAKI4), ("tf32", _lib.PREC_TF32X3), ("f16", _lib.PREC_F16X3)):
     D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=6.0, precision=prec)
     _lib.check(lib.bixcor_timing_enable(1))
     torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -36,7 +36,14 @@ for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI), ("ozaki4"
     tm = _lib.last_timing(); _lib.check(lib.bixcor_timing_enable(0))
     print(f"TOM {name}: wall {1e3*t:.2f} ms  kernels {tm}", flush=True)
     toms[name] = out
-print("max |f64 - ozaki| TOM:", (toms["f64"] - toms["ozaki"]).abs().max().item(), " max |f64 - ozaki4| TOM:", (toms["f64"] - toms["ozaki4"]).abs().max().item(), " max |f64 - tf32| TOM:", (toms["f64"] - toms["tf32"]).abs().max().item())
+print("max |f64 - ozaki| TOM:", (toms["f64"] - toms["ozaki"]).abs().max().item(), " max |f64 - ozaki4| TOM:", (toms["f64"] - toms["ozaki4"]).abs().max().item(), " max |f64 - tf32| TOM:", (toms["f64"] - toms["tf32"]).abs().max().item(), " max |f64 - f16| TOM:", (toms["f64"] - toms["f16"]).abs().max().item())
+for name, prec in (("tf32", _lib.PREC_TF32X3), ("f16", _lib.PREC_F16X3)):  # beta = 1 and Pearson Gram accuracy of the split kinds
+    out, _ = D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=1.0, precision=prec)
+    ref, _ = D.sharded_tom_from_exp(be, xd, n, p, False, True, "v1", beta=1.0, precision=_lib.PREC_F64)
+    print(f"max |f64 - {name}| TOM beta=1:", (ref - out).abs().max().item(), flush=True)
+    g = be.cor_upper_rows(xd, n, p, 0, 1, 1.0, prec, 0, p)
+    gr = be.cor_upper_rows(xd, n, p, 0, 1, 1.0, _lib.PREC_F64, 0, p)
+    print(f"max |f64 - {name}| Pearson packed:", (g - gr).abs().max().item(), flush=True)
 # beta = 1 TOM (reference semantics, dense affinities: the hard case for fixed-point slices)
 t1 = {}
 for name, prec in (("f64", _lib.PREC_F64), ("ozaki", _lib.PREC_OZAKI)):

@@ -37,5 +37,5 @@ for pr in probes:
     kind, d, *rest = pr.split(":")
     beta = rest[0] if rest else "6.0"
     nn = int(rest[1]) if len(rest) > 1 else 1000
-    run(f"umma {kind} dbg {d} beta {beta} n {nn} ctas {os.environ.get('BIXCOR_UMMA_CTAS', '2')}", 2 if kind == "i8" else 1, n=nn,
+    run(f"umma {kind} dbg {d} beta {beta} n {nn} ctas {os.environ.get('BIXCOR_UMMA_CTAS', '2')}", {"i8": 2, "tf32": 1, "f16": 5}[kind], n=nn,
         BIXCOR_UMMA_DEBUG=d, PROBE_BETA=beta)

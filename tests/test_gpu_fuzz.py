@@ -36,7 +36,7 @@ def test_random_shapes_all_precisions(api, n, p, spearman, ties, seed):
         x = np.round(x, 1)
     ref_dense = o.column_pairwise_cor(x, spearman)
     ok_dense = ~np.isnan(ref_dense)
-    precs = [(_lib.PREC_F64, 1e-10), (_lib.PREC_TF32X3, 1e-5), (_lib.PREC_OZAKI, 1e-10)]
+    precs = [(_lib.PREC_F64, 1e-10), (_lib.PREC_TF32X3, 1e-5), (_lib.PREC_F16X3, 1e-5), (_lib.PREC_OZAKI, 1e-10)]
     if spearman and n <= 1860:
         precs.append((_lib.PREC_I8EXACT, 1e-12))
     nb = (p + 127) // 128

@@ -273,12 +273,20 @@ def test_spearman_int8_exact_path(api, n, p):
     assert _maxerr(got6, o.soft_threshold(o.cor_upper_triangle(x, True, False), 6.0)) < 1e-12
 
 
+def _split_prec(name):
+    from bixverse_b200 import _lib
+
+    return {"tf32": _lib.PREC_TF32X3, "f16": _lib.PREC_F16X3}[name]
+
+
 @pytest.mark.parametrize("n,p", [(200, 2000), (1000, 257), (57, 129)])
 @pytest.mark.parametrize("spearman", [False, True])
-def test_tf32x3_fast_path(api, n, p, spearman):
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+def test_tf32x3_fast_path(api, n, p, spearman, kind):
+    """3 x TF32 and 3 x binary16 hi / lo splits (tcgen05 kind::tf32 / kind::f16): the north star's 1e-5 FP32-path bar."""
     from bixverse_b200.synthetic import synthetic_bulk
 
-    tf32, _ = _precisions()
+    tf32 = _split_prec(kind)
     x = synthetic_bulk(n, p, seed=5 * n + p)
     got = api.rs_cor_upper_triangle(x, spearman, True, precision=tf32)
     assert _maxerr(got, o.cor_upper_triangle(x, spearman, True)) < TOL32
@@ -288,14 +296,23 @@ def test_tf32x3_fast_path(api, n, p, spearman):
     assert _maxerr(dense, ref) < TOL32
 
 
-def test_tom_tf32x3_fast_path(api):
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+def test_tom_tf32x3_fast_path(api, kind):
     from bixverse_b200.synthetic import synthetic_bulk
 
-    tf32, _ = _precisions()
+    tf32 = _split_prec(kind)
     x = synthetic_bulk(100, 520, seed=8)
     for signed in (True, False):
-        got = api.calculate_tom_from_exp(x, signed, "v1", "pearson", beta=2.0, precision=tf32)
-        assert _maxerr(got, o.tom_from_exp(x, signed, "v1", False, 2.0)) < TOL32
+        for version in ("v1", "v2"):
+            got = api.calculate_tom_from_exp(x, signed, version, "pearson", beta=2.0, precision=tf32)
+            assert _maxerr(got, o.tom_from_exp(x, signed, version, False, 2.0)) < TOL32
+    cor = np.corrcoef(synthetic_bulk(60, 1300, seed=9).T)  # K = 1300: many promotion chunks, ragged last K block
+    got = api.rs_tom(cor, "v2", True, precision=tf32)
+    off = ~np.eye(1300, dtype=bool)
+    assert np.abs(got - o.calc_tom(cor, True, "v2"))[off].max() < TOL32
+    packed = api.cor_module_tom(api.UpperTriangularSymMat(o.dense_to_upper_triangle(cor, True), list(range(1300)), True),
+                                True, "v2", precision=tf32)
+    assert _maxerr(packed.values, o.dense_to_upper_triangle(o.calc_tom(cor, True, "v2"), True)) < TOL32
 
 
 def test_diffcor_fast_paths(api):
@@ -390,7 +407,7 @@ def test_in_process_multi_device_tom(api, prec_name):
         api.init(1, 0)
 
 
-@pytest.mark.parametrize("prec_name", ["f64", "i8", "tf32"])
+@pytest.mark.parametrize("prec_name", ["f64", "i8", "tf32", "f16"])
 def test_operand_exchange_api(api, prec_name):
     """Gene slabs of the Gram operand built separately (as different ranks would) give the same packed result."""
     import torch
@@ -399,7 +416,7 @@ def test_operand_exchange_api(api, prec_name):
     from bixverse_b200.distributed import DeviceBackend
     from bixverse_b200.synthetic import synthetic_bulk
 
-    prec = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3}[prec_name]
+    prec = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3, "f16": _lib.PREC_F16X3}[prec_name]
     n, p = 90, 700
     x = synthetic_bulk(n, p, seed=12, tie_heavy=True)
     dev = torch.device("cuda", 0)
@@ -420,7 +437,7 @@ def test_operand_exchange_api(api, prec_name):
         o0 = int(o.packed_offset(r0, p, 1))
         assert torch.equal(via, direct[o0 : o0 + via.numel()])
     ref = o.soft_threshold(o.cor_upper_triangle(x, True, True), 6.0)
-    assert _maxerr(direct.cpu().numpy(), ref) < (TOL32 if prec_name == "tf32" else TOL64)
+    assert _maxerr(direct.cpu().numpy(), ref) < (TOL32 if prec_name in ("tf32", "f16") else TOL64)
 
 
 @pytest.mark.parametrize("pinned", [True, False])
