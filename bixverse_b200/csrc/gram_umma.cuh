@@ -347,14 +347,16 @@ struct KindTraits<KIND_TF32> {
   // with round-to-nearest (measured: 1e-5 -> <1e-6 at n = 1000, and independent of K).
   static constexpr int CHUNK_KB = 4;
 };
+// FP32 promotion interval of the f16 kind in K blocks of 64 samples.  Measured on the 20k TOM (run 40): 2 -> 29.9 ms,
+// max deviation 3.2e-6; 4 -> 26.0 ms, 6.6e-6.  3 gives the accuracy of the 3xTF32 path (4.7e-6) that this kind replaces.
 #ifndef BIXCOR_F16_CHUNK_KB
-#define BIXCOR_F16_CHUNK_KB 2
+#define BIXCOR_F16_CHUNK_KB 3
 #endif
 template <>
 struct KindTraits<KIND_F16> {
   static constexpr int NACC = 1;
   static constexpr int ACC_STAGES = 2;
-  static constexpr int CHUNK_KB = BIXCOR_F16_CHUNK_KB;  // K blocks of 64 samples: 2 = the same 128 samples per promotion as TF32
+  static constexpr int CHUNK_KB = BIXCOR_F16_CHUNK_KB;
 };
 template <>
 struct KindTraits<KIND_I8> {
