@@ -218,9 +218,9 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------- GPU arm
 PREC_NAMES = {"f64": "FP64 DMMA (mma.sync) exact path", "i8": "exact-integer Spearman on tcgen05 kind::i8",
-              "tf32": "3xTF32 tcgen05 fast path", "ozaki": "FP64-class Gram on tcgen05 kind::i8 (6 Ozaki digit slices, 24 MMAs per product)"}
+              "tf32": "3xTF32 tcgen05 fast path", "f16": "3 x binary16 (hi/lo split) tcgen05 kind::f16 fast path", "ozaki": "FP64-class Gram on tcgen05 kind::i8 (6 Ozaki digit slices, 24 MMAs per product)"}
 DTYPES = {"f64": "f64", "i8": "int8 x int8 -> int32 (exact), f64 epilogue", "tf32": "tf32 x3 -> f32, f64 epilogue",
-          "ozaki": "6 x int8 slices -> int32 (exact), f64 recombination"}
+          "f16": "f16 x3 -> f32, f64 epilogue", "ozaki": "6 x int8 slices -> int32 (exact), f64 recombination"}
 
 
 def run_ours(args):
@@ -241,7 +241,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     api.init(1, local)
-    PREC = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3, "ozaki": _lib.PREC_OZAKI}
+    PREC = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3, "f16": _lib.PREC_F16X3, "ozaki": _lib.PREC_OZAKI}
     peaks = load_peaks()
     steps, warmup = args.steps, max(args.warmup, 3)
 
@@ -356,6 +356,10 @@ def run_ours(args):
             peak = 2.0 * peaks["bf16_tflops"]
             note = f"2 x {peaks['src']} dense bf16 (= int8 tensor rate); 24 int8 MMAs per algorithmic flop pair (6 passes of 4)"
             mmas = 24
+        elif pname == "f16":
+            peak = peaks["bf16_tflops"]
+            note = f"{peaks['src']} dense bf16 (= f16 tensor rate); the kernel issues 3 f16 MMAs per algorithmic flop pair"
+            mmas = 3
         else:
             peak = 0.5 * peaks["bf16_tflops"]
             note = f"0.5 x {peaks['src']} dense bf16 (= tf32 tensor rate); the kernel issues 3 tf32 MMAs per algorithmic flop pair"
@@ -373,12 +377,12 @@ def run_ours(args):
                 "peak_source": note, "mma_issue_frac": mmas * ach / peak if peak else None,
                 "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / ms_step if ms_step else None,
                 "launches_per_step": tm["gemm_launches"] / k_steps,
-                "hbm_view": {"algorithmic_bytes": out_bytes + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "ozaki": 6.0}[pname] * 1024 * p,
+                "hbm_view": {"algorithmic_bytes": out_bytes + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 6.0}[pname] * 1024 * p,
                              "achieved_gbs": out_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None,
                              "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]},
                 "column_kernel": {"kernel": "rank_columns_warp_kernel", "bound": "hbm", "ms_per_step": cols_ms,
-                                  "algorithmic_bytes": 8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "ozaki": 8.0}[pname] * 1024 * p,
-                                  "achieved_gbs": (8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "ozaki": 8.0}[pname] * 1024 * p) / (cols_ms * 1e-3) / 1e9 if cols_ms > 0 else None,
+                                  "algorithmic_bytes": 8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 8.0}[pname] * 1024 * p,
+                                  "achieved_gbs": (8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 8.0}[pname] * 1024 * p) / (cols_ms * 1e-3) / 1e9 if cols_ms > 0 else None,
                                   "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]}}
         return {"value": P_total / (ms_step * 1e-3), "ms_per_step": ms_step, "roofline": roof, "clocks": clocks,
                 "gpu_launches": int(allsum(launches)), "dtype": DTYPES[pname], "path": PREC_NAMES[pname]}
@@ -387,7 +391,7 @@ def run_ours(args):
     main = measure_dev(primary, steps)
     paths = {}
     if not args.no_alt:
-        for alt in ("f64", "i8", "tf32", "ozaki"):
+        for alt in ("f64", "i8", "tf32", "f16", "ozaki"):
             if alt != primary and not (alt == "ozaki" and world > 1):  # (the operand exchange carries precisions 0..2)
                 r = measure_dev(alt, max(2, min(steps, 5)))
                 paths[alt] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "path": r["path"],
@@ -438,7 +442,7 @@ def run_ours(args):
 
             be = DeviceBackend(dev)
             tom = {}
-            for tname in (("tf32", "ozaki", "f64") if not args.no_alt else ("tf32",)):
+            for tname in (("f16", "tf32", "ozaki", "f64") if not args.no_alt else ("f16",)):
                 tprec = PREC[tname]
                 t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)  # warm-up
                 del t_out
@@ -455,7 +459,7 @@ def run_ours(args):
                               "achieved_tflops": 8.4e12 / t_tom / 1e12,
                               "kernel_ms_rank0": {"gemm": ttm["gemm_ms"], "columns": ttm["cols_ms"], "other": ttm["other_ms"]}}
             tom["config"] = ("config4: signed TOM v1 from expression, 20000 genes x 1000 samples, Pearson, beta=6, packed "
-                             "output, HBM resident; slabs exchanged + k all-reduced over NCCL when N > 1; tf32 = 3xTF32 tcgen05 "
+                             "output, HBM resident; slabs exchanged + k all-reduced over NCCL when N > 1; f16 / tf32 = 3 x binary16 / 3xTF32 tcgen05 "
                              "(<=1e-5), ozaki = 6-slice int8 tcgen05 with FP64 recombination (<=1e-10), f64 = FP64 DMMA")
         except Exception as ex:  # report, do not hide
             tom = {"error": str(ex)}
@@ -504,7 +508,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "i8"), choices=["f64", "i8", "tf32", "ozaki"],
+    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "i8"), choices=["f64", "i8", "tf32", "f16", "ozaki"],
                     help="Gram path of the headline number: i8 = exact-integer Spearman (default), f64 = FP64 DMMA, tf32 = 3xTF32")
     ap.add_argument("--no-alt", action="store_true", help="skip the other precision paths and the FP64 TOM")
     ap.add_argument("--no-tom", action="store_true")

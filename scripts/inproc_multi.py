@@ -41,7 +41,7 @@ for nd in [d for d in (1, 2, 4, 8) if d <= ndev_max]:
 tom_out = torch.empty(P, dtype=torch.float64).pin_memory()
 for nd in [d for d in (1, 2, 4, 8) if d <= ndev_max]:
     api.init(nd, 0)
-    for name, prec in (("tf32", _lib.PREC_TF32X3), ("ozaki", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
+    for name, prec in (("f16", _lib.PREC_F16X3), ("tf32", _lib.PREC_TF32X3), ("ozaki", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
         ts = []
         for rep in range(3):
             t0 = time.perf_counter()

@@ -61,12 +61,12 @@ def emit(d):
 P = 199_990_000
 n, p = 1000, 20000
 x = torch.from_numpy(np.ascontiguousarray(synthetic_bulk(n, p, seed=2024, tie_heavy=True).T)).to(dev)
-for name, prec in (("i8", _lib.PREC_I8EXACT), ("tf32", _lib.PREC_TF32X3), ("ozaki-int8", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
+for name, prec in (("i8", _lib.PREC_I8EXACT), ("f16", _lib.PREC_F16X3), ("tf32", _lib.PREC_TF32X3), ("ozaki-int8", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
     if prec == _lib.PREC_OZAKI and world > 1:
         continue  # the operand-exchange API carries precisions 0..2; the Ozaki Gram is timed on one GPU
     t = timed(lambda: D.sharded_cor_upper(be, x, n, p, True, 1, 6.0, prec))
     emit({"config": "C2 Spearman 20000x1000 |r|^6 packed", "precision": name, "ms": 1e3 * t, "pairs_per_s": P / t})
-for name, prec in (("tf32", _lib.PREC_TF32X3), ("ozaki-int8", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
+for name, prec in (("f16", _lib.PREC_F16X3), ("tf32", _lib.PREC_TF32X3), ("ozaki-int8", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
     t = timed(lambda: D.sharded_tom_from_exp(be, x, n, p, False, True, "v1", beta=6.0, precision=prec), reps=2)
     emit({"config": "C4 TOM-from-exp signed v1 beta=6 20000x1000 packed", "precision": name, "ms": 1e3 * t, "alg_tflops": 8.4e12 / t / 1e12})
 # north-star target: upper-triangle correlation + 20k-gene TOM from a HOST expression matrix, results back on the host
@@ -78,7 +78,8 @@ tom_pin = torch.empty(max(my_len, 1), dtype=torch.float64).pin_memory()
 ws = {}
 for name, prec, tprec in (("f64 (FP64 DMMA Gram + TOM)", _lib.PREC_F64, _lib.PREC_F64),
                           ("exact-class (FP64 DMMA Gram, Ozaki int8 TOM)", _lib.PREC_F64, _lib.PREC_OZAKI),
-                          ("fast (exact int8 Gram, 3xTF32 TOM)", _lib.PREC_I8EXACT, _lib.PREC_TF32X3)):
+                          ("fast (exact int8 Gram, 3xTF32 TOM)", _lib.PREC_I8EXACT, _lib.PREC_TF32X3),
+                          ("fast (exact int8 Gram, 3 x f16 TOM)", _lib.PREC_I8EXACT, _lib.PREC_F16X3)):
     def job():
         D.host_sharded_cor_upper(be, x_pin, n, p, prec == _lib.PREC_I8EXACT, cor_pin, 1, 1.0, prec, workspace=ws)
         xd = x_pin.to(dev, non_blocking=True)
@@ -91,7 +92,7 @@ del x, x_pin, cor_pin, tom_pin
 xa, xb = synthetic_pair(500, 500, p, seed=2025)
 xa = torch.from_numpy(np.ascontiguousarray(xa.T)).to(dev)
 xb = torch.from_numpy(np.ascontiguousarray(xb.T)).to(dev)
-for name, prec, sp in (("f64-pearson", _lib.PREC_F64, False), ("i8-spearman", _lib.PREC_I8EXACT, True), ("tf32-pearson", _lib.PREC_TF32X3, False), ("ozaki-pearson", _lib.PREC_OZAKI, False)):
+for name, prec, sp in (("f64-pearson", _lib.PREC_F64, False), ("i8-spearman", _lib.PREC_I8EXACT, True), ("tf32-pearson", _lib.PREC_TF32X3, False), ("f16-pearson", _lib.PREC_F16X3, False), ("ozaki-pearson", _lib.PREC_OZAKI, False)):
     t = timed(lambda: D.sharded_diffcor(be, xa, 500, xb, 500, p, sp, prec), reps=2)
     emit({"config": "C3 diffcor 20000 genes 500 vs 500", "precision": name, "ms": 1e3 * t, "pairs_per_s": P / t})
 del xa, xb

@@ -14,7 +14,7 @@ x = synthetic_bulk(n, p, seed=2024)
 packed = torch.from_numpy(api.rs_cor_upper_triangle(x, False, True)).pin_memory()
 out = torch.empty(P, dtype=torch.float64).pin_memory()
 rows = []
-for name, prec in (("tf32", _lib.PREC_TF32X3), ("ozaki", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
+for name, prec in (("f16", _lib.PREC_F16X3), ("tf32", _lib.PREC_TF32X3), ("ozaki", _lib.PREC_OZAKI), ("f64", _lib.PREC_F64)):
     ts = []
     for rep in range(3):
         t0 = time.perf_counter()

@@ -33,7 +33,7 @@ def _worker(rank, world, port, tmpdir):
         xt = torch.from_numpy(np.ascontiguousarray(x.T))
         xd = xt.to(dev)
         full = o.soft_threshold(o.cor_upper_triangle(x, True, True), 6.0)
-        for prec, tol in ((_lib.PREC_F64, 1e-10), (_lib.PREC_I8EXACT, 1e-12), (_lib.PREC_TF32X3, 1e-5)):
+        for prec, tol in ((_lib.PREC_F64, 1e-10), (_lib.PREC_I8EXACT, 1e-12), (_lib.PREC_TF32X3, 1e-5), (_lib.PREC_F16X3, 1e-5)):
             sl, (o0, o1) = D.sharded_cor_upper(be, xd, n, p, True, 1, 6.0, prec)
             assert np.abs(sl.cpu().numpy() - full[o0:o1]).max() < tol
             out_host = torch.empty(o1 - o0, dtype=torch.float64).pin_memory()
@@ -45,7 +45,7 @@ def _worker(rank, world, port, tmpdir):
         ref = o.differential_cor(x, xb, False)
         assert np.abs(res["r_a"].cpu().numpy() - ref["r_a"][d0:d1]).max() < 1e-10
         assert np.abs(res["z_score"].cpu().numpy() - ref["z_score"][d0:d1]).max() < 1e-9
-        for prec, tol in ((_lib.PREC_F64, 1e-10), (_lib.PREC_OZAKI, 1e-10), (_lib.PREC_TF32X3, 1e-5)):
+        for prec, tol in ((_lib.PREC_F64, 1e-10), (_lib.PREC_OZAKI, 1e-10), (_lib.PREC_TF32X3, 1e-5), (_lib.PREC_F16X3, 1e-5)):
             for signed in (True, False):
                 t, (t0, t1) = D.sharded_tom_from_exp(be, xd, n, p, False, signed, "v1", beta=2.0, precision=prec)
                 tref = o.dense_to_upper_triangle(o.tom_from_exp(x, signed, "v1", False, 2.0), True)
