@@ -353,6 +353,37 @@ csr_densify_tf32_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   }
 }
 
+// binary16 form of the panel (BIXCOR_PREC_F16X3): hi = f16(2^10 v), lo = f16(2^10 v - hi); |v| >= 63 does not fit
+// and raises *overflow (the caller reports it instead of returning infinities).
+__global__ void __launch_bounds__(256)
+csr_densify_f16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                       const float* __restrict__ data, int64_t c0, int ncell, int64_t genes, __half* __restrict__ planes,
+                       int64_t K, int* __restrict__ overflow) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= ncell) return;
+  const int64_t b = indptr[c0 + warp], e = indptr[c0 + warp + 1];
+  for (int64_t q = b + lane; q < e; q += 32) {
+    const int64_t g = indices[q];
+    if (g < 0 || g >= genes) continue;
+    const double v = (double)data[q];
+    if (fabs(v) >= 63.0) atomicExch(overflow, 1);
+    __half hi, lo;
+    split_f16(v, hi, lo);
+    planes[g * 2 * K + warp] = hi;
+    planes[g * 2 * K + K + warp] = lo;
+  }
+}
+__global__ void __launch_bounds__(128)
+panel_rowsum_f16_kernel(const __half* __restrict__ planes, int64_t K, int ncell, double* __restrict__ colsum) {
+  __shared__ double scr[32];
+  const int64_t g = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < ncell; i += blockDim.x)
+    s += (double)__half2float(planes[g * 2 * K + i]) + (double)__half2float(planes[g * 2 * K + K + i]);
+  s = block_sum(s, scr);
+  if (threadIdx.x == 0) colsum[g] += s * (1.0 / kF16Scale);
+}
+
 __global__ void __launch_bounds__(128)
 panel_rowsum_tf32_kernel(const float* __restrict__ planes, int64_t K, int ncell, double* __restrict__ colsum) {
   __shared__ double scr[32];

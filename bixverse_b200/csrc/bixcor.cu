@@ -126,6 +126,7 @@ struct Ctx {
   Buffer vec;           // k, diag, colsum
   Buffer panel;         // sparse dense panel
   Buffer sparse_in;     // staged CSR
+  Buffer flag;          // one int: device-side overflow / range flags read back by the host
   PinnedBuffer stage[2];
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
   // timing
@@ -176,6 +177,7 @@ static void ctx_destroy(Ctx* c) {
   c->vec.release();
   c->panel.release();
   c->sparse_in.release();
+  c->flag.release();
   for (auto& b : c->stage) b.release();
   for (auto& kv : c->tile_cache)
     if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
@@ -926,9 +928,21 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
     co.f32 = (float*)c->op[1].ptr;
     co.ld32 = 2 * K;
     co.plane32 = K;
-    Timed tm(c, T_COLS);
-    split_tf32_kernel<<<(unsigned)p, 256, 0, c->compute>>>(d_a, p, (int)p, co);
-    g_launches++;
+    RC_TRY(c->flag.reserve(256));
+    int* d_flag = (int*)c->flag.ptr;
+    CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), c->compute));
+    {
+      Timed tm(c, T_COLS);
+      split_tf32_kernel<<<(unsigned)p, 256, 0, c->compute>>>(d_a, p, (int)p, co, d_flag);
+      g_launches++;
+    }
+    if (co.half_planes) {
+      int overflow = 0;
+      CU_TRY(cudaMemcpyAsync(&overflow, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+      CU_TRY(cudaStreamSynchronize(c->compute));
+      if (overflow)
+        return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_F16X3 needs affinities below 63 in magnitude; use BIXCOR_PREC_TF32X3");
+    }
     op.K = K;
     op.f32 = co.f32;
   } else if (is_ozaki(precision)) {
@@ -959,16 +973,22 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
 
 static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
                                  int64_t cells, int64_t genes, int precision, double* d_gram, double* d_colsum) {
-  if (precision != BIXCOR_PREC_F64 && precision != BIXCOR_PREC_TF32X3)
-    return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram runs on BIXCOR_PREC_F64 or BIXCOR_PREC_TF32X3");
-  const bool fast = precision == BIXCOR_PREC_TF32X3;
+  if (precision != BIXCOR_PREC_F64 && !is_split_float(precision))
+    return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram runs on BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3 or BIXCOR_PREC_F16X3");
+  const bool fast = is_split_float(precision), half = precision == BIXCOR_PREC_F16X3;
+  int* d_flag = nullptr;
+  if (half) {
+    RC_TRY(c->flag.reserve(256));
+    d_flag = (int*)c->flag.ptr;
+    CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), c->compute));
+  }
   const int chunk = 8192;  // cells per dense panel (K of one Gram accumulation pass)
   RC_TRY(c->panel.reserve(sizeof(double) * (size_t)chunk * genes));  // f64 panel == two f32 planes
   TileList* tl;
   RC_TRY(get_tiles(c, genes, 0, genes, 1, 8, umma_pairs(precision, EPI_ACCUM), &tl));
   for (int64_t c0 = 0; c0 < cells; c0 += chunk) {
     const int nc = (int)std::min<int64_t>(chunk, cells - c0);
-    const int K = round_up(nc, fast ? 32 : dmma::BK);
+    const int K = round_up(nc, k_padding(precision));
     Operand op;
     op.precision = precision;
     op.K = K;
@@ -976,7 +996,12 @@ static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t*
     {
       Timed tm(c, T_OTHER);
       CU_TRY(cudaMemsetAsync(c->panel.ptr, 0, sizeof(double) * (size_t)K * genes, c->compute));
-      if (fast) {
+      if (half) {
+        csr_densify_f16_kernel<<<(nc * 32 + 255) / 256, 256, 0, c->compute>>>(d_indptr, d_indices, d_data, c0, nc, genes,
+                                                                               (__half*)c->panel.ptr, K, d_flag);
+        panel_rowsum_f16_kernel<<<(unsigned)genes, 128, 0, c->compute>>>((const __half*)c->panel.ptr, K, nc, d_colsum);
+        op.f32 = (const float*)c->panel.ptr;
+      } else if (fast) {
         csr_densify_tf32_kernel<<<(nc * 32 + 255) / 256, 256, 0, c->compute>>>(d_indptr, d_indices, d_data, c0, nc, genes,
                                                                                 (float*)c->panel.ptr, K);
         panel_rowsum_tf32_kernel<<<(unsigned)genes, 128, 0, c->compute>>>((const float*)c->panel.ptr, K, nc, d_colsum);
@@ -995,6 +1020,13 @@ static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t*
     RC_TRY(launch_gram(c, op, nullptr, genes, tl->d_tiles, tl->ntiles, EPI_ACCUM, e));
   }
   CU_TRY(cudaGetLastError());
+  if (half) {
+    int overflow = 0;
+    CU_TRY(cudaMemcpyAsync(&overflow, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    CU_TRY(cudaStreamSynchronize(c->compute));
+    if (overflow)
+      return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_F16X3 needs sparse values below 63 in magnitude; use BIXCOR_PREC_TF32X3");
+  }
   return BIXCOR_OK;
 }
 

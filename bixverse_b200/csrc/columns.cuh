@@ -86,12 +86,6 @@ __device__ __forceinline__ int block_excl_suffix_min(int v, int* scr) {
 
 // Write one standardised column in the requested operand layout.
 // `val(i)` yields the centred value of sample i (double), `scale_div` the norm.
-constexpr double kF16Scale = 1024.0;  // keeps lo = f16(s z - hi) out of the subnormal range for |z| > 1e-4
-__device__ __forceinline__ void split_f16(double z, __half& hi, __half& lo) {
-  const double zs = z * kF16Scale;
-  hi = __float2half_rn((float)zs);
-  lo = __float2half_rn((float)(zs - (double)__half2float(hi)));
-}
 __device__ __forceinline__ void emit_tf32(const ColumnOut& out, int64_t j, int i, double z) {
   if (out.half_planes) {
     __half hi, lo;
@@ -798,10 +792,12 @@ ozaki_finish_tom_kernel(const double* __restrict__ G, const double* __restrict__
 
 // Split an existing f64 matrix (ld = ldin, `rows` x `k`) into TF32 hi/lo planes
 // (used for the TOM A*A fast path, where the operand is the affinity matrix itself).
-__global__ void split_tf32_kernel(const double* __restrict__ in, int64_t ldin, int k, ColumnOut out) {
+// binary16 planes: an entry with |z| >= 63 does not fit (2^10 z overflows) and raises *overflow.
+__global__ void split_tf32_kernel(const double* __restrict__ in, int64_t ldin, int k, ColumnOut out, int* overflow) {
   const int64_t j = blockIdx.x;
   for (int i = threadIdx.x; i < out.kpad; i += blockDim.x) {
     double z = (i < k) ? in[j * ldin + i] : 0.0;
+    if (out.half_planes && fabs(z) >= 63.0) atomicExch(overflow, 1);
     emit_tf32(out, j, i, z);
   }
 }

@@ -62,4 +62,12 @@ __device__ __forceinline__ float to_tf32(float f) {
   return __uint_as_float(u);
 }
 
+// binary16 hi / lo split of the f16 tensor kind (BIXCOR_PREC_F16X3); the planes carry 2^10 z
+constexpr double kF16Scale = 1024.0;  // keeps lo = f16(s z - hi) out of the subnormal range for |z| > 1e-4
+__device__ __forceinline__ void split_f16(double z, __half& hi, __half& lo) {
+  const double zs = z * kF16Scale;
+  hi = __float2half_rn((float)zs);
+  lo = __float2half_rn((float)(zs - (double)__half2float(hi)));
+}
+
 }  // namespace bixcor

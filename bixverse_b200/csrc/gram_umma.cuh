@@ -1340,6 +1340,7 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   BIXCOR_UMMA_CASE(KIND_F16, EPI_PACKED)
   BIXCOR_UMMA_CASE(KIND_F16, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_F16, EPI_TOM)
+  BIXCOR_UMMA_CASE(KIND_F16, EPI_ACCUM)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_PACKED)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DENSE)
   BIXCOR_UMMA_CASE(KIND_I8, EPI_DIFFCOR)

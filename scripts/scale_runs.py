@@ -100,7 +100,7 @@ cells, genes = 1_000_000, 5000
 c0, c1 = cells * rank // world, cells * (rank + 1) // world
 ip, ix, dd = synthetic_sparse_cells_fast(c1 - c0, genes, seed=2027 + rank)  # this rank's cell shard
 lp, li, ld = torch.from_numpy(ip).to(dev), torch.from_numpy(ix).to(dev), torch.from_numpy(dd).to(dev)
-for name, prec in (("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
+for name, prec in (("f16", _lib.PREC_F16X3), ("tf32", _lib.PREC_TF32X3), ("f64", _lib.PREC_F64)):
     t = timed(lambda: D.sharded_sparse_gram_cor(be, lp, li, ld, c1 - c0, genes, prec), reps=2)
     emit({"config": "C5 sparse CSR 1M cells x 5000 genes, cell shards + Gram all-reduce", "precision": name, "ms": 1e3 * t,
           "pairs_per_s": genes * (genes - 1) // 2 / t})

@@ -58,7 +58,7 @@ def _worker(rank, world, port, tmpdir):
         ld = torch.from_numpy(d[ip[c0] : ip[c1]]).to(dev)
         sref = o.sparse_gram_cor(ip, ix, d, cells, genes)
         ok = ~np.isnan(sref)
-        for prec, tol in ((_lib.PREC_F64, 1e-9), (_lib.PREC_TF32X3, 1e-5)):
+        for prec, tol in ((_lib.PREC_F64, 1e-9), (_lib.PREC_TF32X3, 1e-5), (_lib.PREC_F16X3, 1e-5)):
             out = D.sharded_sparse_gram_cor(be, lp, li, ld, c1 - c0, genes, prec)
             assert np.abs(out.cpu().numpy()[ok] - sref[ok]).max() < tol
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")

@@ -243,15 +243,26 @@ def test_sparse_gram_cor(api):
     assert np.abs(pl[ok] - got[sel][ok]).max() < 1e-9
 
 
-def test_sparse_gram_cor_tf32_fast_path(api):
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+def test_sparse_gram_cor_tf32_fast_path(api, kind):
+    from bixverse_b200 import _lib
     from bixverse_b200.synthetic import synthetic_sparse_cells
 
-    tf32, _ = _precisions()
+    prec = {"tf32": _lib.PREC_TF32X3, "f16": _lib.PREC_F16X3}[kind]
     cells, genes = 20000, 300  # three 8192-cell panels
     ip, ix, d = synthetic_sparse_cells(cells, genes, 2028, density=0.05)
-    got = api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes, precision=tf32)
+    got = api.sparse_gene_cor_upper_triangle(ip, ix, d, cells, genes, precision=prec)
     ref = o.sparse_gram_cor(ip, ix, d, cells, genes)
     assert _maxerr(got, ref) < TOL32
+    if kind == "f16":  # values that do not fit the scaled binary16 planes are reported, not turned into infinities
+        big = d.copy()
+        big[5] = 100.0
+        with pytest.raises(api.BixcorError):
+            api.sparse_gene_cor_upper_triangle(ip, ix, big, cells, genes, precision=prec)
+        a = np.eye(200) * 1.0
+        a[3, 7] = a[7, 3] = 80.0
+        with pytest.raises(api.BixcorError):
+            api.rs_tom(a, "v1", True, precision=prec)
 
 
 # ----------------------------------------------------------------------------- fast / exact tensor paths
