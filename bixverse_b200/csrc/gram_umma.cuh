@@ -64,6 +64,9 @@ constexpr bool kFragEpilogue = false;
 #define BIXCOR_UMMA_I8_WIDE 0
 #endif
 constexpr bool kI8Wide = BIXCOR_UMMA_I8_WIDE != 0;
+#ifndef BIXCOR_UMMA_TILE_SYNC_DEFAULT
+#define BIXCOR_UMMA_TILE_SYNC_DEFAULT 1  // measured (run 45): 20k TOM GEMM f16 25.4 -> 23.4 ms, tf32 49.1 -> 42.7 ms
+#endif
 #ifdef BIXCOR_UMMA_PROFILE
 constexpr bool kProfile = true;
 #else
@@ -145,6 +148,8 @@ struct Params {
   unsigned long long* prof;  // optional (env BIXCOR_UMMA_PROF): per epilogue warp cycles {wait, drain, lean epilogue, tiles}
   int plane_a0, plane_b0;  // first digit plane of the row / column operand inside the gene record (0 unless Ozaki groups)
   int zero;  // always 0; opaque to the compiler (scheduling fence, see the epilogue drain)
+  unsigned* tile_sync;  // long-K launches: global arrival counter, the TMA producers of all CTAs start every tile together
+                        // so that CTAs sharing an operand panel stream it through L2 in step (nullptr = off)
   int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = generic path without global stores, 3 = no MMA issue,
             // 4 = lean path without global stores, 5 = lean path without phase B, 6 = no TMA and no MMA (epilogue alone)
   EpiParams E;
@@ -637,7 +642,23 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = unit0; t < P.ntiles; t += unit_stride) {
+      const int n_iter = (P.ntiles + unit_stride - 1) / unit_stride;  // the same for every CTA (barrier participation)
+      bool sync_alive = P.tile_sync != nullptr;
+      for (int it = 0; it < n_iter; ++it) {
+        const int t = unit0 + it * unit_stride;
+        if (sync_alive) {  // all producers of the grid are co-resident (one CTA per SM, grid = SM count): a spin barrier is safe;
+                           // the bail-out only guards against a foreign launch configuration
+          atomicAdd(P.tile_sync, 1u);
+          const unsigned target = (unsigned)(it + 1) * gridDim.x;
+          unsigned seen, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.tile_sync) : "memory");
+            if (seen >= target) break;
+            __nanosleep(40);
+          } while (++spins < (1u << 22));
+          if (seen < target) sync_alive = false;
+        }
+        if (t >= P.ntiles) continue;
         const int2 tile = P.tiles[t];
         const int ty = tile.y & ~TILE_FLAGS;
         // M operand rows (this CTA's 128) and N operand rows (the whole tile, or this CTA's half of it)
@@ -1293,6 +1314,26 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   P.inv_norm[1] = inv1;
   P.E = E;
   P.zero = 0;
+  P.tile_sync = nullptr;
+  {
+    // Long-K Grams (TOM, Ozaki passes, sparse panels): ncu shows the operand panels being re-read from DRAM (f16 TOM: 92 GB,
+    // L2 hit rate 50 %) because the persistent CTAs drift apart along K.  A per-tile arrival barrier of the producers
+    // keeps them in step; it costs a few microseconds per tile, so it is only armed when a tile's K loop is long.
+    static int sync_mode = -1;  // env BIXCOR_UMMA_TILE_SYNC: 0 = off, 1 = on for long K (default), 2 = always
+    if (sync_mode < 0) {
+      const char* v = getenv("BIXCOR_UMMA_TILE_SYNC");
+      sync_mode = v ? atoi(v) : BIXCOR_UMMA_TILE_SYNC_DEFAULT;
+    }
+    static unsigned* d_sync[64] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sync_mode == 2 || (sync_mode == 1 && P.kblocks[0] >= 96)) {
+      if (dev >= 0 && dev < 64) {
+        if (!d_sync[dev]) cudaMalloc(&d_sync[dev], 256);
+        if (d_sync[dev] && cudaMemsetAsync(d_sync[dev], 0, sizeof(unsigned), stream) == cudaSuccess) P.tile_sync = d_sync[dev];
+      }
+    }
+  }
   P.plane_a0 = plane_a0;
   P.plane_b0 = plane_b0;
   P.prof = nullptr;

@@ -1,0 +1,10 @@
+#!/bin/bash
+# run 46: final state (tile sync on by default): full GPU suite, smoke, bench line
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/smoke.log
+timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+echo "bench exit $?" >> gpurun_out/bench_n1.err
+tail -2 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log; tail -1 gpurun_out/bench_n1.err; cut -c1-200 gpurun_out/bench_n1.json
