@@ -48,6 +48,13 @@ def test_packed_helpers_match_oracle(lib_built):
         assert np.array_equal(d, o.upper_triangle_to_dense(v, shift, 9))
     with pytest.raises(ValueError):
         api.rs_upper_triangle_to_dense(np.zeros(5), True, 9)
+    # p >= 2048 takes the multi-threaded row-block path of the host helpers (pure index logic, no GPU involved)
+    p = 2100
+    for shift in (True, False):
+        v = rng.normal(size=lib.bixcor_packed_len(p, int(shift)))
+        d = api.rs_upper_triangle_to_dense(v, shift, p)
+        assert np.array_equal(d, o.upper_triangle_to_dense(v, shift, p))
+        assert np.array_equal(api.rs_dense_to_upper_triangle(d, shift), v)
 
 
 def test_reference_sparse_vector(lib_built, golden_dir):
