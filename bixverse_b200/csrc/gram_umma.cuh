@@ -148,6 +148,7 @@ struct Params {
   unsigned long long* prof;  // optional (env BIXCOR_UMMA_PROF): per epilogue warp cycles {wait, drain, lean epilogue, tiles}
   int plane_a0, plane_b0;  // first digit plane of the row / column operand inside the gene record (0 unless Ozaki groups)
   int zero;  // always 0; opaque to the compiler (scheduling fence, see the epilogue drain)
+  int tile_sync_kb;     // > 0: additionally re-align every tile_sync_kb K blocks (env BIXCOR_UMMA_TILE_SYNC_KB, experiment)
   unsigned* tile_sync;  // long-K launches: global arrival counter, the TMA producers of all CTAs start every tile together
                         // so that CTAs sharing an operand panel stream it through L2 in step (nullptr = off)
   int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = generic path without global stores, 3 = no MMA issue,
@@ -644,21 +645,30 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       uint32_t phase = 0;
       const int n_iter = (P.ntiles + unit_stride - 1) / unit_stride;  // the same for every CTA (barrier participation)
       bool sync_alive = P.tile_sync != nullptr;
+      unsigned epoch = 0;  // barriers passed; every producer of the grid executes the same sequence of them
+      // all producers of the grid are co-resident (one CTA per SM, grid = SM count): a spin barrier is safe; the
+      // bail-out only guards against a foreign launch configuration
+      auto grid_barrier = [&]() {
+        if (!sync_alive) return;
+        atomicAdd(P.tile_sync, 1u);
+        const unsigned target = ++epoch * gridDim.x;
+        unsigned seen, spins = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.tile_sync) : "memory");
+          if (seen >= target) break;
+          __nanosleep(40);
+        } while (++spins < (1u << 22));
+        if (seen < target) sync_alive = false;
+      };
       for (int it = 0; it < n_iter; ++it) {
         const int t = unit0 + it * unit_stride;
-        if (sync_alive) {  // all producers of the grid are co-resident (one CTA per SM, grid = SM count): a spin barrier is safe;
-                           // the bail-out only guards against a foreign launch configuration
-          atomicAdd(P.tile_sync, 1u);
-          const unsigned target = (unsigned)(it + 1) * gridDim.x;
-          unsigned seen, spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.tile_sync) : "memory");
-            if (seen >= target) break;
-            __nanosleep(40);
-          } while (++spins < (1u << 22));
-          if (seen < target) sync_alive = false;
+        grid_barrier();
+        if (t >= P.ntiles) {  // no tile in the last round: still take part in the optional mid-tile barriers
+          if (sync_alive && P.tile_sync_kb > 0)
+            for (int pass = 0; pass < P.npass; ++pass)
+              for (int kb = P.tile_sync_kb; kb < P.kblocks[pass]; kb += P.tile_sync_kb) grid_barrier();
+          continue;
         }
-        if (t >= P.ntiles) continue;
         const int2 tile = P.tiles[t];
         const int ty = tile.y & ~TILE_FLAGS;
         // M operand rows (this CTA's 128) and N operand rows (the whole tile, or this CTA's half of it)
@@ -670,6 +680,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           const int kb_n = P.kblocks[pass];
           const int kelems = (KIND == KIND_TF32) ? 32 : (KIND == KIND_F16 ? 64 : 128);
           for (int kb = 0; kb < kb_n; ++kb) {
+            if (P.tile_sync_kb > 0 && kb > 0 && kb % P.tile_sync_kb == 0) grid_barrier();  // (experiment: re-align mid tile)
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t s0 = base + stage * STAGE_BYTES;
             if (CTAS == 2) {
@@ -1315,6 +1326,8 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   P.E = E;
   P.zero = 0;
   P.tile_sync = nullptr;
+  P.tile_sync_kb = 0;
+  if (const char* v = getenv("BIXCOR_UMMA_TILE_SYNC_KB")) P.tile_sync_kb = atoi(v) > 0 ? atoi(v) : 0;
   {
     // Long-K Grams (TOM, Ozaki passes, sparse panels): ncu shows the operand panels being re-read from DRAM (f16 TOM: 92 GB,
     // L2 hit rate 50 %) because the persistent CTAs drift apart along K.  A per-tile arrival barrier of the producers
