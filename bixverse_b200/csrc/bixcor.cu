@@ -1113,6 +1113,40 @@ static void parallel_rows(int64_t p, F fn) {
   for (auto& t : th) t.join();
 }
 
+// Column c of the symmetric matrix behind a packed vector, visited in row order: rows above the diagonal come from
+// element (r, c) of packed row r, the diagonal is 1 (shift) or stored, rows below are the contiguous run of packed row c.
+template <class F>
+static inline void sym_column_nonzeros(const double* packed, int s, int64_t p, int64_t c, F emit) {
+  for (int64_t r = 0; r < c; ++r) {
+    const double v = packed[packed_row_offset(r, p, s) + (c - r - s)];
+    if (v != 0.0) emit(r, v);
+  }
+  const double d = s ? 1.0 : packed[packed_row_offset(c, p, 0)];
+  if (d != 0.0) emit(c, d);
+  const double* row = packed + packed_row_offset(c, p, s);
+  for (int64_t r = c + 1; r < p; ++r) {
+    const double v = row[r - c - s];
+    if (v != 0.0) emit(r, v);
+  }
+}
+
+// columns [0,p) split evenly over host threads (every column of a symmetric matrix costs the same)
+template <class F>
+static void parallel_cols(int64_t p, F fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nthr = (p < 2048) ? 1 : (int)std::max(1u, std::min(hw ? hw : 4u, 16u));
+  if (nthr == 1) {
+    fn(0, p);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthr; ++t) {
+    const int64_t c0 = p * t / nthr, c1 = p * (t + 1) / nthr;
+    if (c1 > c0) th.emplace_back([=] { fn(c0, c1); });
+  }
+  for (auto& t : th) t.join();
+}
+
 extern "C" {
 
 const char* bixcor_last_error(void) {
@@ -1268,44 +1302,51 @@ int bixcor_dense_to_upper(const double* dense, int shift, int64_t p, double* out
 
 int64_t bixcor_upper_to_sparse_nnz(const double* packed, int shift, int64_t p) {
   if (!packed || p < 0) return -1;
-  const int64_t len = shift ? p * (p - 1) / 2 : p * (p + 1) / 2;
-  int64_t nnz = shift ? p : 0;  // unit diagonal
-  int64_t idx = 0;
-  for (int64_t i = 0; i < p; ++i)
-    for (int64_t j = i + (shift ? 1 : 0); j < p; ++j, ++idx)
-      if (packed[idx] != 0.0) nnz += (i == j) ? 1 : 2;
-  (void)len;
-  return nnz;
+  const int s = shift ? 1 : 0;
+  std::vector<int64_t> part(64, 0);
+  std::atomic<int> slot{0};
+  parallel_rows(p, [&](int64_t r0, int64_t r1) {  // rows of the packed vector: every stored off-diagonal non-zero counts twice
+    int64_t nnz = 0;
+    for (int64_t i = r0; i < r1; ++i) {
+      const double* row = packed + packed_row_offset(i, p, s);
+      if (s) nnz += 1;  // unit diagonal
+      for (int64_t j = i + s; j < p; ++j)
+        if (row[j - i - s] != 0.0) nnz += (i == j) ? 1 : 2;
+    }
+    part[(size_t)slot.fetch_add(1) % part.size()] += nnz;  // (at most 16 workers: one slot each)
+  });
+  int64_t total = 0;
+  for (int64_t v : part) total += v;
+  return total;
 }
-
 int bixcor_upper_to_sparse(const double* packed, int shift, int64_t p, int64_t* indptr, int32_t* indices, double* data) {
   if (!packed || !indptr || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
   const int s = shift ? 1 : 0;
+  // pass 1: non-zeros per column (threads over column blocks), prefix sum, pass 2: every column fills its own range
+  std::vector<int64_t> cnt((size_t)p + 1, 0);
+  parallel_cols(p, [&](int64_t c0, int64_t c1) {
+    for (int64_t c = c0; c < c1; ++c) {
+      int64_t n = 0;
+      sym_column_nonzeros(packed, s, p, c, [&](int64_t, double) { ++n; });
+      cnt[(size_t)c] = n;
+    }
+  });
   int64_t pos = 0;
   for (int64_t c = 0; c < p; ++c) {
     indptr[c] = pos;
-    for (int64_t r = 0; r < c; ++r) {  // rows above the diagonal: element (r, c) of the packed rows r
-      const double v = packed[packed_row_offset(r, p, s) + (c - r - s)];
-      if (v != 0.0) {
-        indices[pos] = (int32_t)r;
-        data[pos++] = v;
-      }
-    }
-    const double d = s ? 1.0 : packed[packed_row_offset(c, p, 0)];
-    if (d != 0.0) {
-      indices[pos] = (int32_t)c;
-      data[pos++] = d;
-    }
-    const double* row = packed + packed_row_offset(c, p, s);  // rows below: the contiguous run of packed row c
-    for (int64_t r = c + 1; r < p; ++r) {
-      const double v = row[r - c - s];
-      if (v != 0.0) {
-        indices[pos] = (int32_t)r;
-        data[pos++] = v;
-      }
-    }
+    pos += cnt[(size_t)c];
   }
   indptr[p] = pos;
+  if (pos > 0 && (!indices || !data)) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  parallel_cols(p, [&](int64_t c0, int64_t c1) {
+    for (int64_t c = c0; c < c1; ++c) {
+      int64_t w = indptr[c];
+      sym_column_nonzeros(packed, s, p, c, [&](int64_t r, double v) {
+        indices[w] = (int32_t)r;
+        data[w++] = v;
+      });
+    }
+  });
   return BIXCOR_OK;
 }
 

@@ -84,7 +84,7 @@ def test_upper_triangle_to_sparse_matches_reference_test(lib_built):
     assert np.array_equal(got["data"], ref.data)
     assert list(got["indptr"]) == [0, 3, 6, 8, 12]
     rng = np.random.default_rng(0)
-    for p, shift in ((1, True), (7, True), (9, False), (40, True)):
+    for p, shift in ((1, True), (7, True), (9, False), (40, True), (2300, True), (2100, False)):  # >= 2048: threaded passes
         v = rng.normal(size=p * (p - 1) // 2 if shift else p * (p + 1) // 2)
         v[rng.uniform(size=v.shape) < 0.4] = 0.0
         got = api.rs_upper_triangle_to_sparse(v, shift, p, "csr")
