@@ -127,3 +127,79 @@ void orc_tom(const double* a_in, int64_t p, int is_signed, int version, double* 
     }
   free(a); free(k);
 }
+
+/* ---- "next" rows of the scope table ----------------------------------------------------------- */
+
+/* cor(x_i, y_j): x is n x p, y is n x q (column-major), out p x q; src/rust/src/base/r_cors_similarity.rs:114-122 */
+void orc_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out) {
+  double* zx = (double*)malloc(sizeof(double) * (size_t)n * (size_t)p);
+  double* zy = (double*)malloc(sizeof(double) * (size_t)n * (size_t)q);
+  for (int side = 0; side < 2; ++side) {
+    const double* src = side ? y : x;
+    double* z = side ? zy : zx;
+    const int64_t cols = side ? q : p;
+    for (int64_t j = 0; j < cols; ++j) {
+      double* col = z + j * n;
+      if (spearman) orc_rank_average(src + j * n, n, col); else memcpy(col, src + j * n, sizeof(double) * (size_t)n);
+      double m = 0.0, ss = 0.0;
+      for (int64_t i = 0; i < n; ++i) m += col[i];
+      m /= (double)n;
+      for (int64_t i = 0; i < n; ++i) { col[i] -= m; ss += col[i] * col[i]; }
+      ss = sqrt(ss);
+      for (int64_t i = 0; i < n; ++i) col[i] /= ss;
+    }
+  }
+  for (int64_t j = 0; j < q; ++j)
+    for (int64_t i = 0; i < p; ++i) {
+      double s = 0.0;
+      for (int64_t t = 0; t < n; ++t) s += zx[t + i * n] * zy[t + j * n];
+      out[i + j * p] = s;
+    }
+  free(zx); free(zy);
+}
+
+static int cmp_desc(const void* a, const void* b) {
+  double x = *(const double*)a, y = *(const double*)b;
+  return (x < y) - (x > y);
+}
+static double kth_best(const double* v, int64_t len, int64_t stride, int k) {
+  double* t = (double*)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+  int64_t m = 0;
+  for (int64_t e = 0; e < len; ++e) { double a = fabs(v[e * stride]); if (a == a) t[m++] = a; }
+  qsort(t, (size_t)m, sizeof(double), cmp_desc);
+  double r = (m >= k) ? t[k - 1] : -INFINITY;
+  free(t);
+  return r;
+}
+/* reciprocal best hits on |cor2| (src/rust/src/methods/r_rbh.rs:187-272): hits origin-major, 0-based; returns their
+ * number; at most `cap` are written */
+int64_t orc_rbh_cor(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int k_best, int spearman,
+                    double min_similarity, int32_t* oi, int32_t* oj, double* osim, int64_t cap) {
+  double* sim = (double*)malloc(sizeof(double) * (size_t)p * (size_t)q);
+  double* rt = (double*)malloc(sizeof(double) * (size_t)p);
+  double* ct = (double*)malloc(sizeof(double) * (size_t)q);
+  orc_cor2(x, n, p, y, q, spearman, sim);
+  for (int64_t i = 0; i < p; ++i) rt[i] = kth_best(sim + i, q, p, k_best);
+  for (int64_t j = 0; j < q; ++j) ct[j] = kth_best(sim + j * p, p, 1, k_best);
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < p; ++i)
+    for (int64_t j = 0; j < q; ++j) {
+      double v = fabs(sim[i + j * p]);
+      if (v >= rt[i] && v >= ct[j] && v > min_similarity) {
+        if (cnt < cap) { oi[cnt] = (int32_t)i; oj[cnt] = (int32_t)j; osim[cnt] = v; }
+        ++cnt;
+      }
+    }
+  free(sim); free(rt); free(ct);
+  return cnt;
+}
+
+/* RBF kernels on distances (src/rust/src/base/r_rbf.rs:36-48): 1 gaussian, 2 bump, 3 inverse quadratic */
+void orc_rbf(const double* d, int64_t len, double eps, int type, double* out) {
+  for (int64_t t = 0; t < len; ++t) {
+    double e2 = (eps * d[t]) * (eps * d[t]);
+    if (type == 1) out[t] = exp(-e2);
+    else if (type == 3) out[t] = 1.0 / (1.0 + e2);
+    else out[t] = (d[t] < 1.0 / eps) ? exp(-1.0 / (1.0 - e2) + 1.0) : 0.0;
+  }
+}

@@ -235,3 +235,26 @@ def test_rbh_cor_k_best_and_threshold():
     h3 = o.rbh_cor(x, y, 3, False, 0.0)
     assert set((i, j) for i, j, _ in h1) <= set((i, j) for i, j, _ in h3) and len(h3) > len(h1)
     assert o.rbh_cor(x, y, 3, False, 0.9) == [h for h in h3 if h[2] > 0.9]
+
+
+def test_c_restatement_next_rows(lib_built, golden_dir):
+    """The plain-C oracle of the 'next' rows: pinned by the reference's rbh known answers, consistent with numpy."""
+    from oracle import c_binding as cb
+
+    g, mats, _ = _rbh_fixture(golden_dir)
+    a, b = mats["origin_1"][0], mats["origin_2"][0][:4]
+    for spearman, key in ((False, "expected_pearson"), (True, "expected_spearman")):
+        hits = cb.rbh_cor(a, b, 1, spearman, 0.0)
+        assert [(g["colnames_a"][i], g["colnames_b"][j]) for i, j, _ in hits] == list(zip(g["expected_origin_modules"], g["expected_target_modules"]))
+        np.testing.assert_allclose([v for _, _, v in hits], g[key], atol=g["tolerance"])
+    rng = np.random.default_rng(4)
+    x, y = np.round(rng.normal(size=(25, 6)), 1), rng.normal(size=(25, 9))
+    for sp in (False, True):
+        assert np.abs(cb.cor2(x, y, sp) - o.cor_two_matrices(x, y, sp)).max() < 1e-14
+        for k in (1, 3):
+            hc, hn = cb.rbh_cor(x, y, k, sp, 0.05), o.rbh_cor(x, y, k, sp, 0.05)
+            assert [(i, j) for i, j, _ in hc] == [(i, j) for i, j, _ in hn]
+            assert np.allclose([v for _, _, v in hc], [v for _, _, v in hn], atol=1e-14)
+    d = np.abs(rng.normal(size=200))
+    for t in ("gaussian", "bump", "inverse_quadratic"):
+        assert np.allclose(cb.rbf(d, 1.3, t), o.rbf_function(d, 1.3, t), rtol=1e-14, atol=0)
