@@ -258,3 +258,17 @@ def test_c_restatement_next_rows(lib_built, golden_dir):
     d = np.abs(rng.normal(size=200))
     for t in ("gaussian", "bump", "inverse_quadratic"):
         assert np.allclose(cb.rbf(d, 1.3, t), o.rbf_function(d, 1.3, t), rtol=1e-14, atol=0)
+
+
+def test_golden_fixtures_regenerate_identically(golden_dir, tmp_path, monkeypatch):
+    """The committed fixtures are exactly what tests/golden/make_golden.py writes (R's RNG restated, self-checked)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(mod, "HERE", str(tmp_path))
+    mod.main()
+    for name in ("reference_kat.json", "r_equality_seed123.json", "rbh_cor_seed42.json"):
+        with open(os.path.join(golden_dir, name)) as f, open(tmp_path / name) as g:
+            assert json.load(f) == json.load(g), name
