@@ -5,7 +5,14 @@ Metric (BASELINE.json): gene-pair correlations/sec on config 2 - Spearman correl
 20 000 genes x 1 000 samples with the |r|^6 soft-threshold adjacency, packed upper triangle
 (P = 199 990 000 pairs) - plus the 20k-gene TOM wall time (config 4) as an extra key.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f64|i8|tf32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision auto|f64|i8|tf32|f16|ozaki]
+
+`--precision auto` (default) is BIXCOR_PREC_AUTO, what the drop-in patch of INTEGRATION.md passes: for this workload
+(Spearman, n = 1000 <= 1860) it resolves to the exact-integer tcgen05 Gram.  `e2e.value` is measured from PAGEABLE host
+buffers (what an R session owns); `e2e.pinned` is the same call with page-locked buffers.  After the timed region every
+rank checks sampled rows of its own packed slice against the CPU oracle (`parity`).  The reference arm
+(`--impl reference`) and the `cpu_baseline` leg run the C/OpenMP + OpenBLAS restatement (oracle/oracle_c.c) on the FULL
+20 000-gene config with every host core.
 
 N > 1 is launched by torchrun (one process per GPU); the triangle is sharded into contiguous
 block-row ranges balanced by pair count, no data-path collective (`scaling: weak` does not
@@ -30,7 +37,7 @@ import numpy as np
 N_SAMPLES, N_GENES, BETA, SEED = 1000, 20000, 6.0, 2024
 METRIC = "gene_pair_correlations_per_sec"
 UNIT = "pairs/s"
-CPU_SAMPLE_GENES = 8000  # bounded CPU sample: first 8000 genes x all 1000 samples (31 996 000 pairs)
+PARITY_ROWS = (0, 1, 127, 128, 5000, 12345, 19871, 19998)  # sampled rows of the post-run parity check (tests use the same)
 
 
 def _env_int(k, d):
@@ -150,65 +157,52 @@ def make_input():
 
 
 # --------------------------------------------------------------------------------------- CPU baseline
-def cpu_step(x_sample):
-    """One pass of the reference algorithm shape on the host (oracle port): rank -> standardise ->
-    FULL p x p Gram (OpenBLAS dgemm, all host threads) -> row-major triangle gather -> |r|^6."""
-    from oracle import oracle as o
-
-    t0 = time.perf_counter()
-    r = o.cor_upper_triangle(x_sample, True, True)
-    a = o.soft_threshold(r, BETA)
-    dt = time.perf_counter() - t0
-    return a.shape[0], dt
+CPU_KIND_NOTE = ("C/OpenMP + OpenBLAS dgemm restatement of the reference algorithm shape (oracle/oracle_c.c: rank -> standardise -> "
+                 "FULL p x p dgemm -> triangle gather -> |r|^6), every host core; the Rust crate bixverse-rs 0.4.4 itself cannot be "
+                 "built in this image (no rustc/cargo, crate not vendored)")
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
+def cpu_step(x_f, out=None):
+    """One pass of the reference algorithm shape over the FULL workload on the host cores."""
+    from oracle import c_binding as cb
 
-        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+    _, secs = cb.cor_upper_pipeline(x_f, True, True, BETA, out=out)
+    return secs
 
 
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1; the reference arm is a CPU job and takes every host core."""
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        from threadpoolctl import threadpool_limits
+def cpu_threads():
+    from oracle import c_binding as cb
 
-        threadpool_limits(limits=ncpu)
-    except Exception:
-        pass
-    return ncpu
+    ncpu = cb.use_all_cores()
+    return ncpu, cb.num_threads(), cb.openblas_dgemm()[1]
 
 
 def run_reference(args):
     rank = _env_int("RANK", 0)
     if rank != 0:
         return 0
-    use_all_host_threads()
-    x = make_input()[:, :CPU_SAMPLE_GENES]
-    x = np.asfortranarray(x)
-    for _ in range(args.warmup):
-        cpu_step(x)
-    tot_pairs, tot_t = 0, 0.0
+    ncpu, omp_t, blas_t = cpu_threads()
+    x = np.asfortranarray(make_input())
+    P_total = N_GENES * (N_GENES - 1) // 2
+    out = np.empty(P_total)
+    for _ in range(min(args.warmup, 1)):  # one untimed pass warms the page tables / thread pools (a pass costs seconds)
+        cpu_step(x, out)
+    tot_t, parts = 0.0, {"columns_s": 0.0, "dgemm_s": 0.0, "gather_s": 0.0}
     for _ in range(args.steps):
-        pairs, dt = cpu_step(x)
-        tot_pairs += pairs
-        tot_t += dt
-    v = tot_pairs / tot_t
-    cores = blas_threads()
+        secs = cpu_step(x, out)
+        tot_t += secs["total_s"]
+        for k in parts:
+            parts[k] += secs[k] / args.steps
+    v = P_total * args.steps / tot_t
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "config2: Spearman 20000 genes x 1000 samples + |r|^6, packed upper triangle (shift=1)",
                    "n_samples": N_SAMPLES, "n_genes": N_GENES, "beta": BETA, "seed": SEED},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {CPU_SAMPLE_GENES} genes x {N_SAMPLES} samples per step "
-                                   f"({CPU_SAMPLE_GENES * (CPU_SAMPLE_GENES - 1) // 2} pairs); numpy/OpenBLAS restatement of the "
-                                   "reference algorithm shape (the Rust crate cannot be built here)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": max(omp_t, blas_t), "host_cpus": ncpu, "kind": "port",
+                         "sample": f"the full workload every step (20000 genes x 1000 samples, {P_total} pairs); " + CPU_KIND_NOTE,
+                         "seconds_per_step": parts},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -217,9 +211,9 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-PREC_NAMES = {"f64": "FP64 DMMA (mma.sync) exact path", "i8": "exact-integer Spearman on tcgen05 kind::i8",
+PREC_NAMES = {"auto": "BIXCOR_PREC_AUTO -> exact-integer Spearman on tcgen05 kind::i8 (n = 1000 <= 1860)", "f64": "FP64 DMMA (mma.sync) exact path", "i8": "exact-integer Spearman on tcgen05 kind::i8",
               "tf32": "3xTF32 tcgen05 fast path", "f16": "3 x binary16 (hi/lo split) tcgen05 kind::f16 fast path", "ozaki": "FP64-class Gram on tcgen05 kind::i8 (6 Ozaki digit slices, 24 MMAs per product)"}
-DTYPES = {"f64": "f64", "i8": "int8 x int8 -> int32 (exact), f64 epilogue", "tf32": "tf32 x3 -> f32, f64 epilogue",
+DTYPES = {"auto": "int8 x int8 -> int32 (exact), f64 epilogue", "f64": "f64", "i8": "int8 x int8 -> int32 (exact), f64 epilogue", "tf32": "tf32 x3 -> f32, f64 epilogue",
           "f16": "f16 x3 -> f32, f64 epilogue", "ozaki": "6 x int8 slices -> int32 (exact), f64 recombination"}
 
 
@@ -241,7 +235,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     api.init(1, local)
-    PREC = {"f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3, "f16": _lib.PREC_F16X3, "ozaki": _lib.PREC_OZAKI}
+    PREC = {"auto": _lib.PREC_AUTO, "f64": _lib.PREC_F64, "i8": _lib.PREC_I8EXACT, "tf32": _lib.PREC_TF32X3, "f16": _lib.PREC_F16X3, "ozaki": _lib.PREC_OZAKI}
     peaks = load_peaks()
     steps, warmup = args.steps, max(args.warmup, 3)
 
@@ -293,8 +287,9 @@ def run_ours(args):
             fp64_peak["v"] = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         return fp64_peak["v"]
 
-    def measure_dev(pname, k_steps):
+    def measure_dev(pname, k_steps, keep_out=False):
         prec = PREC[pname]
+        xprec = _lib.PREC_I8EXACT if pname == "auto" else prec  # the operand-exchange API takes the resolved precision
         _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream, 1))
         _lib.check(lib.bixcor_dev_set_async(1))
 
@@ -306,16 +301,16 @@ def run_ours(args):
             from bixverse_b200.distributed import gene_slab
 
             slab = gene_slab(p, world)
-            rb = int(lib.bixcor_dev_operand_row_bytes(n, prec))
+            rb = int(lib.bixcor_dev_operand_row_bytes(n, xprec))
             operand = torch.empty(world * slab * rb, dtype=torch.uint8, device=dev)
             inv = torch.zeros(world * slab, dtype=torch.float64, device=dev)
             g0, g1 = min(p, rank * slab), min(p, (rank + 1) * slab)
 
             def step():
-                _lib.check(lib.bixcor_dev_build_operand(x_dev.data_ptr(), n, p, 1, prec, g0, g1, operand.data_ptr(), inv.data_ptr()))
+                _lib.check(lib.bixcor_dev_build_operand(x_dev.data_ptr(), n, p, 1, xprec, g0, g1, operand.data_ptr(), inv.data_ptr()))
                 dist.all_gather_into_tensor(operand, operand[rank * slab * rb:(rank + 1) * slab * rb])
-                _lib.check(lib.bixcor_dev_operand_inv_norm(operand.data_ptr(), n, p, prec, inv.data_ptr()))  # no second collective
-                _lib.check(lib.bixcor_dev_cor_upper_rows_op(operand.data_ptr(), inv.data_ptr(), n, p, prec, 1, BETA, r0, r1,
+                _lib.check(lib.bixcor_dev_operand_inv_norm(operand.data_ptr(), n, p, xprec, inv.data_ptr()))  # no second collective
+                _lib.check(lib.bixcor_dev_cor_upper_rows_op(operand.data_ptr(), inv.data_ptr(), n, p, xprec, 1, BETA, r0, r1,
                                                             out_dev.data_ptr()))
 
         for _ in range(warmup):
@@ -348,7 +343,7 @@ def run_ours(args):
             peak = dgemm_peak()
             note = "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry; nominal 40)"
             mmas = 1
-        elif pname == "i8":
+        elif pname in ("i8", "auto"):
             peak = 2.0 * peaks["bf16_tflops"]
             note = f"2 x {peaks['src']} dense bf16 (= int8 tensor rate); the kernel issues 4 int8 MMAs per algorithmic flop pair"
             mmas = 4
@@ -369,7 +364,7 @@ def run_ours(args):
         if world == 1:
             try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
                 tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-                traffic = tr.get("gram_dmma_kernel" if pname == "f64" else f"gram_umma_kernel_{pname}", {}).get("dram_bytes_per_launch")
+                traffic = tr.get("gram_dmma_kernel" if pname == "f64" else f"gram_umma_kernel_{'i8' if pname == 'auto' else pname}", {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         roof = {"bound": "tensor", "kernel": "gram_dmma_kernel" if pname == "f64" else "gram_umma_kernel",
@@ -377,12 +372,12 @@ def run_ours(args):
                 "peak_source": note, "mma_issue_frac": mmas * ach / peak if peak else None,
                 "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / ms_step if ms_step else None,
                 "launches_per_step": tm["gemm_launches"] / k_steps,
-                "hbm_view": {"algorithmic_bytes": out_bytes + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 6.0}[pname] * 1024 * p,
+                "hbm_view": {"algorithmic_bytes": out_bytes + {"f64": 8.0, "i8": 2.0, "auto": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 6.0}[pname] * 1024 * p,
                              "achieved_gbs": out_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None,
                              "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]},
                 "column_kernel": {"kernel": "rank_columns_warp_kernel", "bound": "hbm", "ms_per_step": cols_ms,
-                                  "algorithmic_bytes": 8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 8.0}[pname] * 1024 * p,
-                                  "achieved_gbs": (8.0 * n * p + {"f64": 8.0, "i8": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 8.0}[pname] * 1024 * p) / (cols_ms * 1e-3) / 1e9 if cols_ms > 0 else None,
+                                  "algorithmic_bytes": 8.0 * n * p + {"f64": 8.0, "i8": 2.0, "auto": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 8.0}[pname] * 1024 * p,
+                                  "achieved_gbs": (8.0 * n * p + {"f64": 8.0, "i8": 2.0, "auto": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 8.0}[pname] * 1024 * p) / (cols_ms * 1e-3) / 1e9 if cols_ms > 0 else None,
                                   "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["src"]}}
         return {"value": P_total / (ms_step * 1e-3), "ms_per_step": ms_step, "roofline": roof, "clocks": clocks,
                 "gpu_launches": int(allsum(launches)), "dtype": DTYPES[pname], "path": PREC_NAMES[pname]}

@@ -13,8 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BIXCOR_LIB") or os.path.join(_HERE, "libbixcor.so")
 
 OK = 0
-ERR_NO_GPU, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+ERR_NO_GPU, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_INTERNAL = -1, -2, -3, -4, -5, -6
 PREC_F64, PREC_TF32X3, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_F16X3 = 0, 1, 2, 3, 4, 5
+PREC_AUTO = -1  # what the drop-in patch passes: exact-integer Gram for Spearman with n <= 1860, FP64 otherwise (env BIXCOR_PRECISION)
 TOM_V1, TOM_V2 = 1, 2
 RBF_GAUSSIAN, RBF_BUMP, RBF_INVERSE_QUADRATIC = 1, 2, 3
 
@@ -29,6 +30,7 @@ SIGNATURES = {
     "bixcor_last_error": (C.c_char_p, []),
     "bixcor_launch_count": (i64, []),
     "bixcor_set_fieller": (i32, [f64]),
+    "bixcor_debug_inject": (i32, [i32]),
     "bixcor_packed_len": (i64, [i64, i32]),
     "bixcor_packed_offset": (i64, [i64, i64, i32]),
     "bixcor_upper_to_dense": (i32, [ptr, i32, i64, ptr]),

@@ -7,20 +7,21 @@
 
 namespace bixcor {
 
-// k_i = sum_j |a_ij| (diagonal included, as the 4x4 known-answer test of
-// inst/tinytest/test_cor_modules.R:9-46 requires); unsigned TOM works on |A|
-// (calculate_tom takes abs() in R first, R/functions_stats.R:52-54), so the
-// matrix is replaced by its absolute value in place.  One CTA per column.
+// Connectivity of calc_tom (crate methods::coremo, call site src/rust/src/methods/r_coremo.rs:46-59; formulas
+// R/functions_stats.R:15-37), diagonal included as the 4x4 known-answer test of
+// inst/tinytest/test_cor_modules.R:9-46 requires.  signed: k_i = sum_j |a_ij|; unsigned: k_i = sum_j a_ij - the
+// matrix is used AS PASSED: abs() belongs to the R wrappers calculate_tom / calculate_tom_from_exp
+// (R/functions_stats.R:52-54,114-116), cor_module_tom (R/methods_coexp_cor.R:151) hands rs_tom the raw correlation.
+// One CTA per column.
 __global__ void __launch_bounds__(256)
-tom_connectivity_kernel(double* __restrict__ a, int64_t p, int64_t col0, int make_abs, double* __restrict__ kvec) {
+tom_connectivity_kernel(const double* __restrict__ a, int64_t p, int64_t col0, int take_abs, double* __restrict__ kvec) {
   __shared__ double scr[32];
   const int64_t i = col0 + blockIdx.x;
-  double* col = a + i * p;
+  const double* col = a + i * p;
   double s = 0.0;
   for (int64_t j = threadIdx.x; j < p; j += blockDim.x) {
-    const double v = fabs(col[j]);
-    s += v;
-    if (make_abs) col[j] = v;
+    const double v = col[j];
+    s += take_abs ? fabs(v) : v;
   }
   s = block_sum(s, scr);
   if (threadIdx.x == 0) kvec[i] = s;

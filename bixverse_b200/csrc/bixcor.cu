@@ -14,6 +14,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -31,20 +33,74 @@ namespace bixcor {
 // errors
 // ----------------------------------------------------------------------------
 static std::mutex g_err_mu;
-static std::string g_err = "";
+static char g_err[1024] = "";  // fixed storage: reporting an error never allocates (it may be reporting std::bad_alloc)
 static std::atomic<int64_t> g_launches{0};
 static double g_fieller = 1.06;
 
-static int fail(int code, const char* fmt, ...) {
+static int fail(int code, const char* fmt, ...) noexcept {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  g_err = buf;
+  try {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    memcpy(g_err, buf, sizeof g_err);
+  } catch (...) {
+  }
   return code;
 }
+
+// ---- exception barrier of the C ABI (include/bixcor.h: "No C++ exception crosses the ABI") -------------------
+// Every extern "C" body runs between API_BEGIN and API_END: std::bad_alloc -> BIXCOR_ERR_OOM, anything else ->
+// BIXCOR_ERR_INTERNAL, message in bixcor_last_error().  g_inject is the test hook behind bixcor_debug_inject().
+static std::atomic<int> g_inject{0};
+static void inject_point() {
+  const int what = g_inject.exchange(0);
+  if (what == 1) throw std::bad_alloc();
+  if (what == 2) throw std::runtime_error("injected failure (bixcor_debug_inject)");
+}
+static int api_exception(const char* fn) noexcept {
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    return fail(BIXCOR_ERR_OOM, "%s: host allocation failed (std::bad_alloc)", fn);
+  } catch (const std::exception& e) {
+    return fail(BIXCOR_ERR_INTERNAL, "%s: C++ exception stopped at the ABI: %s", fn, e.what());
+  } catch (...) {
+    return fail(BIXCOR_ERR_INTERNAL, "%s: unknown C++ exception stopped at the ABI", fn);
+  }
+}
+#define API_BEGIN \
+  try {           \
+    inject_point();
+#define API_END                       \
+  }                                   \
+  catch (...) {                       \
+    return api_exception(__func__);   \
+  }
+#define API_END_VAL(v)                \
+  }                                   \
+  catch (...) {                       \
+    api_exception(__func__);          \
+    return (v);                       \
+  }
+
+// Host worker threads that are always joined, also when a later std::thread constructor or the body between
+// creation and join throws (a joinable std::thread destroyed un-joined calls std::terminate).
+struct ThreadGroup {
+  std::vector<std::thread> th;
+  template <class F>
+  void run(F&& f) {
+    th.emplace_back(std::forward<F>(f));
+  }
+  void join() {
+    for (auto& t : th)
+      if (t.joinable()) t.join();
+    th.clear();
+  }
+  ~ThreadGroup() { join(); }
+};
 
 #define CU_TRY(expr)                                                                                    \
   do {                                                                                                  \
@@ -127,6 +183,7 @@ struct Ctx {
   Buffer panel;         // sparse dense panel
   Buffer sparse_in;     // staged CSR
   Buffer flag;          // one int: device-side overflow / range flags read back by the host
+  Buffer tile_sync;     // two words: arrival / bail-out counters of the long-K producer barrier (gram_umma.cuh)
   PinnedBuffer stage[2];
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
   // timing
@@ -178,6 +235,7 @@ static void ctx_destroy(Ctx* c) {
   c->panel.release();
   c->sparse_in.release();
   c->flag.release();
+  c->tile_sync.release();
   for (auto& b : c->stage) b.release();
   for (auto& kv : c->tile_cache)
     if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
@@ -229,7 +287,10 @@ struct Timed {
     if (cat == T_GEMM) c->last_gemm_launches++;
     if (!e0) return;
     cudaEventRecord(e1, c->compute);
-    c->timed.emplace_back(cat, e0, e1);
+    try {
+      c->timed.emplace_back(cat, e0, e1);
+    } catch (...) {  // (a destructor must not throw: the sample is dropped)
+    }
   }
 };
 static void timing_collect(Ctx* c) {
@@ -384,6 +445,41 @@ static int check_precision(int precision, int spearman, int64_t n) {
   return fail(BIXCOR_ERR_INVALID, "unknown precision %d", precision);
 }
 
+// BIXCOR_PREC_AUTO (what the drop-in patch passes).  The reference's API has no precision argument
+// (rs_cor_upper_triangle(x, spearman, shift), src/rust/src/base/r_cors_similarity.rs:251-268), so the library picks the
+// fastest path that provably keeps the FP64 contract: exact-integer tcgen05 Gram for Spearman with n <= 1860, FP64
+// DMMA otherwise; env BIXCOR_PRECISION replaces the rule process-wide (opt-in to the <= 1e-5 fast paths from R).
+static int env_precision() {
+  const char* v = getenv("BIXCOR_PRECISION");
+  if (!v || !*v) return BIXCOR_PREC_AUTO;
+  if (!strcmp(v, "f64")) return BIXCOR_PREC_F64;
+  if (!strcmp(v, "tf32")) return BIXCOR_PREC_TF32X3;
+  if (!strcmp(v, "f16")) return BIXCOR_PREC_F16X3;
+  if (!strcmp(v, "i8")) return BIXCOR_PREC_I8EXACT;
+  if (!strcmp(v, "ozaki")) return BIXCOR_PREC_OZAKI;
+  if (!strcmp(v, "ozaki4")) return BIXCOR_PREC_OZAKI4;
+  return BIXCOR_PREC_AUTO;
+}
+static int resolve_precision(int precision, int spearman, int64_t n) {
+  if (precision != BIXCOR_PREC_AUTO) return precision;
+  int want = env_precision();
+  const bool i8_ok = spearman && n <= 1860;
+  if (want == BIXCOR_PREC_I8EXACT && !i8_ok) want = BIXCOR_PREC_AUTO;
+  if (want == BIXCOR_PREC_AUTO) return i8_ok ? BIXCOR_PREC_I8EXACT : BIXCOR_PREC_F64;
+  return want;
+}
+// precision of an A * A product (TOM) or a sparse Gram: no integer-exact form exists for those
+static int resolve_precision_float(int precision) {
+  if (precision != BIXCOR_PREC_AUTO) return precision;
+  const int want = env_precision();
+  return (want == BIXCOR_PREC_AUTO || want == BIXCOR_PREC_I8EXACT) ? BIXCOR_PREC_F64 : want;
+}
+// precision of the correlation that feeds a TOM of precision `tom_precision` (as given by the caller)
+static int tom_cor_precision(int tom_precision, int spearman, int64_t n) {
+  if (tom_precision == BIXCOR_PREC_AUTO) return resolve_precision(BIXCOR_PREC_AUTO, spearman, n);
+  return (is_split_float(tom_precision) || is_ozaki(tom_precision)) ? tom_precision : BIXCOR_PREC_F64;
+}
+
 // Spearman column kernel dispatch: warp-per-gene register sort for n <= 1024, CTA shared-memory sort above.
 static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, const ColumnOut& co) {
   if (n <= 1024) {
@@ -517,6 +613,12 @@ static int launch_dmma(Ctx* c, const dmma::Params& P, int ntiles) {
   return BIXCOR_OK;
 }
 
+// per-context counters of the long-K producer barrier (nullptr when the allocation fails: the barrier is then off)
+static unsigned* tile_sync_words(Ctx* c) {
+  if (c->tile_sync.reserve(256) != BIXCOR_OK) return nullptr;
+  return (unsigned*)c->tile_sync.ptr;
+}
+
 static EpiParams make_epi(int64_t p) {
   EpiParams e;
   memset(&e, 0, sizeof e);
@@ -563,7 +665,7 @@ static int launch_gram_ozaki(Ctx* c, const Operand& a, int64_t p, const int2* ti
     ea.scale = std::ldexp(1.0, -7 * (2 * ab[0] + 2 * ab[1] + 4));
     Timed tm(c, T_GEMM);
     if (umma::launch_gram_umma(c->compute, c->sm_count, umma::KIND_I8, EPI_ACCUM, umma_pairs(a.precision, epi) ? 2 : 1, p, a.oz, a.ozK, nullptr, nullptr, 0,
-                               nullptr, tiles, ntiles, ea, OZ_SLICES, 2 * ab[0], 2 * ab[1]) != 0)
+                               nullptr, tiles, ntiles, ea, OZ_SLICES, 2 * ab[0], 2 * ab[1], tile_sync_words(c)) != 0)
       return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
     g_launches++;
   }
@@ -621,7 +723,7 @@ static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, co
   const void* pl1 = b ? (kind == umma::KIND_I8 ? (const void*)b->i8 : (const void*)b->f32) : nullptr;
   Timed tm(c, T_GEMM);
   if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, umma_pairs(a.precision, epi) ? 2 : 1, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
-                             b ? b->inv_norm : nullptr, tiles, ntiles, e) != 0)
+                             b ? b->inv_norm : nullptr, tiles, ntiles, e, 2, 0, 0, tile_sync_words(c)) != 0)
     return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
   g_launches++;
   return BIXCOR_OK;
@@ -647,15 +749,15 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     memcpy(dst, src, bytes);
     return;
   }
-  std::vector<std::thread> th;
+  ThreadGroup tg;
   const size_t chunk = ((bytes + nthr - 1) / nthr + 63) & ~size_t(63);
   for (int t = 0; t < nthr; ++t) {
     const size_t o = (size_t)t * chunk;
     if (o >= bytes) break;
     const size_t len = std::min(chunk, bytes - o);
-    th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, len); });
+    tg.run([=] { memcpy((char*)dst + o, (const char*)src + o, len); });
   }
-  for (auto& t : th) t.join();
+  tg.join();
 }
 
 constexpr size_t kStageBytes = size_t(64) << 20;
@@ -741,8 +843,14 @@ static int validate_rows(int64_t p, int64_t row_begin, int64_t row_end) {
   if (row_begin < 0 || row_end > p || row_begin > row_end)
     return fail(BIXCOR_ERR_INVALID, "bad row range [%lld,%lld) for p = %lld", (long long)row_begin, (long long)row_end,
                 (long long)p);
+  if (row_begin == row_end) return BIXCOR_OK;  // an empty shard (small p, many ranks) is a no-op wherever it starts
   if (row_begin % kTile != 0)
     return fail(BIXCOR_ERR_INVALID, "row_begin (%lld) must be a multiple of %d", (long long)row_begin, kTile);
+  // tiles are 128-row blocks and the epilogues guard rows with i < p only: a ragged row_end inside the matrix would
+  // write rows [row_end, next block boundary) past the caller's slice
+  if (row_end % kTile != 0 && row_end != p)
+    return fail(BIXCOR_ERR_INVALID, "row_end (%lld) must be a multiple of %d or p (%lld)", (long long)row_end, kTile,
+                (long long)p);
   return BIXCOR_OK;
 }
 
@@ -793,6 +901,7 @@ static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, i
                               double* h_out, const RbfSpec* rbf = nullptr) {
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (row_begin == row_end) return BIXCOR_OK;
+  precision = resolve_precision(precision, spearman, n);
   Operand op;
   RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
   return dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, d_out, pipe, h_out, rbf);
@@ -812,6 +921,7 @@ static int dev_diffcor_rows(Ctx* c, const double* d_xa, int64_t na, const double
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (na < 4 || nb < 4) return fail(BIXCOR_ERR_INVALID, "differential correlation needs n_a, n_b >= 4");
   if (row_begin == row_end) return BIXCOR_OK;
+  precision = resolve_precision(precision, spearman, std::max(na, nb));
   Operand a, b;
   RC_TRY(prepare_operand(c, d_xa, na, p, spearman, precision, 0, &a));
   RC_TRY(prepare_operand(c, d_xb, nb, p, spearman, precision, 1, &b));
@@ -860,6 +970,7 @@ static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spe
                         int precision, int64_t row_begin, int64_t row_end, double* d_app) {
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (row_begin == row_end) return BIXCOR_OK;
+  precision = resolve_precision(precision, spearman, n);
   Operand op;
   RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
   const bool full = (row_begin == 0 && row_end == p);
@@ -874,12 +985,12 @@ static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spe
   return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_DENSE, e, nullptr, row_begin, row_end);
 }
 
-static int dev_tom_connectivity(Ctx* c, double* d_a, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
+static int dev_tom_connectivity(Ctx* c, const double* d_a, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
                                 double* d_k) {
   if (row_begin < 0 || row_end > p || row_begin > row_end) return fail(BIXCOR_ERR_INVALID, "bad row range");
   if (row_begin == row_end) return BIXCOR_OK;
   Timed tm(c, T_OTHER);
-  tom_connectivity_kernel<<<(unsigned)(row_end - row_begin), 256, 0, c->compute>>>(d_a, p, row_begin, signed_ ? 0 : 1, d_k);
+  tom_connectivity_kernel<<<(unsigned)(row_end - row_begin), 256, 0, c->compute>>>(d_a, p, row_begin, signed_ ? 1 : 0, d_k);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return BIXCOR_OK;
@@ -888,11 +999,11 @@ static int dev_tom_connectivity(Ctx* c, double* d_a, int64_t p, int signed_, int
 // The TOM GEMM operand is the affinity matrix itself (A symmetric: column i == row i).
 static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p, int signed_, int version,
                         int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out) {
-  (void)signed_;  // |A| was substituted in place by the connectivity pass when unsigned
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
     return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
   if (row_begin == row_end) return BIXCOR_OK;
+  precision = resolve_precision_float(precision);
   RC_TRY(c->vec.reserve(sizeof(double) * (size_t)p * 4));
   double* d_diag = (double*)c->vec.ptr;  // first p entries: diagonal
   {
@@ -966,6 +1077,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   e.kvec = d_k;
   e.dvec = d_diag;
   e.tom_v2 = (version == BIXCOR_TOM_V2);
+  e.tom_signed = signed_ ? 1 : 0;
   e.tom_packed = packed ? 1 : 0;
   // non-packed strip mode writes into out + 0 with absolute (i*p + j) addressing
   return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_TOM, e, nullptr, row_begin, row_end);
@@ -973,6 +1085,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
 
 static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
                                  int64_t cells, int64_t genes, int precision, double* d_gram, double* d_colsum) {
+  precision = resolve_precision_float(precision);
   if (precision != BIXCOR_PREC_F64 && !is_split_float(precision))
     return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram runs on BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3 or BIXCOR_PREC_F16X3");
   const bool fast = is_split_float(precision), half = precision == BIXCOR_PREC_F16X3;
@@ -1056,17 +1169,21 @@ static int for_each_device(F fn) {
     return fn(g_ctx[0], 0, 1);
   }
   std::vector<int> rcs(nd, BIXCOR_OK);
-  std::vector<std::thread> th;
+  ThreadGroup tg;
   for (int d = 0; d < nd; ++d)
-    th.emplace_back([&, d] {
-      if (cudaSetDevice(g_ctx[d]->device) != cudaSuccess) {
-        rcs[d] = fail(BIXCOR_ERR_CUDA, "cudaSetDevice(%d) failed", g_ctx[d]->device);
-        return;
+    tg.run([&, d] {
+      try {  // an exception must not leave a worker thread (std::terminate); it becomes this device's return code
+        if (cudaSetDevice(g_ctx[d]->device) != cudaSuccess) {
+          rcs[d] = fail(BIXCOR_ERR_CUDA, "cudaSetDevice(%d) failed", g_ctx[d]->device);
+          return;
+        }
+        call_begin(g_ctx[d]);
+        rcs[d] = fn(g_ctx[d], d, nd);
+      } catch (...) {
+        rcs[d] = api_exception("device worker");
       }
-      call_begin(g_ctx[d]);
-      rcs[d] = fn(g_ctx[d], d, nd);
     });
-  for (auto& t : th) t.join();
+  tg.join();
   for (int rc : rcs)
     if (rc != BIXCOR_OK) return rc;
   return BIXCOR_OK;
@@ -1104,13 +1221,13 @@ static void parallel_rows(int64_t p, F fn) {
     fn(0, p);
     return;
   }
-  std::vector<std::thread> th;
+  ThreadGroup tg;
   for (int t = 0; t < nthr; ++t) {
     int64_t r0, r1;
     shard_rows_impl(p, 1, nthr, t, &r0, &r1);
-    if (r1 > r0) th.emplace_back([=] { fn(r0, r1); });
+    if (r1 > r0) tg.run([=] { fn(r0, r1); });
   }
-  for (auto& t : th) t.join();
+  tg.join();
 }
 
 // Column c of the symmetric matrix behind a packed vector, visited in row order: rows above the diagonal come from
@@ -1139,34 +1256,48 @@ static void parallel_cols(int64_t p, F fn) {
     fn(0, p);
     return;
   }
-  std::vector<std::thread> th;
+  ThreadGroup tg;
   for (int t = 0; t < nthr; ++t) {
     const int64_t c0 = p * t / nthr, c1 = p * (t + 1) / nthr;
-    if (c1 > c0) th.emplace_back([=] { fn(c0, c1); });
+    if (c1 > c0) tg.run([=] { fn(c0, c1); });
   }
-  for (auto& t : th) t.join();
+  tg.join();
 }
 
 extern "C" {
 
 const char* bixcor_last_error(void) {
-  static thread_local std::string copy;
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  copy = g_err;
-  return copy.c_str();
+  static thread_local char copy[sizeof g_err];
+  try {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    memcpy(copy, g_err, sizeof copy);
+  } catch (...) {
+    copy[0] = 0;
+  }
+  copy[sizeof copy - 1] = 0;
+  return copy;
+}
+
+/* test hook: the next API call throws from inside its body (1 = std::bad_alloc, 2 = std::runtime_error) */
+int bixcor_debug_inject(int what) {
+  g_inject.store(what);
+  return BIXCOR_OK;
 }
 
 int64_t bixcor_launch_count(void) { return g_launches.load(); }
 
 int bixcor_set_fieller(double c) {
+  API_BEGIN
   if (!(c > 0.0)) return fail(BIXCOR_ERR_INVALID, "Fieller factor must be positive");
   g_fieller = c;
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_init(int n_gpus) { return bixcor_init_devices(0, n_gpus); }
 
 int bixcor_init_devices(int first_device, int n_gpus) {
+  API_BEGIN
   std::lock_guard<std::mutex> lk(g_init_mu);
   if (!g_ctx.empty()) {
     if ((int)g_ctx.size() == n_gpus && g_ctx[0]->device == first_device) return BIXCOR_OK;
@@ -1207,26 +1338,35 @@ int bixcor_init_devices(int first_device, int n_gpus) {
       cudaGetLastError();  // "already enabled" is fine
     }
   return BIXCOR_OK;
+  API_END
 }
 
 void bixcor_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g_init_mu);
-  for (auto* c : g_ctx) ctx_destroy(c);
-  g_ctx.clear();
+  try {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    for (auto* c : g_ctx) ctx_destroy(c);
+    g_ctx.clear();
+  } catch (...) {
+  }
 }
 
 int bixcor_timing_enable(int on) {
+  API_BEGIN
   g_timing = on != 0;
   for (auto* c : g_ctx) timing_reset(c);
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_dev_set_async(int on) {
+  API_BEGIN
   g_async = on != 0;
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_dev_set_stream(void* stream, int external) {
+  API_BEGIN
   RC_TRY(ensure_init());
   Ctx* c = g_ctx[0];
   CU_TRY(cudaSetDevice(c->device));
@@ -1240,18 +1380,22 @@ int bixcor_dev_set_stream(void* stream, int external) {
     c->owns_compute = true;
   }
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_dev_synchronize(void) {
+  API_BEGIN
   RC_TRY(ensure_init());
   for (auto* c : g_ctx) {
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaStreamSynchronize(c->compute));
   }
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_last_timing(double* what4) {
+  API_BEGIN
   if (g_ctx.empty()) return fail(BIXCOR_ERR_INVALID, "not initialised");
   for (auto* c : g_ctx) {
     cudaSetDevice(c->device);
@@ -1265,6 +1409,7 @@ int bixcor_last_timing(double* what4) {
     what4[3] = std::max(what4[3], (double)c->last_gemm_launches);
   }
   return BIXCOR_OK;
+  API_END
 }
 
 // ---- packed helpers ---------------------------------------------------------
@@ -1272,6 +1417,7 @@ int64_t bixcor_packed_len(int64_t p, int shift) { return shift ? p * (p - 1) / 2
 int64_t bixcor_packed_offset(int64_t i, int64_t p, int shift) { return packed_row_offset(i, p, shift ? 1 : 0); }
 
 int bixcor_upper_to_dense(const double* packed, int shift, int64_t p, double* out) {
+  API_BEGIN
   if (!packed || !out || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
   const int s = shift ? 1 : 0;
   parallel_rows(p, [=](int64_t r0, int64_t r1) {
@@ -1286,9 +1432,11 @@ int bixcor_upper_to_dense(const double* packed, int shift, int64_t p, double* ou
     }
   });
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_dense_to_upper(const double* dense, int shift, int64_t p, double* out) {
+  API_BEGIN
   if (!dense || !out || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
   const int s = shift ? 1 : 0;
   parallel_rows(p, [=](int64_t r0, int64_t r1) {
@@ -1298,9 +1446,11 @@ int bixcor_dense_to_upper(const double* dense, int shift, int64_t p, double* out
     }
   });
   return BIXCOR_OK;
+  API_END
 }
 
 int64_t bixcor_upper_to_sparse_nnz(const double* packed, int shift, int64_t p) {
+  API_BEGIN
   if (!packed || p < 0) return -1;
   const int s = shift ? 1 : 0;
   std::vector<int64_t> part(64, 0);
@@ -1318,8 +1468,10 @@ int64_t bixcor_upper_to_sparse_nnz(const double* packed, int shift, int64_t p) {
   int64_t total = 0;
   for (int64_t v : part) total += v;
   return total;
+  API_END_VAL(-1)
 }
 int bixcor_upper_to_sparse(const double* packed, int shift, int64_t p, int64_t* indptr, int32_t* indices, double* data) {
+  API_BEGIN
   if (!packed || !indptr || p < 0) return fail(BIXCOR_ERR_INVALID, "null pointer / bad p");
   const int s = shift ? 1 : 0;
   // pass 1: non-zeros per column (threads over column blocks), prefix sum, pass 2: every column fills its own range
@@ -1348,13 +1500,16 @@ int bixcor_upper_to_sparse(const double* packed, int shift, int64_t p, int64_t* 
     }
   });
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_shard_rows(int64_t p, int shift, int world, int rank, int64_t* row_begin, int64_t* row_end) {
+  API_BEGIN
   if (world < 1 || rank < 0 || rank >= world || p < 0 || !row_begin || !row_end)
     return fail(BIXCOR_ERR_INVALID, "bad shard arguments");
   shard_rows_impl(p, shift ? 1 : 0, world, rank, row_begin, row_end);
   return BIXCOR_OK;
+  API_END
 }
 
 // ---- device-pointer entry points -------------------------------------------
@@ -1365,6 +1520,7 @@ int bixcor_shard_rows(int64_t p, int shift, int world, int rank, int64_t* row_be
   call_begin(c);
 
 int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_out) {
+  API_BEGIN
   DEV_PROLOGUE();
   if (n < 1 || p < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
   if (n > 16384) return fail(BIXCOR_ERR_UNSUPPORTED, "rank kernel supports n <= 16384");
@@ -1379,14 +1535,17 @@ int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_o
     RC_TRY(launch_rank_kernel(c, d_x, n, p, co));
   }
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_cor_upper_rows(const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
                               int precision, int64_t row_begin, int64_t row_end, double* d_out) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_cor_upper_rows(c, d_x, n, p, spearman, shift ? 1 : 0, beta, precision, row_begin, row_end, d_out, nullptr,
                             nullptr));
   return finish_dev(c);
+  API_END
 }
 
 int64_t bixcor_dev_operand_row_bytes(int64_t n, int precision) {
@@ -1396,12 +1555,15 @@ int64_t bixcor_dev_operand_row_bytes(int64_t n, int precision) {
 
 int bixcor_dev_build_operand(const double* d_x, int64_t n, int64_t p, int spearman, int precision, int64_t gene_begin,
                              int64_t gene_end, void* d_operand, double* d_inv_norm) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(build_operand(c, d_x, n, p, spearman, precision, gene_begin, gene_end, d_operand, d_inv_norm));
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_operand_inv_norm(const void* d_operand, int64_t n, int64_t p, int precision, double* d_inv_norm) {
+  API_BEGIN
   DEV_PROLOGUE();
   if (!d_operand || !d_inv_norm) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (precision != BIXCOR_PREC_I8EXACT) return finish_dev(c);  // the other operands are unit-norm already
@@ -1414,10 +1576,12 @@ int bixcor_dev_operand_inv_norm(const void* d_operand, int64_t n, int64_t p, int
   }
   CU_TRY(cudaGetLastError());
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p, int precision,
                                  int shift, double beta, int64_t row_begin, int64_t row_end, double* d_out) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (!exchangeable(precision)) return fail(BIXCOR_ERR_INVALID, "operand exchange supports precisions 0..2 and 5 (got %d)", precision);
@@ -1427,11 +1591,13 @@ int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm
     RC_TRY(dev_cor_upper_rows_op(c, op, p, shift ? 1 : 0, beta, row_begin, row_end, d_out, nullptr, nullptr));
   }
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
                                          int precision, int shift, double beta, int64_t row_begin,
                                          int64_t row_end, double* h_out_slice) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (!d_operand || !h_out_slice) return fail(BIXCOR_ERR_INVALID, "null pointer");
@@ -1446,61 +1612,77 @@ int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_
   RC_TRY(dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, (double*)c->out.ptr, &pipe, h_out_slice));
   RC_TRY(finish(c));
   return pipe.finish();
+  API_END
 }
 
 int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_affinity(c, d_x, n, p, spearman, 1.0, 1, precision, 0, p, d_out));
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p, int spearman,
                             int precision, int64_t row_begin, int64_t row_end, double* d_r_a, double* d_r_b,
                             double* d_z, double* d_pval) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_diffcor_rows(c, d_xa, na, d_xb, nb, p, spearman, precision, row_begin, row_end, d_r_a, d_r_b, d_z, d_pval,
                           nullptr, nullptr, nullptr, nullptr, nullptr));
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_affinity_cols(const double* d_x, int64_t n, int64_t p, int spearman, int signed_, double beta,
                              int precision, int64_t row_begin, int64_t row_end, double* d_a_pp) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_affinity(c, d_x, n, p, spearman, beta, signed_ ? 1 : 0, precision, row_begin, row_end, d_a_pp));
   return finish_dev(c);
+  API_END
 }
 
-int bixcor_dev_tom_connectivity(double* d_a_pp, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
+int bixcor_dev_tom_connectivity(const double* d_a_pp, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
                                 double* d_k) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_tom_connectivity(c, d_a_pp, p, signed_, row_begin, row_end, d_k));
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_tom_rows(const double* d_a_pp, const double* d_k, int64_t p, int signed_, int version, int precision,
                         int packed, int64_t row_begin, int64_t row_end, double* d_out) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_tom_rows(c, d_a_pp, d_k, p, signed_, version, precision, packed, row_begin, row_end, d_out));
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_sparse_gram_accumulate(const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
                                       int64_t cells, int64_t genes, int precision, double* d_gram_pp,
                                       double* d_colsum) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_sparse_accumulate(c, d_indptr, d_indices, d_data, cells, genes, precision, d_gram_pp, d_colsum));
   return finish_dev(c);
+  API_END
 }
 
 int bixcor_dev_sparse_gram_finalise(const double* d_gram_pp, const double* d_colsum, int64_t total_cells,
                                     int64_t genes, double* d_out_packed) {
+  API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_sparse_finalise(c, d_gram_pp, d_colsum, total_cells, genes, d_out_packed));
   return finish_dev(c);
+  API_END
 }
 
 // ---- host-pointer entry points ---------------------------------------------
 int bixcor_rank_columns(const double* x, int64_t n, int64_t p, double* out) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!x || !out) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (n == 0 || p == 0) return BIXCOR_OK;
@@ -1515,6 +1697,7 @@ int bixcor_rank_columns(const double* x, int64_t n, int64_t p, double* out) {
   D2HPipe pipe(c, out);
   RC_TRY(pipe.push(out, c->out.ptr, bytes, nullptr));
   return pipe.finish();
+  API_END
 }
 
 static int host_shape_check(const void* x, int64_t n, int64_t p, const void* out) {
@@ -1527,6 +1710,7 @@ static int host_shape_check(const void* x, int64_t n, int64_t p, const void* out
 
 int bixcor_cor_upper_rows(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta, int precision,
                           int64_t row_begin, int64_t row_end, double* out_slice) {
+  API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(x, n, p, out_slice));
   RC_TRY(validate_rows(p, row_begin, row_end));
@@ -1555,14 +1739,18 @@ int bixcor_cor_upper_rows(const double* x, int64_t n, int64_t p, int spearman, i
     RC_TRY(finish(c));
     return pipe.finish();
   });
+  API_END
 }
 
 int bixcor_cor_upper(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta, int precision,
                      double* out_packed) {
+  API_BEGIN
   return bixcor_cor_upper_rows(x, n, p, spearman, shift, beta, precision, 0, p, out_packed);
+  API_END
 }
 
 int bixcor_cor_dense(const double* x, int64_t n, int64_t p, int spearman, int precision, double* out_pp) {
+  API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(x, n, p, out_pp));
   Ctx* c = g_ctx[0];
@@ -1577,11 +1765,13 @@ int bixcor_cor_dense(const double* x, int64_t n, int64_t p, int spearman, int pr
   D2HPipe pipe(c, out_pp);
   RC_TRY(pipe.push(out_pp, c->out.ptr, out_bytes, nullptr));
   return pipe.finish();
+  API_END
 }
 
 int bixcor_diffcor_rows(const double* xa, int64_t na, const double* xb, int64_t nb, int64_t p, int spearman,
                         int precision, int64_t row_begin, int64_t row_end, double* r_a, double* r_b, double* z,
                         double* pval) {
+  API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(xa, na, p, r_a));
   RC_TRY(host_shape_check(xb, nb, p, r_b));
@@ -1614,11 +1804,14 @@ int bixcor_diffcor_rows(const double* xa, int64_t na, const double* xb, int64_t 
     RC_TRY(finish(c));
     return pipe.finish();
   });
+  API_END
 }
 
 int bixcor_diffcor(const double* xa, int64_t na, const double* xb, int64_t nb, int64_t p, int spearman, int precision,
                    double* r_a, double* r_b, double* z, double* pval) {
+  API_BEGIN
   return bixcor_diffcor_rows(xa, na, xb, nb, p, spearman, precision, 0, p, r_a, r_b, z, pval);
+  API_END
 }
 
 static int tom_common(Ctx* c, double* d_a, int64_t p, int signed_, int version, int precision, int packed,
@@ -1672,7 +1865,7 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
   const int nd_all = (int)g_ctx.size();
   PhaseBarrier bar(nd_all);
   std::vector<double> k_host((size_t)p, 0.0);
-  const int cor_prec = (is_split_float(precision) || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
+  const int cor_prec = tom_cor_precision(precision, spearman, n);
   return for_each_device([&](Ctx* c, int d, int nd) -> int {
     int64_t c0, c1;
     even_slab(p, nd, d, &c0, &c1);
@@ -1736,6 +1929,7 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
 }
 
 int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int precision, double* out_pp) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!a_pp || !out_pp) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (p < 1) return fail(BIXCOR_ERR_INVALID, "p must be >= 1");
@@ -1750,12 +1944,14 @@ int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int prec
   RC_TRY(c->out2.reserve(bytes));
   RC_TRY(h2d(c, c->out2.ptr, a_pp, bytes, c->compute));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, 0, out_pp);
+  API_END
 }
 
 // cor_module_tom in one call (R/methods_coexp_cor.R:118-164: get_sym_matrix -> rs_tom -> rs_dense_to_upper_triangle):
 // packed correlation in, packed (shift = 1) TOM out; the dense matrices only ever exist in HBM.
 int bixcor_tom_packed(const double* packed_in, int shift_in, int64_t p, int signed_, int version, int precision,
                       double* out_packed) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!packed_in || !out_packed) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (p < 2) return fail(BIXCOR_ERR_INVALID, "p must be >= 2");
@@ -1778,10 +1974,12 @@ int bixcor_tom_packed(const double* packed_in, int shift_in, int64_t p, int sign
   }
   CU_TRY(cudaGetLastError());
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, 1, out_packed);
+  API_END
 }
 
 int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int signed_, int version, double beta,
                         int precision, int packed, double* out) {
+  API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(x, n, p, out));
   if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
@@ -1796,10 +1994,11 @@ int bixcor_tom_from_exp(const double* x, int64_t n, int64_t p, int spearman, int
   RC_TRY(c->out2.reserve(sizeof(double) * (size_t)p * p));
   RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
   // the correlation feeding the TOM is always the exact / requested-precision Gram
-  const int cor_prec = (is_split_float(precision) || is_ozaki(precision)) ? precision : BIXCOR_PREC_F64;
+  const int cor_prec = tom_cor_precision(precision, spearman, n);
   RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, beta, signed_ ? 1 : 0, cor_prec, 0, p,
                       (double*)c->out2.ptr));
   return tom_common(c, (double*)c->out2.ptr, p, signed_, version, precision, packed, out);
+  API_END
 }
 
 // ---- sibling Gram kernels ("next" rows of SURVEY 8f) ---------------------------------------------
@@ -1832,11 +2031,15 @@ static int dense_symmetric(const double* x, int64_t n, int64_t p, int norm_mode,
 }
 
 int bixcor_covariance(const double* x, int64_t n, int64_t p, double* out_pp) {
+  API_BEGIN
   return dense_symmetric(x, n, p, 1, 1.0 / (double)(n - 1), 0, out_pp);
+  API_END
 }
 
 int bixcor_cos(const double* x, int64_t n, int64_t p, double* out_pp) {
+  API_BEGIN
   return dense_symmetric(x, n, p, 2, 1.0, 0, out_pp);
+  API_END
 }
 
 // cor2 on the device: leaves the column-major p x q matrix cor(x_i, y_j) in c->out
@@ -1863,6 +2066,7 @@ static int dev_cor2(Ctx* c, const double* x, int64_t n, int64_t p, const double*
 }
 
 int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int spearman, double* out_pq) {
+  API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(x, n, p, out_pq));
   RC_TRY(host_shape_check(y, n, q, out_pq));
@@ -1874,6 +2078,7 @@ int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t 
   D2HPipe pipe(c, out_pq);
   RC_TRY(pipe.push(out_pq, c->out.ptr, sizeof(double) * (size_t)p * q, nullptr));
   return pipe.finish();
+  API_END
 }
 
 // rs_rbh_cor for one (origin, target) pair of module matrices already restricted to their shared features
@@ -1882,6 +2087,7 @@ int bixcor_cor2(const double* x, int64_t n, int64_t p, const double* y, int64_t 
 int bixcor_rbh_cor(const double* x, int64_t n, int64_t p, const double* y, int64_t q, int k_best, int spearman,
                    double min_similarity, int32_t* out_origin, int32_t* out_target, double* out_sim, int64_t capacity,
                    int64_t* n_hits) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!n_hits) return fail(BIXCOR_ERR_INVALID, "null pointer");
   *n_hits = 0;
@@ -1923,9 +2129,11 @@ int bixcor_rbh_cor(const double* x, int64_t n, int64_t p, const double* y, int64
   *n_hits = cnt;
   if (cnt > capacity) return fail(BIXCOR_ERR_INVALID, "rbh: %lld hits exceed the capacity %lld", (long long)cnt, (long long)capacity);
   return BIXCOR_OK;
+  API_END
 }
 
 int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!cov_pp || !out_pp) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (p < 1) return fail(BIXCOR_ERR_INVALID, "p must be >= 1");
@@ -1947,10 +2155,12 @@ int bixcor_cov2cor(const double* cov_pp, int64_t p, double* out_pp) {
   D2HPipe pipe(c, out_pp);
   RC_TRY(pipe.push(out_pp, c->out.ptr, bytes, nullptr));
   return pipe.finish();
+  API_END
 }
 
 // ---- RBF affinities and CoReMo stability ("next" rows 1-2 of SURVEY 8f) --------------------------
 int bixcor_rbf(const double* x, int64_t len, double epsilon, int rbf_type, double* out) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (len < 0 || (len > 0 && (!x || !out))) return fail(BIXCOR_ERR_INVALID, "null pointer / bad length");
   RC_TRY(check_rbf(rbf_type, epsilon));
@@ -1974,10 +2184,12 @@ int bixcor_rbf(const double* x, int64_t len, double epsilon, int rbf_type, doubl
   D2HPipe pipe(c, out);
   RC_TRY(pipe.push(out, c->out.ptr, bytes, nullptr));
   return pipe.finish();
+  API_END
 }
 
 int bixcor_rbf_iterate_epsilons(const double* dist_packed, int64_t p, int shift, const double* epsilons, int n_eps,
                                 int rbf_type, double* out_p_x_neps) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!dist_packed || !epsilons || !out_p_x_neps) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (p < 1 || n_eps < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
@@ -2012,10 +2224,12 @@ int bixcor_rbf_iterate_epsilons(const double* dist_packed, int64_t p, int shift,
   D2HPipe pipe(c, out_p_x_neps);
   RC_TRY(pipe.push(out_p_x_neps, c->out.ptr, sizeof(double) * (size_t)p * n_eps, nullptr));
   return pipe.finish();
+  API_END
 }
 
 int bixcor_cor_upper_rbf(const double* x, int64_t n, int64_t p, int spearman, int shift, double epsilon, int rbf_type,
                          int complement, int precision, double* out_packed) {
+  API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(x, n, p, out_packed));
   RC_TRY(check_rbf(rbf_type, epsilon));
@@ -2036,10 +2250,12 @@ int bixcor_cor_upper_rbf(const double* x, int64_t n, int64_t p, int spearman, in
                             (double*)c->out.ptr, &pipe, out_packed, &rbf));
   RC_TRY(finish(c));
   return pipe.finish();
+  API_END
 }
 
 int bixcor_coremo_stability(const double* x, int64_t n, int64_t p, const int32_t* indices_1based, int n_idx,
                             double epsilon, int rbf_type, int spearman, int precision, double* const* outs) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!x || !indices_1based || !outs) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (n < 3) return fail(BIXCOR_ERR_INVALID, "need at least 3 samples to leave one out (n = %lld)", (long long)n);
@@ -2090,6 +2306,7 @@ int bixcor_coremo_stability(const double* x, int64_t n, int64_t p, const int32_t
   }
   RC_TRY(finish(c));
   return pipe.finish();
+  API_END
 }
 
 // rs_pairwise_gene_cors_mc (src/rust/src/meta_cell/r_mc_processing.rs:258-283)
@@ -2217,8 +2434,10 @@ static int sparse_pairwise_impl(const int64_t* indptr, const int32_t* indices, c
 int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                                int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
                                int64_t n_pairs, int spearman, double* out) {
+  API_BEGIN
   return sparse_pairwise_impl(indptr, indices, data, cells, genes, is_csr, nullptr, 0, gene_idx1, gene_idx2, n_pairs, spearman,
                               out);
+  API_END
 }
 
 // rs_pairwise_gene_cors (src/rust/src/single_cell/r_sc_processing.rs:474-499): as above over the listed cells only
@@ -2226,13 +2445,16 @@ int bixcor_sparse_pairwise_cor_cells(const int64_t* indptr, const int32_t* indic
                                      int64_t genes, int is_csr, const int32_t* cells_to_keep, int64_t n_keep,
                                      const int32_t* gene_idx1, const int32_t* gene_idx2, int64_t n_pairs, int spearman,
                                      double* out) {
+  API_BEGIN
   if (!cells_to_keep) return fail(BIXCOR_ERR_INVALID, "null pointer");
   return sparse_pairwise_impl(indptr, indices, data, cells, genes, is_csr, cells_to_keep, n_keep, gene_idx1, gene_idx2, n_pairs,
                               spearman, out);
+  API_END
 }
 
 int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                            int64_t genes, int precision, double* out_packed) {
+  API_BEGIN
   RC_TRY(ensure_init());
   if (!indptr || !out_packed) return fail(BIXCOR_ERR_INVALID, "null pointer");
   if (cells < 2 || genes < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
@@ -2266,6 +2488,7 @@ int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const 
   D2HPipe pipe(c, out_packed);
   RC_TRY(pipe.push(out_packed, c->out.ptr, out_bytes, nullptr));
   return pipe.finish();
+  API_END
 }
 
 }  // extern "C"

@@ -39,6 +39,7 @@ struct EpiParams {
   const double* kvec;  // TOM: connectivity
   const double* dvec;  // TOM: diagonal of A
   int tom_v2;
+  int tom_signed;   // signed: |a_ij| in the denominators; unsigned: a_ij as passed (R/functions_stats.R:15-31)
   int tom_packed;
   // RBF affinity transform (crate core::math::rbf behind src/rust/src/base/r_rbf.rs and the
   // distance -> affinity step of rs_coremo_stability, src/rust/src/methods/r_coremo.rs:211-226)
@@ -159,7 +160,7 @@ __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R,
     return v;
   } else {  // EPI_TOM
     const double a = E.A[(int64_t)i * E.p + j];
-    const double absa = fabs(a);
+    const double absa = E.tom_signed ? fabs(a) : a;
     const double shared = v - a * (R.d_i + E.dvec[j]);
     const double mk = fmin(R.k_i, E.kvec[j]);
     double tom = E.tom_v2 ? 0.5 * (a + shared / (mk + absa)) : (a + shared) / (mk + 1.0 - absa);

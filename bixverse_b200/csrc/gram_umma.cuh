@@ -646,8 +646,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       const int n_iter = (P.ntiles + unit_stride - 1) / unit_stride;  // the same for every CTA (barrier participation)
       bool sync_alive = P.tile_sync != nullptr;
       unsigned epoch = 0;  // barriers passed; every producer of the grid executes the same sequence of them
-      // all producers of the grid are co-resident (one CTA per SM, grid = SM count): a spin barrier is safe; the
-      // bail-out only guards against a foreign launch configuration
+      // The barrier is a performance hint, never a correctness dependency: it assumes the grid's CTAs are co-resident
+      // (one CTA per SM, grid <= SM count, checked by the host against the occupancy API).  If foreign work holds SMs
+      // (another stream, MPS) a producer gives up after ~5 ms (a tile takes < 1 ms), counts the bail-out in
+      // tile_sync[1] and every producer of the launch then runs un-synchronised.
       auto grid_barrier = [&]() {
         if (!sync_alive) return;
         atomicAdd(P.tile_sync, 1u);
@@ -657,8 +659,11 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.tile_sync) : "memory");
           if (seen >= target) break;
           __nanosleep(40);
-        } while (++spins < (1u << 22));
-        if (seen < target) sync_alive = false;
+        } while (++spins < (1u << 17));
+        if (seen < target) {
+          sync_alive = false;
+          atomicAdd(P.tile_sync + 1, 1u);
+        }
       };
       for (int it = 0; it < n_iter; ++it) {
         const int t = unit0 + it * unit_stride;
@@ -1220,7 +1225,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline char* err_buf() {
-  static char buf[512] = "";
+  static thread_local char buf[512] = "";  // one per host thread: the multi-device entry points launch from a thread per device
   return buf;
 }
 inline const char* last_error() { return err_buf(); }
@@ -1298,7 +1303,7 @@ inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, 
 inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int ctas, int64_t rows,
                             const void* planes0, int K0, const double* inv0, const void* planes1, int K1,
                             const double* inv1, const int2* tiles, int ntiles, const EpiParams& E, int nplanes = 2,
-                            int plane_a0 = 0, int plane_b0 = 0) {
+                            int plane_a0 = 0, int plane_b0 = 0, unsigned* tile_sync_counter = nullptr) {
   if (ntiles <= 0) return 0;
   const int kelems = kind == KIND_TF32 ? 32 : (kind == KIND_F16 ? 64 : 128);
   if (K0 % kelems != 0 || (planes1 && K1 % kelems != 0)) {
@@ -1332,19 +1337,17 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
     // Long-K Grams (TOM, Ozaki passes, sparse panels): ncu shows the operand panels being re-read from DRAM (f16 TOM: 92 GB,
     // L2 hit rate 50 %) because the persistent CTAs drift apart along K.  A per-tile arrival barrier of the producers
     // keeps them in step; it costs a few microseconds per tile, so it is only armed when a tile's K loop is long.
-    static int sync_mode = -1;  // env BIXCOR_UMMA_TILE_SYNC: 0 = off, 1 = on for long K (default), 2 = always
-    if (sync_mode < 0) {
+    // tile_sync_counter: two words owned by the caller's per-device, per-stream context (so concurrent launches on
+    // other devices / contexts never share it); [0] arrivals, [1] bail-outs of this launch.
+    static const int sync_mode = [] {  // env BIXCOR_UMMA_TILE_SYNC: 0 = off, 1 = on for long K (default), 2 = always
       const char* v = getenv("BIXCOR_UMMA_TILE_SYNC");
-      sync_mode = v ? atoi(v) : BIXCOR_UMMA_TILE_SYNC_DEFAULT;
-    }
-    static unsigned* d_sync[64] = {nullptr};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (sync_mode == 2 || (sync_mode == 1 && P.kblocks[0] >= 96)) {
-      if (dev >= 0 && dev < 64) {
-        if (!d_sync[dev]) cudaMalloc(&d_sync[dev], 256);
-        if (d_sync[dev] && cudaMemsetAsync(d_sync[dev], 0, sizeof(unsigned), stream) == cudaSuccess) P.tile_sync = d_sync[dev];
-      }
+      return v ? atoi(v) : BIXCOR_UMMA_TILE_SYNC_DEFAULT;
+    }();
+    if (tile_sync_counter && (sync_mode == 2 || (sync_mode == 1 && P.kblocks[0] >= 96))) {
+      // armed only when the persistent grid fits the device at once (>= 1 CTA of this kernel per SM)
+      const int units = sm_count / ctas;
+      const bool grid_fits = ctas * (ntiles < units ? ntiles : units) <= sm_count;
+      if (grid_fits && cudaMemsetAsync(tile_sync_counter, 0, 2 * sizeof(unsigned), stream) == cudaSuccess) P.tile_sync = tile_sync_counter;
     }
   }
   P.plane_a0 = plane_a0;

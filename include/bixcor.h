@@ -57,8 +57,15 @@ extern "C" {
 #define BIXCOR_ERR_CUDA (-3)
 #define BIXCOR_ERR_OOM (-4)
 #define BIXCOR_ERR_UNSUPPORTED (-5)
+#define BIXCOR_ERR_INTERNAL (-6) /* a C++ exception other than std::bad_alloc was stopped at the ABI */
 
 /* `precision` argument */
+#define BIXCOR_PREC_AUTO (-1) /* what the drop-in patch passes: the fastest path that provably meets the
+                               * reference's FP64 contract (<= 1e-10) for this call: the exact-integer tcgen05 Gram for Spearman
+                               * with n <= 1860 samples (exact by construction), FP64 DMMA otherwise.  The environment variable
+                               * BIXCOR_PRECISION = auto | f64 | tf32 | f16 | i8 | ozaki | ozaki4 replaces the AUTO rule
+                               * process-wide (an R user opting into the <= 1e-5 fast paths without an API change); a value
+                               * that is not defined for the call (i8 for Pearson or n > 1860) falls back to the AUTO rule. */
 #define BIXCOR_PREC_F64 0    /* FP64 tensor-core (DMMA) Gram: exact path, <=1e-10 */
 #define BIXCOR_PREC_TF32X3 1 /* tcgen05 3xTF32 split, FP32 accumulate in TMEM: fast path, <=1e-5 */
 #define BIXCOR_PREC_I8EXACT 2 /* Spearman only: exact integer Gram of centred ranks on tcgen05 kind::i8 */
@@ -87,6 +94,9 @@ const char* bixcor_last_error(void);
 int64_t bixcor_launch_count(void);
 /* Fisher-z variance inflation for Spearman (default 1.06, Fieller); Pearson uses 1. */
 int bixcor_set_fieller(double c);
+/* Test hook of the exception barrier: the NEXT API call throws from inside its body
+ * (1 = std::bad_alloc -> BIXCOR_ERR_OOM, 2 = std::runtime_error -> BIXCOR_ERR_INTERNAL). */
+int bixcor_debug_inject(int what);
 
 /* ---- packed triangle helpers (pure index logic, run on the host) ------- */
 int64_t bixcor_packed_len(int64_t p, int shift);
@@ -113,7 +123,10 @@ int bixcor_cor_dense(const double* x, int64_t n, int64_t p, int spearman, int pr
 int bixcor_cor_upper(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta,
                      int precision, double* out_packed);
 /* Same, restricted to rows [row_begin,row_end): out_slice receives the packed range
- * starting at bixcor_packed_offset(row_begin,p,shift). */
+ * starting at bixcor_packed_offset(row_begin,p,shift).  Row ranges are block-row ranges of the 128 x 128 tiling:
+ * row_begin must be a multiple of 128 and row_end a multiple of 128 or p (bixcor_shard_rows produces such ranges);
+ * anything else is BIXCOR_ERR_INVALID.  An empty range (row_begin == row_end) is a no-op.  This holds for every
+ * *_rows entry point below, host or device. */
 int bixcor_cor_upper_rows(const double* x, int64_t n, int64_t p, int spearman, int shift, double beta,
                           int precision, int64_t row_begin, int64_t row_end, double* out_slice);
 
@@ -123,6 +136,11 @@ int bixcor_diffcor_rows(const double* xa, int64_t na, const double* xb, int64_t 
                         int precision, int64_t row_begin, int64_t row_end, double* r_a, double* r_b,
                         double* z, double* pval);
 
+/* rs_tom: the affinity matrix is used AS PASSED.  signed_: k_i = sum_j |a_ij| and |a_ij| in the denominators;
+ * unsigned: k_i = sum_j a_ij and a_ij itself (R/functions_stats.R:15-37).  abs() for unsigned networks is the R
+ * wrappers' job (calculate_tom / calculate_tom_from_exp, R/functions_stats.R:52-54,114-116) and stays there;
+ * cor_module_tom passes the raw correlation (R/methods_coexp_cor.R:151), so bixcor_tom_packed does not take abs either.
+ * bixcor_tom_from_exp replaces the whole of calculate_tom_from_exp and therefore does (|r|^beta when unsigned). */
 int bixcor_tom(const double* a_pp, int64_t p, int signed_, int version, int precision, double* out_pp);
 
 /* cor_module_tom (R/methods_coexp_cor.R:118-164) in one call: the stored packed correlation (shift as stored) in,
@@ -230,12 +248,11 @@ int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, 
  * all-reduce k between them:
  *   phase 1: affinity block rows [row_begin,row_end) of the dense p x p matrix
  *            d_a (full columns of those genes: d_a + row_begin*p) from expression;
- *   phase 2: connectivity k_i = sum_j |a_ij| for columns [row_begin,row_end)
- *            (unsigned: also replaces a by |a| in place);
+ *   phase 2: connectivity k_i = sum_j |a_ij| (signed) / sum_j a_ij (unsigned) for columns [row_begin,row_end);
  *   phase 3: TOM for block rows [row_begin,row_end) from the full A and full k. */
 int bixcor_dev_affinity_cols(const double* d_x, int64_t n, int64_t p, int spearman, int signed_, double beta,
                              int precision, int64_t row_begin, int64_t row_end, double* d_a_pp);
-int bixcor_dev_tom_connectivity(double* d_a_pp, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
+int bixcor_dev_tom_connectivity(const double* d_a_pp, int64_t p, int signed_, int64_t row_begin, int64_t row_end,
                                 double* d_k);
 int bixcor_dev_tom_rows(const double* d_a_pp, const double* d_k, int64_t p, int signed_, int version,
                         int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out);

@@ -74,3 +74,78 @@ def rbf(d, eps, rbf_type):
     code = {"gaussian": 1, "bump": 2, "inverse_quadratic": 3}[rbf_type]
     lib().orc_rbf(C.c_void_p(d.ctypes.data), C.c_int64(d.size), C.c_double(eps), C.c_int(code), C.c_void_p(out.ctypes.data))
     return out
+
+
+# ---- timed CPU baseline (bench.py reference arm): OpenMP restatement + threaded OpenBLAS dgemm ----------------------
+_blas = None
+
+
+def openblas_dgemm():
+    """Address of cblas_dgemm in the ILP64 OpenBLAS that numpy bundles (scipy_cblas_dgemm64_), plus its thread count.
+    The image has no system BLAS; this is the same library `numpy.dot` calls."""
+    global _blas
+    if _blas is None:
+        import glob
+
+        d = os.path.join(os.path.dirname(np.__file__), "..", "numpy.libs")
+        cands = sorted(glob.glob(os.path.join(d, "libscipy_openblas64_*.so*")))
+        if not cands:
+            raise RuntimeError("numpy's bundled OpenBLAS (numpy.libs/libscipy_openblas64_*.so) not found")
+        h = C.CDLL(cands[0])
+        fn = C.cast(h.scipy_cblas_dgemm64_, C.c_void_p).value
+        get = h.scipy_openblas_get_num_threads64_
+        get.restype = C.c_int
+        _blas = (h, fn, get)
+    return _blas[1], int(_blas[2]())
+
+
+def set_blas_threads(n):
+    openblas_dgemm()
+    f = _blas[0].scipy_openblas_set_num_threads64_
+    f.argtypes = [C.c_int]
+    f(int(n))
+
+
+def use_all_cores():
+    """OpenMP + OpenBLAS threads := the cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(C.c_int(ncpu))
+    set_blas_threads(ncpu)
+    return ncpu
+
+
+def num_threads():
+    f = lib().orc_num_threads
+    f.restype = C.c_int
+    return int(f())
+
+
+def cor_upper_pipeline(x, spearman, shift, beta, out=None):
+    """rs_cor_upper_triangle (+ |r|^beta) on all host cores; returns (packed vector, seconds dict)."""
+    x = _f(x); n, p = x.shape
+    ln = p * (p - 1) // 2 if shift else p * (p + 1) // 2
+    if out is None:
+        out = np.empty(ln)
+    secs = (C.c_double * 4)()
+    fn, _ = openblas_dgemm()
+    f = lib().orc_cor_upper_pipeline
+    f.restype = C.c_int
+    rc = f(C.c_void_p(x.ctypes.data), C.c_int64(n), C.c_int64(p), C.c_int(int(spearman)), C.c_int(int(shift)), C.c_double(beta),
+           C.c_void_p(fn), C.c_void_p(out.ctypes.data), secs)
+    if rc != 0:
+        raise MemoryError("orc_cor_upper_pipeline: allocation failed")
+    return out, {"columns_s": secs[0], "dgemm_s": secs[1], "gather_s": secs[2], "total_s": secs[3]}
+
+
+def tom_from_exp_pipeline(x, spearman, signed, version, beta):
+    x = _f(x); n, p = x.shape
+    out = np.empty(p * (p - 1) // 2)
+    secs = (C.c_double * 4)()
+    fn, _ = openblas_dgemm()
+    f = lib().orc_tom_from_exp_pipeline
+    f.restype = C.c_int
+    rc = f(C.c_void_p(x.ctypes.data), C.c_int64(n), C.c_int64(p), C.c_int(int(spearman)), C.c_int(int(signed)), C.c_int(int(version)),
+           C.c_double(beta), C.c_void_p(fn), C.c_void_p(out.ctypes.data), secs)
+    if rc != 0:
+        raise MemoryError("orc_tom_from_exp_pipeline: allocation failed")
+    return out, {"affinity_s": secs[0], "dgemm_s": secs[1], "normalise_s": secs[2], "total_s": secs[3]}

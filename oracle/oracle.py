@@ -52,6 +52,7 @@ __all__ = [
     "calculate_diff_correlation",
     "differential_cor",
     "calc_tom",
+    "calculate_tom",
     "tom_from_exp",
     "sparse_gram_cor",
     "pairwise_gene_cors",
@@ -263,9 +264,11 @@ def calc_tom(a: np.ndarray, signed: bool, version: str = "v1") -> np.ndarray:
     a = np.asarray(a, dtype=np.float64)
     if version not in ("v1", "v2"):
         raise ValueError(f"Invalid TOM version type: {version}")
-    if not signed:
-        a = np.abs(a)
-    absa = np.abs(a)
+    # rs_tom level: the matrix is used AS PASSED.  Signed: |a_ij| in k and in the denominators; unsigned: a_ij itself
+    # (R/functions_stats.R:15-37).  abs() for unsigned networks is applied by the R wrappers calculate_tom /
+    # calculate_tom_from_exp (R/functions_stats.R:52-54,114-116) - `calculate_tom` below - and NOT by cor_module_tom
+    # (R/methods_coexp_cor.R:151).  Unsigned with negative entries is unpinned (every reference KAT passes |A|).
+    absa = np.abs(a) if signed else a
     k = absa.sum(axis=1)  # includes the diagonal entry as passed
     d = np.diag(a)
     shared = a @ a - a * (d[:, None] + d[None, :])  # sum over u not in {i, j}
@@ -276,6 +279,12 @@ def calc_tom(a: np.ndarray, signed: bool, version: str = "v1") -> np.ndarray:
         t = 0.5 * (a + shared / (mk + absa))
     t[np.arange(a.shape[0]), np.arange(a.shape[0])] = 1.0  # unpinned; WGCNA convention
     return t
+
+
+def calculate_tom(cor_mat: np.ndarray, signed: bool, version: str = "v1") -> np.ndarray:
+    """R/functions_stats.R:43-59: abs() first when unsigned, then rs_tom."""
+    cor_mat = np.asarray(cor_mat, dtype=np.float64)
+    return calc_tom(cor_mat if signed else np.abs(cor_mat), signed, version)
 
 
 def tom_from_exp(x, signed: bool, version: str = "v1", spearman: bool = False, beta: float = 1.0):

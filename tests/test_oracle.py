@@ -272,3 +272,37 @@ def test_golden_fixtures_regenerate_identically(golden_dir, tmp_path, monkeypatc
     for name in ("reference_kat.json", "r_equality_seed123.json", "rbh_cor_seed42.json"):
         with open(os.path.join(golden_dir, name)) as f, open(tmp_path / name) as g:
             assert json.load(f) == json.load(g), name
+
+
+def test_sampled_row_oracle_equals_the_full_oracle():
+    """oracle/sampled.py (rows of the BASELINE-size results on demand) against the full-matrix oracle."""
+    from oracle import sampled as sm
+
+    rng = np.random.default_rng(5)
+    x = np.round(rng.normal(size=(40, 300)), 1)  # ties
+    xb = rng.normal(size=(31, 300))
+    p = 300
+    for sp in (False, True):
+        so = sm.SampledOracle(x, sp)
+        full = o.cor_upper_triangle(x, sp, True)
+        full6 = o.soft_threshold(full, 6.0)
+        for i in sm.pick_rows(0, p, p):
+            assert np.abs(sm.packed_row(full, 0, i, p) - so.cor_upper_row(i)).max() < 1e-14
+            assert np.abs(sm.packed_row(full6, 0, i, p) - so.cor_upper_row(i, 1, 6.0)).max() < 1e-14
+        sb = sm.SampledOracle(xb, sp)
+        d = o.differential_cor(x, xb, sp)
+        for i in (0, 128, 298):
+            ra, rb, z, pv = sm.diffcor_rows(so, sb, i)
+            for got, key in ((ra, "r_a"), (rb, "r_b"), (z, "z_score"), (pv, "p_val")):
+                assert np.allclose(got, sm.packed_row(d[key], 0, i, p), rtol=1e-12, atol=1e-14)
+    so = sm.SampledOracle(x, False)
+    for signed in (True, False):
+        for ver in ("v1", "v2"):
+            t = o.tom_from_exp(x, signed, ver, False, 6.0)
+            for i in (0, 127, 250):
+                cols = sm.tom_sample_cols(i, p)
+                assert np.abs(so.tom_entries(i, cols, signed, ver, 6.0) - t[i, cols]).max() < 1e-13
+    # shard-aware row picking: inside the range, both ends present, a shard that only holds the pair-less last row is empty
+    assert sm.pick_rows(128, 256, 300)[0] == 128 and sm.pick_rows(128, 256, 300)[-1] == 255
+    assert sm.pick_rows(299, 300, 300) == [] and sm.pick_rows(120, 120, 120) == []
+    assert set(sm.pick_rows(0, 20000, 20000)) == set(sm.ROWS_20K)
