@@ -287,7 +287,7 @@ def run_ours(args):
             fp64_peak["v"] = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         return fp64_peak["v"]
 
-    def measure_dev(pname, k_steps, keep_out=False):
+    def measure_dev(pname, k_steps):
         prec = PREC[pname]
         xprec = _lib.PREC_I8EXACT if pname == "auto" else prec  # the operand-exchange API takes the resolved precision
         _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream, 1))
@@ -382,28 +382,61 @@ def run_ours(args):
         return {"value": P_total / (ms_step * 1e-3), "ms_per_step": ms_step, "roofline": roof, "clocks": clocks,
                 "gpu_launches": int(allsum(launches)), "dtype": DTYPES[pname], "path": PREC_NAMES[pname]}
 
+    # ---- parity leg (outside every timed region): sampled rows of THIS rank's slice against the CPU oracle
+    from oracle import c_binding as cb
+    from oracle import sampled as sm
+
+    oracles = {}
+
+    def oracle_for(spearman):
+        if spearman not in oracles:
+            ranks = cb.rank_matrix_col(x_host) if spearman else None  # C oracle (pinned against oracle.py in tests/)
+            oracles[spearman] = sm.SampledOracle(x_host, spearman, ranks=ranks)
+        return oracles[spearman]
+
+    parity_rows = sm.pick_rows(r0, r1, p)
+
+    def cor_parity(get_row):
+        so, err = oracle_for(True), 0.0
+        for i in parity_rows:
+            err = max(err, float(np.abs(get_row(i) - so.cor_upper_row(i, 1, BETA)).max()))
+        return err
+
+    def slice_row(vec, i):  # row i of this rank's packed slice (torch tensor on any device, or numpy)
+        a = packed_offset(i, p, 1) - o0
+        row = vec[a:a + (p - i - 1)]
+        return row.cpu().numpy() if hasattr(row, "cpu") else np.asarray(row)
+
     primary = args.precision
     main = measure_dev(primary, steps)
+    parity = {"value_arm": cor_parity(lambda i: slice_row(out_dev, i))}
     paths = {}
     if not args.no_alt:
         for alt in ("f64", "i8", "tf32", "f16", "ozaki"):
-            if alt != primary and not (alt == "ozaki" and world > 1):  # (the operand exchange carries precisions 0..2)
-                r = measure_dev(alt, max(2, min(steps, 5)))
-                paths[alt] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "path": r["path"],
-                              "roofline_frac": r["roofline"]["frac"], "roofline_achieved": r["roofline"]["achieved"],
-                              "roofline_peak": r["roofline"]["peak"], "kernel_ms_per_step": r["roofline"]["kernel_ms_per_step"]}
+            if alt == primary or (primary == "auto" and alt == "i8"):
+                continue
+            if alt == "ozaki" and world > 1:  # (the operand exchange carries one record per gene: precisions 0..2 and 5)
+                continue
+            r = measure_dev(alt, max(2, min(steps, 5)))
+            paths[alt] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "path": r["path"],
+                          "roofline_frac": r["roofline"]["frac"], "roofline_achieved": r["roofline"]["achieved"],
+                          "roofline_peak": r["roofline"]["peak"], "kernel_ms_per_step": r["roofline"]["kernel_ms_per_step"],
+                          "parity_max_err": cor_parity(lambda i: slice_row(out_dev, i))}
 
-    # ---- end-to-end arm: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region
+    # ---- end-to-end arm: the reference-facing call with HOST buffers, H2D + D2H inside the timed region.
+    #      Headline = PAGEABLE buffers (what R hands to the Rust binding); page-locked buffers as a second figure.
     del out_dev
-    x_pin = torch.from_numpy(np.ascontiguousarray(x_host.T)).pin_memory()
-    out_pin = torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
+    x_page = torch.from_numpy(np.ascontiguousarray(x_host.T))  # p x n row-major == R's n x p column-major matrix
+    out_page = torch.empty(max(my_pairs, 1), dtype=torch.float64)
+    e2e_prec = PREC[primary]
+    e2e_xprec = _lib.PREC_I8EXACT if primary == "auto" else e2e_prec
 
     if world == 1:
-        e2e_note = "bixcor_cor_upper_rows through the C ABI with pinned host buffers"
+        e2e_note = "bixcor_cor_upper_rows through the C ABI"
         h2d_bytes = int(8 * n * p)
 
-        def step_e2e():
-            _lib.check(lib.bixcor_cor_upper_rows(x_pin.data_ptr(), n, p, 1, 1, BETA, PREC[primary], r0, r1, out_pin.data_ptr()))
+        def make_step(xh, oh):
+            return lambda: _lib.check(lib.bixcor_cor_upper_rows(xh.data_ptr(), n, p, 1, 1, BETA, e2e_prec, r0, r1, oh.data_ptr()))
     else:
         # host -> host multi-process driver: only this rank's gene slab crosses PCIe, operand records are
         # all-gathered over NCCL, the rank's packed rows come back with the D2H of finished bands overlapped
@@ -412,24 +445,32 @@ def run_ours(args):
         be_e2e, ws_e2e = DeviceBackend(dev), {}
         slab_e2e = gene_slab(p, world)
         h2d_bytes = int(8 * n * max(0, min(p, (rank + 1) * slab_e2e) - min(p, rank * slab_e2e)))
-        e2e_note = ("bixverse_b200.distributed.host_sharded_cor_upper (C ABI underneath) with pinned host buffers: gene-slab "
-                    "H2D, operand all-gather over NCCL, band-pipelined D2H")
+        e2e_note = ("bixverse_b200.distributed.host_sharded_cor_upper (C ABI underneath): gene-slab H2D, operand all-gather "
+                    "over NCCL, band-pipelined D2H")
 
-        def step_e2e():
-            host_sharded_cor_upper(be_e2e, x_pin, n, p, True, out_pin, 1, BETA, PREC[primary], workspace=ws_e2e)
+        def make_step(xh, oh):
+            return lambda: host_sharded_cor_upper(be_e2e, xh, n, p, True, oh, 1, BETA, e2e_xprec, workspace=ws_e2e)
 
     e2e_steps = max(1, min(steps, 5))
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    torch.cuda.synchronize(dev)
-    e2e_val = P_total / (allmax(time.perf_counter() - t0) / e2e_steps)
-    checksum = float(out_pin[: min(my_pairs, 1 << 20)].sum())
 
-    # ---- TOM wall time (config 4) as an extra metric, device resident, packed output
+    def time_e2e(step):
+        for _ in range(2):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step()
+        torch.cuda.synchronize(dev)
+        return allmax(time.perf_counter() - t0) / e2e_steps
+
+    t_page = time_e2e(make_step(x_page, out_page))
+    parity["e2e_arm"] = cor_parity(lambda i: slice_row(out_page, i))
+    checksum = float(out_page[: min(my_pairs, 1 << 20)].sum())
+    x_pin, out_pin = x_page.pin_memory(), torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
+    t_pin = time_e2e(make_step(x_pin, out_pin))
+    del x_pin, out_pin
+
+    # ---- TOM wall time (config 4) as an extra metric: HBM resident (all N) and host -> host through the C ABI (N = 1)
     tom = None
     if not args.no_tom:
         try:
@@ -437,6 +478,18 @@ def run_ours(args):
 
             be = DeviceBackend(dev)
             tom = {}
+            po = oracle_for(False)
+
+            def tom_parity(vec, base):
+                err = 0.0
+                for i in parity_rows:
+                    cols = sm.tom_sample_cols(i, p)
+                    a = packed_offset(i, p, 1) - base
+                    got = vec[a:a + (p - i - 1)]
+                    got = (got.cpu().numpy() if hasattr(got, "cpu") else np.asarray(got))[cols - i - 1]
+                    err = max(err, float(np.abs(got - po.tom_entries(i, cols, True, "v1", BETA)).max()))
+                return err
+
             for tname in (("f16", "tf32", "ozaki", "f64") if not args.no_alt else ("f16",)):
                 tprec = PREC[tname]
                 t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)  # warm-up
@@ -444,30 +497,55 @@ def run_ours(args):
                 _lib.check(lib.bixcor_timing_enable(1))
                 barrier()
                 t0 = time.perf_counter()
-                t_out, _ = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)
+                t_out, (to0, _) = sharded_tom_from_exp(be, x_dev, n, p, False, True, "v1", beta=BETA, precision=tprec)
                 barrier()
                 t_tom = allmax(time.perf_counter() - t0)
                 ttm = _lib.last_timing()
                 _lib.check(lib.bixcor_timing_enable(0))
+                terr = allmax(tom_parity(t_out, to0))
                 del t_out
                 tom[tname] = {"metric": "tom_from_exp_wall_ms", "value": 1e3 * t_tom, "unit": "ms", "alg_flops": 8.4e12,
                               "achieved_tflops": 8.4e12 / t_tom / 1e12,
-                              "kernel_ms_rank0": {"gemm": ttm["gemm_ms"], "columns": ttm["cols_ms"], "other": ttm["other_ms"]}}
-            tom["config"] = ("config4: signed TOM v1 from expression, 20000 genes x 1000 samples, Pearson, beta=6, packed "
-                             "output, HBM resident; slabs exchanged + k all-reduced over NCCL when N > 1; f16 / tf32 = 3 x binary16 / 3xTF32 tcgen05 "
-                             "(<=1e-5), ozaki = 6-slice int8 tcgen05 with FP64 recombination (<=1e-10), f64 = FP64 DMMA")
+                              "kernel_ms_rank0": {"gemm": ttm["gemm_ms"], "columns": ttm["cols_ms"], "other": ttm["other_ms"]},
+                              "parity_max_err": terr, "parity_tol": 1e-5 if tname in ("f16", "tf32") else 1e-10}
+                if world == 1:  # calculate_tom_from_exp host -> host: pageable expression matrix in, pageable packed TOM out
+                    tom_page = torch.empty(P_total, dtype=torch.float64)
+
+                    def tom_e2e():
+                        _lib.check(lib.bixcor_tom_from_exp(x_page.data_ptr(), n, p, 0, 1, _lib.TOM_V1, BETA, tprec, 1, tom_page.data_ptr()))
+
+                    tom_e2e()
+                    t0 = time.perf_counter()
+                    tom_e2e()
+                    tom[tname]["e2e_ms"] = 1e3 * (time.perf_counter() - t0)
+                    tom[tname]["e2e_parity_max_err"] = tom_parity(tom_page, 0)
+                    del tom_page
+            tom["config"] = ("config4: signed TOM v1 from expression, 20000 genes x 1000 samples, Pearson, beta=6, packed output; value = "
+                             "HBM resident (slabs exchanged + k all-reduced over NCCL when N > 1), e2e_ms = bixcor_tom_from_exp host -> "
+                             "host with pageable buffers (160 MB in, 1.6 GB out); f16 / tf32 = 3 x binary16 / 3xTF32 tcgen05 (<=1e-5), "
+                             "ozaki = 6-slice int8 tcgen05 with FP64 recombination (<=1e-10), f64 = FP64 DMMA; parity = sampled TOM "
+                             "entries of every rank's rows against the CPU oracle")
         except Exception as ex:  # report, do not hide
             tom = {"error": str(ex)}
 
-    # ---- CPU baseline leg (rank 0, N = 1 only): bounded sample of the same workload
+    # ---- parity summary: max over ranks, every rank checked its own rows
+    par_err = allmax(max(parity.values()))
+    par_ranks = int(allsum(1 if parity_rows else 0))
+    tom_bad = bool(tom) and any(isinstance(v, dict) and v.get("parity_max_err", 0) > v.get("parity_tol", 1) for v in tom.values())
+    parity_line = {"max_err": par_err, "tol": 1e-12, "ok": bool(par_err <= 1e-12 and not tom_bad), "rows": parity_rows,
+                   "rows_per_rank": len(parity_rows), "ranks_checked": par_ranks, "world": world,
+                   "arms_rank0": parity,
+                   "what": "|r|^6 rows of each rank's packed slice (HBM-resident arm and pageable e2e arm) vs oracle/sampled.py; "
+                           "TOM entries per precision under tom.<prec>.parity_max_err"}
+
+    # ---- CPU baseline leg (rank 0, N = 1 only): ONE pass of the full workload on the host cores (seconds)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        xs = np.asfortranarray(x_host[:, :CPU_SAMPLE_GENES])
-        pairs, dtc = cpu_step(xs)
-        cpu_baseline = {"value": pairs / dtc, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-                        "sample": f"first {CPU_SAMPLE_GENES} genes x {N_SAMPLES} samples, one pass ({pairs} pairs, {dtc:.2f} s): "
-                                  "numpy/OpenBLAS oracle following the reference algorithm shape (rank -> standardise -> full "
-                                  "p x p dgemm -> triangle gather); the Rust crate itself cannot be built in this image"}
+        ncpu, omp_t, blas_t = cpu_threads()
+        secs = cpu_step(np.asfortranarray(x_host))
+        cpu_baseline = {"value": P_total / secs["total_s"], "unit": UNIT, "cores": max(omp_t, blas_t), "host_cpus": ncpu, "kind": "port",
+                        "sample": f"one pass of the full workload ({P_total} pairs, {secs['total_s']:.2f} s: columns {secs['columns_s']:.2f}, "
+                                  f"dgemm {secs['dgemm_s']:.2f}, gather+power {secs['gather_s']:.2f}); " + CPU_KIND_NOTE}
 
     if rank == 0:
         line = {
@@ -480,12 +558,15 @@ def run_ours(args):
                                     "slab, operand records all-gathered over NCCL" if world > 1 else "single GPU"),
                        "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
             "clocks": main["clocks"],
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps,
-                    "note": e2e_note + "; bytes are rank 0's"},
+            "e2e": {"value": P_total / t_page, "unit": UNIT, "ms_per_step": 1e3 * t_page, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps, "host_buffers": "pageable",
+                    "pinned": {"value": P_total / t_pin, "ms_per_step": 1e3 * t_pin},
+                    "note": e2e_note + ", precision = " + primary + "; value: pageable host buffers (what an R session owns), "
+                            "pinned: the same call with page-locked buffers; bytes are rank 0's"},
             "gpu_launches": main["gpu_launches"],
             "roofline": main["roofline"],
             "cpu_baseline": cpu_baseline,
+            "parity": parity_line,
             "paths": paths,
             "tom": tom,
             "checksum": checksum,
@@ -503,8 +584,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "i8"), choices=["f64", "i8", "tf32", "f16", "ozaki"],
-                    help="Gram path of the headline number: i8 = exact-integer Spearman (default), f64 = FP64 DMMA, tf32 = 3xTF32")
+    ap.add_argument("--precision", default=os.environ.get("BIXCOR_BENCH_PRECISION", "auto"),
+                    choices=["auto", "f64", "i8", "tf32", "f16", "ozaki"],
+                    help="Gram path of the headline number: auto = BIXCOR_PREC_AUTO, what the drop-in patch passes (exact-integer "
+                         "Spearman here), f64 = FP64 DMMA, tf32 / f16 = 3-way split fast paths, ozaki = FP64-class on int8")
     ap.add_argument("--no-alt", action="store_true", help="skip the other precision paths and the FP64 TOM")
     ap.add_argument("--no-tom", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

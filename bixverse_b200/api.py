@@ -29,21 +29,23 @@ UpperTriangleDiffcorMat     R/classes_triangular_mat.R:224-341
 Matrices are samples x genes; they are handed to the library in R's
 column-major layout (``np.asfortranarray``).  Extra keyword arguments
 (``precision``, ``beta``) are the north-star extensions and default to the
-reference behaviour.
+reference behaviour: ``precision`` defaults to ``PREC_AUTO``, the value the
+drop-in patch of INTEGRATION.md passes (exact-integer Gram for Spearman with
+n <= 1860, FP64 otherwise; env ``BIXCOR_PRECISION`` overrides).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import _lib
-from ._lib import PREC_F16X3, PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_TF32X3, TOM_V1, TOM_V2, BixcorError, check
+from ._lib import PREC_AUTO, PREC_F16X3, PREC_F64, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_TF32X3, TOM_V1, TOM_V2, BixcorError, check
 
 __all__ = [
     "rs_cor", "rs_cor_upper_triangle", "rs_covariance", "rs_cos", "rs_cor2", "rs_cov2cor", "rs_differential_cor", "rs_tom", "rs_rank_matrix_col",
     "rs_upper_triangle_to_dense", "rs_dense_to_upper_triangle", "rs_upper_triangle_to_sparse", "calculate_tom", "calculate_tom_from_exp", "cor_module_tom", "rs_rbh_cor",
     "rs_rbf_function", "rs_rbf_function_mat", "rs_rbf_iterate_epsilons", "rs_coremo_stability", "cor_upper_triangle_rbf", "rs_pairwise_gene_cors_mc",
     "sparse_gene_cor_upper_triangle", "UpperTriangularSymMat", "UpperTriangleDiffcorMat", "init", "shard_rows",
-    "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "PREC_OZAKI4", "PREC_F16X3", "BixcorError",
+    "PREC_AUTO", "PREC_F64", "PREC_TF32X3", "PREC_I8EXACT", "PREC_OZAKI", "PREC_OZAKI4", "PREC_F16X3", "BixcorError",
 ]
 
 
@@ -86,7 +88,7 @@ def rs_rank_matrix_col(x) -> np.ndarray:
     return out
 
 
-def rs_cor(x, spearman: bool, precision: int = PREC_F64) -> np.ndarray:
+def rs_cor(x, spearman: bool, precision: int = PREC_AUTO) -> np.ndarray:
     a = _fmat(x)
     n, p = a.shape
     out = np.empty((p, p), dtype=np.float64, order="F")
@@ -168,7 +170,7 @@ def rs_cov2cor(x) -> np.ndarray:
 
 
 def rs_cor_upper_triangle(x, spearman: bool, shift: bool = True, beta: float = 1.0,
-                          precision: int = PREC_F64, rows: tuple[int, int] | None = None) -> np.ndarray:
+                          precision: int = PREC_AUTO, rows: tuple[int, int] | None = None) -> np.ndarray:
     a = _fmat(x)
     n, p = a.shape
     lib = _lib.load()
@@ -184,7 +186,7 @@ def rs_cor_upper_triangle(x, spearman: bool, shift: bool = True, beta: float = 1
     return out
 
 
-def rs_differential_cor(x_a, x_b, spearman: bool, precision: int = PREC_F64) -> dict:
+def rs_differential_cor(x_a, x_b, spearman: bool, precision: int = PREC_AUTO) -> dict:
     a, b = _fmat(x_a, "x_a"), _fmat(x_b, "x_b")
     if a.shape[1] != b.shape[1]:
         # the reference asserts (panics) here: r_diffcor.rs:51-56
@@ -201,7 +203,7 @@ def rs_differential_cor(x_a, x_b, spearman: bool, precision: int = PREC_F64) -> 
     return res
 
 
-def rs_tom(x, tom_type: str, signed: bool, precision: int = PREC_F64) -> np.ndarray:
+def rs_tom(x, tom_type: str, signed: bool, precision: int = PREC_AUTO) -> np.ndarray:
     version = _parse_tom_types(tom_type)
     a = _fmat(x)
     if a.shape[0] != a.shape[1]:
@@ -212,7 +214,7 @@ def rs_tom(x, tom_type: str, signed: bool, precision: int = PREC_F64) -> np.ndar
     return out
 
 
-def calculate_tom(cor_mat, signed: bool, version: str = "v1", precision: int = PREC_F64) -> np.ndarray:
+def calculate_tom(cor_mat, signed: bool, version: str = "v1", precision: int = PREC_AUTO) -> np.ndarray:
     if version not in ("v1", "v2"):
         raise ValueError("version must be one of 'v1', 'v2'")
     cor_mat = np.asarray(cor_mat, dtype=np.float64)
@@ -222,7 +224,7 @@ def calculate_tom(cor_mat, signed: bool, version: str = "v1", precision: int = P
 
 
 def cor_module_tom(cor_res: "UpperTriangularSymMat", signed: bool = True, version: str = "v2",
-                   precision: int = PREC_F64) -> "UpperTriangularSymMat":
+                   precision: int = PREC_AUTO) -> "UpperTriangularSymMat":
     """R/methods_coexp_cor.R:118-164 on the result container: get_sym_matrix -> rs_tom -> rs_dense_to_upper_triangle,
     fused into one library call; returns the TOM as a new shift = 1 container (the R method stores it back)."""
     ver = _parse_tom_types(version)
@@ -234,7 +236,7 @@ def cor_module_tom(cor_res: "UpperTriangularSymMat", signed: bool = True, versio
 
 
 def calculate_tom_from_exp(x, signed: bool, version: str, cor_method: str = "pearson", beta: float = 1.0,
-                           precision: int = PREC_F64, packed: bool = False) -> np.ndarray:
+                           precision: int = PREC_AUTO, packed: bool = False) -> np.ndarray:
     """Fused on-device rs_cor -> (abs) -> rs_tom chain; the p x p correlation never leaves HBM."""
     if version not in ("v1", "v2"):
         raise ValueError("version must be one of 'v1', 'v2'")
@@ -306,7 +308,7 @@ def rs_rbf_iterate_epsilons(dist, epsilon_vec, original_dim: int, shift: bool, r
 
 
 def rs_coremo_stability(data, indices, epsilon: float, rbf_type: str, spearman: bool,
-                        precision: int = PREC_F64) -> list[np.ndarray]:
+                        precision: int = PREC_AUTO) -> list[np.ndarray]:
     """src/rust/src/methods/r_coremo.rs:191-235: one packed distance vector per left-out (1-based) sample."""
     import ctypes as C
 
@@ -323,7 +325,7 @@ def rs_coremo_stability(data, indices, epsilon: float, rbf_type: str, spearman: 
 
 
 def cor_upper_triangle_rbf(x, spearman: bool, epsilon: float, rbf_type: str, shift: bool = True,
-                           complement: bool = False, precision: int = PREC_F64) -> np.ndarray:
+                           complement: bool = False, precision: int = PREC_AUTO) -> np.ndarray:
     """Fused rs_cor_upper_triangle -> 1 - |r| -> rs_rbf_function (R/methods_coexp_cor.R:357-370) in one Gram pass."""
     mode = _parse_rbf_types(rbf_type)
     a = _fmat(x)
@@ -351,7 +353,7 @@ def rs_upper_triangle_to_sparse(value, shift: bool, n: int, cs_type: str = "csc"
     return {"data": data[:nnz], "indices": indices[:nnz], "indptr": indptr, "nrow": n, "ncol": n, "cs_type": cs_type}
 
 
-def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int, precision: int = PREC_F64) -> np.ndarray:
+def sparse_gene_cor_upper_triangle(indptr, indices, data, cells: int, genes: int, precision: int = PREC_AUTO) -> np.ndarray:
     """All-pairs Pearson over a cells x genes CSR matrix (north-star extension of
     rs_pairwise_gene_cors_mc, src/rust/src/meta_cell/r_mc_processing.rs:258-283)."""
     ip = np.ascontiguousarray(indptr, dtype=np.int64)

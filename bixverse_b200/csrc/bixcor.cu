@@ -3,6 +3,7 @@
 #include "../../include/bixcor.h"
 
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <atomic>
@@ -167,6 +168,8 @@ struct TileList {
 
 enum TimeCat : int { T_COLS = 0, T_GEMM = 1, T_OTHER = 2 };
 
+struct HostStager;  // pinned ring + copier threads for pageable host buffers (below)
+
 struct Ctx {
   int device = -1;
   int sm_count = 148;
@@ -184,7 +187,7 @@ struct Ctx {
   Buffer sparse_in;     // staged CSR
   Buffer flag;          // one int: device-side overflow / range flags read back by the host
   Buffer tile_sync;     // two words: arrival / bail-out counters of the long-K producer barrier (gram_umma.cuh)
-  PinnedBuffer stage[2];
+  HostStager* stager = nullptr;
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
   // timing
   std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> timed;
@@ -200,6 +203,8 @@ static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM
 static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
+
+static void stager_destroy(Ctx* c);
 
 static int ctx_create(int device, Ctx** out) {
   Ctx* c = new Ctx();
@@ -236,7 +241,7 @@ static void ctx_destroy(Ctx* c) {
   c->sparse_in.release();
   c->flag.release();
   c->tile_sync.release();
-  for (auto& b : c->stage) b.release();
+  stager_destroy(c);
   for (auto& kv : c->tile_cache)
     if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
   for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -741,71 +746,259 @@ static bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  const size_t kMin = size_t(8) << 20;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nthr = (int)std::min<size_t>(std::max(1u, std::min(hw, 16u)), std::max<size_t>(1, bytes / kMin));
-  if (nthr <= 1) {
-    memcpy(dst, src, bytes);
+// ----------------------------------------------------------------------------
+// Pageable host buffers (what an R session owns) cannot be DMA'd directly, pinning them in place costs more than
+// the transfer (cudaHostRegister of 1.6 GB: 224 ms against 29 ms of PCIe, scripts/micro/d2h_floor.cu), and the
+// driver's own staging reaches 17 GB/s.  The library stages through a ring of pinned slots and keeps the two
+// halves of the job on different threads: the calling thread only enqueues DMAs, a persistent pool of copier threads
+// moves finished slots into (out of) the caller's memory in 4 MB pieces (16 threads: 75 GB/s, above PCIe's 55 GB/s).
+// ----------------------------------------------------------------------------
+// Streaming copy for the copier threads: non-temporal stores do not read the destination lines first (a plain store
+// to memory that is not in cache costs a read-for-ownership, i.e. 3 bytes of DRAM traffic per byte copied instead of 2),
+// and glibc only switches to them far above the 4 MB pieces used here.
+static void stream_copy(char* dst, const char* src, size_t len) {
+  if (len < 4096) {
+    memcpy(dst, src, len);
     return;
   }
-  ThreadGroup tg;
-  const size_t chunk = ((bytes + nthr - 1) / nthr + 63) & ~size_t(63);
-  for (int t = 0; t < nthr; ++t) {
-    const size_t o = (size_t)t * chunk;
-    if (o >= bytes) break;
-    const size_t len = std::min(chunk, bytes - o);
-    tg.run([=] { memcpy((char*)dst + o, (const char*)src + o, len); });
+  const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+  if (head) {
+    memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    len -= head;
   }
-  tg.join();
+  const size_t n = len / 64;
+  for (size_t i = 0; i < n; ++i) {
+    const __m128i a = _mm_loadu_si128((const __m128i*)(src + 64 * i));
+    const __m128i b = _mm_loadu_si128((const __m128i*)(src + 64 * i + 16));
+    const __m128i c2 = _mm_loadu_si128((const __m128i*)(src + 64 * i + 32));
+    const __m128i d = _mm_loadu_si128((const __m128i*)(src + 64 * i + 48));
+    _mm_stream_si128((__m128i*)(dst + 64 * i), a);
+    _mm_stream_si128((__m128i*)(dst + 64 * i + 16), b);
+    _mm_stream_si128((__m128i*)(dst + 64 * i + 32), c2);
+    _mm_stream_si128((__m128i*)(dst + 64 * i + 48), d);
+  }
+  _mm_sfence();
+  if (len > 64 * n) memcpy(dst + 64 * n, src + 64 * n, len - 64 * n);
 }
 
-constexpr size_t kStageBytes = size_t(64) << 20;
+// Geometry measured on the B200 box (scripts/e2e_sweep.py, profiles/e2e_sweep_r02.json; 1.6 GB result, 16 host threads):
+// 8 x 32 MB slots / 4 MB pieces / blocking events 43.5 ms; 16 x 4 MB / 512 KB / spinning 35.7 ms (pinned buffers: 32 ms).
+// A 64 MB ring stays in the last-level cache the DMA engine writes into, so the copier threads read the data from
+// cache instead of DRAM; small slots need low-latency wake-ups, hence the spin on the DMA events.
+static size_t g_stage_slot_bytes = size_t(4) << 20;   // env BIXCOR_STAGE_SLOT_MB
+static int g_stage_slots = 16;                         // env BIXCOR_STAGE_SLOTS (<= kMaxSlots)
+static size_t g_stage_piece = size_t(512) << 10;       // env BIXCOR_STAGE_PIECE_KB
+static int g_stage_nt = 1;                             // env BIXCOR_STAGE_NT: streaming stores into the caller's buffer
+static int g_stage_spin = 1;                           // env BIXCOR_STAGE_SPIN: copier threads spin on the DMA events instead of blocking
 
-// Host -> device.  Pinned sources are DMA'd directly; pageable ones are copied
-// through a pinned double buffer (multi-threaded memcpy overlapping the DMA).
+struct HostStager {
+  static constexpr int kMaxSlots = 64;
+  size_t kSlotBytes = g_stage_slot_bytes;
+  size_t kPiece = g_stage_piece;
+  int kSlots = g_stage_slots;
+  struct Slot {
+    void* ptr = nullptr;
+    cudaEvent_t dma_done = nullptr;  // D2H: data has landed in the slot; H2D: the DMA has read the slot
+    int pieces_left = 0;             // host copies still running on this slot
+    bool dma_pending = false;        // H2D: dma_done must be waited for before the slot is refilled
+  };
+  struct Task {
+    int slot;
+    char* dst;
+    const char* src;
+    size_t len;
+    bool wait_dma;  // D2H piece: wait for the slot's DMA first
+  };
+  int device = 0;
+  Slot slots[kMaxSlots];
+  int next_slot = 0;
+  std::mutex m;
+  std::condition_variable cv_task, cv_slot;
+  std::vector<Task> queue;  // LIFO is fine: pieces are independent
+  size_t queue_head = 0;
+  bool stop = false;
+  int error = 0;  // first cudaError_t seen by a worker
+  std::vector<std::thread> workers;
+
+  void worker() {
+    cudaSetDevice(device);
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv_task.wait(lk, [&] { return stop || queue_head < queue.size(); });
+        if (queue_head >= queue.size()) return;  // stop requested and nothing left
+        t = queue[queue_head++];
+        if (queue_head == queue.size()) {
+          queue.clear();
+          queue_head = 0;
+        }
+      }
+      cudaError_t e = cudaSuccess;
+      if (t.wait_dma) e = cudaEventSynchronize(slots[t.slot].dma_done);
+      if (e == cudaSuccess) {
+        if (t.wait_dma && g_stage_nt) stream_copy(t.dst, t.src, t.len);  // into the caller's (cold) buffer
+        else memcpy(t.dst, t.src, t.len);
+      }
+      {
+        std::lock_guard<std::mutex> lk(m);
+        if (e != cudaSuccess && !error) error = (int)e;
+        if (--slots[t.slot].pieces_left == 0) cv_slot.notify_all();
+      }
+    }
+  }
+  // the calling thread: next slot of the ring, once its previous host copies (and H2D DMA) are done
+  int acquire(int* out_slot) {
+    const int sidx = next_slot;
+    next_slot = (next_slot + 1) % kSlots;
+    {
+      std::unique_lock<std::mutex> lk(m);
+      cv_slot.wait(lk, [&] { return slots[sidx].pieces_left == 0; });
+      if (error) return fail(BIXCOR_ERR_CUDA, "staging copy: %s", cudaGetErrorString((cudaError_t)error));
+    }
+    if (slots[sidx].dma_pending) {
+      CU_TRY(cudaEventSynchronize(slots[sidx].dma_done));
+      slots[sidx].dma_pending = false;
+    }
+    *out_slot = sidx;
+    return BIXCOR_OK;
+  }
+  // split [0, len) of a slot into pieces for the pool; host_ptr is the caller's memory
+  void post(int sidx, char* host_ptr, size_t len, bool to_host) {
+    std::lock_guard<std::mutex> lk(m);
+    for (size_t o = 0; o < len; o += kPiece) {
+      const size_t l = std::min(kPiece, len - o);
+      Task t;
+      t.slot = sidx;
+      t.len = l;
+      t.wait_dma = to_host;
+      t.dst = to_host ? host_ptr + o : (char*)slots[sidx].ptr + o;
+      t.src = to_host ? (const char*)slots[sidx].ptr + o : host_ptr + o;
+      queue.push_back(t);
+      slots[sidx].pieces_left++;
+    }
+    cv_task.notify_all();
+  }
+  int wait_slot(int sidx) {
+    std::unique_lock<std::mutex> lk(m);
+    cv_slot.wait(lk, [&] { return slots[sidx].pieces_left == 0; });
+    if (error) return fail(BIXCOR_ERR_CUDA, "staging copy: %s", cudaGetErrorString((cudaError_t)error));
+    return BIXCOR_OK;
+  }
+  int drain() {
+    for (int i = 0; i < kSlots; ++i) RC_TRY(wait_slot(i));
+    return BIXCOR_OK;
+  }
+};
+
+static int g_copy_threads = 0;  // env BIXCOR_COPY_THREADS; 0 = from the host's core count
+
+static int stager_get(Ctx* c, HostStager** out) {
+  if (c->stager) {
+    *out = c->stager;
+    return BIXCOR_OK;
+  }
+  HostStager* st = new HostStager();
+  st->device = c->device;
+  for (int si = 0; si < st->kSlots; ++si) {
+    auto& sl = st->slots[si];
+    if (cudaMallocHost(&sl.ptr, st->kSlotBytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.dma_done, cudaEventDisableTiming | (g_stage_spin ? 0 : cudaEventBlockingSync)) != cudaSuccess) {
+      cudaGetLastError();
+      c->stager = st;  // partially built: released below
+      stager_destroy(c);
+      return fail(BIXCOR_ERR_OOM, "cannot allocate the pinned staging ring (%d x %zu MB)", g_stage_slots, g_stage_slot_bytes >> 20);
+    }
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  int nd = std::max<int>(1, (int)g_ctx.size());
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) nd = std::max(nd, atoi(lw));  // one process per GPU (torchrun): share the cores
+  int nthr = g_copy_threads > 0 ? g_copy_threads : (int)std::max(2u, std::min(14u, (hw > 2 ? hw - 2 : 1u) / (unsigned)nd));
+  c->stager = st;
+  try {
+    for (int t = 0; t < nthr; ++t) st->workers.emplace_back([st] {
+      try {
+        st->worker();
+      } catch (...) {  // (mutex / condition variable failure: the pool stops, callers see the error flag)
+        std::lock_guard<std::mutex> lk(st->m);
+        if (!st->error) st->error = (int)cudaErrorUnknown;
+        st->cv_slot.notify_all();
+      }
+    });
+  } catch (...) {
+    if (st->workers.empty()) {
+      stager_destroy(c);
+      throw;
+    }
+  }
+  *out = st;
+  return BIXCOR_OK;
+}
+
+static void stager_destroy(Ctx* c) {
+  HostStager* st = c->stager;
+  if (!st) return;
+  {
+    std::lock_guard<std::mutex> lk(st->m);
+    st->stop = true;
+    st->cv_task.notify_all();
+  }
+  for (auto& t : st->workers)
+    if (t.joinable()) t.join();
+  for (auto& sl : st->slots) {
+    if (sl.dma_done) cudaEventDestroy(sl.dma_done);
+    if (sl.ptr) cudaFreeHost(sl.ptr);
+  }
+  delete st;
+  c->stager = nullptr;
+}
+
+// Host -> device.  Pinned sources are DMA'd directly; pageable ones go through the pinned ring: the pool copies
+// the caller's memory into slot k + 1 while slot k is on the wire.
 static int h2d(Ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return BIXCOR_OK;
   if (is_pinned(h_src)) {
     CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
     return BIXCOR_OK;
   }
-  for (auto& b : c->stage) RC_TRY(b.reserve(kStageBytes));
-  cudaEvent_t done[2];
-  for (auto& e : done) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  int buf = 0;
-  for (size_t o = 0; o < bytes; o += kStageBytes, buf ^= 1) {
-    const size_t len = std::min(kStageBytes, bytes - o);
-    if (o >= 2 * kStageBytes) CU_TRY(cudaEventSynchronize(done[buf]));
-    parallel_memcpy(c->stage[buf].ptr, (const char*)h_src + o, len);
-    CU_TRY(cudaMemcpyAsync((char*)d_dst + o, c->stage[buf].ptr, len, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaEventRecord(done[buf], s));
+  HostStager* st;
+  RC_TRY(stager_get(c, &st));
+  int prev = -1;
+  size_t prev_off = 0, prev_len = 0;
+  auto issue = [&](int sidx, size_t off, size_t len) -> int {  // host copies of the slot are done: put it on the wire
+    RC_TRY(st->wait_slot(sidx));
+    CU_TRY(cudaMemcpyAsync((char*)d_dst + off, st->slots[sidx].ptr, len, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, s));
+    st->slots[sidx].dma_pending = true;
+    return BIXCOR_OK;
+  };
+  for (size_t o = 0; o < bytes; o += st->kSlotBytes) {
+    const size_t len = std::min(st->kSlotBytes, bytes - o);
+    int sidx = 0;
+    RC_TRY(st->acquire(&sidx));
+    st->post(sidx, (char*)const_cast<void*>(h_src) + o, len, false);
+    if (prev >= 0) RC_TRY(issue(prev, prev_off, prev_len));
+    prev = sidx;
+    prev_off = o;
+    prev_len = len;
   }
-  CU_TRY(cudaStreamSynchronize(s));
-  for (auto& e : done) cudaEventDestroy(e);
+  if (prev >= 0) RC_TRY(issue(prev, prev_off, prev_len));
+  CU_TRY(cudaStreamSynchronize(s));  // the caller's buffer may be reused, the ring is free again
+  for (auto& sl : st->slots) sl.dma_pending = false;
   return BIXCOR_OK;
 }
 
-// Device -> host of one finished range; `ready` (may be null) gates the copy.
+// Device -> host of finished ranges; `ready` (may be null) gates the copy.  Pinned destinations: plain async DMA.
+// Pageable destinations: DMA into the pinned ring on the copy stream, the pool moves every landed slot into the
+// caller's memory; the calling thread never copies and only blocks when all slots are in flight.
 struct D2HPipe {
   Ctx* c;
   bool pinned_dst;
-  int buf = 0;
-  struct Pending {
-    void* h_dst;
-    size_t len;
-    cudaEvent_t ev;
-    bool active = false;
-  } pend[2];
+  HostStager* st = nullptr;
   explicit D2HPipe(Ctx* c_, const void* h_dst_probe) : c(c_), pinned_dst(is_pinned(h_dst_probe)) {}
-  int flush_slot(int b) {
-    if (!pend[b].active) return BIXCOR_OK;
-    CU_TRY(cudaEventSynchronize(pend[b].ev));
-    parallel_memcpy(pend[b].h_dst, c->stage[b].ptr, pend[b].len);
-    cudaEventDestroy(pend[b].ev);
-    pend[b].active = false;
-    return BIXCOR_OK;
-  }
   int push(void* h_dst, const void* d_src, size_t bytes, cudaEvent_t ready) {
     if (bytes == 0) return BIXCOR_OK;
     if (ready) CU_TRY(cudaStreamWaitEvent(c->copy_out, ready, 0));
@@ -813,23 +1006,19 @@ struct D2HPipe {
       CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->copy_out));
       return BIXCOR_OK;
     }
-    for (auto& b : c->stage) RC_TRY(b.reserve(kStageBytes));
-    for (size_t o = 0; o < bytes; o += kStageBytes) {
-      const size_t len = std::min(kStageBytes, bytes - o);
-      RC_TRY(flush_slot(buf));
-      CU_TRY(cudaMemcpyAsync(c->stage[buf].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
-      CU_TRY(cudaEventCreateWithFlags(&pend[buf].ev, cudaEventDisableTiming));
-      CU_TRY(cudaEventRecord(pend[buf].ev, c->copy_out));
-      pend[buf].h_dst = (char*)h_dst + o;
-      pend[buf].len = len;
-      pend[buf].active = true;
-      buf ^= 1;
+    if (!st) RC_TRY(stager_get(c, &st));
+    for (size_t o = 0; o < bytes; o += st->kSlotBytes) {
+      const size_t len = std::min(st->kSlotBytes, bytes - o);
+      int sidx = 0;
+      RC_TRY(st->acquire(&sidx));
+      CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
+      CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
+      st->post(sidx, (char*)h_dst + o, len, true);
     }
     return BIXCOR_OK;
   }
   int finish() {
-    RC_TRY(flush_slot(buf));
-    RC_TRY(flush_slot(buf ^ 1));
+    if (st) RC_TRY(st->drain());
     CU_TRY(cudaStreamSynchronize(c->copy_out));
     return BIXCOR_OK;
   }
@@ -982,6 +1171,7 @@ static int dev_affinity(Ctx* c, const double* d_x, int64_t n, int64_t p, int spe
   e.mirror = full ? 1 : 0;
   e.diag_one = 1;
   set_beta(e, beta, keep_sign);
+  e.abs_out = (!keep_sign && beta == 1.0) ? 1 : 0;  // unsigned affinity without a power: |r| (for beta != 1, |r|^beta already is)
   return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_DENSE, e, nullptr, row_begin, row_end);
 }
 
@@ -1316,6 +1506,12 @@ int bixcor_init_devices(int first_device, int n_gpus) {
                 count);
   if (const char* v = getenv("BIXCOR_DMMA_VARIANT")) g_dmma_variant = atoi(v);
   if (const char* v = getenv("BIXCOR_UMMA_CTAS")) g_umma_ctas = (atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 2;
+  if (const char* v = getenv("BIXCOR_COPY_THREADS")) g_copy_threads = std::max(0, std::min(64, atoi(v)));
+  if (const char* v = getenv("BIXCOR_STAGE_SLOT_MB")) g_stage_slot_bytes = (size_t)std::max(1, std::min(256, atoi(v))) << 20;
+  if (const char* v = getenv("BIXCOR_STAGE_SLOTS")) g_stage_slots = std::max(2, std::min((int)HostStager::kMaxSlots, atoi(v)));
+  if (const char* v = getenv("BIXCOR_STAGE_PIECE_KB")) g_stage_piece = (size_t)std::max(64, std::min(65536, atoi(v))) << 10;
+  if (const char* v = getenv("BIXCOR_STAGE_NT")) g_stage_nt = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_STAGE_SPIN")) g_stage_spin = atoi(v) != 0;
   for (int d = 0; d < n_gpus; ++d) {
     Ctx* c = nullptr;
     int rc = ctx_create(first_device + d, &c);

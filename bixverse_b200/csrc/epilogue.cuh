@@ -30,6 +30,7 @@ struct EpiParams {
   double beta;
   int beta_int;      // > 0: beta is this small integer (multiplication chain instead of pow)
   int keep_sign;
+  int abs_out;       // beta == 1 only: write |r| (the abs() of calculate_tom_from_exp for unsigned networks, R/functions_stats.R:114-116)
   double* r_a;
   double* r_b;
   double* z;
@@ -67,7 +68,7 @@ __device__ __forceinline__ double epi_power(const EpiParams& E, double r) {
     const double a = rbf_apply(E.rbf_mode, E.rbf_eps, d);
     return E.rbf_complement ? 1.0 - a : a;
   }
-  if (E.beta == 1.0) return r;
+  if (E.beta == 1.0) return E.abs_out ? fabs(r) : r;
   double a = fabs(r);
   const int bi = E.beta_int;  // warp-uniform: the branches below never diverge
   if (bi > 0) {

@@ -812,7 +812,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int keep_sign = E.keep_sign;
     const double scale = E.scale * (KIND == KIND_F16 ? kF16Unscale : 1.0);  // f16 planes carry 2^10 each
     // 1 identity, 6 = WGCNA default, 0 generic (any other exponent, or an RBF transform)
-    const int pw_mode = E.rbf_mode ? 0 : ((E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0));
+    const int pw_mode = (E.rbf_mode || E.abs_out) ? 0 : ((E.beta == 1.0) ? 1 : (E.beta_int == 6 ? 6 : 0));
     long long prof_acc[4] = {0, 0, 0, 0};
     // tempty arrives go to the leader CTA's barrier (its MMA warp is the only consumer)
     auto arrive_tempty = [&](int st) {

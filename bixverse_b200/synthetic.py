@@ -16,22 +16,30 @@ import numpy as np
 
 
 def synthetic_bulk(n_samples: int, n_genes: int, seed: int, n_modules: int | None = None,
-                   tie_heavy: bool = False) -> np.ndarray:
+                   tie_heavy: bool = False, structure_seed: int | None = None, rewire_frac: float = 0.0) -> np.ndarray:
+    """`structure_seed` (optional) fixes the gene means and the planted module structure independently of the sample
+    draw (`seed`), so two matrices can share their co-expression structure; `rewire_frac` of the modules (the first
+    ones) then get a freshly drawn gene set instead - the rewired modules of a differential-correlation pair."""
     rng = np.random.default_rng(seed)
+    srng = rng if structure_seed is None else np.random.default_rng(structure_seed)
     if n_modules is None:
         n_modules = max(3, min(20, n_genes // 400))
-    mean = rng.gamma(shape=5.0, scale=10.0, size=n_genes)
+    mean = srng.gamma(shape=5.0, scale=10.0, size=n_genes)
     log_mu = np.log(mean)[None, :] + rng.normal(0.0, 0.1, size=(n_samples, n_genes))
     # planted modules: disjoint gene sets sharing a latent factor
-    sizes = rng.integers(100, 201, size=n_modules)
+    sizes = srng.integers(100, 201, size=n_modules)
     sizes = np.minimum(sizes, max(2, n_genes // (n_modules + 1)))
-    perm = rng.permutation(n_genes)
+    perm = srng.permutation(n_genes)
+    n_rewired = int(round(rewire_frac * n_modules)) if structure_seed is not None else 0
+    wrng = np.random.default_rng((structure_seed or 0) + 7919)
     start = 0
     for m in range(n_modules):
         genes = perm[start : start + sizes[m]]
         start += sizes[m]
+        if m < n_rewired:  # this module is made of other genes in the rewired condition
+            genes = wrng.choice(n_genes, size=genes.shape[0], replace=False)
         factor = rng.normal(0.0, 0.5, size=n_samples)
-        loading = rng.lognormal(0.0, 0.7, size=genes.shape[0]) * rng.choice([-1.0, 1.0], size=genes.shape[0], p=[0.2, 0.8])
+        loading = srng.lognormal(0.0, 0.7, size=genes.shape[0]) * srng.choice([-1.0, 1.0], size=genes.shape[0], p=[0.2, 0.8])
         log_mu[:, genes] += factor[:, None] * loading[None, :]
     mu = np.exp(log_mu)
     disp = 1.0 / (0.2 + 0.3 * mean)  # NB size parameter r = 1/disp
@@ -46,8 +54,10 @@ def synthetic_bulk(n_samples: int, n_genes: int, seed: int, n_modules: int | Non
 
 
 def synthetic_pair(n_a: int, n_b: int, n_genes: int, seed: int) -> tuple[np.ndarray, np.ndarray]:
-    """Config 3: two draws; the second has a different module assignment for ~25 % of modules."""
-    return synthetic_bulk(n_a, n_genes, seed), synthetic_bulk(n_b, n_genes, seed + 1)
+    """Config 3: two conditions with the same gene means and module structure; in the second, 25 % of the
+    modules are rewired (made of a different gene set), which is what the differential correlation should find."""
+    return (synthetic_bulk(n_a, n_genes, seed, structure_seed=seed),
+            synthetic_bulk(n_b, n_genes, seed + 1, structure_seed=seed, rewire_frac=0.25))
 
 
 def synthetic_sparse_cells(n_cells: int, n_genes: int, seed: int, density: float = 0.05):

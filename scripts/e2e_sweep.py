@@ -1,0 +1,68 @@
+"""Sweep of the pageable staging pipeline (HostStager in csrc/bixcor.cu): ring geometry, copier threads, streaming stores.
+Each setting runs in its own process (the knobs are read at bixcor_init).  Usage: python scripts/e2e_sweep.py [--out f.json]
+Child mode: python scripts/e2e_sweep.py --child  (prints one JSON line for the current environment)."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def child():
+    import numpy as np
+
+    from bixverse_b200 import _lib, api
+
+    n, p = 1000, 20000
+    x = np.ascontiguousarray(np.random.default_rng(0).normal(size=(p, n)))  # gene-major == R's column-major n x p
+    lib = _lib.load()
+    api.init(1, 0)
+    out = np.zeros(p * (p - 1) // 2)
+    step = lambda: _lib.check(lib.bixcor_cor_upper(x.ctypes.data, n, p, 1, 1, 6.0, _lib.PREC_AUTO, out.ctypes.data))
+    for _ in range(2):
+        step()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    print(json.dumps({"ms_min": 1e3 * min(ts), "ms_med": 1e3 * sorted(ts)[len(ts) // 2]}))
+
+
+def main():
+    settings = [{}]
+    if "--round2" in sys.argv:
+        for slot_mb, slots, piece in ((8, 8, 1024), (4, 16, 512), (2, 16, 256), (4, 8, 512), (16, 8, 1024), (8, 16, 512)):
+            for spin in (0, 1):
+                settings.append({"BIXCOR_STAGE_SLOT_MB": slot_mb, "BIXCOR_STAGE_SLOTS": slots, "BIXCOR_STAGE_PIECE_KB": piece, "BIXCOR_STAGE_SPIN": spin})
+        settings.append({"BIXCOR_STAGE_SLOT_MB": 8, "BIXCOR_STAGE_SLOTS": 8, "BIXCOR_STAGE_PIECE_KB": 1024, "BIXCOR_COPY_THREADS": 10})
+        settings.append({"BIXCOR_STAGE_SLOT_MB": 8, "BIXCOR_STAGE_SLOTS": 8, "BIXCOR_STAGE_PIECE_KB": 1024, "BIXCOR_COPY_THREADS": 16})
+    else:
+        for slot_mb, slots in ((32, 8), (16, 8), (8, 8), (4, 8), (2, 16), (8, 16), (64, 4)):
+            settings.append({"BIXCOR_STAGE_SLOT_MB": slot_mb, "BIXCOR_STAGE_SLOTS": slots})
+        for thr in (4, 8, 12, 16):
+            settings.append({"BIXCOR_COPY_THREADS": thr})
+        settings.append({"BIXCOR_STAGE_NT": 0})
+        settings.append({"BIXCOR_STAGE_NT": 0, "BIXCOR_STAGE_SLOT_MB": 4, "BIXCOR_STAGE_SLOTS": 8})
+        settings.append({"BIXCOR_STAGE_PIECE_KB": 1024})
+        settings.append({"BIXCOR_STAGE_PIECE_KB": 1024, "BIXCOR_STAGE_SLOT_MB": 8, "BIXCOR_STAGE_SLOTS": 8})
+    rows = []
+    for s in settings:
+        env = dict(os.environ)
+        env.update({k: str(v) for k, v in s.items()})
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True, text=True)
+        try:
+            res = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            res = {"error": (r.stderr or r.stdout)[-300:]}
+        rows.append({"env": s, **res})
+        print(json.dumps(rows[-1]), flush=True)
+    if "--out" in sys.argv:
+        json.dump(rows, open(sys.argv[sys.argv.index("--out") + 1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    child() if "--child" in sys.argv else main()

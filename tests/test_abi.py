@@ -147,3 +147,35 @@ def test_product_package_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt, f
+
+
+def test_exception_barrier_stops_injected_failures(lib_built):
+    """include/bixcor.h: no C++ exception crosses the ABI.  bixcor_debug_inject makes the NEXT entry point throw from
+    inside its body; the barrier turns std::bad_alloc into BIXCOR_ERR_OOM and anything else into BIXCOR_ERR_INTERNAL,
+    and the library keeps working afterwards.  (Host-only entry point, so this runs without a GPU.)"""
+    from bixverse_b200 import _lib
+
+    lib = _lib.load()
+    packed = np.array([0.3, 0.0, 1.0, 0.0, 0.2, -0.5])
+    out = np.empty((4, 4), order="F")
+    for what, code, text in ((1, _lib.ERR_OOM, b"std::bad_alloc"), (2, _lib.ERR_INTERNAL, b"injected failure")):
+        assert lib.bixcor_debug_inject(what) == 0
+        rc = lib.bixcor_upper_to_dense(packed.ctypes.data, 1, 4, out.ctypes.data)
+        assert rc == code, rc
+        msg = lib.bixcor_last_error()
+        assert text in msg and b"bixcor_upper_to_dense" in msg
+        assert lib.bixcor_upper_to_dense(packed.ctypes.data, 1, 4, out.ctypes.data) == 0  # one-shot: the next call is clean
+        assert out[0, 1] == 0.3 and out[3, 3] == 1.0
+    lib.bixcor_debug_inject(1)
+    assert lib.bixcor_upper_to_sparse_nnz(packed.ctypes.data, 1, 4) == -1  # count-returning entry point: -1 on failure
+
+
+def test_small_p_shards_are_empty_not_invalid(lib_built):
+    """for 99 <= p <= 127 and 5-8 ranks the 128-aligned boundaries clamp to p and a rank owns (p, p)."""
+    from bixverse_b200 import api
+
+    for p in (99, 120, 127):
+        ranges = [api.shard_rows(p, True, 8, r) for r in range(8)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == p
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert sum(1 for r0, r1 in ranges if r1 > r0) == 1  # one rank owns everything, the others are empty

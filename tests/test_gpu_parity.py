@@ -211,7 +211,7 @@ def test_cor_module_tom_fused(api, shift):
         got = api.cor_module_tom(res, signed, version)
         dense = o.upper_triangle_to_dense(packed, shift, 450)
         ref = o.dense_to_upper_triangle(o.calc_tom(dense, signed, version), True)  # rs_tom level: the matrix as passed
-        assert got.shift and _maxerr(got.values, ref) < TOL64
+        assert got.shift and _maxerr(got.values, ref) < TOL64 * max(1.0, float(np.abs(ref).max()))
         chain = api.rs_dense_to_upper_triangle(api.rs_tom(api.rs_upper_triangle_to_dense(packed, shift, 450), version, signed), True)
         assert _maxerr(got.values, chain) < 1e-13
 
@@ -771,3 +771,94 @@ def test_ozaki_nan_and_constant_columns(api):
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     ok = ~np.isnan(ref)
     assert np.abs(got[ok] - ref[ok]).max() < TOL64
+
+
+# ----------------------------------------------------------------------------- boundary behaviour (round 2)
+def test_row_range_contract(api):
+    """bixcor.h: row_begin % 128 == 0, row_end % 128 == 0 or row_end == p; empty ranges are no-ops wherever they start
+    (a ragged row_end wrote past the caller's slice; empty shards of a small module were rejected)."""
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    x = synthetic_bulk(50, 300, seed=3)
+    for bad in ((0, 200), (128, 129), (64, 300)):
+        with pytest.raises(api.BixcorError) as ei:
+            api.rs_cor_upper_triangle(x, False, True, rows=bad)
+        assert ei.value.code == -2
+    assert api.rs_cor_upper_triangle(x, False, True, rows=(300, 300)).shape[0] == 0
+    assert api.rs_cor_upper_triangle(x, False, True, rows=(77, 77)).shape[0] == 0
+    # a 120-gene module over 8 ranks: seven empty shards + one that owns the whole triangle
+    x = synthetic_bulk(40, 120, seed=4)
+    full = api.rs_cor_upper_triangle(x, True, True)
+    parts = [api.rs_cor_upper_triangle(x, True, True, rows=api.shard_rows(120, True, 8, r)) for r in range(8)]
+    assert np.array_equal(np.concatenate(parts), full)
+    xa, xb = synthetic_bulk(30, 120, seed=5), synthetic_bulk(33, 120, seed=6)
+    lib = __import__("bixverse_b200._lib", fromlist=["load"]).load()
+    a, b = np.asfortranarray(xa), np.asfortranarray(xb)
+    dummy = np.zeros(4)
+    assert lib.bixcor_diffcor_rows(a.ctypes.data, 30, b.ctypes.data, 33, 120, 0, 0, 120, 120, *[dummy.ctypes.data] * 4) == 0
+
+
+def test_precision_auto_policy(api, monkeypatch):
+    """BIXCOR_PREC_AUTO (what INTEGRATION.md's patched bodies pass): Spearman with n <= 1860 -> exact-integer tcgen05
+    Gram, everything else FP64; env BIXCOR_PRECISION replaces the rule; an undefined choice falls back to it."""
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    monkeypatch.delenv("BIXCOR_PRECISION", raising=False)
+    x = synthetic_bulk(200, 500, seed=8, tie_heavy=True)
+    auto = lambda sp, **kw: api.rs_cor_upper_triangle(x, sp, True, precision=_lib.PREC_AUTO, **kw)
+    assert np.array_equal(auto(True), api.rs_cor_upper_triangle(x, True, True, precision=_lib.PREC_I8EXACT))
+    assert np.array_equal(auto(False), api.rs_cor_upper_triangle(x, False, True, precision=_lib.PREC_F64))
+    assert np.array_equal(auto(True, beta=6.0), api.rs_cor_upper_triangle(x, True, True, beta=6.0, precision=_lib.PREC_I8EXACT))
+    xl = np.random.default_rng(2).normal(size=(1900, 130))  # n > 1860: the int32 recombination could overflow -> FP64
+    assert np.array_equal(api.rs_cor_upper_triangle(xl, True, True, precision=_lib.PREC_AUTO),
+                          api.rs_cor_upper_triangle(xl, True, True, precision=_lib.PREC_F64))
+    assert _maxerr(api.rs_cor(x, True, precision=_lib.PREC_AUTO), o.column_pairwise_cor(x, True)) < 1e-12  # dense epilogue too
+    d_auto = api.rs_differential_cor(x[:90], x[90:], True, precision=_lib.PREC_AUTO)
+    d_i8 = api.rs_differential_cor(x[:90], x[90:], True, precision=_lib.PREC_I8EXACT)
+    assert all(np.array_equal(d_auto[k], d_i8[k], equal_nan=True) for k in d_auto)
+    t_auto = api.calculate_tom_from_exp(x, True, "v1", "spearman", precision=_lib.PREC_AUTO)
+    assert _maxerr(t_auto, o.tom_from_exp(x, True, "v1", True)) < TOL64
+    monkeypatch.setenv("BIXCOR_PRECISION", "tf32")
+    assert np.array_equal(auto(False), api.rs_cor_upper_triangle(x, False, True, precision=_lib.PREC_TF32X3))
+    monkeypatch.setenv("BIXCOR_PRECISION", "i8")
+    assert np.array_equal(auto(False), api.rs_cor_upper_triangle(x, False, True, precision=_lib.PREC_F64))  # Pearson: undefined
+    monkeypatch.setenv("BIXCOR_PRECISION", "f64")
+    assert np.array_equal(auto(True), api.rs_cor_upper_triangle(x, True, True, precision=_lib.PREC_F64))
+    monkeypatch.delenv("BIXCOR_PRECISION")
+    with pytest.raises(api.BixcorError):
+        api.rs_cor_upper_triangle(x, False, True, precision=-7)
+
+
+def test_exception_barrier_on_a_gpu_entry_point(api):
+    from bixverse_b200 import _lib
+
+    x = np.random.default_rng(3).normal(size=(20, 40))
+    lib = _lib.load()
+    lib.bixcor_debug_inject(1)
+    with pytest.raises(api.BixcorError) as ei:
+        api.rs_cor(x, False)
+    assert ei.value.code == _lib.ERR_OOM and "bixcor_cor_dense" in ei.value.message
+    lib.bixcor_debug_inject(2)
+    with pytest.raises(api.BixcorError) as ei:
+        api.rs_tom(np.eye(5), "v1", True)
+    assert ei.value.code == _lib.ERR_INTERNAL
+    assert _maxerr(api.rs_cor(x, False), o.column_pairwise_cor(x, False)) < TOL64  # and the library still works
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_rs_tom_unsigned_uses_the_matrix_as_passed(api, version):
+    """abs() for unsigned networks belongs to the R wrappers (R/functions_stats.R:52-54), not to rs_tom:
+    cor_module_tom (R/methods_coexp_cor.R:151) hands rs_tom the raw correlation.  rs_tom(signed = FALSE) on a matrix with
+    negative entries follows the documented unsigned formulas on a_ij itself; calculate_tom takes abs() first."""
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-0.2, 0.9, size=(150, 150))
+    a = 0.5 * (a + a.T)
+    np.fill_diagonal(a, 1.0)
+    raw = api.rs_tom(a, version, False)
+    ref_raw = o.calc_tom(a, False, version)
+    off = ~np.eye(150, dtype=bool)
+    assert np.abs(raw - ref_raw)[off].max() < 1e-10 * max(1.0, np.abs(ref_raw[off]).max())
+    wrapped = api.calculate_tom(a, False, version)
+    assert _maxerr(wrapped, o.calculate_tom(a, False, version)) < TOL64
+    assert np.abs(raw - wrapped)[off].max() > 1e-3  # the two semantics differ once an entry is negative
