@@ -27,6 +27,7 @@ SIGNATURES = {
     "bixcor_init": (i32, [i32]),
     "bixcor_init_devices": (i32, [i32, i32]),
     "bixcor_shutdown": (None, []),
+    "bixcor_nccl_version": (i32, []),
     "bixcor_last_error": (C.c_char_p, []),
     "bixcor_launch_count": (i64, []),
     "bixcor_set_fieller": (i32, [f64]),

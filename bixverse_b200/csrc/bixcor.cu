@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "gram_dmma.cuh"
 #include "gram_umma.cuh"
+#include "nccl_dyn.h"
 
 namespace bixcor {
 
@@ -186,6 +187,7 @@ struct Ctx {
   Buffer panel;         // sparse dense panel
   Buffer sparse_in;     // staged CSR
   Buffer flag;          // one int: device-side overflow / range flags read back by the host
+  Buffer rank_scratch;  // sorted chunks / ranks of the n > 16384 Spearman path
   Buffer tile_sync;     // two words: arrival / bail-out counters of the long-K producer barrier (gram_umma.cuh)
   HostStager* stager = nullptr;
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
@@ -198,6 +200,22 @@ struct Ctx {
 };
 
 static std::vector<Ctx*> g_ctx;
+// NCCL communicators over the devices of this process (bixcor_init(n), n > 1): g_comms[d] belongs to g_ctx[d].
+// Empty when there is one device, when libnccl cannot be opened or with env BIXCOR_NCCL=0 (the multi-device entry
+// points then exchange with peer copies / through the host, as in round 1).
+static NcclApi g_nccl;
+static std::vector<ncclComm_t> g_comms;
+#define NCCL_TRY(expr)                                                                                        \
+  do {                                                                                                        \
+    ncclResult_t r__ = (expr);                                                                                \
+    if (r__ != ncclSuccess)                                                                                   \
+      return fail(BIXCOR_ERR_CUDA, "%s:%d %s: NCCL %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(r__)); \
+  } while (0)
+static void nccl_teardown() {
+  for (auto cm : g_comms)
+    if (cm) g_nccl.CommDestroy(cm);
+  g_comms.clear();
+}
 static std::mutex g_init_mu;
 static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM: measured fastest), env BIXCOR_DMMA_VARIANT
 static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
@@ -241,6 +259,7 @@ static void ctx_destroy(Ctx* c) {
   c->sparse_in.release();
   c->flag.release();
   c->tile_sync.release();
+  c->rank_scratch.release();
   stager_destroy(c);
   for (auto& kv : c->tile_cache)
     if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
@@ -485,6 +504,48 @@ static int tom_cor_precision(int tom_precision, int spearman, int64_t n) {
   return (is_split_float(tom_precision) || is_ozaki(tom_precision)) ? tom_precision : BIXCOR_PREC_F64;
 }
 
+// ColumnOut addressed from gene `g0` on (the column kernels index their outputs by the gene number inside the launch)
+static ColumnOut column_out_from(ColumnOut co, int64_t g0) {
+  if (co.f64) co.f64 += g0 * co.ld64;
+  if (co.i8) co.i8 += g0 * co.ld8;
+  if (co.f32) {
+    if (co.half_planes) co.f32 = (float*)((__half*)co.f32 + g0 * co.ld32);
+    else co.f32 += g0 * co.ld32;
+  }
+  if (co.inv_norm) co.inv_norm += g0;
+  return co;
+}
+
+// Spearman for n > 16384 samples: chunked shared-memory sorts + rank by counting (columns.cuh), genes in batches so that
+// the scratch (12 bytes per padded sample for the sorted chunks, 4 per sample for the ranks) stays below ~2 GB.
+// ld = column stride of d_x in elements.
+static int launch_rank_big(Ctx* c, const double* d_x, int64_t ld, int n, int64_t p, const ColumnOut& co) {
+  if ((int64_t)n > (int64_t(1) << 21))
+    return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman rank kernel supports n <= 2097152 samples (got %d)", n);
+  const int nchunks = (n + kBigChunk - 1) / kBigChunk;
+  const size_t per_gene = (size_t)nchunks * kBigChunk * 12 + (size_t)n * 4 + 16;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(p, (int64_t)((size_t(2) << 30) / per_gene)));
+  RC_TRY(c->rank_scratch.reserve(per_gene * (size_t)batch + 1024));
+  char* base = (char*)c->rank_scratch.ptr;
+  uint64_t* keys = (uint64_t*)base;
+  uint32_t* idx = (uint32_t*)(base + (size_t)batch * nchunks * kBigChunk * 8);
+  uint32_t* rk2 = idx + (size_t)batch * nchunks * kBigChunk;
+  int* nan_flag = (int*)(rk2 + (size_t)batch * n);
+  constexpr int smem = kBigChunk * 12;
+  CU_TRY(cudaFuncSetAttribute(rank_big_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int64_t g0 = 0; g0 < p; g0 += batch) {
+    const int64_t ng = std::min(batch, p - g0);
+    CU_TRY(cudaMemsetAsync(nan_flag, 0, sizeof(int) * (size_t)ng, c->compute));
+    const dim3 grid((unsigned)nchunks, (unsigned)ng);
+    rank_big_sort_kernel<<<grid, kBigThreads, smem, c->compute>>>(d_x + g0 * ld, ld, n, nchunks, keys, idx, nan_flag);
+    rank_big_count_kernel<<<grid, 256, 0, c->compute>>>(keys, idx, n, nchunks, rk2);
+    rank_big_emit_kernel<<<(unsigned)ng, 256, 0, c->compute>>>(rk2, nan_flag, n, column_out_from(co, g0));
+    g_launches += 3;
+  }
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
+
 // Spearman column kernel dispatch: warp-per-gene register sort for n <= 1024, CTA shared-memory sort above.
 static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, const ColumnOut& co) {
   if (n <= 1024) {
@@ -499,12 +560,14 @@ static int launch_rank_kernel(Ctx* c, const double* d_x, int64_t n, int64_t p, c
       case 16: rank_columns_warp_kernel<16><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
       default: rank_columns_warp_kernel<32><<<grid, 128, 0, c->compute>>>(d_x, n, (int)n, p, co); break;
     }
-  } else {
+  } else if (n <= 16384) {
     int npow2 = 2048;
     while (npow2 < n) npow2 <<= 1;
     const size_t smem = (size_t)npow2 * 12;
     CU_TRY(cudaFuncSetAttribute(rank_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rank_columns_kernel<<<(unsigned)p, 256, smem, c->compute>>>(d_x, n, (int)n, npow2, co);
+  } else {
+    return launch_rank_big(c, d_x, n, (int)n, p, co);
   }
   g_launches++;
   CU_TRY(cudaGetLastError());
@@ -536,8 +599,8 @@ static void bind_operand(Operand* op, int64_t n, int64_t p, int precision, const
 static int build_operand(Ctx* c, const double* d_x, int64_t n, int64_t p, int spearman, int precision, int64_t g0,
                          int64_t g1, void* dst, double* inv, int norm_mode = 0) {
   if (n < 2) return fail(BIXCOR_ERR_INVALID, "need at least 2 samples (n = %lld)", (long long)n);
-  if (n > (spearman ? 16384 : (1 << 30)))
-    return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman rank kernel supports n <= 16384 samples (got %lld)", (long long)n);
+  if (n > (spearman ? (1 << 21) : (1 << 30)))
+    return fail(BIXCOR_ERR_UNSUPPORTED, "supported sample counts: n <= 2097152 (Spearman), n <= 2^30 (Pearson); got %lld", (long long)n);
   RC_TRY(check_precision(precision, spearman, n));
   if (g0 < 0 || g1 > p || g0 > g1) return fail(BIXCOR_ERR_INVALID, "bad gene range");
   if (g0 == g1) return BIXCOR_OK;
@@ -996,13 +1059,12 @@ static int h2d(Ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_
 // caller's memory; the calling thread never copies and only blocks when all slots are in flight.
 struct D2HPipe {
   Ctx* c;
-  bool pinned_dst;
   HostStager* st = nullptr;
-  explicit D2HPipe(Ctx* c_, const void* h_dst_probe) : c(c_), pinned_dst(is_pinned(h_dst_probe)) {}
+  explicit D2HPipe(Ctx* c_, const void* = nullptr) : c(c_) {}
   int push(void* h_dst, const void* d_src, size_t bytes, cudaEvent_t ready) {
     if (bytes == 0) return BIXCOR_OK;
     if (ready) CU_TRY(cudaStreamWaitEvent(c->copy_out, ready, 0));
-    if (pinned_dst) {
+    if (is_pinned(h_dst)) {
       CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->copy_out));
       return BIXCOR_OK;
     }
@@ -1454,6 +1516,33 @@ static void parallel_cols(int64_t p, F fn) {
   tg.join();
 }
 
+// Reusable barrier of the per-device host threads; a failed thread makes every thread leave with its code.
+struct PhaseBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, count = 0, gen = 0, rc = BIXCOR_OK;
+  explicit PhaseBarrier(int n_) : n(n_) {}
+  int arrive(int my_rc) {
+    std::unique_lock<std::mutex> lk(m);
+    if (my_rc != BIXCOR_OK && rc == BIXCOR_OK) rc = my_rc;
+    const int g = gen;
+    if (++count == n) {
+      count = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != g; });
+    }
+    return rc;
+  }
+};
+
+static void even_slab(int64_t p, int nd, int d, int64_t* c0, int64_t* c1) {
+  const int64_t nb = (p + kTile - 1) / kTile;
+  *c0 = std::min<int64_t>(p, nb * d / nd * kTile);
+  *c1 = std::min<int64_t>(p, nb * (d + 1) / nd * kTile);
+}
+
 extern "C" {
 
 const char* bixcor_last_error(void) {
@@ -1491,6 +1580,7 @@ int bixcor_init_devices(int first_device, int n_gpus) {
   std::lock_guard<std::mutex> lk(g_init_mu);
   if (!g_ctx.empty()) {
     if ((int)g_ctx.size() == n_gpus && g_ctx[0]->device == first_device) return BIXCOR_OK;
+    nccl_teardown();
     for (auto* c : g_ctx) ctx_destroy(c);
     g_ctx.clear();
   }
@@ -1533,13 +1623,33 @@ int bixcor_init_devices(int first_device, int n_gpus) {
       }
       cudaGetLastError();  // "already enabled" is fine
     }
+  // collectives between the devices of this process (north star: k and the partial Grams are all-reduced with NCCL)
+  const char* nv = getenv("BIXCOR_NCCL");
+  if (n_gpus > 1 && !(nv && atoi(nv) == 0)) {
+    if (g_nccl.load()) {
+      std::vector<int> devs;
+      for (auto* c : g_ctx) devs.push_back(c->device);
+      g_comms.assign((size_t)n_gpus, nullptr);
+      ncclResult_t r = g_nccl.CommInitAll(g_comms.data(), n_gpus, devs.data());
+      if (r != ncclSuccess) {
+        fail(BIXCOR_ERR_CUDA, "ncclCommInitAll: %s (falling back to peer copies)", g_nccl.GetErrorString(r));
+        g_comms.clear();
+      }
+    } else {
+      fail(BIXCOR_ERR_CUDA, "NCCL unavailable: %s (falling back to peer copies)", g_nccl.error);
+    }
+  }
   return BIXCOR_OK;
   API_END
 }
 
+/* NCCL_VERSION_CODE of the library serving the in-process collectives, 0 when they are not active */
+int bixcor_nccl_version(void) { return g_comms.empty() ? 0 : g_nccl.version; }
+
 void bixcor_shutdown(void) {
   try {
     std::lock_guard<std::mutex> lk(g_init_mu);
+    nccl_teardown();
     for (auto* c : g_ctx) ctx_destroy(c);
     g_ctx.clear();
   } catch (...) {
@@ -1719,7 +1829,6 @@ int bixcor_dev_rank_columns(const double* d_x, int64_t n, int64_t p, double* d_o
   API_BEGIN
   DEV_PROLOGUE();
   if (n < 1 || p < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
-  if (n > 16384) return fail(BIXCOR_ERR_UNSUPPORTED, "rank kernel supports n <= 16384");
   ColumnOut co;
   memset(&co, 0, sizeof co);
   co.mode = COL_RANKS;
@@ -1949,10 +2058,28 @@ int bixcor_cor_dense(const double* x, int64_t n, int64_t p, int spearman, int pr
   API_BEGIN
   RC_TRY(ensure_init());
   RC_TRY(host_shape_check(x, n, p, out_pp));
+  const size_t in_bytes = sizeof(double) * (size_t)n * p;
+  if (g_ctx.size() > 1 && p >= 2 * kTile) {
+    // several devices: every device ranks / standardises all genes (cheap) and computes the full-width strip of an equal
+    // gene slab; column i of the column-major result is row i of the strip, so a slab is one contiguous host range
+    return for_each_device([&](Ctx* c, int d, int nd) -> int {
+      int64_t c0, c1;
+      even_slab(p, nd, d, &c0, &c1);
+      if (c1 <= c0) return BIXCOR_OK;
+      RC_TRY(c->x[0].reserve(in_bytes));
+      RC_TRY(c->out.reserve(sizeof(double) * (size_t)p * p));  // strip mode addresses the full matrix
+      RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
+      RC_TRY(dev_affinity(c, (const double*)c->x[0].ptr, n, p, spearman, 1.0, 1, precision, c0, c1, (double*)c->out.ptr));
+      RC_TRY(finish(c));
+      D2HPipe pipe(c);
+      RC_TRY(pipe.push(out_pp + c0 * p, (double*)c->out.ptr + c0 * p, sizeof(double) * (size_t)(c1 - c0) * p, nullptr));
+      return pipe.finish();
+    });
+  }
   Ctx* c = g_ctx[0];
   CU_TRY(cudaSetDevice(c->device));
   call_begin(c);
-  const size_t in_bytes = sizeof(double) * (size_t)n * p, out_bytes = sizeof(double) * (size_t)p * p;
+  const size_t out_bytes = sizeof(double) * (size_t)p * p;
   RC_TRY(c->x[0].reserve(in_bytes));
   RC_TRY(c->out.reserve(out_bytes));
   RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
@@ -2024,43 +2151,18 @@ static int tom_common(Ctx* c, double* d_a, int64_t p, int signed_, int version, 
   return pipe.finish();
 }
 
-// Reusable barrier of the per-device host threads; a failed thread makes every thread leave with its code.
-struct PhaseBarrier {
-  std::mutex m;
-  std::condition_variable cv;
-  int n, count = 0, gen = 0, rc = BIXCOR_OK;
-  explicit PhaseBarrier(int n_) : n(n_) {}
-  int arrive(int my_rc) {
-    std::unique_lock<std::mutex> lk(m);
-    if (my_rc != BIXCOR_OK && rc == BIXCOR_OK) rc = my_rc;
-    const int g = gen;
-    if (++count == n) {
-      count = 0;
-      ++gen;
-      cv.notify_all();
-    } else {
-      cv.wait(lk, [&] { return gen != g; });
-    }
-    return rc;
-  }
-};
-
-static void even_slab(int64_t p, int nd, int d, int64_t* c0, int64_t* c1) {
-  const int64_t nb = (p + kTile - 1) / kTile;
-  *c0 = std::min<int64_t>(p, nb * d / nd * kTile);
-  *c1 = std::min<int64_t>(p, nb * (d + 1) / nd * kTile);
-}
-
 // TOM on every device of the process (bixcor_init(n), n > 1): the same three phases as the one-process-per-GPU
 // driver (bixverse_b200/distributed.py), with cudaMemcpyPeer over NVLink for the slab exchange and the host for k.
 //   phase 1  device d: affinity columns of gene slab d (from x, or uploaded from a_pp) + their connectivity
-//   exchange every device pulls the other slabs into its copy of A; k is gathered through the host
+//   exchange NCCL (communicators of bixcor_init): grouped ncclBroadcast of every slab + ncclAllReduce(sum) of k in one
+//            fused launch per device; without libnccl: peer copies of the slabs, k through the host
 //   phase 3  device d: TOM rows of its share (pair-balanced when packed, equal strips when dense) -> caller's buffer
 static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int64_t p, int spearman, int signed_,
                             int version, double beta, int precision, int packed, double* out) {
   const int nd_all = (int)g_ctx.size();
   PhaseBarrier bar(nd_all);
-  std::vector<double> k_host((size_t)p, 0.0);
+  const bool use_nccl = !g_comms.empty();
+  std::vector<double> k_host(use_nccl ? 0 : (size_t)p, 0.0);
   const int cor_prec = tom_cor_precision(precision, spearman, n);
   return for_each_device([&](Ctx* c, int d, int nd) -> int {
     int64_t c0, c1;
@@ -2072,6 +2174,7 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
       RC_TRY(c->vec.reserve(sizeof(double) * (size_t)p * 4));
       d_a = (double*)c->out2.ptr;
       d_k = (double*)c->vec.ptr + p;
+      if (use_nccl) CU_TRY(cudaMemsetAsync(d_k, 0, sizeof(double) * (size_t)p, c->compute));  // all-reduce(sum) of slab-wise k
       if (c1 > c0) {
         if (x) {
           RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
@@ -2081,14 +2184,30 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
           RC_TRY(h2d(c, d_a + c0 * p, a_pp + c0 * p, sizeof(double) * (size_t)(c1 - c0) * p, c->compute));
         }
         RC_TRY(dev_tom_connectivity(c, d_a, p, signed_, c0, c1, d_k));
-        RC_TRY(finish(c));
-        CU_TRY(cudaMemcpy(k_host.data() + c0, d_k + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost));
+        if (!use_nccl) {
+          RC_TRY(finish(c));
+          CU_TRY(cudaMemcpy(k_host.data() + c0, d_k + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost));
+        }
       }
-      return BIXCOR_OK;
+      return use_nccl ? BIXCOR_OK : finish(c);
     }();
-    rc = bar.arrive(rc);
+    rc = bar.arrive(rc);  // every device reaches the exchange or none does (a collective with a missing rank would hang)
     if (rc != BIXCOR_OK) return rc;
     rc = [&]() -> int {
+      if (use_nccl) {
+        // one fused NCCL launch per device: every slab is broadcast from its owner over NVLink / NVSwitch and the
+        // connectivity vector is all-reduced (sum of slab-wise contributions, zero elsewhere)
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int s_ = 0; s_ < nd; ++s_) {
+          int64_t s0, s1;
+          even_slab(p, nd, s_, &s0, &s1);
+          if (s1 > s0)
+            NCCL_TRY(g_nccl.Broadcast(d_a + s0 * p, d_a + s0 * p, (size_t)(s1 - s0) * p, ncclDouble, s_, g_comms[d], c->compute));
+        }
+        NCCL_TRY(g_nccl.AllReduce(d_k, d_k, (size_t)p, ncclDouble, ncclSum, g_comms[d], c->compute));
+        NCCL_TRY(g_nccl.GroupEnd());
+        return finish(c);
+      }
       for (int s_ = 0; s_ < nd; ++s_) {
         if (s_ == d) continue;
         int64_t s0, s1;
@@ -2462,46 +2581,43 @@ int bixcor_coremo_stability(const double* x, int64_t n, int64_t p, const int32_t
       return fail(BIXCOR_ERR_INVALID, "sample index %d out of range 1..%lld", indices_1based[k], (long long)n);
     if (!outs[k]) return fail(BIXCOR_ERR_INVALID, "null output vector %d", k);
   }
-  Ctx* c = g_ctx[0];
-  CU_TRY(cudaSetDevice(c->device));
-  call_begin(c);
   const int64_t len = p * (p - 1) / 2;
-  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
-  RC_TRY(c->x[1].reserve(sizeof(double) * (size_t)(n - 1) * p));
-  RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
-  RbfSpec rbf;
-  rbf.mode = rbf_type;
-  rbf.eps = epsilon;
-  rbf.complement = 1;  // 1 - phi(1 - |r|)
-  // two result buffers: the D2H of sample k overlaps the kernels of sample k + 1
-  Buffer* res[2] = {&c->out, &c->out2};
-  for (auto* b : res) RC_TRY(b->reserve(sizeof(double) * (size_t)std::max<int64_t>(1, len)));
-  D2HPipe pipe(c, n_idx ? outs[0] : nullptr);
-  cudaEvent_t reuse[2] = {nullptr, nullptr};
-  for (int k = 0; k < n_idx; ++k) {
-    const int b = k & 1;
-    if (reuse[b]) CU_TRY(cudaStreamWaitEvent(c->compute, reuse[b], 0));  // its previous D2H has drained
-    {
-      Timed tm(c, T_OTHER);
-      remove_row_kernel<<<(unsigned)p, 128, 0, c->compute>>>((const double*)c->x[0].ptr, n, indices_1based[k] - 1,
-                                                             (double*)c->x[1].ptr);
-      g_launches++;
-    }
-    RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[1].ptr, n - 1, p, spearman, 1, 1.0, precision, 0, p,
-                              (double*)res[b]->ptr, nullptr, nullptr, &rbf));
-    cudaEvent_t ev = ctx_event(c);
-    CU_TRY(cudaEventRecord(ev, c->compute));
-    RC_TRY(pipe.push(outs[k], res[b]->ptr, sizeof(double) * (size_t)len, ev));
-    if (!pipe.pinned_dst) {
-      RC_TRY(pipe.finish());  // pageable destinations go through the staging ring synchronously
-      reuse[b] = nullptr;
-    } else {
+  // the left-out samples are independent jobs: with several devices, device d takes samples d, d + nd, ...
+  // (the reference runs them on a rayon pool, r_coremo.rs:204-226)
+  return for_each_device([&](Ctx* c, int d, int nd) -> int {
+    if (d >= n_idx) return BIXCOR_OK;
+    RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
+    RC_TRY(c->x[1].reserve(sizeof(double) * (size_t)(n - 1) * p));
+    RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
+    RbfSpec rbf;
+    rbf.mode = rbf_type;
+    rbf.eps = epsilon;
+    rbf.complement = 1;  // 1 - phi(1 - |r|)
+    // two result buffers: the D2H of one sample overlaps the kernels of the next
+    Buffer* res[2] = {&c->out, &c->out2};
+    for (auto* b : res) RC_TRY(b->reserve(sizeof(double) * (size_t)std::max<int64_t>(1, len)));
+    D2HPipe pipe(c);
+    cudaEvent_t reuse[2] = {nullptr, nullptr};
+    int b = 0;
+    for (int k = d; k < n_idx; k += nd, b ^= 1) {
+      if (reuse[b]) CU_TRY(cudaStreamWaitEvent(c->compute, reuse[b], 0));  // its previous D2H has left the buffer
+      {
+        Timed tm(c, T_OTHER);
+        remove_row_kernel<<<(unsigned)p, 128, 0, c->compute>>>((const double*)c->x[0].ptr, n, indices_1based[k] - 1,
+                                                               (double*)c->x[1].ptr);
+        g_launches++;
+      }
+      RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[1].ptr, n - 1, p, spearman, 1, 1.0, precision, 0, p,
+                                (double*)res[b]->ptr, nullptr, nullptr, &rbf));
+      cudaEvent_t ev = ctx_event(c);
+      CU_TRY(cudaEventRecord(ev, c->compute));
+      RC_TRY(pipe.push(outs[k], res[b]->ptr, sizeof(double) * (size_t)len, ev));
       reuse[b] = ctx_event(c);
-      CU_TRY(cudaEventRecord(reuse[b], c->copy_out));
+      CU_TRY(cudaEventRecord(reuse[b], c->copy_out));  // pinned: the DMA itself; pageable: the DMAs into the staging ring
     }
-  }
-  RC_TRY(finish(c));
-  return pipe.finish();
+    RC_TRY(finish(c));
+    return pipe.finish();
+  });
   API_END
 }
 
@@ -2596,21 +2712,37 @@ static int sparse_pairwise_impl(const int64_t* indptr, const int32_t* indices, c
   if (sparse_ranks) {
     constexpr int kCap = 16384;
     constexpr int kSmem = kCap * 12;
-    RC_TRY(c->vec.reserve(256));
-    CU_TRY(cudaMemsetAsync(c->vec.ptr, 0, sizeof(int), c->compute));
+    RC_TRY(c->vec.reserve(sizeof(int) * (size_t)u + 256));
+    int* d_over = (int*)c->vec.ptr;  // one flag per densified gene: more than kCap non-zero cells
+    CU_TRY(cudaMemsetAsync(d_over, 0, sizeof(int) * (size_t)u, c->compute));
     CU_TRY(cudaFuncSetAttribute(rank_sparse_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     {
       Timed tm(c, T_COLS);
-      rank_sparse_columns_kernel<<<(unsigned)u, kSparseRankThreads, kSmem, c->compute>>>((double*)c->x[0].ptr, cells, cells, kCap,
-                                                                                        (int*)c->vec.ptr);
+      rank_sparse_columns_kernel<<<(unsigned)u, kSparseRankThreads, kSmem, c->compute>>>((double*)c->x[0].ptr, cells, cells, kCap, d_over);
       g_launches++;
     }
-    int overflow = 0;
-    CU_TRY(cudaMemcpyAsync(&overflow, c->vec.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    std::vector<int> over((size_t)u, 0);
+    CU_TRY(cudaMemcpyAsync(over.data(), d_over, sizeof(int) * (size_t)u, cudaMemcpyDeviceToHost, c->compute));
     CU_TRY(cudaStreamSynchronize(c->compute));
-    if (overflow)
-      return fail(BIXCOR_ERR_UNSUPPORTED, "Spearman pair correlations over %lld cells support <= %d non-zero cells per gene",
-                  (long long)cells, kCap);
+    // dense genes (more non-zero cells than one CTA sorts in shared memory): the chunked dense rank kernels rank the whole
+    // column in place - the zeros are one more tie run
+    for (int64_t g = 0; g < u;) {
+      if (!over[(size_t)g]) {
+        ++g;
+        continue;
+      }
+      int64_t g1 = g;
+      while (g1 < u && over[(size_t)g1]) ++g1;
+      ColumnOut co;
+      memset(&co, 0, sizeof co);
+      co.mode = COL_RANKS;
+      co.f64 = (double*)c->x[0].ptr + g * cells;
+      co.ld64 = cells;
+      co.kpad = (int)cells;
+      Timed tm(c, T_COLS);
+      RC_TRY(launch_rank_big(c, (const double*)c->x[0].ptr + g * cells, cells, (int)cells, g1 - g, co));
+      g = g1;
+    }
   }
   Operand op;
   RC_TRY(prepare_operand(c, (const double*)c->x[0].ptr, cells, u, sparse_ranks ? 0 : spearman, BIXCOR_PREC_F64, 0, &op));
@@ -2648,6 +2780,38 @@ int bixcor_sparse_pairwise_cor_cells(const int64_t* indptr, const int32_t* indic
   API_END
 }
 
+// One device's share of the sparse Gram: upload cells [cs0, cs1) of the CSR (row pointers rebased to the shard),
+// accumulate the partial X'X and the column sums into d_gram / d_colsum (zeroed here).
+static int sparse_shard_accumulate(Ctx* c, const int64_t* indptr, const int32_t* indices, const float* data, int64_t cs0,
+                                   int64_t cs1, int64_t genes, int precision, double** d_gram, double** d_colsum) {
+  const int64_t nc = cs1 - cs0, off = indptr[cs0], nnz = indptr[cs1] - off;
+  const size_t b_ptr = sizeof(int64_t) * (size_t)(nc + 1), b_idx = sizeof(int32_t) * (size_t)nnz, b_dat = sizeof(float) * (size_t)nnz;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + 256));
+  char* base = (char*)c->sparse_in.ptr;
+  int64_t* d_ptr = (int64_t*)base;
+  int32_t* d_idx = (int32_t*)(base + al(b_ptr));
+  float* d_dat = (float*)(base + al(b_ptr) + al(b_idx));
+  if (off == 0) {
+    RC_TRY(h2d(c, d_ptr, indptr + cs0, b_ptr, c->compute));
+  } else {
+    std::vector<int64_t> local((size_t)nc + 1);
+    for (int64_t i = 0; i <= nc; ++i) local[(size_t)i] = indptr[cs0 + i] - off;
+    RC_TRY(h2d(c, d_ptr, local.data(), b_ptr, c->compute));
+    CU_TRY(cudaStreamSynchronize(c->compute));  // `local` is a stack-owned staging vector
+  }
+  RC_TRY(h2d(c, d_idx, indices + off, b_idx, c->compute));
+  RC_TRY(h2d(c, d_dat, data + off, b_dat, c->compute));
+  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)genes * genes));
+  RC_TRY(c->vec.reserve(sizeof(double) * (size_t)genes * 4));
+  CU_TRY(cudaMemsetAsync(c->out2.ptr, 0, sizeof(double) * (size_t)genes * genes, c->compute));
+  CU_TRY(cudaMemsetAsync(c->vec.ptr, 0, sizeof(double) * (size_t)genes, c->compute));
+  *d_gram = (double*)c->out2.ptr;
+  *d_colsum = (double*)c->vec.ptr;
+  if (nc > 0) RC_TRY(dev_sparse_accumulate(c, d_ptr, d_idx, d_dat, nc, genes, precision, *d_gram, *d_colsum));
+  return BIXCOR_OK;
+}
+
 int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                            int64_t genes, int precision, double* out_packed) {
   API_BEGIN
@@ -2656,30 +2820,37 @@ int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const 
   if (cells < 2 || genes < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
   const int64_t nnz = indptr[cells];
   if (nnz < 0 || (nnz > 0 && (!indices || !data))) return fail(BIXCOR_ERR_INVALID, "bad CSR arrays");
+  const size_t out_bytes = sizeof(double) * (size_t)(genes * (genes - 1) / 2);
+  if (g_ctx.size() > 1 && !g_comms.empty() && cells >= 8192 * (int64_t)g_ctx.size()) {
+    // contiguous cell shards, one per device; the partial Gram matrices and column sums are summed with
+    // ncclAllReduce over NVLink; device 0 turns the total into Pearson correlations and returns the packed vector
+    PhaseBarrier bar((int)g_ctx.size());
+    return for_each_device([&](Ctx* c, int d, int nd) -> int {
+      double *d_gram = nullptr, *d_colsum = nullptr;
+      const int64_t cs0 = cells * d / nd, cs1 = cells * (d + 1) / nd;
+      int rc = sparse_shard_accumulate(c, indptr, indices, data, cs0, cs1, genes, precision, &d_gram, &d_colsum);
+      rc = bar.arrive(rc);  // all devices reach the collective or none does
+      if (rc != BIXCOR_OK) return rc;
+      NCCL_TRY(g_nccl.GroupStart());
+      NCCL_TRY(g_nccl.AllReduce(d_gram, d_gram, (size_t)genes * genes, ncclDouble, ncclSum, g_comms[d], c->compute));
+      NCCL_TRY(g_nccl.AllReduce(d_colsum, d_colsum, (size_t)genes, ncclDouble, ncclSum, g_comms[d], c->compute));
+      NCCL_TRY(g_nccl.GroupEnd());
+      if (d != 0) return finish(c);
+      RC_TRY(c->out.reserve(std::max<size_t>(out_bytes, 8)));
+      RC_TRY(dev_sparse_finalise(c, d_gram, d_colsum, cells, genes, (double*)c->out.ptr));
+      RC_TRY(finish(c));
+      D2HPipe pipe(c);
+      RC_TRY(pipe.push(out_packed, c->out.ptr, out_bytes, nullptr));
+      return pipe.finish();
+    });
+  }
   Ctx* c = g_ctx[0];
   CU_TRY(cudaSetDevice(c->device));
   call_begin(c);
-  const size_t b_ptr = sizeof(int64_t) * (size_t)(cells + 1), b_idx = sizeof(int32_t) * (size_t)nnz,
-               b_dat = sizeof(float) * (size_t)nnz;
-  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + 256));
-  char* base = (char*)c->sparse_in.ptr;
-  int64_t* d_ptr = (int64_t*)base;
-  int32_t* d_idx = (int32_t*)(base + al(b_ptr));
-  float* d_dat = (float*)(base + al(b_ptr) + al(b_idx));
-  RC_TRY(h2d(c, d_ptr, indptr, b_ptr, c->compute));
-  RC_TRY(h2d(c, d_idx, indices, b_idx, c->compute));
-  RC_TRY(h2d(c, d_dat, data, b_dat, c->compute));
-  RC_TRY(c->out2.reserve(sizeof(double) * (size_t)genes * genes));
-  RC_TRY(c->vec.reserve(sizeof(double) * (size_t)genes * 4));
-  CU_TRY(cudaMemsetAsync(c->out2.ptr, 0, sizeof(double) * (size_t)genes * genes, c->compute));
-  CU_TRY(cudaMemsetAsync(c->vec.ptr, 0, sizeof(double) * (size_t)genes, c->compute));
-  RC_TRY(dev_sparse_accumulate(c, d_ptr, d_idx, d_dat, cells, genes, precision, (double*)c->out2.ptr,
-                               (double*)c->vec.ptr));
-  const size_t out_bytes = sizeof(double) * (size_t)(genes * (genes - 1) / 2);
+  double *d_gram = nullptr, *d_colsum = nullptr;
+  RC_TRY(sparse_shard_accumulate(c, indptr, indices, data, 0, cells, genes, precision, &d_gram, &d_colsum));
   RC_TRY(c->out.reserve(std::max<size_t>(out_bytes, 8)));
-  RC_TRY(dev_sparse_finalise(c, (const double*)c->out2.ptr, (const double*)c->vec.ptr, cells, genes,
-                             (double*)c->out.ptr));
+  RC_TRY(dev_sparse_finalise(c, d_gram, d_colsum, cells, genes, (double*)c->out.ptr));
   RC_TRY(finish(c));
   D2HPipe pipe(c, out_packed);
   RC_TRY(pipe.push(out_packed, c->out.ptr, out_bytes, nullptr));

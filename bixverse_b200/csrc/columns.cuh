@@ -101,11 +101,79 @@ __device__ __forceinline__ void emit_tf32(const ColumnOut& out, int64_t j, int i
   out.f32[out.plane32 + j * out.ld32 + i] = lo;
 }
 
+// A column holding NaN: base-R cor() gives NA against everything.  One CTA writes the operand record of gene j.
+__device__ __forceinline__ void emit_nan_column_block(const ColumnOut& out, int64_t j, int n) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (out.mode == COL_RANKS) {
+    for (int i = tid; i < n; i += nt) out.f64[j * out.ld64 + i] = qnan;
+  } else if (out.mode == COL_Z64) {
+    for (int i = tid; i < out.kpad; i += nt) out.f64[j * out.ld64 + i] = (i < n) ? qnan : 0.0;
+  } else if (out.mode == COL_I8) {
+    for (int i = tid; i < out.kpad; i += nt) {
+      out.i8[j * out.ld8 + i] = 0;
+      out.i8[out.plane8 + j * out.ld8 + i] = 0;
+    }
+    if (tid == 0) out.inv_norm[j] = qnan;
+  } else {
+    for (int i = tid; i < out.kpad; i += nt) {
+      if (out.half_planes) {
+        emit_tf32(out, j, i, (i < n) ? qnan : 0.0);
+        continue;
+      }
+      float f = (i < n) ? __int_as_float(0x7fc00000) : 0.f;
+      out.f32[j * out.ld32 + i] = f;
+      out.f32[out.plane32 + j * out.ld32 + i] = 0.f;
+    }
+  }
+}
+
+// Operand record of gene j from rk2[i] = 2 * (average 1-based rank of sample i) (shared or global memory), one CTA.
+// The centred integer rank is d = 2*rank - (n+1); the rank mean is (n+1)/2 with or without ties.
+__device__ __forceinline__ void emit_ranked_column_block(const ColumnOut& out, int64_t j, int n, const uint32_t* rk2,
+                                                         long long* scr_ll) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (out.mode == COL_RANKS) {
+    for (int i = tid; i < n; i += nt) out.f64[j * out.ld64 + i] = 0.5 * (double)rk2[i];
+    return;
+  }
+  long long ss = 0;
+  for (int i = tid; i < n; i += nt) {
+    const long long d = (long long)rk2[i] - (long long)(n + 1);
+    ss += d * d;
+  }
+  ss = block_sum_ll(ss, scr_ll);
+  const double norm = sqrt((double)ss);
+  if (out.mode == COL_Z64) {
+    for (int i = tid; i < out.kpad; i += nt) {
+      double z = 0.0;
+      if (i < n) z = (double)((long long)rk2[i] - (long long)(n + 1)) / norm;
+      out.f64[j * out.ld64 + i] = z;
+    }
+  } else if (out.mode == COL_I8) {
+    for (int i = tid; i < out.kpad; i += nt) {
+      int d = (i < n) ? (int)rk2[i] - (n + 1) : 0;
+      const int l = ((d + 8) & 15) - 8;  // low digit in [-8, 7]
+      const int h = (d - l) >> 4;        // |h| <= 127 for n <= 2025
+      out.i8[j * out.ld8 + i] = (int8_t)h;
+      out.i8[out.plane8 + j * out.ld8 + i] = (int8_t)l;
+    }
+    if (tid == 0) out.inv_norm[j] = 1.0 / norm;
+  } else {
+    for (int i = tid; i < out.kpad; i += nt) {
+      double z = 0.0;
+      if (i < n) z = (double)((long long)rk2[i] - (long long)(n + 1)) / norm;
+      emit_tf32(out, j, i, z);
+    }
+  }
+}
+
 // Average-tie ranks of a mostly-zero column held dense (sparse single-cell genes, any number of cells): one CTA per
 // gene compacts the non-zero entries into shared memory (at most `cap`, a power of two; dynamic smem cap * 12
 // bytes), sorts them, and ranks the zeros analytically: with `neg` negative and `zc` zero entries the zeros share
 // rank neg + (zc + 1) / 2, the s-th smallest non-zero sits at full position s (negative) or s + zc (positive).
-// Ranks overwrite the column in place.  A column with more than `cap` non-zeros raises *overflow (nothing written).
+// Ranks overwrite the column in place.  A column with more than `cap` non-zeros sets overflow[gene] and is left
+// untouched: the host ranks those columns with the chunked dense kernels below (zeros tie like any other value).
 constexpr int kSparseRankThreads = 512;
 __global__ void __launch_bounds__(kSparseRankThreads)
 rank_sparse_columns_kernel(double* __restrict__ x, int64_t ldx, int64_t n, int cap, int* __restrict__ overflow) {
@@ -147,7 +215,7 @@ rank_sparse_columns_kernel(double* __restrict__ x, int64_t ldx, int64_t n, int c
     return;
   }
   if (cnt > cap) {
-    if (tid == 0) atomicExch(overflow, 1);
+    if (tid == 0) overflow[blockIdx.x] = 1;
     return;
   }
   int npow2 = 2;
@@ -235,28 +303,7 @@ rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2,
   __syncthreads();
 
   if (s_nan) {  // base-R cor(): a column holding NA correlates to NA with everything
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    if (out.mode == COL_RANKS) {
-      for (int i = tid; i < n; i += nt) out.f64[j * out.ld64 + i] = qnan;
-    } else if (out.mode == COL_Z64) {
-      for (int i = tid; i < out.kpad; i += nt) out.f64[j * out.ld64 + i] = (i < n) ? qnan : 0.0;
-    } else if (out.mode == COL_I8) {
-      for (int i = tid; i < out.kpad; i += nt) {
-        out.i8[j * out.ld8 + i] = 0;
-        out.i8[out.plane8 + j * out.ld8 + i] = 0;
-      }
-      if (tid == 0) out.inv_norm[j] = qnan;
-    } else {
-      for (int i = tid; i < out.kpad; i += nt) {
-        if (out.half_planes) {
-          emit_tf32(out, j, i, (i < n) ? qnan : 0.0);
-          continue;
-        }
-        float f = (i < n) ? __int_as_float(0x7fc00000) : 0.f;
-        out.f32[j * out.ld32 + i] = f;
-        out.f32[out.plane32 + j * out.ld32 + i] = 0.f;
-      }
-    }
+    emit_nan_column_block(out, j, n);
     return;
   }
 
@@ -316,41 +363,111 @@ rank_columns_kernel(const double* __restrict__ x, int64_t ldx, int n, int npow2,
   for (int s = tid; s < n; s += nt) rk2[idx[s] & 0x7fffffffu] = val[s];
   __syncthreads();
 
-  // ---- emit ----------------------------------------------------------------
-  if (out.mode == COL_RANKS) {
-    for (int i = tid; i < n; i += nt) out.f64[j * out.ld64 + i] = 0.5 * (double)rk2[i];
+  emit_ranked_column_block(out, j, n, rk2, scr_ll);
+}
+
+// ----------------------------------------------------------------------------
+// Spearman for n > 16384 samples (no upper limit in the reference: rank_matrix_col sorts any column).  A column no
+// longer fits one CTA's shared memory, so it is cut into chunks of kBigChunk samples:
+//   rank_big_sort_kernel   CTA (chunk, gene): bitonic sort of the chunk in shared memory -> sorted keys + sample indices
+//   rank_big_count_kernel  CTA (chunk, gene): every element counts, over ALL chunks of its gene, the keys below it (lo) and
+//                          the keys not above it (hi) by binary search: its tie run occupies sorted positions [lo, hi - 1],
+//                          so 2 * average rank = lo + hi + 1.  No merge passes; the sorted chunks of a gene (<= a few MB) stay in L2.
+//   rank_big_emit_kernel   CTA per gene: operand record from the 2 * rank values
+// ----------------------------------------------------------------------------
+constexpr int kBigChunk = 16384;
+constexpr int kBigThreads = 1024;
+
+__global__ void __launch_bounds__(kBigThreads)
+rank_big_sort_kernel(const double* __restrict__ x, int64_t ldx, int n, int nchunks, uint64_t* __restrict__ keys,
+                     uint32_t* __restrict__ idx_out, int* __restrict__ nan_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* idx = reinterpret_cast<uint32_t*>(key + kBigChunk);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int c = blockIdx.x;
+  const int64_t g = blockIdx.y;
+  const double* col = x + g * ldx;
+  const int base = c * kBigChunk;
+  bool has_nan = false;
+  for (int i = tid; i < kBigChunk; i += nt) {
+    uint64_t k = ~0ull;
+    if (base + i < n) {
+      const double v = col[base + i];
+      if (v != v) has_nan = true;
+      k = sortable_key(v);
+    }
+    key[i] = k;
+    idx[i] = (uint32_t)(base + i);
+  }
+  if (has_nan) nan_flag[g] = 1;
+  __syncthreads();
+  constexpr int half = kBigChunk >> 1;
+  for (int k = 2; k <= kBigChunk; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int t = tid; t < half; t += nt) {
+        const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+        const int l = i | jj;
+        const bool up = (i & k) == 0;
+        const uint64_t ki = key[i], kl = key[l];
+        if ((ki > kl) == up && ki != kl) {
+          key[i] = kl;
+          key[l] = ki;
+          const uint32_t ti = idx[i];
+          idx[i] = idx[l];
+          idx[l] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  uint64_t* ko = keys + ((size_t)g * nchunks + c) * kBigChunk;
+  uint32_t* io = idx_out + ((size_t)g * nchunks + c) * kBigChunk;
+  for (int i = tid; i < kBigChunk; i += nt) {
+    ko[i] = key[i];
+    io[i] = idx[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rank_big_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, int n, int nchunks,
+                      uint32_t* __restrict__ rk2) {
+  const int c = blockIdx.x;
+  const int64_t g = blockIdx.y;
+  const uint64_t* gk = keys + (size_t)g * nchunks * kBigChunk;
+  const int valid = min(kBigChunk, n - c * kBigChunk);
+  for (int s = threadIdx.x; s < valid; s += blockDim.x) {
+    const uint64_t k = gk[(size_t)c * kBigChunk + s];
+    uint32_t lo = 0, hi = 0;
+    for (int cc = 0; cc < nchunks; ++cc) {
+      const uint64_t* b = gk + (size_t)cc * kBigChunk;
+      const int v = min(kBigChunk, n - cc * kBigChunk);
+      int a0 = 0, a1 = v;  // first position with key >= k
+      while (a0 < a1) {
+        const int mid = (a0 + a1) >> 1;
+        if (__ldg(b + mid) < k) a0 = mid + 1; else a1 = mid;
+      }
+      lo += (uint32_t)a0;
+      a1 = v;  // first position with key > k (continue from the lower bound)
+      while (a0 < a1) {
+        const int mid = (a0 + a1) >> 1;
+        if (__ldg(b + mid) <= k) a0 = mid + 1; else a1 = mid;
+      }
+      hi += (uint32_t)a0;
+    }
+    rk2[(size_t)g * n + idx[((size_t)g * nchunks + c) * kBigChunk + s]] = lo + hi + 1u;  // lo + (hi - 1) + 2
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rank_big_emit_kernel(const uint32_t* __restrict__ rk2, const int* __restrict__ nan_flag, int n, ColumnOut out) {
+  __shared__ long long scr_ll[32];
+  const int64_t j = blockIdx.x;
+  if (nan_flag[j]) {
+    emit_nan_column_block(out, j, n);
     return;
   }
-  // centred integer rank d = 2*rank - (n+1); the rank mean is (n+1)/2 with or without ties
-  long long ss = 0;
-  for (int i = tid; i < n; i += nt) {
-    const long long d = (long long)rk2[i] - (long long)(n + 1);
-    ss += d * d;
-  }
-  ss = block_sum_ll(ss, scr_ll);
-  const double norm = sqrt((double)ss);
-  if (out.mode == COL_Z64) {
-    for (int i = tid; i < out.kpad; i += nt) {
-      double z = 0.0;
-      if (i < n) z = (double)((int)rk2[i] - (n + 1)) / norm;
-      out.f64[j * out.ld64 + i] = z;
-    }
-  } else if (out.mode == COL_I8) {
-    for (int i = tid; i < out.kpad; i += nt) {
-      int d = (i < n) ? (int)rk2[i] - (n + 1) : 0;
-      const int l = ((d + 8) & 15) - 8;  // low digit in [-8, 7]
-      const int h = (d - l) >> 4;        // |h| <= 127 for n <= 2025
-      out.i8[j * out.ld8 + i] = (int8_t)h;
-      out.i8[out.plane8 + j * out.ld8 + i] = (int8_t)l;
-    }
-    if (tid == 0) out.inv_norm[j] = 1.0 / norm;
-  } else {
-    for (int i = tid; i < out.kpad; i += nt) {
-      double z = 0.0;
-      if (i < n) z = (double)((int)rk2[i] - (n + 1)) / norm;
-      emit_tf32(out, j, i, z);
-    }
-  }
+  emit_ranked_column_block(out, j, n, rk2 + (size_t)j * n, scr_ll);
 }
 
 // ----------------------------------------------------------------------------

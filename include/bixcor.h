@@ -88,6 +88,13 @@ extern "C" {
  * (0, 1) by the compute entry points. */
 int bixcor_init(int n_gpus);
 int bixcor_init_devices(int first_device, int n_gpus);
+/* With n_gpus > 1 the library opens libnccl.so.2 at run time and creates one communicator per device
+ * (ncclCommInitAll): bixcor_cor_upper / bixcor_diffcor / bixcor_cor_dense / bixcor_coremo_stability shard their rows /
+ * slabs / samples over the devices; bixcor_tom* exchange affinity slabs by grouped ncclBroadcast and all-reduce the
+ * connectivity vector k; bixcor_sparse_gram_cor shards the cells and all-reduces the partial Gram + column sums.
+ * Returns NCCL's version code, or 0 when the collectives are not active (one device, BIXCOR_NCCL=0 or no libnccl:
+ * slabs then move by peer copies and k through the host). */
+int bixcor_nccl_version(void);
 void bixcor_shutdown(void);
 const char* bixcor_last_error(void);
 /* number of kernels launched by this library since init (bench `gpu_launches`) */
@@ -202,7 +209,7 @@ int bixcor_sparse_gram_cor(const int64_t* indptr, const int32_t* indices, const 
  * (or Spearman: average-tie ranks over ALL cells, zeros tie) correlation of the two genes of pair k over all
  * cells including the implicit zeros.  Only the genes named in the pair lists are densified on the device.
  * Spearman over more than 16384 cells ranks the non-zero entries of a gene only (the zeros' shared rank follows
- * analytically) and supports up to 16384 non-zero cells per gene. */
+ * analytically); genes with more than 16384 non-zero cells are ranked by the chunked dense rank kernels. */
 int bixcor_sparse_pairwise_cor(const int64_t* indptr, const int32_t* indices, const float* data, int64_t cells,
                                int64_t genes, int is_csr, const int32_t* gene_idx1, const int32_t* gene_idx2,
                                int64_t n_pairs, int spearman, double* out);

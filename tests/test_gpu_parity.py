@@ -670,13 +670,16 @@ def test_pairwise_spearman_many_cells(api, fmt):
     ok = ~np.isnan(ref)
     assert ok.sum() == len(g1) - (genes - 1) and np.isnan(got[~ok]).all()
     assert np.abs(got[ok] - ref[ok]).max() < 1e-10
-    # more than 16384 non-zero cells in one gene: reported, not silently wrong
-    dense[:20000, 2] = 1.5
+    # genes with more than 16384 non-zero cells (too many for one CTA's shared memory) take the chunked dense rank kernels
+    dense[:20000, 2] = 1.5                                        # one huge tie run
+    dense[:, 11] = np.round(rng.normal(0.0, 1.0, cells), 2)       # a fully dense gene with ties and negatives
     m2 = sp.csr_matrix(dense)
-    sl2 = {"data": m2.data, "indptr": m2.indptr, "indices": m2.indices, "nrow": cells, "ncol": genes, "format": "csr"}
-    with pytest.raises(api.BixcorError):
-        api.rs_pairwise_gene_cors_mc(sl2, g1, g2, True)
-    assert np.isfinite(api.rs_pairwise_gene_cors_mc(sl2, g1[:5], g2[:5], False)).all()  # Pearson has no such limit
+    ref2 = o.pairwise_gene_cors_spearman(m2.indptr.astype(np.int64), m2.indices.astype(np.int32), m2.data, cells, genes, g1, g2)
+    mm2 = m2.tocsc() if fmt == "csc" else m2
+    sl2 = {"data": mm2.data, "indptr": mm2.indptr, "indices": mm2.indices, "nrow": cells, "ncol": genes, "format": fmt}
+    got2 = api.rs_pairwise_gene_cors_mc(sl2, g1, g2, True)
+    ok2 = ~np.isnan(ref2)
+    assert np.isnan(got2[~ok2]).all() and np.abs(got2[ok2] - ref2[ok2]).max() < 1e-10
 
 
 # ----------------------------------------------------------------------------- FP64-class Gram on the int8 tensor cores (Ozaki slices)
@@ -862,3 +865,80 @@ def test_rs_tom_unsigned_uses_the_matrix_as_passed(api, version):
     wrapped = api.calculate_tom(a, False, version)
     assert _maxerr(wrapped, o.calculate_tom(a, False, version)) < TOL64
     assert np.abs(raw - wrapped)[off].max() > 1e-3  # the two semantics differ once an entry is negative
+
+
+# ----------------------------------------------------------------------------- Spearman beyond 16384 samples (round 2)
+@pytest.mark.parametrize("n,p", [(16385, 3), (40000, 5), (70001, 2)])
+def test_ranks_bit_exact_large_n(api, n, p):
+    """rank_matrix_col has no sample limit in the reference (r_singscore.rs:89-95 sorts any column); above one CTA's
+    shared memory the library sorts chunks and ranks by counting (columns.cuh: rank_big_*).  Bit-exact incl. ties."""
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(n, p))
+    x[:, 0] = np.round(x[:, 0], 1)                      # heavy ties
+    if p > 1:
+        x[: n // 2, 1] = 0.0                            # one tie run across several chunks
+        x[7, 1], x[8, 1] = -0.0, 0.0
+    if p > 2:
+        x[::3, 2] = np.inf
+        x[1::3, 2] = -np.inf
+    assert np.array_equal(api.rs_rank_matrix_col(x), o.rank_matrix_col(x))
+    xn = x.copy()
+    xn[n - 1, p - 1] = np.nan
+    got = api.rs_rank_matrix_col(xn)
+    assert np.isnan(got[:, p - 1]).all() and np.array_equal(got[:, : p - 1], o.rank_matrix_col(x)[:, : p - 1])
+
+
+@pytest.mark.parametrize("prec_name", ["auto", "tf32"])
+def test_spearman_correlation_large_n(api, prec_name):
+    from bixverse_b200 import _lib
+
+    rng = np.random.default_rng(77)
+    n, p = 20000, 140
+    f = rng.normal(size=(n, 3))
+    x = np.round(f @ rng.normal(size=(3, p)) + rng.normal(size=(n, p)), 1)
+    prec = {"auto": _lib.PREC_AUTO, "tf32": _lib.PREC_TF32X3}[prec_name]
+    got = api.rs_cor_upper_triangle(x, True, True, precision=prec)
+    ref = o.cor_upper_triangle(x, True, True)
+    assert _maxerr(got, ref) < (TOL64 if prec_name == "auto" else TOL32)
+
+
+# ----------------------------------------------------------------------------- in-process NCCL (round 2)
+@pytest.mark.parametrize("use_nccl", [True, False])
+def test_in_process_collectives(api, use_nccl, monkeypatch):
+    """bixcor_init(2): the library opens libnccl itself (ncclCommInitAll): TOM slabs by grouped ncclBroadcast + k by
+    ncclAllReduce, sparse Gram sharded by cells with ncclAllReduce of the partial Gram / column sums, dense correlation by
+    gene slabs, leave-one-out stability by samples, empty shards of a small module.  BIXCOR_NCCL=0: the peer-copy path."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk, synthetic_sparse_cells
+
+    lib = _lib.load()
+    x = synthetic_bulk(90, 900, seed=43)
+    cells, genes = 40000, 300
+    ip, ix, dd = synthetic_sparse_cells(cells, genes, 2029, density=0.05)
+    small = synthetic_bulk(40, 120, seed=4)
+    single = {"dense": api.rs_cor(x, True), "sparse": api.sparse_gene_cor_upper_triangle(ip, ix, dd, cells, genes),
+              "stab": api.rs_coremo_stability(x[:, :300], [1, 5, 9, 90], 2.0, "gaussian", True),
+              "small": api.rs_cor_upper_triangle(small, True, True), "small_tom": api.calculate_tom_from_exp(small, True, "v1", "pearson")}
+    monkeypatch.setenv("BIXCOR_NCCL", "1" if use_nccl else "0")
+    try:
+        api.init(2, 0)
+        assert (lib.bixcor_nccl_version() >= 20000) == use_nccl
+        for signed in (True, False):
+            ref = o.tom_from_exp(x, signed, "v2", True, 1.0)
+            packed = api.calculate_tom_from_exp(x, signed, "v2", "spearman", packed=True)
+            assert _maxerr(packed, o.dense_to_upper_triangle(ref, True)) < TOL64
+        assert _maxerr(api.rs_cor(x, True), single["dense"]) < 1e-14  # strips compute (i, j) and (j, i) separately: last-bit differences
+        got_sparse = api.sparse_gene_cor_upper_triangle(ip, ix, dd, cells, genes)
+        assert _maxerr(got_sparse, o.sparse_gram_cor(ip, ix, dd, cells, genes)) < 1e-9
+        assert _maxerr(got_sparse, single["sparse"]) < 1e-12  # (the sum order differs between one and two shards)
+        stab = api.rs_coremo_stability(x[:, :300], [1, 5, 9, 90], 2.0, "gaussian", True)
+        assert all(np.array_equal(a, b) for a, b in zip(stab, single["stab"]))
+        assert np.array_equal(api.rs_cor_upper_triangle(small, True, True), single["small"])  # p = 120: one device owns nothing
+        assert np.array_equal(api.calculate_tom_from_exp(small, True, "v1", "pearson"), single["small_tom"])
+    finally:
+        monkeypatch.delenv("BIXCOR_NCCL")
+        api.init(1, 0)
