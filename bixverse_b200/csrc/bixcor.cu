@@ -189,7 +189,8 @@ struct Ctx {
   Buffer flag;          // one int: device-side overflow / range flags read back by the host
   Buffer rank_scratch;  // sorted chunks / ranks of the n > 16384 Spearman path
   Buffer tile_sync;     // two words: arrival / bail-out counters of the long-K producer barrier (gram_umma.cuh)
-  HostStager* stager = nullptr;
+  HostStager* stager = nullptr;     // device -> pageable host (results)
+  HostStager* stager_in = nullptr;  // pageable host -> device (inputs): its own small ring, so uploads never queue behind result slots
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
   // timing
   std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> timed;
@@ -958,20 +959,23 @@ struct HostStager {
 
 static int g_copy_threads = 0;  // env BIXCOR_COPY_THREADS; 0 = from the host's core count
 
-static int stager_get(Ctx* c, HostStager** out) {
-  if (c->stager) {
-    *out = c->stager;
+static void stager_free(HostStager* st);
+
+static int stager_get(Ctx* c, HostStager** out, bool inbound = false) {
+  HostStager*& slot_ref = inbound ? c->stager_in : c->stager;
+  if (slot_ref) {
+    *out = slot_ref;
     return BIXCOR_OK;
   }
   HostStager* st = new HostStager();
   st->device = c->device;
+  if (inbound) st->kSlots = std::min(st->kSlots, 6);
   for (int si = 0; si < st->kSlots; ++si) {
     auto& sl = st->slots[si];
     if (cudaMallocHost(&sl.ptr, st->kSlotBytes) != cudaSuccess ||
         cudaEventCreateWithFlags(&sl.dma_done, cudaEventDisableTiming | (g_stage_spin ? 0 : cudaEventBlockingSync)) != cudaSuccess) {
       cudaGetLastError();
-      c->stager = st;  // partially built: released below
-      stager_destroy(c);
+      stager_free(st);
       return fail(BIXCOR_ERR_OOM, "cannot allocate the pinned staging ring (%d x %zu MB)", g_stage_slots, g_stage_slot_bytes >> 20);
     }
   }
@@ -980,7 +984,8 @@ static int stager_get(Ctx* c, HostStager** out) {
   int nd = std::max<int>(1, (int)g_ctx.size());
   if (const char* lw = getenv("LOCAL_WORLD_SIZE")) nd = std::max(nd, atoi(lw));  // one process per GPU (torchrun): share the cores
   int nthr = g_copy_threads > 0 ? g_copy_threads : (int)std::max(2u, std::min(14u, (hw > 2 ? hw - 2 : 1u) / (unsigned)nd));
-  c->stager = st;
+  if (inbound) nthr = std::max(2, std::min(4, nthr / 3));  // inputs are a tenth of the traffic
+  slot_ref = st;
   try {
     for (int t = 0; t < nthr; ++t) st->workers.emplace_back([st] {
       try {
@@ -993,7 +998,8 @@ static int stager_get(Ctx* c, HostStager** out) {
     });
   } catch (...) {
     if (st->workers.empty()) {
-      stager_destroy(c);
+      stager_free(st);
+      slot_ref = nullptr;
       throw;
     }
   }
@@ -1002,7 +1008,12 @@ static int stager_get(Ctx* c, HostStager** out) {
 }
 
 static void stager_destroy(Ctx* c) {
-  HostStager* st = c->stager;
+  stager_free(c->stager);
+  stager_free(c->stager_in);
+  c->stager = c->stager_in = nullptr;
+}
+
+static void stager_free(HostStager* st) {
   if (!st) return;
   {
     std::lock_guard<std::mutex> lk(st->m);
@@ -1016,7 +1027,6 @@ static void stager_destroy(Ctx* c) {
     if (sl.ptr) cudaFreeHost(sl.ptr);
   }
   delete st;
-  c->stager = nullptr;
 }
 
 // Host -> device.  Pinned sources are DMA'd directly; pageable ones go through the pinned ring: the pool copies
@@ -1028,7 +1038,7 @@ static int h2d(Ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_
     return BIXCOR_OK;
   }
   HostStager* st;
-  RC_TRY(stager_get(c, &st));
+  RC_TRY(stager_get(c, &st, true));
   int prev = -1;
   size_t prev_off = 0, prev_len = 0;
   auto issue = [&](int sidx, size_t off, size_t len) -> int {  // host copies of the slot are done: put it on the wire
@@ -1156,6 +1166,119 @@ static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, i
   Operand op;
   RC_TRY(prepare_operand(c, d_x, n, p, spearman, precision, 0, &op));
   return dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, d_out, pipe, h_out, rbf);
+}
+
+static int finish(Ctx* c);
+
+// Host -> host packed correlation of rows [row_begin,row_end) with both PCIe directions busy at once.  The packed
+// result (8 bytes per pair) is ten times the input, so the device-to-host stream is the floor of the call; it should
+// start at once and never wait.  Tile (i, j), i <= j, only needs the genes of block rows i and j, so the bands of the
+// triangle are processed BOTTOM-UP: the last band needs the last genes only - their columns are uploaded, ranked /
+// standardised and multiplied first, and its packed range is already on its way back while the earlier gene slabs are
+// still being uploaded (host-to-device on its own stream and DMA engine).  Per band: upload the band's gene columns
+// (8 MB), column kernel for those genes, Gram of the band, device-to-host of its packed range.
+static int host_cor_upper_pipelined(Ctx* c, const double* h_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                                    int precision, int64_t row_begin, int64_t row_end, double* h_out, const RbfSpec* rbf) {
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (row_begin == row_end) return BIXCOR_OK;
+  precision = resolve_precision(precision, spearman, n);
+  RC_TRY(check_precision(precision, spearman, n));
+  const int64_t o_base = packed_row_offset(row_begin, p, shift), o_end = packed_row_offset(row_end, p, shift);
+  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o_end - o_base)));
+  double* d_x = (double*)c->x[0].ptr;
+  double* d_out = (double*)c->out.ptr;
+  D2HPipe pipe(c);
+  if (!exchangeable(precision)) {  // Ozaki: the digit slicing runs over the whole operand, no per-slab form
+    RC_TRY(h2d(c, d_x, h_x, sizeof(double) * (size_t)n * p, c->compute));
+    RC_TRY(dev_cor_upper_rows(c, d_x, n, p, spearman, shift, beta, precision, row_begin, row_end, d_out, &pipe, h_out, rbf));
+    RC_TRY(finish(c));
+    return pipe.finish();
+  }
+  RC_TRY(c->op[0].reserve((size_t)operand_row_bytes(n, precision) * p));
+  RC_TRY(c->aux[0].reserve(sizeof(double) * p));
+  Operand op;
+  bind_operand(&op, n, p, precision, c->op[0].ptr, (const double*)c->aux[0].ptr);
+  EpiParams e = make_epi(p);
+  e.out = d_out;
+  e.out_base = o_base;
+  e.shift = shift;
+  set_beta(e, beta, 0);
+  if (rbf && rbf->mode) {
+    e.rbf_mode = rbf->mode;
+    e.rbf_eps = rbf->eps;
+    e.rbf_from_cor = rbf->from_cor;
+    e.rbf_complement = rbf->complement;
+  }
+  TileList* tl;
+  RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(precision, EPI_PACKED), &tl, swap_tiles(precision, e)));
+  const int ngroups = (int)tl->group_tile.size() - 1;
+  const bool pinned_src = is_pinned(h_x);
+  // Band g misses the genes [lo(g), hi(g)): its own block rows; the bottom band also brings everything to its right.
+  auto lo = [&](int g) { return tl->group_row[g]; };
+  auto hi = [&](int g) { return g == ngroups - 1 ? p : tl->group_row[g + 1]; };
+  std::vector<cudaEvent_t> up((size_t)ngroups);
+  for (auto& ev : up) ev = ctx_event(c);
+  auto upload = [&](int g) -> int {  // enqueue the upload of band g's genes and record up[g] behind it
+    const size_t off = (size_t)lo(g) * n, bytes = sizeof(double) * (size_t)(hi(g) - lo(g)) * n;
+    if (pinned_src) CU_TRY(cudaMemcpyAsync(d_x + off, h_x + off, bytes, cudaMemcpyHostToDevice, c->copy_in));
+    else RC_TRY(h2d(c, d_x + off, h_x + off, bytes, c->copy_in));  // staged through the inbound pinned ring (blocks this thread)
+    CU_TRY(cudaEventRecord(up[(size_t)g], c->copy_in));
+    return BIXCOR_OK;
+  };
+  // Pinned source: the uploads are asynchronous DMAs, all of them are queued here and now.  Pageable source: staging
+  // needs a host thread for the whole upload, so a helper thread runs it bottom-up while this thread launches the bands
+  // and feeds the device-to-host stream; `enqueued` is the lowest band whose event has been recorded.
+  std::mutex um;
+  std::condition_variable ucv;
+  int enqueued = ngroups, up_rc = BIXCOR_OK;
+  ThreadGroup uploader;
+  if (pinned_src) {
+    for (int g = ngroups - 1; g >= 0; --g) RC_TRY(upload(g));
+    enqueued = 0;
+  } else {
+    uploader.run([&] {
+      int rc = BIXCOR_OK;
+      try {
+        if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(BIXCOR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+        for (int g = ngroups - 1; g >= 0 && rc == BIXCOR_OK; --g) {
+          rc = upload(g);
+          std::lock_guard<std::mutex> lk(um);
+          if (rc == BIXCOR_OK) enqueued = g;
+          else up_rc = rc;
+          ucv.notify_all();
+        }
+      } catch (...) {
+        rc = api_exception("upload thread");
+      }
+      std::lock_guard<std::mutex> lk(um);
+      if (rc != BIXCOR_OK) up_rc = rc;
+      ucv.notify_all();
+    });
+  }
+  int loop_rc = BIXCOR_OK;
+  for (int g = ngroups - 1; g >= 0 && loop_rc == BIXCOR_OK; --g) {
+    loop_rc = [&]() -> int {
+      {
+        std::unique_lock<std::mutex> lk(um);
+        ucv.wait(lk, [&] { return enqueued <= g || up_rc != BIXCOR_OK; });
+        if (up_rc != BIXCOR_OK) return up_rc;
+      }
+      CU_TRY(cudaStreamWaitEvent(c->compute, up[(size_t)g], 0));
+      RC_TRY(build_operand(c, d_x, n, p, spearman, precision, lo(g), hi(g), c->op[0].ptr, (double*)c->aux[0].ptr));
+      const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
+      RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e, nullptr, tl->group_row[g], tl->group_row[g + 1]));
+      cudaEvent_t ev = ctx_event(c);
+      CU_TRY(cudaEventRecord(ev, c->compute));
+      const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - o_base;
+      const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - o_base;
+      return pipe.push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev);
+    }();
+  }
+  uploader.join();  // (also on the error path: the thread references this frame)
+  if (loop_rc != BIXCOR_OK) return loop_rc;
+  RC_TRY(finish(c));
+  return pipe.finish();
 }
 
 static int check_rbf(int rbf_type, double epsilon) {
@@ -2032,17 +2155,9 @@ int bixcor_cor_upper_rows(const double* x, int64_t n, int64_t p, int spearman, i
       if (d == nd - 1) r1 = row_end;
       if (r0 > r1) r0 = r1;
     }
-    const size_t in_bytes = sizeof(double) * (size_t)n * p;
     const int64_t base = packed_row_offset(row_begin, p, shift);
-    const int64_t o0 = packed_row_offset(r0, p, shift), o1 = packed_row_offset(r1, p, shift);
-    RC_TRY(c->x[0].reserve(in_bytes));
-    RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o1 - o0)));
-    RC_TRY(h2d(c, c->x[0].ptr, x, in_bytes, c->compute));
-    D2HPipe pipe(c, out_slice);
-    RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[0].ptr, n, p, spearman, shift, beta, precision, r0, r1,
-                              (double*)c->out.ptr, &pipe, out_slice + (o0 - base)));
-    RC_TRY(finish(c));
-    return pipe.finish();
+    const int64_t o0 = packed_row_offset(r0, p, shift);
+    return host_cor_upper_pipelined(c, x, n, p, spearman, shift, beta, precision, r0, r1, out_slice + (o0 - base), nullptr);
   });
   API_END
 }
@@ -2552,19 +2667,11 @@ int bixcor_cor_upper_rbf(const double* x, int64_t n, int64_t p, int spearman, in
   CU_TRY(cudaSetDevice(c->device));
   call_begin(c);
   shift = shift ? 1 : 0;
-  const int64_t len = shift ? p * (p - 1) / 2 : p * (p + 1) / 2;
-  RC_TRY(c->x[0].reserve(sizeof(double) * (size_t)n * p));
-  RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, len)));
-  RC_TRY(h2d(c, c->x[0].ptr, x, sizeof(double) * (size_t)n * p, c->compute));
   RbfSpec rbf;
   rbf.mode = rbf_type;
   rbf.eps = epsilon;
   rbf.complement = complement ? 1 : 0;
-  D2HPipe pipe(c, out_packed);
-  RC_TRY(dev_cor_upper_rows(c, (const double*)c->x[0].ptr, n, p, spearman, shift, 1.0, precision, 0, p,
-                            (double*)c->out.ptr, &pipe, out_packed, &rbf));
-  RC_TRY(finish(c));
-  return pipe.finish();
+  return host_cor_upper_pipelined(c, x, n, p, spearman, shift, 1.0, precision, 0, p, out_packed, &rbf);
   API_END
 }
 
