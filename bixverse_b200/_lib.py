@@ -72,6 +72,9 @@ SIGNATURES = {
     "bixcor_dev_affinity_cols": (i32, [ptr, i64, i64, i32, i32, f64, i32, i64, i64, ptr]),
     "bixcor_dev_tom_connectivity": (i32, [ptr, i64, i32, i64, i64, ptr]),
     "bixcor_dev_tom_rows": (i32, [ptr, ptr, i64, i32, i32, i32, i32, i64, i64, ptr]),
+    "bixcor_dev_tom_plane_row_bytes": (i64, [i64, i32]),
+    "bixcor_dev_tom_split_planes": (i32, [ptr, i64, i32, i64, i64, ptr]),
+    "bixcor_dev_tom_rows_planes": (i32, [ptr, ptr, i64, i32, i32, i32, i32, i64, i64, ptr]),
     "bixcor_dev_sparse_gram_accumulate": (i32, [ptr, ptr, ptr, i64, i64, i32, ptr, ptr]),
     "bixcor_dev_sparse_gram_finalise": (i32, [ptr, ptr, i64, i64, ptr]),
     "bixcor_dev_set_stream": (i32, [ptr, i32]),

@@ -27,6 +27,20 @@ tom_connectivity_kernel(const double* __restrict__ a, int64_t p, int64_t col0, i
   if (threadIdx.x == 0) kvec[i] = s;
 }
 
+// diagonal of A from its hi / lo operand planes (records [K hi][K lo] per gene)
+__global__ void extract_diag_planes_kernel(const void* __restrict__ planes, int64_t ld, int K, int half, int64_t p,
+                                           double* __restrict__ d) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  if (half) {
+    const __half* r = reinterpret_cast<const __half*>(planes) + i * ld;
+    d[i] = ((double)__half2float(r[i]) + (double)__half2float(r[K + i])) * (1.0 / kF16Scale);
+  } else {
+    const float* r = reinterpret_cast<const float*>(planes) + i * ld;
+    d[i] = (double)r[i] + (double)r[K + i];
+  }
+}
+
 __global__ void extract_diag_kernel(const double* __restrict__ a, int64_t p, double* __restrict__ d) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < p) d[i] = a[i * p + i];

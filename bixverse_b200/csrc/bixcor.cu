@@ -1371,72 +1371,101 @@ static int dev_tom_connectivity(Ctx* c, const double* d_a, int64_t p, int signed
   return BIXCOR_OK;
 }
 
+// Split rows [row_begin,row_end) of the dense affinity matrix (column i == row i) into the hi / lo operand planes of a
+// split-float kind: records [K hi][K lo] per gene in `d_planes` (base pointer of the full p-gene buffer).
+static int dev_split_planes(Ctx* c, const double* d_a, int64_t p, int precision, int64_t row_begin, int64_t row_end,
+                            void* d_planes) {
+  if (!is_split_float(precision)) return fail(BIXCOR_ERR_INVALID, "operand planes exist for BIXCOR_PREC_TF32X3 / BIXCOR_PREC_F16X3");
+  if (row_begin < 0 || row_end > p || row_begin > row_end) return fail(BIXCOR_ERR_INVALID, "bad row range");
+  if (row_begin == row_end) return BIXCOR_OK;
+  const int K = round_up((int)p, k_padding(precision));
+  const bool half = precision == BIXCOR_PREC_F16X3;
+  ColumnOut co;
+  memset(&co, 0, sizeof co);
+  co.mode = COL_TF32;
+  co.half_planes = half;
+  co.kpad = K;
+  co.f32 = half ? (float*)((__half*)d_planes + row_begin * 2 * K) : (float*)d_planes + row_begin * 2 * K;
+  co.ld32 = 2 * K;
+  co.plane32 = K;
+  RC_TRY(c->flag.reserve(256));
+  int* d_flag = (int*)c->flag.ptr;
+  CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), c->compute));
+  {
+    Timed tm(c, T_COLS);
+    split_tf32_kernel<<<(unsigned)(row_end - row_begin), 256, 0, c->compute>>>(d_a + row_begin * p, p, (int)p, co, d_flag);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  if (half) {
+    int overflow = 0;
+    CU_TRY(cudaMemcpyAsync(&overflow, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    CU_TRY(cudaStreamSynchronize(c->compute));
+    if (overflow)
+      return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_F16X3 needs affinities below 63 in magnitude; use BIXCOR_PREC_TF32X3");
+  }
+  return BIXCOR_OK;
+}
+
 // The TOM GEMM operand is the affinity matrix itself (A symmetric: column i == row i).
+// d_planes != nullptr (split-float kinds): the hi / lo planes of ALL genes are given (built per slab by their owners and
+// exchanged); d_a may then be nullptr - the epilogue rebuilds a_ij and the diagonal from the planes.
 static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p, int signed_, int version,
-                        int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out) {
+                        int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out,
+                        const void* d_planes = nullptr) {
   RC_TRY(validate_rows(p, row_begin, row_end));
   if (version != BIXCOR_TOM_V1 && version != BIXCOR_TOM_V2)
     return fail(BIXCOR_ERR_INVALID, "Invalid TOM version type: %d", version);
   if (row_begin == row_end) return BIXCOR_OK;
   precision = resolve_precision_float(precision);
+  if (d_planes && !is_split_float(precision)) return fail(BIXCOR_ERR_INVALID, "operand planes exist for the split-float kinds only");
+  if (!d_a && !d_planes) return fail(BIXCOR_ERR_INVALID, "null pointer");
   RC_TRY(c->vec.reserve(sizeof(double) * (size_t)p * 4));
   double* d_diag = (double*)c->vec.ptr;  // first p entries: diagonal
-  {
-    Timed tm(c, T_OTHER);
-    extract_diag_kernel<<<(unsigned)((p + 255) / 256), 256, 0, c->compute>>>(d_a, p, d_diag);
-    g_launches++;
-  }
   Operand op;
   op.precision = precision;
   op.p = p;
-  if (precision == BIXCOR_PREC_F64) {
-    if (p % dmma::BK != 0) {
-      // pad K: copy A into a K-padded operand buffer
-      const int K = round_up((int)p, dmma::BK);
-      RC_TRY(c->op[1].reserve(sizeof(double) * (size_t)K * p));
-      CU_TRY(cudaMemsetAsync(c->op[1].ptr, 0, sizeof(double) * (size_t)K * p, c->compute));
-      CU_TRY(cudaMemcpy2DAsync(c->op[1].ptr, sizeof(double) * K, d_a, sizeof(double) * p, sizeof(double) * p, p,
-                               cudaMemcpyDeviceToDevice, c->compute));
-      op.K = K;
-      op.z64 = (const double*)c->op[1].ptr;
-    } else {
-      op.K = (int)p;
-      op.z64 = d_a;
-    }
-  } else if (is_split_float(precision)) {
+  if (d_planes) {
     const int K = round_up((int)p, k_padding(precision));
-    RC_TRY(c->op[1].reserve(sizeof(float) * 2 * (size_t)K * p));
-    ColumnOut co;
-    memset(&co, 0, sizeof co);
-    co.mode = COL_TF32;
-    co.half_planes = precision == BIXCOR_PREC_F16X3;
-    co.kpad = K;
-    co.f32 = (float*)c->op[1].ptr;
-    co.ld32 = 2 * K;
-    co.plane32 = K;
-    RC_TRY(c->flag.reserve(256));
-    int* d_flag = (int*)c->flag.ptr;
-    CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), c->compute));
+    op.K = K;
+    op.f32 = (const float*)d_planes;
+    Timed tm(c, T_OTHER);
+    extract_diag_planes_kernel<<<(unsigned)((p + 255) / 256), 256, 0, c->compute>>>(d_planes, 2 * (int64_t)K, K, precision == BIXCOR_PREC_F16X3, p,
+                                                                                   d_diag);
+    g_launches++;
+  } else {
     {
-      Timed tm(c, T_COLS);
-      split_tf32_kernel<<<(unsigned)p, 256, 0, c->compute>>>(d_a, p, (int)p, co, d_flag);
+      Timed tm(c, T_OTHER);
+      extract_diag_kernel<<<(unsigned)((p + 255) / 256), 256, 0, c->compute>>>(d_a, p, d_diag);
       g_launches++;
     }
-    if (co.half_planes) {
-      int overflow = 0;
-      CU_TRY(cudaMemcpyAsync(&overflow, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
-      CU_TRY(cudaStreamSynchronize(c->compute));
-      if (overflow)
-        return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_F16X3 needs affinities below 63 in magnitude; use BIXCOR_PREC_TF32X3");
+    if (precision == BIXCOR_PREC_F64) {
+      if (p % dmma::BK != 0) {
+        // pad K: copy A into a K-padded operand buffer
+        const int K = round_up((int)p, dmma::BK);
+        RC_TRY(c->op[1].reserve(sizeof(double) * (size_t)K * p));
+        CU_TRY(cudaMemsetAsync(c->op[1].ptr, 0, sizeof(double) * (size_t)K * p, c->compute));
+        CU_TRY(cudaMemcpy2DAsync(c->op[1].ptr, sizeof(double) * K, d_a, sizeof(double) * p, sizeof(double) * p, p,
+                                 cudaMemcpyDeviceToDevice, c->compute));
+        op.K = K;
+        op.z64 = (const double*)c->op[1].ptr;
+      } else {
+        op.K = (int)p;
+        op.z64 = d_a;
+      }
+    } else if (is_split_float(precision)) {
+      const int K = round_up((int)p, k_padding(precision));
+      RC_TRY(c->op[1].reserve(sizeof(float) * 2 * (size_t)K * p));
+      RC_TRY(dev_split_planes(c, d_a, p, precision, 0, p, c->op[1].ptr));
+      op.K = K;
+      op.f32 = (const float*)c->op[1].ptr;
+    } else if (is_ozaki(precision)) {
+      op.K = (int)p;
+      op.z64 = d_a;
+      RC_TRY(ozaki_slice(c, d_a, p, p, p, 1, &op));  // rows of A are its columns (symmetric): digit planes of every gene
+    } else {
+      return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3, BIXCOR_PREC_F16X3 and BIXCOR_PREC_OZAKI");
     }
-    op.K = K;
-    op.f32 = co.f32;
-  } else if (is_ozaki(precision)) {
-    op.K = (int)p;
-    op.z64 = d_a;
-    RC_TRY(ozaki_slice(c, d_a, p, p, p, 1, &op));  // rows of A are its columns (symmetric): digit planes of every gene
-  } else {
-    return fail(BIXCOR_ERR_INVALID, "TOM supports BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3, BIXCOR_PREC_F16X3 and BIXCOR_PREC_OZAKI");
   }
   const bool full = (row_begin == 0 && row_end == p);
   const int upper = (packed || full) ? 1 : 0;
@@ -1449,6 +1478,12 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   e.out_base = packed ? packed_row_offset(row_begin, p, 1) : 0;
   e.mirror = (!packed && full) ? 1 : 0;
   e.A = d_a;
+  if (!d_a) {
+    e.A_planes = d_planes;
+    e.planes_K = op.K;
+    e.planes_ld = 2 * (int64_t)op.K;
+    e.planes_half = precision == BIXCOR_PREC_F16X3;
+  }
   e.kvec = d_k;
   e.dvec = d_diag;
   e.tom_v2 = (version == BIXCOR_TOM_V2);
@@ -2085,6 +2120,31 @@ int bixcor_dev_tom_rows(const double* d_a_pp, const double* d_k, int64_t p, int 
   API_BEGIN
   DEV_PROLOGUE();
   RC_TRY(dev_tom_rows(c, d_a_pp, d_k, p, signed_, version, precision, packed, row_begin, row_end, d_out));
+  return finish_dev(c);
+  API_END
+}
+
+int64_t bixcor_dev_tom_plane_row_bytes(int64_t p, int precision) {
+  if (p < 1 || !is_split_float(precision)) return -1;
+  return (int64_t)round_up((int)p, k_padding(precision)) * (precision == BIXCOR_PREC_F16X3 ? 4 : 8);
+}
+
+int bixcor_dev_tom_split_planes(const double* d_a_pp, int64_t p, int precision, int64_t row_begin, int64_t row_end,
+                                void* d_planes) {
+  API_BEGIN
+  DEV_PROLOGUE();
+  if (!d_a_pp || !d_planes) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  RC_TRY(dev_split_planes(c, d_a_pp, p, precision, row_begin, row_end, d_planes));
+  return finish_dev(c);
+  API_END
+}
+
+int bixcor_dev_tom_rows_planes(const void* d_planes, const double* d_k, int64_t p, int signed_, int version, int precision,
+                               int packed, int64_t row_begin, int64_t row_end, double* d_out) {
+  API_BEGIN
+  DEV_PROLOGUE();
+  if (!d_planes || !d_k || !d_out) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  RC_TRY(dev_tom_rows(c, nullptr, d_k, p, signed_, version, precision, packed, row_begin, row_end, d_out, d_planes));
   return finish_dev(c);
   API_END
 }

@@ -36,7 +36,11 @@ struct EpiParams {
   double* z;
   double* pv;
   double inv_se;
-  const double* A;     // TOM: dense p x p affinity (symmetric), ld = p
+  const double* A;     // TOM: dense p x p affinity (symmetric), ld = p; nullptr: a_ij is rebuilt from the hi / lo operand planes
+  const void* A_planes;  // TOM without the f64 matrix: gene-major records [K hi][K lo] (float, or __half scaled by 2^10)
+  int64_t planes_ld;     // elements per record (2 K)
+  int planes_K;          // padded K of a plane
+  int planes_half;       // binary16 planes
   const double* kvec;  // TOM: connectivity
   const double* dvec;  // TOM: diagonal of A
   int tom_v2;
@@ -160,7 +164,16 @@ __device__ __forceinline__ double epi_store(const EpiParams& E, const EpiRow& R,
     }
     return v;
   } else {  // EPI_TOM
-    const double a = E.A[(int64_t)i * E.p + j];
+    double a;
+    if (E.A) {
+      a = E.A[(int64_t)i * E.p + j];
+    } else if (E.planes_half) {  // hi + lo carries 22 significant bits: inside the 1e-5 class this path serves
+      const __half* r = reinterpret_cast<const __half*>(E.A_planes) + (int64_t)i * E.planes_ld;
+      a = ((double)__half2float(r[j]) + (double)__half2float(r[E.planes_K + j])) * (1.0 / kF16Scale);
+    } else {
+      const float* r = reinterpret_cast<const float*>(E.A_planes) + (int64_t)i * E.planes_ld;
+      a = (double)r[j] + (double)r[E.planes_K + j];
+    }
     const double absa = E.tom_signed ? fabs(a) : a;
     const double shared = v - a * (R.d_i + E.dvec[j]);
     const double mk = fmin(R.k_i, E.kvec[j]);

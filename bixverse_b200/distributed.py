@@ -126,6 +126,22 @@ class DeviceBackend:
         self._sync_in()
         check(self.lib.bixcor_dev_tom_connectivity(a_full.data_ptr(), p, int(signed), c0, c1, k.data_ptr()))
 
+    def tom_plane_row_bytes(self, p, precision):
+        return int(self.lib.bixcor_dev_tom_plane_row_bytes(p, precision))
+
+    def tom_split_planes(self, a_full, p, precision, c0, c1, planes):
+        """hi / lo operand planes of the affinity rows [c0,c1) into the full plane buffer (split-float kinds)."""
+        self._sync_in()
+        check(self.lib.bixcor_dev_tom_split_planes(a_full.data_ptr(), p, precision, c0, c1, planes.data_ptr()))
+
+    def tom_rows_planes(self, planes, k, p, signed, version, precision, r0, r1):
+        ln = packed_offset(r1, p, 1) - packed_offset(r0, p, 1)
+        out = self.empty(max(ln, 1))[:ln]
+        self._sync_in()
+        check(self.lib.bixcor_dev_tom_rows_planes(planes.data_ptr(), k.data_ptr(), p, int(signed), version, precision, 1,
+                                                  r0, r1, out.data_ptr()))
+        return out
+
     def tom_rows(self, a_full, k, p, signed, version, precision, r0, r1):
         ln = packed_offset(r1, p, 1) - packed_offset(r0, p, 1)
         out = self.empty(max(ln, 1))[:ln]
@@ -230,27 +246,39 @@ def sharded_tom_from_exp(backend, x, n, p, spearman, signed, version, beta=1.0, 
     """calculate_tom_from_exp, packed (shift = 1) output slice of this rank.
 
     phase 1  affinity columns of this rank's gene slab (full-width strip)
-    phase 2  connectivity of the slab (and |A| in place when unsigned)
-    exchange slabs -> full A on every rank; all-reduce(sum) of k
+    phase 2  connectivity of the slab
+    exchange ONE collective for the operand + all-reduce(sum) of k.  Split-float kinds (3xTF32 / 3xF16): every rank splits
+             its own slab into the hi / lo operand planes and the PLANES are all-gathered (f16: half the bytes of the f64
+             matrix; no rank converts the whole matrix) - phase 3 rebuilds a_ij from hi + lo.  FP64 / Ozaki: the f64 slabs
+             are all-gathered.  Slabs are equal (128-aligned, the last one ragged) so that a single all-gather serves.
     phase 3  TOM block rows of the pair-balanced range, upper tiles only
     """
     rank, world = _world(group)
     ver = TOM_V1 if version in ("v1", TOM_V1) else TOM_V2
-    a_full = backend.empty(p, p)  # row i of this tensor == column i of the column-major matrix
-    k = backend.zeros(p)
-    c0, c1 = even_slab(p, world, rank)
     cor_prec = precision if precision in (PREC_F64, _lib.PREC_TF32X3, _lib.PREC_F16X3, _lib.PREC_OZAKI, _lib.PREC_OZAKI4) else PREC_F64
+    r0, r1 = pair_balanced_rows(p, 1, world, rank)
+    rng = (packed_offset(r0, p, 1), packed_offset(r1, p, 1))
+    k = backend.zeros(p)
+    if world == 1:
+        a_full = backend.empty(p, p)  # row i of this tensor == column i of the column-major matrix
+        backend.affinity_cols(x, n, p, spearman, signed, beta, cor_prec, 0, p, a_full)
+        backend.tom_connectivity(a_full, p, signed, 0, p, k)
+        return backend.tom_rows(a_full, k, p, signed, ver, precision, r0, r1), rng
+    slab = gene_slab(p, world)
+    c0, c1 = min(p, rank * slab), min(p, (rank + 1) * slab)
+    a_full = backend.empty(world * slab, p)
     backend.affinity_cols(x, n, p, spearman, signed, beta, cor_prec, c0, c1, a_full)
     backend.tom_connectivity(a_full, p, signed, c0, c1, k)
-    if world > 1:
-        for r in range(world):
-            s0, s1 = even_slab(p, world, r)
-            if s1 > s0:
-                dist.broadcast(a_full[s0:s1], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    if precision in (_lib.PREC_TF32X3, _lib.PREC_F16X3):
+        rb = backend.tom_plane_row_bytes(p, precision)
+        planes = backend.empty_bytes(world * slab * rb)
+        backend.tom_split_planes(a_full, p, precision, c0, c1, planes)
+        dist.all_gather_into_tensor(planes, planes[rank * slab * rb : (rank + 1) * slab * rb], group=group)
         dist.all_reduce(k, op=dist.ReduceOp.SUM, group=group)
-    r0, r1 = pair_balanced_rows(p, 1, world, rank)
-    out = backend.tom_rows(a_full, k, p, signed, ver, precision, r0, r1)
-    return out, (packed_offset(r0, p, 1), packed_offset(r1, p, 1))
+        return backend.tom_rows_planes(planes, k, p, signed, ver, precision, r0, r1), rng
+    dist.all_gather_into_tensor(a_full, a_full[rank * slab : (rank + 1) * slab], group=group)
+    dist.all_reduce(k, op=dist.ReduceOp.SUM, group=group)
+    return backend.tom_rows(a_full, k, p, signed, ver, precision, r0, r1), rng
 
 
 def sharded_sparse_gram_cor(backend, indptr, indices, data, local_cells, genes, precision=PREC_F64, group=None):

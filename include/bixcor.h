@@ -263,6 +263,16 @@ int bixcor_dev_tom_connectivity(const double* d_a_pp, int64_t p, int signed_, in
                                 double* d_k);
 int bixcor_dev_tom_rows(const double* d_a_pp, const double* d_k, int64_t p, int signed_, int version,
                         int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out);
+/* Split-float kinds (BIXCOR_PREC_TF32X3 / BIXCOR_PREC_F16X3) with several ranks: the A * A operand is the pair of hi / lo
+ * planes of A, bixcor_dev_tom_plane_row_bytes(p, precision) contiguous bytes per gene.  Every rank splits only its own
+ * slab (rows [row_begin,row_end) of d_a_pp) into the full plane buffer, the planes are all-gathered (half the bytes of
+ * the f64 matrix for the f16 kind, and no rank converts the whole matrix), and phase 3 runs from the planes alone: the
+ * epilogue rebuilds a_ij and the diagonal from hi + lo (22 significant bits, inside the 1e-5 class of these kinds). */
+int64_t bixcor_dev_tom_plane_row_bytes(int64_t p, int precision);
+int bixcor_dev_tom_split_planes(const double* d_a_pp, int64_t p, int precision, int64_t row_begin, int64_t row_end,
+                                void* d_planes);
+int bixcor_dev_tom_rows_planes(const void* d_planes, const double* d_k, int64_t p, int signed_, int version,
+                               int precision, int packed, int64_t row_begin, int64_t row_end, double* d_out);
 /* sparse: accumulate the partial Gram (dense genes x genes, upper tiles valid) and
  * column sums of this rank's cell shard; finalise after the all-reduce. */
 int bixcor_dev_sparse_gram_accumulate(const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,

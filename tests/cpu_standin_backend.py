@@ -69,15 +69,25 @@ class OracleBackend:
         a_full[c0:c1] = torch.from_numpy(a[c0:c1])
 
     def tom_connectivity(self, a_full, p, signed, c0, c1, k):
-        if not signed:
-            a_full[c0:c1] = a_full[c0:c1].abs()
-        k[c0:c1] = a_full[c0:c1].abs().sum(dim=1)
+        k[c0:c1] = (a_full[c0:c1].abs() if signed else a_full[c0:c1]).sum(dim=1)
 
     def tom_rows(self, a_full, k, p, signed, version, precision, r0, r1):
-        a = a_full.numpy()
-        assert np.allclose(k.numpy(), np.abs(a).sum(axis=1))  # the all-reduced k is the full connectivity
-        t = o.calc_tom(a, True, "v1" if version == 1 else "v2")  # |A| already substituted when unsigned
+        a = a_full.numpy()[:p]  # multi-rank: equal padded slabs, the rows beyond p are never written
+        assert np.allclose(k.numpy(), (np.abs(a) if signed else a).sum(axis=1))  # the all-reduced k is the full connectivity
+        t = o.calc_tom(a, bool(signed), "v1" if version == 1 else "v2")
         return torch.from_numpy(np.ascontiguousarray(self._slice(o.dense_to_upper_triangle(t, True), p, 1, r0, r1)))
+
+    # split-float kinds: the stand-in's "planes" are the f64 rows themselves (8 bytes per entry), which exercises the
+    # slab split / plane all-gather / k all-reduce plumbing of sharded_tom_from_exp
+    def tom_plane_row_bytes(self, p, precision):
+        return 8 * p
+
+    def tom_split_planes(self, a_full, p, precision, c0, c1, planes):
+        planes.numpy().view(np.float64).reshape(-1, p)[c0:c1] = a_full.numpy()[c0:c1]
+
+    def tom_rows_planes(self, planes, k, p, signed, version, precision, r0, r1):
+        a = torch.from_numpy(planes.numpy().view(np.float64).reshape(-1, p)[:p].copy())
+        return self.tom_rows(a, k, p, signed, version, precision, r0, r1)
 
     def sparse_accumulate(self, indptr, indices, data, cells, genes, precision, gram, colsum):
         d = o._csr_to_dense(indptr.numpy(), indices.numpy(), data.numpy(), cells, genes)

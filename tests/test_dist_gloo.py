@@ -49,6 +49,9 @@ def _worker(rank, world, port, tmpdir):
             t, (t0, t1) = D.sharded_tom_from_exp(be, xt, n, p, False, signed, "v1", beta=2.0)
             tref = o.dense_to_upper_triangle(o.tom_from_exp(x, signed, "v1", False, 2.0), True)
             assert np.abs(t.numpy() - tref[t0:t1]).max() < 1e-12
+            # split-float kinds exchange the operand planes of each rank's slab instead of the f64 matrix
+            t2, (u0, u1) = D.sharded_tom_from_exp(be, xt, n, p, False, signed, "v1", beta=2.0, precision=D._lib.PREC_F16X3)
+            assert (u0, u1) == (t0, t1) and np.abs(t2.numpy() - tref[t0:t1]).max() < 1e-12
         # --- sparse: cell shards, Gram all-reduce
         cells, genes = 600, 30
         ip, ix, d = synthetic_sparse_cells(cells, genes, 3, density=0.2)
