@@ -59,6 +59,29 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def load_mma_peaks():
+    """tcgen05 issue peaks per MMA kind measured on this pool's B200 by scripts/micro/mma_peak.cu (back-to-back MMAs on
+    shared-memory-resident operands; profiles/mma_peaks_r02.json).  MEASURED_PEAKS.json only holds a cuBLAS bf16 figure."""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "mma_peaks_r02.json")))["rows"]
+        out = {}
+        for r in rows:
+            if "tflops" in r:
+                out[r["kind"]] = max(out.get(r["kind"], 0.0), float(r["tflops"]))
+        return out
+    except Exception:
+        return {}
+
+
+def load_d2h_floor():
+    """Device -> pinned host bandwidth of one GPU measured by scripts/micro/d2h_floor.cu (profiles/d2h_floor_n1_r02.json)."""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "d2h_floor_n1_r02.json")))["d2h_pinned"]
+        return max(float(r["gbs_per_gpu"]) for r in rows if r["gpus"] == 1)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons during the timed region.  NVML is polled from a thread every
     ~1 ms (the timed region of the default run is ~10 ms, shorter than one nvidia-smi -lms period);
@@ -339,26 +362,23 @@ def run_ours(args):
         cols_ms = tm["cols_ms"] / k_steps
         alg_flops = 2.0 * n * my_pairs  # 2n flop per pair, upper-triangle count
         ach = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        mma_peaks = load_mma_peaks()
         if pname == "f64":
             peak = dgemm_peak()
             note = "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry; nominal 40)"
-            mmas = 1
-        elif pname in ("i8", "auto"):
-            peak = 2.0 * peaks["bf16_tflops"]
-            note = f"2 x {peaks['src']} dense bf16 (= int8 tensor rate); the kernel issues 4 int8 MMAs per algorithmic flop pair"
-            mmas = 4
-        elif pname == "ozaki":
-            peak = 2.0 * peaks["bf16_tflops"]
-            note = f"2 x {peaks['src']} dense bf16 (= int8 tensor rate); 24 int8 MMAs per algorithmic flop pair (6 passes of 4)"
-            mmas = 24
-        elif pname == "f16":
-            peak = peaks["bf16_tflops"]
-            note = f"{peaks['src']} dense bf16 (= f16 tensor rate); the kernel issues 3 f16 MMAs per algorithmic flop pair"
-            mmas = 3
+            mmas, r1_basis = 1, peak
         else:
-            peak = 0.5 * peaks["bf16_tflops"]
-            note = f"0.5 x {peaks['src']} dense bf16 (= tf32 tensor rate); the kernel issues 3 tf32 MMAs per algorithmic flop pair"
-            mmas = 3
+            kind = {"i8": "i8", "auto": "i8", "ozaki": "i8", "f16": "f16", "tf32": "tf32"}[pname]
+            mmas = {"i8": 4, "auto": 4, "ozaki": 24, "f16": 3, "tf32": 3}[pname]
+            r1_basis = {"i8": 2.0, "f16": 1.0, "tf32": 0.5}[kind] * peaks["bf16_tflops"]  # round 1's assumed ratio of cuBLAS bf16
+            if kind in mma_peaks:
+                peak = mma_peaks[kind]
+                note = (f"tcgen05.mma kind::{kind} issue peak measured on this pool's B200 (scripts/micro/mma_peak.cu, "
+                        f"profiles/mma_peaks_r02.json); the kernel issues {mmas} MMAs per algorithmic flop pair; round 1 assumed "
+                        f"{r1_basis:.0f} (a ratio of the {peaks['src']} cuBLAS bf16 figure)")
+            else:
+                peak = r1_basis
+                note = f"assumed ratio of the {peaks['src']} cuBLAS bf16 figure (profiles/mma_peaks_r02.json missing)"
         out_bytes = 8.0 * my_pairs
         traffic = None
         if world == 1:
@@ -370,6 +390,7 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "gram_dmma_kernel" if pname == "f64" else "gram_umma_kernel",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": traffic,
                 "peak_source": note, "mma_issue_frac": mmas * ach / peak if peak else None,
+                "frac_of_round1_basis": ach / r1_basis if r1_basis else None,
                 "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / ms_step if ms_step else None,
                 "launches_per_step": tm["gemm_launches"] / k_steps,
                 "hbm_view": {"algorithmic_bytes": out_bytes + {"f64": 8.0, "i8": 2.0, "auto": 2.0, "tf32": 8.0, "f16": 4.0, "ozaki": 6.0}[pname] * 1024 * p,
@@ -470,6 +491,15 @@ def run_ours(args):
     t_pin = time_e2e(make_step(x_pin, out_pin))
     del x_pin, out_pin
 
+    # PCIe floor of the step: this rank's packed rows over one GPU's measured device -> pinned-host bandwidth
+    d2h_gbs = load_d2h_floor()
+    e2e_floor = None
+    if d2h_gbs:
+        floor_ms = allmax(8.0 * my_pairs / (d2h_gbs * 1e9) * 1e3)
+        e2e_floor = {"ms": floor_ms, "d2h_gbs_per_gpu": d2h_gbs, "frac_pageable": floor_ms / (1e3 * t_page), "frac_pinned": floor_ms / (1e3 * t_pin),
+                     "what": "largest per-rank result slice / measured cudaMemcpyAsync device->pinned bandwidth of one GPU "
+                             "(scripts/micro/d2h_floor.cu, profiles/d2h_floor_n1_r02.json); the input upload overlaps it (duplex)"}
+
     # ---- TOM wall time (config 4) as an extra metric: HBM resident (all N) and host -> host through the C ABI (N = 1)
     tom = None
     if not args.no_tom:
@@ -559,6 +589,7 @@ def run_ours(args):
                        "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
             "clocks": main["clocks"],
             "e2e": {"value": P_total / t_page, "unit": UNIT, "ms_per_step": 1e3 * t_page, "h2d_bytes_per_step": h2d_bytes,
+                    "floor": e2e_floor,
                     "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps, "host_buffers": "pageable",
                     "pinned": {"value": P_total / t_pin, "ms_per_step": 1e3 * t_pin},
                     "note": e2e_note + ", precision = " + primary + "; value: pageable host buffers (what an R session owns), "

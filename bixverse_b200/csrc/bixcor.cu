@@ -2339,6 +2339,11 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
   const bool use_nccl = !g_comms.empty();
   std::vector<double> k_host(use_nccl ? 0 : (size_t)p, 0.0);
   const int cor_prec = tom_cor_precision(precision, spearman, n);
+  const int tom_prec = resolve_precision_float(precision);
+  // split-float kinds: every device splits its own slab into the hi / lo operand planes and the PLANES are exchanged
+  // (f16: half the bytes of the f64 slabs, and no device converts the whole matrix); phase 3 runs from the planes alone
+  const bool planes_mode = use_nccl && is_split_float(tom_prec);
+  const size_t plane_rb = planes_mode ? (size_t)round_up((int)p, k_padding(tom_prec)) * (tom_prec == BIXCOR_PREC_F16X3 ? 4 : 8) : 0;
   return for_each_device([&](Ctx* c, int d, int nd) -> int {
     int64_t c0, c1;
     even_slab(p, nd, d, &c0, &c1);
@@ -2364,6 +2369,10 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
           CU_TRY(cudaMemcpy(k_host.data() + c0, d_k + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost));
         }
       }
+      if (planes_mode) {
+        RC_TRY(c->op[1].reserve(plane_rb * (size_t)p));
+        RC_TRY(dev_split_planes(c, d_a, p, tom_prec, c0, c1, c->op[1].ptr));
+      }
       return use_nccl ? BIXCOR_OK : finish(c);
     }();
     rc = bar.arrive(rc);  // every device reaches the exchange or none does (a collective with a missing rank would hang)
@@ -2376,8 +2385,13 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
         for (int s_ = 0; s_ < nd; ++s_) {
           int64_t s0, s1;
           even_slab(p, nd, s_, &s0, &s1);
-          if (s1 > s0)
+          if (s1 <= s0) continue;
+          if (planes_mode) {
+            char* pl = (char*)c->op[1].ptr + (size_t)s0 * plane_rb;
+            NCCL_TRY(g_nccl.Broadcast(pl, pl, (size_t)(s1 - s0) * plane_rb, ncclChar, s_, g_comms[d], c->compute));
+          } else {
             NCCL_TRY(g_nccl.Broadcast(d_a + s0 * p, d_a + s0 * p, (size_t)(s1 - s0) * p, ncclDouble, s_, g_comms[d], c->compute));
+          }
         }
         NCCL_TRY(g_nccl.AllReduce(d_k, d_k, (size_t)p, ncclDouble, ncclSum, g_comms[d], c->compute));
         NCCL_TRY(g_nccl.GroupEnd());
@@ -2403,14 +2417,16 @@ static int tom_multi_device(const double* x, int64_t n, const double* a_pp, int6
     if (packed) {
       const int64_t o0 = packed_row_offset(r0, p, 1), o1 = packed_row_offset(r1, p, 1);
       RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o1 - o0)));
-      RC_TRY(dev_tom_rows(c, d_a, d_k, p, signed_, version, precision, 1, r0, r1, (double*)c->out.ptr));
+      RC_TRY(dev_tom_rows(c, planes_mode ? nullptr : d_a, d_k, p, signed_, version, precision, 1, r0, r1, (double*)c->out.ptr,
+                          planes_mode ? c->op[1].ptr : nullptr));
       RC_TRY(finish(c));
       D2HPipe pipe(c, out);
       RC_TRY(pipe.push(out + o0, c->out.ptr, sizeof(double) * (size_t)(o1 - o0), nullptr));
       return pipe.finish();
     }
     RC_TRY(c->out.reserve(sizeof(double) * (size_t)p * p));  // strip mode addresses the full matrix
-    RC_TRY(dev_tom_rows(c, d_a, d_k, p, signed_, version, precision, 0, r0, r1, (double*)c->out.ptr));
+    RC_TRY(dev_tom_rows(c, planes_mode ? nullptr : d_a, d_k, p, signed_, version, precision, 0, r0, r1, (double*)c->out.ptr,
+                        planes_mode ? c->op[1].ptr : nullptr));
     RC_TRY(finish(c));
     D2HPipe pipe(c, out);
     RC_TRY(pipe.push(out + r0 * p, (double*)c->out.ptr + r0 * p, sizeof(double) * (size_t)(r1 - r0) * p, nullptr));
