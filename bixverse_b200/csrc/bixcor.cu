@@ -219,6 +219,9 @@ static void nccl_teardown() {
 }
 static std::mutex g_init_mu;
 static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM: measured fastest), env BIXCOR_DMMA_VARIANT
+static int g_umma_mc = 0;       // tcgen05 long-K kernels in 2 x 2 multicast clusters (env BIXCOR_UMMA_MC = 1): verified, measured, NOT
+                                // faster (20k TOM f16 25.2 vs 23.2 ms, TF32 44.4 vs 42.1 ms, profiles/README_r02.md): L2 already merges the
+                                // requests of up to ~4 SMs for the same lines, so 2-way multicast saves no L2 -> SM bandwidth
 static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
@@ -341,7 +344,7 @@ static void timing_collect(Ctx* c) {
 static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int upper_only, int band, int pairs,
                      TileList** out, int swap = 0) {
   if (!upper_only) swap = 0;
-  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs ? 1 : 0) + (swap ? 4 : 0), band);
+  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs == 1 ? 1 : 0) + (swap ? 4 : 0) + (pairs == 2 ? 8 : 0), band);
   auto it = c->tile_cache.find(key);
   if (it != c->tile_cache.end()) {
     *out = &it->second;
@@ -374,6 +377,12 @@ static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int 
           tiles.push_back(make_int2(bi, y));
         }
       }
+      continue;
+    }
+    if (pairs == 2) {  // 2 x 2 multicast super-tiles (first block row, first block column); validity is decided per CTA in the kernel
+      for (int bj = upper_only ? bb : 0; bj < nb; bj += 2)
+        for (int bi = bb; bi < be; bi += 2)
+          if (!upper_only || bi <= bj) tiles.push_back(make_int2(bi, bj));
       continue;
     }
     for (int bj = j0; bj < nb; ++bj) {
@@ -420,13 +429,18 @@ struct Operand {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static bool is_ozaki(int precision) { return precision == BIXCOR_PREC_OZAKI || precision == BIXCOR_PREC_OZAKI4; }
+static bool is_split_float(int precision) { return precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_F16X3; }
 
 // Does this (precision, epilogue) run on the CTA-pair tcgen05 kernels (=> pair tile lists)?  g_umma_ctas: 1 = never,
 // 3 = always, 2 (default) = where it measured faster on B200: the packed correlation (short K; -3 %).  With the
 // chunked FP32 promotion of the long-K TOM / sparse Grams the cross-CTA drain handshake costs more than the
 // halved B traffic saves (TOM 20k: 54 ms vs 43 ms), see profiles/umma_probe_r01.txt.
+// Returns the tile geometry: 0 = one CTA per 128 x 128 tile, 1 = CTA pair (256 x 128), 2 = 2 x 2 multicast cluster of single
+// CTAs (gram_umma.cuh, MC): the long-K A * A of the split-float TOM, which ncu shows bound by L2 -> SM operand traffic.
 static int umma_pairs(int precision, int epi) {
-  if (precision == BIXCOR_PREC_F64 || g_umma_ctas == 1) return 0;
+  if (precision == BIXCOR_PREC_F64) return 0;
+  if (g_umma_mc && epi == EPI_TOM && is_split_float(precision)) return 2;
+  if (g_umma_ctas == 1) return 0;
   if (is_ozaki(precision)) return 1;  // long-K digit passes stream their operands from HBM / L2: half the B traffic pays
   if (precision == BIXCOR_PREC_F16X3) return 1;  // f16 kind: pairs measured faster on the long-K TOM as well (29.9 -> 28.6 ms)
   return (g_umma_ctas == 3 || epi == EPI_PACKED) ? 1 : 0;
@@ -436,7 +450,6 @@ static int k_padding(int precision) {
   if (precision == BIXCOR_PREC_F16X3) return 64;
   return (precision == BIXCOR_PREC_F64 || is_ozaki(precision)) ? dmma::BK : (precision == BIXCOR_PREC_I8EXACT ? 128 : 32);
 }
-static bool is_split_float(int precision) { return precision == BIXCOR_PREC_TF32X3 || precision == BIXCOR_PREC_F16X3; }
 // precisions whose operand is ONE record per gene that ranks can exchange (F64, 3xTF32, int8 exact, 3xF16)
 static bool exchangeable(int precision) { return (precision >= 0 && precision <= 2) || precision == BIXCOR_PREC_F16X3; }
 
@@ -733,7 +746,7 @@ static int launch_gram_ozaki(Ctx* c, const Operand& a, int64_t p, const int2* ti
     ea.ldo = p;
     ea.scale = std::ldexp(1.0, -7 * (2 * ab[0] + 2 * ab[1] + 4));
     Timed tm(c, T_GEMM);
-    if (umma::launch_gram_umma(c->compute, c->sm_count, umma::KIND_I8, EPI_ACCUM, umma_pairs(a.precision, epi) ? 2 : 1, p, a.oz, a.ozK, nullptr, nullptr, 0,
+    if (umma::launch_gram_umma(c->compute, c->sm_count, umma::KIND_I8, EPI_ACCUM, umma_pairs(a.precision, epi) == 1 ? 2 : 1, p, a.oz, a.ozK, nullptr, nullptr, 0,
                                nullptr, tiles, ntiles, ea, OZ_SLICES, 2 * ab[0], 2 * ab[1], tile_sync_words(c)) != 0)
       return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
     g_launches++;
@@ -791,8 +804,12 @@ static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, co
   const void* pl0 = kind == umma::KIND_I8 ? (const void*)a.i8 : (const void*)a.f32;
   const void* pl1 = b ? (kind == umma::KIND_I8 ? (const void*)b->i8 : (const void*)b->f32) : nullptr;
   Timed tm(c, T_GEMM);
-  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, umma_pairs(a.precision, epi) ? 2 : 1, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
-                             b ? b->inv_norm : nullptr, tiles, ntiles, e, 2, 0, 0, tile_sync_words(c)) != 0)
+  const int geom = umma_pairs(a.precision, epi);
+  const int nbk = (int)((p + kTile - 1) / kTile);
+  const int rb0 = row0 >= 0 ? (int)(row0 / kTile) : 0, rb1 = row1 >= 0 ? (int)((row1 + kTile - 1) / kTile) : nbk;
+  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, geom == 1 ? 2 : 1, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
+                             b ? b->inv_norm : nullptr, tiles, ntiles, e, 2, 0, 0, tile_sync_words(c), geom == 2, rb0, rb1,
+                             e.upper_tiles) != 0)
     return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
   g_launches++;
   return BIXCOR_OK;
@@ -1489,6 +1506,7 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   e.tom_v2 = (version == BIXCOR_TOM_V2);
   e.tom_signed = signed_ ? 1 : 0;
   e.tom_packed = packed ? 1 : 0;
+  e.upper_tiles = upper;
   // non-packed strip mode writes into out + 0 with absolute (i*p + j) addressing
   return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_TOM, e, nullptr, row_begin, row_end);
 }
@@ -1754,6 +1772,7 @@ int bixcor_init_devices(int first_device, int n_gpus) {
                 count);
   if (const char* v = getenv("BIXCOR_DMMA_VARIANT")) g_dmma_variant = atoi(v);
   if (const char* v = getenv("BIXCOR_UMMA_CTAS")) g_umma_ctas = (atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 2;
+  if (const char* v = getenv("BIXCOR_UMMA_MC")) g_umma_mc = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_COPY_THREADS")) g_copy_threads = std::max(0, std::min(64, atoi(v)));
   if (const char* v = getenv("BIXCOR_STAGE_SLOT_MB")) g_stage_slot_bytes = (size_t)std::max(1, std::min(256, atoi(v))) << 20;
   if (const char* v = getenv("BIXCOR_STAGE_SLOTS")) g_stage_slots = std::max(2, std::min((int)HostStager::kMaxSlots, atoi(v)));

@@ -46,6 +46,7 @@ struct EpiParams {
   int tom_v2;
   int tom_signed;   // signed: |a_ij| in the denominators; unsigned: a_ij as passed (R/functions_stats.R:15-31)
   int tom_packed;
+  int upper_tiles;   // the launch's tile list holds upper-triangle tiles only (validity rule of the multicast super-tiles)
   // RBF affinity transform (crate core::math::rbf behind src/rust/src/base/r_rbf.rs and the
   // distance -> affinity step of rs_coremo_stability, src/rust/src/methods/r_coremo.rs:211-226)
   int rbf_mode;        // 0 none, BIXCOR_RBF_GAUSSIAN / _BUMP / _INVERSE_QUADRATIC

@@ -151,6 +151,8 @@ struct Params {
   int tile_sync_kb;     // > 0: additionally re-align every tile_sync_kb K blocks (env BIXCOR_UMMA_TILE_SYNC_KB, experiment)
   unsigned* tile_sync;  // long-K launches: global arrival counter, the TMA producers of all CTAs start every tile together
                         // so that CTAs sharing an operand panel stream it through L2 in step (nullptr = off)
+  int prefetch_kb;  // long-K launches: the producer asks the TMA unit to pull the operand boxes of K block kb + prefetch_kb into L2
+  int mc_nb, mc_rb0, mc_rb1, mc_upper;  // MC kernels: number of block columns, block rows of this launch, upper-triangle-only
   int dbg;  // profiling aid (env BIXCOR_UMMA_DEBUG): 1 = drain only, 2 = generic path without global stores, 3 = no MMA issue,
             // 4 = lean path without global stores, 5 = lean path without phase B, 6 = no TMA and no MMA (epilogue alone)
   EpiParams E;
@@ -249,6 +251,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// L2 prefetch of one box (no shared memory, no barrier): the long-K kernels run all CTAs in step along K, so the first CTA to
+// ask for a K slice misses to DRAM and its neighbours queue behind the same miss - every stage then waits a DRAM round trip
+// (~2 us) with only 128-144 KB in flight per SM.  Prefetching a few K blocks ahead turns those loads into L2 hits.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// Multicast TMA load (cluster of single CTAs): the box lands at the same shared-memory offset in every CTA of `mask` and
+// each destination CTA's own mbarrier (same offset) receives the complete_tx bytes.
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask` (the CTAs whose TMA multicasts write this
+// CTA's stage wait for its MMAs to have read it)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -579,7 +604,14 @@ __device__ __forceinline__ void packed_interior_bulk(const uint32_t (&racc)[EPI_
 
 // map0 / map1: 128-row boxes (A operand of pass 0 / 1); mapb0 / mapb1: the B operand boxes (128 rows for CTAS = 1,
 // 64 rows = this CTA's half of the B tile for CTAS = 2).
-template <int KIND, int EPI, int CTAS>
+// MC = 1 (CTAS must be 1; ablation, off by default - env BIXCOR_UMMA_MC=1): clusters of 2 x 2 CTAs work on 2 x 2 neighbouring tiles.  The A operand of a block row is needed
+// by the two CTAs of that cluster row, the B operand of a block column by the two CTAs of that cluster column: every CTA
+// loads HALF of its A tile and HALF of its B tile and multicasts each half to the two CTAs that need it, so a CTA pulls 32 KB
+// per K block out of L2 instead of 64 KB (a CTA pair: 48 KB).  ncu on the 20k TOM: 195 GB (f16, pairs) / 511 GB (TF32) of
+// L2 -> SM reads for a 1.6 / 3.2 GB operand, 8.9 TB/s sustained: the long-K kernels are bound by that path.  Measured: correct,
+// but no faster (profiles/README_r02.md) - the L2 already merges concurrent requests of a few SMs for the same lines, so a 2-way
+// multicast removes no traffic from the limiting L2 -> SM path; only more flops per operand byte (256-wide tiles) would.
+template <int KIND, int EPI, int CTAS, int MC = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                  const __grid_constant__ CUtensorMap mapb0, const __grid_constant__ CUtensorMap mapb1, const Params P) {
@@ -588,9 +620,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   constexpr int STAGES = Cfg<CTAS>::STAGES;
   constexpr int STAGE_BYTES = Cfg<CTAS>::STAGE_BYTES;
   constexpr int B_TILE_BYTES = Cfg<CTAS>::B_TILE_BYTES;
+  static_assert(!MC || CTAS == 1, "the multicast clusters are made of single CTAs");
+  constexpr int CL = MC ? 4 : CTAS;  // CTAs per scheduling unit (cluster size)
   uint32_t cta_rank = 0;
-  if (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-  const int unit0 = (int)blockIdx.x / CTAS, unit_stride = (int)gridDim.x / CTAS;  // tile (pair) scheduling units
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int mc_r = MC ? (int)(cta_rank >> 1) : 0, mc_c = MC ? (int)(cta_rank & 1u) : 0;  // position in the 2 x 2 cluster
+  const uint16_t mc_mask_a = (uint16_t)(0x3u << (2 * mc_r));                  // the CTAs of my cluster row (same block row)
+  const uint16_t mc_mask_b = (uint16_t)((1u << mc_c) | (1u << (mc_c + 2)));   // the CTAs of my cluster column (same block column)
+  const int unit0 = (int)blockIdx.x / CL, unit_stride = (int)gridDim.x / CL;  // tile (pair / cluster) scheduling units
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -613,7 +650,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), CTAS);  // one expect_tx arrive per CTA of the pair (the leader's barrier collects both)
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 3 : 1);  // MC: my MMAs and those of my row / column mates, whose stages my multicasts fill
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -633,7 +670,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     }
   }
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+  if (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
@@ -677,15 +714,28 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         const int2 tile = P.tiles[t];
         const int ty = tile.y & ~TILE_FLAGS;
         // M operand rows (this CTA's 128) and N operand rows (the whole tile, or this CTA's half of it)
-        const int a_row = ((tile.y & TILE_SWAPPED) ? ty + (int)cta_rank : tile.x + (int)cta_rank) * BM;
-        const int b_row = ((tile.y & TILE_SWAPPED) ? tile.x : ty) * BN + (CTAS == 2 ? (int)cta_rank * (BN / 2) : 0);
+        const int a_row = MC ? (tile.x + mc_r) * BM : ((tile.y & TILE_SWAPPED) ? ty + (int)cta_rank : tile.x + (int)cta_rank) * BM;
+        const int b_row = MC ? (ty + mc_c) * BN : ((tile.y & TILE_SWAPPED) ? tile.x : ty) * BN + (CTAS == 2 ? (int)cta_rank * (BN / 2) : 0);
         for (int pass = 0; pass < P.npass; ++pass) {
           const CUtensorMap* map = pass ? &map1 : &map0;
           const CUtensorMap* mapb = pass ? &mapb1 : &mapb0;
           const int kb_n = P.kblocks[pass];
           const int kelems = (KIND == KIND_TF32) ? 32 : (KIND == KIND_F16 ? 64 : 128);
+          // rows / maps of the boxes this CTA loads itself (they are also what it prefetches)
+          const CUtensorMap* pmap_a = (MC ? mapb : map);
+          const int pa_row = MC ? a_row + 64 * mc_c : a_row, pb_row = MC ? b_row + 64 * mc_r : b_row;
+          auto prefetch_kb = [&](int kq) {
+            tma_prefetch_3d(pmap_a, kq * kelems, P.plane_a0, pa_row);
+            tma_prefetch_3d(pmap_a, kq * kelems, P.plane_a0 + 1, pa_row);
+            tma_prefetch_3d(mapb, kq * kelems, P.plane_b0, pb_row);
+            tma_prefetch_3d(mapb, kq * kelems, P.plane_b0 + 1, pb_row);
+          };
+          const int pf = P.prefetch_kb;
+          if (pf > 0)
+            for (int kq = 0; kq < pf && kq < kb_n; ++kq) prefetch_kb(kq);
           for (int kb = 0; kb < kb_n; ++kb) {
             if (P.tile_sync_kb > 0 && kb > 0 && kb % P.tile_sync_kb == 0) grid_barrier();  // (experiment: re-align mid tile)
+            if (pf > 0 && kb + pf < kb_n) prefetch_kb(kb + pf);
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t s0 = base + stage * STAGE_BYTES;
             if (CTAS == 2) {
@@ -696,6 +746,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0 + 1, a_row);
               tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0, b_row);
               tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0 + 1, b_row);
+            } else if (MC) {
+              // my halves of the A / B tiles (64 rows each), multicast to the row / column mates; the other halves arrive from them
+              mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+              const uint32_t ha = (uint32_t)mc_c * (PLANE_TILE_BYTES / 2), hb = (uint32_t)mc_r * (PLANE_TILE_BYTES / 2);
+              tma_load_3d_mc(s0 + 0 * PLANE_TILE_BYTES + ha, mapb, full_bar(stage), kb * kelems, P.plane_a0, a_row + 64 * mc_c, mc_mask_a);
+              tma_load_3d_mc(s0 + 1 * PLANE_TILE_BYTES + ha, mapb, full_bar(stage), kb * kelems, P.plane_a0 + 1, a_row + 64 * mc_c, mc_mask_a);
+              tma_load_3d_mc(s0 + 2 * PLANE_TILE_BYTES + hb, mapb, full_bar(stage), kb * kelems, P.plane_b0, b_row + 64 * mc_r, mc_mask_b);
+              tma_load_3d_mc(s0 + 3 * PLANE_TILE_BYTES + hb, mapb, full_bar(stage), kb * kelems, P.plane_b0 + 1, b_row + 64 * mc_r, mc_mask_b);
             } else if (kProfile && P.dbg == 6) {  // profiling: no operand traffic at all
               mbar_arrive(full_bar(stage));
             } else {
@@ -715,7 +773,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA of a pair only) ===
-    if (lane == 0 && cta_rank == 0) {
+    if (lane == 0 && (MC || cta_rank == 0)) {  // MC: every CTA of the cluster issues its own cta_group::1 MMAs
       constexpr uint32_t idesc = make_idesc<KIND, CTAS>();
       constexpr uint32_t idesc_wide = make_idesc<KIND, CTAS, 2 * BN>();
       int stage = 0, acc_stage = 0;
@@ -761,6 +819,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               }
               // smem stage reusable (in both CTAs) once these MMAs have read it
               if (CTAS == 2) tc_commit_pair(empty_bar(stage));
+              else if (MC) tc_commit_mc(empty_bar(stage), (uint16_t)(mc_mask_a | mc_mask_b));
               else tc_commit(empty_bar(stage));
               if (++stage == STAGES) {
                 stage = 0;
@@ -821,10 +880,16 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     };
     for (int t = unit0; t < P.ntiles; t += unit_stride) {
       int2 tile = P.tiles[t];
-      const bool tile_valid = !(CTAS == 2 && cta_rank == 1 && (tile.y & TILE_SECOND_INVALID));
+      bool tile_valid = !(CTAS == 2 && cta_rank == 1 && (tile.y & TILE_SECOND_INVALID));
       const bool swapped = kSwapInterior && (EPI == EPI_PACKED) && (tile.y & TILE_SWAPPED);
       tile.y &= ~TILE_FLAGS;
       if (CTAS == 2) (swapped ? tile.y : tile.x) += (int)cta_rank;  // this CTA's block column / block row of the pair
+      if (MC) {  // this CTA's tile of the 2 x 2 super-tile; tiles outside the launch's rows / the matrix / the upper triangle
+                 // still run the protocol (their operand halves are needed by the mates) but store nothing
+        tile.x += mc_r;
+        tile.y += mc_c;
+        tile_valid = tile.x >= P.mc_rb0 && tile.x < P.mc_rb1 && tile.y < P.mc_nb && (!P.mc_upper || tile.x <= tile.y);
+      }
       const int row_base = tile.x * BM + ew * 32;
       const int i = row_base + lane;
       const int col_base = tile.y * BN + ch * EPI_COLS;
@@ -1208,7 +1273,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   }
 
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all();  // the peer's shared memory / TMEM stay alive until both CTAs are done
+  if (CL > 1) cluster_sync_all();  // the peers' shared memory / TMEM stay alive until all CTAs of the cluster are done
   else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
@@ -1266,33 +1331,40 @@ inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, i
   return 0;
 }
 
-template <int KIND, int EPI, int CTAS>
+template <int KIND, int EPI, int CTAS, int MC = 0>
 inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& b0,
                       const CUtensorMap& b1, const Params& P) {
-  auto kern = gram_umma_kernel<KIND, EPI, CTAS>;
+  auto kern = gram_umma_kernel<KIND, EPI, CTAS, MC>;
   constexpr int smem = smem_bytes_of<CTAS>();
+  constexpr int CL = MC ? 4 : CTAS;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     snprintf(err_buf(), 512, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return -1;
   }
-  const int units = sm_count / CTAS;  // persistent: one CTA (pair) per SM (TPC)
-  const int grid = CTAS * (P.ntiles < units ? P.ntiles : units);
+  int units = sm_count / CL;  // persistent: one CTA (pair / cluster) per SM (TPC / 4 SMs of a GPC)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (MC) {  // clusters of 4 must fit a GPC: ask how many can be resident at once (the long-K barrier needs all of them)
+    cfg.gridDim = dim3((unsigned)(units * CL));
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0 && max_clusters < units) units = max_clusters;
+    else cudaGetLastError();
+  }
+  const int grid = CL * (P.ntiles < units ? P.ntiles : units);
+  cfg.gridDim = dim3((unsigned)grid);
   e = cudaLaunchKernelEx(&cfg, kern, m0, m1, b0, b1, P);
   if (e != cudaSuccess) {
-    snprintf(err_buf(), 512, "gram_umma_kernel launch (CTAS = %d): %s", CTAS, cudaGetErrorString(e));
+    snprintf(err_buf(), 512, "gram_umma_kernel launch (CTAS = %d, MC = %d): %s", CTAS, MC, cudaGetErrorString(e));
     return -1;
   }
   return 0;
@@ -1303,7 +1375,8 @@ inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, 
 inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi, int ctas, int64_t rows,
                             const void* planes0, int K0, const double* inv0, const void* planes1, int K1,
                             const double* inv1, const int2* tiles, int ntiles, const EpiParams& E, int nplanes = 2,
-                            int plane_a0 = 0, int plane_b0 = 0, unsigned* tile_sync_counter = nullptr) {
+                            int plane_a0 = 0, int plane_b0 = 0, unsigned* tile_sync_counter = nullptr, int mc = 0,
+                            int mc_rb0 = 0, int mc_rb1 = 0, int mc_upper = 0) {
   if (ntiles <= 0) return 0;
   const int kelems = kind == KIND_TF32 ? 32 : (kind == KIND_F16 ? 64 : 128);
   if (K0 % kelems != 0 || (planes1 && K1 % kelems != 0)) {
@@ -1312,7 +1385,11 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   }
   CUtensorMap m0, m1, b0, b1;
   if (make_map(&m0, kind, planes0, rows, K0, BM, nplanes)) return -1;
-  if (make_map(&b0, kind, planes0, rows, K0, BN / ctas, nplanes)) return -1;
+  if (mc && (ctas != 1 || planes1)) {
+    snprintf(err_buf(), 512, "multicast clusters are made of single CTAs and take one operand set");
+    return -1;
+  }
+  if (make_map(&b0, kind, planes0, rows, K0, mc ? BN / 2 : BN / ctas, nplanes)) return -1;  // MC: 64-row halves of both tiles
   if (planes1) {
     if (make_map(&m1, kind, planes1, rows, K1)) return -1;
     if (make_map(&b1, kind, planes1, rows, K1, BN / ctas)) return -1;
@@ -1345,13 +1422,26 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
     }();
     if (tile_sync_counter && (sync_mode == 2 || (sync_mode == 1 && P.kblocks[0] >= 96))) {
       // armed only when the persistent grid fits the device at once (>= 1 CTA of this kernel per SM)
-      const int units = sm_count / ctas;
-      const bool grid_fits = ctas * (ntiles < units ? ntiles : units) <= sm_count;
+      const int cl = mc ? 4 : ctas;
+      const int units = sm_count / cl;
+      const bool grid_fits = cl * (ntiles < units ? ntiles : units) <= sm_count;
       if (grid_fits && cudaMemsetAsync(tile_sync_counter, 0, 2 * sizeof(unsigned), stream) == cudaSuccess) P.tile_sync = tile_sync_counter;
     }
   }
+  {
+    // env BIXCOR_UMMA_PREFETCH_KB: L2 prefetch distance of the long-K launches in K blocks (0 = off)
+    static const int pf_env = [] {
+      const char* v = getenv("BIXCOR_UMMA_PREFETCH_KB");
+      return v ? atoi(v) : 0;  // measured slower (20k TOM f16 23.2 -> 24.5 ms, TF32 42.1 -> 54.4 ms): kept as an ablation switch
+    }();
+    P.prefetch_kb = (P.kblocks[0] >= 96 && pf_env > 0) ? pf_env : 0;
+  }
   P.plane_a0 = plane_a0;
   P.plane_b0 = plane_b0;
+  P.mc_nb = (int)((rows + BM - 1) / BM);
+  P.mc_rb0 = mc_rb0;
+  P.mc_rb1 = mc_rb1;
+  P.mc_upper = mc_upper;
   P.prof = nullptr;
   {
     const char* d = getenv("BIXCOR_UMMA_DEBUG");
@@ -1385,6 +1475,18 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
                 dr / nt, ep / nt, nt);
     }
   } prof_dump{stream, want_prof ? d_prof : nullptr, sm_count};
+#define BIXCOR_UMMA_MC_CASE(KIND, EPI) \
+  if (mc && kind == KIND && epi == EPI) return launch_one<KIND, EPI, 1, 1>(stream, sm_count, m0, m1, b0, b1, P);
+  BIXCOR_UMMA_MC_CASE(KIND_F16, EPI_TOM)
+  BIXCOR_UMMA_MC_CASE(KIND_TF32, EPI_TOM)
+  BIXCOR_UMMA_MC_CASE(KIND_F16, EPI_ACCUM)
+  BIXCOR_UMMA_MC_CASE(KIND_TF32, EPI_ACCUM)
+  BIXCOR_UMMA_MC_CASE(KIND_I8, EPI_ACCUM)
+#undef BIXCOR_UMMA_MC_CASE
+  if (mc) {
+    snprintf(err_buf(), 512, "no multicast tcgen05 kernel for kind %d / epilogue %d", kind, epi);
+    return -1;
+  }
 #define BIXCOR_UMMA_CASE(KIND, EPI)                                                          \
   if (kind == KIND && epi == EPI)                                                            \
     return ctas == 2 ? launch_one<KIND, EPI, 2>(stream, sm_count, m0, m1, b0, b1, P)          \
