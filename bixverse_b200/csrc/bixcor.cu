@@ -222,6 +222,7 @@ static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM
 static int g_umma_mc = 0;       // tcgen05 long-K kernels in 2 x 2 multicast clusters (env BIXCOR_UMMA_MC = 1): verified, measured, NOT
                                 // faster (20k TOM f16 25.2 vs 23.2 ms, TF32 44.4 vs 42.1 ms, profiles/README_r02.md): L2 already merges the
                                 // requests of up to ~4 SMs for the same lines, so 2-way multicast saves no L2 -> SM bandwidth
+static int g_umma_wide = 0;     // split-float TOM on 256 x 256 pair tiles (env BIXCOR_UMMA_WIDE)
 static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
@@ -344,7 +345,7 @@ static void timing_collect(Ctx* c) {
 static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int upper_only, int band, int pairs,
                      TileList** out, int swap = 0) {
   if (!upper_only) swap = 0;
-  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs == 1 ? 1 : 0) + (swap ? 4 : 0) + (pairs == 2 ? 8 : 0), band);
+  auto key = std::make_tuple(p, row_begin, row_end, upper_only * 2 + (pairs == 1 ? 1 : 0) + (swap ? 4 : 0) + (pairs == 2 ? 8 : 0) + (pairs == 3 ? 16 : 0), band);
   auto it = c->tile_cache.find(key);
   if (it != c->tile_cache.end()) {
     *out = &it->second;
@@ -377,6 +378,16 @@ static int get_tiles(Ctx* c, int64_t p, int64_t row_begin, int64_t row_end, int 
           tiles.push_back(make_int2(bi, y));
         }
       }
+      continue;
+    }
+    if (pairs == 3) {  // wide pair tiles: (first block row of the pair, 256-column block | flags); the epilogue predicates j > i
+      const int nw = (nb + 1) / 2;
+      for (int wj = upper_only ? bb / 2 : 0; wj < nw; ++wj)
+        for (int bi = bb; bi < be; bi += 2) {
+          if (upper_only && wj < bi / 2) continue;
+          const bool second_ok = (bi + 1 < b1) && (!upper_only || wj >= (bi + 1) / 2);
+          tiles.push_back(make_int2(bi, second_ok ? wj : (wj | umma::TILE_SECOND_INVALID)));
+        }
       continue;
     }
     if (pairs == 2) {  // 2 x 2 multicast super-tiles (first block row, first block column); validity is decided per CTA in the kernel
@@ -439,6 +450,7 @@ static bool is_split_float(int precision) { return precision == BIXCOR_PREC_TF32
 // CTAs (gram_umma.cuh, MC): the long-K A * A of the split-float TOM, which ncu shows bound by L2 -> SM operand traffic.
 static int umma_pairs(int precision, int epi) {
   if (precision == BIXCOR_PREC_F64) return 0;
+  if (g_umma_wide && epi == EPI_TOM && is_split_float(precision)) return 3;  // 256 x 256 tiles per CTA pair
   if (g_umma_mc && epi == EPI_TOM && is_split_float(precision)) return 2;
   if (g_umma_ctas == 1) return 0;
   if (is_ozaki(precision)) return 1;  // long-K digit passes stream their operands from HBM / L2: half the B traffic pays
@@ -807,9 +819,9 @@ static int launch_gram(Ctx* c, const Operand& a, const Operand* b, int64_t p, co
   const int geom = umma_pairs(a.precision, epi);
   const int nbk = (int)((p + kTile - 1) / kTile);
   const int rb0 = row0 >= 0 ? (int)(row0 / kTile) : 0, rb1 = row1 >= 0 ? (int)((row1 + kTile - 1) / kTile) : nbk;
-  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, geom == 1 ? 2 : 1, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
-                             b ? b->inv_norm : nullptr, tiles, ntiles, e, 2, 0, 0, tile_sync_words(c), geom == 2, rb0, rb1,
-                             e.upper_tiles) != 0)
+  if (umma::launch_gram_umma(c->compute, c->sm_count, kind, epi, (geom == 1 || geom == 3) ? 2 : 1, p, pl0, a.K, a.inv_norm, pl1, b ? b->K : 0,
+                             b ? b->inv_norm : nullptr, tiles, ntiles, e, 2, 0, 0, tile_sync_words(c), geom == 2 ? 1 : (geom == 3 ? 2 : 0),
+                             rb0, rb1, e.upper_tiles) != 0)
     return fail(BIXCOR_ERR_UNSUPPORTED, "tcgen05 path: %s", umma::last_error());
   g_launches++;
   return BIXCOR_OK;
@@ -1533,8 +1545,21 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   return BIXCOR_OK;
 }
 
+// binary16 planes: values of magnitude >= 63 do not fit; the densify kernels raise a device flag that the host reads once
+static int sparse_overflow_check(Ctx* c) {
+  int overflow = 0;
+  CU_TRY(cudaMemcpyAsync(&overflow, c->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+  CU_TRY(cudaStreamSynchronize(c->compute));
+  if (overflow)
+    return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_F16X3 needs sparse values below 63 in magnitude; use BIXCOR_PREC_TF32X3");
+  return BIXCOR_OK;
+}
+
+// streamed != 0: one slab of a longer sequence - the caller has cleared the overflow flag and checks it at the end (the
+// check synchronises the stream, which would serialise the upload of the next slab behind this one's kernels)
 static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t* d_indices, const float* d_data,
-                                 int64_t cells, int64_t genes, int precision, double* d_gram, double* d_colsum) {
+                                 int64_t cells, int64_t genes, int precision, double* d_gram, double* d_colsum,
+                                 int streamed = 0) {
   precision = resolve_precision_float(precision);
   if (precision != BIXCOR_PREC_F64 && !is_split_float(precision))
     return fail(BIXCOR_ERR_UNSUPPORTED, "sparse Gram runs on BIXCOR_PREC_F64, BIXCOR_PREC_TF32X3 or BIXCOR_PREC_F16X3");
@@ -1543,7 +1568,7 @@ static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t*
   if (half) {
     RC_TRY(c->flag.reserve(256));
     d_flag = (int*)c->flag.ptr;
-    CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), c->compute));
+    if (!streamed) CU_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), c->compute));
   }
   const int chunk = 8192;  // cells per dense panel (K of one Gram accumulation pass)
   RC_TRY(c->panel.reserve(sizeof(double) * (size_t)chunk * genes));  // f64 panel == two f32 planes
@@ -1583,13 +1608,7 @@ static int dev_sparse_accumulate(Ctx* c, const int64_t* d_indptr, const int32_t*
     RC_TRY(launch_gram(c, op, nullptr, genes, tl->d_tiles, tl->ntiles, EPI_ACCUM, e));
   }
   CU_TRY(cudaGetLastError());
-  if (half) {
-    int overflow = 0;
-    CU_TRY(cudaMemcpyAsync(&overflow, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
-    CU_TRY(cudaStreamSynchronize(c->compute));
-    if (overflow)
-      return fail(BIXCOR_ERR_UNSUPPORTED, "BIXCOR_PREC_F16X3 needs sparse values below 63 in magnitude; use BIXCOR_PREC_TF32X3");
-  }
+  if (half && !streamed) RC_TRY(sparse_overflow_check(c));
   return BIXCOR_OK;
 }
 
@@ -1795,6 +1814,7 @@ int bixcor_init_devices(int first_device, int n_gpus) {
   if (const char* v = getenv("BIXCOR_DMMA_VARIANT")) g_dmma_variant = atoi(v);
   if (const char* v = getenv("BIXCOR_UMMA_CTAS")) g_umma_ctas = (atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 2;
   if (const char* v = getenv("BIXCOR_UMMA_MC")) g_umma_mc = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_UMMA_WIDE")) g_umma_wide = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_COPY_THREADS")) g_copy_threads = std::max(0, std::min(64, atoi(v)));
   if (const char* v = getenv("BIXCOR_STAGE_SLOT_MB")) g_stage_slot_bytes = (size_t)std::max(1, std::min(256, atoi(v))) << 20;
   if (const char* v = getenv("BIXCOR_STAGE_SLOTS")) g_stage_slots = std::max(2, std::min((int)HostStager::kMaxSlots, atoi(v)));
@@ -3005,31 +3025,55 @@ int bixcor_sparse_pairwise_cor_cells(const int64_t* indptr, const int32_t* indic
 // accumulate the partial X'X and the column sums into d_gram / d_colsum (zeroed here).
 static int sparse_shard_accumulate(Ctx* c, const int64_t* indptr, const int32_t* indices, const float* data, int64_t cs0,
                                    int64_t cs1, int64_t genes, int precision, double** d_gram, double** d_colsum) {
-  const int64_t nc = cs1 - cs0, off = indptr[cs0], nnz = indptr[cs1] - off;
-  const size_t b_ptr = sizeof(int64_t) * (size_t)(nc + 1), b_idx = sizeof(int32_t) * (size_t)nnz, b_dat = sizeof(float) * (size_t)nnz;
-  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-  RC_TRY(c->sparse_in.reserve(al(b_ptr) + al(b_idx) + al(b_dat) + 256));
-  char* base = (char*)c->sparse_in.ptr;
-  int64_t* d_ptr = (int64_t*)base;
-  int32_t* d_idx = (int32_t*)(base + al(b_ptr));
-  float* d_dat = (float*)(base + al(b_ptr) + al(b_idx));
-  if (off == 0) {
-    RC_TRY(h2d(c, d_ptr, indptr + cs0, b_ptr, c->compute));
-  } else {
-    std::vector<int64_t> local((size_t)nc + 1);
-    for (int64_t i = 0; i <= nc; ++i) local[(size_t)i] = indptr[cs0 + i] - off;
-    RC_TRY(h2d(c, d_ptr, local.data(), b_ptr, c->compute));
-    CU_TRY(cudaStreamSynchronize(c->compute));  // `local` is a stack-owned staging vector
-  }
-  RC_TRY(h2d(c, d_idx, indices + off, b_idx, c->compute));
-  RC_TRY(h2d(c, d_dat, data + off, b_dat, c->compute));
+  const int64_t nc = cs1 - cs0;
+  precision = resolve_precision_float(precision);
   RC_TRY(c->out2.reserve(sizeof(double) * (size_t)genes * genes));
   RC_TRY(c->vec.reserve(sizeof(double) * (size_t)genes * 4));
+  RC_TRY(c->flag.reserve(256));
   CU_TRY(cudaMemsetAsync(c->out2.ptr, 0, sizeof(double) * (size_t)genes * genes, c->compute));
   CU_TRY(cudaMemsetAsync(c->vec.ptr, 0, sizeof(double) * (size_t)genes, c->compute));
+  CU_TRY(cudaMemsetAsync(c->flag.ptr, 0, sizeof(int), c->compute));
   *d_gram = (double*)c->out2.ptr;
   *d_colsum = (double*)c->vec.ptr;
-  if (nc > 0) RC_TRY(dev_sparse_accumulate(c, d_ptr, d_idx, d_dat, nc, genes, precision, *d_gram, *d_colsum));
+  if (nc <= 0) return BIXCOR_OK;
+  // The CSR arrays (2 GB at 1M cells x 250 non-zeros) go up in slabs of 8 dense panels; the upload of slab s + 1 (copy-in
+  // stream, two device buffers) runs while the densify + Gram kernels of slab s are busy, so the host -> device transfer is
+  // hidden behind the math instead of preceding it.
+  const int64_t kSlab = 8 * 8192;
+  const int64_t nslab = (nc + kSlab - 1) / kSlab;
+  int64_t max_nnz = 0;
+  for (int64_t sl = 0; sl < nslab; ++sl) {
+    const int64_t b = cs0 + sl * kSlab, e = std::min(cs1, b + kSlab);
+    max_nnz = std::max(max_nnz, indptr[e] - indptr[b]);
+  }
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t b_ptr = al(sizeof(int64_t) * (size_t)(std::min(nc, kSlab) + 1)), b_idx = al(sizeof(int32_t) * (size_t)max_nnz),
+               b_dat = al(sizeof(float) * (size_t)max_nnz), half_bytes = b_ptr + b_idx + b_dat;
+  RC_TRY(c->sparse_in.reserve(2 * half_bytes + 256));
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  std::vector<int64_t> local;
+  for (int64_t sl = 0; sl < nslab; ++sl) {
+    const int h = (int)(sl & 1);
+    const int64_t b = cs0 + sl * kSlab, e = std::min(cs1, b + kSlab), ncell = e - b, off = indptr[b], nnz = indptr[e] - off;
+    char* base = (char*)c->sparse_in.ptr + (size_t)h * half_bytes;
+    int64_t* d_ptr = (int64_t*)base;
+    int32_t* d_idx = (int32_t*)(base + b_ptr);
+    float* d_dat = (float*)(base + b_ptr + b_idx);
+    if (done[h]) CU_TRY(cudaStreamWaitEvent(c->copy_in, done[h], 0));  // the kernels that read this buffer two slabs ago
+    local.resize((size_t)ncell + 1);
+    for (int64_t i = 0; i <= ncell; ++i) local[(size_t)i] = indptr[b + i] - off;  // row pointers relative to the slab
+    RC_TRY(h2d(c, d_ptr, local.data(), sizeof(int64_t) * (size_t)(ncell + 1), c->copy_in));
+    CU_TRY(cudaStreamSynchronize(c->copy_in));  // `local` is reused by the next slab (pinned callers: plain async DMA above)
+    RC_TRY(h2d(c, d_idx, indices + off, sizeof(int32_t) * (size_t)nnz, c->copy_in));
+    RC_TRY(h2d(c, d_dat, data + off, sizeof(float) * (size_t)nnz, c->copy_in));
+    cudaEvent_t up = ctx_event(c);
+    CU_TRY(cudaEventRecord(up, c->copy_in));
+    CU_TRY(cudaStreamWaitEvent(c->compute, up, 0));
+    RC_TRY(dev_sparse_accumulate(c, d_ptr, d_idx, d_dat, ncell, genes, precision, *d_gram, *d_colsum, 1));
+    done[h] = ctx_event(c);
+    CU_TRY(cudaEventRecord(done[h], c->compute));
+  }
+  if (precision == BIXCOR_PREC_F16X3) RC_TRY(sparse_overflow_check(c));
   return BIXCOR_OK;
 }
 

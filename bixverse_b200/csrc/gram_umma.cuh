@@ -611,15 +611,30 @@ __device__ __forceinline__ void packed_interior_bulk(const uint32_t (&racc)[EPI_
 // L2 -> SM reads for a 1.6 / 3.2 GB operand, 8.9 TB/s sustained: the long-K kernels are bound by that path.  Measured: correct,
 // but no faster (profiles/README_r02.md) - the L2 already merges concurrent requests of a few SMs for the same lines, so a 2-way
 // multicast removes no traffic from the limiting L2 -> SM path; only more flops per operand byte (256-wide tiles) would.
-template <int KIND, int EPI, int CTAS, int MC = 0>
-__global__ void __launch_bounds__(THREADS, 1)
+// WIDE = 1 (CTA pairs, split-float kinds, EPI_TOM): 256 x 256 tiles per pair.  Each CTA stages its 128 rows of A and 128 of
+// the 256 B rows, one MMA covers M = 256 x N = 256: operand bytes per flop drop by a third against the 256 x 128 pair tile
+// (the long-K kernels sit on the L2 -> SM operand path, profiles/README_r02.md).  The two accumulator stages of the chunked
+// promotion take all 512 TMEM columns; 16 epilogue warps (640 threads, 96 registers) keep the 64 running sums per thread;
+// the epilogue stores straight from the lane = row layout (no shared-memory staging: the smem holds 3 stages of 64 KB).
+constexpr int WIDE_EPI_WARPS = 16;
+constexpr int WIDE_THREADS = 128 + 32 * WIDE_EPI_WARPS;
+constexpr int WIDE_STAGES = 3;
+constexpr int WIDE_STAGE_BYTES = 4 * PLANE_TILE_BYTES;
+constexpr int wide_smem_bytes() { return WIDE_STAGES * WIDE_STAGE_BYTES + 1024 + 256; }
+
+template <int KIND, int EPI, int CTAS, int MC = 0, int WIDE = 0>
+__global__ void __launch_bounds__(WIDE ? WIDE_THREADS : THREADS, 1)
 gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                  const __grid_constant__ CUtensorMap mapb0, const __grid_constant__ CUtensorMap mapb1, const Params P) {
   using T = KindTraits<KIND>;
-  constexpr int TMEM_COLS = (T::NACC * T::ACC_STAGES * BN <= 256) ? 256 : 512;
-  constexpr int STAGES = Cfg<CTAS>::STAGES;
-  constexpr int STAGE_BYTES = Cfg<CTAS>::STAGE_BYTES;
-  constexpr int B_TILE_BYTES = Cfg<CTAS>::B_TILE_BYTES;
+  static_assert(!WIDE || (CTAS == 2 && !MC && KIND != KIND_I8 && EPI == EPI_TOM), "wide tiles: CTA pairs, split-float kinds, TOM epilogue");
+  constexpr int BNT = WIDE ? 2 * BN : BN;                      // tile width (accumulator columns)
+  constexpr int EPIW = WIDE ? WIDE_EPI_WARPS : EPI_WARPS;      // epilogue warps: (TMEM lane quarter) x (64-column slice)
+  constexpr int TMEM_COLS = (T::NACC * T::ACC_STAGES * BNT <= 256) ? 256 : 512;
+  static_assert(T::NACC * T::ACC_STAGES * BNT <= 512, "TMEM has 512 columns");
+  constexpr int STAGES = WIDE ? WIDE_STAGES : Cfg<CTAS>::STAGES;
+  constexpr int STAGE_BYTES = WIDE ? WIDE_STAGE_BYTES : Cfg<CTAS>::STAGE_BYTES;
+  constexpr int B_TILE_BYTES = WIDE ? PLANE_TILE_BYTES : Cfg<CTAS>::B_TILE_BYTES;
   static_assert(!MC || CTAS == 1, "the multicast clusters are made of single CTAs");
   constexpr int CL = MC ? 4 : CTAS;  // CTAs per scheduling unit (cluster size)
   uint32_t cta_rank = 0;
@@ -654,7 +669,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs, on the leader)
+      mbar_init(tempty_bar(s), EPIW * CTAS);  // one arrive per epilogue warp (of both CTAs, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -715,7 +730,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         const int ty = tile.y & ~TILE_FLAGS;
         // M operand rows (this CTA's 128) and N operand rows (the whole tile, or this CTA's half of it)
         const int a_row = MC ? (tile.x + mc_r) * BM : ((tile.y & TILE_SWAPPED) ? ty + (int)cta_rank : tile.x + (int)cta_rank) * BM;
-        const int b_row = MC ? (ty + mc_c) * BN : ((tile.y & TILE_SWAPPED) ? tile.x : ty) * BN + (CTAS == 2 ? (int)cta_rank * (BN / 2) : 0);
+        const int b_row = MC ? (ty + mc_c) * BN : ((tile.y & TILE_SWAPPED) ? tile.x : ty) * BNT + (CTAS == 2 ? (int)cta_rank * (BNT / 2) : 0);
         for (int pass = 0; pass < P.npass; ++pass) {
           const CUtensorMap* map = pass ? &map1 : &map0;
           const CUtensorMap* mapb = pass ? &mapb1 : &mapb0;
@@ -741,11 +756,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             if (CTAS == 2) {
               // the leader's full barrier counts the bytes of both CTAs; B rows: this CTA's half of the tile
               const uint32_t fb = mapa_rank(full_bar(stage), 0);
-              mbar_expect_tx_cluster(fb, STAGE_BYTES);
+              // profiling (dbg 11 / 12): leave out one / two of the four operand boxes - the results are garbage, the time
+              // tells how much of the K loop is operand traffic (profiles/README_r02.md)
+              const int skip = (kProfile && (P.dbg == 11 || P.dbg == 12)) ? P.dbg - 10 : 0;
+              mbar_expect_tx_cluster(fb, STAGE_BYTES - (skip >= 1 ? B_TILE_BYTES : 0) - (skip >= 2 ? PLANE_TILE_BYTES : 0));
               tma_load_3d_pair(s0 + 0 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0, a_row);
-              tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0 + 1, a_row);
+              if (skip < 2) tma_load_3d_pair(s0 + 1 * PLANE_TILE_BYTES, map, fb, kb * kelems, P.plane_a0 + 1, a_row);
               tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0, b_row);
-              tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0 + 1, b_row);
+              if (skip < 1) tma_load_3d_pair(s0 + 2 * PLANE_TILE_BYTES + B_TILE_BYTES, mapb, fb, kb * kelems, P.plane_b0 + 1, b_row);
             } else if (MC) {
               // my halves of the A / B tiles (64 rows each), multicast to the row / column mates; the other halves arrive from them
               mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -774,7 +792,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA of a pair only) ===
     if (lane == 0 && (MC || cta_rank == 0)) {  // MC: every CTA of the cluster issues its own cta_group::1 MMAs
-      constexpr uint32_t idesc = make_idesc<KIND, CTAS>();
+      constexpr uint32_t idesc = make_idesc<KIND, CTAS, BNT>();
       constexpr uint32_t idesc_wide = make_idesc<KIND, CTAS, 2 * BN>();
       int stage = 0, acc_stage = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -788,7 +806,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             if (CTAS == 2) mbar_wait_cluster(tempty_bar(acc_stage), acc_phase ^ 1u);
             else mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);
             tc_fence_after();
-            const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * T::NACC * BN);
+            const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * T::NACC * BNT);
             for (int kb = kb0; kb < kb1; ++kb) {
               if (CTAS == 2) mbar_wait_cluster(full_bar(stage), phase);
               else mbar_wait(full_bar(stage), phase);
@@ -892,7 +910,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       }
       const int row_base = tile.x * BM + ew * 32;
       const int i = row_base + lane;
-      const int col_base = tile.y * BN + ch * EPI_COLS;
+      const int col_base = tile.y * BNT + ch * EPI_COLS;
       for (int pass = 0; pass < P.npass; ++pass) {
         // Interior tiles of the packed correlation (97% of the tiles at p = 20000) lie strictly above the
         // diagonal and fully inside the matrix: nothing is predicated and they take the lean path below.
@@ -1026,7 +1044,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             mbar_wait(tfull_bar(acc_stage), acc_phase);
             if (kProfile && P.prof && kb0 == 0) pt1 = clock64();
             tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BN);
+            const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_stage * T::NACC * BNT);
             if (KIND == KIND_I8) {
               // `dep` is always 0 (P.zero is a runtime 0): it chains each batch of loads to the previous
               // batch's sums (all 16 of them, or ptxas only hurries the one it needs), otherwise ptxas hoists all 12 tcgen05.ld (192 registers) and spills.
@@ -1088,6 +1106,20 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         };
         if (dbg == 1 || !tile_valid) {  // (a pair's second block row that holds nothing: protocol only)
           if (direct) release_direct();
+          continue;
+        }
+        // ---- wide tiles: straight from the lane = row layout (every lane finishes 64 consecutive entries of its own row)
+        if (WIDE) {
+          if (i < pp) {
+            const EpiRow R = epi_row<EPI>(E, i);
+#pragma unroll
+            for (int q = 0; q < EPI_COLS; ++q) {
+              const int j = col_base + q;
+              double v = (double)__uint_as_float(racc[q]);
+              if (scale != 1.0) v *= scale;
+              if (j < pp) epi_store<EPI, true>(E, R, j, v, pass);
+            }
+          }
           continue;
         }
         // ---- transposed interior tile: lane = output column, register = output row; coalesced stores from registers
@@ -1331,11 +1363,11 @@ inline int make_map(CUtensorMap* map, int kind, const void* ptr, int64_t rows, i
   return 0;
 }
 
-template <int KIND, int EPI, int CTAS, int MC = 0>
+template <int KIND, int EPI, int CTAS, int MC = 0, int WIDE = 0>
 inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& b0,
                       const CUtensorMap& b1, const Params& P) {
-  auto kern = gram_umma_kernel<KIND, EPI, CTAS, MC>;
-  constexpr int smem = smem_bytes_of<CTAS>();
+  auto kern = gram_umma_kernel<KIND, EPI, CTAS, MC, WIDE>;
+  constexpr int smem = WIDE ? wide_smem_bytes() : smem_bytes_of<CTAS>();
   constexpr int CL = MC ? 4 : CTAS;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
@@ -1344,7 +1376,7 @@ inline int launch_one(cudaStream_t stream, int sm_count, const CUtensorMap& m0, 
   }
   int units = sm_count / CL;  // persistent: one CTA (pair / cluster) per SM (TPC / 4 SMs of a GPC)
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(WIDE ? WIDE_THREADS : THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1385,11 +1417,18 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
   }
   CUtensorMap m0, m1, b0, b1;
   if (make_map(&m0, kind, planes0, rows, K0, BM, nplanes)) return -1;
+  const int wide = (mc == 2);  // mc: 0 plain, 1 = 2 x 2 multicast clusters, 2 = 256 x 256 tiles per CTA pair
+  if (wide) mc = 0;
   if (mc && (ctas != 1 || planes1)) {
     snprintf(err_buf(), 512, "multicast clusters are made of single CTAs and take one operand set");
     return -1;
   }
-  if (make_map(&b0, kind, planes0, rows, K0, mc ? BN / 2 : BN / ctas, nplanes)) return -1;  // MC: 64-row halves of both tiles
+  if (wide && (ctas != 2 || planes1)) {
+    snprintf(err_buf(), 512, "wide tiles run on CTA pairs and take one operand set");
+    return -1;
+  }
+  // B boxes: MC 64-row halves of both tiles; wide: this CTA's 128 of the 256 tile columns; pairs: 64; single: 128
+  if (make_map(&b0, kind, planes0, rows, K0, mc ? BN / 2 : (wide ? BN : BN / ctas), nplanes)) return -1;
   if (planes1) {
     if (make_map(&m1, kind, planes1, rows, K1)) return -1;
     if (make_map(&b1, kind, planes1, rows, K1, BN / ctas)) return -1;
@@ -1475,6 +1514,12 @@ inline int launch_gram_umma(cudaStream_t stream, int sm_count, int kind, int epi
                 dr / nt, ep / nt, nt);
     }
   } prof_dump{stream, want_prof ? d_prof : nullptr, sm_count};
+  if (wide) {
+    if (kind == KIND_F16 && epi == EPI_TOM) return launch_one<KIND_F16, EPI_TOM, 2, 0, 1>(stream, sm_count, m0, m1, b0, b1, P);
+    if (kind == KIND_TF32 && epi == EPI_TOM) return launch_one<KIND_TF32, EPI_TOM, 2, 0, 1>(stream, sm_count, m0, m1, b0, b1, P);
+    snprintf(err_buf(), 512, "no wide-tile tcgen05 kernel for kind %d / epilogue %d", kind, epi);
+    return -1;
+  }
 #define BIXCOR_UMMA_MC_CASE(KIND, EPI) \
   if (mc && kind == KIND && epi == EPI) return launch_one<KIND, EPI, 1, 1>(stream, sm_count, m0, m1, b0, b1, P);
   BIXCOR_UMMA_MC_CASE(KIND_F16, EPI_TOM)
