@@ -222,7 +222,8 @@ static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM
 static int g_umma_mc = 0;       // tcgen05 long-K kernels in 2 x 2 multicast clusters (env BIXCOR_UMMA_MC = 1): verified, measured, NOT
                                 // faster (20k TOM f16 25.2 vs 23.2 ms, TF32 44.4 vs 42.1 ms, profiles/README_r02.md): L2 already merges the
                                 // requests of up to ~4 SMs for the same lines, so 2-way multicast saves no L2 -> SM bandwidth
-static int g_umma_wide = 0;     // split-float TOM on 256 x 256 pair tiles (env BIXCOR_UMMA_WIDE)
+static int g_umma_wide = 1;     // TOM on 256 x 256 pair tiles (env BIXCOR_UMMA_WIDE): 0 never, 1 = the TF32 kind (20k TOM 42.1 -> 40.3 ms; its
+                                // plain form runs single CTAs), 2 = the f16 kind as well (measured slower: 25.2 vs 23.2 ms)
 static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
@@ -450,7 +451,8 @@ static bool is_split_float(int precision) { return precision == BIXCOR_PREC_TF32
 // CTAs (gram_umma.cuh, MC): the long-K A * A of the split-float TOM, which ncu shows bound by L2 -> SM operand traffic.
 static int umma_pairs(int precision, int epi) {
   if (precision == BIXCOR_PREC_F64) return 0;
-  if (g_umma_wide && epi == EPI_TOM && is_split_float(precision)) return 3;  // 256 x 256 tiles per CTA pair
+  if (epi == EPI_TOM && ((g_umma_wide == 2 && is_split_float(precision)) || (g_umma_wide == 1 && precision == BIXCOR_PREC_TF32X3)))
+    return 3;  // 256 x 256 tiles per CTA pair
   if (g_umma_mc && epi == EPI_TOM && is_split_float(precision)) return 2;
   if (g_umma_ctas == 1) return 0;
   if (is_ozaki(precision)) return 1;  // long-K digit passes stream their operands from HBM / L2: half the B traffic pays
@@ -1814,7 +1816,7 @@ int bixcor_init_devices(int first_device, int n_gpus) {
   if (const char* v = getenv("BIXCOR_DMMA_VARIANT")) g_dmma_variant = atoi(v);
   if (const char* v = getenv("BIXCOR_UMMA_CTAS")) g_umma_ctas = (atoi(v) >= 1 && atoi(v) <= 3) ? atoi(v) : 2;
   if (const char* v = getenv("BIXCOR_UMMA_MC")) g_umma_mc = atoi(v) != 0;
-  if (const char* v = getenv("BIXCOR_UMMA_WIDE")) g_umma_wide = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_UMMA_WIDE")) g_umma_wide = std::max(0, std::min(2, atoi(v)));
   if (const char* v = getenv("BIXCOR_COPY_THREADS")) g_copy_threads = std::max(0, std::min(64, atoi(v)));
   if (const char* v = getenv("BIXCOR_STAGE_SLOT_MB")) g_stage_slot_bytes = (size_t)std::max(1, std::min(256, atoi(v))) << 20;
   if (const char* v = getenv("BIXCOR_STAGE_SLOTS")) g_stage_slots = std::max(2, std::min((int)HostStager::kMaxSlots, atoi(v)));
