@@ -942,3 +942,36 @@ def test_in_process_collectives(api, use_nccl, monkeypatch):
     finally:
         monkeypatch.delenv("BIXCOR_NCCL")
         api.init(1, 0)
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+def test_tom_from_exchanged_operand_planes(api, kind):
+    """The multi-rank TOM of the split-float kinds on ONE device: the hi / lo operand planes are built slab by slab (as
+    different ranks would), phase 3 runs from the planes alone (a_ij and the diagonal rebuilt from hi + lo) for row ranges
+    that tile the packed vector.  bixcor_dev_tom_split_planes / bixcor_dev_tom_rows_planes (bixcor.h)."""
+    import torch
+
+    from bixverse_b200 import _lib
+    from bixverse_b200 import distributed as D
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    prec = {"f16": _lib.PREC_F16X3, "tf32": _lib.PREC_TF32X3}[kind]
+    dev = torch.device("cuda", 0)
+    be = D.DeviceBackend(dev)
+    n, p = 90, 1000
+    x = synthetic_bulk(n, p, seed=61)
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
+    for signed in (True, False):
+        ref = o.dense_to_upper_triangle(o.tom_from_exp(x, signed, "v2", False, 2.0), True)
+        a_full = be.empty(p, p)
+        k = be.zeros(p)
+        rb = be.tom_plane_row_bytes(p, prec)
+        planes = be.empty_bytes(p * rb)
+        for c0, c1 in ((0, 384), (384, 1000)):  # two "ranks": affinity slab, its connectivity, its planes
+            be.affinity_cols(xd, n, p, False, signed, 2.0, prec, c0, c1, a_full)
+            be.tom_connectivity(a_full, p, signed, c0, c1, k)
+            be.tom_split_planes(a_full, p, prec, c0, c1, planes)
+        parts = [be.tom_rows_planes(planes, k, p, signed, _lib.TOM_V2, prec, r0, r1).cpu().numpy() for r0, r1 in ((0, 256), (256, 1000))]
+        assert _maxerr(np.concatenate(parts), ref) < TOL32
+        whole = be.tom_rows(a_full, k, p, signed, _lib.TOM_V2, prec, 0, p).cpu().numpy()  # the f64-matrix form of the same kind
+        assert _maxerr(np.concatenate(parts), whole) < 2e-6
