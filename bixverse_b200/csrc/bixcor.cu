@@ -222,8 +222,8 @@ static int g_dmma_variant = 1;  // dmma::Shape<CFG> (1 = 128x64 tiles, 2 CTAs/SM
 static int g_umma_mc = 0;       // tcgen05 long-K kernels in 2 x 2 multicast clusters (env BIXCOR_UMMA_MC = 1): verified, measured, NOT
                                 // faster (20k TOM f16 25.2 vs 23.2 ms, TF32 44.4 vs 42.1 ms, profiles/README_r02.md): L2 already merges the
                                 // requests of up to ~4 SMs for the same lines, so 2-way multicast saves no L2 -> SM bandwidth
-static int g_umma_wide = 1;     // TOM on 256 x 256 pair tiles (env BIXCOR_UMMA_WIDE): 0 never, 1 = the TF32 kind (20k TOM 42.1 -> 40.3 ms; its
-                                // plain form runs single CTAs), 2 = the f16 kind as well (measured slower: 25.2 vs 23.2 ms)
+static int g_umma_wide = 0;     // TOM on 256 x 256 pair tiles (env BIXCOR_UMMA_WIDE): 0 never (default), 1 = the TF32 kind (20k TOM: 40.3-41.9 ms
+                                // against 41.2-42.1, inside the run-to-run spread), 2 = the f16 kind as well (slower: 25.2 vs 23.2 ms)
 static int g_umma_ctas = 2;     // tcgen05 kernels: CTA pairs (cta_group::2) 1 = never, 2 = auto, 3 = always; env BIXCOR_UMMA_CTAS
 static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
