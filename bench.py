@@ -59,6 +59,10 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def par_ranks_hint(world):
+    return world  # every rank checks rows of its own slice
+
+
 def load_mma_peaks():
     """tcgen05 issue peaks per MMA kind measured on this pool's B200 by scripts/micro/mma_peak.cu (back-to-back MMAs on
     shared-memory-resident operands; profiles/mma_peaks_r02.json).  MEASURED_PEAKS.json only holds a cuBLAS bf16 figure."""
@@ -566,15 +570,101 @@ def run_ours(args):
         except Exception as ex:  # report, do not hide
             tom = {"error": str(ex)}
 
+    # ---- the other sharded configs as extra keys, so that every N the driver runs carries them with parity:
+    #      config 3 (differential correlation, 20 000 genes, 500 vs 500 samples; block rows per rank, no collective) and
+    #      config 5 (sparse all-pairs Gram, 1M cells x 5 000 genes; cell shards, NCCL all-reduce of Gram + column sums)
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        try:
+            from bixverse_b200.distributed import DeviceBackend, sharded_diffcor, sharded_sparse_gram_cor
+            from bixverse_b200.synthetic import synthetic_pair, synthetic_sparse_cells_fast
+
+            be_x = DeviceBackend(dev)
+            xa_h, xb_h = synthetic_pair(500, 500, p, seed=2025)
+            xa_d = torch.from_numpy(np.ascontiguousarray(xa_h.T)).to(dev)
+            xb_d = torch.from_numpy(np.ascontiguousarray(xb_h.T)).to(dev)
+            for sp_name, spear in (("pearson", False), ("spearman", True)):
+                sharded_diffcor(be_x, xa_d, 500, xb_d, 500, p, spear, _lib.PREC_AUTO)  # warm-up
+                barrier()
+                t0 = time.perf_counter()
+                res, (d0, _) = sharded_diffcor(be_x, xa_d, 500, xb_d, 500, p, spear, _lib.PREC_AUTO)
+                barrier()
+                t_dc = allmax(time.perf_counter() - t0)
+                oa = sm.SampledOracle(xa_h, spear, ranks=cb.rank_matrix_col(xa_h) if spear else None)
+                ob = sm.SampledOracle(xb_h, spear, ranks=cb.rank_matrix_col(xb_h) if spear else None)
+                er, ez = 0.0, 0.0
+                for i in parity_rows[:4] + parity_rows[-1:]:
+                    ra, rb_, z, _pv = sm.diffcor_rows(oa, ob, i)
+                    a0 = packed_offset(i, p, 1) - d0
+                    sl = slice(a0, a0 + (p - i - 1))
+                    er = max(er, float(np.abs(res["r_a"][sl].cpu().numpy() - ra).max()), float(np.abs(res["r_b"][sl].cpu().numpy() - rb_).max()))
+                    ez = max(ez, float(np.abs(res["z_score"][sl].cpu().numpy() - z).max()))
+                del res
+                extras[f"diffcor_{sp_name}"] = {"config": "config3: rs_differential_cor, 20000 genes, 500 vs 500 samples, HBM resident, BIXCOR_PREC_AUTO",
+                                               "ms": 1e3 * t_dc, "pairs_per_s": P_total / t_dc, "parity_max_err_r": allmax(er),
+                                               "parity_max_err_z": allmax(ez), "ranks_checked": par_ranks_hint(world)}
+            del xa_d, xb_d
+            cells, genes = 1000000, 5000
+            ip, ix, dd = synthetic_sparse_cells_fast(cells, genes, 2027)
+            c0, c1 = cells * rank // world, cells * (rank + 1) // world
+            lp = torch.from_numpy(ip[c0:c1 + 1] - ip[c0]).to(dev)
+            li = torch.from_numpy(ix[ip[c0]:ip[c1]]).to(dev)
+            ld_ = torch.from_numpy(dd[ip[c0]:ip[c1]]).to(dev)
+            sparse = {}
+            for sname in ("f16", "tf32"):
+                sharded_sparse_gram_cor(be_x, lp, li, ld_, c1 - c0, genes, PREC[sname])  # warm-up
+                barrier()
+                t0 = time.perf_counter()
+                so_ = sharded_sparse_gram_cor(be_x, lp, li, ld_, c1 - c0, genes, PREC[sname])
+                barrier()
+                t_sp = allmax(time.perf_counter() - t0)
+                serr = None
+                if rank == 0:  # every rank holds the same all-reduced result; rows of it against a sparse-algebra oracle
+                    s1 = np.bincount(ix, weights=dd.astype(np.float64), minlength=genes)
+                    s2 = np.bincount(ix, weights=dd.astype(np.float64) ** 2, minlength=genes)
+                    var = s2 - s1 * s1 / cells
+                    serr = 0.0
+                    for gi in (0, 128, 2500, 4998):
+                        hit = np.flatnonzero(ix == gi)
+                        cls = np.searchsorted(ip, hit, side="right") - 1  # the cells expressing gene i
+                        g = np.zeros(genes)
+                        for q, cl in zip(hit, cls):  # X'x_i = sum over those cells of value * the cell's row
+                            g[ix[ip[cl]:ip[cl + 1]]] += float(dd[q]) * dd[ip[cl]:ip[cl + 1]].astype(np.float64)
+                        r_ref = (g - s1[gi] * s1 / cells) / np.sqrt(var[gi] * var)
+                        a0 = packed_offset(gi, genes, 1)
+                        serr = max(serr, float(np.abs(so_[a0:a0 + genes - gi - 1].cpu().numpy() - r_ref[gi + 1:]).max()))
+                ck = float(so_[:100000].sum().item())
+                sparse[sname] = {"ms": 1e3 * t_sp, "parity_max_err_rank0": serr, "checksum_min_over_ranks": -allmax(-ck), "checksum_max_over_ranks": allmax(ck)}
+                del so_
+            sparse["config"] = ("config5: sparse all-pairs Gram, 1 000 000 cells x 5 000 genes (250 non-zeros per cell), CSR shard of each rank "
+                                "resident in HBM, partial Gram + column sums all-reduced over NCCL when N > 1, packed Pearson on every rank")
+            extras["sparse_gram"] = sparse
+            del lp, li, ld_, ip, ix, dd
+        except Exception as ex:  # report, do not hide
+            extras["error"] = repr(ex)
+
     # ---- parity summary: max over ranks, every rank checked its own rows
     par_err = allmax(max(parity.values()))
     par_ranks = int(allsum(1 if parity_rows else 0))
     tom_bad = bool(tom) and any(isinstance(v, dict) and v.get("parity_max_err", 0) > v.get("parity_tol", 1) for v in tom.values())
-    parity_line = {"max_err": par_err, "tol": 1e-12, "ok": bool(par_err <= 1e-12 and not tom_bad), "rows": parity_rows,
+    extras_bad = False
+    if extras:
+        for k_, v_ in extras.items():
+            if k_ == "error":
+                extras_bad = True
+            elif k_.startswith("diffcor"):
+                extras_bad |= not (v_["parity_max_err_r"] <= 1e-10 and v_["parity_max_err_z"] <= 1e-8)
+            elif k_ == "sparse_gram":
+                extras_bad |= any(isinstance(x_, dict) and x_["parity_max_err_rank0"] is not None and x_["parity_max_err_rank0"] > 1e-5
+                                  for x_ in v_.values())
+                extras_bad |= any(isinstance(x_, dict) and abs(x_["checksum_max_over_ranks"] - x_["checksum_min_over_ranks"]) > 1e-9
+                                  for x_ in v_.values())
+    parity_line = {"max_err": par_err, "tol": 1e-12, "ok": bool(par_err <= 1e-12 and not tom_bad and not extras_bad), "rows": parity_rows,
                    "rows_per_rank": len(parity_rows), "ranks_checked": par_ranks, "world": world,
                    "arms_rank0": parity,
                    "what": "|r|^6 rows of each rank's packed slice (HBM-resident arm and pageable e2e arm) vs oracle/sampled.py; "
-                           "TOM entries per precision under tom.<prec>.parity_max_err"}
+                           "TOM entries per precision under tom.<prec>.parity_max_err; config 3 / 5 under extras.*.parity_*"}
 
     # ---- CPU baseline leg (rank 0, N = 1 only): ONE pass of the full workload on the host cores (seconds)
     cpu_baseline = None
@@ -608,6 +698,7 @@ def run_ours(args):
             "parity": parity_line,
             "paths": paths,
             "tom": tom,
+            "extras": extras,
             "checksum": checksum,
         }
         print(json.dumps(line), flush=True)
@@ -630,6 +721,7 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="skip the other precision paths and the FP64 TOM")
     ap.add_argument("--no-tom", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 / config-5 extra keys")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
