@@ -485,30 +485,38 @@ def run_ours(args):
 
     e2e_steps = max(1, min(steps, 5))
 
+    import ctypes as C
+
     def time_e2e(step):
+        """seconds per step (max over ranks) and the bytes this rank's library moved over PCIe per step"""
         for _ in range(2):
             step()
         barrier()
+        lib.bixcor_transfer_counters(None, None, 1)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             step()
         torch.cuda.synchronize(dev)
-        return allmax(time.perf_counter() - t0) / e2e_steps
+        dt = allmax(time.perf_counter() - t0) / e2e_steps
+        up, down = C.c_int64(), C.c_int64()
+        lib.bixcor_transfer_counters(C.byref(up), C.byref(down), 1)
+        return dt, up.value // e2e_steps, down.value // e2e_steps
 
-    t_page = time_e2e(make_step(x_page, out_page))
+    t_page, up_page, down_page = time_e2e(make_step(x_page, out_page))
     parity["e2e_arm"] = cor_parity(lambda i: slice_row(out_page, i))
     checksum = float(out_page[: min(my_pairs, 1 << 20)].sum())
     x_pin, out_pin = x_page.pin_memory(), torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
-    t_pin = time_e2e(make_step(x_pin, out_pin))
+    t_pin, _up_pin, _down_pin = time_e2e(make_step(x_pin, out_pin))
     del x_pin, out_pin
 
     # PCIe floor of the step: this rank's packed rows over one GPU's measured device -> pinned-host bandwidth
     d2h_gbs = load_d2h_floor(world)
     e2e_floor = None
     if d2h_gbs:
-        floor_ms = allmax(8.0 * my_pairs / (d2h_gbs * 1e9) * 1e3)
+        floor_ms = allmax(float(down_page) / (d2h_gbs * 1e9) * 1e3)  # the bytes that actually cross PCIe (int32 transport: 4 per pair)
         e2e_floor = {"ms": floor_ms, "d2h_gbs_per_gpu": d2h_gbs, "frac_pageable": floor_ms / (1e3 * t_page), "frac_pinned": floor_ms / (1e3 * t_pin),
-                     "what": "largest per-rank result slice / measured cudaMemcpyAsync device->pinned bandwidth per GPU with this many GPUs "
+                     "what": "largest per-rank device->host byte count of a step (counted by the library; the exact Spearman Gram travels as int32, "
+                             "4 bytes per pair, and is completed to f64 by the host staging threads) / measured cudaMemcpyAsync device->pinned bandwidth per GPU with this many GPUs "
                              "copying at once (scripts/micro/d2h_floor.cu, profiles/d2h_floor_n8_r02.json: the host caps the aggregate at "
                              "~72 GB/s for 2-4 GPUs and ~92 GB/s for 8); the input upload overlaps it (duplex)"}
 
@@ -686,9 +694,9 @@ def run_ours(args):
                                     "slab, operand records all-gathered over NCCL" if world > 1 else "single GPU"),
                        "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
             "clocks": main["clocks"],
-            "e2e": {"value": P_total / t_page, "unit": UNIT, "ms_per_step": 1e3 * t_page, "h2d_bytes_per_step": h2d_bytes,
+            "e2e": {"value": P_total / t_page, "unit": UNIT, "ms_per_step": 1e3 * t_page, "h2d_bytes_per_step": int(max(h2d_bytes, up_page)),
                     "floor": e2e_floor,
-                    "d2h_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps, "host_buffers": "pageable",
+                    "d2h_bytes_per_step": int(down_page), "result_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps, "host_buffers": "pageable",
                     "pinned": {"value": P_total / t_pin, "ms_per_step": 1e3 * t_pin},
                     "note": e2e_note + ", precision = " + primary + "; value: pageable host buffers (what an R session owns), "
                             "pinned: the same call with page-locked buffers; bytes are rank 0's"},

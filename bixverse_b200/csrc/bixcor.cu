@@ -37,6 +37,7 @@ namespace bixcor {
 static std::mutex g_err_mu;
 static char g_err[1024] = "";  // fixed storage: reporting an error never allocates (it may be reporting std::bad_alloc)
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // bytes that crossed PCIe through the host entry points (bixcor_transfer_counters)
 static double g_fieller = 1.06;
 
 static int fail(int code, const char* fmt, ...) noexcept {
@@ -189,6 +190,7 @@ struct Ctx {
   Buffer flag;          // one int: device-side overflow / range flags read back by the host
   Buffer rank_scratch;  // sorted chunks / ranks of the n > 16384 Spearman path
   Buffer tile_sync;     // two words: arrival / bail-out counters of the long-K producer barrier (gram_umma.cuh)
+  PinnedBuffer inv_host;            // host copy of the per-gene 1/|d| (int32 transport of the exact Spearman Gram)
   HostStager* stager = nullptr;     // device -> pageable host (results)
   HostStager* stager_in = nullptr;  // pageable host -> device (inputs): its own small ring, so uploads never queue behind result slots
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
@@ -267,6 +269,7 @@ static void ctx_destroy(Ctx* c) {
   c->tile_sync.release();
   c->rank_scratch.release();
   stager_destroy(c);
+  c->inv_host.release();
   for (auto& kv : c->tile_cache)
     if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
   for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -878,6 +881,57 @@ static void stream_copy(char* dst, const char* src, size_t len) {
   if (len > 64 * n) memcpy(dst + 64 * n, src + 64 * n, len - 64 * n);
 }
 
+// int32 transport of the exact Spearman Gram (EpiParams::out_s32): the Gram kernel leaves the exact integers S_ij in
+// the packed layout (4 bytes per pair), half the bytes cross PCIe, and the copier threads - which touch every element
+// anyway - finish r_ij = S_ij / (|d_i| |d_j|) (and |r|^6) while they move the piece into the caller's pageable buffer.
+// The arithmetic is the device epilogue's, operation for operation (int -> double, times 1/|d_i|, times 1/|d_j|, then
+// sq = v v, sq sq sq): IEEE multiplications only, so host and device results are bit-identical.
+struct ExpandS32 {
+  const double* inv = nullptr;  // host copy of 1/|d| per gene
+  int64_t p = 0;
+  int shift = 1;
+  int pow6 = 0;
+};
+
+static inline int64_t packed_row_of(int64_t g, int64_t p, int shift) {  // largest i with packed_row_offset(i) <= g
+  const double a = shift ? 2.0 * (double)p - 1.0 : 2.0 * (double)p + 1.0;
+  int64_t i = (int64_t)((a - std::sqrt(std::max(0.0, a * a - 8.0 * (double)g))) / 2.0);
+  i = std::max<int64_t>(0, std::min<int64_t>(p - 1, i));
+  while (i > 0 && packed_row_offset(i, p, shift) > g) --i;
+  while (i + 1 < p && packed_row_offset(i + 1, p, shift) <= g) ++i;
+  return i;
+}
+
+// one run of a packed row (host_simd.cpp): AVX2 when the host has it, scalar otherwise - bit-identical forms
+extern "C" __attribute__((visibility("hidden"))) int bixcor_host_has_avx2(void);
+extern "C" __attribute__((visibility("hidden"))) void bixcor_expand_run_scalar(double* dst, const int32_t* src, int64_t n, double rf, const double* cf, int pow6);
+extern "C" __attribute__((visibility("hidden"))) void bixcor_expand_run_avx2(double* dst, const int32_t* src, int64_t n, double rf, const double* cf, int pow6);
+static inline void expand_run(double* dst, const int32_t* src, int64_t n, double rf, const double* cf, int pow6) {
+  static const bool have_avx2 = bixcor_host_has_avx2() != 0;
+  if (have_avx2) bixcor_expand_run_avx2(dst, src, n, rf, cf, pow6);
+  else bixcor_expand_run_scalar(dst, src, n, rf, cf, pow6);
+}
+
+// dst[t] for the packed elements [g0, g0 + count) from their integer Gram values
+static void expand_packed_s32(double* dst, const int32_t* src, int64_t count, int64_t g0, const ExpandS32& X) {
+  int64_t i = packed_row_of(g0, X.p, X.shift), pos = g0;
+  while (count > 0) {
+    const int64_t row_start = packed_row_offset(i, X.p, X.shift), row_len = X.p - i - X.shift;
+    if (pos >= row_start + row_len) {  // (rows without stored elements)
+      ++i;
+      continue;
+    }
+    const int64_t j0 = i + X.shift + (pos - row_start), nrun = std::min(count, row_start + row_len - pos);
+    expand_run(dst, src, nrun, X.inv[i], X.inv + j0, X.pow6);
+    dst += nrun;
+    src += nrun;
+    pos += nrun;
+    count -= nrun;
+    ++i;
+  }
+  _mm_sfence();
+}
+
 // Geometry measured on the B200 box (scripts/e2e_sweep.py, profiles/e2e_sweep_r02.json; 1.6 GB result, 16 host threads):
 // 8 x 32 MB slots / 4 MB pieces / blocking events 43.5 ms; 16 x 4 MB / 512 KB / spinning 35.7 ms (pinned buffers: 32 ms).
 // A 64 MB ring stays in the last-level cache the DMA engine writes into, so the copier threads read the data from
@@ -887,6 +941,7 @@ static int g_stage_slots = 16;                         // env BIXCOR_STAGE_SLOTS
 static size_t g_stage_piece = size_t(512) << 10;       // env BIXCOR_STAGE_PIECE_KB
 static int g_stage_nt = 1;                             // env BIXCOR_STAGE_NT: streaming stores into the caller's buffer
 static int g_stage_spin = 1;                           // env BIXCOR_STAGE_SPIN: copier threads spin on the DMA events instead of blocking
+static int g_s32_transport = 1;                        // env BIXCOR_S32_TRANSPORT: int32 transport of the exact Spearman Gram to pageable hosts
 
 struct HostStager {
   static constexpr int kMaxSlots = 64;
@@ -905,6 +960,8 @@ struct HostStager {
     const char* src;
     size_t len;
     bool wait_dma;  // D2H piece: wait for the slot's DMA first
+    const ExpandS32* ex = nullptr;  // D2H piece of an int32 Gram: src holds len / 4 integers, dst receives as many doubles
+    int64_t g0 = 0;                 // packed index of the piece's first element
   };
   int device = 0;
   Slot slots[kMaxSlots];
@@ -934,7 +991,8 @@ struct HostStager {
       cudaError_t e = cudaSuccess;
       if (t.wait_dma) e = cudaEventSynchronize(slots[t.slot].dma_done);
       if (e == cudaSuccess) {
-        if (t.wait_dma && g_stage_nt) stream_copy(t.dst, t.src, t.len);  // into the caller's (cold) buffer
+        if (t.ex) expand_packed_s32((double*)t.dst, (const int32_t*)t.src, (int64_t)(t.len / 4), t.g0, *t.ex);
+        else if (t.wait_dma && g_stage_nt) stream_copy(t.dst, t.src, t.len);  // into the caller's (cold) buffer
         else memcpy(t.dst, t.src, t.len);
       }
       {
@@ -961,7 +1019,8 @@ struct HostStager {
     return BIXCOR_OK;
   }
   // split [0, len) of a slot into pieces for the pool; host_ptr is the caller's memory
-  void post(int sidx, char* host_ptr, size_t len, bool to_host) {
+  // ex != nullptr (to_host only): the slot holds int32 Gram values, host_ptr is the double destination of its first one
+  void post(int sidx, char* host_ptr, size_t len, bool to_host, const ExpandS32* ex = nullptr, int64_t g0 = 0) {
     std::lock_guard<std::mutex> lk(m);
     for (size_t o = 0; o < len; o += kPiece) {
       const size_t l = std::min(kPiece, len - o);
@@ -969,7 +1028,9 @@ struct HostStager {
       t.slot = sidx;
       t.len = l;
       t.wait_dma = to_host;
-      t.dst = to_host ? host_ptr + o : (char*)slots[sidx].ptr + o;
+      t.ex = ex;
+      t.g0 = g0 + (int64_t)(o / 4);
+      t.dst = to_host ? host_ptr + (ex ? 2 * o : o) : (char*)slots[sidx].ptr + o;
       t.src = to_host ? (const char*)slots[sidx].ptr + o : host_ptr + o;
       queue.push_back(t);
       slots[sidx].pieces_left++;
@@ -1064,6 +1125,7 @@ static void stager_free(HostStager* st) {
 // the caller's memory into slot k + 1 while slot k is on the wire.
 static int h2d(Ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return BIXCOR_OK;
+  g_h2d_bytes += (int64_t)bytes;
   if (is_pinned(h_src)) {
     CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
     return BIXCOR_OK;
@@ -1104,6 +1166,7 @@ struct D2HPipe {
   explicit D2HPipe(Ctx* c_, const void* = nullptr) : c(c_) {}
   int push(void* h_dst, const void* d_src, size_t bytes, cudaEvent_t ready) {
     if (bytes == 0) return BIXCOR_OK;
+    g_d2h_bytes += (int64_t)bytes;
     if (ready) CU_TRY(cudaStreamWaitEvent(c->copy_out, ready, 0));
     if (is_pinned(h_dst)) {
       CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->copy_out));
@@ -1117,6 +1180,24 @@ struct D2HPipe {
       CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
       CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
       st->post(sidx, (char*)h_dst + o, len, true);
+    }
+    return BIXCOR_OK;
+  }
+  // int32 transport: `count` exact Gram integers at d_src become doubles at h_dst (pageable), g0 = packed index of the first
+  ExpandS32 ex;
+  int push_s32(double* h_dst, const int32_t* d_src, int64_t count, int64_t g0, cudaEvent_t ready) {
+    if (count <= 0) return BIXCOR_OK;
+    if (ready) CU_TRY(cudaStreamWaitEvent(c->copy_out, ready, 0));
+    if (!st) RC_TRY(stager_get(c, &st));
+    const size_t bytes = sizeof(int32_t) * (size_t)count;
+    g_d2h_bytes += (int64_t)bytes;
+    for (size_t o = 0; o < bytes; o += st->kSlotBytes) {
+      const size_t len = std::min(st->kSlotBytes, bytes - o);
+      int sidx = 0;
+      RC_TRY(st->acquire(&sidx));
+      CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
+      CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
+      st->post(sidx, (char*)(h_dst + o / 4), len, true, &ex, g0 + (int64_t)(o / 4));
     }
     return BIXCOR_OK;
   }
@@ -1170,6 +1251,21 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
     e.rbf_from_cor = rbf->from_cor;
     e.rbf_complement = rbf->complement;
   }
+  // exact Spearman Gram into a pageable buffer: int32 transport (see host_cor_upper_pipelined); the norms go over first
+  const bool s32 = pipe && g_s32_transport && op.precision == BIXCOR_PREC_I8EXACT && op.inv_norm && !e.rbf_mode && !e.keep_sign &&
+                   (e.beta == 1.0 || e.beta_int == 6) && !umma::kI8Wide;
+  if (s32) {
+    RC_TRY(c->inv_host.reserve(sizeof(double) * (size_t)p));
+    cudaEvent_t here = ctx_event(c);
+    CU_TRY(cudaEventRecord(here, c->compute));
+    CU_TRY(cudaStreamWaitEvent(c->copy_out, here, 0));
+    CU_TRY(cudaMemcpyAsync(c->inv_host.ptr, op.inv_norm, sizeof(double) * (size_t)p, cudaMemcpyDeviceToHost, c->copy_out));
+    e.out_s32 = 1;
+    pipe->ex.inv = (const double*)c->inv_host.ptr;
+    pipe->ex.p = p;
+    pipe->ex.shift = shift;
+    pipe->ex.pow6 = e.beta_int == 6;
+  }
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(op.precision, EPI_PACKED), &tl, swap_tiles(op.precision, e)));
   if (!pipe)  // results stay in HBM: one launch over all tiles (no per-band tail)
@@ -1183,7 +1279,8 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
     CU_TRY(cudaEventRecord(ev, c->compute));
     const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - e.out_base;
     const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - e.out_base;
-    RC_TRY(pipe->push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev));
+    if (s32) RC_TRY(pipe->push_s32(h_out + o0, (const int32_t*)d_out + o0, o1 - o0, e.out_base + o0, ev));
+    else RC_TRY(pipe->push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev));
   }
   return BIXCOR_OK;
 }
@@ -1241,6 +1338,17 @@ static int host_cor_upper_pipelined(Ctx* c, const double* h_x, int64_t n, int64_
     e.rbf_from_cor = rbf->from_cor;
     e.rbf_complement = rbf->complement;
   }
+  // exact Spearman Gram into a pageable buffer: int32 transport (half the PCIe bytes; the copier threads finish r)
+  const bool s32 = g_s32_transport && precision == BIXCOR_PREC_I8EXACT && !e.rbf_mode && !e.keep_sign &&
+                   (e.beta == 1.0 || e.beta_int == 6) && !umma::kI8Wide;  // (page-locked destinations too: 4 instead of 8 bytes per pair on the wire)
+  if (s32) {
+    RC_TRY(c->inv_host.reserve(sizeof(double) * (size_t)p));
+    e.out_s32 = 1;
+    pipe.ex.inv = (const double*)c->inv_host.ptr;
+    pipe.ex.p = p;
+    pipe.ex.shift = shift;
+    pipe.ex.pow6 = e.beta_int == 6;
+  }
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(precision, EPI_PACKED), &tl, swap_tiles(precision, e)));
   const int ngroups = (int)tl->group_tile.size() - 1;
@@ -1252,8 +1360,10 @@ static int host_cor_upper_pipelined(Ctx* c, const double* h_x, int64_t n, int64_
   for (auto& ev : up) ev = ctx_event(c);
   auto upload = [&](int g) -> int {  // enqueue the upload of band g's genes and record up[g] behind it
     const size_t off = (size_t)lo(g) * n, bytes = sizeof(double) * (size_t)(hi(g) - lo(g)) * n;
-    if (pinned_src) CU_TRY(cudaMemcpyAsync(d_x + off, h_x + off, bytes, cudaMemcpyHostToDevice, c->copy_in));
-    else RC_TRY(h2d(c, d_x + off, h_x + off, bytes, c->copy_in));  // staged through the inbound pinned ring (blocks this thread)
+    if (pinned_src) {
+      g_h2d_bytes += (int64_t)bytes;
+      CU_TRY(cudaMemcpyAsync(d_x + off, h_x + off, bytes, cudaMemcpyHostToDevice, c->copy_in));
+    } else RC_TRY(h2d(c, d_x + off, h_x + off, bytes, c->copy_in));  // staged through the inbound pinned ring (blocks this thread)
     CU_TRY(cudaEventRecord(up[(size_t)g], c->copy_in));
     return BIXCOR_OK;
   };
@@ -1297,12 +1407,20 @@ static int host_cor_upper_pipelined(Ctx* c, const double* h_x, int64_t n, int64_
       }
       CU_TRY(cudaStreamWaitEvent(c->compute, up[(size_t)g], 0));
       RC_TRY(build_operand(c, d_x, n, p, spearman, precision, lo(g), hi(g), c->op[0].ptr, (double*)c->aux[0].ptr));
+      if (s32) {  // the norms of the new genes go to the host ahead of the band's data (same stream: ordered before its DMAs)
+        cudaEvent_t cols = ctx_event(c);
+        CU_TRY(cudaEventRecord(cols, c->compute));
+        CU_TRY(cudaStreamWaitEvent(c->copy_out, cols, 0));
+        CU_TRY(cudaMemcpyAsync((double*)c->inv_host.ptr + lo(g), (const double*)c->aux[0].ptr + lo(g), sizeof(double) * (size_t)(hi(g) - lo(g)),
+                               cudaMemcpyDeviceToHost, c->copy_out));
+      }
       const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
       RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e, nullptr, tl->group_row[g], tl->group_row[g + 1]));
       cudaEvent_t ev = ctx_event(c);
       CU_TRY(cudaEventRecord(ev, c->compute));
       const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - o_base;
       const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - o_base;
+      if (s32) return pipe.push_s32(h_out + o0, (const int32_t*)d_out + o0, o1 - o0, o_base + o0, ev);
       return pipe.push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev);
     }();
   }
@@ -1784,6 +1902,17 @@ int bixcor_debug_inject(int what) {
 
 int64_t bixcor_launch_count(void) { return g_launches.load(); }
 
+/* bytes moved host -> device and device -> host by the host entry points since the last reset */
+int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset) {
+  if (h2d_bytes) *h2d_bytes = g_h2d_bytes.load();
+  if (d2h_bytes) *d2h_bytes = g_d2h_bytes.load();
+  if (reset) {
+    g_h2d_bytes = 0;
+    g_d2h_bytes = 0;
+  }
+  return BIXCOR_OK;
+}
+
 int bixcor_set_fieller(double c) {
   API_BEGIN
   if (!(c > 0.0)) return fail(BIXCOR_ERR_INVALID, "Fieller factor must be positive");
@@ -1823,6 +1952,7 @@ int bixcor_init_devices(int first_device, int n_gpus) {
   if (const char* v = getenv("BIXCOR_STAGE_PIECE_KB")) g_stage_piece = (size_t)std::max(64, std::min(65536, atoi(v))) << 10;
   if (const char* v = getenv("BIXCOR_STAGE_NT")) g_stage_nt = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_STAGE_SPIN")) g_stage_spin = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_S32_TRANSPORT")) g_s32_transport = atoi(v) != 0;
   for (int d = 0; d < n_gpus; ++d) {
     Ctx* c = nullptr;
     int rc = ctx_create(first_device + d, &c);

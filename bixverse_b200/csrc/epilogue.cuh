@@ -46,6 +46,9 @@ struct EpiParams {
   int tom_v2;
   int tom_signed;   // signed: |a_ij| in the denominators; unsigned: a_ij as passed (R/functions_stats.R:15-31)
   int tom_packed;
+  int out_s32;       // EPI_PACKED on the exact int8 kind: `out` is an int32 vector in the packed layout that receives the exact
+                     // integer Gram S_ij; the host staging threads turn it into r = S / (|d_i| |d_j|) (and the power) while they
+                     // move it into the caller's pageable buffer - half the bytes cross PCIe (csrc/bixcor.cu, expand_packed_s32)
   int upper_tiles;   // the launch's tile list holds upper-triangle tiles only (validity rule of the multicast super-tiles)
   // RBF affinity transform (crate core::math::rbf behind src/rust/src/base/r_rbf.rs and the
   // distance -> affinity step of rs_coremo_stability, src/rust/src/methods/r_coremo.rs:211-226)

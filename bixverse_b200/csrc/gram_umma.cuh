@@ -497,6 +497,36 @@ __device__ __forceinline__ void packed_interior(const uint32_t (&racc)[EPI_COLS]
   }
 }
 
+// Interior tile of the packed correlation in the int32 transport form (EpiParams::out_s32): the exact integer Gram values
+// of this warp's 32 rows x EPI_COLS columns go out as they are.  Lane = row while the accumulators sit in registers; each
+// 32 x 32 block is transposed through the warp's staging (16-byte units XOR-swizzled by the row, conflict free) so that a
+// store instruction writes one 128-byte run of one packed row.  wbase32: element (row_base, col_base) of the int32 vector;
+// a = p - row_base - shift - 1 (packed length step between consecutive rows).
+__device__ __forceinline__ void packed_interior_s32(const uint32_t (&racc)[EPI_COLS], double* stg, int lane, int* wbase32, int a) {
+  const uint32_t stg_s = smem_u32(stg);
+#pragma unroll
+  for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // phase A: my row's 32 values as eight 16-byte units
+      const uint32_t addr = stg_s + (uint32_t)lane * 128u + ((((uint32_t)u) ^ ((uint32_t)lane & 7u)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(racc[c0 + 4 * u]), "r"(racc[c0 + 4 * u + 1]),
+                   "r"(racc[c0 + 4 * u + 2]), "r"(racc[c0 + 4 * u + 3])
+                   : "memory");
+    }
+    __syncwarp();
+    uint32_t off = 0;  // element offset of row m relative to row 0 of the tile (running sum: a, a - 1, ...)
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {  // phase B: lane = column; one row per store instruction
+      uint32_t v;
+      const uint32_t addr = stg_s + (uint32_t)m * 128u + (((((uint32_t)lane >> 2) ^ ((uint32_t)m & 7u)) << 4) | (((uint32_t)lane & 3u) << 2));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+      wbase32[off + (uint32_t)(c0 + lane)] = (int)v;
+      off += (uint32_t)(a - m);
+    }
+    __syncwarp();
+  }
+}
+
 // Lean epilogue of one transposed (TILE_SWAPPED) interior tile for one epilogue warp: lane = output column, racc[q] =
 // output row rb + q.  rowv: 1/|d| of rows rb .. rb + EPI_COLS (KIND_I8), read as warp-uniform 16-byte loads; colf: the
 // lane's column factor; gp: the lane's element of row rb; a = packed length step ro(rb + 1) - ro(rb).
@@ -1133,6 +1163,32 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           const int a = pp - rb - shift - 1;  // ro(i + 1) - ro(i) = p - i - shift - 1
           if (pw_mode == 6) packed_swapped<KIND, true>(racc, colf, scale, scale != 1.0, rowv, gp, a);
           else packed_swapped<KIND, false>(racc, colf, scale, scale != 1.0, rowv, gp, a);
+          continue;
+        }
+        // ---- int32 transport of the exact Spearman Gram (host staging threads finish r and the power)
+        if (KIND == KIND_I8 && EPI == EPI_PACKED && E.out_s32) {
+          int* const out32 = reinterpret_cast<int*>(out);
+          if (interior) {
+            const EpiRow R0 = epi_row<EPI>(E, row_base);  // warp uniform
+            packed_interior_s32(racc, stg, lane, out32 + (R0.ro + col_base), pp - row_base - shift - 1);
+          } else {  // diagonal / ragged tiles (3 % of them): straight from TMEM, lane = row, predicated scalar stores
+            const bool row_ok = i < pp;
+            const int64_t ro_i = row_ok ? epi_row<EPI>(E, i).ro : 0;
+#pragma unroll
+            for (int c = 0; c < EPI_COLS; c += 16) {
+              uint32_t r0[16], r1[16], r2[16];
+              tmem_ld16(tacc_direct + o_hl + c, r1);
+              tmem_ld16(tacc_direct + o_hh + c, r0);
+              tmem_ld16(tacc_direct + o_ll + c, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int j = col_base + c + q;
+                if (row_ok && j < pp && j >= i + shift) out32[ro_i + j] = 256 * (int)r0[q] + 16 * (int)r1[q] + (int)r2[q];
+              }
+            }
+            release_direct();
+          }
           continue;
         }
         // ---- lean path: row-side factors are applied with lane = row, column-side factors and the power

@@ -99,6 +99,11 @@ void bixcor_shutdown(void);
 const char* bixcor_last_error(void);
 /* number of kernels launched by this library since init (bench `gpu_launches`) */
 int64_t bixcor_launch_count(void);
+/* Bytes the host entry points moved over PCIe since the last reset (bench `e2e.h2d_bytes_per_step` / `d2h_bytes_per_step`).
+ * The exact Spearman Gram (BIXCOR_PREC_I8EXACT / AUTO with beta = 1 or 6) travels as int32 - 4 bytes per pair instead of 8 -
+ * and the library's host staging threads finish r = S / (|d_i| |d_j|) while they move it into the caller's f64 buffer
+ * (bit-identical to the device epilogue; env BIXCOR_S32_TRANSPORT=0 sends the f64 values instead). */
+int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
 /* Fisher-z variance inflation for Spearman (default 1.06, Fieller); Pearson uses 1. */
 int bixcor_set_fieller(double c);
 /* Test hook of the exception barrier: the NEXT API call throws from inside its body

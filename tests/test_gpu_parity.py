@@ -975,3 +975,51 @@ def test_tom_from_exchanged_operand_planes(api, kind):
         assert _maxerr(np.concatenate(parts), ref) < TOL32
         whole = be.tom_rows(a_full, k, p, signed, _lib.TOM_V2, prec, 0, p).cpu().numpy()  # the f64-matrix form of the same kind
         assert _maxerr(np.concatenate(parts), whole) < 2e-6
+
+
+def test_int32_transport_of_the_exact_spearman_gram(api, monkeypatch):
+    """The exact Spearman Gram travels as int32 (4 bytes per pair) and the host staging threads finish r = S / (|d_i| |d_j|)
+    and the power: bit-identical to the f64 transport (BIXCOR_S32_TRANSPORT=0), for pageable and page-locked buffers, on
+    interior, diagonal and ragged tiles, NaN / constant columns included; the library's byte counters show the halved D2H."""
+    import ctypes as C
+
+    import torch
+
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    lib = _lib.load()
+    n, p = 120, 1300
+    x = synthetic_bulk(n, p, seed=91, tie_heavy=True)
+    x[:, 7] = 3.0        # zero variance -> NaN row / column
+    x[5, 40] = np.nan    # NaN column
+    P_ = p * (p - 1) // 2
+    res = {}
+    try:
+        for mode in ("1", "0"):
+            monkeypatch.setenv("BIXCOR_S32_TRANSPORT", mode)
+            lib.bixcor_shutdown()
+            api.init(1, 0)
+            for beta in (1.0, 6.0):
+                lib.bixcor_transfer_counters(None, None, 1)
+                res[(mode, beta, "pageable")] = api.rs_cor_upper_triangle(x, True, True, beta=beta)
+                down = C.c_int64()
+                lib.bixcor_transfer_counters(None, C.byref(down), 1)
+                assert down.value == (4 if mode == "1" else 8) * P_
+                xp = torch.from_numpy(np.ascontiguousarray(x.T)).pin_memory()
+                out = torch.empty(P_, dtype=torch.float64).pin_memory()
+                _lib.check(lib.bixcor_cor_upper(xp.data_ptr(), n, p, 1, 1, beta, _lib.PREC_AUTO, out.data_ptr()))
+                res[(mode, beta, "pinned")] = out.numpy().copy()
+            res[(mode, 2.0, "pageable")] = api.rs_cor_upper_triangle(x, True, True, beta=2.0)  # other powers: f64 transport
+    finally:
+        monkeypatch.delenv("BIXCOR_S32_TRANSPORT")
+        lib.bixcor_shutdown()
+        api.init(1, 0)
+    for beta in (1.0, 6.0):
+        ref = res[("0", beta, "pageable")]
+        for key in (("1", beta, "pageable"), ("1", beta, "pinned"), ("0", beta, "pinned")):
+            assert np.array_equal(res[key], ref, equal_nan=True), key
+        oref = o.soft_threshold(o.cor_upper_triangle(x, True, True), beta)
+        ok = ~np.isnan(oref)
+        assert np.isnan(ref[~ok]).all() and np.abs(ref[ok] - oref[ok]).max() < 1e-12
+    assert np.array_equal(res[("1", 2.0, "pageable")], res[("0", 2.0, "pageable")], equal_nan=True)
