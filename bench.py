@@ -510,14 +510,38 @@ def run_ours(args):
     del x_pin, out_pin
 
     # PCIe floor of the step: this rank's packed rows over one GPU's measured device -> pinned-host bandwidth
-    d2h_gbs = load_d2h_floor(world)
+    d2h_gbs_file = load_d2h_floor(world)
+    # ... and measured live on THIS box: every rank copies its own D2H byte count device -> pinned host at the same time
+    # (plain cudaMemcpyAsync, CUDA events); boxes of the pool differ (57 GB/s on one, ~40 on another), so the floor
+    # the e2e figures are compared with is the box's own
+    d2h_gbs_live = None
+    try:
+        nbytes = int(max(down_page, 1 << 20))
+        src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        d2h_gbs_live = 3 * nbytes / (allmax(ev0.elapsed_time(ev1)) * 1e-3) / 1e9
+        del src, dst
+    except Exception:
+        d2h_gbs_live = None
+    d2h_gbs = d2h_gbs_live or d2h_gbs_file
     e2e_floor = None
     if d2h_gbs:
         floor_ms = allmax(float(down_page) / (d2h_gbs * 1e9) * 1e3)  # the bytes that actually cross PCIe (int32 transport: 4 per pair)
-        e2e_floor = {"ms": floor_ms, "d2h_gbs_per_gpu": d2h_gbs, "frac_pageable": floor_ms / (1e3 * t_page), "frac_pinned": floor_ms / (1e3 * t_pin),
+        e2e_floor = {"ms": floor_ms, "d2h_gbs_per_gpu": d2h_gbs, "d2h_gbs_source": "live" if d2h_gbs_live else "profiles/d2h_floor_*_r02.json",
+                     "d2h_gbs_per_gpu_file": d2h_gbs_file, "frac_pageable": floor_ms / (1e3 * t_page), "frac_pinned": floor_ms / (1e3 * t_pin),
                      "what": "largest per-rank device->host byte count of a step (counted by the library; the exact Spearman Gram travels as int32, "
-                             "4 bytes per pair, and is completed to f64 by the host staging threads) / measured cudaMemcpyAsync device->pinned bandwidth per GPU with this many GPUs "
-                             "copying at once (scripts/micro/d2h_floor.cu, profiles/d2h_floor_n8_r02.json: the host caps the aggregate at "
+                             "4 bytes per pair, and is completed to f64 by the host staging threads) / cudaMemcpyAsync device->pinned bandwidth per GPU with this many GPUs "
+                             "copying at once, measured live on this box right after the e2e arms (d2h_gbs_source; the committed figures of "
+                             "scripts/micro/d2h_floor.cu are kept as d2h_gbs_per_gpu_file: the host caps the aggregate at "
                              "~72 GB/s for 2-4 GPUs and ~92 GB/s for 8); the input upload overlaps it (duplex)"}
 
     # ---- TOM wall time (config 4) as an extra metric: HBM resident (all N) and host -> host through the C ABI (N = 1)

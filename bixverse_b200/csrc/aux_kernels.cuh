@@ -266,6 +266,15 @@ mirror_upper_kernel(double* __restrict__ dense, int64_t p) {  // dense[j][i] = d
   }
 }
 
+// binary32 transport of a <= 1e-5-class result (3xTF32 / 3xF16 kinds): finished values are rounded to float before they
+// cross PCIe (half the bytes) and the host staging threads widen them into the caller's f64 buffer.  A streaming pass
+// over one band: 8 bytes read + 4 written per element, grid-stride, fully coalesced.
+__global__ void __launch_bounds__(256)
+narrow_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) dst[t] = (float)src[t];
+}
+
 // Reciprocal best hits on a correlation block (rs_rbh_cor, src/rust/src/methods/r_rbh.rs:187-272).  sim is the
 // column-major p x q matrix of cor2; one warp per line (a row i: stride p over j; a column j: contiguous) finds the
 // k-th largest |r| of the line (with multiplicity; NaN never counts; fewer than k values: -inf).

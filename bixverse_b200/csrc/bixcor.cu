@@ -184,6 +184,7 @@ struct Ctx {
   Buffer ozg;           // Ozaki FP64 accumulation matrix (p x p)
   Buffer out;           // packed / dense result
   Buffer out2;          // affinity matrix for TOM
+  Buffer out32;         // binary32 copy of finished bands (f32 transport of the <= 1e-5-class results)
   Buffer vec;           // k, diag, colsum
   Buffer panel;         // sparse dense panel
   Buffer sparse_in;     // staged CSR
@@ -262,6 +263,7 @@ static void ctx_destroy(Ctx* c) {
   c->ozg.release();
   c->out.release();
   c->out2.release();
+  c->out32.release();
   c->vec.release();
   c->panel.release();
   c->sparse_in.release();
@@ -906,6 +908,15 @@ static inline int64_t packed_row_of(int64_t g, int64_t p, int shift) {  // large
 extern "C" __attribute__((visibility("hidden"))) int bixcor_host_has_avx2(void);
 extern "C" __attribute__((visibility("hidden"))) void bixcor_expand_run_scalar(double* dst, const int32_t* src, int64_t n, double rf, const double* cf, int pow6);
 extern "C" __attribute__((visibility("hidden"))) void bixcor_expand_run_avx2(double* dst, const int32_t* src, int64_t n, double rf, const double* cf, int pow6);
+extern "C" __attribute__((visibility("hidden"))) void bixcor_widen_f32_scalar(double* dst, const float* src, int64_t n);
+extern "C" __attribute__((visibility("hidden"))) void bixcor_widen_f32_avx2(double* dst, const float* src, int64_t n);
+// binary32 transport of the <= 1e-5-class results: the copier threads widen float -> double into the caller's buffer
+static inline void widen_f32(double* dst, const float* src, int64_t n) {
+  static const bool have_avx2 = bixcor_host_has_avx2() != 0;
+  if (have_avx2) bixcor_widen_f32_avx2(dst, src, n);
+  else bixcor_widen_f32_scalar(dst, src, n);
+  _mm_sfence();
+}
 static inline void expand_run(double* dst, const int32_t* src, int64_t n, double rf, const double* cf, int pow6) {
   static const bool have_avx2 = bixcor_host_has_avx2() != 0;
   if (have_avx2) bixcor_expand_run_avx2(dst, src, n, rf, cf, pow6);
@@ -942,6 +953,7 @@ static size_t g_stage_piece = size_t(512) << 10;       // env BIXCOR_STAGE_PIECE
 static int g_stage_nt = 1;                             // env BIXCOR_STAGE_NT: streaming stores into the caller's buffer
 static int g_stage_spin = 1;                           // env BIXCOR_STAGE_SPIN: copier threads spin on the DMA events instead of blocking
 static int g_s32_transport = 1;                        // env BIXCOR_S32_TRANSPORT: int32 transport of the exact Spearman Gram to pageable hosts
+static int g_f32_transport = 1;                        // env BIXCOR_F32_TRANSPORT: binary32 transport of the split-float (<= 1e-5 class) correlation / TOM results
 
 struct HostStager {
   static constexpr int kMaxSlots = 64;
@@ -962,6 +974,7 @@ struct HostStager {
     bool wait_dma;  // D2H piece: wait for the slot's DMA first
     const ExpandS32* ex = nullptr;  // D2H piece of an int32 Gram: src holds len / 4 integers, dst receives as many doubles
     int64_t g0 = 0;                 // packed index of the piece's first element
+    bool widen = false;             // D2H piece of a binary32 result: src holds len / 4 floats, dst receives as many doubles
   };
   int device = 0;
   Slot slots[kMaxSlots];
@@ -992,6 +1005,7 @@ struct HostStager {
       if (t.wait_dma) e = cudaEventSynchronize(slots[t.slot].dma_done);
       if (e == cudaSuccess) {
         if (t.ex) expand_packed_s32((double*)t.dst, (const int32_t*)t.src, (int64_t)(t.len / 4), t.g0, *t.ex);
+        else if (t.widen) widen_f32((double*)t.dst, (const float*)t.src, (int64_t)(t.len / 4));
         else if (t.wait_dma && g_stage_nt) stream_copy(t.dst, t.src, t.len);  // into the caller's (cold) buffer
         else memcpy(t.dst, t.src, t.len);
       }
@@ -1020,7 +1034,8 @@ struct HostStager {
   }
   // split [0, len) of a slot into pieces for the pool; host_ptr is the caller's memory
   // ex != nullptr (to_host only): the slot holds int32 Gram values, host_ptr is the double destination of its first one
-  void post(int sidx, char* host_ptr, size_t len, bool to_host, const ExpandS32* ex = nullptr, int64_t g0 = 0) {
+  // widen (to_host only): the slot holds floats, host_ptr is the double destination of its first one
+  void post(int sidx, char* host_ptr, size_t len, bool to_host, const ExpandS32* ex = nullptr, int64_t g0 = 0, bool widen = false) {
     std::lock_guard<std::mutex> lk(m);
     for (size_t o = 0; o < len; o += kPiece) {
       const size_t l = std::min(kPiece, len - o);
@@ -1029,8 +1044,9 @@ struct HostStager {
       t.len = l;
       t.wait_dma = to_host;
       t.ex = ex;
+      t.widen = widen;
       t.g0 = g0 + (int64_t)(o / 4);
-      t.dst = to_host ? host_ptr + (ex ? 2 * o : o) : (char*)slots[sidx].ptr + o;
+      t.dst = to_host ? host_ptr + ((ex || widen) ? 2 * o : o) : (char*)slots[sidx].ptr + o;
       t.src = to_host ? (const char*)slots[sidx].ptr + o : host_ptr + o;
       queue.push_back(t);
       slots[sidx].pieces_left++;
@@ -1201,12 +1217,53 @@ struct D2HPipe {
     }
     return BIXCOR_OK;
   }
+  // binary32 transport: `count` floats at d_src become doubles at h_dst (pageable or page-locked: the widening needs a host pass)
+  int push_f32(double* h_dst, const float* d_src, int64_t count, cudaEvent_t ready) {
+    if (count <= 0) return BIXCOR_OK;
+    if (ready) CU_TRY(cudaStreamWaitEvent(c->copy_out, ready, 0));
+    if (!st) RC_TRY(stager_get(c, &st));
+    const size_t bytes = sizeof(float) * (size_t)count;
+    g_d2h_bytes += (int64_t)bytes;
+    for (size_t o = 0; o < bytes; o += st->kSlotBytes) {
+      const size_t len = std::min(st->kSlotBytes, bytes - o);
+      int sidx = 0;
+      RC_TRY(st->acquire(&sidx));
+      CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
+      CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
+      st->post(sidx, (char*)(h_dst + o / 4), len, true, nullptr, 0, true);
+    }
+    return BIXCOR_OK;
+  }
   int finish() {
     if (st) RC_TRY(st->drain());
     CU_TRY(cudaStreamSynchronize(c->copy_out));
     return BIXCOR_OK;
   }
 };
+
+// Binary32 transport of a finished band of a split-float (<= 1e-5 class: 3xTF32 / 3xF16) result.  Those values carry ~22
+// significant bits, so rounding them to float before they cross PCIe changes nothing inside their accuracy class
+// (relative 6e-8) and halves the device-to-host bytes - the floor of every host -> host call.  The band [d_src, +count)
+// of the f64 result is narrowed into the same element range of c->out32 on the compute stream (a streaming pass of 12
+// bytes per element: ~0.4 ms for the 1.6 GB of a 20 000-gene result) and the copier threads widen it into h_dst.
+// d_base: element 0 of the result buffer the band belongs to (out32 mirrors its indexing).
+static int push_band_f32(Ctx* c, D2HPipe* pipe, double* h_dst, const double* d_base, const double* d_src, int64_t count) {
+  if (count <= 0) return BIXCOR_OK;
+  float* d_n = (float*)c->out32.ptr + (d_src - d_base);
+  {
+    Timed tm(c, T_OTHER);
+    const unsigned blocks = (unsigned)std::min<int64_t>((count + 1023) / 1024, (int64_t)c->sm_count * 16);
+    narrow_f64_f32_kernel<<<blocks, 256, 0, c->compute>>>(d_src, d_n, count);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  cudaEvent_t ev = ctx_event(c);
+  CU_TRY(cudaEventRecord(ev, c->compute));
+  return pipe->push_f32(h_dst, d_n, count, ev);
+}
+static bool f32_transport(int precision, const EpiParams& e) {
+  return g_f32_transport && is_split_float(precision) && e.scale == 1.0;  // (correlations / affinities / TOM: magnitudes <= 1)
+}
 
 // ----------------------------------------------------------------------------
 // device-level building blocks (all pointers device, ctx current)
@@ -1266,6 +1323,8 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
     pipe->ex.shift = shift;
     pipe->ex.pow6 = e.beta_int == 6;
   }
+  const bool f32t = pipe && f32_transport(op.precision, e);
+  if (f32t) RC_TRY(c->out32.reserve(sizeof(float) * (size_t)std::max<int64_t>(1, packed_row_offset(row_end, p, shift) - e.out_base)));
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(op.precision, EPI_PACKED), &tl, swap_tiles(op.precision, e)));
   if (!pipe)  // results stay in HBM: one launch over all tiles (no per-band tail)
@@ -1275,10 +1334,14 @@ static int dev_cor_upper_rows_op(Ctx* c, const Operand& op, int64_t p, int shift
     const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
     RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e, nullptr, tl->group_row[g],
                        tl->group_row[g + 1]));
-    cudaEvent_t ev = ctx_event(c);
-    CU_TRY(cudaEventRecord(ev, c->compute));
     const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - e.out_base;
     const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - e.out_base;
+    if (f32t) {
+      RC_TRY(push_band_f32(c, pipe, h_out + o0, d_out, d_out + o0, o1 - o0));
+      continue;
+    }
+    cudaEvent_t ev = ctx_event(c);
+    CU_TRY(cudaEventRecord(ev, c->compute));
     if (s32) RC_TRY(pipe->push_s32(h_out + o0, (const int32_t*)d_out + o0, o1 - o0, e.out_base + o0, ev));
     else RC_TRY(pipe->push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev));
   }
@@ -1349,6 +1412,8 @@ static int host_cor_upper_pipelined(Ctx* c, const double* h_x, int64_t n, int64_
     pipe.ex.shift = shift;
     pipe.ex.pow6 = e.beta_int == 6;
   }
+  const bool f32t = f32_transport(precision, e);  // split-float kinds: binary32 on the wire
+  if (f32t) RC_TRY(c->out32.reserve(sizeof(float) * (size_t)std::max<int64_t>(1, o_end - o_base)));
   TileList* tl;
   RC_TRY(get_tiles(c, p, row_begin, row_end, 1, 8, umma_pairs(precision, EPI_PACKED), &tl, swap_tiles(precision, e)));
   const int ngroups = (int)tl->group_tile.size() - 1;
@@ -1416,10 +1481,11 @@ static int host_cor_upper_pipelined(Ctx* c, const double* h_x, int64_t n, int64_
       }
       const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
       RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_PACKED, e, nullptr, tl->group_row[g], tl->group_row[g + 1]));
-      cudaEvent_t ev = ctx_event(c);
-      CU_TRY(cudaEventRecord(ev, c->compute));
       const int64_t o0 = packed_row_offset(tl->group_row[g], p, shift) - o_base;
       const int64_t o1 = packed_row_offset(tl->group_row[g + 1], p, shift) - o_base;
+      if (f32t) return push_band_f32(c, &pipe, h_out + o0, d_out, d_out + o0, o1 - o0);
+      cudaEvent_t ev = ctx_event(c);
+      CU_TRY(cudaEventRecord(ev, c->compute));
       if (s32) return pipe.push_s32(h_out + o0, (const int32_t*)d_out + o0, o1 - o0, o_base + o0, ev);
       return pipe.push(h_out + o0, d_out + o0, sizeof(double) * (size_t)(o1 - o0), ev);
     }();
@@ -1647,12 +1713,24 @@ static int dev_tom_rows(Ctx* c, const double* d_a, const double* d_k, int64_t p,
   e.upper_tiles = upper;
   // non-packed strip mode writes into out + 0 with absolute (i*p + j) addressing
   if (!pipe) return launch_gram(c, op, nullptr, p, tl->d_tiles, tl->ntiles, EPI_TOM, e, nullptr, row_begin, row_end);
+  const bool f32t = f32_transport(precision, e);  // split-float kinds: binary32 on the wire (out32 mirrors d_out's indexing)
+  if (f32t)
+    RC_TRY(c->out32.reserve(sizeof(float) * (size_t)(packed ? std::max<int64_t>(1, packed_row_offset(row_end, p, 1) - e.out_base) : row_end * p)));
   const int ngroups = (int)tl->group_tile.size() - 1;
   for (int t = 0; t < ngroups; ++t) {
     const int g = t;
     const int t0 = tl->group_tile[g], t1 = tl->group_tile[g + 1];
     const int64_t g0 = tl->group_row[g], g1 = tl->group_row[g + 1];
     RC_TRY(launch_gram(c, op, nullptr, p, tl->d_tiles + t0, t1 - t0, EPI_TOM, e, nullptr, g0, g1));
+    if (f32t) {
+      if (packed) {
+        const int64_t o0 = packed_row_offset(g0, p, 1) - e.out_base, o1 = packed_row_offset(g1, p, 1) - e.out_base;
+        RC_TRY(push_band_f32(c, pipe, h_out + o0, d_out, d_out + o0, o1 - o0));
+      } else {
+        RC_TRY(push_band_f32(c, pipe, h_out + g0 * p, d_out, d_out + g0 * p, (g1 - g0) * p));
+      }
+      continue;
+    }
     cudaEvent_t ev = ctx_event(c);
     CU_TRY(cudaEventRecord(ev, c->compute));
     if (packed) {
@@ -1948,11 +2026,13 @@ int bixcor_init_devices(int first_device, int n_gpus) {
   if (const char* v = getenv("BIXCOR_UMMA_WIDE")) g_umma_wide = std::max(0, std::min(2, atoi(v)));
   if (const char* v = getenv("BIXCOR_COPY_THREADS")) g_copy_threads = std::max(0, std::min(64, atoi(v)));
   if (const char* v = getenv("BIXCOR_STAGE_SLOT_MB")) g_stage_slot_bytes = (size_t)std::max(1, std::min(256, atoi(v))) << 20;
+  if (const char* v = getenv("BIXCOR_STAGE_SLOT_KB")) g_stage_slot_bytes = (size_t)std::max(64, std::min(262144, atoi(v))) << 10;
   if (const char* v = getenv("BIXCOR_STAGE_SLOTS")) g_stage_slots = std::max(2, std::min((int)HostStager::kMaxSlots, atoi(v)));
   if (const char* v = getenv("BIXCOR_STAGE_PIECE_KB")) g_stage_piece = (size_t)std::max(64, std::min(65536, atoi(v))) << 10;
   if (const char* v = getenv("BIXCOR_STAGE_NT")) g_stage_nt = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_STAGE_SPIN")) g_stage_spin = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_S32_TRANSPORT")) g_s32_transport = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_F32_TRANSPORT")) g_f32_transport = atoi(v) != 0;
   for (int d = 0; d < n_gpus; ++d) {
     Ctx* c = nullptr;
     int rc = ctx_create(first_device + d, &c);

@@ -45,3 +45,27 @@ extern "C" __attribute__((visibility("hidden"), target("avx2"))) void bixcor_exp
   }
   for (; t < n; ++t) expand_one(dst + t, src[t], rf, cf[t], pow6);
 }
+
+// binary32 transport of the <= 1e-5-class results (bixcor.cu, D2HPipe::push_f32): dst[t] = (double)src[t], streaming stores
+extern "C" __attribute__((visibility("hidden"))) void bixcor_widen_f32_scalar(double* dst, const float* src, int64_t n) {
+  for (int64_t t = 0; t < n; ++t) {
+    const double v = (double)src[t];
+    long long bits;
+    memcpy(&bits, &v, sizeof bits);
+    _mm_stream_si64(reinterpret_cast<long long*>(dst + t), bits);
+  }
+}
+
+extern "C" __attribute__((visibility("hidden"), target("avx2"))) void bixcor_widen_f32_avx2(double* dst, const float* src, int64_t n) {
+  int64_t t = 0;
+  while (t < n && ((uintptr_t)(dst + t) & 31)) {
+    bixcor_widen_f32_scalar(dst + t, src + t, 1);
+    ++t;
+  }
+  for (; t + 8 <= n; t += 8) {
+    const __m256 f = _mm256_loadu_ps(src + t);
+    _mm256_stream_pd(dst + t, _mm256_cvtps_pd(_mm256_castps256_ps128(f)));
+    _mm256_stream_pd(dst + t + 4, _mm256_cvtps_pd(_mm256_extractf128_ps(f, 1)));
+  }
+  if (t < n) bixcor_widen_f32_scalar(dst + t, src + t, n - t);
+}

@@ -102,7 +102,11 @@ int64_t bixcor_launch_count(void);
 /* Bytes the host entry points moved over PCIe since the last reset (bench `e2e.h2d_bytes_per_step` / `d2h_bytes_per_step`).
  * The exact Spearman Gram (BIXCOR_PREC_I8EXACT / AUTO with beta = 1 or 6) travels as int32 - 4 bytes per pair instead of 8 -
  * and the library's host staging threads finish r = S / (|d_i| |d_j|) while they move it into the caller's f64 buffer
- * (bit-identical to the device epilogue; env BIXCOR_S32_TRANSPORT=0 sends the f64 values instead). */
+ * (bit-identical to the device epilogue; env BIXCOR_S32_TRANSPORT=0 sends the f64 values instead).
+ * Results of the <= 1e-5-class precisions (BIXCOR_PREC_TF32X3 / BIXCOR_PREC_F16X3: packed correlation, TOM) carry ~22
+ * significant bits; their finished bands are rounded to binary32 on the device, travel as 4 bytes per value and are widened
+ * into the caller's f64 buffer by the same threads (relative 6e-8, far inside the class; env BIXCOR_F32_TRANSPORT=0 sends
+ * f64).  The FP64-class precisions (F64, OZAKI) and every differential-correlation output always travel as f64. */
 int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
 /* Fisher-z variance inflation for Spearman (default 1.06, Fieller); Pearson uses 1. */
 int bixcor_set_fieller(double c);

@@ -40,6 +40,21 @@ def main():
                 settings.append({"BIXCOR_STAGE_SLOT_MB": slot_mb, "BIXCOR_STAGE_SLOTS": slots, "BIXCOR_STAGE_PIECE_KB": piece, "BIXCOR_STAGE_SPIN": spin})
         settings.append({"BIXCOR_STAGE_SLOT_MB": 8, "BIXCOR_STAGE_SLOTS": 8, "BIXCOR_STAGE_PIECE_KB": 1024, "BIXCOR_COPY_THREADS": 10})
         settings.append({"BIXCOR_STAGE_SLOT_MB": 8, "BIXCOR_STAGE_SLOTS": 8, "BIXCOR_STAGE_PIECE_KB": 1024, "BIXCOR_COPY_THREADS": 16})
+    elif "--round2b" in sys.argv:  # int32 transport (4 bytes per pair on the wire, the copier threads expand to f64)
+        settings.append({"BIXCOR_S32_TRANSPORT": 0})
+        for thr in (6, 8, 10, 12, 16):
+            settings.append({"BIXCOR_COPY_THREADS": thr})
+        for slot_mb, slots, piece in ((2, 32, 256), (2, 16, 256), (4, 16, 256), (4, 16, 1024), (8, 8, 512), (1, 32, 256), (4, 32, 512)):
+            settings.append({"BIXCOR_STAGE_SLOT_MB": slot_mb, "BIXCOR_STAGE_SLOTS": slots, "BIXCOR_STAGE_PIECE_KB": piece})
+        settings.append({"BIXCOR_STAGE_SPIN": 0})
+    elif "--round2c" in sys.argv:  # small rings (the ring should stay in the cache level the DMA writes into)
+        for slot_kb, slots, piece in ((1024, 32, 256), (1024, 16, 256), (1024, 64, 256), (512, 32, 256), (512, 64, 256), (512, 32, 128), (1024, 32, 128),
+                                      (256, 64, 128), (2048, 8, 256)):
+            settings.append({"BIXCOR_STAGE_SLOT_KB": slot_kb, "BIXCOR_STAGE_SLOTS": slots, "BIXCOR_STAGE_PIECE_KB": piece})
+        settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_COPY_THREADS": 16})
+        settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_COPY_THREADS": 10})
+        settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_STAGE_SPIN": 0})
+        settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_S32_TRANSPORT": 0})
     else:
         for slot_mb, slots in ((32, 8), (16, 8), (8, 8), (4, 8), (2, 16), (8, 16), (64, 4)):
             settings.append({"BIXCOR_STAGE_SLOT_MB": slot_mb, "BIXCOR_STAGE_SLOTS": slots})

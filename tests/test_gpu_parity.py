@@ -1023,3 +1023,65 @@ def test_int32_transport_of_the_exact_spearman_gram(api, monkeypatch):
         ok = ~np.isnan(oref)
         assert np.isnan(ref[~ok]).all() and np.abs(ref[ok] - oref[ok]).max() < 1e-12
     assert np.array_equal(res[("1", 2.0, "pageable")], res[("0", 2.0, "pageable")], equal_nan=True)
+
+
+def test_binary32_transport_of_the_split_float_results(api, monkeypatch):
+    """Results of the <= 1e-5-class kinds (3xTF32 / 3xF16) are rounded to binary32 before they cross PCIe and widened by the
+    host staging threads: against the f64 transport (BIXCOR_F32_TRANSPORT=0) every value agrees to float rounding (relative
+    2^-24), the byte counters show the halved D2H, and both stay inside the 1e-5 class against the oracle - packed
+    correlation (with and without a power, ragged last block), packed and dense TOM, pageable and page-locked buffers."""
+    import ctypes as C
+
+    import torch
+
+    from bixverse_b200 import _lib
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    lib = _lib.load()
+    n, p = 150, 1100
+    x = synthetic_bulk(n, p, seed=57)
+    P_ = p * (p - 1) // 2
+    res = {}
+    try:
+        for mode in ("1", "0"):
+            monkeypatch.setenv("BIXCOR_F32_TRANSPORT", mode)
+            lib.bixcor_shutdown()
+            api.init(1, 0)
+            for prec in (_lib.PREC_TF32X3, _lib.PREC_F16X3):
+                for beta in (1.0, 6.0):
+                    lib.bixcor_transfer_counters(None, None, 1)
+                    res[(mode, prec, "cor", beta)] = api.rs_cor_upper_triangle(x, False, True, beta=beta, precision=prec)
+                    down = C.c_int64()
+                    lib.bixcor_transfer_counters(None, C.byref(down), 1)
+                    assert down.value == (4 if mode == "1" else 8) * P_
+                xp = torch.from_numpy(np.ascontiguousarray(x.T)).pin_memory()
+                out = torch.empty(P_, dtype=torch.float64).pin_memory()
+                _lib.check(lib.bixcor_cor_upper(xp.data_ptr(), n, p, 0, 1, 1.0, prec, out.data_ptr()))
+                res[(mode, prec, "cor_pinned", 1.0)] = out.numpy().copy()
+                res[(mode, prec, "tom_packed", 6.0)] = api.calculate_tom_from_exp(x, True, "v1", "pearson", beta=6.0, precision=prec, packed=True)
+                res[(mode, prec, "tom_dense", 6.0)] = api.calculate_tom_from_exp(x, True, "v1", "pearson", beta=6.0, precision=prec)
+            # the FP64-class kinds never use it
+            lib.bixcor_transfer_counters(None, None, 1)
+            api.rs_cor_upper_triangle(x, False, True, precision=_lib.PREC_F64)
+            down = C.c_int64()
+            lib.bixcor_transfer_counters(None, C.byref(down), 1)
+            assert down.value == 8 * P_
+    finally:
+        monkeypatch.delenv("BIXCOR_F32_TRANSPORT")
+        lib.bixcor_shutdown()
+        api.init(1, 0)
+    cor_ref = o.cor_upper_triangle(x, False, True)
+    tom_ref = o.tom_from_exp(x, True, "v1", beta=6.0)
+    iu = np.triu_indices(p, 1)  # row-major upper triangle == the packed order (shift = 1)
+    for key, narrow in res.items():
+        if key[0] != "1":
+            continue
+        wide = res[("0",) + key[1:]]
+        assert narrow.shape == wide.shape
+        assert np.array_equal(narrow, wide.astype(np.float32).astype(np.float64)), key  # exactly the float rounding of the f64 result
+        if key[2].startswith("cor"):
+            assert np.abs(narrow - o.soft_threshold(cor_ref, key[3])).max() < TOL32, key
+        elif key[2] == "tom_dense":
+            assert np.abs(narrow - tom_ref).max() < TOL32, key
+        else:
+            assert np.abs(narrow - tom_ref[iu]).max() < TOL32, key
