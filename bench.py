@@ -321,7 +321,8 @@ def run_ours(args):
             fp64_peak["v"] = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         return fp64_peak["v"]
 
-    def measure_dev(pname, k_steps):
+    def measure_dev(pname, k_steps, exchange=None):
+        exchange = exchange or args.exchange
         prec = PREC[pname]
         xprec = _lib.PREC_I8EXACT if pname == "auto" else prec  # the operand-exchange API takes the resolved precision
         _lib.check(lib.bixcor_dev_set_stream(stream.cuda_stream, 1))
@@ -330,6 +331,15 @@ def run_ours(args):
         if world == 1:
             def step():
                 _lib.check(lib.bixcor_dev_cor_upper_rows(x_dev.data_ptr(), n, p, 1, 1, BETA, prec, r0, r1, out_dev.data_ptr()))
+        elif exchange == "peer" and pname != "ozaki":
+            # ONE library call per step: the rank kernel stores the records of this rank's gene slab into every peer's operand
+            # buffer over NVLink (P2P-mapped memory), a flag barrier in the same block replaces the all-gather, then the Gram
+            from bixverse_b200.distributed import DeviceBackend, xchg_setup
+
+            xchg_setup(DeviceBackend(dev), n, p, xprec)
+
+            def step():
+                _lib.check(lib.bixcor_dev_cor_upper_rows_xchg(x_dev.data_ptr(), n, p, 1, 1, BETA, r0, r1, out_dev.data_ptr()))
         else:
             # gene-sharded rank transform, operand records all-gathered over NCCL, then this rank's block rows
             from bixverse_b200.distributed import gene_slab
@@ -442,6 +452,13 @@ def run_ours(args):
     primary = args.precision
     main = measure_dev(primary, steps)
     parity = {"value_arm": cor_parity(lambda i: slice_row(out_dev, i))}
+    exchange_cmp = None
+    if world > 1 and args.exchange == "peer":  # the same step through NCCL (build, all-gather, norm kernel, Gram) for comparison
+        alt = measure_dev(primary, steps, exchange="nccl")
+        exchange_cmp = {"peer_ms_per_step": main["ms_per_step"], "nccl_ms_per_step": alt["ms_per_step"],
+                        "nccl_parity_max_err": cor_parity(lambda i: slice_row(out_dev, i)),
+                        "what": "HBM-resident step: rank kernel with peer stores + flag barrier + Gram in one library call, against "
+                                "bixcor_dev_build_operand / all_gather_into_tensor (NCCL) / bixcor_dev_operand_inv_norm / Gram"}
     paths = {}
     if not args.no_alt:
         for alt in ("f64", "i8", "tf32", "f16", "ozaki"):
@@ -480,8 +497,18 @@ def run_ours(args):
         e2e_note = ("bixverse_b200.distributed.host_sharded_cor_upper (C ABI underneath): gene-slab H2D, operand all-gather "
                     "over NCCL, band-pipelined D2H")
 
-        def make_step(xh, oh):
-            return lambda: host_sharded_cor_upper(be_e2e, xh, n, p, True, oh, 1, BETA, e2e_xprec, workspace=ws_e2e)
+        if args.exchange == "peer":
+            from bixverse_b200.distributed import host_sharded_cor_upper_xchg, xchg_setup
+
+            xchg_setup(be_e2e, n, p, e2e_xprec)
+            e2e_note = ("bixverse_b200.distributed.host_sharded_cor_upper_xchg (C ABI underneath): gene-slab H2D, rank kernel storing its "
+                        "records into every peer's operand buffer over NVLink + flag barrier, band-pipelined D2H")
+
+            def make_step(xh, oh):
+                return lambda: host_sharded_cor_upper_xchg(be_e2e, xh, n, p, True, oh, 1, BETA)
+        else:
+            def make_step(xh, oh):
+                return lambda: host_sharded_cor_upper(be_e2e, xh, n, p, True, oh, 1, BETA, e2e_xprec, workspace=ws_e2e)
 
     e2e_steps = max(1, min(steps, 5))
 
@@ -714,8 +741,10 @@ def run_ours(args):
             "dtype": main["dtype"], "data": "synthetic",
             "config": {"workload": "config2: Spearman 20000 genes x 1000 samples + |r|^6, packed upper triangle (shift=1)",
                        "n_samples": n, "n_genes": p, "beta": BETA, "seed": SEED, "precision": primary, "path": main["path"],
-                       "sharding": (f"{world} contiguous block-row ranges balanced by pair count; rank transform sharded by gene "
-                                    "slab, operand records all-gathered over NCCL" if world > 1 else "single GPU"),
+                       "sharding": ((f"{world} contiguous block-row ranges balanced by pair count; rank transform sharded by gene slab, "
+                                     + ("every rank's kernel stores its operand records into all peers' buffers over NVLink (P2P-mapped "
+                                        "memory, flag barrier; no collective library in the data path)" if args.exchange == "peer"
+                                        else "operand records all-gathered over NCCL")) if world > 1 else "single GPU"),
                        "l2": "no flush needed: per-step input 160 MB + output 1.6 GB/N exceed the 126 MB L2"},
             "clocks": main["clocks"],
             "e2e": {"value": P_total / t_page, "unit": UNIT, "ms_per_step": 1e3 * t_page, "h2d_bytes_per_step": int(max(h2d_bytes, up_page)),
@@ -729,6 +758,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "parity": parity_line,
             "paths": paths,
+            "exchange": exchange_cmp,
             "tom": tom,
             "extras": extras,
             "checksum": checksum,
@@ -750,6 +780,9 @@ def main():
                     choices=["auto", "f64", "i8", "tf32", "f16", "ozaki"],
                     help="Gram path of the headline number: auto = BIXCOR_PREC_AUTO, what the drop-in patch passes (exact-integer "
                          "Spearman here), f64 = FP64 DMMA, tf32 / f16 = 3-way split fast paths, ozaki = FP64-class on int8")
+    ap.add_argument("--exchange", default=os.environ.get("BIXCOR_BENCH_EXCHANGE", "peer"), choices=["peer", "nccl"],
+                    help="N > 1: operand exchange by peer stores from inside the rank kernel + flag barrier (bixcor_xchg_*), or "
+                         "build / NCCL all-gather / norm kernel")
     ap.add_argument("--no-alt", action="store_true", help="skip the other precision paths and the FP64 TOM")
     ap.add_argument("--no-tom", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

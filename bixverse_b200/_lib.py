@@ -18,6 +18,7 @@ PREC_F64, PREC_TF32X3, PREC_I8EXACT, PREC_OZAKI, PREC_OZAKI4, PREC_F16X3 = 0, 1,
 PREC_AUTO = -1  # what the drop-in patch passes: exact-integer Gram for Spearman with n <= 1860, FP64 otherwise (env BIXCOR_PRECISION)
 TOM_V1, TOM_V2 = 1, 2
 RBF_GAUSSIAN, RBF_BUMP, RBF_INVERSE_QUADRATIC = 1, 2, 3
+XCHG_HANDLE_BYTES = 64
 
 i64, i32, f64 = C.c_int64, C.c_int, C.c_double
 ptr = C.c_void_p
@@ -68,6 +69,12 @@ SIGNATURES = {
     "bixcor_dev_operand_inv_norm": (i32, [ptr, i64, i64, i32, ptr]),
     "bixcor_dev_cor_upper_rows_op": (i32, [ptr, ptr, i64, i64, i32, i32, f64, i64, i64, ptr]),
     "bixcor_dev_cor_upper_rows_op_to_host": (i32, [ptr, ptr, i64, i64, i32, i32, f64, i64, i64, ptr]),
+    "bixcor_xchg_create": (i32, [i64, i64, i32, i32, i32, ptr]),
+    "bixcor_xchg_open": (i32, [ptr]),
+    "bixcor_xchg_release_peers": (i32, []),
+    "bixcor_xchg_destroy": (i32, []),
+    "bixcor_dev_cor_upper_rows_xchg": (i32, [ptr, i64, i64, i32, i32, f64, i64, i64, ptr]),
+    "bixcor_dev_cor_upper_rows_xchg_to_host": (i32, [ptr, i64, i64, i32, i32, f64, i64, i64, ptr]),
     "bixcor_dev_cor_dense": (i32, [ptr, i64, i64, i32, i32, ptr]),
     "bixcor_dev_diffcor_rows": (i32, [ptr, i64, ptr, i64, i64, i32, i32, i64, i64, ptr, ptr, ptr, ptr]),
     "bixcor_dev_affinity_cols": (i32, [ptr, i64, i64, i32, i32, f64, i32, i64, i64, ptr]),

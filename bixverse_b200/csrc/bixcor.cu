@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cmath>
 #include <cstdarg>
@@ -172,6 +173,22 @@ enum TimeCat : int { T_COLS = 0, T_GEMM = 1, T_OTHER = 2 };
 
 struct HostStager;  // pinned ring + copier threads for pageable host buffers (below)
 
+// Fused operand exchange between the GPUs of one box, one process per GPU (bixcor_xchg_*): one cudaMalloc block per rank,
+// exported with cudaIpc and mapped by every peer -
+//   [operand buffer 0][operand buffer 1][1/|d| buffer 0][1/|d| buffer 1][flags: world x 64 bytes]
+// The column kernel of rank r stores the records of ITS gene slab into buffer (epoch & 1) of every rank; a one-CTA barrier
+// kernel (system-scope flags in the same block) tells every peer that the slab is complete and waits for theirs; the Gram
+// kernel then reads the local buffer.  Two buffers: a peer may already be writing step t + 1 while this rank's Gram of step t
+// is still reading; it cannot reach step t + 2 before this rank has signalled step t + 1, i.e. finished the Gram of step t.
+struct Xchg {
+  int world = 0, rank = 0, precision = 0, opened = 0;
+  int64_t n = 0, p = 0, slab = 0;
+  size_t rb = 0, op_off[2] = {0, 0}, inv_off[2] = {0, 0}, flag_off = 0, total = 0;
+  char* local = nullptr;
+  char* peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // peer[rank] == local
+  uint32_t epoch = 0;
+};
+
 struct Ctx {
   int device = -1;
   int sm_count = 148;
@@ -192,6 +209,7 @@ struct Ctx {
   Buffer rank_scratch;  // sorted chunks / ranks of the n > 16384 Spearman path
   Buffer tile_sync;     // two words: arrival / bail-out counters of the long-K producer barrier (gram_umma.cuh)
   PinnedBuffer inv_host;            // host copy of the per-gene 1/|d| (int32 transport of the exact Spearman Gram)
+  Xchg xchg;                        // fused operand exchange over P2P-mapped peer memory (one process per GPU)
   HostStager* stager = nullptr;     // device -> pageable host (results)
   HostStager* stager_in = nullptr;  // pageable host -> device (inputs): its own small ring, so uploads never queue behind result slots
   std::map<std::tuple<int64_t, int64_t, int64_t, int, int>, TileList> tile_cache;
@@ -232,6 +250,7 @@ static bool g_timing = false;   // bixcor_timing_enable
 static bool g_async = false;    // device-pointer entry points return without synchronising
 
 static void stager_destroy(Ctx* c);
+static void xchg_free(Ctx* c);
 
 static int ctx_create(int device, Ctx** out) {
   Ctx* c = new Ctx();
@@ -271,6 +290,7 @@ static void ctx_destroy(Ctx* c) {
   c->tile_sync.release();
   c->rank_scratch.release();
   stager_destroy(c);
+  xchg_free(c);
   c->inv_host.release();
   for (auto& kv : c->tile_cache)
     if (kv.second.d_tiles) cudaFree(kv.second.d_tiles);
@@ -952,19 +972,49 @@ static int g_stage_slots = 16;                         // env BIXCOR_STAGE_SLOTS
 static size_t g_stage_piece = size_t(512) << 10;       // env BIXCOR_STAGE_PIECE_KB
 static int g_stage_nt = 1;                             // env BIXCOR_STAGE_NT: streaming stores into the caller's buffer
 static int g_stage_spin = 1;                           // env BIXCOR_STAGE_SPIN: copier threads spin on the DMA events instead of blocking
+// The int32 transport has its own ring geometry: its copier threads write two bytes for every byte they read, the DMA of a
+// slot is short (1 MB: 19 us) against its expansion, and a finer grain keeps all threads busy (scripts/e2e_sweep.py --round2b /
+// --round2c, profiles/e2e_sweep_s32_r02.json: 32 x 1 MB / 256 KB pieces 22-23 ms, 16 x 4 MB / 512 KB 29-31 ms at config 2;
+// below 1 MB the cudaMemcpyAsync + event-record calls of the launching thread dominate).  The same pinned slots are used.
+static size_t g_s32_slot_bytes = size_t(1) << 20;      // env BIXCOR_S32_SLOT_KB
+static int g_s32_slots = 32;                           // env BIXCOR_S32_SLOTS
+static size_t g_s32_piece = size_t(256) << 10;         // env BIXCOR_S32_PIECE_KB
 static int g_s32_transport = 1;                        // env BIXCOR_S32_TRANSPORT: int32 transport of the exact Spearman Gram to pageable hosts
 static int g_f32_transport = 1;                        // env BIXCOR_F32_TRANSPORT: binary32 transport of the split-float (<= 1e-5 class) correlation / TOM results
+
+// How a copier thread learns that the DMA of a slot has landed: by default it waits on the slot's CUDA event.  The
+// alternative kept here (env BIXCOR_STAGE_SEQ=1) keeps the copier threads out of the driver altogether: the copy stream writes
+// a sequence number into one pinned host word after every device-to-host DMA (cuStreamWriteValue32, stream ordered) and the
+// threads spin on that word with plain loads.  Measured at config 2 (scripts/e2e_sweep.py --round2e, three alternating
+// repetitions, profiles/e2e_sweep_s32_r02.json): 26.8-28.9 ms against 23.3-23.9 ms with events - a stream memory operation
+// between two copies costs the copy engine more than an event record does - so it stays off.
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static int g_stage_seq = 0;
+static StreamWriteValue32Fn stream_write_value_fn() {
+  static StreamWriteValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    fn = (StreamWriteValue32Fn)p;
+  else cudaGetLastError();
+  return fn;
+}
 
 struct HostStager {
   static constexpr int kMaxSlots = 64;
   size_t kSlotBytes = g_stage_slot_bytes;
   size_t kPiece = g_stage_piece;
-  int kSlots = g_stage_slots;
+  int kSlots = g_stage_slots;   // slots allocated
+  int kCycle = g_stage_slots;   // slots a transfer cycles through unless it says otherwise (the int32 transport: g_s32_slots)
   struct Slot {
     void* ptr = nullptr;
     cudaEvent_t dma_done = nullptr;  // D2H: data has landed in the slot; H2D: the DMA has read the slot
     int pieces_left = 0;             // host copies still running on this slot
     bool dma_pending = false;        // H2D: dma_done must be waited for before the slot is refilled
+    uint32_t seq = 0;                // D2H: sequence number the copy stream writes to *seq_host once this slot's DMA has landed
   };
   struct Task {
     int slot;
@@ -975,7 +1025,12 @@ struct HostStager {
     const ExpandS32* ex = nullptr;  // D2H piece of an int32 Gram: src holds len / 4 integers, dst receives as many doubles
     int64_t g0 = 0;                 // packed index of the piece's first element
     bool widen = false;             // D2H piece of a binary32 result: src holds len / 4 floats, dst receives as many doubles
+    uint32_t wait_seq = 0;          // D2H piece, sequence mode: the slot has landed once *seq_host has reached this number
   };
+  volatile uint32_t* seq_host = nullptr;  // pinned word written by the copy stream after every D2H DMA (nullptr: event mode)
+  CUdeviceptr seq_dev = 0;
+  uint32_t seq_issued = 0;
+  StreamWriteValue32Fn write_fn = nullptr;
   int device = 0;
   Slot slots[kMaxSlots];
   int next_slot = 0;
@@ -1002,7 +1057,18 @@ struct HostStager {
         }
       }
       cudaError_t e = cudaSuccess;
-      if (t.wait_dma) e = cudaEventSynchronize(slots[t.slot].dma_done);
+      if (t.wait_dma && seq_host) {
+        uint64_t spins = 0;
+        const auto t_start = std::chrono::steady_clock::now();
+        while ((int32_t)(*seq_host - t.wait_seq) < 0) {
+          _mm_pause();
+          if ((++spins & 0xFFFFFu) == 0 && std::chrono::steady_clock::now() - t_start > std::chrono::seconds(120)) {
+            e = cudaErrorLaunchTimeout;  // (the stream died: the launching thread reports its error, nobody hangs)
+            break;
+          }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+      } else if (t.wait_dma) e = cudaEventSynchronize(slots[t.slot].dma_done);
       if (e == cudaSuccess) {
         if (t.ex) expand_packed_s32((double*)t.dst, (const int32_t*)t.src, (int64_t)(t.len / 4), t.g0, *t.ex);
         else if (t.widen) widen_f32((double*)t.dst, (const float*)t.src, (int64_t)(t.len / 4));
@@ -1016,10 +1082,24 @@ struct HostStager {
       }
     }
   }
+  // the calling thread, right after it enqueued the D2H DMA into slot sidx on stream s: how the copier threads will see it land
+  int mark_landing(int sidx, cudaStream_t s) {
+    if (seq_host) {
+      ++seq_issued;
+      const CUresult r = write_fn((CUstream)s, seq_dev, seq_issued, 0);
+      if (r != CUDA_SUCCESS) return fail(BIXCOR_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult %d", (int)r);
+      slots[sidx].seq = seq_issued;
+      return BIXCOR_OK;
+    }
+    CU_TRY(cudaEventRecord(slots[sidx].dma_done, s));
+    return BIXCOR_OK;
+  }
   // the calling thread: next slot of the ring, once its previous host copies (and H2D DMA) are done
-  int acquire(int* out_slot) {
-    const int sidx = next_slot;
-    next_slot = (next_slot + 1) % kSlots;
+  // nslots: how many of the ring's slots this transfer cycles through (0 = all of them)
+  int acquire(int* out_slot, int nslots = 0) {
+    if (nslots <= 0 || nslots > kSlots) nslots = kCycle;
+    const int sidx = next_slot % nslots;
+    next_slot = (sidx + 1) % nslots;
     {
       std::unique_lock<std::mutex> lk(m);
       cv_slot.wait(lk, [&] { return slots[sidx].pieces_left == 0; });
@@ -1035,16 +1115,19 @@ struct HostStager {
   // split [0, len) of a slot into pieces for the pool; host_ptr is the caller's memory
   // ex != nullptr (to_host only): the slot holds int32 Gram values, host_ptr is the double destination of its first one
   // widen (to_host only): the slot holds floats, host_ptr is the double destination of its first one
-  void post(int sidx, char* host_ptr, size_t len, bool to_host, const ExpandS32* ex = nullptr, int64_t g0 = 0, bool widen = false) {
+  void post(int sidx, char* host_ptr, size_t len, bool to_host, const ExpandS32* ex = nullptr, int64_t g0 = 0, bool widen = false,
+            size_t piece = 0) {
+    if (piece == 0) piece = kPiece;
     std::lock_guard<std::mutex> lk(m);
-    for (size_t o = 0; o < len; o += kPiece) {
-      const size_t l = std::min(kPiece, len - o);
+    for (size_t o = 0; o < len; o += piece) {
+      const size_t l = std::min(piece, len - o);
       Task t;
       t.slot = sidx;
       t.len = l;
       t.wait_dma = to_host;
       t.ex = ex;
       t.widen = widen;
+      t.wait_seq = slots[sidx].seq;
       t.g0 = g0 + (int64_t)(o / 4);
       t.dst = to_host ? host_ptr + ((ex || widen) ? 2 * o : o) : (char*)slots[sidx].ptr + o;
       t.src = to_host ? (const char*)slots[sidx].ptr + o : host_ptr + o;
@@ -1077,7 +1160,9 @@ static int stager_get(Ctx* c, HostStager** out, bool inbound = false) {
   }
   HostStager* st = new HostStager();
   st->device = c->device;
-  if (inbound) st->kSlots = std::min(st->kSlots, 6);
+  if (inbound) st->kSlots = st->kCycle = std::min(st->kSlots, 6);
+  else st->kSlots = std::max(st->kSlots, std::min((int)HostStager::kMaxSlots, g_s32_slots));  // (the int32 transport cycles through more, smaller slots)
+  st->kSlotBytes = std::max(st->kSlotBytes, inbound ? size_t(0) : g_s32_slot_bytes);
   for (int si = 0; si < st->kSlots; ++si) {
     auto& sl = st->slots[si];
     if (cudaMallocHost(&sl.ptr, st->kSlotBytes) != cudaSuccess ||
@@ -1085,6 +1170,19 @@ static int stager_get(Ctx* c, HostStager** out, bool inbound = false) {
       cudaGetLastError();
       stager_free(st);
       return fail(BIXCOR_ERR_OOM, "cannot allocate the pinned staging ring (%d x %zu MB)", g_stage_slots, g_stage_slot_bytes >> 20);
+    }
+  }
+  if (!inbound && g_stage_seq && g_stage_spin && stream_write_value_fn()) {
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (cudaHostAlloc(&hp, 64, cudaHostAllocDefault) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+      memset(hp, 0, 64);
+      st->seq_host = (volatile uint32_t*)hp;
+      st->seq_dev = (CUdeviceptr)(uintptr_t)dp;
+      st->write_fn = stream_write_value_fn();
+    } else {
+      cudaGetLastError();
+      if (hp) cudaFreeHost(hp);
     }
   }
   unsigned hw = std::thread::hardware_concurrency();
@@ -1134,6 +1232,7 @@ static void stager_free(HostStager* st) {
     if (sl.dma_done) cudaEventDestroy(sl.dma_done);
     if (sl.ptr) cudaFreeHost(sl.ptr);
   }
+  if (st->seq_host) cudaFreeHost((void*)st->seq_host);
   delete st;
 }
 
@@ -1194,7 +1293,7 @@ struct D2HPipe {
       int sidx = 0;
       RC_TRY(st->acquire(&sidx));
       CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
-      CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
+      RC_TRY(st->mark_landing(sidx, c->copy_out));
       st->post(sidx, (char*)h_dst + o, len, true);
     }
     return BIXCOR_OK;
@@ -1207,13 +1306,14 @@ struct D2HPipe {
     if (!st) RC_TRY(stager_get(c, &st));
     const size_t bytes = sizeof(int32_t) * (size_t)count;
     g_d2h_bytes += (int64_t)bytes;
-    for (size_t o = 0; o < bytes; o += st->kSlotBytes) {
-      const size_t len = std::min(st->kSlotBytes, bytes - o);
+    const size_t slot_bytes = std::min(st->kSlotBytes, g_s32_slot_bytes);
+    for (size_t o = 0; o < bytes; o += slot_bytes) {
+      const size_t len = std::min(slot_bytes, bytes - o);
       int sidx = 0;
-      RC_TRY(st->acquire(&sidx));
+      RC_TRY(st->acquire(&sidx, g_s32_slots));
       CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
-      CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
-      st->post(sidx, (char*)(h_dst + o / 4), len, true, &ex, g0 + (int64_t)(o / 4));
+      RC_TRY(st->mark_landing(sidx, c->copy_out));
+      st->post(sidx, (char*)(h_dst + o / 4), len, true, &ex, g0 + (int64_t)(o / 4), false, g_s32_piece);
     }
     return BIXCOR_OK;
   }
@@ -1229,7 +1329,7 @@ struct D2HPipe {
       int sidx = 0;
       RC_TRY(st->acquire(&sidx));
       CU_TRY(cudaMemcpyAsync(st->slots[sidx].ptr, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, c->copy_out));
-      CU_TRY(cudaEventRecord(st->slots[sidx].dma_done, c->copy_out));
+      RC_TRY(st->mark_landing(sidx, c->copy_out));
       st->post(sidx, (char*)(h_dst + o / 4), len, true, nullptr, 0, true);
     }
     return BIXCOR_OK;
@@ -1360,6 +1460,109 @@ static int dev_cor_upper_rows(Ctx* c, const double* d_x, int64_t n, int64_t p, i
 }
 
 static int finish(Ctx* c);
+
+// ---- fused operand exchange over peer memory (struct Xchg) -------------------------------------------------------------
+// unmap the peers' blocks (this rank's own block stays: peers may still have it mapped)
+static void xchg_release_peers(Ctx* c) {
+  Xchg& X = c->xchg;
+  if (!X.local) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < X.world; ++r)
+    if (r != X.rank && X.peer[r]) {
+      cudaIpcCloseMemHandle(X.peer[r]);
+      X.peer[r] = nullptr;
+    }
+  X.opened = 0;
+  cudaGetLastError();
+}
+static void xchg_free(Ctx* c) {
+  Xchg& X = c->xchg;
+  if (!X.local) return;
+  xchg_release_peers(c);
+  cudaFree(X.local);
+  cudaGetLastError();
+  X = Xchg();
+}
+
+// Column kernel of this rank's gene slab with the records stored into every rank's buffer `b`, then the cross-GPU barrier.
+// d_x: the full n x p matrix (x_is_slab == 0) or only the slab's genes (x_is_slab != 0).
+static int xchg_build_and_sync(Ctx* c, const double* d_x, int x_is_slab, int spearman) {
+  Xchg& X = c->xchg;
+  const uint32_t epoch = ++X.epoch;
+  const int b = (int)(epoch & 1u);
+  const int64_t n = X.n, p = X.p;
+  const int64_t g0 = std::min(p, (int64_t)X.rank * X.slab), g1 = std::min(p, g0 + X.slab);
+  const int K = round_up((int)n, k_padding(X.precision));
+  if (g1 > g0) {
+    const double* xs = x_is_slab ? d_x : d_x + g0 * n;
+    const bool fused = spearman && X.precision == BIXCOR_PREC_I8EXACT && n <= 1024;
+    if (fused) {  // rank kernel with peer stores: the NVLink traffic overlaps the sort
+      ColumnOut co;
+      memset(&co, 0, sizeof co);
+      co.kpad = K;
+      co.mode = COL_I8;
+      co.i8 = (int8_t*)(X.local + X.op_off[b]) + g0 * 2 * K;
+      co.ld8 = 2 * K;
+      co.plane8 = K;
+      co.inv_norm = (double*)(X.local + X.inv_off[b]) + g0;
+      PeerOut po;
+      memset(&po, 0, sizeof po);
+      for (int r = 0; r < X.world; ++r) {
+        if (r == X.rank) continue;
+        po.i8[po.n] = (int8_t*)(X.peer[r] + X.op_off[b]) + g0 * 2 * K;
+        po.inv_norm[po.n] = (double*)(X.peer[r] + X.inv_off[b]) + g0;
+        po.n++;
+      }
+      int e = 1;
+      while (32 * e < n) e <<= 1;
+      const int64_t cnt = g1 - g0;
+      const unsigned grid = (unsigned)((cnt + 3) / 4);
+      Timed tm(c, T_COLS);
+      switch (e) {
+        case 1: rank_columns_warp_peers_kernel<1><<<grid, 128, 0, c->compute>>>(xs, n, (int)n, cnt, co, po); break;
+        case 2: rank_columns_warp_peers_kernel<2><<<grid, 128, 0, c->compute>>>(xs, n, (int)n, cnt, co, po); break;
+        case 4: rank_columns_warp_peers_kernel<4><<<grid, 128, 0, c->compute>>>(xs, n, (int)n, cnt, co, po); break;
+        case 8: rank_columns_warp_peers_kernel<8><<<grid, 128, 0, c->compute>>>(xs, n, (int)n, cnt, co, po); break;
+        case 16: rank_columns_warp_peers_kernel<16><<<grid, 128, 0, c->compute>>>(xs, n, (int)n, cnt, co, po); break;
+        default: rank_columns_warp_peers_kernel<32><<<grid, 128, 0, c->compute>>>(xs, n, (int)n, cnt, co, po); break;
+      }
+      g_launches++;
+      CU_TRY(cudaGetLastError());
+    } else {  // any other column kernel: build the slab locally, then copy its records (and norms) to the peers
+      RC_TRY(build_operand(c, xs, n, g1 - g0, spearman, X.precision, 0, g1 - g0, X.local + X.op_off[b] + (size_t)g0 * X.rb,
+                           (double*)(X.local + X.inv_off[b]) + g0));
+      Timed tm(c, T_OTHER);
+      PeerCopy pc;
+      memset(&pc, 0, sizeof pc);
+      for (int r = 0; r < X.world; ++r)
+        if (r != X.rank) pc.dst[pc.n++] = X.peer[r] + X.op_off[b] + (size_t)g0 * X.rb;
+      const int64_t bytes = (int64_t)(g1 - g0) * (int64_t)X.rb;  // records are multiples of 16 bytes, cudaMalloc-aligned
+      peer_broadcast_kernel<<<(unsigned)std::min<int64_t>((bytes / 16 + 255) / 256, (int64_t)c->sm_count * 8), 256, 0, c->compute>>>(
+          X.local + X.op_off[b] + (size_t)g0 * X.rb, pc, bytes);
+      g_launches++;
+      if (X.precision == BIXCOR_PREC_I8EXACT) {
+        for (int r = 0, q = 0; r < X.world; ++r)
+          if (r != X.rank) pc.dst[q++] = X.peer[r] + X.inv_off[b] + sizeof(double) * (size_t)g0;
+        const int64_t ib = (int64_t)sizeof(double) * (X.slab);  // whole (128-aligned) slab: a multiple of 16 bytes
+        peer_broadcast_kernel<<<(unsigned)((ib / 16 + 255) / 256), 256, 0, c->compute>>>(X.local + X.inv_off[b] + sizeof(double) * (size_t)g0, pc, ib);
+        g_launches++;
+      }
+      CU_TRY(cudaGetLastError());
+    }
+  }
+  {
+    Timed tm(c, T_OTHER);
+    PeerFlags pf;
+    memset(&pf, 0, sizeof pf);
+    pf.n = X.world;
+    for (int r = 0; r < X.world; ++r) pf.flags[r] = (uint32_t*)(X.peer[r] + X.flag_off);
+    peer_barrier_kernel<<<1, 32, 0, c->compute>>>(pf, X.rank, epoch);
+    g_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  return BIXCOR_OK;
+}
 
 // Host -> host packed correlation of rows [row_begin,row_end) with both PCIe directions busy at once.  The packed
 // result (8 bytes per pair) is ten times the input, so the device-to-host stream is the floor of the call; it should
@@ -2031,7 +2234,11 @@ int bixcor_init_devices(int first_device, int n_gpus) {
   if (const char* v = getenv("BIXCOR_STAGE_PIECE_KB")) g_stage_piece = (size_t)std::max(64, std::min(65536, atoi(v))) << 10;
   if (const char* v = getenv("BIXCOR_STAGE_NT")) g_stage_nt = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_STAGE_SPIN")) g_stage_spin = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_STAGE_SEQ")) g_stage_seq = atoi(v) != 0;
   if (const char* v = getenv("BIXCOR_S32_TRANSPORT")) g_s32_transport = atoi(v) != 0;
+  if (const char* v = getenv("BIXCOR_S32_SLOT_KB")) g_s32_slot_bytes = (size_t)std::max(64, std::min(262144, atoi(v))) << 10;
+  if (const char* v = getenv("BIXCOR_S32_SLOTS")) g_s32_slots = std::max(2, std::min((int)HostStager::kMaxSlots, atoi(v)));
+  if (const char* v = getenv("BIXCOR_S32_PIECE_KB")) g_s32_piece = (size_t)std::max(64, std::min(65536, atoi(v))) << 10;
   if (const char* v = getenv("BIXCOR_F32_TRANSPORT")) g_f32_transport = atoi(v) != 0;
   for (int d = 0; d < n_gpus; ++d) {
     Ctx* c = nullptr;
@@ -2348,6 +2555,128 @@ int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_
   RC_TRY(dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, (double*)c->out.ptr, &pipe, h_out_slice));
   RC_TRY(finish(c));
   return pipe.finish();
+  API_END
+}
+
+int bixcor_xchg_create(int64_t n, int64_t p, int precision, int world, int rank, void* handle_out) {
+  API_BEGIN
+  DEV_PROLOGUE();
+  if (!handle_out) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (n < 2 || p < 1) return fail(BIXCOR_ERR_INVALID, "bad shape");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(BIXCOR_ERR_INVALID, "the operand exchange serves 1..%d ranks of one box (world %d, rank %d)", kMaxPeers, world, rank);
+  precision = resolve_precision(precision, 1, n);  // AUTO: what a Spearman call resolves to (pass the precision explicitly for Pearson)
+  if (!exchangeable(precision)) return fail(BIXCOR_ERR_INVALID, "precision %d has no per-gene operand record", precision);
+  static_assert(sizeof(cudaIpcMemHandle_t) == BIXCOR_XCHG_HANDLE_BYTES, "handle size");
+  xchg_free(c);
+  Xchg& X = c->xchg;
+  X.world = world;
+  X.rank = rank;
+  X.precision = precision;
+  X.n = n;
+  X.p = p;
+  X.slab = ((p + world - 1) / world + kTile - 1) / kTile * kTile;  // equal 128-aligned gene slabs, the last one ragged
+  X.rb = (size_t)operand_row_bytes(n, precision);
+  auto up = [](size_t v) { return (v + 1023) & ~size_t(1023); };
+  const size_t opb = up(X.rb * (size_t)X.slab * (size_t)world), invb = up(sizeof(double) * (size_t)X.slab * (size_t)world);
+  X.op_off[0] = 0;
+  X.op_off[1] = opb;
+  X.inv_off[0] = 2 * opb;
+  X.inv_off[1] = 2 * opb + invb;
+  X.flag_off = 2 * opb + 2 * invb;
+  X.total = X.flag_off + 64 * (size_t)kMaxPeers;
+  void* ptr = nullptr;
+  if (cudaMalloc(&ptr, X.total) != cudaSuccess) {
+    cudaGetLastError();
+    const size_t mb = X.total >> 20;
+    X = Xchg();
+    return fail(BIXCOR_ERR_OOM, "cannot allocate the %zu MB exchange block", mb);
+  }
+  X.local = (char*)ptr;
+  X.peer[rank] = X.local;
+  CU_TRY(cudaMemset(X.local, 0, X.total));
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out, X.local));
+  return BIXCOR_OK;
+  API_END
+}
+
+int bixcor_xchg_open(const void* handles) {
+  API_BEGIN
+  DEV_PROLOGUE();
+  Xchg& X = c->xchg;
+  if (!X.local) return fail(BIXCOR_ERR_INVALID, "bixcor_xchg_create comes first");
+  if (!handles) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  if (X.opened) return BIXCOR_OK;
+  for (int r = 0; r < X.world; ++r) {
+    if (r == X.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+    void* ptr = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    X.peer[r] = (char*)ptr;
+  }
+  X.opened = 1;
+  return BIXCOR_OK;
+  API_END
+}
+
+int bixcor_xchg_release_peers(void) {
+  API_BEGIN
+  if (g_ctx.empty()) return BIXCOR_OK;
+  xchg_release_peers(g_ctx[0]);
+  return BIXCOR_OK;
+  API_END
+}
+
+int bixcor_xchg_destroy(void) {
+  API_BEGIN
+  if (g_ctx.empty()) return BIXCOR_OK;
+  xchg_free(g_ctx[0]);
+  return BIXCOR_OK;
+  API_END
+}
+
+// d_out_slice (device) or h_out_slice (host) receives the packed rows; exactly one of them is non-null
+static int cor_upper_rows_xchg(Ctx* c, const double* d_x, int x_is_slab, int64_t n, int64_t p, int spearman, int shift, double beta,
+                               int64_t row_begin, int64_t row_end, double* d_out_slice, double* h_out_slice) {
+  Xchg& X = c->xchg;
+  if (!X.opened && X.world > 1) return fail(BIXCOR_ERR_INVALID, "bixcor_xchg_create / bixcor_xchg_open come first");
+  if (!X.local || n != X.n || p != X.p) return fail(BIXCOR_ERR_INVALID, "shape differs from the one the exchange was created for");
+  RC_TRY(validate_rows(p, row_begin, row_end));
+  if (!d_x || (!d_out_slice && !h_out_slice)) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  RC_TRY(check_precision(X.precision, spearman, n));
+  shift = shift ? 1 : 0;
+  RC_TRY(xchg_build_and_sync(c, d_x, x_is_slab, spearman));  // every rank takes part, also one with an empty row range
+  if (row_begin == row_end) return d_out_slice ? finish_dev(c) : finish(c);
+  const int b = (int)(X.epoch & 1u);
+  Operand op;
+  bind_operand(&op, n, p, X.precision, X.local + X.op_off[b], (const double*)(X.local + X.inv_off[b]));
+  if (d_out_slice) {
+    RC_TRY(dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, d_out_slice, nullptr, nullptr));
+    return finish_dev(c);
+  }
+  const int64_t o0 = packed_row_offset(row_begin, p, shift), o1 = packed_row_offset(row_end, p, shift);
+  RC_TRY(c->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(1, o1 - o0)));
+  D2HPipe pipe(c, h_out_slice);
+  RC_TRY(dev_cor_upper_rows_op(c, op, p, shift, beta, row_begin, row_end, (double*)c->out.ptr, &pipe, h_out_slice));
+  RC_TRY(finish(c));
+  return pipe.finish();
+}
+
+int bixcor_dev_cor_upper_rows_xchg(const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                                   int64_t row_begin, int64_t row_end, double* d_out_slice) {
+  API_BEGIN
+  DEV_PROLOGUE();
+  return cor_upper_rows_xchg(c, d_x, 0, n, p, spearman, shift, beta, row_begin, row_end, d_out_slice, nullptr);
+  API_END
+}
+
+int bixcor_dev_cor_upper_rows_xchg_to_host(const double* d_x_slab, int64_t n, int64_t p, int spearman, int shift, double beta,
+                                           int64_t row_begin, int64_t row_end, double* h_out_slice) {
+  API_BEGIN
+  DEV_PROLOGUE();
+  return cor_upper_rows_xchg(c, d_x_slab, 1, n, p, spearman, shift, beta, row_begin, row_end, nullptr, h_out_slice);
   API_END
 }
 

@@ -40,6 +40,17 @@ struct ColumnOut {
   double* inv_norm;    // COL_I8: 1/sqrt(sum d^2) per gene
 };
 
+// Fused operand exchange (one process per GPU, bixcor_xchg_* in csrc/bixcor.cu): the column kernel stores every COL_I8 record
+// it finishes not only into its own operand buffer but straight into the operand buffer of every peer GPU, through
+// P2P-mapped (cudaIpc) pointers over NVLink / NVSwitch, so that the separate all-gather collective disappears and the
+// transfer overlaps the sort.  Pointers are laid out like ColumnOut::i8 / inv_norm (already offset to the launch's first gene).
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+  int n;                       // peer destinations (the local buffer is ColumnOut's and not listed here)
+  int8_t* i8[kMaxPeers];
+  double* inv_norm[kMaxPeers];
+};
+
 __device__ __forceinline__ uint64_t sortable_key(double v) {
   v = v + 0.0;  // -0.0 -> +0.0 so that signed zeros tie (base-R semantics)
   uint64_t b = (uint64_t)__double_as_longlong(v);
@@ -477,8 +488,9 @@ rank_big_emit_kernel(const uint32_t* __restrict__ rk2, const int* __restrict__ n
 // registers of one thread; the others are lane exchanges by shuffle.  No
 // shared-memory traffic and no block barrier in the sort.
 // ----------------------------------------------------------------------------
-template <typename RK>
-__device__ __forceinline__ void emit_ranked_column_warp(const ColumnOut& out, int64_t j, int n, const RK* rk2, int lane) {
+template <typename RK, bool PEERS = false>
+__device__ __forceinline__ void emit_ranked_column_warp(const ColumnOut& out, int64_t j, int n, const RK* rk2, int lane,
+                                                        const PeerOut* po = nullptr) {
   if (out.mode == COL_RANKS) {
     for (int i = lane; i < n; i += 32) out.f64[j * out.ld64 + i] = 0.5 * (double)rk2[i];
     return;
@@ -511,8 +523,18 @@ __device__ __forceinline__ void emit_ranked_column_warp(const ColumnOut& out, in
       }
       *reinterpret_cast<uint32_t*>(out.i8 + j * out.ld8 + i4) = wh;
       *reinterpret_cast<uint32_t*>(out.i8 + out.plane8 + j * out.ld8 + i4) = wl;
+      if (PEERS) {  // the same two words into every peer's operand buffer (128 contiguous bytes per warp store, over NVLink)
+        for (int r = 0; r < po->n; ++r) {
+          *reinterpret_cast<uint32_t*>(po->i8[r] + j * out.ld8 + i4) = wh;
+          *reinterpret_cast<uint32_t*>(po->i8[r] + out.plane8 + j * out.ld8 + i4) = wl;
+        }
+      }
     }
-    if (lane == 0) out.inv_norm[j] = 1.0 / norm;
+    if (lane == 0) {
+      out.inv_norm[j] = 1.0 / norm;
+      if (PEERS)
+        for (int r = 0; r < po->n; ++r) po->inv_norm[r][j] = 1.0 / norm;
+    }
   } else {
     for (int i = lane; i < out.kpad; i += 32) {
       double z = 0.0;
@@ -553,9 +575,9 @@ __device__ __forceinline__ void ce_lane(double& k, uint32_t& i, double ok, uint3
       : "d"(ok), "r"(oi), "r"(keep_min));
 }
 
-template <int E>
-__global__ void __launch_bounds__(128)
-rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out) {
+template <int E, bool PEERS>
+__device__ __forceinline__ void rank_columns_warp_body(const double* __restrict__ x, int64_t ldx, int n, int64_t p, const ColumnOut& out,
+                                                       const PeerOut* po) {
   constexpr int NP = 32 * E;
   __shared__ uint16_t rk2s[4][NP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -589,8 +611,17 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
       for (int i = lane; i < out.kpad; i += 32) {
         out.i8[j * out.ld8 + i] = 0;
         out.i8[out.plane8 + j * out.ld8 + i] = 0;
+        if (PEERS)
+          for (int r = 0; r < po->n; ++r) {
+            po->i8[r][j * out.ld8 + i] = 0;
+            po->i8[r][out.plane8 + j * out.ld8 + i] = 0;
+          }
       }
-      if (lane == 0) out.inv_norm[j] = qnan;
+      if (lane == 0) {
+        out.inv_norm[j] = qnan;
+        if (PEERS)
+          for (int r = 0; r < po->n; ++r) po->inv_norm[r][j] = qnan;
+      }
     } else {
       for (int i = lane; i < out.kpad; i += 32) {
         if (out.half_planes) {
@@ -716,7 +747,61 @@ rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64
     if (idx[r] < (uint32_t)n) rk2[idx[r]] = (uint16_t)(lo[r] + (uint32_t)min(cur, n - 1) + 2u);
   }
   __syncwarp();
-  emit_ranked_column_warp(out, j, n, rk2, lane);
+  emit_ranked_column_warp<uint16_t, PEERS>(out, j, n, rk2, lane, po);
+}
+
+template <int E>
+__global__ void __launch_bounds__(128)
+rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out) {
+  rank_columns_warp_body<E, false>(x, ldx, n, p, out, nullptr);
+}
+// the same kernel with the peer stores of the fused operand exchange (COL_I8 only)
+template <int E>
+__global__ void __launch_bounds__(128)
+rank_columns_warp_peers_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out,
+                               const __grid_constant__ PeerOut peers) {
+  rank_columns_warp_body<E, true>(x, ldx, n, p, out, &peers);
+}
+
+// Generic form of the exchange for the column kernels without fused peer stores: copies `bytes` (a multiple of 16) from the
+// local buffer to the same offset of every peer buffer with 128-bit stores.
+struct PeerCopy {
+  int n;
+  char* dst[kMaxPeers];
+};
+__global__ void __launch_bounds__(256)
+peer_broadcast_kernel(const char* __restrict__ src, const __grid_constant__ PeerCopy peers, int64_t bytes) {
+  const int64_t n16 = bytes >> 4, stride = (int64_t)gridDim.x * blockDim.x;
+  const int4* s16 = reinterpret_cast<const int4*>(src);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += stride) {
+    const int4 v = s16[t];
+    for (int r = 0; r < peers.n; ++r) reinterpret_cast<int4*>(peers.dst[r])[t] = v;
+  }
+}
+
+// Cross-GPU barrier of the exchange (one CTA): thread r tells peer r that this rank's records of step `epoch` are complete
+// (system-scope release store into the peer's flag array; the column kernel's peer stores were performed before this
+// kernel started) and waits until peer r has said the same here.  A peer that never arrives traps after ~20 s instead of
+// hanging the GPU.
+struct PeerFlags {
+  int n;                        // world size (own rank included)
+  uint32_t* flags[kMaxPeers];   // flag array of every rank (16 words = 64 bytes apart per writer)
+};
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(const __grid_constant__ PeerFlags pf, int rank, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r >= pf.n) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[r] + rank * 16), "r"(epoch) : "memory");
+  const uint32_t* mine = pf.flags[rank] + r * 16;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t seen;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    if ((int32_t)(seen - epoch) >= 0) break;
+    if (clock64() - t0 > 40000000000ll) __trap();
+    __nanosleep(100);
+  }
 }
 
 // Pearson: centre and scale one gene per CTA to unit Euclidean norm, so that

@@ -190,6 +190,66 @@ def exchange_operand(backend, x, n, p, spearman, precision, group=None):
     return operand, inv
 
 
+def xchg_setup(backend, n, p, precision, group=None):
+    """Collective: create this rank's exchange block, all-gather the cudaIpc handles and map the peers' blocks
+    (include/bixcor.h, bixcor_xchg_*).  Afterwards bixcor_dev_cor_upper_rows_xchg needs no collective library: the column
+    kernel stores its records into every peer's operand buffer over NVLink and a flag barrier in peer memory replaces the
+    all-gather.  One box, world <= 8."""
+    import ctypes as C
+
+    rank, world = _world(group)
+    lib = backend.lib
+    check(lib.bixcor_xchg_release_peers())  # (a previous exchange: nobody maps a block any more when its owner frees it)
+    if world > 1:
+        dist.barrier(group=group)
+    h = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES)()
+    check(lib.bixcor_xchg_create(n, p, precision, world, rank, h))
+    mine = torch.tensor(list(bytes(h)), dtype=torch.uint8, device=backend.device)
+    every = torch.empty(world * _lib.XCHG_HANDLE_BYTES, dtype=torch.uint8, device=backend.device)
+    if world > 1:
+        dist.all_gather_into_tensor(every, mine, group=group)
+    else:
+        every.copy_(mine)
+    blob = bytes(every.cpu().numpy().tobytes())
+    check(lib.bixcor_xchg_open(blob))
+    if world > 1:
+        dist.barrier(group=group)  # every rank has mapped every block before anybody stores into one
+
+
+def xchg_teardown(backend, group=None):
+    """Collective: unmap the peers' blocks, synchronise, free this rank's block."""
+    _rank, world = _world(group)
+    check(backend.lib.bixcor_xchg_release_peers())
+    if world > 1:
+        dist.barrier(group=group)
+    check(backend.lib.bixcor_xchg_destroy())
+
+
+def sharded_cor_upper_xchg(backend, x, n, p, spearman, shift=1, beta=1.0, group=None):
+    """sharded_cor_upper through the fused operand exchange (xchg_setup first): one library call per rank and step."""
+    rank, world = _world(group)
+    r0, r1 = pair_balanced_rows(p, shift, world, rank)
+    ln = packed_offset(r1, p, shift) - packed_offset(r0, p, shift)
+    out = backend.empty(max(ln, 1))[:ln]
+    backend._sync_in()
+    check(backend.lib.bixcor_dev_cor_upper_rows_xchg(x.data_ptr(), n, p, int(spearman), int(shift), float(beta), r0, r1, out.data_ptr()))
+    return out, (packed_offset(r0, p, shift), packed_offset(r1, p, shift))
+
+
+def host_sharded_cor_upper_xchg(backend, x_host, n, p, spearman, out_host, shift=1, beta=1.0, group=None):
+    """host_sharded_cor_upper through the fused operand exchange: H2D of this rank's gene slab, rank kernel with peer stores,
+    flag barrier, Gram rows with the band-pipelined D2H into out_host."""
+    rank, world = _world(group)
+    r0, r1 = pair_balanced_rows(p, shift, world, rank)
+    slab = gene_slab(p, world)
+    g0, g1 = min(p, rank * slab), min(p, (rank + 1) * slab)
+    x_slab = backend.to_device(x_host[g0:max(g1, g0 + 1)] if g1 > g0 else x_host[0:1])
+    backend._sync_in()
+    check(backend.lib.bixcor_dev_cor_upper_rows_xchg_to_host(x_slab.data_ptr(), n, p, int(spearman), int(shift), float(beta), r0, r1,
+                                                             out_host.data_ptr()))
+    return packed_offset(r0, p, shift), packed_offset(r1, p, shift)
+
+
 def sharded_cor_upper(backend, x, n, p, spearman, shift=1, beta=1.0, precision=PREC_F64, group=None):
     """Rank-local slice of the packed correlation vector and its [o0,o1) range.
 

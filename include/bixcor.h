@@ -256,6 +256,32 @@ int bixcor_dev_cor_upper_rows_op(const void* d_operand, const double* d_inv_norm
 int bixcor_dev_cor_upper_rows_op_to_host(const void* d_operand, const double* d_inv_norm, int64_t n, int64_t p,
                                          int precision, int shift, double beta, int64_t row_begin,
                                          int64_t row_end, double* h_out_slice);
+/* Fused operand exchange over peer memory: the multi-process (one process per GPU, one box) form of the three calls above
+ * without a collective library in the data path.  Every rank allocates one exchange block (two operand buffers, two norm
+ * buffers, flags) and exports it with cudaIpc (bixcor_xchg_create: `handle_out` receives BIXCOR_XCHG_HANDLE_BYTES bytes); the
+ * caller all-gathers the handles in rank order by whatever means it has (torch.distributed, MPI, a file) and every rank maps
+ * its peers' blocks (bixcor_xchg_open).  bixcor_dev_cor_upper_rows_xchg then (1) runs the column kernel on this rank's
+ * gene slab (equal 128-aligned slabs in rank order) and stores every finished record straight into the operand buffer of
+ * EVERY rank over NVLink / NVSwitch - for the exact Spearman kind with n <= 1024 from inside the rank kernel, so the
+ * transfer overlaps the sort; other kinds copy the slab with a peer-store kernel -, (2) synchronises the ranks with a
+ * one-CTA flag barrier in the same peer-mapped block, (3) computes the packed rows [row_begin,row_end) from the local
+ * buffer.  It replaces the all-gather collective + bixcor_dev_operand_inv_norm of the three-call form (no separate
+ * collective kernel, no norm kernel).  A collective call: every rank of the exchange must make it, with its own row range
+ * (an empty one is fine).  precision: as for the other calls, BIXCOR_PREC_AUTO resolved for Spearman; FP64, 3xTF32, 3xF16 and
+ * exact int8 have per-gene records (Ozaki does not).  world <= 8.  d_x: the full n x p matrix in HBM; the _to_host form
+ * takes only this rank's gene slab (genes [rank*slab, ...)) and returns the rows through the band-pipelined D2H. */
+#define BIXCOR_XCHG_HANDLE_BYTES 64
+int bixcor_xchg_create(int64_t n, int64_t p, int precision, int world, int rank, void* handle_out);
+int bixcor_xchg_open(const void* handles_in_rank_order);
+/* Teardown / re-creation is two-phase because a block must outlive its remote mappings: every rank unmaps its peers' blocks
+ * (bixcor_xchg_release_peers), the caller synchronises the ranks, then bixcor_xchg_destroy / the next bixcor_xchg_create
+ * frees the rank's own block. */
+int bixcor_xchg_release_peers(void);
+int bixcor_xchg_destroy(void);
+int bixcor_dev_cor_upper_rows_xchg(const double* d_x, int64_t n, int64_t p, int spearman, int shift, double beta,
+                                   int64_t row_begin, int64_t row_end, double* d_out_slice);
+int bixcor_dev_cor_upper_rows_xchg_to_host(const double* d_x_slab, int64_t n, int64_t p, int spearman, int shift, double beta,
+                                           int64_t row_begin, int64_t row_end, double* h_out_slice);
 int bixcor_dev_cor_dense(const double* d_x, int64_t n, int64_t p, int spearman, int precision, double* d_out_pp);
 int bixcor_dev_diffcor_rows(const double* d_xa, int64_t na, const double* d_xb, int64_t nb, int64_t p,
                             int spearman, int precision, int64_t row_begin, int64_t row_end, double* d_r_a,

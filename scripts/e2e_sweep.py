@@ -55,6 +55,18 @@ def main():
         settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_COPY_THREADS": 10})
         settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_STAGE_SPIN": 0})
         settings.append({"BIXCOR_STAGE_SLOT_KB": 1024, "BIXCOR_STAGE_SLOTS": 32, "BIXCOR_STAGE_PIECE_KB": 256, "BIXCOR_S32_TRANSPORT": 0})
+    elif "--round2d" in sys.argv:  # ring geometry of the int32 transport alone (BIXCOR_S32_*)
+        for slot_kb, slots, piece in ((4096, 16, 512), (1024, 32, 256), (1024, 24, 256), (1024, 48, 256), (2048, 16, 256), (2048, 32, 512), (1024, 32, 512), (1536, 32, 256)):
+            settings.append({"BIXCOR_S32_SLOT_KB": slot_kb, "BIXCOR_S32_SLOTS": slots, "BIXCOR_S32_PIECE_KB": piece})
+        settings.append({})
+    elif "--round2e" in sys.argv:  # landing signal: stream-written sequence word vs CUDA events; repeated to see the run-to-run spread
+        for rep in range(3):
+            settings.append({"BIXCOR_STAGE_SEQ": 1})
+            settings.append({"BIXCOR_STAGE_SEQ": 0})
+        for slot_kb, slots, piece in ((4096, 16, 512), (2048, 16, 256), (1024, 16, 256), (512, 32, 128), (512, 64, 256), (1024, 32, 128)):
+            settings.append({"BIXCOR_S32_SLOT_KB": slot_kb, "BIXCOR_S32_SLOTS": slots, "BIXCOR_S32_PIECE_KB": piece})
+        for thr in (12, 16):
+            settings.append({"BIXCOR_COPY_THREADS": thr})
     else:
         for slot_mb, slots in ((32, 8), (16, 8), (8, 8), (4, 8), (2, 16), (8, 16), (64, 4)):
             settings.append({"BIXCOR_STAGE_SLOT_MB": slot_mb, "BIXCOR_STAGE_SLOTS": slots})

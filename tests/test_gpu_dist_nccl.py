@@ -39,6 +39,37 @@ def _worker(rank, world, port, tmpdir):
             out_host = torch.empty(o1 - o0, dtype=torch.float64).pin_memory()
             assert D.host_sharded_cor_upper(be, xt.pin_memory(), n, p, True, out_host, 1, 6.0, prec) == (o0, o1)
             assert np.abs(out_host.numpy() - full[o0:o1]).max() < tol
+        # fused operand exchange over peer memory (bixcor_xchg_*): the rank kernel stores its records into every rank's buffer,
+        # a flag barrier replaces the all-gather; several steps on changing data exercise the two buffers and the epochs
+        x2 = synthetic_bulk(n, p, seed=77)
+        x2[:, 3] = 1.5       # zero variance -> NaN row / column
+        x2[4, 900] = np.nan  # NaN column (a gene of the second slab)
+        x2d = torch.from_numpy(np.ascontiguousarray(x2.T)).to(dev)
+        full2 = o.soft_threshold(o.cor_upper_triangle(x2, True, True), 6.0)
+        ok2 = ~np.isnan(full2)
+        for prec, tol in ((_lib.PREC_I8EXACT, 1e-12), (_lib.PREC_AUTO, 1e-12), (_lib.PREC_F64, 1e-10), (_lib.PREC_TF32X3, 1e-5), (_lib.PREC_F16X3, 1e-5)):
+            D.xchg_setup(be, n, p, prec)
+            for step in range(5):
+                if step % 2 == 0:
+                    sl, (o0, o1) = D.sharded_cor_upper_xchg(be, xd, n, p, True, 1, 6.0)
+                    assert np.abs(sl.cpu().numpy() - full[o0:o1]).max() < tol, (prec, step)
+                else:
+                    sl, (o0, o1) = D.sharded_cor_upper_xchg(be, x2d, n, p, True, 1, 6.0)
+                    got, ref2 = sl.cpu().numpy(), full2[o0:o1]
+                    assert np.isnan(got[~ok2[o0:o1]]).all() and np.abs(got[ok2[o0:o1]] - ref2[ok2[o0:o1]]).max() < tol, (prec, step)
+            out_host = torch.empty(o1 - o0, dtype=torch.float64)  # pageable
+            assert D.host_sharded_cor_upper_xchg(be, xt, n, p, True, out_host, 1, 6.0) == (o0, o1)
+            assert np.abs(out_host.numpy() - full[o0:o1]).max() < tol
+        # more than 1024 samples: the CTA rank kernel has no fused peer stores, its slab goes out through the peer-copy kernel
+        n3, p3 = 1100, 300
+        x3 = synthetic_bulk(n3, p3, seed=8, tie_heavy=True)
+        x3d = torch.from_numpy(np.ascontiguousarray(x3.T)).to(dev)
+        full3 = o.cor_upper_triangle(x3, True, True)
+        D.xchg_setup(be, n3, p3, _lib.PREC_AUTO)
+        for step in range(2):
+            sl, (o0, o1) = D.sharded_cor_upper_xchg(be, x3d, n3, p3, True, 1, 1.0)
+            assert np.abs(sl.cpu().numpy() - full3[o0:o1]).max() < 1e-12
+        D.xchg_teardown(be)
         xb = synthetic_bulk(n + 9, p, seed=6)
         xbd = torch.from_numpy(np.ascontiguousarray(xb.T)).to(dev)
         res, (d0, d1) = D.sharded_diffcor(be, xd, n, xbd, n + 9, p, False)

@@ -1085,3 +1085,32 @@ def test_binary32_transport_of_the_split_float_results(api, monkeypatch):
             assert np.abs(narrow - tom_ref).max() < TOL32, key
         else:
             assert np.abs(narrow - tom_ref[iu]).max() < TOL32, key
+
+
+def test_fused_operand_exchange_single_rank(api):
+    """bixcor_xchg_* with a world of one (the multi-rank form runs in tests/test_gpu_dist_nccl.py): the exchange block, the
+    rank kernel's peer-store variant (no peers), the flag barrier on itself and the two alternating buffers give exactly the
+    result of the plain call, step after step, for the fused (int8, n <= 1024) and the copy-kernel forms."""
+    import torch
+
+    from bixverse_b200 import _lib
+    from bixverse_b200 import distributed as D
+    from bixverse_b200.synthetic import synthetic_bulk
+
+    dev = torch.device("cuda", 0)
+    be = D.DeviceBackend(dev)
+    for n, p, precs in ((90, 700, (_lib.PREC_AUTO, _lib.PREC_F64, _lib.PREC_F16X3)), (1100, 260, (_lib.PREC_AUTO,))):
+        xs = [synthetic_bulk(n, p, seed=s, tie_heavy=(s == 1)) for s in (1, 2)]
+        xd = [torch.from_numpy(np.ascontiguousarray(x.T)).to(dev) for x in xs]
+        for prec in precs:
+            want = [be.cor_upper_rows(x, n, p, True, 1, 6.0, prec, 0, p).cpu().numpy() for x in xd]
+            D.xchg_setup(be, n, p, prec)
+            for step in range(4):
+                got, (o0, o1) = D.sharded_cor_upper_xchg(be, xd[step % 2], n, p, True, 1, 6.0)
+                assert (o0, o1) == (0, p * (p - 1) // 2)
+                assert np.array_equal(got.cpu().numpy(), want[step % 2]), (n, p, prec, step)
+            D.xchg_teardown(be)
+    # misuse is an error, not a crash
+    lib = _lib.load()
+    out = torch.empty(10, dtype=torch.float64, device=dev)
+    assert lib.bixcor_dev_cor_upper_rows_xchg(xd[0].data_ptr(), 1100, 260, 1, 1, 1.0, 0, 260, out.data_ptr()) == _lib.ERR_INVALID
