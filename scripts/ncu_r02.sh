@@ -31,6 +31,10 @@ case "${1:-c2}" in
     cap tom_f16 gram_umma 5 1 tom f16
     cap tom_tf32 gram_umma 5 1 tom tf32
     ;;
+  s32)
+    # host -> host call: 20 band launches per invocation, bottom-up; launch 59 (3 invocations) is the top band (8 block rows x 157)
+    cap c2_s32_gram_topband gram_umma 59 1 c2host auto
+    ;;
   list)
     python bench.py --steps 2 --warmup 3 --no-alt --no-tom --no-cpu > $O/bench_plain.log 2>&1 && \
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_default.csv \

@@ -3,6 +3,8 @@
   python scripts/ncu_target.py c2 <auto|f64|tf32|f16|ozaki>     config 2: Spearman 20000 x 1000, |r|^6, packed
   python scripts/ncu_target.py tom <f16|tf32|ozaki|f64>         config 4: signed TOM v1 from expression, beta 6, packed
   python scripts/ncu_target.py c3 <auto|f64>                    config 3: differential correlation 20000 x (500 vs 500)
+  python scripts/ncu_target.py c2host <auto|f16>                config 2 host -> host (page-locked buffers): the int32-transport
+                                                                instantiation of the Gram kernel (auto), 20 band launches per call
 
 Two warm-up invocations, then one measured; `-k regex:<kernel> -s <launches of the warm-ups>` selects the last one."""
 import os
@@ -31,6 +33,11 @@ if what == "c2":
     out = torch.empty(P, dtype=torch.float64, device=dev)
     for _ in range(reps):
         _lib.check(lib.bixcor_dev_cor_upper_rows(xd.data_ptr(), n, p, 1, 1, 6.0, PREC, 0, p, out.data_ptr()))
+elif what == "c2host":
+    xh = torch.from_numpy(np.ascontiguousarray(synthetic_bulk(n, p, seed=2024, tie_heavy=True).T)).pin_memory()
+    out = torch.empty(P, dtype=torch.float64).pin_memory()
+    for _ in range(reps):
+        _lib.check(lib.bixcor_cor_upper(xh.data_ptr(), n, p, 1, 1, 6.0, PREC, out.data_ptr()))
 elif what == "tom":
     xd = torch.from_numpy(np.ascontiguousarray(synthetic_bulk(n, p, seed=2026).T)).to(dev)
     for _ in range(reps):
