@@ -450,6 +450,15 @@ def run_ours(args):
         return row.cpu().numpy() if hasattr(row, "cpu") else np.asarray(row)
 
     primary = args.precision
+    exchange_note = None
+    if world > 1 and args.exchange == "peer":  # cudaIpc peer mapping unavailable (container policy, no P2P): every rank falls back together
+        try:
+            from bixverse_b200.distributed import DeviceBackend as _DB, xchg_setup as _xs
+
+            _xs(_DB(dev), n, p, _lib.PREC_I8EXACT if primary == "auto" else PREC[primary])
+        except Exception as ex:  # noqa: BLE001
+            exchange_note = f"peer exchange unavailable ({ex}); NCCL all-gather form used"
+            args.exchange = "nccl"
     main = measure_dev(primary, steps)
     parity = {"value_arm": cor_parity(lambda i: slice_row(out_dev, i))}
     exchange_cmp = None
@@ -758,7 +767,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "parity": parity_line,
             "paths": paths,
-            "exchange": exchange_cmp,
+            "exchange": exchange_cmp if exchange_cmp else ({"note": exchange_note} if exchange_note else None),
             "tom": tom,
             "extras": extras,
             "checksum": checksum,

@@ -1165,7 +1165,9 @@ static int stager_get(Ctx* c, HostStager** out, bool inbound = false) {
   st->kSlotBytes = std::max(st->kSlotBytes, inbound ? size_t(0) : g_s32_slot_bytes);
   for (int si = 0; si < st->kSlots; ++si) {
     auto& sl = st->slots[si];
-    if (cudaMallocHost(&sl.ptr, st->kSlotBytes) != cudaSuccess ||
+    // slots beyond the default cycle only ever serve the int32 transport's (smaller) slot size
+    const size_t cap = (inbound || si < st->kCycle) ? st->kSlotBytes : std::min(st->kSlotBytes, g_s32_slot_bytes);
+    if (cudaMallocHost(&sl.ptr, cap) != cudaSuccess ||
         cudaEventCreateWithFlags(&sl.dma_done, cudaEventDisableTiming | (g_stage_spin ? 0 : cudaEventBlockingSync)) != cudaSuccess) {
       cudaGetLastError();
       stager_free(st);

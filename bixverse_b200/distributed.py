@@ -202,8 +202,16 @@ def xchg_setup(backend, n, p, precision, group=None):
     check(lib.bixcor_xchg_release_peers())  # (a previous exchange: nobody maps a block any more when its owner frees it)
     if world > 1:
         dist.barrier(group=group)
+    def agree(rc):  # a failure on one rank fails the set-up on every rank (nobody waits in a collective for a rank that raised)
+        if world > 1:
+            worst = torch.tensor([rc], dtype=torch.int32, device=backend.device)
+            dist.all_reduce(worst, op=dist.ReduceOp.MIN, group=group)
+            if rc == _lib.OK and int(worst.item()) != _lib.OK:
+                raise _lib.BixcorError(int(worst.item()), "operand exchange set-up failed on another rank")
+        check(rc)
+
     h = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES)()
-    check(lib.bixcor_xchg_create(n, p, precision, world, rank, h))
+    agree(lib.bixcor_xchg_create(n, p, precision, world, rank, h))
     mine = torch.tensor(list(bytes(h)), dtype=torch.uint8, device=backend.device)
     every = torch.empty(world * _lib.XCHG_HANDLE_BYTES, dtype=torch.uint8, device=backend.device)
     if world > 1:
@@ -211,9 +219,7 @@ def xchg_setup(backend, n, p, precision, group=None):
     else:
         every.copy_(mine)
     blob = bytes(every.cpu().numpy().tobytes())
-    check(lib.bixcor_xchg_open(blob))
-    if world > 1:
-        dist.barrier(group=group)  # every rank has mapped every block before anybody stores into one
+    agree(lib.bixcor_xchg_open(blob))  # (also the barrier: every rank has mapped every block before anybody stores into one)
 
 
 def xchg_teardown(backend, group=None):

@@ -36,9 +36,9 @@ case "${1:-c2}" in
     cap c2_s32_gram_topband gram_umma 59 1 c2host auto
     ;;
   list)
-    python bench.py --steps 2 --warmup 3 --no-alt --no-tom --no-cpu > $O/bench_plain.log 2>&1 && \
+    python bench.py --steps 2 --warmup 3 --no-alt --no-tom --no-cpu --no-extras > $O/bench_plain.log 2>&1 && \
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_default.csv \
-        python bench.py --steps 2 --warmup 3 --no-alt --no-tom --no-cpu > $O/bench_ncu.log 2>&1
+        python bench.py --steps 2 --warmup 3 --no-alt --no-tom --no-cpu --no-extras > $O/bench_ncu.log 2>&1
     echo "list rc=$?"
     ;;
 esac
