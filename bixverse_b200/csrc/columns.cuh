@@ -575,6 +575,171 @@ __device__ __forceinline__ void ce_lane(double& k, uint32_t& i, double ok, uint3
       : "d"(ok), "r"(oi), "r"(keep_min));
 }
 
+// ---- the sort network, generic over the element type ------------------------------------------------------------------
+// SortKI: (full key, sample index) - the exact form.  SortPK: ONE double whose low 10 bits hold the sample index (see
+// rank_columns_warp_body): 2 instead of 3 registers per element, a compare-exchange moves 2 instead of 3 words, a lane
+// exchange shuffles 2 instead of 3, and - all elements being distinct - needs one comparison instead of two.
+struct SortKI {
+  double k;
+  uint32_t i;
+};
+struct SortPK {
+  double k;
+};
+__device__ __forceinline__ void ce_asc(SortKI& a, SortKI& b) { ce_asc(a.k, b.k, a.i, b.i); }
+__device__ __forceinline__ void ce_asc(SortPK& a, SortPK& b) {  // afterwards a.k <= b.k
+  const double x = a.k, y = b.k;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.lt.f64 p, %3, %2;\n\t"
+      "selp.f64 %0, %3, %2, p;\n\t"
+      "selp.f64 %1, %2, %3, p;\n\t}"
+      : "=&d"(a.k), "=&d"(b.k)
+      : "d"(x), "d"(y));
+}
+__device__ __forceinline__ void ce_lane(SortKI& own, int lm, int keep_min, const SortKI& give) {
+  const double ok = __shfl_xor_sync(0xffffffffu, give.k, lm);
+  const uint32_t oi = __shfl_xor_sync(0xffffffffu, give.i, lm);
+  ce_lane(own.k, own.i, ok, oi, keep_min);
+}
+__device__ __forceinline__ void ce_lane(SortPK& own, int lm, int keep_min, const SortPK& give) {
+  const double ok = __shfl_xor_sync(0xffffffffu, give.k, lm);
+  // distinct keys: take = keep_min ? (partner < own) : (partner > own) = (partner < own) XOR (keep_min == 0)
+  asm("{\n\t.reg .pred m, t;\n\t"
+      "setp.eq.s32 m, %2, 0;\n\t"
+      "setp.lt.xor.f64 t, %1, %0, m;\n\t"
+      "selp.f64 %0, %1, %0, t;\n\t}"
+      : "+d"(own.k)
+      : "d"(ok), "r"(keep_min));
+}
+
+// Bitonic sort of the warp's 32 * E elements, position s = lane*E + r, ascending everywhere.
+// Each merge of size k opens with the MIRROR stage (s <-> s ^ (k-1)), after which every
+// half-cleaner stage (s <-> s ^ jj) sorts upwards: no direction flags, no key flipping.
+// Merges inside one lane (k <= E) are fully unrolled register networks; merges across lanes
+// run in a RUNTIME loop over k (the fully unrolled network is instruction-fetch bound).
+template <int E, class T>
+__device__ __forceinline__ void bitonic_sort_warp(T (&a)[E], int lane) {
+  constexpr int NP = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const int l = r ^ (k - 1);
+      if (r < l) ce_asc(a[r], a[l]);
+    }
+#pragma unroll
+    for (int jj = k >> 2; jj > 0; jj >>= 1) {
+#pragma unroll
+      for (int r = 0; r < E; ++r)
+        if ((r & jj) == 0) ce_asc(a[r], a[r | jj]);
+    }
+  }
+#pragma unroll 1
+  for (int k = 2 * E; k <= NP; k <<= 1) {
+    {  // mirror stage: partner lane = lane ^ (k/E - 1), partner register = E-1-r
+      const int lm = k / E - 1;
+      const int keep_min = ((lane & (k / (2 * E))) == 0) ? 1 : 0;
+      if (E == 1) ce_lane(a[0], lm, keep_min, a[0]);
+#pragma unroll
+      for (int r = 0; r < E / 2; ++r) {  // registers r and E-1-r trade places across the lane pair
+        const int m = E - 1 - r;
+        const T gm = a[m], gr = a[r];
+        ce_lane(a[r], lm, keep_min, gm);
+        ce_lane(a[m], lm, keep_min, gr);
+      }
+    }
+#pragma unroll 1
+    for (int jj = k >> 2; jj >= E; jj >>= 1) {
+      const int lm = jj / E;  // partner lane = lane ^ lm, same register
+      const int keep_min = ((lane & lm) == 0) ? 1 : 0;
+#pragma unroll
+      for (int r = 0; r < E; ++r) ce_lane(a[r], lm, keep_min, a[r]);
+    }
+#pragma unroll
+    for (int jj = E / 2; jj > 0; jj >>= 1) {
+#pragma unroll
+      for (int r = 0; r < E; ++r)
+        if ((r & jj) == 0) ce_asc(a[r], a[r | jj]);
+    }
+  }
+}
+
+// -DBIXCOR_RANK_PACKED=0 builds the kernel without the packed fast path (ablation: every column takes the exact sort)
+#ifndef BIXCOR_RANK_PACKED
+#define BIXCOR_RANK_PACKED 1
+#endif
+
+// Tie runs -> 2 * average rank of every element, written to rk2[sample index].  start_mask bit r: position lane*E + r
+// starts a run of equal values; last: the lane's last run start (-1 if none); idx[r]: sample index at position lane*E + r.
+template <int E>
+__device__ __forceinline__ void assign_ranks_warp(uint32_t start_mask, int last, const uint32_t (&idx)[E], int n, int lane, uint16_t* rk2) {
+  // exclusive prefix max of `last` over lanes
+  int inc = last;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, t);
+  }
+  int cur = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) cur = -1;
+  uint32_t lo[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    if (start_mask & (1u << r)) cur = lane * E + r;
+    lo[r] = (uint32_t)cur;
+  }
+  // run ends: position s ends a run iff s+1 starts one (or s is the last slot)
+  uint32_t next_first = __shfl_down_sync(0xffffffffu, start_mask & 1u, 1);
+  if (lane == 31) next_first = 1u;
+  const uint32_t end_mask = (E == 32) ? ((start_mask >> 1) | (next_first << 31))
+                                      : (((start_mask >> 1) | (next_first << (E - 1))) & ((E == 32) ? 0xffffffffu : ((1u << E) - 1u)));
+  int first = 0x7fffffff;
+  if (end_mask) first = lane * E + (__ffs(end_mask) - 1);
+  int dec = first;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, dec, o);
+    if (lane + o < 32) dec = min(dec, t);
+  }
+  cur = __shfl_down_sync(0xffffffffu, dec, 1);
+  if (lane == 31) cur = 0x7fffffff;
+#pragma unroll
+  for (int r = E - 1; r >= 0; --r) {
+    const int s = lane * E + r;
+    if (end_mask & (1u << r)) cur = s;
+    // lo + hi + 2 == 2 * average 1-based rank; hi is clamped to the last real slot (+inf ties with padding)
+    if (idx[r] < (uint32_t)n) rk2[idx[r]] = (uint16_t)(lo[r] + (uint32_t)min(cur, n - 1) + 2u);
+  }
+}
+
+// Exact form: sort on (full key, sample index).  Out of line: it only runs for columns the packed fast path hands back
+// (values closer than 1024 ulp that are not equal), and keeping it out of the hot code keeps that within the instruction cache.
+template <int E>
+__device__ __noinline__ void rank_exact_warp(const double* __restrict__ col, int n, int lane, uint16_t* rk2) {
+  SortKI ki[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int i = r * 32 + lane;
+    ki[r].k = (i < n) ? col[i] : __longlong_as_double(0x7ff0000000000000ll);
+    ki[r].i = (uint32_t)i;
+  }
+  bitonic_sort_warp<E>(ki, lane);
+  const double prev_last = __shfl_up_sync(0xffffffffu, ki[E - 1].k, 1);
+  uint32_t start_mask = 0, idx[E];
+  int last = -1;
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int s = lane * E + r;
+    const double prev = (r == 0) ? prev_last : ki[r - 1].k;
+    idx[r] = ki[r].i;
+    if ((s == 0) || (ki[r].k != prev)) {
+      start_mask |= 1u << r;
+      last = s;
+    }
+  }
+  assign_ranks_warp<E>(start_mask, last, idx, n, lane, rk2);
+}
+
 template <int E, bool PEERS>
 __device__ __forceinline__ void rank_columns_warp_body(const double* __restrict__ x, int64_t ldx, int n, int64_t p, const ColumnOut& out,
                                                        const PeerOut* po) {
@@ -584,11 +749,20 @@ __device__ __forceinline__ void rank_columns_warp_body(const double* __restrict_
   const int64_t j = (int64_t)blockIdx.x * 4 + warp;
   if (j >= p) return;  // whole warp leaves; no block-level barrier below
   const double* col = x + j * ldx;
+  uint16_t* rk2 = rk2s[warp];
 
   // Padding slots hold +inf with an index >= n.  A real +inf ties with the padding, which is
   // harmless: the tie run then starts at the first real +inf and its end is clamped to n - 1.
-  double key[E];
-  uint32_t idx[E];
+  //
+  // Fast path (packed keys).  The sort only needs the ORDER of the values; ties are resolved afterwards.  Every element
+  // becomes one double: the value with -0 folded into +0, +-inf replaced by +-DBL_MAX, its low 10 mantissa bits replaced by
+  // the sample index (< 1024).  All packed keys of a column are distinct, they order like the values wherever the values
+  // differ above those 10 bits, and elements that agree above them (true ties, or values closer than 1024 ulp) end up
+  // adjacent.  The replaced bits (plus an "was infinite" flag) are parked in shared memory by sample index; after the sort
+  // every neighbour pair that agrees above the index bits is checked there: equal parked bits = the same value = a true tie
+  // (the only case in practice: tied data is tied exactly).  If any such pair differs, the column is redone with the exact
+  // (key, index) sort.  Bit-exact either way.
+  SortPK pk[E];
   bool has_nan = false;
 #pragma unroll
   for (int r = 0; r < E; ++r) {
@@ -598,8 +772,14 @@ __device__ __forceinline__ void rank_columns_warp_body(const double* __restrict_
       v = col[i];
       if (v != v) has_nan = true;
     }
-    key[r] = v;
-    idx[r] = (uint32_t)i;
+    unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+    uint32_t parked = (uint32_t)b & 1023u;
+    if ((b & 0x7ff0000000000000ull) == 0x7ff0000000000000ull) {
+      b = (b & 0x8000000000000000ull) | 0x7fefffffffffffffull;
+      parked = 1024u | 1023u;
+    }
+    if (BIXCOR_RANK_PACKED) rk2[i] = (uint16_t)parked;
+    pk[r].k = __longlong_as_double((long long)((b & ~0x3ffull) | (unsigned long long)i));
   }
   if (__any_sync(0xffffffffu, has_nan)) {
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
@@ -634,130 +814,51 @@ __device__ __forceinline__ void rank_columns_warp_body(const double* __restrict_
     }
     return;
   }
-
-  // ---- bitonic sort, position s = lane*E + r, ascending everywhere ---------------------------
-  // Each merge of size k opens with the MIRROR stage (s <-> s ^ (k-1)), after which every
-  // half-cleaner stage (s <-> s ^ jj) sorts upwards: no direction flags, no key flipping.
-  // Merges inside one lane (k <= E) are fully unrolled register networks; merges across lanes
-  // run in a RUNTIME loop over k (the fully unrolled network is instruction-fetch bound).
-#pragma unroll
-  for (int k = 2; k <= E; k <<= 1) {
+  bool redo = !BIXCOR_RANK_PACKED;
+  if (BIXCOR_RANK_PACKED) {
+    __syncwarp();  // parked bits visible to every lane
+    bitonic_sort_warp<E>(pk, lane);
+    const unsigned long long prev_last = (unsigned long long)__double_as_longlong(__shfl_up_sync(0xffffffffu, pk[E - 1].k, 1));
+    uint32_t start_mask = 0, idx[E];  // bit r: position lane*E + r starts a run of equal values
+    int last = -1;
+    uint32_t prev_parked = rk2[(uint32_t)prev_last & 1023u];
+    bool mixed = false;
 #pragma unroll
     for (int r = 0; r < E; ++r) {
-      const int l = r ^ (k - 1);
-      if (r < l) ce_asc(key[r], key[l], idx[r], idx[l]);
-    }
-#pragma unroll
-    for (int jj = k >> 2; jj > 0; jj >>= 1) {
-#pragma unroll
-      for (int r = 0; r < E; ++r)
-        if ((r & jj) == 0) ce_asc(key[r], key[r | jj], idx[r], idx[r | jj]);
-    }
-  }
-#pragma unroll 1
-  for (int k = 2 * E; k <= NP; k <<= 1) {
-    {  // mirror stage: partner lane = lane ^ (k/E - 1), partner register = E-1-r
-      const int lm = k / E - 1;
-      const int keep_min = ((lane & (k / (2 * E))) == 0) ? 1 : 0;
-      if (E == 1) {
-        const double ok = __shfl_xor_sync(0xffffffffu, key[0], lm);
-        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[0], lm);
-        ce_lane(key[0], idx[0], ok, oi, keep_min);
+      const int s = lane * E + r;
+      const unsigned long long cur = (unsigned long long)__double_as_longlong(pk[r].k);
+      const unsigned long long prv = (r == 0) ? prev_last : (unsigned long long)__double_as_longlong(pk[r - 1].k);
+      idx[r] = (uint32_t)cur & 1023u;
+      const uint32_t parked = rk2[idx[r]];
+      const bool same = (s != 0) && ((cur ^ prv) < 1024ull);  // agree above the index bits
+      if (same && parked != prev_parked) mixed = true;        // ... but are different values: needs the exact sort
+      if (!same) {
+        start_mask |= 1u << r;
+        last = s;
       }
-#pragma unroll
-      for (int r = 0; r < E / 2; ++r) {  // registers r and E-1-r trade places across the lane pair
-        const int m = E - 1 - r;
-        const double oka = __shfl_xor_sync(0xffffffffu, key[m], lm);
-        const uint32_t oia = __shfl_xor_sync(0xffffffffu, idx[m], lm);
-        const double okb = __shfl_xor_sync(0xffffffffu, key[r], lm);
-        const uint32_t oib = __shfl_xor_sync(0xffffffffu, idx[r], lm);
-        ce_lane(key[r], idx[r], oka, oia, keep_min);
-        ce_lane(key[m], idx[m], okb, oib, keep_min);
-      }
+      prev_parked = parked;
     }
-#pragma unroll 1
-    for (int jj = k >> 2; jj >= E; jj >>= 1) {
-      const int lm = jj / E;  // partner lane = lane ^ lm, same register
-      const int keep_min = ((lane & lm) == 0) ? 1 : 0;
-#pragma unroll
-      for (int r = 0; r < E; ++r) {
-        const double ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
-        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
-        ce_lane(key[r], idx[r], ok, oi, keep_min);
-      }
-    }
-#pragma unroll
-    for (int jj = E / 2; jj > 0; jj >>= 1) {
-#pragma unroll
-      for (int r = 0; r < E; ++r)
-        if ((r & jj) == 0) ce_asc(key[r], key[r | jj], idx[r], idx[r | jj]);
-    }
+    redo = __any_sync(0xffffffffu, mixed);  // (also orders the reads of the parked bits before the rank writes below)
+    if (!redo) assign_ranks_warp<E>(start_mask, last, idx, n, lane, rk2);
   }
-
-  // ---- tie runs -> 2 * average rank ------------------------------------------
-  const double prev_last = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
-  uint32_t start_mask = 0;  // bit r: position lane*E + r starts a run of equal keys
-  int last = -1;
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    const int s = lane * E + r;
-    const double prev = (r == 0) ? prev_last : key[r - 1];
-    const bool st = (s == 0) || (key[r] != prev);
-    if (st) {
-      start_mask |= 1u << r;
-      last = s;
-    }
-  }
-  // exclusive prefix max of `last` over lanes
-  int inc = last;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc = max(inc, t);
-  }
-  int cur = __shfl_up_sync(0xffffffffu, inc, 1);
-  if (lane == 0) cur = -1;
-  uint32_t lo[E];
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    if (start_mask & (1u << r)) cur = lane * E + r;
-    lo[r] = (uint32_t)cur;
-  }
-  // run ends: position s ends a run iff s+1 starts one (or s is the last slot)
-  uint32_t next_first = __shfl_down_sync(0xffffffffu, start_mask & 1u, 1);
-  if (lane == 31) next_first = 1u;
-  const uint32_t end_mask = (E == 32) ? ((start_mask >> 1) | (next_first << 31))
-                                      : (((start_mask >> 1) | (next_first << (E - 1))) & ((E == 32) ? 0xffffffffu : ((1u << E) - 1u)));
-  int first = 0x7fffffff;
-  if (end_mask) first = lane * E + (__ffs(end_mask) - 1);
-  int dec = first;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_down_sync(0xffffffffu, dec, o);
-    if (lane + o < 32) dec = min(dec, t);
-  }
-  cur = __shfl_down_sync(0xffffffffu, dec, 1);
-  if (lane == 31) cur = 0x7fffffff;
-  uint16_t* rk2 = rk2s[warp];
-#pragma unroll
-  for (int r = E - 1; r >= 0; --r) {
-    const int s = lane * E + r;
-    if (end_mask & (1u << r)) cur = s;
-    // lo + hi + 2 == 2 * average 1-based rank; hi is clamped to the last real slot (+inf ties with padding)
-    if (idx[r] < (uint32_t)n) rk2[idx[r]] = (uint16_t)(lo[r] + (uint32_t)min(cur, n - 1) + 2u);
-  }
+  if (redo) rank_exact_warp<E>(col, n, lane, rk2);
   __syncwarp();
   emit_ranked_column_warp<uint16_t, PEERS>(out, j, n, rk2, lane, po);
 }
 
+// Measured on 20 000 genes x 1 000 samples (scripts/rank_probe.py, profiles/rank_probe_r02.txt): 3 CTAs per SM (167 registers, no
+// spills) 0.247 ms, 4 CTAs per SM (capped at 128 registers, 12 bytes of spills) 0.260 ms; the (key, index) sort of round 1: 0.303 ms
+#ifndef BIXCOR_RANK_MIN_CTAS
+#define BIXCOR_RANK_MIN_CTAS 3
+#endif
 template <int E>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BIXCOR_RANK_MIN_CTAS)
 rank_columns_warp_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out) {
   rank_columns_warp_body<E, false>(x, ldx, n, p, out, nullptr);
 }
 // the same kernel with the peer stores of the fused operand exchange (COL_I8 only)
 template <int E>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BIXCOR_RANK_MIN_CTAS)
 rank_columns_warp_peers_kernel(const double* __restrict__ x, int64_t ldx, int n, int64_t p, ColumnOut out,
                                const __grid_constant__ PeerOut peers) {
   rank_columns_warp_body<E, true>(x, ldx, n, p, out, &peers);

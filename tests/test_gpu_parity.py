@@ -1114,3 +1114,39 @@ def test_fused_operand_exchange_single_rank(api):
     lib = _lib.load()
     out = torch.empty(10, dtype=torch.float64, device=dev)
     assert lib.bixcor_dev_cor_upper_rows_xchg(xd[0].data_ptr(), 1100, 260, 1, 1, 1.0, 0, 260, out.data_ptr()) == _lib.ERR_INVALID
+
+
+@pytest.mark.parametrize("n", [37, 64, 500, 1000, 1024])
+def test_ranks_bit_exact_packed_key_corner_cases(api, n):
+    """The register rank kernel sorts ONE double per element (value with its low 10 mantissa bits replaced by the sample
+    index) and verifies afterwards that elements agreeing above those bits are true ties; otherwise the column is redone with
+    the exact (key, index) sort.  Columns built to hit that machinery: values closer than 1024 ulp (differing only in the
+    replaced bits), mixtures of such near-ties and true ties, values next to +-DBL_MAX together with +-inf, subnormals and
+    signed zeros, negative near-ties (whose bit patterns order backwards), a constant column."""
+    rng = np.random.default_rng(n)
+    cols = []
+    base = 1.0 + rng.integers(0, 4, size=n) * 2.0 ** -20
+    cols.append(base + rng.integers(0, 1024, size=n) * 2.0 ** -52)          # near-ties: differ only in the low 10 bits
+    c = np.full(n, 3.0)
+    c[::2] = np.nextafter(3.0, 4.0)                                         # two values one ulp apart, each tied many times
+    cols.append(c)
+    c = -(1.0 + rng.integers(0, 1024, size=n) * 2.0 ** -52)                 # negative near-ties
+    cols.append(c)
+    big = np.finfo(np.float64).max
+    c = rng.normal(size=n)
+    c[: min(n, 6)] = [np.inf, big, np.nextafter(big, 0), -np.inf, -big, np.inf][: min(n, 6)]
+    cols.append(c)
+    tiny = np.finfo(np.float64).smallest_subnormal
+    c = rng.integers(-3, 4, size=n) * tiny                                  # subnormals around +-0
+    c[0], c[1] = 0.0, -0.0
+    cols.append(c)
+    cols.append(np.full(n, -7.25))                                          # constant
+    cols.append(np.round(rng.normal(size=n), 1))                            # ordinary tie-heavy column
+    cols.append(rng.normal(size=n))                                         # ordinary column
+    x = np.stack(cols, axis=1)
+    assert np.array_equal(api.rs_rank_matrix_col(x), o.rank_matrix_col(x))
+    # the same columns through the Spearman correlation (the int8 digit emission of the same kernel)
+    got = api.rs_cor_upper_triangle(x, True, True)
+    ref = o.cor_upper_triangle(x, True, True)
+    ok = ~np.isnan(ref)
+    assert np.isnan(got[~ok]).all() and (not ok.any() or np.abs(got[ok] - ref[ok]).max() < 1e-12)
