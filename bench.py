@@ -543,6 +543,20 @@ def run_ours(args):
     checksum = float(out_page[: min(my_pairs, 1 << 20)].sum())
     x_pin, out_pin = x_page.pin_memory(), torch.empty(max(my_pairs, 1), dtype=torch.float64).pin_memory()
     t_pin, _up_pin, _down_pin = time_e2e(make_step(x_pin, out_pin))
+    # the same calls with f64 on the wire (bixcor_set_transport(0, .)): every arithmetic operation of the result then runs on the
+    # GPU and the host threads only copy; the default sends the exact integer Gram as int32 and lets them finish r and the power
+    e2e_f64_wire = None
+    if primary in ("auto", "i8"):
+        _lib.check(lib.bixcor_set_transport(0, -1))
+        try:
+            t_page64, _u, down64 = time_e2e(make_step(x_page, out_page))
+            err64 = cor_parity(lambda i: slice_row(out_page, i))
+            t_pin64, _u, _d = time_e2e(make_step(x_pin, out_pin))
+            e2e_f64_wire = {"pageable_ms_per_step": 1e3 * t_page64, "pinned_ms_per_step": 1e3 * t_pin64, "d2h_bytes_per_step": int(down64),
+                            "parity_max_err": err64,
+                            "what": "BIXCOR_S32_TRANSPORT=0: the f64 epilogue runs on the GPU, 8 bytes per pair cross PCIe"}
+        finally:
+            _lib.check(lib.bixcor_set_transport(1, -1))
     del x_pin, out_pin
 
     # PCIe floor of the step: this rank's packed rows over one GPU's measured device -> pinned-host bandwidth
@@ -760,6 +774,7 @@ def run_ours(args):
                     "floor": e2e_floor,
                     "d2h_bytes_per_step": int(down_page), "result_bytes_per_step": int(8 * my_pairs), "steps": e2e_steps, "host_buffers": "pageable",
                     "pinned": {"value": P_total / t_pin, "ms_per_step": 1e3 * t_pin},
+                    "f64_on_the_wire": e2e_f64_wire,
                     "note": e2e_note + ", precision = " + primary + "; value: pageable host buffers (what an R session owns), "
                             "pinned: the same call with page-locked buffers; bytes are rank 0's"},
             "gpu_launches": main["gpu_launches"],

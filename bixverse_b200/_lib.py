@@ -32,6 +32,7 @@ SIGNATURES = {
     "bixcor_last_error": (C.c_char_p, []),
     "bixcor_launch_count": (i64, []),
     "bixcor_transfer_counters": (i32, [C.POINTER(i64), C.POINTER(i64), i32]),
+    "bixcor_set_transport": (i32, [i32, i32]),
     "bixcor_set_fieller": (i32, [f64]),
     "bixcor_debug_inject": (i32, [i32]),
     "bixcor_packed_len": (i64, [i64, i32]),

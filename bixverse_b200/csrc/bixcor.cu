@@ -2196,6 +2196,14 @@ int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset) 
   return BIXCOR_OK;
 }
 
+int bixcor_set_transport(int int32_exact_spearman, int binary32_split_float) {
+  API_BEGIN
+  if (int32_exact_spearman >= 0) g_s32_transport = int32_exact_spearman != 0;
+  if (binary32_split_float >= 0) g_f32_transport = binary32_split_float != 0;
+  return BIXCOR_OK;
+  API_END
+}
+
 int bixcor_set_fieller(double c) {
   API_BEGIN
   if (!(c > 0.0)) return fail(BIXCOR_ERR_INVALID, "Fieller factor must be positive");

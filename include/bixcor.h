@@ -108,6 +108,9 @@ int64_t bixcor_launch_count(void);
  * into the caller's f64 buffer by the same threads (relative 6e-8, far inside the class; env BIXCOR_F32_TRANSPORT=0 sends
  * f64).  The FP64-class precisions (F64, OZAKI) and every differential-correlation output always travel as f64. */
 int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
+/* Run-time form of BIXCOR_S32_TRANSPORT / BIXCOR_F32_TRANSPORT (1 = on, 0 = off: f64 on the wire, every arithmetic operation of
+ * the result on the GPU; negative = leave as it is).  bench.py reports the end-to-end time both ways. */
+int bixcor_set_transport(int int32_exact_spearman, int binary32_split_float);
 /* Fisher-z variance inflation for Spearman (default 1.06, Fieller); Pearson uses 1. */
 int bixcor_set_fieller(double c);
 /* Test hook of the exception barrier: the NEXT API call throws from inside its body
