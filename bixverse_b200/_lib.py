@@ -33,6 +33,8 @@ SIGNATURES = {
     "bixcor_launch_count": (i64, []),
     "bixcor_transfer_counters": (i32, [C.POINTER(i64), C.POINTER(i64), i32]),
     "bixcor_set_transport": (i32, [i32, i32]),
+    "bixcor_host_expand_s32": (i32, [ptr, i64, i64, ptr, i64, i32, i32, ptr]),
+    "bixcor_host_widen_f32": (i32, [ptr, i64, ptr]),
     "bixcor_set_fieller": (i32, [f64]),
     "bixcor_debug_inject": (i32, [i32]),
     "bixcor_packed_len": (i64, [i64, i32]),

@@ -2196,6 +2196,33 @@ int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset) 
   return BIXCOR_OK;
 }
 
+// Host halves of the two transports as plain functions (no GPU involved), so that the CPU-only test suite can check what the
+// staging threads do to a piece: the int32 -> r (-> |r|^6) expansion of packed elements [g0, g0 + count) and the float -> double
+// widening.
+int bixcor_host_expand_s32(const int32_t* src, int64_t count, int64_t g0, const double* inv_norm, int64_t p, int shift, int pow6,
+                           double* dst) {
+  API_BEGIN
+  if (!src || !dst || !inv_norm) return fail(BIXCOR_ERR_INVALID, "null pointer");
+  shift = shift ? 1 : 0;
+  if (p < 1 || count < 0 || g0 < 0 || g0 + count > packed_row_offset(p, p, shift)) return fail(BIXCOR_ERR_INVALID, "bad packed range");
+  ExpandS32 X;
+  X.inv = inv_norm;
+  X.p = p;
+  X.shift = shift;
+  X.pow6 = pow6 ? 1 : 0;
+  expand_packed_s32(dst, src, count, g0, X);
+  return BIXCOR_OK;
+  API_END
+}
+
+int bixcor_host_widen_f32(const float* src, int64_t count, double* dst) {
+  API_BEGIN
+  if (!src || !dst || count < 0) return fail(BIXCOR_ERR_INVALID, "bad arguments");
+  widen_f32(dst, src, count);
+  return BIXCOR_OK;
+  API_END
+}
+
 int bixcor_set_transport(int int32_exact_spearman, int binary32_split_float) {
   API_BEGIN
   if (int32_exact_spearman >= 0) g_s32_transport = int32_exact_spearman != 0;

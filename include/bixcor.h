@@ -111,6 +111,13 @@ int bixcor_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
 /* Run-time form of BIXCOR_S32_TRANSPORT / BIXCOR_F32_TRANSPORT (1 = on, 0 = off: f64 on the wire, every arithmetic operation of
  * the result on the GPU; negative = leave as it is).  bench.py reports the end-to-end time both ways. */
 int bixcor_set_transport(int int32_exact_spearman, int binary32_split_float);
+/* The host halves of the two transports as plain functions (no GPU involved; what the staging threads do to one piece):
+ * dst[t] = (double)src[t] * inv_norm[i] * inv_norm[j] (and, with pow6, sq = v v, sq sq sq) for the packed elements
+ * [g0, g0 + count) of a p-gene triangle - the device epilogue's IEEE operations in the device epilogue's order - and the
+ * float -> double widening.  Exposed for the CPU-only tests (tests/test_abi.py). */
+int bixcor_host_expand_s32(const int32_t* src, int64_t count, int64_t g0, const double* inv_norm, int64_t p, int shift, int pow6,
+                           double* dst);
+int bixcor_host_widen_f32(const float* src, int64_t count, double* dst);
 /* Fisher-z variance inflation for Spearman (default 1.06, Fieller); Pearson uses 1. */
 int bixcor_set_fieller(double c);
 /* Test hook of the exception barrier: the NEXT API call throws from inside its body

@@ -179,3 +179,43 @@ def test_small_p_shards_are_empty_not_invalid(lib_built):
         assert ranges[0][0] == 0 and ranges[-1][1] == p
         assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
         assert sum(1 for r0, r1 in ranges if r1 > r0) == 1  # one rank owns everything, the others are empty
+
+
+def test_host_halves_of_the_transports(lib_built):
+    """What the staging threads do to a piece of a result (no GPU involved): the exact Spearman Gram arrives as int32 and is
+    completed to r = S / (|d_i| |d_j|) (and |r|^6) with the device epilogue's IEEE multiplications in its order - so the
+    values must equal the same chain evaluated in numpy bit for bit, for any piece of the packed vector (ragged starts / ends,
+    pieces spanning many rows, unaligned destinations that take the scalar head / tail of the AVX2 loop), both shifts; the
+    binary32 transport widens float -> double exactly."""
+    import ctypes as C
+
+    from bixverse_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    for p, shift in ((37, 1), (130, 1), (64, 0), (301, 1)):
+        total = lib.bixcor_packed_len(p, shift)
+        s_all = rng.integers(-(2 ** 31) + 1, 2 ** 31 - 1, size=total, dtype=np.int64).astype(np.int32)
+        inv = 1.0 / np.sqrt(rng.uniform(1.0, 3.0e8, size=p))
+        inv[3] = np.nan  # a constant / NaN gene: its 1/|d| is NaN and poisons its row and column
+        # reference chain: ((double)S * inv_i) * inv_j, then sq = v * v, (sq * sq) * sq
+        ii, jj = np.triu_indices(p, 1 if shift else 0)
+        v = (s_all.astype(np.float64) * inv[ii]) * inv[jj]
+        sq = v * v
+        want = {0: v, 1: (sq * sq) * sq}
+        for pow6 in (0, 1):
+            for g0, count in ((0, total), (1, total - 1), (5, min(total - 5, 77)), (total // 3 + 1, total // 2), (total - 1, 1), (2, 0)):
+                buf = np.full(count + 3, -123.0)
+                for off in (0, 1):  # off = 1: the destination is 8 (mod 16/32): scalar head of the vector loop
+                    dst = buf[off:off + count]
+                    src = np.ascontiguousarray(s_all[g0:g0 + count])
+                    _lib.check(lib.bixcor_host_expand_s32(src.ctypes.data, count, g0, inv.ctypes.data, p, shift, pow6, dst.ctypes.data))
+                    assert np.array_equal(dst, want[pow6][g0:g0 + count], equal_nan=True), (p, shift, pow6, g0, count, off)
+                    assert buf[off + count] == -123.0  # nothing written past the piece
+        assert lib.bixcor_host_expand_s32(s_all.ctypes.data, total, 1, inv.ctypes.data, p, shift, 0, np.empty(total).ctypes.data) == _lib.ERR_INVALID
+    f = np.concatenate([rng.normal(size=1001).astype(np.float32), np.float32([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 3.4e38])])
+    for off in (0, 1, 3):
+        out = np.empty(f.size + 4)
+        _lib.check(lib.bixcor_host_widen_f32(f.ctypes.data, f.size, out[off:off + f.size].ctypes.data))
+        assert np.array_equal(out[off:off + f.size], f.astype(np.float64), equal_nan=True)
+        assert np.array_equal(np.signbit(out[off:off + f.size]), np.signbit(f))
