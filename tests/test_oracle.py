@@ -306,3 +306,70 @@ def test_sampled_row_oracle_equals_the_full_oracle():
     assert sm.pick_rows(128, 256, 300)[0] == 128 and sm.pick_rows(128, 256, 300)[-1] == 255
     assert sm.pick_rows(299, 300, 300) == [] and sm.pick_rows(120, 120, 120) == []
     assert set(sm.pick_rows(0, 20000, 20000)) == set(sm.ROWS_20K)
+
+
+def _packed_key_rank_model(col):
+    """NumPy model of the register rank kernel's fast path (bixverse_b200/csrc/columns.cuh, rank_columns_warp_body): every
+    element becomes one double - the value with -0 folded into +0, +-inf replaced by +-DBL_MAX and its low 10 mantissa bits
+    replaced by the sample index; the replaced bits (+ an "infinite" flag) are parked by sample index.  After the sort,
+    neighbours that agree above the index bits must have equal parked bits (a true tie), otherwise the kernel falls back to
+    the exact (key, index) sort.  Returns (2 * average ranks or None, fallback?)."""
+    n = col.size
+    assert n <= 1024 and not np.isnan(col).any()
+    b = (col + 0.0).view(np.uint64).copy()
+    parked = (b & np.uint64(1023)).astype(np.uint32)
+    isinf = (b & np.uint64(0x7FF0000000000000)) == np.uint64(0x7FF0000000000000)
+    b[isinf] = (b[isinf] & np.uint64(0x8000000000000000)) | np.uint64(0x7FEFFFFFFFFFFFFF)
+    parked[isinf] = 1024 | 1023
+    packed = ((b & ~np.uint64(1023)) | np.arange(n, dtype=np.uint64)).view(np.float64)
+    assert np.unique(packed).size == n  # all keys distinct: one comparison per exchange suffices
+    order = np.argsort(packed, kind="stable")  # the sorting network orders by the packed DOUBLE values
+    bits = packed.view(np.uint64)[order]
+    same = np.zeros(n, dtype=bool)
+    same[1:] = (bits[1:] ^ bits[:-1]) < np.uint64(1024)
+    pk = parked[order]
+    mixed = same.copy()
+    mixed[1:] &= pk[1:] != pk[:-1]
+    if mixed.any():
+        return None, True
+    start = ~same
+    run_id = np.cumsum(start) - 1
+    lo = np.flatnonzero(start)[run_id]
+    ends = np.r_[np.flatnonzero(start)[1:] - 1, n - 1]
+    hi = ends[run_id]
+    rk2 = np.empty(n, dtype=np.int64)
+    rk2[order] = lo + hi + 2
+    return rk2, False
+
+
+def test_packed_key_rank_model_is_exact_or_falls_back():
+    """The correctness argument of the packed-key rank kernel, checked on the CPU: whenever the fast path accepts a column its
+    ranks equal the reference's average-tie ranks exactly; columns it cannot decide (values closer than 1024 ulp that are not
+    equal, finite values next to +-DBL_MAX beside infinities) are handed to the exact sort, never mis-ranked."""
+    rng = np.random.default_rng(11)
+    big, tiny = np.finfo(np.float64).max, np.finfo(np.float64).smallest_subnormal
+    accepted = rejected = 0
+    cols = []
+    for n in (2, 31, 64, 333, 1000, 1024):
+        cols += [rng.normal(size=n), np.round(rng.normal(size=n), 1), np.full(n, 2.5), rng.integers(-3, 4, size=n).astype(float),
+                 np.where(rng.random(n) < 0.3, np.inf, rng.normal(size=n)), np.where(rng.random(n) < 0.3, -np.inf, np.round(rng.normal(size=n), 1)),
+                 rng.integers(-3, 4, size=n) * tiny * 2048, np.where(rng.random(n) < 0.5, 0.0, -0.0)]
+        near = 1.0 + rng.integers(0, 1024, size=n) * 2.0 ** -52            # distinct values inside one 1024-ulp bucket
+        cols += [near, -near, np.r_[near[: n // 2], np.full(n - n // 2, 1.0)]]
+        edge = rng.normal(size=n)
+        edge[: min(n, 3)] = [np.inf, big, np.nextafter(big, 0)][: min(n, 3)]
+        cols.append(edge)
+        cols.append(rng.integers(-3, 4, size=n) * tiny)                      # subnormals: all inside the bucket around zero
+    for col in cols:
+        rk2, fallback = _packed_key_rank_model(col)
+        want = 2.0 * o.rank_matrix_col(col[:, None])[:, 0]
+        if fallback:
+            rejected += 1
+            # the fast path only rejects when two different values share the bits above the index field
+            bb = (col + 0.0).view(np.uint64) >> np.uint64(10)
+            inf_like = np.isinf(col) | (np.abs(col) >= np.nextafter(big, 0) * (1 - 2.0 ** -42))
+            assert any(np.unique(col[bb == u]).size > 1 for u in np.unique(bb)) or (inf_like.any() and np.unique(col[inf_like]).size > 1)
+        else:
+            accepted += 1
+            assert np.array_equal(rk2.astype(np.float64), want), col[:8]
+    assert accepted > 40 and rejected > 10
