@@ -882,8 +882,8 @@ peer_broadcast_kernel(const char* __restrict__ src, const __grid_constant__ Peer
 
 // Cross-GPU barrier of the exchange (one CTA): thread r tells peer r that this rank's records of step `epoch` are complete
 // (system-scope release store into the peer's flag array; the column kernel's peer stores were performed before this
-// kernel started) and waits until peer r has said the same here.  A peer that never arrives traps after ~20 s instead of
-// hanging the GPU.
+// kernel started) and waits until peer r has said the same here.  A peer that never arrives (a dead process) traps after ~2 minutes
+// instead of hanging the GPU for good; ordinary skew between ranks (first-call set-up, a slow host) stays far below that.
 struct PeerFlags {
   int n;                        // world size (own rank included)
   uint32_t* flags[kMaxPeers];   // flag array of every rank (16 words = 64 bytes apart per writer)
@@ -900,7 +900,7 @@ peer_barrier_kernel(const __grid_constant__ PeerFlags pf, int rank, uint32_t epo
     uint32_t seen;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
     if ((int32_t)(seen - epoch) >= 0) break;
-    if (clock64() - t0 > 40000000000ll) __trap();
+    if (clock64() - t0 > 240000000000ll) __trap();  // ~2 minutes at 2 GHz
     __nanosleep(100);
   }
 }
