@@ -249,7 +249,7 @@ def host_sharded_cor_upper_xchg(backend, x_host, n, p, spearman, out_host, shift
     r0, r1 = pair_balanced_rows(p, shift, world, rank)
     slab = gene_slab(p, world)
     g0, g1 = min(p, rank * slab), min(p, (rank + 1) * slab)
-    x_slab = backend.to_device(x_host[g0:max(g1, g0 + 1)] if g1 > g0 else x_host[0:1])
+    x_slab = backend.to_device(x_host[g0:g1] if g1 > g0 else x_host[0:1])  # (an empty slab still takes part in the barrier; its pointer is not read)
     backend._sync_in()
     check(backend.lib.bixcor_dev_cor_upper_rows_xchg_to_host(x_slab.data_ptr(), n, p, int(spearman), int(shift), float(beta), r0, r1,
                                                              out_host.data_ptr()))
